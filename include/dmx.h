@@ -1,0 +1,188 @@
+/*
+ * dmx.h — C ABI of the B200 noisy density-matrix engine (libdmx.so).
+ *
+ * The reference (MiniSean/VQE_ErrorMitigation) has no FFI of its own: its hot path is the handful of
+ * calls into cirq's DensityMatrixSimulator followed by Tr(rho H).  This header is the explicit form
+ * of that boundary.  Each entry point names the reference call it stands in for
+ * (paths relative to the reference checkout).
+ *
+ * Conventions
+ *   - plain C, no C++/torch types; all device buffers are caller-owned (e.g. torch tensors), the
+ *     plan owns only its own constant tables.
+ *   - qubit 0 is the most significant bit of a basis-state index (cirq's big-endian order); density
+ *     matrices are row-major complex128 (re,im interleaved), element (r,c) at rho[(r<<n)+c].
+ *   - every function returns 0 on success or a negative dmx_status; dmx_last_error() gives the
+ *     message of the last failure on the calling thread.  No exceptions cross the ABI.
+ *   - there is no CPU execution path: without a CUDA device the execution calls fail with
+ *     DMX_ERR_CUDA.  Plan construction/inspection is host-only work and needs no device.
+ *   - a plan is immutable after dmx_plan_finalize(); it may be used from several host threads /
+ *     streams concurrently (workspace is per call).
+ */
+#ifndef DMX_H_
+#define DMX_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DMX_VERSION 100 /* 0.1.0 */
+#define DMX_MAX_QUBITS 14
+
+typedef enum dmx_status {
+    DMX_OK = 0,
+    DMX_ERR_INVALID = -1,     /* bad argument / malformed op table */
+    DMX_ERR_UNSUPPORTED = -2, /* valid request the engine cannot run (e.g. > DMX_MAX_QUBITS) */
+    DMX_ERR_CUDA = -3,        /* CUDA runtime error or no device */
+    DMX_ERR_NOMEM = -4,
+    DMX_ERR_STATE = -5        /* call order (e.g. executing a plan that was not finalized) */
+} dmx_status;
+
+/* Operation kinds.  Matrices live in one pool of doubles (complex128 interleaved, row-major); an op
+ * refers to its first matrix by offset (in doubles).  A 1-qubit matrix is 8 doubles, a 2-qubit matrix
+ * 32 doubles with q0 the more significant qubit (np.kron(A_q0, B_q1) ordering). */
+typedef enum dmx_op_kind {
+    /* rho <- U rho U^dagger.  U is NOT checked for unitarity: the reference wraps projectors as gates
+     * (IBasisGateSingle/Two, src/error_mitigation.py:277-300) and cirq applies them as-is. */
+    DMX_OP_UNITARY = 1,
+    /* rho <- sum_k K_k rho K_k^dagger, n_mats Kraus operators back to back (a cirq mixture
+     * (p_k, U_k) is passed as K_k = sqrt(p_k) U_k; channels of src/error_mitigation.py:743-910,
+     * cirq.depolarize / bit_flip / phase_flip / amplitude_damp / phase_damp). */
+    DMX_OP_KRAUS = 2,
+    /* U = exp(-i theta sigma_axis / 2), theta = scale * params[b, param] + offset: the resolved form of
+     * cirq.rx/ry/rz(2*sign*alpha_k) (src/data_containers/helper_interfaces/i_wave_function.py:183,
+     * src/processors/processor_quantum.py:63-65).  axis: 0 = X, 1 = Y, 2 = Z. */
+    DMX_OP_ROTATION = 3,
+    /* Per-circuit basis operation of quasi-probability error mitigation: circuit b applies
+     * B[variants[b, slot]] where B is a table of 16 one-qubit matrices starting at `mat`
+     * (BasisUnitarySet order, src/error_mitigation.py:119-136).  On two qubits the index is
+     * 16*a + b and the operation is kron(B[a], B[b]) (src/error_mitigation.py:150-153,556-565). */
+    DMX_OP_VARIANT = 4,
+    /* Terminal measurement marker: ignored by the evolution (cirq evolves once and samples the
+     * diagonal); kept so op indices line up with the caller's circuit. */
+    DMX_OP_MEASURE = 5
+} dmx_op_kind;
+
+/* flag: apply this UNITARY/KRAUS op only in circuits whose variant index at `slot` is non-zero
+ * ("noise after correction", src/error_mitigation.py:570-571).  Must directly follow the
+ * DMX_OP_VARIANT op of the same slot (other conditional ops of that slot may sit in between). */
+#define DMX_OPF_IF_VARIANT_NONZERO 1u
+
+typedef struct dmx_op {
+    int32_t kind;     /* dmx_op_kind */
+    int32_t n_qubits; /* 1 or 2 */
+    int32_t q0, q1;   /* qubit indices (q1 ignored for 1-qubit ops) */
+    int32_t mat;      /* offset (in doubles) of the first matrix in the pool; -1 if none */
+    int32_t n_mats;   /* UNITARY: 1; KRAUS: number of Kraus operators; VARIANT: 16 */
+    int32_t param;    /* ROTATION: parameter column; otherwise -1 */
+    int32_t axis;     /* ROTATION: 0/1/2 */
+    int32_t slot;     /* VARIANT and conditional ops: column of the variant table; otherwise -1 */
+    uint32_t flags;
+    double scale;     /* ROTATION */
+    double offset;    /* ROTATION */
+} dmx_op;
+
+typedef struct dmx_plan dmx_plan;
+
+/* What the planner decided; filled by dmx_plan_get_info. */
+typedef struct dmx_plan_info {
+    int32_t n_qubits, n_params, n_slots, n_ops_in;
+    int32_t n_blocks;       /* fused micro-ops after gate+channel fusion */
+    int32_t n_segments;     /* full-vector monomial segments (segment kernel); 0 if not eligible */
+    int32_t n_passes;       /* tile passes (1 when the whole state fits one CTA's shared memory) */
+    int32_t tile_qubits;    /* qubits resident per tile */
+    int32_t path;           /* 0 = tile kernel (whole state in smem), 1 = segment kernel, 2 = streaming */
+    int32_t n_terms;        /* Hamiltonian terms */
+    int64_t state_bytes;    /* bytes of one state vector in the engine's representation (8 * 4^n) */
+    double flops_per_circuit;     /* FP64 flops the planned kernels execute per circuit */
+    double hbm_bytes_per_circuit; /* algorithmic HBM bytes per circuit (params/variants/energy + state passes) */
+    double smem_bytes_per_circuit;/* shared-memory bytes moved per circuit */
+    double canonical_flops_per_circuit; /* SURVEY.md §8d cost model (complex rho) for the same circuit */
+    double canonical_hbm_bytes_per_circuit;
+} dmx_plan_info;
+
+int dmx_version(void);
+const char* dmx_last_error(void);
+
+/* ---- plan construction (host only) ---------------------------------------------------------------
+ * Stands in for building + resolving the cirq.Circuit that the reference hands to
+ * DensityMatrixSimulator.simulate (src/processors/processor_quantum.py:30-31,
+ * src/error_mitigation.py:365-374): the op list is the circuit, params are the ParamResolver values,
+ * variants are the QuasiCircuitIdentifier ids. */
+int dmx_plan_create(int n_qubits, int n_params, int n_slots, const dmx_op* ops, int n_ops,
+                    const double* matrix_pool, size_t pool_len, dmx_plan** out);
+
+/* Observable H = sum_t coeff[t] * P_t, P_t given by bit masks over qubits (bit n-1-q <-> qubit q):
+ * X on xmask&~zmask, Z on zmask&~xmask, Y on xmask&zmask.  Replaces get_sparse_operator(jordan_wigner(...))
+ * + (csc(rho) * H).diagonal().sum().real (src/processors/processor_quantum.py:33-39,
+ * src/error_mitigation.py:377-383). */
+int dmx_plan_set_hamiltonian(dmx_plan* plan, int n_terms, const uint32_t* xmask, const uint32_t* zmask,
+                             const double* coeff);
+
+/* Planner options (before finalize).  key/value pairs; unknown keys -> DMX_ERR_INVALID.
+ *   "fuse"      0/1   gate+channel block fusion (default 1)
+ *   "segments"  0/1   allow the segment kernel when eligible (default 1)
+ *   "tile_qubits" k   resident qubits per streaming tile, 4..7 (default 7)
+ */
+int dmx_plan_set_option(dmx_plan* plan, const char* key, int value);
+
+/* Lowers, fuses and schedules the op list (host only); uploads tables lazily on first execution. */
+int dmx_plan_finalize(dmx_plan* plan);
+int dmx_plan_get_info(const dmx_plan* plan, dmx_plan_info* info);
+/* Text dump of the lowered program (for tests / debugging).  Returns bytes needed incl. NUL. */
+int64_t dmx_plan_dump(const dmx_plan* plan, char* buf, int64_t buf_len);
+void dmx_plan_destroy(dmx_plan* plan);
+
+/* ---- execution (device pointers, caller-owned; stream is a cudaStream_t passed as void*) ------------
+ * d_params   [B, n_params] float64 row-major (may be NULL when n_params == 0)
+ * d_variants [B, n_slots]  uint8  row-major (NULL = all-identity variants)
+ * d_workspace: dmx_workspace_bytes(plan, B) bytes (may be NULL when that is 0). */
+size_t dmx_workspace_bytes(const dmx_plan* plan, int64_t batch);
+
+/* energies[b] = Re Tr(rho_b H): QPU.get_simulated_noisy_expectation_value
+ * (src/processors/processor_quantum.py:28-39) and the density branch of
+ * IErrorMitigationManager.process_circuit (src/error_mitigation.py:372-383), batched.
+ * rho is NOT renormalised (projector basis ops leave Tr rho < 1). */
+int dmx_energy_batch(dmx_plan* plan, int64_t batch, const double* d_params, const uint8_t* d_variants,
+                     double* d_energy, void* d_workspace, size_t workspace_bytes, void* stream);
+
+/* d_rho [B, 2^n, 2^n] complex128: simulate(...).final_density_matrix. */
+int dmx_density_batch(dmx_plan* plan, int64_t batch, const double* d_params, const uint8_t* d_variants,
+                      double* d_rho, void* d_workspace, size_t workspace_bytes, void* stream);
+
+/* d_diag [B, 2^n]: |diag rho|, divided by its sum when renormalise != 0 — the probability vector
+ * DensityMatrixSimulator.run samples from (src/data_containers/model_hydrogen.py:132,155,
+ * src/error_mitigation.py:391). */
+int dmx_diag_batch(dmx_plan* plan, int64_t batch, const double* d_params, const uint8_t* d_variants,
+                   double* d_diag, int renormalise, void* d_workspace, size_t workspace_bytes, void* stream);
+
+/* d_pauli [B, 4^n]: the engine's native state, r[P] = Tr(rho P) (index: 2 bits per qubit,
+ * qubit 0 most significant, code 0=I 1=Z 2=X 3=Y). */
+int dmx_pauli_batch(dmx_plan* plan, int64_t batch, const double* d_params, const uint8_t* d_variants,
+                    double* d_pauli, void* d_workspace, size_t workspace_bytes, void* stream);
+
+/* d_out[3] = { sum_b w[b]*v[b], sum_b (w[b]*v[b])^2, sum_b |w[b]|>0 ? count[b] : 0 } with
+ * w[b] = d_weights[b] (sign * prod(weights) * count) — the per-rank partial of np.mean at
+ * src/error_mitigation.py:399,451; the 24-byte cross-GPU sum is the caller's all-reduce.
+ * d_counts may be NULL (every row counts 1).  Deterministic (fixed reduction tree). */
+int dmx_qp_reduce(const double* d_values, const double* d_weights, const int32_t* d_counts, int64_t batch,
+                  double* d_out3, void* stream);
+
+/* Same as dmx_energy_batch but with HOST buffers: copies params/variants in, runs, copies energies
+ * out, and waits.  This is the call a non-CUDA-aware host (the reference's Python) binds. */
+int dmx_energy_batch_host(dmx_plan* plan, int64_t batch, const double* h_params, const uint8_t* h_variants,
+                          double* h_energy);
+
+/* ---- measurement helpers ---------------------------------------------------------------------------- */
+/* FP64 FMA micro-benchmark on the current device: returns achieved TFLOP/s (roofline denominator the
+ * driver's MEASURED_PEAKS.json does not carry).  iters FMAs per thread, 148*k CTAs. */
+int dmx_measure_fp64_peak(double* tflops_out, void* stream);
+/* Number of kernel launches issued by this library since load (for bench.py's gpu_launches). */
+int64_t dmx_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DMX_H_ */

@@ -1,0 +1,226 @@
+"""numpy interpreter of ``dmx_plan_dump`` output — test infrastructure.
+
+Executes the *lowered* program (fused Pauli-transfer blocks, the device op table with its packed
+coefficient tables, and the segment-kernel tables) exactly as the CUDA kernels are specified to, so the
+host-side lowering in ``csrc/dmx_lower.cpp`` can be verified against the oracle on a machine without a GPU.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+
+def _nums(s, typ=float):
+    return np.array([typ(x) for x in s.split(",")] if s else [], dtype=typ)
+
+
+def parse(dump: str) -> dict:
+    plan = {"blocks": [], "passes": [], "devops": [], "segs": [], "slots": {}, "rots": []}
+    for line in dump.splitlines():
+        if not line.strip():
+            continue
+        toks = line.split(" ")
+        head = toks[0]
+        kv = {}
+        pos = []
+        for t in toks[1:]:
+            if "=" in t:
+                k, v = t.split("=", 1)
+                kv[k] = v
+            else:
+                pos.append(t)
+        if head == "plan":
+            for k in ("n", "params", "path", "tile_k", "nseg"):
+                plan[k] = int(kv[k])
+            plan["n_slots"] = int(kv["slots"])
+        elif head == "block":
+            b = {k: int(kv[k]) for k in ("kind", "nq", "q0", "q1", "cls")}
+            for k in ("M", "A", "C", "S", "tab", "cond"):
+                if k in kv:
+                    b[k] = _nums(kv[k])
+            for k in ("rot", "param", "slot"):
+                if k in kv:
+                    b[k] = int(kv[k])
+            for k in ("scale", "offset"):
+                if k in kv:
+                    b[k] = float(kv[k])
+            plan["blocks"].append(b)
+        elif head == "pass":
+            plan["passes"].append({"first": int(kv["first"]), "nops": int(kv["nops"]), "tile": _nums(kv["tile"], int), "rots": _nums(kv["rots"], int)})
+        elif head == "devop":
+            plan["devops"].append({k: int(kv[k]) for k in ("kind", "p0", "p1", "coef", "a0", "a1", "a2")})
+        elif head == "" and "coefs" in kv:
+            plan["coefs"] = _nums(kv["coefs"])
+        elif head == "terms":
+            plan["term_idx"] = _nums(kv["idx"], int)
+            plan["term_coef"] = _nums(kv["coef"])
+        elif head == "seg":
+            plan["segs"].append({"rot": int(kv["rot"]), "src0": _nums(kv["src0"], int), "src1": _nums(kv["src1"], int),
+                                 "active": _nums(kv["active"], int), "w0": _nums(kv["w0"]), "w1": _nums(kv["w1"])})
+        elif head == "estage":
+            plan["e_src"] = _nums(kv["src"], int)
+            plan["e_w"] = _nums(kv["w"])
+        elif head == "slot":
+            plan["slots"][int(pos[0])] = {"nq": int(kv["nq"]), "seg": int(kv["seg"]), "tab": int(kv["tab"]),
+                                          "diag_ok": _nums(kv["diag_ok"], int), "label": _nums(kv["label"], int)}
+        elif head == "rot":
+            plan["rots"].append({"param": int(kv["param"]), "scale": float(kv["scale"]), "offset": float(kv["offset"])})
+    return plan
+
+
+def init_state(n: int) -> np.ndarray:
+    idx = np.arange(4 ** n)
+    return np.where(idx & 0xAAAAAAAA, 0.0, 1.0)
+
+
+def _apply_local(r, n, qubits, M):
+    k = len(qubits)
+    t = r.reshape((4,) * n)
+    m = M.reshape((4,) * (2 * k))
+    out = np.tensordot(m, t, axes=(list(range(k, 2 * k)), list(qubits)))
+    return np.moveaxis(out, list(range(k)), list(qubits)).reshape(-1)
+
+
+def run_blocks(plan, params=None, variants=None) -> np.ndarray:
+    n = plan["n"]
+    r = init_state(n)
+    for b in plan["blocks"]:
+        qs = [b["q0"]] if b["nq"] == 1 else [b["q0"], b["q1"]]
+        dim = 4 ** b["nq"]
+        if b["kind"] == 0:
+            r = _apply_local(r, n, qs, b["M"].reshape(dim, dim))
+        elif b["kind"] == 1:
+            th = b["scale"] * params[b["param"]] + b["offset"]
+            M = b["A"] + np.cos(th) * b["C"] + np.sin(th) * b["S"]
+            r = _apply_local(r, n, qs, M.reshape(dim, dim))
+        else:
+            idx = 0 if variants is None else int(variants[b["slot"]])
+            if idx == 0:
+                continue
+            tab = b["tab"].reshape(16, 4, 4)
+            B = tab[idx] if b["nq"] == 1 else np.kron(tab[idx >> 4], tab[idx & 15])
+            r = _apply_local(r, n, qs, b["cond"].reshape(dim, dim) @ B)
+    return r
+
+
+def energy(plan, r) -> float:
+    return float(np.dot(plan["term_coef"], r[plan["term_idx"]]))
+
+
+def run_devops(plan, params=None, variants=None) -> np.ndarray:
+    """Interpret the device op table pass by pass (tile-local bit positions -> global positions)."""
+    n = plan["n"]
+    r = init_state(n)
+    cf = plan["coefs"]
+    E = 4 ** n
+    idx = np.arange(E)
+    for ps in plan["passes"]:
+        tile = list(ps["tile"])
+        k = len(tile)
+        # local position p of tile qubit i is 2*(k-1-i); global position 2*(n-1-q)
+        gpos = {2 * (k - 1 - i): 2 * (n - 1 - q) for i, q in enumerate(tile)}
+        for op in plan["devops"][ps["first"]:ps["first"] + ps["nops"]]:
+            kind = op["kind"]
+            g0 = gpos[op["p0"]]
+            c0 = (idx >> g0) & 3
+            if kind in (0, 1, 2, 3, 7):
+                if kind == 0:
+                    r = r * cf[op["coef"] + c0]
+                elif kind == 1:
+                    src_code = (op["a0"] >> (2 * c0)) & 3
+                    src = (idx & ~(3 << g0)) | (src_code << g0)
+                    r = cf[op["coef"] + c0] * r[src]
+                else:
+                    if kind == 2:
+                        M = cf[op["coef"]:op["coef"] + 16].reshape(4, 4)
+                    elif kind == 3:
+                        rot = plan["rots"][ps["rots"][op["a0"]]]
+                        assert ps["rots"][op["a0"]] == op["a2"]
+                        th = rot["scale"] * params[rot["param"]] + rot["offset"]
+                        acs = cf[op["coef"]:op["coef"] + 48].reshape(3, 4, 4)
+                        M = acs[0] + np.cos(th) * acs[1] + np.sin(th) * acs[2]
+                    else:
+                        v = 0 if variants is None else int(variants[op["a0"]])
+                        if v == 0:
+                            continue
+                        M = cf[op["coef"] + 16 * v: op["coef"] + 16 * v + 16].reshape(4, 4)
+                    new = np.zeros_like(r)
+                    for b in range(4):
+                        src = (idx & ~(3 << g0)) | (b << g0)
+                        new += M[c0, b] * r[src]
+                    r = new
+            else:
+                g1 = gpos[op["p1"]]
+                c1 = (idx >> g1) & 3
+                loc = c0 * 4 + c1
+                clear = idx & ~(3 << g0) & ~(3 << g1)
+
+                def dense(M, r):
+                    new = np.zeros_like(r)
+                    for b in range(16):
+                        src = clear | ((b >> 2) << g0) | ((b & 3) << g1)
+                        new += M[loc, b] * r[src]
+                    return new
+
+                if kind == 4:
+                    r = r * cf[op["coef"] + loc]
+                elif kind == 5:
+                    pk = (op["a0"] & 0xFFFFFFFF) | ((op["a1"] & 0xFFFFFFFF) << 32)
+                    s = np.array([(pk >> (4 * int(e))) & 15 for e in loc])
+                    src = clear | ((s >> 2) << g0) | ((s & 3) << g1)
+                    r = cf[op["coef"] + loc] * r[src]
+                elif kind == 6:
+                    r = dense(cf[op["coef"]:op["coef"] + 256].reshape(16, 16), r)
+                else:
+                    v = 0 if variants is None else int(variants[op["a0"]])
+                    if v == 0:
+                        continue
+                    tab = cf[op["coef"]:op["coef"] + 256].reshape(16, 4, 4)
+                    r = dense(np.kron(tab[v >> 4], tab[v & 15]), r)
+                    if op["a2"] == 1:
+                        r = r * cf[op["a1"] + loc]
+                    else:
+                        r = dense(cf[op["a1"]:op["a1"] + 256].reshape(16, 16), r)
+    return r
+
+
+def run_segments(plan, params=None, variants=None):
+    """Interpret the segment-kernel tables; returns the energy, or None when the variant row needs the
+    general path (a non-diagonal correction op)."""
+    cf = plan["coefs"]
+    j = np.arange(256)
+    r = np.where(j & 0xAA, 0.0, 1.0)
+    act = []
+    if variants is not None:
+        for s, v in enumerate(variants):
+            v = int(v)
+            if v == 0 or s not in plan["slots"] or plan["slots"][s]["seg"] < 0:
+                continue
+            sl = plan["slots"][s]
+            if not (int(sl["diag_ok"][v >> 5]) >> (v & 31)) & 1:
+                return None
+            act.append((s, v))
+    nseg = plan["nseg"]
+    for k in range(nseg + 1):
+        for s, v in act:
+            sl = plan["slots"][s]
+            if sl["seg"] != k:
+                continue
+            lab = sl["label"]
+            t = sl["tab"]
+            if sl["nq"] == 1:
+                f = cf[t + v * 4 + lab]
+            else:
+                f = cf[t + (v >> 4) * 4 + (lab >> 2)] * cf[t + (v & 15) * 4 + (lab & 3)] * cf[t + 64 + lab]
+            r = r * f
+        if k == nseg:
+            break
+        sg = plan["segs"][k]
+        a = sg["w0"] * r[sg["src0"]]
+        if sg["rot"] >= 0:
+            rot = plan["rots"][sg["rot"]]
+            th = rot["scale"] * params[rot["param"]] + rot["offset"]
+            b = sg["w1"] * r[sg["src1"]]
+            r = np.where(sg["active"] == 1, np.cos(th) * a + np.sin(th) * b, a)
+        else:
+            r = a
+    return float(np.dot(plan["e_w"], r[plan["e_src"]]))

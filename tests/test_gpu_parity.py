@@ -1,0 +1,250 @@
+"""GPU parity tests: CUDA path (through the C ABI) vs the numpy oracle on the same seeded inputs.
+
+Tolerance: 1e-10 absolute on energies / density-matrix elements / probabilities — the bar BASELINE.json's
+north_star states for FP64.  All tests here need a B200 (``-m gpu``).
+"""
+import numpy as np
+import pytest
+
+from oracle import dm_oracle as O
+from workloads import ALPHA_STAR, build_program, h2_ops, h2_program, h2_terms
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-10
+
+
+def torch_cuda():
+    import torch
+    assert torch.cuda.is_available()
+    return torch
+
+
+def oracle_energy(ops, n, ham):
+    return O.energy_sparse(O.simulate(n, ops), ham)
+
+
+NOISES = {
+    "depol+2qdepol": ([O.depolarize(1e-3)], [O.two_qubit_depolarize(1e-3)]),
+    "depol_only_1q": ([O.depolarize(1e-3)], []),
+    "asym_pauli": ([O.asymmetric_depolarize(1e-4, 1e-4, 6e-4)], [O.two_qubit_pauli_channel(1e-4, 1e-4, 6e-4)]),
+    "bitflip+phaseflip": ([O.bit_flip(1e-3), O.phase_flip(2e-3)], []),
+    "noiseless": ([], []),
+    "amp_damp": ([O.amplitude_damp(5e-3)], [O.two_qubit_depolarize(1e-3)]),
+}
+
+
+@pytest.mark.parametrize("noise", sorted(NOISES))
+@pytest.mark.parametrize("options", [{}, {"segments": 0}, {"segments": 0, "fuse": 0}])
+def test_h2_energy_matches_oracle(noise, options):
+    torch = torch_cuda()
+    n1, n2 = NOISES[noise]
+    terms = h2_terms()
+    ham = O.pauli_terms_to_matrix(4, *terms)
+    prog = build_program(h2_ops(n1, n2), 4, terms, **options)
+    if noise == "amp_damp":
+        assert prog.info["path"] == 0  # non-Pauli channel: dense blocks, tile kernel
+    elif not options:
+        assert prog.info["path"] == 1
+    alphas = np.array([0.0, ALPHA_STAR, -0.37, 0.5, 1.234, -2.0, 3.0])
+    got = prog.energies(torch.tensor(alphas).reshape(-1, 1)).cpu().numpy()
+    for a, g in zip(alphas, got):
+        want = oracle_energy(h2_ops(n1, n2, alpha=a), 4, ham)
+        assert abs(g - want) < TOL, (noise, options, a, g, want)
+
+
+def test_h2_known_answers_all_bond_lengths():
+    """Noiseless E(alpha=0) = stored hf_energy for all 30 bond lengths; min over alpha reaches fci_energy."""
+    torch = torch_cuda()
+    from workloads import h2_golden
+    alphas = np.linspace(-0.6, 0.6, 4801)
+    for r, rec in h2_golden()["molecules"].items():
+        terms = h2_terms(r)
+        prog = build_program(h2_ops([], []), 4, terms)
+        e = prog.energies(torch.tensor(alphas).reshape(-1, 1)).cpu().numpy()
+        e0 = prog.energies(torch.zeros(1, 1, dtype=torch.float64)).cpu().numpy()[0]
+        assert abs(e0 - rec["hf_energy"]) < 1e-10, r
+        # grid minimum is within the quadratic error of the grid step of the FCI energy
+        assert 0 <= e.min() - rec["fci_energy"] < 2e-6, (r, e.min(), rec["fci_energy"])
+
+
+def test_batch_sizes_and_host_api():
+    torch = torch_cuda()
+    prog, ham = h2_program()
+    rng = np.random.default_rng(5)
+    for B in (1, 7, 8, 9, 255, 4099):
+        a = rng.normal(0, 0.3, size=(B, 1))
+        dev = prog.energies(torch.tensor(a)).cpu().numpy()
+        host = prog.energies_host(a)
+        assert np.max(np.abs(dev - host)) < 1e-13
+        i = B // 2
+        want = oracle_energy(h2_ops([O.depolarize(1e-3)], [O.two_qubit_depolarize(1e-3)], alpha=a[i, 0]), 4, ham)
+        assert abs(dev[i] - want) < TOL
+    assert prog.energies(torch.zeros(0, 1, dtype=torch.float64)).numel() == 0
+
+
+def random_unitary(rng, d):
+    m = rng.normal(size=(d, d)) + 1j * rng.normal(size=(d, d))
+    q, r = np.linalg.qr(m)
+    return q * (np.diag(r) / np.abs(np.diag(r)))
+
+
+def random_kraus(rng, d, k):
+    mats = [rng.normal(size=(d, d)) + 1j * rng.normal(size=(d, d)) for _ in range(k)]
+    s = sum(m.conj().T @ m for m in mats)
+    w, v = np.linalg.eigh(s)
+    inv_sqrt = v @ np.diag(w ** -0.5) @ v.conj().T
+    return [m @ inv_sqrt for m in mats]
+
+
+def random_circuit(rng, n, depth, n_params=3):
+    ops = []
+    for _ in range(depth):
+        kind = rng.integers(0, 6)
+        if n == 1 and kind in (1, 3):
+            kind = 0
+        if kind == 0:
+            ops.append(("u", (int(rng.integers(n)),), random_unitary(rng, 2)))
+        elif kind == 1:
+            a, b = rng.choice(n, 2, replace=False)
+            ops.append(("u", (int(a), int(b)), random_unitary(rng, 4)))
+        elif kind == 2:
+            ops.append(("k", (int(rng.integers(n)),), random_kraus(rng, 2, int(rng.integers(1, 4)))))
+        elif kind == 3:
+            a, b = rng.choice(n, 2, replace=False)
+            ops.append(("k", (int(a), int(b)), random_kraus(rng, 4, int(rng.integers(1, 4)))))
+        elif kind == 4:
+            ops.append(("r", (int(rng.integers(n)),), (int(rng.integers(3)), f"t{int(rng.integers(n_params))}", float(rng.normal()), float(rng.normal()))))
+        else:
+            a, b = rng.choice(n, 2, replace=False) if n > 1 else (0, 0)
+            if n > 1:
+                ops.append(("u", (int(a), int(b)), O.CNOT))
+    return ops
+
+
+def resolve(ops, names, values):
+    out = []
+    rot = {0: O.rx, 1: O.ry, 2: O.rz}
+    for kind, qs, pl in ops:
+        if kind == "r":
+            axis, name, scale, offset = pl
+            out.append(("u", qs, rot[axis](scale * values[names.index(name)] + offset)))
+        else:
+            out.append((kind, qs, pl))
+    return out
+
+
+def random_hamiltonian(rng, n, terms):
+    x = rng.integers(0, 1 << n, size=terms).astype(np.uint32)
+    z = rng.integers(0, 1 << n, size=terms).astype(np.uint32)
+    return x, z, rng.normal(size=terms)
+
+
+@pytest.mark.parametrize("n", [1, 2, 3, 4, 5, 6, 7])
+def test_random_circuits_density_energy_probabilities(n):
+    torch = torch_cuda()
+    rng = np.random.default_rng(100 + n)
+    ops = random_circuit(rng, n, depth=40)
+    terms = random_hamiltonian(rng, n, 12)
+    ham = O.pauli_terms_to_matrix(n, *terms)
+    prog = build_program(ops, n, terms)
+    names = prog.param_names
+    B = 5
+    params = rng.normal(size=(B, max(len(names), 1)))
+    p_in = torch.tensor(params[:, :len(names)]) if names else None
+    rho = prog.density(p_in, batch=B)
+    en = prog.energies(p_in, batch=B).cpu().numpy()
+    pr = prog.probabilities(p_in, batch=B)
+    for b in range(B):
+        ref = O.simulate(n, resolve(ops, names, params[b]))
+        assert np.max(np.abs(rho[b] - ref)) < TOL
+        assert abs(en[b] - O.energy_sparse(ref, ham)) < TOL
+        assert np.max(np.abs(pr[b] - O.probabilities(ref))) < TOL
+
+
+def qp_noisy_variant_program(noise1, noise2, terms, **options):
+    """H2 clean circuit at alpha* with a variant slot after every gate (get_updated_circuit structure)."""
+    gates = O.h2_gate_list(ALPHA_STAR)
+    basis = O.basis_operations()
+    ops = []
+    for s, (kind, qs, pl) in enumerate(gates):
+        noise = noise1 if len(qs) == 1 else noise2
+        ops.append((kind, qs, pl))
+        for kr in noise:
+            ops.append(("k", qs, kr))
+        ops.append(("v", qs, (basis, s)))
+        for kr in noise:
+            ops.append(("ck", qs, (kr, s)))
+    return build_program(ops, 4, terms, **options), gates
+
+
+@pytest.mark.parametrize("options", [{}, {"segments": 0}])
+def test_qp_variants_match_oracle(options):
+    torch = torch_cuda()
+    terms = h2_terms()
+    ham = O.pauli_terms_to_matrix(4, *terms)
+    n1 = [O.bit_flip(1e-3), O.depolarize(1e-3)]
+    n2 = [O.two_qubit_depolarize(1e-3)]
+    prog, gates = qp_noisy_variant_program(n1, n2, terms, **options)
+    assert prog.n_slots == 122
+    rng = np.random.default_rng(20260102)
+    B = 48
+    variants = np.zeros((B, 122), np.uint8)
+    arity = np.array([len(g[1]) for g in gates])
+    for b in range(1, B):
+        k = rng.integers(1, 5)
+        for s in rng.choice(122, k, replace=False):
+            if b < 24:   # Pauli corrections only (what the reference distribution produces)
+                variants[b, s] = rng.integers(1, 4) if arity[s] == 1 else 16 * rng.integers(0, 4) + rng.integers(0, 4)
+            else:        # stress: any basis op incl. rotations and projectors
+                variants[b, s] = rng.integers(0, 16) if arity[s] == 1 else rng.integers(0, 256)
+    got = prog.energies(None, torch.tensor(variants)).cpu().numpy()
+    host = prog.energies_host(None, variants)
+    assert np.max(np.abs(host - got)) < 1e-13
+    for b in range(B):
+        want = oracle_energy(O.variant_ops(gates, n1, n2, variants[b]), 4, ham)
+        assert abs(got[b] - want) < TOL, (b, got[b], want)
+
+
+@pytest.mark.parametrize("n,tile", [(8, 7), (8, 5), (9, 6), (9, 4)])
+def test_streaming_matches_oracle(n, tile):
+    torch = torch_cuda()
+    rng = np.random.default_rng(300 + n + tile)
+    ops = []
+    for layer in range(3):
+        for q in range(n):
+            ops.append(("r", (q,), (1, f"y{layer}_{q}", 1.0, 0.0)))
+            ops.append(("k", (q,), O.depolarize(1e-3)))
+            ops.append(("r", (q,), (2, f"z{layer}_{q}", 1.0, 0.0)))
+            ops.append(("k", (q,), O.depolarize(1e-3)))
+        for q in range(n - 1):
+            ops.append(("u", (q, q + 1), O.CNOT))
+            ops.append(("k", (q, q + 1), O.two_qubit_depolarize(1e-3)))
+    ops.append(("u", (0, n - 1), random_unitary(rng, 4)))
+    ops.append(("k", (1,), O.amplitude_damp(0.01)))
+    terms = random_hamiltonian(rng, n, 30)
+    ham = O.pauli_terms_to_matrix(n, *terms)
+    prog = build_program(ops, n, terms, tile_qubits=tile)
+    assert prog.info["path"] == 2 and prog.info["n_passes"] >= 2
+    B = 3
+    params = rng.uniform(-np.pi, np.pi, size=(B, prog.n_params))
+    en = prog.energies(torch.tensor(params), workspace_states=2).cpu().numpy()
+    rho = prog.density(torch.tensor(params[:1]))
+    for b in range(B):
+        ref = O.simulate(n, resolve(ops, prog.param_names, params[b]))
+        assert abs(en[b] - O.energy_sparse(ref, ham)) < TOL
+        if b == 0:
+            assert np.max(np.abs(rho[0] - ref)) < TOL
+
+
+def test_qp_reduce():
+    torch = torch_cuda()
+    from vqe_errormitigation_b200 import engine
+    rng = np.random.default_rng(9)
+    for B in (1, 1000, 300001):
+        v = rng.normal(size=B)
+        w = rng.normal(size=B)
+        c = rng.integers(1, 5, size=B)
+        out = engine.qp_reduce(torch.tensor(v, device="cuda"), torch.tensor(w, device="cuda"), torch.tensor(c, device="cuda")).cpu().numpy()
+        assert abs(out[0] - np.sum(w * v)) < 1e-9 * max(1, B ** 0.5)
+        assert abs(out[1] - np.sum((w * v) ** 2)) < 1e-9 * B
+        assert out[2] == c.sum()

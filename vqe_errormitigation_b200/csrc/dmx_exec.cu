@@ -1,0 +1,1164 @@
+// dmx_exec.cu — sm_100a kernels and the C ABI of libdmx (include/dmx.h).
+//
+// Kernels (all FP64, no tensor cores — SURVEY.md §2.1):
+//   dmx_tile_kernel     Pauli-vector tile resident in shared memory; interprets the fused block list of one
+//                       pass (DIAG/MONO/MAT/ROT/VAR on 1 or 2 qubits).  n <= 7: whole circuit in one launch
+//                       (several circuits per CTA for small n), fused Tr(rho H) epilogue.  n > 7: one tile of a
+//                       streaming pass (coalesced 16-byte loads/stores of 128-byte runs).
+//   dmx_segment_kernel  n <= 4, Clifford+Pauli-noise circuits: thread-per-Pauli-coefficient; each segment is one
+//                       shared-memory exchange (gather through the fused monomial) + an in-register rotation.
+//   dmx_energy_kernel   gather-dot Tr(rho H) on a state in global memory (streaming path).
+//   dmx_pauli_to_rho / dmx_pauli_to_diag   output converters (final_density_matrix, run() probabilities).
+//   dmx_qp_reduce_*     deterministic two-stage reduction of the QP-weighted estimator.
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "dmx_plan.hpp"
+
+using namespace dmx;
+
+// ---------------------------------------------------------------------------------------------------------
+// error plumbing
+// ---------------------------------------------------------------------------------------------------------
+static thread_local std::string g_last_error;
+static std::atomic<int64_t> g_launches{0};
+
+static int fail(int code, const std::string& msg) {
+    g_last_error = msg;
+    return code;
+}
+
+#define CUDA_TRY(expr)                                                                              \
+    do {                                                                                            \
+        cudaError_t _e = (expr);                                                                    \
+        if (_e != cudaSuccess)                                                                      \
+            return fail(DMX_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));          \
+    } while (0)
+
+// ---------------------------------------------------------------------------------------------------------
+// device structures
+// ---------------------------------------------------------------------------------------------------------
+struct BitRun {
+    int lshift, gshift, width;
+};
+
+struct TileArgs {
+    const DevOp* ops;
+    int n_ops;
+    const double* coefs;
+    const RotInfo* rots;
+    const int* pass_rots;  // global rot ids evaluated in this pass
+    int n_rots;
+    const double* params;
+    int n_params;
+    const uint8_t* variants;
+    int n_slots;
+    int n, k, cpb;
+    long long batch;
+    const int* worklist;        // optional indirection: circuit id = worklist[i], count in *work_count
+    const int* work_count;
+    double* state;              // streaming: [chunk, 4^n]
+    long long circuit_offset;   // streaming: first circuit of this chunk (for params/variants rows)
+    int load, store;
+    int n_truns, n_oruns;
+    BitRun truns[8], oruns[8];
+    int epilogue;               // 0 none, 1 energy, 2 copy state out
+    const uint32_t* term_idx;
+    const double* term_coef;
+    int n_terms;
+    double* out;
+};
+
+__device__ __forceinline__ unsigned map_bits(unsigned v, const BitRun* runs, int n) {
+    unsigned g = 0;
+    for (int i = 0; i < n; ++i) g |= ((v >> runs[i].lshift) & ((1u << runs[i].width) - 1u)) << runs[i].gshift;
+    return g;
+}
+
+__device__ __forceinline__ unsigned insert2(unsigned g, int p) {  // open a 2-bit hole at bit p
+    return ((g >> p) << (p + 2)) | (g & ((1u << p) - 1u));
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// tile kernel
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void mat4_apply(const double* __restrict__ M, double& v0, double& v1, double& v2, double& v3) {
+    double n0 = M[0] * v0 + M[1] * v1 + M[2] * v2 + M[3] * v3;
+    double n1 = M[4] * v0 + M[5] * v1 + M[6] * v2 + M[7] * v3;
+    double n2 = M[8] * v0 + M[9] * v1 + M[10] * v2 + M[11] * v3;
+    double n3 = M[12] * v0 + M[13] * v1 + M[14] * v2 + M[15] * v3;
+    v0 = n0; v1 = n1; v2 = n2; v3 = n3;
+}
+
+extern __shared__ __align__(16) double dmx_smem[];
+
+__global__ void __launch_bounds__(512) dmx_tile_kernel(const TileArgs a) {
+    double* tile = dmx_smem;
+    const int tid = threadIdx.x, nthr = blockDim.x;
+    const int kbits = 2 * a.k;
+    const unsigned tile_elems = 1u << kbits;
+    const unsigned E = (unsigned)a.cpb << kbits;
+    double* cs = tile + E;  // [cpb][n_rots][2]
+    const bool streaming = a.k < a.n;
+
+    long long total = a.batch;
+    if (a.work_count) total = *a.work_count;
+    long long ngroups;
+    unsigned tiles_per_circuit = 1;
+    if (streaming) {
+        tiles_per_circuit = 1u << (2 * (a.n - a.k));
+        ngroups = total * tiles_per_circuit;
+    } else {
+        ngroups = (total + a.cpb - 1) / a.cpb;
+    }
+
+    for (long long grp = blockIdx.x; grp < ngroups; grp += gridDim.x) {
+        // circuit ids handled by this CTA iteration
+        long long c_first;
+        unsigned tile_base = 0;
+        if (streaming) {
+            c_first = grp / tiles_per_circuit;
+            tile_base = map_bits((unsigned)(grp % tiles_per_circuit), a.oruns, a.n_oruns);
+        } else {
+            c_first = grp * a.cpb;
+        }
+        // ---- load / init ----
+        if (streaming) {
+            double* st = a.state + (c_first << (2 * a.n));
+            if (a.load) {
+                for (unsigned i = tid; i < tile_elems / 2; i += nthr) {
+                    unsigned t = 2 * i;
+                    unsigned g = map_bits(t, a.truns, a.n_truns) | tile_base;
+                    double2 v = *reinterpret_cast<const double2*>(st + g);
+                    *reinterpret_cast<double2*>(tile + t) = v;
+                }
+            } else {
+                for (unsigned t = tid; t < tile_elems; t += nthr) {
+                    unsigned g = map_bits(t, a.truns, a.n_truns) | tile_base;
+                    tile[t] = (g & 0xAAAAAAAAu) ? 0.0 : 1.0;
+                }
+            }
+        } else {
+            for (unsigned e = tid; e < E; e += nthr) tile[e] = ((e & (tile_elems - 1)) & 0xAAAAAAAAu) ? 0.0 : 1.0;
+        }
+        // ---- per-circuit rotation angles ----
+        for (int i = tid; i < a.cpb * a.n_rots; i += nthr) {
+            int c = i / a.n_rots, r = i - c * a.n_rots;
+            long long ci = c_first + c;
+            double sv = 0.0, cv = 1.0;
+            if (ci < total) {
+                long long b = a.worklist ? a.worklist[ci] : ci + a.circuit_offset;
+                RotInfo ri = a.rots[a.pass_rots[r]];
+                double theta = ri.scale * a.params[b * a.n_params + ri.param] + ri.offset;
+                sincos(theta, &sv, &cv);
+            }
+            cs[2 * i] = cv;
+            cs[2 * i + 1] = sv;
+        }
+        __syncthreads();
+
+        // ---- op loop ----
+        for (int oi = 0; oi < a.n_ops; ++oi) {
+            const DevOp op = a.ops[oi];
+            const double* __restrict__ cf = a.coefs + op.coef;
+            if (op.kind <= DK_ROT1 || op.kind == DK_VAR1) {
+                const int p = op.p0;
+                const unsigned G = E >> 2;
+                for (unsigned g = tid; g < G; g += nthr) {
+                    unsigned base = insert2(g, p);
+                    double v0 = tile[base], v1 = tile[base | (1u << p)], v2 = tile[base | (2u << p)], v3 = tile[base | (3u << p)];
+                    switch (op.kind) {
+                        case DK_DIAG1:
+                            v0 *= cf[0]; v1 *= cf[1]; v2 *= cf[2]; v3 *= cf[3];
+                            break;
+                        case DK_MONO1: {
+                            double in[4] = {v0, v1, v2, v3};
+                            unsigned pk = (unsigned)op.a0;
+                            // 2-bit source codes; select without dynamic register indexing
+                            auto pick = [&](unsigned s) { return s == 0 ? in[0] : (s == 1 ? in[1] : (s == 2 ? in[2] : in[3])); };
+                            v0 = cf[0] * pick(pk & 3u);
+                            v1 = cf[1] * pick((pk >> 2) & 3u);
+                            v2 = cf[2] * pick((pk >> 4) & 3u);
+                            v3 = cf[3] * pick((pk >> 6) & 3u);
+                            break;
+                        }
+                        case DK_MAT1:
+                            mat4_apply(cf, v0, v1, v2, v3);
+                            break;
+                        case DK_ROT1: {
+                            int c = (int)(base >> kbits);
+                            double cv = cs[2 * (c * a.n_rots + op.a0)], sv = cs[2 * (c * a.n_rots + op.a0) + 1];
+                            double M[16];
+#pragma unroll
+                            for (int e = 0; e < 16; ++e) M[e] = cf[e] + cv * cf[16 + e] + sv * cf[32 + e];
+                            mat4_apply(M, v0, v1, v2, v3);
+                            break;
+                        }
+                        default: {  // DK_VAR1
+                            long long ci = c_first + (long long)(base >> kbits);
+                            if (a.variants && ci < total) {
+                                long long b = a.worklist ? a.worklist[ci] : ci + a.circuit_offset;
+                                unsigned idx = a.variants[b * a.n_slots + op.a0];
+                                if (idx) mat4_apply(cf + 16 * (idx & 15u), v0, v1, v2, v3);
+                            }
+                            break;
+                        }
+                    }
+                    tile[base] = v0; tile[base | (1u << p)] = v1; tile[base | (2u << p)] = v2; tile[base | (3u << p)] = v3;
+                }
+            } else {
+                const int p0 = op.p0, p1 = op.p1;
+                const int pa = p0 < p1 ? p0 : p1, pb = p0 < p1 ? p1 : p0;
+                const unsigned G = E >> 4;
+                for (unsigned g = tid; g < G; g += nthr) {
+                    unsigned base = insert2(insert2(g, pa), pb);
+                    double v[16];
+#pragma unroll
+                    for (int c0 = 0; c0 < 4; ++c0)
+#pragma unroll
+                        for (int c1 = 0; c1 < 4; ++c1) v[c0 * 4 + c1] = tile[base | ((unsigned)c0 << p0) | ((unsigned)c1 << p1)];
+                    if (op.kind == DK_DIAG2) {
+#pragma unroll
+                        for (int e = 0; e < 16; ++e) v[e] *= cf[e];
+                    } else if (op.kind == DK_MONO2) {
+                        unsigned long long pk = ((unsigned long long)(unsigned)op.a1 << 32) | (unsigned)op.a0;
+#pragma unroll
+                        for (int e = 0; e < 16; ++e) {
+                            unsigned s = (unsigned)(pk >> (4 * e)) & 15u;
+                            v[e] = cf[e] * tile[base | ((s >> 2) << p0) | ((s & 3u) << p1)];
+                        }
+                    } else if (op.kind == DK_MAT2) {
+                        double nv[16];
+#pragma unroll
+                        for (int r = 0; r < 16; ++r) {
+                            double s = 0.0;
+#pragma unroll
+                            for (int c = 0; c < 16; ++c) s += cf[r * 16 + c] * v[c];
+                            nv[r] = s;
+                        }
+#pragma unroll
+                        for (int e = 0; e < 16; ++e) v[e] = nv[e];
+                    } else {  // DK_VAR2
+                        long long ci = c_first + (long long)(base >> kbits);
+                        unsigned idx = 0;
+                        if (a.variants && ci < total) {
+                            long long b = a.worklist ? a.worklist[ci] : ci + a.circuit_offset;
+                            idx = a.variants[b * a.n_slots + op.a0];
+                        }
+                        if (idx) {
+                            const double* Ma = cf + 16 * (idx >> 4);
+                            const double* Mb = cf + 16 * (idx & 15u);
+#pragma unroll
+                            for (int c1 = 0; c1 < 4; ++c1) mat4_apply(Ma, v[c1], v[4 + c1], v[8 + c1], v[12 + c1]);
+#pragma unroll
+                            for (int c0 = 0; c0 < 4; ++c0) mat4_apply(Mb, v[4 * c0], v[4 * c0 + 1], v[4 * c0 + 2], v[4 * c0 + 3]);
+                            const double* cc = a.coefs + op.a1;
+                            if (op.a2 == CLS_DIAG) {
+#pragma unroll
+                                for (int e = 0; e < 16; ++e) v[e] *= cc[e];
+                            } else {
+                                double nv[16];
+#pragma unroll
+                                for (int r = 0; r < 16; ++r) {
+                                    double s = 0.0;
+#pragma unroll
+                                    for (int c = 0; c < 16; ++c) s += cc[r * 16 + c] * v[c];
+                                    nv[r] = s;
+                                }
+#pragma unroll
+                                for (int e = 0; e < 16; ++e) v[e] = nv[e];
+                            }
+                        }
+                    }
+                    // MONO2 read its sources straight from the tile: all reads of this group are done
+                    // (each thread owns its whole 16-element group), so the in-place write is safe.
+#pragma unroll
+                    for (int c0 = 0; c0 < 4; ++c0)
+#pragma unroll
+                        for (int c1 = 0; c1 < 4; ++c1) tile[base | ((unsigned)c0 << p0) | ((unsigned)c1 << p1)] = v[c0 * 4 + c1];
+                }
+            }
+            __syncthreads();
+        }
+
+        // ---- epilogue ----
+        if (streaming) {
+            if (a.store) {
+                double* st = a.state + (c_first << (2 * a.n));
+                for (unsigned i = tid; i < tile_elems / 2; i += nthr) {
+                    unsigned t = 2 * i;
+                    unsigned g = map_bits(t, a.truns, a.n_truns) | tile_base;
+                    *reinterpret_cast<double2*>(st + g) = *reinterpret_cast<const double2*>(tile + t);
+                }
+            }
+        } else if (a.epilogue == 1) {
+            const int warp = tid >> 5, lane = tid & 31, nwarps = nthr >> 5;
+            for (int c = warp; c < a.cpb; c += nwarps) {
+                long long ci = c_first + c;
+                if (ci >= total) continue;
+                const double* r = tile + ((unsigned)c << kbits);
+                double e = 0.0;
+                for (int t = lane; t < a.n_terms; t += 32) e += a.term_coef[t] * r[a.term_idx[t]];
+#pragma unroll
+                for (int off = 16; off > 0; off >>= 1) e += __shfl_xor_sync(0xffffffffu, e, off);
+                if (lane == 0) {
+                    long long b = a.worklist ? a.worklist[ci] : ci;
+                    a.out[b] = e;
+                }
+            }
+        } else if (a.epilogue == 2) {
+            for (unsigned e = tid; e < E; e += nthr) {
+                long long ci = c_first + (e >> kbits);
+                if (ci < total) a.out[(ci << kbits) + (e & (tile_elems - 1))] = tile[e];
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// segment kernel (n <= 4 padded to 4: 256 Pauli coefficients, thread j owns coefficient j of CPB circuits)
+// ---------------------------------------------------------------------------------------------------------
+struct SlotDev {
+    int seg, nq, tab_off, pad;
+    unsigned diag_ok[8];
+};
+
+struct SegArgs {
+    int nseg, n_rots, n_params, n_slots, n_terms;
+    long long batch;
+    const unsigned* seg_pk;     // [nseg][256]  src0 | src1<<8 | active<<16
+    const double2* seg_w;       // [nseg][256]  (w0, w1)
+    const int* seg_rot;         // [nseg]
+    const RotInfo* rots;
+    const double* params;
+    const uint8_t* variants;
+    const SlotDev* slots;
+    const uint8_t* labels;      // [n_slots][256]
+    const double* coefs;
+    const uint8_t* e_src;
+    const double* e_w;
+    double* out;
+    int* worklist;              // circuits that need the general path
+    int* work_count;
+};
+
+constexpr int SEG_MAXACT = 24;
+
+template <int CPB>
+__global__ void __launch_bounds__(256) dmx_segment_kernel(const SegArgs a) {
+    double* ex = dmx_smem;                         // [2][CPB][256]
+    double* cs = ex + 2 * CPB * 256;               // [CPB][nseg][2]
+    int* nact = reinterpret_cast<int*>(cs + 2 * CPB * a.nseg);   // [CPB] (-1: general path)
+    unsigned* act = reinterpret_cast<unsigned*>(nact + CPB + 1); // [CPB][SEG_MAXACT]  slot<<8 | idx
+    int* any_act = nact + CPB;
+    const int j = threadIdx.x, warp = j >> 5, lane = j & 31;
+    const long long ngroups = (a.batch + CPB - 1) / CPB;
+    const double init = (j & 0xAA) ? 0.0 : 1.0;
+
+    for (long long grp = blockIdx.x; grp < ngroups; grp += gridDim.x) {
+        const long long b0 = grp * CPB;
+        // rotation angles
+        for (int i = j; i < CPB * a.nseg; i += 256) {
+            int c = i / a.nseg, k = i - c * a.nseg;
+            double sv = 0.0, cv = 1.0;
+            int rid = a.seg_rot[k];
+            if (b0 + c < a.batch && rid >= 0) {
+                RotInfo ri = a.rots[rid];
+                sincos(ri.scale * a.params[(b0 + c) * a.n_params + ri.param] + ri.offset, &sv, &cv);
+            }
+            cs[2 * i] = cv;
+            cs[2 * i + 1] = sv;
+        }
+        // variant rows -> short lists of non-identity slots
+        if (j == 0) *any_act = 0;
+        __syncthreads();
+        if (a.variants) {
+            for (int c = warp; c < CPB; c += 8) {
+                int count = 0;
+                bool general = false;
+                if (b0 + c < a.batch) {
+                    const uint8_t* row = a.variants + (b0 + c) * a.n_slots;
+                    for (int s0 = 0; s0 < a.n_slots; s0 += 32) {
+                        int s = s0 + lane;
+                        unsigned idx = s < a.n_slots ? row[s] : 0u;
+                        if (idx && a.slots[s].seg < 0) idx = 0;  // slot not present in the circuit
+                        bool nz = idx != 0;
+                        if (nz && !((a.slots[s].diag_ok[idx >> 5] >> (idx & 31)) & 1u)) general = true;
+                        unsigned m = __ballot_sync(0xffffffffu, nz);
+                        int pos = count + __popc(m & ((1u << lane) - 1u));
+                        if (nz && pos < SEG_MAXACT) act[c * SEG_MAXACT + pos] = ((unsigned)s << 8) | idx;
+                        count += __popc(m);
+                    }
+                    general = __any_sync(0xffffffffu, general) || count > SEG_MAXACT;
+                }
+                if (lane == 0) {
+                    nact[c] = general ? -1 : count;
+                    if (general || count) atomicOr(any_act, 1);
+                    if (general) a.worklist[atomicAdd(a.work_count, 1)] = (int)(b0 + c);
+                }
+            }
+            __syncthreads();
+        }
+        const bool have_act = a.variants && *any_act;
+
+        double r[CPB];
+#pragma unroll
+        for (int c = 0; c < CPB; ++c) r[c] = init;
+
+        for (int k = 0; k <= a.nseg; ++k) {
+            if (have_act) {
+#pragma unroll
+                for (int c = 0; c < CPB; ++c) {
+                    int na = nact[c];
+                    for (int e = 0; e < na; ++e) {
+                        unsigned ent = act[c * SEG_MAXACT + e];
+                        int s = ent >> 8;
+                        unsigned idx = ent & 255u;
+                        SlotDev sd = a.slots[s];
+                        if (sd.seg != k) continue;
+                        unsigned lab = a.labels[s * 256 + j];
+                        const double* t = a.coefs + sd.tab_off;
+                        double f = sd.nq == 1 ? t[idx * 4 + lab]
+                                              : t[(idx >> 4) * 4 + (lab >> 2)] * t[(idx & 15u) * 4 + (lab & 3u)] * t[64 + lab];
+                        r[c] *= f;
+                    }
+                }
+            }
+            double* buf = ex + (k & 1) * CPB * 256;
+#pragma unroll
+            for (int c = 0; c < CPB; ++c) buf[c * 256 + j] = r[c];
+            __syncthreads();
+            if (k == a.nseg) break;
+            const unsigned pk = a.seg_pk[k * 256 + j];
+            const double2 w = a.seg_w[k * 256 + j];
+            const unsigned s0 = pk & 255u, s1 = (pk >> 8) & 255u;
+            const bool active = (pk >> 16) & 1u;
+#pragma unroll
+            for (int c = 0; c < CPB; ++c) {
+                double av = w.x * buf[c * 256 + s0];
+                if (active) {
+                    double bv = w.y * buf[c * 256 + s1];
+                    double cv = cs[2 * (c * a.nseg + k)], sv = cs[2 * (c * a.nseg + k) + 1];
+                    av = cv * av + sv * bv;
+                }
+                r[c] = av;
+            }
+        }
+        // energy stage: E = sum_t e_w[t] * r[e_src[t]]
+        {
+            const double* buf = ex + (a.nseg & 1) * CPB * 256;
+            for (int c = warp; c < CPB; c += 8) {
+                if (b0 + c >= a.batch) continue;
+                double e = 0.0;
+                for (int t = lane; t < a.n_terms; t += 32) e += a.e_w[t] * buf[c * 256 + a.e_src[t]];
+#pragma unroll
+                for (int off = 16; off > 0; off >>= 1) e += __shfl_xor_sync(0xffffffffu, e, off);
+                if (lane == 0 && !(a.variants && nact[c] < 0)) a.out[b0 + c] = e;
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// small kernels
+// ---------------------------------------------------------------------------------------------------------
+__global__ void dmx_energy_kernel(const double* __restrict__ state, int n, long long batch, const uint32_t* __restrict__ term_idx,
+                                  const double* __restrict__ term_coef, int n_terms, double* __restrict__ out, long long out_offset) {
+    const int lane = threadIdx.x & 31;
+    long long w = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (w >= batch) return;
+    const double* r = state + (w << (2 * n));
+    double e = 0.0;
+    for (int t = lane; t < n_terms; t += 32) e += term_coef[t] * r[term_idx[t]];
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) e += __shfl_xor_sync(0xffffffffu, e, off);
+    if (lane == 0) out[out_offset + w] = e;
+}
+
+__device__ __forceinline__ unsigned spread_bits(unsigned v) {  // bit b -> bit 2b
+    v &= 0xFFFFu;
+    v = (v | (v << 8)) & 0x00FF00FFu;
+    v = (v | (v << 4)) & 0x0F0F0F0Fu;
+    v = (v | (v << 2)) & 0x33333333u;
+    v = (v | (v << 1)) & 0x55555555u;
+    return v;
+}
+
+// rho[i][j] = 2^-n sum_z r[idx(x=i^j, z)] * i^{ny} (-1)^{popc(i&z&~x) + popc(~i&x&z)}
+__global__ void dmx_pauli_to_rho(const double* __restrict__ pauli, int n, long long batch, double2* __restrict__ rho) {
+    const unsigned dim = 1u << n;
+    long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    long long per = (long long)dim * dim;
+    if (e >= batch * per) return;
+    long long b = e / per;
+    unsigned ij = (unsigned)(e - b * per);
+    unsigned i = ij >> n, jc = ij & (dim - 1), x = i ^ jc;
+    const double* r = pauli + (b << (2 * n));
+    const unsigned xs = spread_bits(x) << 1;
+    double re = 0.0, im = 0.0;
+    for (unsigned z = 0; z < dim; ++z) {
+        double v = r[xs | spread_bits(z)];
+        int ny = __popc(x & z);
+        int sg = (__popc(i & z & ~x) + __popc(~i & x & z)) & 1;
+        if (sg) v = -v;
+        switch (ny & 3) {
+            case 0: re += v; break;
+            case 1: im += v; break;
+            case 2: re -= v; break;
+            default: im -= v; break;
+        }
+    }
+    const double sc = 1.0 / (double)dim;
+    rho[e] = make_double2(re * sc, im * sc);
+}
+
+// diag[i] = | 2^-n sum_z r[idx(0,z)] (-1)^{popc(i&z)} |, optionally divided by the sum over i
+__global__ void dmx_pauli_to_diag(const double* __restrict__ pauli, int n, long long batch, double* __restrict__ diag, int renorm) {
+    __shared__ double red[32];
+    __shared__ double total;
+    const unsigned dim = 1u << n;
+    const long long b = blockIdx.x;
+    const double* r = pauli + (b << (2 * n));
+    double* d = diag + b * dim;
+    double part = 0.0;
+    for (unsigned i = threadIdx.x; i < dim; i += blockDim.x) {
+        double s = 0.0;
+        for (unsigned z = 0; z < dim; ++z) {
+            double v = r[spread_bits(z)];
+            s += (__popc(i & z) & 1) ? -v : v;
+        }
+        s = fabs(s / (double)dim);
+        d[i] = s;
+        part += s;
+    }
+    if (!renorm) return;
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) part += __shfl_xor_sync(0xffffffffu, part, off);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = part;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (unsigned w = 0; w < (blockDim.x + 31) / 32; ++w) t += red[w];
+        total = t;
+    }
+    __syncthreads();
+    const double inv = 1.0 / total;
+    for (unsigned i = threadIdx.x; i < dim; i += blockDim.x) d[i] *= inv;
+}
+
+constexpr int QP_BLOCKS = 148, QP_THREADS = 256;
+
+__global__ void dmx_qp_reduce_stage1(const double* __restrict__ v, const double* __restrict__ w, const int* __restrict__ cnt,
+                                     long long batch, double* __restrict__ partial) {
+    __shared__ double red[3][QP_THREADS / 32];
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0;
+    // fixed assignment of elements to threads -> bit-reproducible result for a given batch
+    for (long long i = (long long)blockIdx.x * QP_THREADS + threadIdx.x; i < batch; i += (long long)QP_BLOCKS * QP_THREADS) {
+        double x = w[i] * v[i];
+        s0 += x;
+        s1 += x * x;
+        s2 += cnt ? (double)cnt[i] : 1.0;
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        s0 += __shfl_xor_sync(0xffffffffu, s0, off);
+        s1 += __shfl_xor_sync(0xffffffffu, s1, off);
+        s2 += __shfl_xor_sync(0xffffffffu, s2, off);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        red[0][threadIdx.x >> 5] = s0; red[1][threadIdx.x >> 5] = s1; red[2][threadIdx.x >> 5] = s2;
+    }
+    __syncthreads();
+    if (threadIdx.x < 3) {
+        double t = 0.0;
+        for (int k = 0; k < QP_THREADS / 32; ++k) t += red[threadIdx.x][k];
+        partial[blockIdx.x * 3 + threadIdx.x] = t;
+    }
+}
+
+__global__ void dmx_qp_reduce_stage2(const double* __restrict__ partial, double* __restrict__ out3) {
+    if (threadIdx.x < 3) {
+        double t = 0.0;
+        for (int k = 0; k < QP_BLOCKS; ++k) t += partial[k * 3 + threadIdx.x];
+        out3[threadIdx.x] = t;
+    }
+}
+
+__global__ void dmx_fp64_fma_kernel(double* out, int iters) {
+    double a0 = threadIdx.x * 1e-9, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+    const double m = 1.0000001, c = 1e-7;
+    for (int i = 0; i < iters; ++i) {
+        a0 = fma(a0, m, c); a1 = fma(a1, m, c); a2 = fma(a2, m, c); a3 = fma(a3, m, c);
+        a4 = fma(a4, m, c); a5 = fma(a5, m, c); a6 = fma(a6, m, c); a7 = fma(a7, m, c);
+    }
+    double s = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+    if (s == 12345.678) out[0] = s;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// device mirror of a plan
+// ---------------------------------------------------------------------------------------------------------
+struct DevPlan {
+    int device = -1;
+    DevOp* ops = nullptr;
+    double* coefs = nullptr;
+    RotInfo* rots = nullptr;
+    int* pass_rots = nullptr;          // concatenated
+    std::vector<int> pass_rot_off;
+    uint32_t* term_idx = nullptr;
+    double* term_coef = nullptr;
+    // segment
+    unsigned* seg_pk = nullptr;
+    double2* seg_w = nullptr;
+    int* seg_rot = nullptr;
+    SlotDev* slots = nullptr;
+    uint8_t* labels = nullptr;
+    uint8_t* e_src = nullptr;
+    double* e_w = nullptr;
+    int* worklist = nullptr;           // capacity wl_cap (+ counter at the end)
+    long long wl_cap = 0;
+    // host-buffer API staging
+    cudaStream_t stream = nullptr;
+    void* h_stage = nullptr; size_t h_cap = 0;
+    void* d_stage = nullptr; size_t d_cap = 0;
+    std::mutex mu;
+    int sm_count = 148;
+};
+
+template <class T>
+static cudaError_t upload(T** dst, const std::vector<T>& src) {
+    *dst = nullptr;
+    if (src.empty()) return cudaSuccess;
+    cudaError_t e = cudaMalloc((void**)dst, src.size() * sizeof(T));
+    if (e != cudaSuccess) return e;
+    return cudaMemcpy(*dst, src.data(), src.size() * sizeof(T), cudaMemcpyHostToDevice);
+}
+
+static std::mutex g_upload_mu;
+
+static int ensure_device(Plan& p, DevPlan** out) {
+    std::lock_guard<std::mutex> lock(g_upload_mu);
+    if (p.dev) { *out = (DevPlan*)p.dev; return DMX_OK; }
+    int dev = 0;
+    CUDA_TRY(cudaGetDevice(&dev));
+    DevPlan* d = new DevPlan();
+    d->device = dev;
+    CUDA_TRY(cudaDeviceGetAttribute(&d->sm_count, cudaDevAttrMultiProcessorCount, dev));
+    CUDA_TRY(upload(&d->ops, p.dev_ops));
+    {
+        std::vector<double> c = p.coefs;
+        if (c.empty()) c.push_back(0.0);
+        CUDA_TRY(upload(&d->coefs, c));
+    }
+    {
+        std::vector<RotInfo> r = p.rots;
+        if (r.empty()) r.push_back(RotInfo{0, 0, 0.0, 0.0});
+        CUDA_TRY(upload(&d->rots, r));
+    }
+    std::vector<int> pr;
+    for (const Pass& ps : p.passes) {
+        d->pass_rot_off.push_back((int)pr.size());
+        pr.insert(pr.end(), ps.rot_ids.begin(), ps.rot_ids.end());
+    }
+    if (pr.empty()) pr.push_back(0);
+    CUDA_TRY(upload(&d->pass_rots, pr));
+    CUDA_TRY(upload(&d->term_idx, p.term_idx));
+    CUDA_TRY(upload(&d->term_coef, p.term_coef));
+    if (p.seg_eligible) {
+        std::vector<unsigned> pk((size_t)std::max(p.nseg, 1) * 256, 0u);
+        std::vector<double2> w((size_t)std::max(p.nseg, 1) * 256, make_double2(0, 0));
+        std::vector<int> sr(std::max(p.nseg, 1), -1);
+        for (int k = 0; k < p.nseg; ++k) {
+            const Segment& s = p.segs[k];
+            sr[k] = s.rot_id;
+            for (int j = 0; j < 256; ++j) {
+                pk[k * 256 + j] = (unsigned)s.src0[j] | ((unsigned)s.src1[j] << 8) | ((unsigned)s.active[j] << 16);
+                w[k * 256 + j] = make_double2(s.w0[j], s.w1[j]);
+            }
+        }
+        CUDA_TRY(upload(&d->seg_pk, pk));
+        CUDA_TRY(upload(&d->seg_w, w));
+        CUDA_TRY(upload(&d->seg_rot, sr));
+        std::vector<SlotDev> sl(std::max(p.n_slots, 1));
+        std::vector<uint8_t> lab((size_t)std::max(p.n_slots, 1) * 256, 0);
+        for (int s = 0; s < p.n_slots; ++s) {
+            sl[s].seg = p.slots[s].seg; sl[s].nq = p.slots[s].nq; sl[s].tab_off = p.slots[s].tab_off; sl[s].pad = 0;
+            std::memcpy(sl[s].diag_ok, p.slots[s].diag_ok, sizeof(sl[s].diag_ok));
+            std::memcpy(&lab[(size_t)s * 256], p.slots[s].label.data(), 256);
+        }
+        CUDA_TRY(upload(&d->slots, sl));
+        CUDA_TRY(upload(&d->labels, lab));
+        CUDA_TRY(upload(&d->e_src, p.e_src));
+        CUDA_TRY(upload(&d->e_w, p.e_w));
+        // coefficient table may have grown with slot tables after dev-op emission: p.coefs is final here
+    }
+    p.dev = d;
+    *out = d;
+    return DMX_OK;
+}
+
+static void free_device(Plan& p) {
+    DevPlan* d = (DevPlan*)p.dev;
+    if (!d) return;
+    cudaFree(d->ops); cudaFree(d->coefs); cudaFree(d->rots); cudaFree(d->pass_rots); cudaFree(d->term_idx); cudaFree(d->term_coef);
+    cudaFree(d->seg_pk); cudaFree(d->seg_w); cudaFree(d->seg_rot); cudaFree(d->slots); cudaFree(d->labels);
+    cudaFree(d->e_src); cudaFree(d->e_w); cudaFree(d->worklist);
+    if (d->h_stage) cudaFreeHost(d->h_stage);
+    if (d->d_stage) cudaFree(d->d_stage);
+    if (d->stream) cudaStreamDestroy(d->stream);
+    delete d;
+    p.dev = nullptr;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// launch helpers
+// ---------------------------------------------------------------------------------------------------------
+static void make_runs(const std::vector<int>& qubits, int n, BitRun* runs, int* n_runs) {
+    // qubits ascending; local position of qubits[i] = 2*(m-1-i); merge neighbours into runs
+    const int m = (int)qubits.size();
+    int count = 0;
+    int i = m - 1;
+    while (i >= 0) {
+        int jv = i;
+        while (jv - 1 >= 0 && qubits[jv - 1] == qubits[jv] - 1) --jv;
+        BitRun r;
+        r.lshift = 2 * (m - 1 - i);
+        r.gshift = 2 * (n - 1 - qubits[i]);
+        r.width = 2 * (i - jv + 1);
+        if (count >= 8) throw std::runtime_error("tile qubits form more than 8 runs");
+        runs[count++] = r;
+        i = jv - 1;
+    }
+    *n_runs = count;
+}
+
+static int tile_threads(unsigned elems) { return elems >= 16384 ? 512 : 256; }
+
+static int tile_cpb(int n) {
+    int cpb = 1;
+    while ((cpb << (2 * n)) < 4096) cpb <<= 1;
+    return cpb;
+}
+
+static size_t tile_smem(int k, int cpb, int n_rots) {
+    return ((size_t)cpb << (2 * k)) * 8 + (size_t)cpb * std::max(n_rots, 1) * 16;
+}
+
+static int launch_tile(const TileArgs& a, int grid, int threads, size_t smem, cudaStream_t st) {
+    static std::mutex mu;
+    static size_t configured = 0;
+    {
+        std::lock_guard<std::mutex> lock(mu);
+        if (smem > configured) {
+            CUDA_TRY(cudaFuncSetAttribute(dmx_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max(smem, (size_t)48 * 1024)));
+            configured = std::max(smem, (size_t)48 * 1024);
+        }
+    }
+    dmx_tile_kernel<<<grid, threads, smem, st>>>(a);
+    ++g_launches;
+    CUDA_TRY(cudaGetLastError());
+    return DMX_OK;
+}
+
+enum OutMode { OUT_ENERGY = 1, OUT_PAULI = 2 };
+
+// Whole-state-in-smem execution (n <= 7).  worklist != nullptr: run only the listed circuits (energy only).
+static int run_tile_single(Plan& p, DevPlan* d, long long batch, const double* params, const uint8_t* variants, double* out,
+                           int mode, const int* worklist, const int* work_count, cudaStream_t st) {
+    const Pass& ps = p.passes[0];
+    TileArgs a{};
+    a.ops = d->ops; a.n_ops = ps.n_ops; a.coefs = d->coefs; a.rots = d->rots; a.pass_rots = d->pass_rots;
+    a.n_rots = (int)ps.rot_ids.size(); a.params = params; a.n_params = p.n_params; a.variants = variants; a.n_slots = p.n_slots;
+    a.n = p.n; a.k = p.n; a.cpb = tile_cpb(p.n); a.batch = batch; a.worklist = worklist; a.work_count = work_count;
+    a.epilogue = mode; a.term_idx = d->term_idx; a.term_coef = d->term_coef; a.n_terms = (int)p.term_idx.size(); a.out = out;
+    const unsigned E = (unsigned)a.cpb << (2 * p.n);
+    const int threads = tile_threads(E);
+    const size_t smem = tile_smem(p.n, a.cpb, a.n_rots);
+    if (smem > 227 * 1024) return fail(DMX_ERR_UNSUPPORTED, "tile does not fit shared memory (too many rotations in one pass)");
+    long long groups = (batch + a.cpb - 1) / a.cpb;
+    int per_sm = (int)std::max<size_t>(1, std::min<size_t>(2048 / threads, (227 * 1024) / std::max<size_t>(smem, 1)));
+    long long cap = (long long)d->sm_count * per_sm;
+    int grid = (int)std::max<long long>(1, std::min(groups, cap));
+    return launch_tile(a, grid, threads, smem, st);
+}
+
+// Streaming execution (n > tile_k): state[chunk][4^n] in `state`; all passes over one chunk of circuits.
+static int run_streaming(Plan& p, DevPlan* d, long long chunk, long long circuit_offset, const double* params, const uint8_t* variants,
+                         double* state, cudaStream_t st) {
+    for (size_t pi = 0; pi < p.passes.size(); ++pi) {
+        const Pass& ps = p.passes[pi];
+        TileArgs a{};
+        a.ops = d->ops + ps.first_op; a.n_ops = ps.n_ops; a.coefs = d->coefs; a.rots = d->rots;
+        a.pass_rots = d->pass_rots + d->pass_rot_off[pi]; a.n_rots = (int)ps.rot_ids.size();
+        a.params = params; a.n_params = p.n_params; a.variants = variants; a.n_slots = p.n_slots;
+        a.n = p.n; a.k = (int)ps.tile_q.size(); a.cpb = 1; a.batch = chunk; a.state = state; a.circuit_offset = circuit_offset;
+        a.load = pi > 0; a.store = 1;
+        std::vector<int> others;
+        {
+            std::vector<char> in(p.n, 0);
+            for (int q : ps.tile_q) in[q] = 1;
+            for (int q = 0; q < p.n; ++q) if (!in[q]) others.push_back(q);
+        }
+        try {
+            make_runs(ps.tile_q, p.n, a.truns, &a.n_truns);
+            make_runs(others, p.n, a.oruns, &a.n_oruns);
+        } catch (const std::exception& e) { return fail(DMX_ERR_UNSUPPORTED, e.what()); }
+        const unsigned E = 1u << (2 * a.k);
+        const int threads = tile_threads(E);
+        const size_t smem = tile_smem(a.k, 1, a.n_rots);
+        if (smem > 227 * 1024) return fail(DMX_ERR_UNSUPPORTED, "tile does not fit shared memory");
+        long long groups = chunk << (2 * (p.n - a.k));
+        int grid = (int)std::min<long long>(groups, 1LL << 30);
+        int rc = launch_tile(a, grid, threads, smem, st);
+        if (rc) return rc;
+    }
+    return DMX_OK;
+}
+
+template <int CPB>
+static int launch_segment(const SegArgs& a, int sm_count, cudaStream_t st) {
+    size_t smem = (size_t)2 * CPB * 256 * 8 + (size_t)2 * CPB * std::max(a.nseg, 1) * 8 + (CPB + 1) * 4 + (size_t)CPB * SEG_MAXACT * 4 + 16;
+    if (smem > 227 * 1024) return fail(DMX_ERR_UNSUPPORTED, "segment kernel: too many segments for shared memory");
+    static std::mutex mu;
+    static size_t configured = 0;
+    {
+        std::lock_guard<std::mutex> lock(mu);
+        if (smem > configured) {
+            CUDA_TRY(cudaFuncSetAttribute(dmx_segment_kernel<CPB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max(smem, (size_t)48 * 1024)));
+            configured = std::max(smem, (size_t)48 * 1024);
+        }
+    }
+    long long groups = (a.batch + CPB - 1) / CPB;
+    int per_sm = (int)std::max<size_t>(1, std::min<size_t>(8, (227 * 1024) / smem));
+    int grid = (int)std::max<long long>(1, std::min<long long>(groups, (long long)sm_count * per_sm));
+    dmx_segment_kernel<CPB><<<grid, 256, smem, st>>>(a);
+    ++g_launches;
+    CUDA_TRY(cudaGetLastError());
+    return DMX_OK;
+}
+
+static int g_seg_cpb = 8;
+
+static int run_segment(Plan& p, DevPlan* d, long long batch, const double* params, const uint8_t* variants, double* out, cudaStream_t st) {
+    SegArgs a{};
+    a.nseg = p.nseg; a.n_rots = (int)p.rots.size(); a.n_params = p.n_params; a.n_slots = p.n_slots; a.n_terms = (int)p.e_w.size();
+    a.batch = batch; a.seg_pk = d->seg_pk; a.seg_w = d->seg_w; a.seg_rot = d->seg_rot; a.rots = d->rots; a.params = params;
+    a.variants = variants; a.slots = d->slots; a.labels = d->labels; a.coefs = d->coefs; a.e_src = d->e_src; a.e_w = d->e_w; a.out = out;
+    if (variants) {
+        std::lock_guard<std::mutex> lock(d->mu);
+        if (d->wl_cap < batch) {
+            if (d->worklist) CUDA_TRY(cudaFree(d->worklist));
+            d->worklist = nullptr;
+            CUDA_TRY(cudaMalloc((void**)&d->worklist, (size_t)(batch + 1) * sizeof(int)));
+            d->wl_cap = batch;
+        }
+        a.worklist = d->worklist + 1;
+        a.work_count = d->worklist;
+        CUDA_TRY(cudaMemsetAsync(d->worklist, 0, sizeof(int), st));
+    }
+    int rc;
+    switch (g_seg_cpb) {
+        case 2: rc = launch_segment<2>(a, d->sm_count, st); break;
+        case 4: rc = launch_segment<4>(a, d->sm_count, st); break;
+        case 16: rc = launch_segment<16>(a, d->sm_count, st); break;
+        default: rc = launch_segment<8>(a, d->sm_count, st); break;
+    }
+    if (rc) return rc;
+    if (variants) {
+        // circuits with non-diagonal correction ops (R-type / projector basis ops) take the general tile path
+        rc = run_tile_single(p, d, batch, params, variants, out, OUT_ENERGY, d->worklist + 1, d->worklist, st);
+    }
+    return rc;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// C ABI
+// ---------------------------------------------------------------------------------------------------------
+extern "C" {
+
+int dmx_version(void) { return DMX_VERSION; }
+const char* dmx_last_error(void) { return g_last_error.c_str(); }
+int64_t dmx_launch_count(void) { return g_launches.load(); }
+
+int dmx_plan_create(int n_qubits, int n_params, int n_slots, const dmx_op* ops, int n_ops, const double* matrix_pool,
+                    size_t pool_len, dmx_plan** out) {
+    if (!out) return fail(DMX_ERR_INVALID, "out is NULL");
+    *out = nullptr;
+    if (n_qubits < 1) return fail(DMX_ERR_INVALID, "n_qubits must be >= 1");
+    if (n_qubits > DMX_MAX_QUBITS) return fail(DMX_ERR_UNSUPPORTED, "n_qubits exceeds DMX_MAX_QUBITS");
+    if (n_params < 0 || n_slots < 0 || n_ops < 0 || (n_ops > 0 && !ops)) return fail(DMX_ERR_INVALID, "bad sizes");
+    try {
+        dmx_plan* pl = new dmx_plan();
+        pl->p.n = n_qubits; pl->p.n_params = n_params; pl->p.n_slots = n_slots;
+        pl->p.ops.assign(ops, ops + n_ops);
+        if (pool_len) pl->p.pool.assign(matrix_pool, matrix_pool + pool_len);
+        *out = pl;
+    } catch (const std::bad_alloc&) { return fail(DMX_ERR_NOMEM, "out of host memory"); }
+    return DMX_OK;
+}
+
+int dmx_plan_set_hamiltonian(dmx_plan* plan, int n_terms, const uint32_t* xmask, const uint32_t* zmask, const double* coeff) {
+    if (!plan || n_terms < 0 || (n_terms && (!xmask || !zmask || !coeff))) return fail(DMX_ERR_INVALID, "bad Hamiltonian arguments");
+    if (plan->p.finalized) return fail(DMX_ERR_STATE, "plan already finalized");
+    const uint32_t lim = plan->p.n >= 32 ? 0xffffffffu : ((1u << plan->p.n) - 1u);
+    for (int t = 0; t < n_terms; ++t)
+        if ((xmask[t] | zmask[t]) & ~lim) return fail(DMX_ERR_INVALID, "Hamiltonian mask has bits beyond n_qubits");
+    plan->p.hx.assign(xmask, xmask + n_terms);
+    plan->p.hz.assign(zmask, zmask + n_terms);
+    plan->p.hc.assign(coeff, coeff + n_terms);
+    return DMX_OK;
+}
+
+int dmx_plan_set_option(dmx_plan* plan, const char* key, int value) {
+    if (!plan || !key) return fail(DMX_ERR_INVALID, "NULL argument");
+    if (plan->p.finalized) return fail(DMX_ERR_STATE, "plan already finalized");
+    std::string k(key);
+    if (k == "fuse") plan->p.opt_fuse = value != 0;
+    else if (k == "segments") plan->p.opt_segments = value != 0;
+    else if (k == "tile_qubits") {
+        if (value < 4 || value > 7) return fail(DMX_ERR_INVALID, "tile_qubits must be in 4..7");
+        plan->p.opt_tile_qubits = value;
+    } else if (k == "segment_cpb") {
+        if (value != 2 && value != 4 && value != 8 && value != 16) return fail(DMX_ERR_INVALID, "segment_cpb must be 2, 4, 8 or 16");
+        g_seg_cpb = value;
+    } else return fail(DMX_ERR_INVALID, "unknown option: " + k);
+    return DMX_OK;
+}
+
+int dmx_plan_finalize(dmx_plan* plan) {
+    if (!plan) return fail(DMX_ERR_INVALID, "plan is NULL");
+    if (plan->p.finalized) return fail(DMX_ERR_STATE, "plan already finalized");
+    try {
+        lower_plan(plan->p);
+    } catch (const std::bad_alloc&) {
+        return fail(DMX_ERR_NOMEM, "out of host memory");
+    } catch (const std::exception& e) {
+        return fail(DMX_ERR_INVALID, e.what());
+    }
+    return DMX_OK;
+}
+
+int dmx_plan_get_info(const dmx_plan* plan, dmx_plan_info* info) {
+    if (!plan || !info) return fail(DMX_ERR_INVALID, "NULL argument");
+    if (!plan->p.finalized) return fail(DMX_ERR_STATE, "plan not finalized");
+    *info = plan->p.info;
+    return DMX_OK;
+}
+
+int64_t dmx_plan_dump(const dmx_plan* plan, char* buf, int64_t buf_len) {
+    if (!plan || !plan->p.finalized) { fail(DMX_ERR_STATE, "plan not finalized"); return -1; }
+    std::string s = dump_plan(plan->p);
+    if (buf && buf_len > 0) {
+        size_t ncopy = std::min<size_t>(s.size(), (size_t)buf_len - 1);
+        std::memcpy(buf, s.data(), ncopy);
+        buf[ncopy] = 0;
+    }
+    return (int64_t)s.size() + 1;
+}
+
+void dmx_plan_destroy(dmx_plan* plan) {
+    if (!plan) return;
+    free_device(plan->p);
+    delete plan;
+}
+
+size_t dmx_workspace_bytes(const dmx_plan* plan, int64_t batch) {
+    if (!plan || !plan->p.finalized || batch <= 0) return 0;
+    if (plan->p.path != 2) return 0;
+    // at least one state; more lets several circuits share a launch (caller may pass any multiple)
+    return (size_t)plan->p.info.state_bytes * (size_t)std::min<int64_t>(batch, 64);
+}
+
+static int check_exec(dmx_plan* plan, int64_t batch, const double* d_params, const void* out) {
+    if (!plan || !out) return fail(DMX_ERR_INVALID, "NULL argument");
+    if (!plan->p.finalized) return fail(DMX_ERR_STATE, "plan not finalized");
+    if (batch < 0) return fail(DMX_ERR_INVALID, "negative batch");
+    if (plan->p.n_params > 0 && !plan->p.rots.empty() && !d_params && batch > 0) return fail(DMX_ERR_INVALID, "d_params is NULL but the circuit has parameters");
+    return DMX_OK;
+}
+
+static int energy_impl(dmx_plan* plan, int64_t batch, const double* d_params, const uint8_t* d_variants, double* d_energy,
+                       void* d_workspace, size_t workspace_bytes, cudaStream_t st) {
+    Plan& p = plan->p;
+    if (p.term_idx.empty()) return fail(DMX_ERR_STATE, "no Hamiltonian set");
+    DevPlan* d;
+    int rc = ensure_device(p, &d);
+    if (rc) return rc;
+    if (batch == 0) return DMX_OK;
+    if (p.path == 1) return run_segment(p, d, batch, d_params, d_variants, d_energy, st);
+    if (p.path == 0) return run_tile_single(p, d, batch, d_params, d_variants, d_energy, OUT_ENERGY, nullptr, nullptr, st);
+    const size_t sb = (size_t)p.info.state_bytes;
+    long long chunk = (long long)(workspace_bytes / sb);
+    if (!d_workspace || chunk < 1) return fail(DMX_ERR_INVALID, "workspace too small: need dmx_workspace_bytes()");
+    for (long long off = 0; off < batch; off += chunk) {
+        long long cur = std::min<long long>(chunk, batch - off);
+        rc = run_streaming(p, d, cur, off, d_params, d_variants, (double*)d_workspace, st);
+        if (rc) return rc;
+        int threads = 128;
+        long long warps = cur;
+        int grid = (int)((warps * 32 + threads - 1) / threads);
+        dmx_energy_kernel<<<grid, threads, 0, st>>>((const double*)d_workspace, p.n, cur, d->term_idx, d->term_coef, (int)p.term_idx.size(), d_energy, off);
+        ++g_launches;
+        CUDA_TRY(cudaGetLastError());
+    }
+    return DMX_OK;
+}
+
+int dmx_energy_batch(dmx_plan* plan, int64_t batch, const double* d_params, const uint8_t* d_variants, double* d_energy,
+                     void* d_workspace, size_t workspace_bytes, void* stream) {
+    int rc = check_exec(plan, batch, d_params, d_energy);
+    if (rc) return rc;
+    return energy_impl(plan, batch, d_params, d_variants, d_energy, d_workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+int dmx_pauli_batch(dmx_plan* plan, int64_t batch, const double* d_params, const uint8_t* d_variants, double* d_pauli,
+                    void* d_workspace, size_t workspace_bytes, void* stream) {
+    (void)d_workspace; (void)workspace_bytes;
+    int rc = check_exec(plan, batch, d_params, d_pauli);
+    if (rc) return rc;
+    Plan& p = plan->p;
+    DevPlan* d;
+    rc = ensure_device(p, &d);
+    if (rc) return rc;
+    if (batch == 0) return DMX_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (p.n <= 7) return run_tile_single(p, d, batch, d_params, d_variants, d_pauli, OUT_PAULI, nullptr, nullptr, st);
+    // streaming: the output buffer is the state buffer
+    return run_streaming(p, d, batch, 0, d_params, d_variants, d_pauli, st);
+}
+
+int dmx_density_batch(dmx_plan* plan, int64_t batch, const double* d_params, const uint8_t* d_variants, double* d_rho,
+                      void* d_workspace, size_t workspace_bytes, void* stream) {
+    int rc = check_exec(plan, batch, d_params, d_rho);
+    if (rc) return rc;
+    Plan& p = plan->p;
+    const size_t need = (size_t)p.info.state_bytes * (size_t)batch;
+    if (batch > 0 && (!d_workspace || workspace_bytes < need)) return fail(DMX_ERR_INVALID, "density output needs batch * 8 * 4^n bytes of workspace");
+    rc = dmx_pauli_batch(plan, batch, d_params, d_variants, (double*)d_workspace, nullptr, 0, stream);
+    if (rc || batch == 0) return rc;
+    long long total = (long long)batch << (2 * p.n);
+    int threads = 256;
+    long long grid = (total + threads - 1) / threads;
+    dmx_pauli_to_rho<<<(unsigned)grid, threads, 0, (cudaStream_t)stream>>>((const double*)d_workspace, p.n, batch, (double2*)d_rho);
+    ++g_launches;
+    CUDA_TRY(cudaGetLastError());
+    return DMX_OK;
+}
+
+int dmx_diag_batch(dmx_plan* plan, int64_t batch, const double* d_params, const uint8_t* d_variants, double* d_diag, int renormalise,
+                   void* d_workspace, size_t workspace_bytes, void* stream) {
+    int rc = check_exec(plan, batch, d_params, d_diag);
+    if (rc) return rc;
+    Plan& p = plan->p;
+    const size_t need = (size_t)p.info.state_bytes * (size_t)batch;
+    if (batch > 0 && (!d_workspace || workspace_bytes < need)) return fail(DMX_ERR_INVALID, "diag output needs batch * 8 * 4^n bytes of workspace");
+    rc = dmx_pauli_batch(plan, batch, d_params, d_variants, (double*)d_workspace, nullptr, 0, stream);
+    if (rc || batch == 0) return rc;
+    dmx_pauli_to_diag<<<(unsigned)batch, 256, 0, (cudaStream_t)stream>>>((const double*)d_workspace, p.n, batch, d_diag, renormalise);
+    ++g_launches;
+    CUDA_TRY(cudaGetLastError());
+    return DMX_OK;
+}
+
+int dmx_qp_reduce(const double* d_values, const double* d_weights, const int32_t* d_counts, int64_t batch, double* d_out3, void* stream) {
+    if (!d_values || !d_weights || !d_out3 || batch < 0) return fail(DMX_ERR_INVALID, "bad arguments");
+    static std::mutex mu;
+    static double* partial[64] = {nullptr};
+    int dev = 0;
+    CUDA_TRY(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64) return fail(DMX_ERR_UNSUPPORTED, "device ordinal too large");
+    {
+        std::lock_guard<std::mutex> lock(mu);
+        if (!partial[dev]) CUDA_TRY(cudaMalloc((void**)&partial[dev], QP_BLOCKS * 3 * sizeof(double)));
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    dmx_qp_reduce_stage1<<<QP_BLOCKS, QP_THREADS, 0, st>>>(d_values, d_weights, d_counts, batch, partial[dev]);
+    dmx_qp_reduce_stage2<<<1, 32, 0, st>>>(partial[dev], d_out3);
+    g_launches += 2;
+    CUDA_TRY(cudaGetLastError());
+    return DMX_OK;
+}
+
+int dmx_energy_batch_host(dmx_plan* plan, int64_t batch, const double* h_params, const uint8_t* h_variants, double* h_energy) {
+    int rc = check_exec(plan, batch, h_params, h_energy);
+    if (rc) return rc;
+    Plan& p = plan->p;
+    DevPlan* d;
+    rc = ensure_device(p, &d);
+    if (rc) return rc;
+    if (batch == 0) return DMX_OK;
+    std::lock_guard<std::mutex> lock(d->mu);
+    if (!d->stream) CUDA_TRY(cudaStreamCreateWithFlags(&d->stream, cudaStreamNonBlocking));
+    auto align = [](size_t v) { return (v + 255) & ~(size_t)255; };
+    const size_t pb = align((size_t)batch * p.n_params * 8), vb = h_variants ? align((size_t)batch * p.n_slots) : 0, eb = align((size_t)batch * 8);
+    size_t ws = 0;
+    if (p.path == 2) ws = (size_t)p.info.state_bytes * (size_t)std::min<int64_t>(batch, 16);
+    const size_t hneed = pb + vb + eb, dneed = hneed + ws;
+    if (d->h_cap < hneed) {
+        if (d->h_stage) CUDA_TRY(cudaFreeHost(d->h_stage));
+        d->h_stage = nullptr; d->h_cap = 0;
+        CUDA_TRY(cudaMallocHost(&d->h_stage, hneed));
+        d->h_cap = hneed;
+    }
+    if (d->d_cap < dneed) {
+        if (d->d_stage) CUDA_TRY(cudaFree(d->d_stage));
+        d->d_stage = nullptr; d->d_cap = 0;
+        CUDA_TRY(cudaMalloc(&d->d_stage, dneed));
+        d->d_cap = dneed;
+    }
+    char* hs = (char*)d->h_stage;
+    char* ds = (char*)d->d_stage;
+    if (pb) std::memcpy(hs, h_params, (size_t)batch * p.n_params * 8);
+    if (vb) std::memcpy(hs + pb, h_variants, (size_t)batch * p.n_slots);
+    if (pb + vb) CUDA_TRY(cudaMemcpyAsync(ds, hs, pb + vb, cudaMemcpyHostToDevice, d->stream));
+    // the mutex is released around nothing: the staging buffers belong to this call until the sync below
+    rc = energy_impl(plan, batch, pb ? (const double*)ds : nullptr, vb ? (const uint8_t*)(ds + pb) : nullptr, (double*)(ds + pb + vb),
+                     ws ? ds + hneed : nullptr, ws, d->stream);
+    if (rc) return rc;
+    CUDA_TRY(cudaMemcpyAsync(hs + pb + vb, ds + pb + vb, (size_t)batch * 8, cudaMemcpyDeviceToHost, d->stream));
+    CUDA_TRY(cudaStreamSynchronize(d->stream));
+    std::memcpy(h_energy, hs + pb + vb, (size_t)batch * 8);
+    return DMX_OK;
+}
+
+int dmx_measure_fp64_peak(double* tflops_out, void* stream) {
+    if (!tflops_out) return fail(DMX_ERR_INVALID, "NULL argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    int dev = 0, sms = 148;
+    CUDA_TRY(cudaGetDevice(&dev));
+    CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    double* out = nullptr;
+    CUDA_TRY(cudaMalloc((void**)&out, 8));
+    const int iters = 1 << 15, threads = 512, grid = sms * 4;
+    cudaEvent_t e0, e1;
+    CUDA_TRY(cudaEventCreate(&e0));
+    CUDA_TRY(cudaEventCreate(&e1));
+    dmx_fp64_fma_kernel<<<grid, threads, 0, st>>>(out, iters);  // warm-up
+    float best = 1e30f;
+    for (int rep = 0; rep < 3; ++rep) {
+        CUDA_TRY(cudaEventRecord(e0, st));
+        dmx_fp64_fma_kernel<<<grid, threads, 0, st>>>(out, iters);
+        CUDA_TRY(cudaEventRecord(e1, st));
+        CUDA_TRY(cudaEventSynchronize(e1));
+        float ms = 0;
+        CUDA_TRY(cudaEventElapsedTime(&ms, e0, e1));
+        best = std::min(best, ms);
+    }
+    g_launches += 4;
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(out);
+    double flops = 2.0 * 8.0 * (double)iters * (double)threads * (double)grid;
+    *tflops_out = flops / (best * 1e-3) / 1e12;
+    return DMX_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,912 @@
+// dmx_lower.cpp — host-only part of libdmx: lowers a circuit of gates / Kraus channels / rotations /
+// QP-variant slots to real Pauli-transfer blocks, fuses gate+channel blocks, and schedules them either as
+//   path 0: one tile pass with the whole state resident in shared memory (n <= 7),
+//   path 1: the segment kernel (n <= 4, all fixed blocks monomial: Clifford gates + Pauli channels),
+//   path 2: streaming tile passes over a state kept in HBM/L2 (n > 7).
+// No CUDA in this file; it is exercised on CPU by tests/test_lowering.py through dmx_plan_dump().
+#include <algorithm>
+#include <cmath>
+#include <complex>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <sstream>
+#include <stdexcept>
+
+#include "dmx_plan.hpp"
+
+namespace dmx {
+
+using cplx = std::complex<double>;
+static const double kTol = 1e-13;
+
+uint32_t pauli_index(int n, uint32_t xmask, uint32_t zmask) {
+    uint32_t idx = 0;
+    for (int b = 0; b < n; ++b) {
+        uint32_t x = (xmask >> b) & 1u, z = (zmask >> b) & 1u;
+        idx |= ((x << 1) | z) << (2 * b);
+    }
+    return idx;
+}
+
+// Pauli matrices by code: 0=I 1=Z 2=X 3=Y
+static void pauli1(int code, cplx out[4]) {
+    static const cplx I(0, 1);
+    switch (code) {
+        case 0: out[0] = 1; out[1] = 0; out[2] = 0; out[3] = 1; break;
+        case 1: out[0] = 1; out[1] = 0; out[2] = 0; out[3] = -1; break;
+        case 2: out[0] = 0; out[1] = 1; out[2] = 1; out[3] = 0; break;
+        default: out[0] = 0; out[1] = -I; out[2] = I; out[3] = 0; break;
+    }
+}
+
+static std::vector<cplx> pauli_matrix(int nq, int code) {
+    if (nq == 1) {
+        std::vector<cplx> m(4);
+        pauli1(code, m.data());
+        return m;
+    }
+    cplx a[4], b[4];
+    pauli1(code >> 2, a);
+    pauli1(code & 3, b);
+    std::vector<cplx> m(16);
+    for (int i0 = 0; i0 < 2; ++i0)
+        for (int i1 = 0; i1 < 2; ++i1)
+            for (int j0 = 0; j0 < 2; ++j0)
+                for (int j1 = 0; j1 < 2; ++j1)
+                    m[(i0 * 2 + i1) * 4 + (j0 * 2 + j1)] = a[i0 * 2 + j0] * b[i1 * 2 + j1];
+    return m;
+}
+
+// R[a][b] = (1/d) sum_k Tr(P_a K_k P_b K_k^dagger), d = 2^nq.  Real for Hermiticity-preserving maps.
+static std::vector<double> ptm_from_kraus(int nq, const std::vector<std::vector<cplx>>& kraus) {
+    const int d = 1 << nq, dim = d * d;
+    std::vector<double> R(dim * dim, 0.0);
+    std::vector<std::vector<cplx>> P(dim);
+    for (int a = 0; a < dim; ++a) P[a] = pauli_matrix(nq, a);
+    std::vector<cplx> KP(d * d), KPK(d * d);
+    for (const auto& K : kraus) {
+        for (int b = 0; b < dim; ++b) {
+            // KP = K * P_b ; KPK = KP * K^dagger
+            for (int i = 0; i < d; ++i)
+                for (int j = 0; j < d; ++j) {
+                    cplx s = 0;
+                    for (int l = 0; l < d; ++l) s += K[i * d + l] * P[b][l * d + j];
+                    KP[i * d + j] = s;
+                }
+            for (int i = 0; i < d; ++i)
+                for (int j = 0; j < d; ++j) {
+                    cplx s = 0;
+                    for (int l = 0; l < d; ++l) s += KP[i * d + l] * std::conj(K[j * d + l]);
+                    KPK[i * d + j] = s;
+                }
+            for (int a = 0; a < dim; ++a) {
+                cplx tr = 0;
+                for (int i = 0; i < d; ++i)
+                    for (int l = 0; l < d; ++l) tr += P[a][i * d + l] * KPK[l * d + i];
+                R[a * dim + b] += tr.real() / d;
+            }
+        }
+    }
+    return R;
+}
+
+static std::vector<double> identity(int dim) {
+    std::vector<double> m(dim * dim, 0.0);
+    for (int i = 0; i < dim; ++i) m[i * dim + i] = 1.0;
+    return m;
+}
+
+static std::vector<double> matmul(const std::vector<double>& a, const std::vector<double>& b, int dim) {
+    std::vector<double> c(dim * dim, 0.0);
+    for (int i = 0; i < dim; ++i)
+        for (int l = 0; l < dim; ++l) {
+            double av = a[i * dim + l];
+            if (av == 0.0) continue;
+            for (int j = 0; j < dim; ++j) c[i * dim + j] += av * b[l * dim + j];
+        }
+    return c;
+}
+
+static std::vector<double> kron4(const std::vector<double>& a, const std::vector<double>& b) {
+    std::vector<double> c(256);
+    for (int a0 = 0; a0 < 4; ++a0)
+        for (int a1 = 0; a1 < 4; ++a1)
+            for (int b0 = 0; b0 < 4; ++b0)
+                for (int b1 = 0; b1 < 4; ++b1)
+                    c[(a0 * 4 + a1) * 16 + (b0 * 4 + b1)] = a[a0 * 4 + b0] * b[a1 * 4 + b1];
+    return c;
+}
+
+// swap the two qubits of a 16x16 PTM
+static std::vector<double> swap_qubits(const std::vector<double>& m) {
+    std::vector<double> c(256);
+    auto sw = [](int i) { return ((i & 3) << 2) | (i >> 2); };
+    for (int i = 0; i < 16; ++i)
+        for (int j = 0; j < 16; ++j) c[sw(i) * 16 + sw(j)] = m[i * 16 + j];
+    return c;
+}
+
+// classify and snap: entries below tolerance become exact zeros (error <= 1e-13 * |r|, far below the
+// 1e-10 parity bar); entries within tolerance of +-1 in monomial matrices become exact.
+static int classify(std::vector<double>& m, int dim) {
+    bool diag = true, mono = true;
+    for (double& v : m)
+        if (std::fabs(v) < kTol) v = 0.0;
+    std::vector<int> colcount(dim, 0);
+    for (int i = 0; i < dim; ++i) {
+        int nz = 0;
+        for (int j = 0; j < dim; ++j)
+            if (m[i * dim + j] != 0.0) {
+                ++nz;
+                ++colcount[j];
+                if (i != j) diag = false;
+            }
+        if (nz != 1) mono = false;
+    }
+    for (int j = 0; j < dim; ++j)
+        if (colcount[j] != 1) mono = false;
+    if (mono)
+        for (double& v : m)
+            if (v != 0.0 && std::fabs(std::fabs(v) - 1.0) < kTol) v = v > 0 ? 1.0 : -1.0;
+    if (diag && mono) {
+        bool ident = true;
+        for (int i = 0; i < dim; ++i)
+            if (m[i * dim + i] != 1.0) ident = false;
+        if (ident) return CLS_IDENT;
+    }
+    if (diag) {
+        // a diagonal with zero entries (not a permutation) is still "diag" for execution purposes
+        return CLS_DIAG;
+    }
+    return mono ? CLS_MONO : CLS_DENSE;
+}
+
+static bool is_diag(const std::vector<double>& m, int dim) {
+    for (int i = 0; i < dim; ++i)
+        for (int j = 0; j < dim; ++j)
+            if (i != j && std::fabs(m[i * dim + j]) >= kTol) return false;
+    return true;
+}
+
+// 16x16 form of block-like matrix `m` (on qubits bq[0..nq)) in the ordering (q0,q1)
+static std::vector<double> embed16(const std::vector<double>& m, int nq, const int* bq, int q0, int q1) {
+    if (nq == 2) {
+        if (bq[0] == q0 && bq[1] == q1) return m;
+        if (bq[0] == q1 && bq[1] == q0) return swap_qubits(m);
+        throw std::runtime_error("embed16: qubit mismatch");
+    }
+    if (bq[0] == q0) return kron4(m, identity(4));
+    if (bq[0] == q1) return kron4(identity(4), m);
+    throw std::runtime_error("embed16: qubit mismatch");
+}
+
+static std::vector<std::vector<cplx>> read_mats(const Plan& p, const dmx_op& op, int count) {
+    const int d = 1 << op.n_qubits, len = 2 * d * d;
+    if (op.mat < 0 || (size_t)op.mat + (size_t)count * len > p.pool.size())
+        throw std::runtime_error("matrix offset out of range");
+    std::vector<std::vector<cplx>> out(count, std::vector<cplx>(d * d));
+    for (int k = 0; k < count; ++k)
+        for (int i = 0; i < d * d; ++i)
+            out[k][i] = cplx(p.pool[op.mat + k * len + 2 * i], p.pool[op.mat + k * len + 2 * i + 1]);
+    return out;
+}
+
+static std::vector<cplx> rotation_matrix(int axis, double theta) {
+    const double c = std::cos(theta / 2), s = std::sin(theta / 2);
+    const cplx I(0, 1);
+    switch (axis) {
+        case 0: return {c, -I * s, -I * s, c};
+        case 1: return {c, -s, s, c};
+        default: return {std::exp(-I * (theta / 2)), 0, 0, std::exp(I * (theta / 2))};
+    }
+}
+
+// ---- canonical (complex-rho) cost model of SURVEY.md §8d, evaluated on the source ops ---------------
+static bool is_exact_permutation(const std::vector<cplx>& m, int d) {
+    for (int i = 0; i < d; ++i) {
+        int ones = 0;
+        for (int j = 0; j < d; ++j) {
+            cplx v = m[i * d + j];
+            if (v == cplx(1, 0)) ++ones;
+            else if (v != cplx(0, 0)) return false;
+        }
+        if (ones != 1) return false;
+    }
+    return true;
+}
+
+static bool is_scaled_pauli(const std::vector<cplx>& m, int nq) {
+    const int d = 1 << nq, dim = d * d;
+    for (int a = 0; a < dim; ++a) {
+        auto P = pauli_matrix(nq, a);
+        cplx ratio = 0;
+        bool ok = true, have = false;
+        for (int i = 0; i < d * d && ok; ++i) {
+            if (std::abs(P[i]) > 0.5) {
+                cplx r = m[i] / P[i];
+                if (!have) { ratio = r; have = true; }
+                else if (std::abs(r - ratio) > 1e-12) ok = false;
+            } else if (std::abs(m[i]) > 1e-12) ok = false;
+        }
+        if (ok) return true;
+    }
+    return false;
+}
+
+static double canonical_flops_of_op(const Plan& p, const dmx_op& op) {
+    const double N = std::pow(4.0, p.n);
+    switch (op.kind) {
+        case DMX_OP_UNITARY: {
+            auto m = read_mats(p, op, 1)[0];
+            if (is_exact_permutation(m, 1 << op.n_qubits)) return 0.0;
+            return (op.n_qubits == 1 ? 28.0 : 56.0) * N;
+        }
+        case DMX_OP_ROTATION: return 28.0 * N;
+        case DMX_OP_KRAUS: {
+            auto ms = read_mats(p, op, op.n_mats);
+            bool pauli = true;
+            for (auto& m : ms) pauli = pauli && is_scaled_pauli(m, op.n_qubits);
+            if (pauli) {
+                if (op.n_qubits == 1) return 6.0 * N;
+                // 2q: depolarizing (uniform weight on the 15 non-identity Paulis) = 6N, product form = 12N
+                std::vector<double> w;
+                for (auto& m : ms) {
+                    double s = 0;
+                    for (auto& v : m) s += std::norm(v);
+                    w.push_back(s / 4.0);
+                }
+                std::sort(w.begin(), w.end());
+                bool uniform = ms.size() >= 16 && std::fabs(w[0] - w[14]) < 1e-15;
+                return (uniform ? 6.0 : 12.0) * N;
+            }
+            return ms.size() * (op.n_qubits == 1 ? 30.0 : 62.0) * N;
+        }
+        case DMX_OP_VARIANT: return 0.0;  // identity correction in the typical variant
+        default: return 0.0;
+    }
+}
+
+// ---- lowering -----------------------------------------------------------------------------------------
+
+static void lower_ops(Plan& p) {
+    p.blocks.clear();
+    const int n = p.n;
+    double canon = 0.0;
+    for (size_t i = 0; i < p.ops.size(); ++i) {
+        const dmx_op& op = p.ops[i];
+        if (op.kind == DMX_OP_MEASURE) continue;
+        if (op.n_qubits != 1 && op.n_qubits != 2) throw std::runtime_error("op acts on neither 1 nor 2 qubits");
+        if (op.q0 < 0 || op.q0 >= n || (op.n_qubits == 2 && (op.q1 < 0 || op.q1 >= n || op.q1 == op.q0)))
+            throw std::runtime_error("qubit index out of range");
+        canon += canonical_flops_of_op(p, op);
+        Block b;
+        b.nq = op.n_qubits;
+        b.q[0] = op.q0;
+        b.q[1] = op.n_qubits == 2 ? op.q1 : op.q0;
+        b.src_op = (int)i;
+        const int dim = b.dim();
+        if (op.flags & DMX_OPF_IF_VARIANT_NONZERO) {
+            if (op.kind != DMX_OP_UNITARY && op.kind != DMX_OP_KRAUS)
+                throw std::runtime_error("only UNITARY/KRAUS ops can be conditional");
+            if (p.blocks.empty() || p.blocks.back().kind != BK_VAR || p.blocks.back().slot != op.slot)
+                throw std::runtime_error("conditional op does not follow the VARIANT op of its slot");
+            Block& v = p.blocks.back();
+            auto R = ptm_from_kraus(op.n_qubits, read_mats(p, op, op.kind == DMX_OP_UNITARY ? 1 : op.n_mats));
+            if (v.nq != b.nq) throw std::runtime_error("conditional op arity differs from its VARIANT op");
+            if (v.nq == 2) R = embed16(R, 2, b.q, v.q[0], v.q[1]);
+            else if (b.q[0] != v.q[0]) throw std::runtime_error("conditional op on a different qubit");
+            v.cond = matmul(R, v.cond, dim);
+            continue;
+        }
+        switch (op.kind) {
+            case DMX_OP_UNITARY:
+                b.kind = BK_FIXED;
+                b.M = ptm_from_kraus(op.n_qubits, read_mats(p, op, 1));
+                break;
+            case DMX_OP_KRAUS:
+                if (op.n_mats < 1) throw std::runtime_error("KRAUS op without matrices");
+                b.kind = BK_FIXED;
+                b.M = ptm_from_kraus(op.n_qubits, read_mats(p, op, op.n_mats));
+                break;
+            case DMX_OP_ROTATION: {
+                if (op.n_qubits != 1) throw std::runtime_error("ROTATION must be a 1-qubit op");
+                if (op.axis < 0 || op.axis > 2) throw std::runtime_error("ROTATION axis must be 0,1,2");
+                if (op.param < 0 || op.param >= p.n_params) throw std::runtime_error("ROTATION param column out of range");
+                b.kind = BK_ROT;
+                auto P0 = ptm_from_kraus(1, {rotation_matrix(op.axis, 0.0)});
+                auto P1 = ptm_from_kraus(1, {rotation_matrix(op.axis, M_PI / 2)});
+                auto P2 = ptm_from_kraus(1, {rotation_matrix(op.axis, M_PI)});
+                b.A.resize(16); b.C.resize(16); b.S.resize(16);
+                for (int e = 0; e < 16; ++e) {
+                    b.A[e] = 0.5 * (P0[e] + P2[e]);
+                    b.C[e] = 0.5 * (P0[e] - P2[e]);
+                    b.S[e] = P1[e] - b.A[e];
+                    // the three are exact 0/+-1 patterns; snap away the 1e-17 dust of cos(pi/2)
+                    for (std::vector<double>* v : {&b.A, &b.C, &b.S})
+                        (*v)[e] = std::fabs((*v)[e]) < kTol ? 0.0 : ((*v)[e] > 0 ? 1.0 : -1.0);
+                }
+                b.param = op.param;
+                b.scale = op.scale;
+                b.offset = op.offset;
+                break;
+            }
+            case DMX_OP_VARIANT: {
+                if (op.slot < 0 || op.slot >= p.n_slots) throw std::runtime_error("VARIANT slot out of range");
+                if (op.n_mats != 16) throw std::runtime_error("VARIANT needs a table of 16 one-qubit matrices");
+                b.kind = BK_VAR;
+                b.slot = op.slot;
+                dmx_op one = op;
+                one.n_qubits = 1;
+                auto mats = read_mats(p, one, 16);
+                b.tab.resize(16 * 16);
+                for (int k = 0; k < 16; ++k) {
+                    auto R = ptm_from_kraus(1, {mats[k]});
+                    for (double& v : R) if (std::fabs(v) < kTol) v = 0.0;
+                    std::copy(R.begin(), R.end(), b.tab.begin() + 16 * k);
+                }
+                b.cond = identity(dim);
+                break;
+            }
+            default: throw std::runtime_error("unknown op kind");
+        }
+        if (b.kind == BK_FIXED) b.cls = classify(b.M, dim);
+        p.blocks.push_back(std::move(b));
+    }
+    p.info.canonical_flops_per_circuit = canon;
+}
+
+// gate+channel fusion: a fixed block is composed into the latest block on its qubits when that block
+// covers them; 1-qubit blocks are absorbed into the 2-qubit block that follows; fixed 1-qubit blocks
+// around a rotation are folded into its A/C/S matrices.
+static void fuse_blocks(Plan& p) {
+    const int n = p.n;
+    std::vector<int> frontier(n, -1);
+    std::vector<Block>& B = p.blocks;
+    for (size_t i = 0; i < B.size(); ++i) {
+        Block& b = B[i];
+        const int dim = b.dim();
+        if (b.kind == BK_FIXED) {
+            if (b.cls == CLS_IDENT) { b.dead = true; continue; }
+            int f0 = frontier[b.q[0]], f1 = b.nq == 2 ? frontier[b.q[1]] : f0;
+            if (f0 >= 0 && f0 == f1) {
+                Block& f = B[f0];
+                bool covers = f.nq == 2 || b.nq == 1;
+                if (covers && f.kind == BK_FIXED) {
+                    if (f.nq == 2) f.M = matmul(embed16(b.M, b.nq, b.q, f.q[0], f.q[1]), f.M, 16);
+                    else f.M = matmul(b.M, f.M, 4);
+                    f.cls = classify(f.M, f.dim());
+                    b.dead = true;
+                    continue;
+                }
+                if (covers && f.kind == BK_ROT && b.nq == 1) {
+                    f.A = matmul(b.M, f.A, 4); f.C = matmul(b.M, f.C, 4); f.S = matmul(b.M, f.S, 4);
+                    b.dead = true;
+                    continue;
+                }
+            }
+            if (b.nq == 2) {
+                // absorb fixed 1-qubit frontier blocks of either qubit
+                std::vector<double> pre = identity(16);
+                bool any = false;
+                for (int s = 0; s < 2; ++s) {
+                    int f = frontier[b.q[s]];
+                    if (f >= 0 && B[f].kind == BK_FIXED && B[f].nq == 1 && !B[f].dead) {
+                        pre = matmul(embed16(B[f].M, 1, B[f].q, b.q[0], b.q[1]), pre, 16);
+                        B[f].dead = true;
+                        any = true;
+                    }
+                }
+                if (any) { b.M = matmul(b.M, pre, 16); b.cls = classify(b.M, 16); }
+            }
+        } else if (b.kind == BK_ROT) {
+            int f = frontier[b.q[0]];
+            if (f >= 0 && B[f].kind == BK_FIXED && B[f].nq == 1 && !B[f].dead) {
+                b.A = matmul(b.A, B[f].M, 4); b.C = matmul(b.C, B[f].M, 4); b.S = matmul(b.S, B[f].M, 4);
+                B[f].dead = true;
+            }
+        }
+        (void)dim;
+        frontier[b.q[0]] = (int)i;
+        if (b.nq == 2) frontier[b.q[1]] = (int)i;
+    }
+    std::vector<Block> live;
+    for (auto& b : B)
+        if (!b.dead && !(b.kind == BK_FIXED && b.cls == CLS_IDENT)) live.push_back(std::move(b));
+    B.swap(live);
+}
+
+static void drop_identities(Plan& p) {
+    std::vector<Block> live;
+    for (auto& b : p.blocks)
+        if (!(b.kind == BK_FIXED && b.cls == CLS_IDENT)) live.push_back(std::move(b));
+    p.blocks.swap(live);
+}
+
+// ---- device op emission -------------------------------------------------------------------------------
+
+static int push_coefs(Plan& p, const std::vector<double>& v) {
+    int off = (int)p.coefs.size();
+    p.coefs.insert(p.coefs.end(), v.begin(), v.end());
+    return off;
+}
+
+// identical tables are stored once (gate+noise blocks repeat many times in ansatz circuits)
+struct CoefCache {
+    std::map<std::vector<double>, int> seen;
+    int get(Plan& p, const std::vector<double>& v) {
+        auto it = seen.find(v);
+        if (it != seen.end()) return it->second;
+        int off = push_coefs(p, v);
+        seen.emplace(v, off);
+        return off;
+    }
+};
+
+static void mono_tables(const std::vector<double>& M, int dim, std::vector<double>& scale, uint64_t& packed) {
+    scale.assign(dim, 0.0);
+    packed = 0;
+    const int bits = dim == 4 ? 2 : 4;
+    for (int a = 0; a < dim; ++a)
+        for (int b = 0; b < dim; ++b)
+            if (M[a * dim + b] != 0.0) {
+                scale[a] = M[a * dim + b];
+                packed |= (uint64_t)b << (bits * a);
+            }
+}
+
+static DevOp emit_block(Plan& p, CoefCache& cc, const Block& b, const std::vector<int>& local_pos, int rot_ord) {
+    DevOp d{};
+    d.p0 = local_pos[b.q[0]];
+    d.p1 = b.nq == 2 ? local_pos[b.q[1]] : 0;
+    const int dim = b.dim();
+    if (b.kind == BK_FIXED) {
+        if (b.cls == CLS_DIAG || b.cls == CLS_IDENT) {
+            std::vector<double> dg(dim);
+            for (int i = 0; i < dim; ++i) dg[i] = b.M[i * dim + i];
+            d.kind = b.nq == 1 ? DK_DIAG1 : DK_DIAG2;
+            d.coef = cc.get(p, dg);
+        } else if (b.cls == CLS_MONO) {
+            std::vector<double> sc;
+            uint64_t packed;
+            mono_tables(b.M, dim, sc, packed);
+            d.kind = b.nq == 1 ? DK_MONO1 : DK_MONO2;
+            d.coef = cc.get(p, sc);
+            d.a0 = (int32_t)(packed & 0xffffffffu);
+            d.a1 = (int32_t)(packed >> 32);
+        } else {
+            d.kind = b.nq == 1 ? DK_MAT1 : DK_MAT2;
+            d.coef = cc.get(p, b.M);
+        }
+    } else if (b.kind == BK_ROT) {
+        std::vector<double> acs;
+        acs.insert(acs.end(), b.A.begin(), b.A.end());
+        acs.insert(acs.end(), b.C.begin(), b.C.end());
+        acs.insert(acs.end(), b.S.begin(), b.S.end());
+        d.kind = DK_ROT1;
+        d.coef = cc.get(p, acs);
+        d.a0 = rot_ord;
+        d.a2 = b.rot_id;
+    } else {
+        d.a0 = b.slot;
+        if (b.nq == 1) {
+            // T[idx] = cond * B_idx, T[0] unused (identity correction is skipped)
+            std::vector<double> T(16 * 16);
+            for (int k = 0; k < 16; ++k) {
+                std::vector<double> Bk(b.tab.begin() + 16 * k, b.tab.begin() + 16 * (k + 1));
+                auto t = matmul(b.cond, Bk, 4);
+                std::copy(t.begin(), t.end(), T.begin() + 16 * k);
+            }
+            d.kind = DK_VAR1;
+            d.coef = cc.get(p, T);
+        } else {
+            d.kind = DK_VAR2;
+            d.coef = cc.get(p, b.tab);
+            std::vector<double> cond = b.cond;
+            int cls = classify(cond, 16);
+            d.a2 = cls;
+            if (cls == CLS_DIAG || cls == CLS_IDENT) {
+                std::vector<double> dg(16);
+                for (int i = 0; i < 16; ++i) dg[i] = cond[i * 16 + i];
+                d.a1 = cc.get(p, dg);
+                d.a2 = CLS_DIAG;
+            } else {
+                d.a1 = cc.get(p, cond);
+                d.a2 = CLS_DENSE;
+            }
+        }
+    }
+    return d;
+}
+
+// flops / smem bytes actually executed per element for one block (tile kernel)
+static double block_flops_per_elem(const Block& b) {
+    if (b.kind == BK_FIXED) {
+        if (b.cls == CLS_DIAG || b.cls == CLS_MONO) return 1.0;
+        return b.nq == 1 ? 7.0 : 31.0;
+    }
+    if (b.kind == BK_ROT) return 7.0 + 8.0;
+    return 0.0;
+}
+
+static void schedule_single_pass(Plan& p) {
+    CoefCache cc;
+    std::vector<int> local_pos(p.n);
+    Pass pass;
+    for (int q = 0; q < p.n; ++q) { pass.tile_q.push_back(q); local_pos[q] = code_pos(p.n, q); }
+    pass.first_op = 0;
+    for (const Block& b : p.blocks) {
+        int ord = -1;
+        if (b.kind == BK_ROT) { ord = (int)pass.rot_ids.size(); pass.rot_ids.push_back(b.rot_id); }
+        p.dev_ops.push_back(emit_block(p, cc, b, local_pos, ord));
+    }
+    pass.n_ops = (int)p.dev_ops.size();
+    p.passes.push_back(pass);
+    p.tile_k = p.n;
+}
+
+// DAG-greedy pass builder for n > tile_k: the two lowest qubits stay resident (128-byte runs in HBM),
+// blocks join the open pass when all their predecessors are scheduled and their qubits still fit.
+static void schedule_streaming(Plan& p) {
+    const int n = p.n, k = std::min(p.opt_tile_qubits, n);
+    p.tile_k = k;
+    CoefCache cc;
+    const size_t nb = p.blocks.size();
+    std::vector<char> done(nb, 0);
+    // per-qubit ordered list of blocks
+    std::vector<std::vector<int>> chain(n);
+    for (size_t i = 0; i < nb; ++i) {
+        chain[p.blocks[i].q[0]].push_back((int)i);
+        if (p.blocks[i].nq == 2) chain[p.blocks[i].q[1]].push_back((int)i);
+    }
+    std::vector<size_t> head(n, 0);
+    size_t remaining = nb;
+    while (remaining > 0) {
+        std::vector<char> in_tile(n, 0);
+        int count = 0;
+        for (int q = n - 1; q >= n - 2 && q >= 0; --q) { in_tile[q] = 1; ++count; }
+        std::vector<int> order;
+        while (true) {
+            // candidates are the heads of the per-qubit chains; take the earliest one that is ready and fits
+            int best = -1;
+            for (int q0 = 0; q0 < n; ++q0) {
+                if (head[q0] >= chain[q0].size()) continue;
+                int i = chain[q0][head[q0]];
+                if (best >= 0 && i >= best) continue;
+                const Block& b = p.blocks[i];
+                bool ready = true;
+                int need = 0;
+                for (int s = 0; s < b.nq; ++s) {
+                    int q = b.q[s];
+                    if (head[q] >= chain[q].size() || chain[q][head[q]] != i) ready = false;
+                    if (!in_tile[q]) ++need;
+                }
+                if (!ready || count + need > k) continue;
+                best = i;
+            }
+            if (best < 0) break;
+            const Block& b = p.blocks[best];
+            for (int s = 0; s < b.nq; ++s) {
+                if (!in_tile[b.q[s]]) { in_tile[b.q[s]] = 1; ++count; }
+                ++head[b.q[s]];
+            }
+            done[best] = 1;
+            --remaining;
+            order.push_back(best);
+        }
+        if (order.empty()) throw std::runtime_error("streaming scheduler made no progress");
+        // fill the tile up to k qubits (highest free qubits first: longer contiguous runs)
+        for (int q = n - 1; q >= 0 && count < k; --q) if (!in_tile[q]) { in_tile[q] = 1; ++count; }
+        Pass pass;
+        std::vector<int> local_pos(n, -1);
+        for (int q = 0; q < n; ++q) if (in_tile[q]) pass.tile_q.push_back(q);
+        for (size_t i = 0; i < pass.tile_q.size(); ++i) local_pos[pass.tile_q[i]] = 2 * ((int)pass.tile_q.size() - 1 - (int)i);
+        pass.first_op = (int)p.dev_ops.size();
+        for (int bi : order) {
+            const Block& b = p.blocks[bi];
+            int ord = -1;
+            if (b.kind == BK_ROT) { ord = (int)pass.rot_ids.size(); pass.rot_ids.push_back(b.rot_id); }
+            p.dev_ops.push_back(emit_block(p, cc, b, local_pos, ord));
+        }
+        pass.n_ops = (int)p.dev_ops.size() - pass.first_op;
+        p.passes.push_back(std::move(pass));
+    }
+}
+
+// ---- segment tables (path 1) --------------------------------------------------------------------------
+
+static const int SEG_N = 4, SEG_E = 256;
+
+struct Mono {  // r_out[j] = w[j] * r_in[src[j]]
+    int src[SEG_E];
+    double w[SEG_E];
+    void reset() { for (int j = 0; j < SEG_E; ++j) { src[j] = j; w[j] = 1.0; } }
+};
+
+static inline int get_code(int idx, int pos) { return (idx >> pos) & 3; }
+static inline int set_code(int idx, int pos, int c) { return (idx & ~(3 << pos)) | (c << pos); }
+
+// compose a monomial/diagonal fixed block onto the running monomial
+static void apply_mono_block(Mono& m, const Block& b) {
+    const int dim = b.dim();
+    const int p0 = code_pos(SEG_N, b.q[0]), p1 = code_pos(SEG_N, b.q[1]);
+    int srcl[16];
+    double wl[16];
+    for (int a = 0; a < dim; ++a) {
+        srcl[a] = a; wl[a] = 0.0;
+        for (int c = 0; c < dim; ++c)
+            if (b.M[a * dim + c] != 0.0) { srcl[a] = c; wl[a] = b.M[a * dim + c]; }
+    }
+    Mono out;
+    for (int j = 0; j < SEG_E; ++j) {
+        int a = b.nq == 1 ? get_code(j, p0) : get_code(j, p0) * 4 + get_code(j, p1);
+        int c = srcl[a];
+        int jin = b.nq == 1 ? set_code(j, p0, c) : set_code(set_code(j, p0, c >> 2), p1, c & 3);
+        out.src[j] = m.src[jin];
+        out.w[j] = wl[a] * m.w[jin];
+    }
+    m = out;
+}
+
+static bool build_segments(Plan& p, std::string& why) {
+    if (p.n > SEG_N) { why = "n > 4"; return false; }
+    if (p.term_idx.empty()) { why = "no Hamiltonian"; return false; }
+    // qubit q of the circuit sits at the same index as in a 4-qubit register whose extra qubits idle
+    p.segs.clear();
+    p.slots.assign(p.n_slots, SlotInfo());
+    std::vector<char> slot_seen(p.n_slots, 0);
+    Mono cur;
+    cur.reset();
+    CoefCache cc;
+    for (const Block& b : p.blocks) {
+        if (b.kind == BK_FIXED) {
+            if (b.cls == CLS_DENSE) { why = "dense fixed block (non-Clifford gate or non-Pauli channel)"; return false; }
+            apply_mono_block(cur, b);
+        } else if (b.kind == BK_VAR) {
+            if (slot_seen[b.slot]) { why = "variant slot used twice"; return false; }
+            slot_seen[b.slot] = 1;
+            SlotInfo& s = p.slots[b.slot];
+            s.nq = b.nq;
+            s.seg = (int)p.segs.size();
+            s.label.resize(SEG_E);
+            // label of INPUT element i = local code of the position it currently occupies
+            const int p0 = code_pos(SEG_N, b.q[0]), p1 = code_pos(SEG_N, b.q[1]);
+            std::vector<int> where(SEG_E, -1);  // input element -> current position (cur.src is position -> input)
+            for (int j = 0; j < SEG_E; ++j) where[cur.src[j]] = j;
+            for (int i = 0; i < SEG_E; ++i) {
+                int j = where[i];
+                if (j < 0) { why = "non-invertible monomial before a variant slot"; return false; }
+                s.label[i] = (uint8_t)(b.nq == 1 ? get_code(j, p0) : get_code(j, p0) * 4 + get_code(j, p1));
+            }
+            if (b.nq == 1) {
+                std::vector<double> dt(16 * 4, 1.0);
+                for (int k = 0; k < 16; ++k) {
+                    std::vector<double> Bk(b.tab.begin() + 16 * k, b.tab.begin() + 16 * (k + 1));
+                    auto t = k == 0 ? identity(4) : matmul(b.cond, Bk, 4);
+                    if (is_diag(t, 4)) {
+                        s.diag_ok[k >> 5] |= 1u << (k & 31);
+                        for (int c = 0; c < 4; ++c) dt[k * 4 + c] = t[c * 4 + c];
+                    }
+                }
+                s.tab_off = cc.get(p, dt);
+            } else {
+                std::vector<double> dt(16 * 4 + 16, 1.0);
+                std::vector<char> ok1(16, 0);
+                for (int k = 0; k < 16; ++k) {
+                    std::vector<double> Bk(b.tab.begin() + 16 * k, b.tab.begin() + 16 * (k + 1));
+                    if (is_diag(Bk, 4)) {
+                        ok1[k] = 1;
+                        for (int c = 0; c < 4; ++c) dt[k * 4 + c] = Bk[c * 4 + c];
+                    }
+                }
+                bool cond_diag = is_diag(b.cond, 16);
+                for (int c = 0; c < 16; ++c) dt[64 + c] = cond_diag ? b.cond[c * 16 + c] : 1.0;
+                for (int k = 0; k < 256; ++k) {
+                    bool ok = k == 0 || (cond_diag && ok1[k >> 4] && ok1[k & 15]);
+                    if (ok) s.diag_ok[k >> 5] |= 1u << (k & 31);
+                }
+                s.tab_off = cc.get(p, dt);
+            }
+        } else {  // BK_ROT: close the segment
+            Segment sg;
+            sg.src0.resize(SEG_E); sg.src1.resize(SEG_E); sg.active.resize(SEG_E);
+            sg.w0.resize(SEG_E); sg.w1.resize(SEG_E);
+            sg.rot_id = b.rot_id;
+            const int p0 = code_pos(SEG_N, b.q[0]);
+            for (int j = 0; j < SEG_E; ++j) {
+                int a = get_code(j, p0);
+                int nA = 0, nC = 0, nS = 0, bA = 0, bC = 0, bS = 0;
+                for (int c = 0; c < 4; ++c) {
+                    if (b.A[a * 4 + c] != 0.0) { ++nA; bA = c; }
+                    if (b.C[a * 4 + c] != 0.0) { ++nC; bC = c; }
+                    if (b.S[a * 4 + c] != 0.0) { ++nS; bS = c; }
+                }
+                if (nA > 1 || nC > 1 || nS > 1 || (nA == 1 && (nC || nS)) || (nC != nS)) {
+                    why = "rotation block is not a 2-sparse row pattern";
+                    return false;
+                }
+                if (nC == 1) {
+                    int j0 = set_code(j, p0, bC), j1 = set_code(j, p0, bS);
+                    sg.active[j] = 1;
+                    sg.src0[j] = (uint8_t)cur.src[j0]; sg.w0[j] = b.C[a * 4 + bC] * cur.w[j0];
+                    sg.src1[j] = (uint8_t)cur.src[j1]; sg.w1[j] = b.S[a * 4 + bS] * cur.w[j1];
+                } else {
+                    int j0 = set_code(j, p0, bA);
+                    sg.active[j] = 0;
+                    sg.src0[j] = (uint8_t)cur.src[j0]; sg.w0[j] = nA ? b.A[a * 4 + bA] * cur.w[j0] : 0.0;
+                    sg.src1[j] = sg.src0[j]; sg.w1[j] = 0.0;
+                }
+            }
+            p.segs.push_back(std::move(sg));
+            cur.reset();
+        }
+    }
+    for (int s = 0; s < p.n_slots; ++s)
+        if (!slot_seen[s]) { p.slots[s].seg = -1; p.slots[s].label.assign(SEG_E, 0); }
+    // energy stage: E = sum_t c_t * w[idx_t] * r_in[src[idx_t]]
+    const int shift = 2 * (SEG_N - p.n);
+    p.e_src.clear(); p.e_w.clear();
+    for (size_t t = 0; t < p.term_idx.size(); ++t) {
+        int j = (int)(p.term_idx[t] << shift);
+        p.e_src.push_back((uint8_t)cur.src[j]);
+        p.e_w.push_back(p.term_coef[t] * cur.w[j]);
+    }
+    p.nseg = (int)p.segs.size();
+    p.coefs.reserve(p.coefs.size());
+    return true;
+}
+
+// ---- top level ------------------------------------------------------------------------------------------
+
+void lower_plan(Plan& p) {
+    if (p.n < 1 || p.n > DMX_MAX_QUBITS) throw std::runtime_error("n_qubits out of range");
+    p.blocks.clear(); p.rots.clear(); p.dev_ops.clear(); p.coefs.clear(); p.passes.clear();
+    p.segs.clear(); p.slots.clear(); p.term_idx.clear(); p.term_coef.clear();
+    std::memset(&p.info, 0, sizeof(p.info));
+    lower_ops(p);
+    if (p.opt_fuse) fuse_blocks(p); else drop_identities(p);
+    int rid = 0;
+    for (Block& b : p.blocks)
+        if (b.kind == BK_ROT) {
+            b.rot_id = rid++;
+            p.rots.push_back(RotInfo{b.param, 0, b.scale, b.offset});
+        }
+    // merge Hamiltonian terms onto engine indices
+    {
+        std::map<uint32_t, double> acc;
+        std::vector<uint32_t> order;
+        for (size_t t = 0; t < p.hc.size(); ++t) {
+            uint32_t idx = pauli_index(p.n, p.hx[t], p.hz[t]);
+            if (!acc.count(idx)) order.push_back(idx);
+            acc[idx] += p.hc[t];
+        }
+        for (uint32_t idx : order) { p.term_idx.push_back(idx); p.term_coef.push_back(acc[idx]); }
+    }
+    if (p.n <= 7) schedule_single_pass(p); else schedule_streaming(p);
+    p.path = p.n <= 7 ? 0 : 2;
+    p.seg_eligible = false;
+    if (p.opt_segments && p.n <= SEG_N) {
+        p.seg_eligible = build_segments(p, p.seg_reason);
+        if (p.seg_eligible) p.path = 1;
+    } else if (p.n <= SEG_N) {
+        p.seg_reason = "disabled by option";
+    }
+    // cost model
+    const double N = std::pow(4.0, p.n);
+    dmx_plan_info& in = p.info;
+    in.n_qubits = p.n; in.n_params = p.n_params; in.n_slots = p.n_slots; in.n_ops_in = (int)p.ops.size();
+    in.n_blocks = (int)p.blocks.size();
+    in.n_segments = p.seg_eligible ? p.nseg : 0;
+    in.n_passes = (int)p.passes.size();
+    in.tile_qubits = p.tile_k;
+    in.path = p.path;
+    in.n_terms = (int)p.term_idx.size();
+    in.state_bytes = (int64_t)(8.0 * N);
+    const double io = 8.0 * p.n_params + (double)p.n_slots + 8.0;
+    if (p.path == 1) {
+        in.flops_per_circuit = (p.nseg * 4.0 + 1.0) * SEG_E + 2.0 * p.e_w.size();
+        in.smem_bytes_per_circuit = p.nseg * SEG_E * (8.0 + 12.0);
+        in.hbm_bytes_per_circuit = io;
+    } else {
+        double fl = 0;
+        for (const Block& b : p.blocks) fl += block_flops_per_elem(b) * N;
+        in.flops_per_circuit = fl + 2.0 * p.term_idx.size();
+        in.smem_bytes_per_circuit = 16.0 * N * p.blocks.size();
+        // streaming: every pass reads and writes the state once, except the first (init in smem, no read)
+        in.hbm_bytes_per_circuit = io + (p.path == 2 ? (2.0 * p.passes.size() - 1.0) * 8.0 * N : 0.0);
+    }
+    in.canonical_flops_per_circuit += 0.0;
+    {
+        // canonical energy epilogue: 8*G*2^n + 2*T*2^n with G distinct x-masks
+        std::map<uint32_t, int> xs;
+        for (uint32_t x : p.hx) xs[x] = 1;
+        in.canonical_flops_per_circuit += (8.0 * xs.size() + 2.0 * p.hc.size()) * std::pow(2.0, p.n);
+        in.canonical_hbm_bytes_per_circuit = io + (p.n > 7 ? 32.0 * N * p.passes.size() : 0.0);
+    }
+    p.finalized = true;
+}
+
+static void dump_vec(std::ostringstream& os, const char* name, const std::vector<double>& v) {
+    os << " " << name << "=";
+    char buf[40];
+    for (size_t i = 0; i < v.size(); ++i) {
+        std::snprintf(buf, sizeof buf, "%.17g", v[i]);
+        os << (i ? "," : "") << buf;
+    }
+}
+
+template <class T>
+static void dump_ints(std::ostringstream& os, const char* name, const std::vector<T>& v) {
+    os << " " << name << "=";
+    for (size_t i = 0; i < v.size(); ++i) os << (i ? "," : "") << (long long)v[i];
+}
+
+std::string dump_plan(const Plan& p) {
+    std::ostringstream os;
+    os << "plan n=" << p.n << " params=" << p.n_params << " slots=" << p.n_slots << " path=" << p.path
+       << " tile_k=" << p.tile_k << " blocks=" << p.blocks.size() << " passes=" << p.passes.size()
+       << " nseg=" << (p.seg_eligible ? p.nseg : 0) << " seg_reason=\"" << p.seg_reason << "\"\n";
+    for (size_t i = 0; i < p.blocks.size(); ++i) {
+        const Block& b = p.blocks[i];
+        os << "block " << i << " kind=" << b.kind << " nq=" << b.nq << " q0=" << b.q[0] << " q1=" << b.q[1]
+           << " cls=" << b.cls;
+        if (b.kind == BK_FIXED) dump_vec(os, "M", b.M);
+        if (b.kind == BK_ROT) {
+            os << " rot=" << b.rot_id << " param=" << b.param;
+            dump_vec(os, "scale", {b.scale}); dump_vec(os, "offset", {b.offset});
+            dump_vec(os, "A", b.A); dump_vec(os, "C", b.C); dump_vec(os, "S", b.S);
+        }
+        if (b.kind == BK_VAR) { os << " slot=" << b.slot; dump_vec(os, "tab", b.tab); dump_vec(os, "cond", b.cond); }
+        os << "\n";
+    }
+    for (size_t i = 0; i < p.passes.size(); ++i) {
+        const Pass& ps = p.passes[i];
+        os << "pass " << i << " first=" << ps.first_op << " nops=" << ps.n_ops;
+        dump_ints(os, "tile", ps.tile_q);
+        dump_ints(os, "rots", ps.rot_ids);
+        os << "\n";
+    }
+    for (size_t i = 0; i < p.dev_ops.size(); ++i) {
+        const DevOp& d = p.dev_ops[i];
+        os << "devop " << i << " kind=" << d.kind << " p0=" << d.p0 << " p1=" << d.p1 << " coef=" << d.coef
+           << " a0=" << d.a0 << " a1=" << d.a1 << " a2=" << d.a2 << "\n";
+    }
+    dump_vec(os, "coefs", p.coefs);
+    os << "\n";
+    {
+        std::vector<long long> ti(p.term_idx.begin(), p.term_idx.end());
+        os << "terms";
+        dump_ints(os, "idx", ti);
+        dump_vec(os, "coef", p.term_coef);
+        os << "\n";
+    }
+    if (p.seg_eligible) {
+        for (int k = 0; k < p.nseg; ++k) {
+            const Segment& s = p.segs[k];
+            os << "seg " << k << " rot=" << s.rot_id;
+            dump_ints(os, "src0", s.src0); dump_ints(os, "src1", s.src1); dump_ints(os, "active", s.active);
+            dump_vec(os, "w0", s.w0); dump_vec(os, "w1", s.w1);
+            os << "\n";
+        }
+        os << "estage";
+        dump_ints(os, "src", p.e_src);
+        dump_vec(os, "w", p.e_w);
+        os << "\n";
+        for (int s = 0; s < p.n_slots; ++s) {
+            const SlotInfo& si = p.slots[s];
+            os << "slot " << s << " nq=" << si.nq << " seg=" << si.seg << " tab=" << si.tab_off;
+            std::vector<long long> ok(si.diag_ok, si.diag_ok + 8);
+            dump_ints(os, "diag_ok", ok);
+            dump_ints(os, "label", si.label);
+            os << "\n";
+        }
+    }
+    for (size_t i = 0; i < p.rots.size(); ++i) {
+        os << "rot " << i << " param=" << p.rots[i].param;
+        dump_vec(os, "scale", {p.rots[i].scale}); dump_vec(os, "offset", {p.rots[i].offset});
+        os << "\n";
+    }
+    return os.str();
+}
+
+}  // namespace dmx

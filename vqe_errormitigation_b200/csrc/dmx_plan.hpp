@@ -1,0 +1,142 @@
+// dmx_plan.hpp — internal plan structures shared by the host-side lowering (dmx_lower.cpp) and the
+// CUDA execution layer (dmx_exec.cu).  Not part of the public ABI (include/dmx.h is).
+//
+// Representation.  The engine does not store rho as a 2^n x 2^n complex matrix.  It stores the
+// Pauli-coefficient vector r[P] = Tr(rho P) over all 4^n Pauli strings: 4^n REAL doubles — exactly the
+// degrees of freedom of a Hermitian rho, i.e. half the bytes of complex128 rho (SURVEY.md App. E.9 notes
+// that every map on the path preserves Hermiticity).  In this basis
+//   * U rho U^dagger and sum_k K rho K^dagger on one/two qubits are real 4x4 / 16x16 matrices acting on
+//     the 2-bit Pauli code(s) of those qubits (the Pauli transfer matrix),
+//   * every Pauli-type channel of the reference (depolarize, bit/phase flip, asymmetric Pauli, two-qubit
+//     depolarizing, product Pauli) is DIAGONAL, every Clifford gate (H, CNOT, X, rx(+-pi/2), rx(pi)) is a
+//     signed permutation, so gate+noise blocks are "monomial" (one non-zero per row),
+//   * Tr(rho H) = sum_t c_t r[P_t] is a gather-dot over the Hamiltonian's terms.
+// Index layout: qubit q owns bits [2(n-1-q)+1 : 2(n-1-q)] = (x,z); code = 2x+z: 0=I 1=Z 2=X 3=Y.
+#pragma once
+#include <cstdint>
+#include <string>
+#include <vector>
+
+#include "../../include/dmx.h"
+
+namespace dmx {
+
+enum BlockKind : int { BK_FIXED = 0, BK_ROT = 1, BK_VAR = 2 };
+enum MatClass : int { CLS_IDENT = 0, CLS_DIAG = 1, CLS_MONO = 2, CLS_DENSE = 3 };
+
+// One lowered micro-op on 1 or 2 qubits.  dim = 4 (1q) or 16 (2q); local index = code(q[0])*4 + code(q[1]).
+struct Block {
+    int kind = BK_FIXED;
+    int nq = 1;
+    int q[2] = {0, 0};
+    int dim() const { return nq == 1 ? 4 : 16; }
+    // FIXED: M (dim*dim row-major).  ROT: M(theta) = A + cos(theta) C + sin(theta) S.
+    std::vector<double> M, A, C, S;
+    int cls = CLS_DENSE;
+    // ROT
+    int param = -1;
+    double scale = 0.0, offset = 0.0;
+    int rot_id = -1;
+    // VAR: slot, tab = 16 one-qubit PTMs (16*16 doubles) of the pure basis ops, cond = PTM (dim*dim) of the
+    // ops applied only when idx != 0 (identity when there are none).
+    int slot = -1;
+    std::vector<double> tab, cond;
+    int cond_cls = CLS_IDENT;
+    bool dead = false;
+    int src_op = -1;  // index of the first source op (for diagnostics)
+};
+
+// ---- device-facing tables -------------------------------------------------------------------------
+
+enum DevKind : int32_t {
+    DK_DIAG1 = 0, DK_MONO1 = 1, DK_MAT1 = 2, DK_ROT1 = 3,
+    DK_DIAG2 = 4, DK_MONO2 = 5, DK_MAT2 = 6,
+    DK_VAR1 = 7, DK_VAR2 = 8
+};
+
+struct DevOp {        // 32 bytes, read through the constant/L1 path by every thread
+    int32_t kind;
+    int32_t p0, p1;   // tile-local bit position of the code of q0 / q1 (p1 unused for 1q)
+    int32_t coef;     // offset into the coefficient table (doubles)
+    int32_t a0;       // MONO1/2: packed source codes (low word); ROT1: rot ordinal in pass; VAR: slot
+    int32_t a1;       // MONO2: packed source codes (high word); VAR: offset of cond coefficients
+    int32_t a2;       // VAR: cond class (MatClass); ROT1: rot_id (global)
+    int32_t a3;       // reserved
+};
+
+struct RotInfo {      // per global rotation id
+    int32_t param;
+    int32_t pad;
+    double scale, offset;
+};
+
+struct Pass {         // one sweep over the state with `tile_q` resident
+    std::vector<int> tile_q;          // resident qubits, ascending qubit index
+    int first_op = 0, n_ops = 0;      // range in Plan::dev_ops
+    std::vector<int> rot_ids;         // rotations evaluated in this pass (ordinal = position)
+};
+
+// Segment kernel tables (n padded to 4 qubits: 256 elements).
+struct Segment {
+    std::vector<uint8_t> src0, src1, active;  // 256 each
+    std::vector<double> w0, w1;               // 256 each
+    int rot_id = -1;                          // -1: pure monomial (no local op)
+};
+
+struct SlotInfo {
+    int nq = 1;
+    int seg = 0;                  // segment whose INPUT index space the labels refer to (n_segments = energy stage)
+    std::vector<uint8_t> label;   // 256: local code (1q) or code0*4+code1 (2q) per input element
+    int tab_off = 0;              // coefficient offset: 1q -> dtab[16][4] (diag of T[idx]); 2q -> d1[16][4] then dcond[16]
+    uint32_t diag_ok[8] = {0, 0, 0, 0, 0, 0, 0, 0};  // bit idx set if T[idx] is diagonal (256 bits)
+};
+
+struct Plan {
+    // inputs
+    int n = 0, n_params = 0, n_slots = 0;
+    std::vector<dmx_op> ops;
+    std::vector<double> pool;
+    std::vector<uint32_t> hx, hz;
+    std::vector<double> hc;
+    int opt_fuse = 1, opt_segments = 1, opt_tile_qubits = 7;
+    bool finalized = false;
+
+    // lowered program
+    std::vector<Block> blocks;
+    std::vector<RotInfo> rots;
+    std::vector<DevOp> dev_ops;
+    std::vector<double> coefs;
+    std::vector<Pass> passes;
+    int path = 0;           // 0 tile (single pass, state in smem), 1 segment, 2 streaming
+    int tile_k = 0;
+    // energy terms in the engine's index space
+    std::vector<uint32_t> term_idx;
+    std::vector<double> term_coef;
+    // segment path
+    int nseg = 0;
+    std::vector<Segment> segs;
+    std::vector<uint8_t> e_src;   // energy stage: E = sum_t e_w[t] * r[e_src[t]]
+    std::vector<double> e_w;
+    std::vector<SlotInfo> slots;
+    bool seg_eligible = false;
+    std::string seg_reason;
+
+    dmx_plan_info info{};
+
+    // device mirror (owned by dmx_exec.cu)
+    void* dev = nullptr;
+};
+
+// host-only lowering: ops -> blocks -> dev_ops/passes (+ segment tables).  Throws std::runtime_error.
+void lower_plan(Plan& p);
+std::string dump_plan(const Plan& p);
+
+// helpers shared with exec
+inline int code_pos(int n, int q) { return 2 * (n - 1 - q); }
+uint32_t pauli_index(int n, uint32_t xmask, uint32_t zmask);
+
+}  // namespace dmx
+
+struct dmx_plan {
+    dmx::Plan p;
+};
