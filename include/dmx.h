@@ -53,7 +53,8 @@ typedef enum dmx_op_kind {
     DMX_OP_KRAUS = 2,
     /* U = exp(-i theta sigma_axis / 2), theta = scale * params[b, param] + offset: the resolved form of
      * cirq.rx/ry/rz(2*sign*alpha_k) (src/data_containers/helper_interfaces/i_wave_function.py:183,
-     * src/processors/processor_quantum.py:63-65).  axis: 0 = X, 1 = Y, 2 = Z. */
+     * src/processors/processor_quantum.py:63-65).  axis: 0 = X, 1 = Y, 2 = Z.  param = -1: constant angle
+     * theta = offset. */
     DMX_OP_ROTATION = 3,
     /* Per-circuit basis operation of quasi-probability error mitigation: circuit b applies
      * B[variants[b, slot]] where B is a table of 16 one-qubit matrices starting at `mat`

@@ -221,6 +221,8 @@ def run_segments(plan, params=None, variants=None):
             th = rot["scale"] * params[rot["param"]] + rot["offset"]
             b = sg["w1"] * r[sg["src1"]]
             r = np.where(sg["active"] == 1, np.cos(th) * a + np.sin(th) * b, a)
+        elif sg["rot"] == -2:
+            r = np.where(sg["active"] == 1, a + sg["w1"] * r[sg["src1"]], a)
         else:
             r = a
     return float(np.dot(plan["e_w"], r[plan["e_src"]]))

@@ -248,3 +248,28 @@ def test_qp_reduce():
         assert abs(out[0] - np.sum(w * v)) < 1e-9 * max(1, B ** 0.5)
         assert abs(out[1] - np.sum((w * v) ** 2)) < 1e-9 * B
         assert out[2] == c.sum()
+
+
+def test_golden_fixture_energies():
+    """Committed golden vectors (tests/golden/h2_noisy_energies.json, made by tools/make_golden_energies.py)."""
+    import json
+    import os
+    from workloads import GOLDEN
+    torch = torch_cuda()
+    with open(os.path.join(GOLDEN, "h2_noisy_energies.json")) as fh:
+        gold = json.load(fh)
+    noises = {"depolarize1e-3+2qdepolarize1e-3": ([O.depolarize(1e-3)], [O.two_qubit_depolarize(1e-3)]),
+              "depolarize1e-3_1q_only": ([O.depolarize(1e-3)], []),
+              "pauli(1e-4,1e-4,6e-4)_1q+2q": ([O.asymmetric_depolarize(1e-4, 1e-4, 6e-4)], [O.two_qubit_pauli_channel(1e-4, 1e-4, 6e-4)]),
+              "bit_flip1e-3_1q_only": ([O.bit_flip(1e-3)], []), "noiseless": ([], [])}
+    alphas = torch.tensor(gold["alphas"], dtype=torch.float64).reshape(-1, 1)
+    for name, (n1, n2) in noises.items():
+        prog = build_program(h2_ops(n1, n2), 4, h2_terms())
+        got = prog.energies(alphas).cpu().numpy()
+        assert np.max(np.abs(got - np.array(gold["energies"][name]))) < TOL, name
+    n1, n2 = [O.bit_flip(1e-3), O.depolarize(1e-3)], [O.two_qubit_depolarize(1e-3)]
+    prog, _ = qp_noisy_variant_program(n1, n2, h2_terms())
+    assert prog.info["path"] == 1
+    rows = np.array([c["identifier"] for c in gold["variant_cases"]], np.uint8)
+    got = prog.energies(None, torch.tensor(rows)).cpu().numpy()
+    assert np.max(np.abs(got - np.array([c["energy"] for c in gold["variant_cases"]]))) < TOL

@@ -309,6 +309,11 @@ class _EigenGate(Gate):
         e = float(np.real(self._exponent))
         base = self._base
         dim = base.shape[0]
+        if e == round(e):
+            # integer power: exact matrix (no 1e-17 dust in CNOT / X / H), times the global phase
+            core = base.copy() if int(round(e)) % 2 else np.eye(dim, dtype=complex)
+            phase = np.exp(1j * np.pi * e * self._global_shift) if self._global_shift else 1.0
+            return phase * core
         # base has eigenvalues +-1: base^e = P+ + e^{i pi e} P-
         p_plus = (np.eye(dim) + base) / 2
         p_minus = (np.eye(dim) - base) / 2

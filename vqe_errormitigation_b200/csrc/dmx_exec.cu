@@ -369,8 +369,8 @@ __global__ void __launch_bounds__(256) dmx_segment_kernel(const SegArgs a) {
         // rotation angles
         for (int i = j; i < CPB * a.nseg; i += 256) {
             int c = i / a.nseg, k = i - c * a.nseg;
-            double sv = 0.0, cv = 1.0;
             int rid = a.seg_rot[k];
+            double sv = rid == -2 ? 1.0 : 0.0, cv = 1.0;   // -2: constant 2-sparse block, weights carry the values
             if (b0 + c < a.batch && rid >= 0) {
                 RotInfo ri = a.rots[rid];
                 sincos(ri.scale * a.params[(b0 + c) * a.n_params + ri.param] + ri.offset, &sv, &cv);
@@ -631,7 +631,8 @@ struct DevPlan {
     cudaStream_t stream = nullptr;
     void* h_stage = nullptr; size_t h_cap = 0;
     void* d_stage = nullptr; size_t d_cap = 0;
-    std::mutex mu;
+    std::mutex mu;       // host-buffer API staging (held for the whole dmx_energy_batch_host call)
+    std::mutex wl_mu;    // worklist (re)allocation only — never held across a launch that may take `mu`
     int sm_count = 148;
 };
 
@@ -855,7 +856,7 @@ static int run_segment(Plan& p, DevPlan* d, long long batch, const double* param
     a.batch = batch; a.seg_pk = d->seg_pk; a.seg_w = d->seg_w; a.seg_rot = d->seg_rot; a.rots = d->rots; a.params = params;
     a.variants = variants; a.slots = d->slots; a.labels = d->labels; a.coefs = d->coefs; a.e_src = d->e_src; a.e_w = d->e_w; a.out = out;
     if (variants) {
-        std::lock_guard<std::mutex> lock(d->mu);
+        std::lock_guard<std::mutex> lock(d->wl_mu);
         if (d->wl_cap < batch) {
             if (d->worklist) CUDA_TRY(cudaFree(d->worklist));
             d->worklist = nullptr;

@@ -312,7 +312,12 @@ static void lower_ops(Plan& p) {
             case DMX_OP_ROTATION: {
                 if (op.n_qubits != 1) throw std::runtime_error("ROTATION must be a 1-qubit op");
                 if (op.axis < 0 || op.axis > 2) throw std::runtime_error("ROTATION axis must be 0,1,2");
-                if (op.param < 0 || op.param >= p.n_params) throw std::runtime_error("ROTATION param column out of range");
+                if (op.param >= p.n_params) throw std::runtime_error("ROTATION param column out of range");
+                if (op.param < 0) {  // constant angle: theta = offset
+                    b.kind = BK_FIXED;
+                    b.M = ptm_from_kraus(1, {rotation_matrix(op.axis, op.offset)});
+                    break;
+                }
                 b.kind = BK_ROT;
                 auto P0 = ptm_from_kraus(1, {rotation_matrix(op.axis, 0.0)});
                 auto P1 = ptm_from_kraus(1, {rotation_matrix(op.axis, M_PI / 2)});
@@ -660,7 +665,35 @@ static bool build_segments(Plan& p, std::string& why) {
     CoefCache cc;
     for (const Block& b : p.blocks) {
         if (b.kind == BK_FIXED) {
-            if (b.cls == CLS_DENSE) { why = "dense fixed block (non-Clifford gate or non-Pauli channel)"; return false; }
+            if (b.cls == CLS_DENSE) {
+                // A fixed block whose rows hold at most two non-zeros (a resolved rz/rx/ry, possibly fused with
+                // Clifford gates and Pauli noise) closes a segment like a rotation with constant coefficients.
+                const int dim = b.dim();
+                const int p0 = code_pos(SEG_N, b.q[0]), p1 = code_pos(SEG_N, b.q[1]);
+                Segment sg;
+                sg.src0.resize(SEG_E); sg.src1.resize(SEG_E); sg.active.resize(SEG_E);
+                sg.w0.resize(SEG_E); sg.w1.resize(SEG_E);
+                sg.rot_id = -2;
+                for (int j = 0; j < SEG_E; ++j) {
+                    int a = b.nq == 1 ? get_code(j, p0) : get_code(j, p0) * 4 + get_code(j, p1);
+                    int cols[2] = {a, a}, nnz = 0;
+                    double vals[2] = {0.0, 0.0};
+                    for (int c = 0; c < dim; ++c)
+                        if (b.M[a * dim + c] != 0.0) {
+                            if (nnz == 2) { why = "dense fixed block (non-Clifford gate or non-Pauli channel)"; return false; }
+                            cols[nnz] = c; vals[nnz] = b.M[a * dim + c]; ++nnz;
+                        }
+                    int jj[2];
+                    for (int t = 0; t < 2; ++t)
+                        jj[t] = b.nq == 1 ? set_code(j, p0, cols[t]) : set_code(set_code(j, p0, cols[t] >> 2), p1, cols[t] & 3);
+                    sg.src0[j] = (uint8_t)cur.src[jj[0]]; sg.w0[j] = vals[0] * cur.w[jj[0]];
+                    sg.src1[j] = (uint8_t)cur.src[jj[1]]; sg.w1[j] = vals[1] * cur.w[jj[1]];
+                    sg.active[j] = nnz == 2;
+                }
+                p.segs.push_back(std::move(sg));
+                cur.reset();
+                continue;
+            }
             apply_mono_block(cur, b);
         } else if (b.kind == BK_VAR) {
             if (slot_seen[b.slot]) { why = "variant slot used twice"; return false; }

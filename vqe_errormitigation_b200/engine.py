@@ -151,6 +151,10 @@ class CircuitProgram:
         self.n_slots = builder.n_slots
         self.qubits = list(qubits) if qubits is not None else list(range(self.n_qubits))
         self.measurements = list(measurements or [])
+        # kept for introspection / tests (same table the C ABI received)
+        self.ops = list(builder.ops)
+        self.pool = builder.pool()
+        self.hamiltonian = hamiltonian
         self._handle = C.c_void_p()
         ops = (DmxOp * max(len(builder.ops), 1))(*builder.ops)
         pool = np.ascontiguousarray(builder.pool(), dtype=np.float64)
@@ -423,13 +427,17 @@ _PROGRAM_CACHE: "OrderedDict[tuple, CircuitProgram]" = OrderedDict()
 _PROGRAM_CACHE_SIZE = 32
 
 
-def program_for_circuit(resolved: cirq.Circuit, qubit_order=None) -> Tuple[CircuitProgram, Optional[np.ndarray]]:
-    """Plan cache used by the DensityMatrixSimulator facade."""
+def program_for_circuit(resolved: cirq.Circuit, qubit_order=None, hamiltonian=None) -> Tuple[CircuitProgram, Optional[np.ndarray]]:
+    """Plan cache used by the DensityMatrixSimulator facade and the single-evaluation QPU calls: resolved
+    circuits that differ only in their rotation angles map to one compiled plan."""
     builder, qubits, measurements, lifted, key = lower_circuit(resolved, qubit_order, lift_numeric_rotations=True)
-    full_key = (tuple(qubits), key)
+    ham_key = None
+    if hamiltonian is not None:
+        ham_key = tuple(np.ascontiguousarray(a).tobytes() for a in hamiltonian)
+    full_key = (tuple(qubits), key, ham_key)
     prog = _PROGRAM_CACHE.get(full_key)
     if prog is None:
-        prog = CircuitProgram(builder, qubits=qubits, measurements=measurements)
+        prog = CircuitProgram(builder, qubits=qubits, measurements=measurements, hamiltonian=hamiltonian)
         _PROGRAM_CACHE[full_key] = prog
         while len(_PROGRAM_CACHE) > _PROGRAM_CACHE_SIZE:
             _PROGRAM_CACHE.popitem(last=False)

@@ -1,0 +1,724 @@
+"""Quasi-probability error mitigation (mirror of ``src/error_mitigation.py``).
+
+Host side: the 16-operation basis set, Pauli-transfer matrices, the quasi-probability (QP) solve, the
+per-gate sampling of correction operations and the assembly of the corrected circuits.  Device side: all
+sampled circuit variants are evaluated as ONE batch — the clean circuit is compiled once with a variant slot
+after every gate (``DMX_OP_VARIANT``) and the ``uint8[B, n_gates]`` identifier table selects the correction
+per circuit (the reference builds and simulates one cirq.Circuit per unique identifier in a
+``multiprocessing.Pool(6)``, error_mitigation.py:416-427).
+"""
+from __future__ import annotations
+
+import itertools as it
+from typing import Any, Callable, Dict, Iterator, List, Optional, Sequence, Tuple, Union
+
+import numpy as np
+
+from . import cirq_compat as cirq
+from . import engine
+from .data_containers.helper_interfaces.i_noise_wrapper import INoiseModel
+from .data_containers.helper_interfaces.i_wave_function import IWaveFunction
+
+MAX_MULTI_PROCESSING_COUNT = 6  # kept for API compatibility; the GPU batch replaces the process pool
+
+_I = np.eye(2, dtype=complex)
+_X = np.array([[0, 1], [1, 0]], dtype=complex)
+_Y = np.array([[0, -1j], [1j, 0]], dtype=complex)
+_Z = np.array([[1, 0], [0, -1]], dtype=complex)
+_PAULI = (_I, _X, _Y, _Z)
+
+
+def _word(*factors: np.ndarray) -> np.ndarray:
+    """Matrix product of the factors, leftmost factor applied last (ordinary operator product)."""
+    out = np.eye(2, dtype=complex)
+    for f in factors:
+        out = out @ f
+    return out
+
+
+class BasisUnitarySet:
+    """The 16 single-qubit basis operations of Endo/Benjamin/Li-style QP mitigation, generated from the
+    Hadamard H, the phase S = (I - iZ)/sqrt(2) and the projector pi_z = (I + Z)/2
+    (reference error_mitigation.py:18-136; order of get_basis_unitary_set is part of the identifier format)."""
+
+    @staticmethod
+    def _h_unitary() -> np.ndarray:
+        return cirq.unitary(cirq.H)
+
+    @staticmethod
+    def _s_unitary() -> np.ndarray:
+        return (_I - 1j * _Z) / np.sqrt(2)
+
+    @staticmethod
+    def piz_unitary() -> np.ndarray:
+        return 0.5 * (_I + _Z)
+
+    @staticmethod
+    def rz_unitary() -> np.ndarray:
+        s = BasisUnitarySet._s_unitary()
+        return _word(s, s, s)
+
+    @staticmethod
+    def rx_unitary() -> np.ndarray:
+        h = BasisUnitarySet._h_unitary()
+        return _word(h, BasisUnitarySet.rz_unitary(), h)
+
+    @staticmethod
+    def i_unitary() -> np.ndarray:
+        return _I.copy()
+
+    @staticmethod
+    def sx_unitary() -> np.ndarray:
+        rx = BasisUnitarySet.rx_unitary()
+        return _word(rx, rx)
+
+    @staticmethod
+    def sz_unitary() -> np.ndarray:
+        rz = BasisUnitarySet.rz_unitary()
+        return _word(rz, rz)
+
+    @staticmethod
+    def sy_unitary() -> np.ndarray:
+        return _word(BasisUnitarySet.sx_unitary(), BasisUnitarySet.sz_unitary())
+
+    @staticmethod
+    def ry_unitary() -> np.ndarray:
+        rz, rx = BasisUnitarySet.rz_unitary(), BasisUnitarySet.rx_unitary()
+        return _word(rz, rz, rz, rx, rz)
+
+    @staticmethod
+    def ryz_unitary() -> np.ndarray:
+        rz, rx = BasisUnitarySet.rz_unitary(), BasisUnitarySet.rx_unitary()
+        return _word(rx, rz, rz)
+
+    @staticmethod
+    def rzx_unitary() -> np.ndarray:
+        rz, rx = BasisUnitarySet.rz_unitary(), BasisUnitarySet.rx_unitary()
+        return _word(rz, rx, rz)
+
+    @staticmethod
+    def rxy_unitary() -> np.ndarray:
+        rz, rx = BasisUnitarySet.rz_unitary(), BasisUnitarySet.rx_unitary()
+        return _word(rx, rx, rz)
+
+    @staticmethod
+    def pix_unitary() -> np.ndarray:
+        rz, rx, pz = BasisUnitarySet.rz_unitary(), BasisUnitarySet.rx_unitary(), BasisUnitarySet.piz_unitary()
+        return _word(rz, rz, rz, rx, rx, rx, pz, rx, rz)
+
+    @staticmethod
+    def piy_unitary() -> np.ndarray:
+        rx, pz = BasisUnitarySet.rx_unitary(), BasisUnitarySet.piz_unitary()
+        return _word(rx, pz, rx, rx, rx)
+
+    @staticmethod
+    def piyz_unitary() -> np.ndarray:
+        rz, rx, pz = BasisUnitarySet.rz_unitary(), BasisUnitarySet.rx_unitary(), BasisUnitarySet.piz_unitary()
+        return _word(rz, rz, rz, rx, rx, rx, pz, rx, rx, rx, rz)
+
+    @staticmethod
+    def pizx_unitary() -> np.ndarray:
+        rz = BasisUnitarySet.rz_unitary()
+        return _word(BasisUnitarySet.piy_unitary(), rz, rz)
+
+    @staticmethod
+    def pixy_unitary() -> np.ndarray:
+        rx = BasisUnitarySet.rx_unitary()
+        return _word(BasisUnitarySet.piz_unitary(), rx, rx)
+
+    _ORDER = ("i", "sx", "sy", "sz", "rx", "ry", "rz", "ryz", "rzx", "rxy", "pix", "piy", "piz", "piyz", "pizx", "pixy")
+
+    @staticmethod
+    def get_basis_unitary_set() -> Iterator[np.ndarray]:
+        for name in BasisUnitarySet._ORDER:
+            yield getattr(BasisUnitarySet, f"{name}_unitary")()
+
+    @staticmethod
+    def get_basis_set(dim: int) -> Iterator[np.ndarray]:
+        """dim 2: the 16 operations; dim 4: the 256 Kronecker pairs, index 16*a + b."""
+        singles = list(BasisUnitarySet.get_basis_unitary_set())
+        if dim == 2:
+            yield from singles
+        elif dim == 4:
+            for a, b in it.product(singles, repeat=2):
+                yield np.kron(a, b)
+        else:
+            raise NotImplementedError
+
+    @staticmethod
+    def get_t_map(dim: int) -> np.ndarray:
+        t_map = np.array([[1, 1, 1, 1], [0, 0, 1, 0], [0, 0, 0, 1], [1, -1, 0, 0]])
+        if dim == 2:
+            return t_map
+        if dim == 4:
+            return np.kron(t_map, t_map)
+        raise NotImplementedError
+
+    @staticmethod
+    def get_observable_set(dim: int) -> Iterator[np.ndarray]:
+        if dim == 2:
+            yield from (p.copy() for p in _PAULI)
+        elif dim == 4:
+            for a, b in it.product(_PAULI, repeat=2):
+                yield np.kron(a, b)
+        else:
+            raise NotImplementedError
+
+    @staticmethod
+    def get_initial_state_set(gate: np.ndarray) -> Iterator[np.ndarray]:
+        d = gate.shape[0]
+        if gate.shape != (d, d) or d not in (2, 4):
+            raise NotImplementedError
+        for observable in BasisUnitarySet.get_observable_set(dim=d):
+            yield (gate @ observable @ gate.conj().T) / d
+
+    @staticmethod
+    def get_ptm_basis_set(dim: int) -> Iterator[np.ndarray]:
+        singles = [BasisUnitarySet.pauli_transfer_matrix(u) for u in BasisUnitarySet.get_basis_unitary_set()]
+        if dim == 2:
+            yield from singles
+        elif dim == 4:
+            for a, b in it.product(singles, repeat=2):
+                yield np.kron(a, b)
+        else:
+            raise NotImplementedError
+
+    @staticmethod
+    def pauli_transfer_matrix(gate: np.ndarray, noise_wrapper: Callable[[np.ndarray], np.ndarray] = None) -> np.ndarray:
+        """PTM[j, k] = Tr(Q_j . N(U Q_k U^dagger / d)) with Q the Pauli (pair) basis (reference :224-259)."""
+        d = gate.shape[0]
+        observables = list(BasisUnitarySet.get_observable_set(dim=d))
+        states = list(BasisUnitarySet.get_initial_state_set(gate=gate))
+        if noise_wrapper is not None:
+            states = [noise_wrapper(rho) for rho in states]
+        ptm = np.zeros((d * d, d * d), dtype=complex)
+        for j, obs in enumerate(observables):
+            for k, rho in enumerate(states):
+                ptm[j, k] = np.trace(obs @ rho)
+        return ptm
+
+    @staticmethod
+    def get_quasiprobabilities(target: np.ndarray, basis_set: List[np.ndarray]) -> List[float]:
+        """Solve sum_i q_i vec(B_i) = vec(target) (column-major vec), keep real parts (reference :262-274)."""
+        if target.shape != basis_set[0].shape:
+            raise ValueError(f"Target gate \n{target}\n and Basis set operation matrices should have the same shape.")
+        columns = np.array([b.flatten("F") for b in basis_set]).T
+        try:
+            return [float(v.real) for v in np.linalg.solve(columns, target.flatten("F"))]
+        except np.linalg.LinAlgError:
+            print("WARNING: Not able to solve system of linear equations with ill defined basis.")
+            fallback = [0.0] * len(basis_set)
+            fallback[0] = 1
+            return fallback
+
+
+class IBasisGateSingle(cirq.SingleQubitGate):
+    """Arbitrary 2x2 matrix (possibly a projector) applied as rho -> B rho B^dagger (reference :277-287)."""
+
+    def __init__(self, unitary: np.ndarray, exponent=1):
+        self._unitary = np.asarray(unitary)
+        self._exponent = exponent
+
+    def _unitary_(self):
+        return np.linalg.matrix_power(self._unitary, self._exponent)
+
+    def _value_equality_values_(self):
+        return (self._unitary, self._exponent)
+
+    def __str__(self):
+        return "Su.Op."
+
+
+class IBasisGateTwo(cirq.TwoQubitGate):
+    def __init__(self, unitary: np.ndarray, exponent=1):
+        self._unitary = np.asarray(unitary)
+        self._exponent = exponent
+
+    def _unitary_(self):
+        return np.linalg.matrix_power(self._unitary, self._exponent)
+
+    def _value_equality_values_(self):
+        return (self._unitary, self._exponent)
+
+    def __str__(self):
+        return "Su.Op."
+
+
+class QuasiCircuitIdentifier:
+    """One sampled circuit variant: a basis-operation index per gate, the overall sign and the per-gate QP
+    weights (reference :303-346)."""
+
+    def __init__(self, circuit: cirq.Circuit, gate_lookup: Dict[cirq.Gate, List[float]]):
+        self.identifiers_id, self.sign, self.identifiers_weight = QuasiCircuitIdentifier._get_identifiers(circuit, gate_lookup)
+
+    @staticmethod
+    def _get_identifiers(circuit: cirq.Circuit, gate_lookup: Dict[cirq.Gate, List[float]]) -> Tuple[List[int], int, List[float]]:
+        ids, chosen, weights = [], [], []
+        for op in circuit.all_operations():
+            if isinstance(op.gate, cirq.MeasurementGate):
+                weights.append(1)
+                continue
+            qp = gate_lookup[op.gate]
+            basis_id, weight = QuasiCircuitIdentifier._get_identifier(quasi_probabilities=qp)
+            ids.append(basis_id)
+            chosen.append(qp[basis_id])
+            weights.append(weight)
+        return ids, np.sign(np.prod(chosen)), weights
+
+    @staticmethod
+    def _get_identifier(quasi_probabilities: List[float]) -> Tuple[int, float]:
+        c_weight = sum(abs(p) for p in quasi_probabilities)
+        index = np.random.choice(range(len(quasi_probabilities)), p=np.abs(quasi_probabilities) / c_weight)
+        return index, c_weight
+
+    @classmethod
+    def from_arrays(cls, ids: Sequence[int], sign: float, weights: Sequence[float]) -> "QuasiCircuitIdentifier":
+        obj = cls.__new__(cls)
+        obj.identifiers_id, obj.sign, obj.identifiers_weight = list(int(i) for i in ids), sign, list(weights)
+        return obj
+
+    @property
+    def identity(self):
+        return [0] * len(self.identifiers_id)
+
+    def __eq__(self, other):
+        return hash(other) == hash(self)
+
+    def __hash__(self):
+        return hash(tuple(self.identifiers_id))
+
+
+class IErrorMitigationManager:
+    """Manages the family of sampled circuit variants and their (batched) evaluation."""
+
+    def __init__(self, clean_circuit: cirq.Circuit, noise_model: INoiseModel, hamiltonian_objective: Union[np.ndarray, IWaveFunction, None]):
+        self.circuit = clean_circuit
+        self._noise_model = noise_model
+        self._gate_lookup = IErrorMitigationManager.get_qp_lookup(clean_circuit, noise_model.get_effective_gate)
+        self._objective_measure_cost = 1
+        if isinstance(hamiltonian_objective, IWaveFunction):
+            self._hamiltonian_objective = None
+            self._wave_function = hamiltonian_objective
+            _, self._objective_measure_cost = self._wave_function.observable_measurement()
+        else:
+            self._hamiltonian_objective = hamiltonian_objective
+            self._wave_function = None
+        self._error_mitigation = False
+        self._density_representation = True
+        self._meas_reps = 1
+        self._identifier_count = 0
+        # variant table (vectorised form of the reference's dict identifier -> count)
+        self._gate_ops = [op for op in clean_circuit.all_operations() if not isinstance(op.gate, cirq.MeasurementGate)]
+        self._n_measure_ops = sum(1 for op in clean_circuit.all_operations() if isinstance(op.gate, cirq.MeasurementGate))
+        self._rows = np.zeros((0, len(self._gate_ops)), np.uint8)
+        self._counts = np.zeros(0, np.int64)
+        self._dict_cache: Optional[Dict[QuasiCircuitIdentifier, int]] = None
+        self._programs: Dict[Tuple, Any] = {}
+
+    # ---- QP tables ------------------------------------------------------------------------------------------
+    @staticmethod
+    def get_qp_lookup(clean_circuit: cirq.Circuit, noise_wrapper: Callable[[np.ndarray], np.ndarray]) -> Dict[cirq.Gate, List[float]]:
+        """Per distinct gate: N^-1 = PTM_clean . inv(PTM_noisy) decomposed over the basis-op PTMs (reference :499-526)."""
+        lookup: Dict[cirq.Gate, List[float]] = {}
+        basis_cache: Dict[int, List[np.ndarray]] = {}
+        for op in clean_circuit.all_operations():
+            if isinstance(op.gate, cirq.MeasurementGate) or op.gate in lookup:
+                continue
+            clean_gate = cirq.unitary(op)
+            clean_ptm = BasisUnitarySet.pauli_transfer_matrix(clean_gate)
+            noisy_ptm = BasisUnitarySet.pauli_transfer_matrix(clean_gate, noise_wrapper=noise_wrapper)
+            n_inv = clean_ptm.dot(np.linalg.inv(noisy_ptm))
+            d = clean_gate.shape[0]
+            if d not in basis_cache:
+                basis_cache[d] = list(BasisUnitarySet.get_ptm_basis_set(dim=d))
+            lookup[op.gate] = BasisUnitarySet.get_quasiprobabilities(target=n_inv, basis_set=basis_cache[d])
+        return lookup
+
+    # ---- identifier sampling ----------------------------------------------------------------------------------
+    @property
+    def _dict_identifiers(self) -> Dict[QuasiCircuitIdentifier, int]:
+        if self._dict_cache is None:
+            signs, weights = self._signs_and_weights(self._rows)
+            self._dict_cache = {QuasiCircuitIdentifier.from_arrays(row, sg, weights): int(c)
+                                for row, sg, c in zip(self._rows, signs, self._counts)}
+        return self._dict_cache
+
+    def _qp_matrix(self) -> List[np.ndarray]:
+        return [np.asarray(self._gate_lookup[op.gate], dtype=np.float64) for op in self._gate_ops]
+
+    def _signs_and_weights(self, rows: np.ndarray) -> Tuple[np.ndarray, List[float]]:
+        qps = self._qp_matrix()
+        weights = [float(np.sum(np.abs(qp))) for qp in qps] + [1] * self._n_measure_ops
+        if rows.shape[0] == 0:
+            return np.zeros(0), weights
+        negative = np.zeros(rows.shape[0], dtype=np.int64)
+        zero = np.zeros(rows.shape[0], dtype=bool)
+        for s, qp in enumerate(qps):
+            chosen = qp[rows[:, s]]
+            negative += chosen < 0
+            zero |= chosen == 0
+        signs = np.where(zero, 0.0, np.where(negative % 2 == 1, -1.0, 1.0))
+        return signs, weights
+
+    def set_identifier_range(self, count: int):
+        """Draw ``count // objective_cost`` identifiers (reference :484-489) — vectorised per gate over all
+        draws, then deduplicated into (unique rows, counts)."""
+        count = int(count / self._objective_measure_cost)
+        self._identifier_count = count
+        self._dict_cache = None
+        qps = self._qp_matrix()
+        rows = np.zeros((count, len(qps)), np.uint8)
+        for s, qp in enumerate(qps):
+            prob = np.abs(qp) / np.sum(np.abs(qp))
+            rows[:, s] = np.random.choice(len(qp), size=count, p=prob)
+        if count:
+            self._rows, self._counts = np.unique(rows, axis=0, return_counts=True)
+        else:
+            self._rows, self._counts = rows, np.zeros(0, np.int64)
+
+    def add_circuit_identifier(self):
+        ident = QuasiCircuitIdentifier(circuit=self.circuit, gate_lookup=self._gate_lookup)
+        row = np.array(ident.identifiers_id, np.uint8)[None, :]
+        match = np.flatnonzero((self._rows == row).all(axis=1)) if self._rows.shape[0] else []
+        if len(match):
+            self._counts[match[0]] += 1
+        else:
+            self._rows = np.concatenate([self._rows, row])
+            self._counts = np.concatenate([self._counts, [1]])
+        self._dict_cache = None
+
+    def get_identifiers(self) -> Iterator[List[int]]:
+        for row in self._rows:
+            yield [int(v) for v in row]
+
+    # ---- circuits -----------------------------------------------------------------------------------------------
+    @staticmethod
+    def get_updated_circuit(clean_circuit: cirq.Circuit, noise_wrapper: Callable, circuit_identifier: List[int], include_measurements: bool = False) -> cirq.Circuit:
+        """gate, noise, basis op[id] (always), noise again iff id != 0 (reference :528-572)."""
+        result = cirq.Circuit()
+        bases = {2: list(BasisUnitarySet.get_basis_set(2)), 4: None}
+        for i, op in enumerate(clean_circuit.all_operations()):
+            if isinstance(op.gate, cirq.MeasurementGate):
+                if include_measurements:
+                    result.append(op)
+                continue
+            result.append(op)
+            arity = len(op.qubits)
+            if arity == 1:
+                corrector = IBasisGateSingle(unitary=bases[2][circuit_identifier[i]]).on(*op.qubits)
+            elif arity == 2:
+                a, b = divmod(int(circuit_identifier[i]), 16)
+                corrector = IBasisGateTwo(unitary=np.kron(bases[2][a], bases[2][b])).on(*op.qubits)
+            else:
+                raise NotImplementedError("Can only construct single and two qubit operators")
+            noise_ops = noise_wrapper(*op.qubits)
+            result.append(noise_ops)
+            result.append(corrector)
+            if circuit_identifier[i] != 0:
+                result.append(noise_ops)
+        return result
+
+    def _observable_terms(self, n_qubits: int):
+        obj = self._hamiltonian_objective
+        if obj is None:
+            # kron(eye(d/2), Z): Z on the LAST qubit (reference :381)
+            return np.array([0], np.uint32), np.array([1], np.uint32), np.array([1.0])
+        if hasattr(obj, "toarray"):
+            return engine.pauli_decompose(obj.toarray())
+        obj = np.asarray(obj)
+        # ndarray objective: `*` is element-wise, so only diag(H) contributes to the trace (reference :382)
+        return engine.pauli_decompose(np.diag(np.diagonal(obj)))
+
+    def _variant_program(self, tail_ops=(), with_hamiltonian: bool = True, measure_all: bool = False):
+        """Clean circuit + noise + one variant slot per gate (+ optional measurement tail), compiled once."""
+        key = (tuple(tail_ops), with_hamiltonian, measure_all)
+        if key in self._programs:
+            return self._programs[key]
+        qubits = sorted(self.circuit.all_qubits())
+        pos = {q: i for i, q in enumerate(qubits)}
+        basis = list(BasisUnitarySet.get_basis_unitary_set())
+        b = engine.ProgramBuilder(len(qubits))
+        measurements = []
+        slot = 0
+        for op in self.circuit.all_operations():
+            idx = [pos[q] for q in op.qubits]
+            if isinstance(op.gate, cirq.MeasurementGate):
+                measurements.append((op.gate.key, idx, op.gate.invert_mask))
+                continue
+            b.add_unitary(idx, cirq.unitary(op))
+            noise_ops = self._noise_model.get_operators(*op.qubits)
+            for nop in noise_ops:
+                b.add_kraus(idx, cirq.channel(nop))
+            b.add_variant(idx, basis, slot=slot)
+            for nop in noise_ops:
+                b.add_kraus(idx, cirq.channel(nop), if_slot=slot)
+            slot += 1
+        for op in tail_ops:
+            idx = [pos[q] for q in op.qubits]
+            if isinstance(op.gate, cirq.MeasurementGate):
+                measurements.append((op.gate.key, idx, op.gate.invert_mask))
+            elif cirq.has_unitary(op.gate) and getattr(op.gate, "_mixture_", None) is None:
+                b.add_unitary(idx, cirq.unitary(op))
+            else:
+                b.add_kraus(idx, cirq.channel(op))
+        ham = self._observable_terms(len(qubits)) if with_hamiltonian else None
+        prog = engine.CircuitProgram(b, qubits=qubits, measurements=measurements, hamiltonian=ham)
+        self._programs[key] = prog
+        return prog
+
+    # ---- evaluation -----------------------------------------------------------------------------------------------
+    def _measure_rows(self, rows: np.ndarray, counts: np.ndarray) -> np.ndarray:
+        """One measurement value per variant row (un-weighted, un-signed)."""
+        if self._density_representation:
+            prog = self._variant_program()
+            return prog.energies_host(None, rows)
+        reps = self._meas_reps * np.asarray(counts, dtype=np.int64)
+        if self._wave_function is not None:
+            return self._sampled_energy_rows(rows, reps)
+        prog = self._variant_program(with_hamiltonian=False)
+        if not prog.measurements:
+            raise ValueError("Circuit has no measurements to sample.")
+        probs = prog.probabilities(None, rows, renormalise=True)
+        key_pos = [m for m in prog.measurements if m[0] == "M"]
+        if not key_pos:
+            raise KeyError("M")
+        n = prog.n_qubits
+        measured = key_pos[0][1]
+        states = np.arange(probs.shape[1])
+        all_zero = np.ones(probs.shape[1], dtype=bool)
+        for pos in measured:
+            all_zero &= ((states >> (n - 1 - pos)) & 1) == 0
+        p0 = probs[:, all_zero].sum(axis=1)
+        rng = np.random.default_rng(np.random.randint(0, 2 ** 31 - 1))
+        hits = rng.binomial(reps, np.clip(p0, 0.0, 1.0))
+        return 2.0 * hits / reps - 1.0
+
+    def _sampled_energy_rows(self, rows: np.ndarray, reps: np.ndarray) -> np.ndarray:
+        """``measure_observable`` (model_hydrogen.py:114-175) for every variant row: the five measurement
+        circuits are the variant circuit plus basis-change gates (+ their noise); shots are drawn per row."""
+        from .openfermion_compat import jordan_wigner
+        w = self._wave_function
+        hamiltonian = jordan_wigner(w.molecule.get_molecular_hamiltonian())
+        qubits = w.qubits
+        n = len(qubits)
+        to_z = w.pauli_basis_map()
+        noise = self._noise_model.get_operators
+        by_size: Dict[int, list] = {}
+        for term in hamiltonian.terms:
+            by_size.setdefault(len(term), []).append(term)
+        rng = np.random.default_rng(np.random.randint(0, 2 ** 31 - 1))
+
+        def tail(term_list):
+            ops = []
+            for term in term_list:
+                for q, p in term:
+                    ops.append(to_z[p](qubits[q], 1))
+                    ops.extend(noise(qubits[q]))
+            return tuple(ops)
+
+        def parities(tail_ops):
+            prog = self._variant_program(tail_ops=tail_ops, with_hamiltonian=False)
+            probs = prog.probabilities(None, rows, renormalise=True)
+            counts = rng.multinomial(reps, probs / probs.sum(axis=1, keepdims=True))
+            return counts
+
+        states = np.arange(1 << n)
+        bit = lambda q: (states >> (n - 1 - q)) & 1
+        z_counts = parities(tail(by_size.get(1, [])))
+        total = np.full(rows.shape[0], 0.0)
+        expectation = {(): np.ones(rows.shape[0])}
+        for i in range(n):
+            even = bit(i) == 0
+            expectation[((i, "Z"),)] = 2.0 * z_counts[:, even].sum(axis=1) / reps - 1.0
+        for i, j in it.combinations(range(n), 2):
+            even = (bit(i) ^ bit(j)) == 0
+            expectation[((i, "Z"), (j, "Z"))] = 2.0 * z_counts[:, even].sum(axis=1) / reps - 1.0
+        for term in by_size.get(4, []):
+            c = parities(tail([term]))
+            par = np.zeros(1 << n, dtype=np.int64)
+            for q in range(n):
+                par ^= bit(q)
+            expectation[term] = 2.0 * c[:, par == 0].sum(axis=1) / reps - 1.0
+        for term, coefficient in hamiltonian.terms.items():
+            if term in expectation:
+                total = total + complex(coefficient).real * expectation[term]
+        return total
+
+    def process_circuit(self, process_settings: Tuple[QuasiCircuitIdentifier, int]) -> List[float]:
+        """One unique variant, ``count`` occurrences (reference :352-399) — evaluated by the same batched path."""
+        ident, count = process_settings
+        ids = ident.identifiers_id if self._error_mitigation else ident.identity
+        sign = ident.sign if self._error_mitigation else 1
+        weights = ident.identifiers_weight if self._error_mitigation else [1]
+        rows = np.array([ids], np.uint8)
+        value = self._measure_rows(rows, np.array([count]))[0]
+        return [sign * np.prod(weights) * value] * count
+
+    def get_mu_effective(self, error_mitigation: bool, density_representation: bool, meas_reps: int = 1) -> Tuple[np.ndarray, float]:
+        """All unique variants as one GPU batch; returns (per-sample weighted values, their mean) like the
+        reference (:401-452).  When torch.distributed is initialised the unique rows are sharded across ranks
+        and the three partial sums are all-reduced (parallel.sharded_mean)."""
+        self._error_mitigation = error_mitigation
+        self._density_representation = density_representation
+        self._meas_reps = meas_reps
+        if error_mitigation:
+            rows, counts = self._rows, self._counts
+            signs, weights = self._signs_and_weights(rows)
+            scale = float(np.prod(weights))
+        else:
+            rows = np.zeros((1, len(self._gate_ops)), np.uint8)
+            counts = np.array([self._identifier_count * meas_reps], np.int64)
+            signs, scale = np.ones(1), 1.0
+        if rows.shape[0] == 0:
+            return np.zeros(0), float("nan")
+        from . import parallel
+        values = parallel.sharded_rows(lambda r, c: self._measure_rows(r, c), rows, counts)
+        weighted = signs * scale * values
+        results = np.repeat(weighted, counts)
+        return results, float(np.sum(weighted * counts) / np.sum(counts))
+
+    def __str__(self):
+        return str(self._dict_identifiers)
+
+
+def reconstruct_from_basis(quasi_probabilities: List[float], basis_set: List[np.ndarray]) -> np.ndarray:
+    """Inverse of the QP solve: sum_i q_i B_i (reference :578-582)."""
+    if len(quasi_probabilities) != len(basis_set):
+        raise ValueError("Quasi probabilities and basis set should have the same length")
+    return sum(q * b for q, b in zip(quasi_probabilities, basis_set))
+
+
+def get_matrix_difference(a: np.ndarray, b: np.ndarray) -> float:
+    return float(np.linalg.norm(np.asarray(a) - np.asarray(b)))
+
+
+# ---- channels (reference :743-910) -------------------------------------------------------------------------------
+
+
+class TwoQubitDepolarizingChannel(cirq.TwoQubitGate):
+    """(1 - 16p/15) on II plus p/15 on each of the 16 Pauli pairs *including* II (net identity weight 1 - p)."""
+
+    def __init__(self, p: float) -> None:
+        self._p = cirq.validate_probability(p / 15, "p")
+        self._p_i = 1 - cirq.validate_probability(16 * p / 15, "sum_p")
+
+    def _mixture_(self):
+        terms = [(self._p_i, np.kron(_I, _I))]
+        terms += [(self._p, np.kron(a, b)) for a, b in it.product(_PAULI, repeat=2)]
+        return tuple(terms)
+
+    def _has_mixture_(self) -> bool:
+        return True
+
+    def _value_equality_values_(self):
+        return self._p
+
+    @property
+    def p_(self) -> float:
+        return self._p
+
+    def __repr__(self) -> str:
+        return f"cirq.two_qubit_depolarize(p={self._p!r})"
+
+    def __str__(self) -> str:
+        return f"two_qubit_depolarize(p={self._p!r})"
+
+
+class SingleQubitPauliChannel(cirq.SingleQubitGate):
+    def __init__(self, p_x: float, p_y: float, p_z: float) -> None:
+        self._p_i = 1 - p_x - p_y - p_z
+        self._p_x, self._p_y, self._p_z = p_x, p_y, p_z
+
+    def _mixture_(self):
+        return ((self._p_i, _I), (self._p_x, _X), (self._p_y, _Y), (self._p_z, _Z))
+
+    @staticmethod
+    def _has_mixture_() -> bool:
+        return True
+
+    def _value_equality_values_(self):
+        return (self._p_x, self._p_y, self._p_z)
+
+    def __repr__(self) -> str:
+        return f"cirq.single_qubit_asymmetry_depolarize(p_x={self._p_x}, p_y={self._p_y}, p_z={self._p_z})"
+
+    def __str__(self) -> str:
+        return f"single_qubit_asymmetry_depolarize(p_x={self._p_x}, p_y={self._p_y}, p_z={self._p_z})"
+
+
+class TwoQubitPauliChannel(cirq.TwoQubitGate):
+    """Product of two single-qubit Pauli mixtures: 16 Kraus operators (reference :825-845)."""
+
+    def __init__(self, p_x: float, p_y: float, p_z: float) -> None:
+        self._p_i = 1 - p_x - p_y - p_z
+        self._p_x, self._p_y, self._p_z = p_x, p_y, p_z
+
+    def _single_mixture_(self):
+        return ((self._p_i, _I), (self._p_x, _X), (self._p_y, _Y), (self._p_z, _Z))
+
+    def _mixture_(self):
+        single = self._single_mixture_()
+        return tuple((pa * pb, np.kron(a, b)) for (pa, a), (pb, b) in it.product(single, repeat=2))
+
+    @staticmethod
+    def _has_mixture_() -> bool:
+        return True
+
+    def _value_equality_values_(self):
+        return (self._p_x, self._p_y, self._p_z)
+
+    def __repr__(self) -> str:
+        return f"cirq.two_qubit_asymmetry_depolarize(p_x={self._p_x}, p_y={self._p_y}, p_z={self._p_z})"
+
+    def __str__(self) -> str:
+        return f"two_qubit_asymmetry_depolarize(p_x={self._p_x}, p_y={self._p_y}, p_z={self._p_z})"
+
+
+_P0 = np.array([[1, 0], [0, 0]], dtype=complex)
+_P1 = np.array([[0, 0], [0, 1]], dtype=complex)
+
+
+class SingleQubitLeakageChannel(cirq.SingleQubitGate):
+    """"Mixture" (1, |0><0|), (sqrt(1-p), |1><1|) exactly as the reference declares it (:860-871); unused there."""
+
+    def __init__(self, p: float) -> None:
+        self._p = p
+
+    def _mixture_(self):
+        return ((1, _P0), (np.sqrt(1 - self._p), _P1))
+
+    @staticmethod
+    def _has_mixture_() -> bool:
+        return True
+
+    def _value_equality_values_(self):
+        return self._p
+
+    def __str__(self) -> str:
+        return f"single_qubit_leakage(p={self._p})"
+
+    __repr__ = __str__
+
+
+class TwoQubitLeakageChannel(cirq.TwoQubitGate):
+    def __init__(self, p: float) -> None:
+        self._p = p
+
+    def _single_mixture_(self):
+        return ((1, _P0), (np.sqrt(1 - self._p), _P1))
+
+    def _mixture_(self):
+        single = self._single_mixture_()
+        return tuple((pa * pb, np.kron(a, b)) for (pa, a), (pb, b) in it.product(single, repeat=2))
+
+    @staticmethod
+    def _has_mixture_() -> bool:
+        return True
+
+    def _value_equality_values_(self):
+        return self._p
+
+    def __str__(self) -> str:
+        return f"two_qubit_leakage(p={self._p})"
+
+    __repr__ = __str__
