@@ -36,6 +36,9 @@ UNIT = "circuits/s"
 # workloads (built through the repo's public API: HydrogenAnsatz + INoiseWrapper + QPU, or the op builder)
 # ---------------------------------------------------------------------------------------------------------
 
+PLAN_OPTIONS = {}
+
+
 def workload_h2_sweep():
     from vqe_errormitigation_b200 import cirq_compat as cirq
     from vqe_errormitigation_b200.data_containers.helper_interfaces.i_noise_wrapper import INoiseModel, INoiseWrapper
@@ -45,7 +48,7 @@ def workload_h2_sweep():
     w = HydrogenAnsatz()
     noise = INoiseModel([cirq.depolarize(1e-3)], [TwoQubitDepolarizingChannel(1e-3)], "depolarize p=1e-3")
     n_w = INoiseWrapper(w, noise)
-    prog = QPU.compile_energy_program(n_w, n_w.get_noisy_circuit())
+    prog = QPU.compile_energy_program(n_w, n_w.get_noisy_circuit(), **PLAN_OPTIONS)
     B = 65536
 
     def make_inputs(rank: int, seed_offset: int = 0):
@@ -252,7 +255,11 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--opt", action="append", default=[], help="planner option key=value (dmx_plan_set_option)")
     args = ap.parse_args()
+    for kv in args.opt:
+        k, v = kv.split("=")
+        PLAN_OPTIONS[k] = int(v)
     args.warmup = max(args.warmup, 3)
 
     rank = int(os.environ.get("RANK", "0"))

@@ -14,7 +14,7 @@ def _nums(s, typ=float):
 
 
 def parse(dump: str) -> dict:
-    plan = {"blocks": [], "passes": [], "devops": [], "segs": [], "slots": {}, "rots": []}
+    plan = {"blocks": [], "passes": [], "devops": [], "segs": [], "slots": {}, "rots": [], "fsegs": [], "fclasses": [], "flabels": {}}
     for line in dump.splitlines():
         if not line.strip():
             continue
@@ -56,6 +56,16 @@ def parse(dump: str) -> dict:
         elif head == "seg":
             plan["segs"].append({"rot": int(kv["rot"]), "src0": _nums(kv["src0"], int), "src1": _nums(kv["src1"], int),
                                  "active": _nums(kv["active"], int), "w0": _nums(kv["w0"]), "w1": _nums(kv["w1"])})
+        elif head == "fseg":
+            plan["fsegs"].append({"mask": int(kv["mask"]), "shfl": int(kv["shfl"]), "cs": int(kv["cs"]), "w": _nums(kv["w"]).reshape(256, 2)})
+        elif head == "frame":
+            plan["single_class"] = int(kv["single_class"])
+            plan["f_init"] = _nums(kv["init"])
+            plan["f_eweight"] = _nums(kv["eweight"])
+        elif head == "fclass":
+            plan["fclasses"].append({"param": int(kv["param"]), "scale": float(kv["scale"]), "offset": float(kv["offset"])})
+        elif head == "flabel":
+            plan["flabels"][int(pos[0])] = _nums(kv["label"], int)
         elif head == "estage":
             plan["e_src"] = _nums(kv["src"], int)
             plan["e_w"] = _nums(kv["w"])
@@ -226,3 +236,49 @@ def run_segments(plan, params=None, variants=None):
         else:
             r = a
     return float(np.dot(plan["e_w"], r[plan["e_src"]]))
+
+
+def run_frame(plan, params=None, variants=None):
+    """Interpret the fixed-frame tables exactly as dmx_frame_kernel does (thread t = array index t)."""
+    cf = plan["coefs"]
+    t = np.arange(256)
+    r = plan["f_init"].copy()
+    act = []
+    if variants is not None:
+        for s, v in enumerate(variants):
+            v = int(v)
+            if v == 0 or s not in plan["slots"] or plan["slots"][s]["seg"] < 0:
+                continue
+            sl = plan["slots"][s]
+            if not (int(sl["diag_ok"][v >> 5]) >> (v & 31)) & 1:
+                return None
+            act.append((s, v))
+    nseg = plan["nseg"]
+    for k in range(nseg + 1):
+        for s, v in act:
+            sl = plan["slots"][s]
+            if sl["seg"] != k:
+                continue
+            lab = plan["flabels"][s]
+            tb = sl["tab"]
+            if sl["nq"] == 1:
+                f = cf[tb + v * 4 + lab]
+            else:
+                f = cf[tb + (v >> 4) * 4 + (lab >> 2)] * cf[tb + (v & 15) * 4 + (lab & 3)] * cf[tb + 64 + lab]
+            r = r * f
+        if k == nseg:
+            break
+        fs = plan["fsegs"][k]
+        if fs["shfl"]:
+            assert fs["mask"] < 32
+        other = r[t ^ fs["mask"]]
+        if fs["cs"] >= 0:
+            cl = plan["fclasses"][fs["cs"]]
+            th = cl["scale"] * params[cl["param"]] + cl["offset"]
+            cm, sm = np.cos(th), np.sin(th)
+        else:
+            cm = sm = 1.0
+        w0, w1 = fs["w"][:, 0], fs["w"][:, 1]
+        cme = np.where(w1 != 0.0, cm, 1.0)
+        r = cme * (w0 * r) + sm * (w1 * other)
+    return float(np.dot(plan["f_eweight"], r))

@@ -46,6 +46,46 @@ def test_h2_lowering(noise, options):
         assert abs(PI.energy(plan, PI.run_devops(plan, [a])) - want) < TOL
         if plan["nseg"]:
             assert abs(PI.run_segments(plan, [a]) - want) < TOL
+            assert abs(PI.run_frame(plan, [a]) - want) < TOL
+
+
+def test_frame_relabelling_keeps_h2_exchanges_inside_warps():
+    """The 8 rotation axes of the H2 ansatz span a rank-4 GF(2) space, so all partner exchanges are warp shuffles."""
+    prog = build_program(h2_ops([O.depolarize(1e-3)], [O.two_qubit_depolarize(1e-3)]), 4, h2_terms())
+    plan = PI.parse(prog.dump())
+    assert len(plan["fsegs"]) == 8 and all(f["shfl"] == 1 and 0 < f["mask"] < 32 for f in plan["fsegs"])
+    assert plan["single_class"] == 1 and len(plan["fclasses"]) == 1
+
+
+def test_frame_mixed_axes_random_clifford_rotation_circuits():
+    """Random Clifford + Pauli-noise + rx/ry/rz circuits on 2-4 qubits: frame tables (shuffle and smem segments,
+    several rotation classes) reproduce the oracle."""
+    rng = np.random.default_rng(77)
+    cliff1 = [O.H, O.rx(np.pi / 2), O.rx(-np.pi / 2), O.rx(np.pi), O.rz(np.pi / 2), O.X, O.Z]
+    for trial in range(6):
+        n = int(rng.integers(2, 5))
+        ops = []
+        for _ in range(40):
+            kind = rng.integers(0, 5)
+            if kind == 0:
+                ops.append(("u", (int(rng.integers(n)),), cliff1[int(rng.integers(len(cliff1)))]))
+            elif kind == 1:
+                a, b = rng.choice(n, 2, replace=False)
+                ops.append(("u", (int(a), int(b)), O.CNOT))
+                ops.append(("k", (int(a), int(b)), O.two_qubit_depolarize(0.01)))
+            elif kind == 2:
+                ops.append(("k", (int(rng.integers(n)),), O.asymmetric_depolarize(0.01, 0.02, 0.005)))
+            elif kind == 3:
+                ops.append(("r", (int(rng.integers(n)),), (int(rng.integers(3)), f"t{int(rng.integers(3))}", float(rng.choice([1.0, -1.0, 2.0])), float(rng.choice([0.0, 0.0, 0.3])))))
+            else:
+                ops.append(("u", (int(rng.integers(n)),), O.rz(float(rng.normal()))))
+        terms = random_hamiltonian(rng, n, 10)
+        prog = build_program(ops, n, terms)
+        assert prog.info["path"] == 1, prog.dump().splitlines()[0]
+        plan = PI.parse(prog.dump())
+        vals = rng.normal(size=max(prog.n_params, 1))
+        want = O.energy_sparse(O.simulate(n, resolve(ops, prog.param_names, vals)), O.pauli_terms_to_matrix(n, *terms))
+        assert abs(PI.run_frame(plan, vals) - want) < TOL
 
 
 def test_canonical_cost_model_matches_survey():
@@ -83,10 +123,13 @@ def test_variant_lowering_against_golden():
         assert abs(PI.energy(plan, PI.run_blocks(plan, None, v)) - case["energy"]) < TOL
         assert abs(PI.energy(plan, PI.run_devops(plan, None, v)) - case["energy"]) < TOL
         seg = PI.run_segments(plan, None, v)
+        frame = PI.run_frame(plan, None, v)
         if seg is None:
             general += 1        # non-diagonal correction op: kernel defers this row to the tile path
+            assert frame is None
         else:
             assert abs(seg - case["energy"]) < TOL
+            assert abs(frame - case["energy"]) < TOL
     assert general >= 1
 
 

@@ -5,8 +5,9 @@
 //                       pass (DIAG/MONO/MAT/ROT/VAR on 1 or 2 qubits).  n <= 7: whole circuit in one launch
 //                       (several circuits per CTA for small n), fused Tr(rho H) epilogue.  n > 7: one tile of a
 //                       streaming pass (coalesced 16-byte loads/stores of 128-byte runs).
-//   dmx_segment_kernel  n <= 4, Clifford+Pauli-noise circuits: thread-per-Pauli-coefficient; each segment is one
-//                       shared-memory exchange (gather through the fused monomial) + an in-register rotation.
+//   dmx_frame_kernel    n <= 4, Clifford + Pauli-noise (+ rotations) circuits: thread-per-Pauli-coefficient in a
+//                       fixed frame; a segment is r <- cm*w0*r + sm*w1*r[t^mask] with the partner fetched by a
+//                       warp shuffle (or one shared-memory exchange when the mask crosses warps).
 //   dmx_energy_kernel   gather-dot Tr(rho H) on a state in global memory (streaming path).
 //   dmx_pauli_to_rho / dmx_pauli_to_diag   output converters (final_density_matrix, run() probabilities).
 //   dmx_qp_reduce_*     deterministic two-stage reduction of the QP-weighted estimator.
@@ -325,27 +326,31 @@ __global__ void __launch_bounds__(512) dmx_tile_kernel(const TileArgs a) {
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// segment kernel (n <= 4 padded to 4: 256 Pauli coefficients, thread j owns coefficient j of CPB circuits)
+// segment kernel, fixed frame (n <= 4 padded to 4 qubits: 256 Pauli coefficients).
+// Thread t owns one Pauli coefficient of CPB circuits for the whole circuit.  Per segment
+//     r <- cm * w0[t] * r + sm * w1[t] * r[t ^ mask]
+// where the partner value comes from a warp shuffle when the mask stays inside the warp (the GF(2) relabelling
+// in dmx_lower.cpp arranges that for as many segments as possible) or from one shared-memory exchange.
 // ---------------------------------------------------------------------------------------------------------
 struct SlotDev {
     int seg, nq, tab_off, pad;
     unsigned diag_ok[8];
 };
 
-struct SegArgs {
-    int nseg, n_rots, n_params, n_slots, n_terms;
+struct FrameArgs {
+    int nseg, n_params, n_slots, n_classes, n_eterms;
     long long batch;
-    const unsigned* seg_pk;     // [nseg][256]  src0 | src1<<8 | active<<16
-    const double2* seg_w;       // [nseg][256]  (w0, w1)
-    const int* seg_rot;         // [nseg]
-    const RotInfo* rots;
+    const double2* w;           // [nseg][256] (w0, w1)
+    const int4* segs;           // [nseg] (xor_mask, use_shfl, cs_sel, 0)
+    const RotInfo* classes;     // [n_classes]
+    const double* init;         // [256]
+    const double* eweight;      // [256]
+    const int* eslot;           // [256] compact index of the thread's energy term or -1
     const double* params;
     const uint8_t* variants;
     const SlotDev* slots;
     const uint8_t* labels;      // [n_slots][256]
     const double* coefs;
-    const uint8_t* e_src;
-    const double* e_w;
     double* out;
     int* worklist;              // circuits that need the general path
     int* work_count;
@@ -353,33 +358,38 @@ struct SegArgs {
 
 constexpr int SEG_MAXACT = 24;
 
-template <int CPB>
-__global__ void __launch_bounds__(256) dmx_segment_kernel(const SegArgs a) {
-    double* ex = dmx_smem;                         // [2][CPB][256]
-    double* cs = ex + 2 * CPB * 256;               // [CPB][nseg][2]
-    int* nact = reinterpret_cast<int*>(cs + 2 * CPB * a.nseg);   // [CPB] (-1: general path)
-    unsigned* act = reinterpret_cast<unsigned*>(nact + CPB + 1); // [CPB][SEG_MAXACT]  slot<<8 | idx
+// CSMODE 0: no rotation classes (all segments constant), 1: one class, (cos, sin) kept in registers,
+// 2: general, (cos, sin) per (circuit, class) read from shared memory each segment.
+template <int CPB, int CSMODE>
+__global__ void __launch_bounds__(256) dmx_frame_kernel(const FrameArgs a) {
+    const int NC = a.n_classes > 0 ? a.n_classes : 1;
+    double* ex = dmx_smem;                                        // [2][CPB][256]
+    double2* cs = reinterpret_cast<double2*>(ex + 2 * CPB * 256);  // [CPB][NC]
+    double* esm = reinterpret_cast<double*>(cs + CPB * NC);        // [CPB][32*ceil(n_eterms/32)]
+    const int epad = ((a.n_eterms + 31) / 32) * 32;
+    int* nact = reinterpret_cast<int*>(esm + CPB * (epad > 0 ? epad : 32));   // [CPB] (-1: general path)
     int* any_act = nact + CPB;
-    const int j = threadIdx.x, warp = j >> 5, lane = j & 31;
+    unsigned* act = reinterpret_cast<unsigned*>(nact + CPB + 1);   // [CPB][SEG_MAXACT]  slot<<8 | idx
+    const int p = threadIdx.x, warp = p >> 5, lane = p & 31;
     const long long ngroups = (a.batch + CPB - 1) / CPB;
-    const double init = (j & 0xAA) ? 0.0 : 1.0;
+    const double init = a.init[p];
+    const double ew = a.eweight[p];
+    const int eslot = a.eslot[p];
 
     for (long long grp = blockIdx.x; grp < ngroups; grp += gridDim.x) {
         const long long b0 = grp * CPB;
-        // rotation angles
-        for (int i = j; i < CPB * a.nseg; i += 256) {
-            int c = i / a.nseg, k = i - c * a.nseg;
-            int rid = a.seg_rot[k];
-            double sv = rid == -2 ? 1.0 : 0.0, cv = 1.0;   // -2: constant 2-sparse block, weights carry the values
-            if (b0 + c < a.batch && rid >= 0) {
-                RotInfo ri = a.rots[rid];
-                sincos(ri.scale * a.params[(b0 + c) * a.n_params + ri.param] + ri.offset, &sv, &cv);
+        if (CSMODE != 0) {
+            for (int i = p; i < CPB * NC; i += 256) {
+                int c = i / NC, cl = i - c * NC;
+                double sv = 0.0, cv = 1.0;
+                if (b0 + c < a.batch) {
+                    RotInfo ri = a.classes[cl];
+                    sincos(ri.scale * a.params[(b0 + c) * a.n_params + ri.param] + ri.offset, &sv, &cv);
+                }
+                cs[i] = make_double2(cv, sv);
             }
-            cs[2 * i] = cv;
-            cs[2 * i + 1] = sv;
         }
-        // variant rows -> short lists of non-identity slots
-        if (j == 0) *any_act = 0;
+        if (p == 0) *any_act = 0;
         __syncthreads();
         if (a.variants) {
             for (int c = warp; c < CPB; c += 8) {
@@ -411,8 +421,13 @@ __global__ void __launch_bounds__(256) dmx_segment_kernel(const SegArgs a) {
         const bool have_act = a.variants && *any_act;
 
         double r[CPB];
+        double2 csr[CPB];
 #pragma unroll
-        for (int c = 0; c < CPB; ++c) r[c] = init;
+        for (int c = 0; c < CPB; ++c) {
+            r[c] = init;
+            csr[c] = CSMODE == 1 ? cs[c * NC] : make_double2(1.0, 1.0);
+        }
+        int parity = 0;
 
         for (int k = 0; k <= a.nseg; ++k) {
             if (have_act) {
@@ -425,7 +440,7 @@ __global__ void __launch_bounds__(256) dmx_segment_kernel(const SegArgs a) {
                         unsigned idx = ent & 255u;
                         SlotDev sd = a.slots[s];
                         if (sd.seg != k) continue;
-                        unsigned lab = a.labels[s * 256 + j];
+                        unsigned lab = a.labels[s * 256 + p];
                         const double* t = a.coefs + sd.tab_off;
                         double f = sd.nq == 1 ? t[idx * 4 + lab]
                                               : t[(idx >> 4) * 4 + (lab >> 2)] * t[(idx & 15u) * 4 + (lab & 3u)] * t[64 + lab];
@@ -433,37 +448,47 @@ __global__ void __launch_bounds__(256) dmx_segment_kernel(const SegArgs a) {
                     }
                 }
             }
-            double* buf = ex + (k & 1) * CPB * 256;
-#pragma unroll
-            for (int c = 0; c < CPB; ++c) buf[c * 256 + j] = r[c];
-            __syncthreads();
             if (k == a.nseg) break;
-            const unsigned pk = a.seg_pk[k * 256 + j];
-            const double2 w = a.seg_w[k * 256 + j];
-            const unsigned s0 = pk & 255u, s1 = (pk >> 8) & 255u;
-            const bool active = (pk >> 16) & 1u;
+            const int4 sg = a.segs[k];
+            const double2 wk = a.w[k * 256 + p];
+            const bool active = wk.y != 0.0;
+            double other[CPB];
+            if (sg.y) {
+#pragma unroll
+                for (int c = 0; c < CPB; ++c) other[c] = __shfl_xor_sync(0xffffffffu, r[c], sg.x);
+            } else {
+                double* buf = ex + parity * CPB * 256;
+                parity ^= 1;
+#pragma unroll
+                for (int c = 0; c < CPB; ++c) buf[c * 256 + p] = r[c];
+                __syncthreads();
+#pragma unroll
+                for (int c = 0; c < CPB; ++c) other[c] = active ? buf[c * 256 + (p ^ sg.x)] : 0.0;
+            }
 #pragma unroll
             for (int c = 0; c < CPB; ++c) {
-                double av = w.x * buf[c * 256 + s0];
-                if (active) {
-                    double bv = w.y * buf[c * 256 + s1];
-                    double cv = cs[2 * (c * a.nseg + k)], sv = cs[2 * (c * a.nseg + k) + 1];
-                    av = cv * av + sv * bv;
-                }
-                r[c] = av;
+                double2 v;
+                if (sg.z < 0) v = make_double2(1.0, 1.0);
+                else if (CSMODE == 1) v = csr[c];
+                else v = cs[c * NC + sg.z];
+                const double cm = active ? v.x : 1.0;
+                r[c] = cm * (wk.x * r[c]) + v.y * (wk.y * other[c]);
             }
         }
-        // energy stage: E = sum_t e_w[t] * r[e_src[t]]
-        {
-            const double* buf = ex + (a.nseg & 1) * CPB * 256;
-            for (int c = warp; c < CPB; c += 8) {
-                if (b0 + c >= a.batch) continue;
-                double e = 0.0;
-                for (int t = lane; t < a.n_terms; t += 32) e += a.e_w[t] * buf[c * 256 + a.e_src[t]];
+        // energy stage: threads that hold a Hamiltonian term drop weight * r into a compact row, one warp per
+        // circuit sums it in a fixed order
+        if (eslot >= 0) {
 #pragma unroll
-                for (int off = 16; off > 0; off >>= 1) e += __shfl_xor_sync(0xffffffffu, e, off);
-                if (lane == 0 && !(a.variants && nact[c] < 0)) a.out[b0 + c] = e;
-            }
+            for (int c = 0; c < CPB; ++c) esm[c * epad + eslot] = ew * r[c];
+        }
+        __syncthreads();
+        for (int c = warp; c < CPB; c += 8) {
+            if (b0 + c >= a.batch) continue;
+            double e = 0.0;
+            for (int t = lane; t < a.n_eterms; t += 32) e += esm[c * epad + t];
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) e += __shfl_xor_sync(0xffffffffu, e, off);
+            if (lane == 0 && !(a.variants && nact[c] < 0)) a.out[b0 + c] = e;
         }
         __syncthreads();
     }
@@ -617,14 +642,16 @@ struct DevPlan {
     std::vector<int> pass_rot_off;
     uint32_t* term_idx = nullptr;
     double* term_coef = nullptr;
-    // segment
-    unsigned* seg_pk = nullptr;
-    double2* seg_w = nullptr;
-    int* seg_rot = nullptr;
+    // segment (fixed frame)
+    double2* f_w = nullptr;
+    int4* f_segs = nullptr;
+    RotInfo* f_classes = nullptr;
+    double* f_init = nullptr;
+    double* f_eweight = nullptr;
+    int* f_eslot = nullptr;
+    int n_eterms = 0, n_smem_segs = 0;
     SlotDev* slots = nullptr;
     uint8_t* labels = nullptr;
-    uint8_t* e_src = nullptr;
-    double* e_w = nullptr;
     int* worklist = nullptr;           // capacity wl_cap (+ counter at the end)
     long long wl_cap = 0;
     // host-buffer API staging
@@ -676,32 +703,35 @@ static int ensure_device(Plan& p, DevPlan** out) {
     CUDA_TRY(upload(&d->term_idx, p.term_idx));
     CUDA_TRY(upload(&d->term_coef, p.term_coef));
     if (p.seg_eligible) {
-        std::vector<unsigned> pk((size_t)std::max(p.nseg, 1) * 256, 0u);
-        std::vector<double2> w((size_t)std::max(p.nseg, 1) * 256, make_double2(0, 0));
-        std::vector<int> sr(std::max(p.nseg, 1), -1);
+        const int K = std::max(p.nseg, 1);
+        std::vector<double2> w((size_t)K * 256, make_double2(0, 0));
+        std::vector<int4> sg(K, make_int4(0, 1, -2, 0));
         for (int k = 0; k < p.nseg; ++k) {
-            const Segment& s = p.segs[k];
-            sr[k] = s.rot_id;
-            for (int j = 0; j < 256; ++j) {
-                pk[k * 256 + j] = (unsigned)s.src0[j] | ((unsigned)s.src1[j] << 8) | ((unsigned)s.active[j] << 16);
-                w[k * 256 + j] = make_double2(s.w0[j], s.w1[j]);
-            }
+            sg[k] = make_int4(p.fsegs[k].xor_mask, p.fsegs[k].use_shfl, p.fsegs[k].cs_sel, 0);
+            d->n_smem_segs += !p.fsegs[k].use_shfl;
+            for (int j = 0; j < 256; ++j) w[(size_t)k * 256 + j] = make_double2(p.f_w[((size_t)k * 256 + j) * 2], p.f_w[((size_t)k * 256 + j) * 2 + 1]);
         }
-        CUDA_TRY(upload(&d->seg_pk, pk));
-        CUDA_TRY(upload(&d->seg_w, w));
-        CUDA_TRY(upload(&d->seg_rot, sr));
+        CUDA_TRY(upload(&d->f_w, w));
+        CUDA_TRY(upload(&d->f_segs, sg));
+        std::vector<RotInfo> cl = p.f_classes;
+        if (cl.empty()) cl.push_back(RotInfo{0, 0, 0.0, 0.0});
+        CUDA_TRY(upload(&d->f_classes, cl));
+        CUDA_TRY(upload(&d->f_init, p.f_init));
+        CUDA_TRY(upload(&d->f_eweight, p.f_eweight));
+        std::vector<int> eslot(256, -1);
+        int ne = 0;
+        for (int j = 0; j < 256; ++j) if (p.f_eweight[j] != 0.0) eslot[j] = ne++;
+        d->n_eterms = ne;
+        CUDA_TRY(upload(&d->f_eslot, eslot));
         std::vector<SlotDev> sl(std::max(p.n_slots, 1));
-        std::vector<uint8_t> lab((size_t)std::max(p.n_slots, 1) * 256, 0);
-        for (int s = 0; s < p.n_slots; ++s) {
-            sl[s].seg = p.slots[s].seg; sl[s].nq = p.slots[s].nq; sl[s].tab_off = p.slots[s].tab_off; sl[s].pad = 0;
-            std::memcpy(sl[s].diag_ok, p.slots[s].diag_ok, sizeof(sl[s].diag_ok));
-            std::memcpy(&lab[(size_t)s * 256], p.slots[s].label.data(), 256);
+        std::vector<uint8_t> lab = p.f_labels;
+        if (lab.empty()) lab.assign(256, 0);
+        for (int s2 = 0; s2 < p.n_slots; ++s2) {
+            sl[s2].seg = p.slots[s2].seg; sl[s2].nq = p.slots[s2].nq; sl[s2].tab_off = p.slots[s2].tab_off; sl[s2].pad = 0;
+            std::memcpy(sl[s2].diag_ok, p.slots[s2].diag_ok, sizeof(sl[s2].diag_ok));
         }
         CUDA_TRY(upload(&d->slots, sl));
         CUDA_TRY(upload(&d->labels, lab));
-        CUDA_TRY(upload(&d->e_src, p.e_src));
-        CUDA_TRY(upload(&d->e_w, p.e_w));
-        // coefficient table may have grown with slot tables after dev-op emission: p.coefs is final here
     }
     p.dev = d;
     *out = d;
@@ -712,8 +742,8 @@ static void free_device(Plan& p) {
     DevPlan* d = (DevPlan*)p.dev;
     if (!d) return;
     cudaFree(d->ops); cudaFree(d->coefs); cudaFree(d->rots); cudaFree(d->pass_rots); cudaFree(d->term_idx); cudaFree(d->term_coef);
-    cudaFree(d->seg_pk); cudaFree(d->seg_w); cudaFree(d->seg_rot); cudaFree(d->slots); cudaFree(d->labels);
-    cudaFree(d->e_src); cudaFree(d->e_w); cudaFree(d->worklist);
+    cudaFree(d->f_w); cudaFree(d->f_segs); cudaFree(d->f_classes); cudaFree(d->f_init); cudaFree(d->f_eweight); cudaFree(d->f_eslot);
+    cudaFree(d->slots); cudaFree(d->labels); cudaFree(d->worklist);
     if (d->h_stage) cudaFreeHost(d->h_stage);
     if (d->d_stage) cudaFree(d->d_stage);
     if (d->stream) cudaStreamDestroy(d->stream);
@@ -826,23 +856,27 @@ static int run_streaming(Plan& p, DevPlan* d, long long chunk, long long circuit
     return DMX_OK;
 }
 
-template <int CPB>
-static int launch_segment(const SegArgs& a, int sm_count, cudaStream_t st) {
-    size_t smem = (size_t)2 * CPB * 256 * 8 + (size_t)2 * CPB * std::max(a.nseg, 1) * 8 + (CPB + 1) * 4 + (size_t)CPB * SEG_MAXACT * 4 + 16;
-    if (smem > 227 * 1024) return fail(DMX_ERR_UNSUPPORTED, "segment kernel: too many segments for shared memory");
+template <int CPB, int CSMODE>
+static int launch_frame(const FrameArgs& a, int sm_count, cudaStream_t st) {
+    const int NC = a.n_classes > 0 ? a.n_classes : 1;
+    const int epad = std::max(((a.n_eterms + 31) / 32) * 32, 32);
+    size_t smem = (size_t)2 * CPB * 256 * 8 + (size_t)CPB * NC * 16 + (size_t)CPB * epad * 8 + (CPB + 1) * 4 + (size_t)CPB * SEG_MAXACT * 4 + 16;
+    if (smem > 227 * 1024) return fail(DMX_ERR_UNSUPPORTED, "segment kernel: tables do not fit shared memory");
     static std::mutex mu;
     static size_t configured = 0;
     {
         std::lock_guard<std::mutex> lock(mu);
         if (smem > configured) {
-            CUDA_TRY(cudaFuncSetAttribute(dmx_segment_kernel<CPB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max(smem, (size_t)48 * 1024)));
+            CUDA_TRY(cudaFuncSetAttribute(dmx_frame_kernel<CPB, CSMODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max(smem, (size_t)48 * 1024)));
             configured = std::max(smem, (size_t)48 * 1024);
         }
     }
     long long groups = (a.batch + CPB - 1) / CPB;
-    int per_sm = (int)std::max<size_t>(1, std::min<size_t>(8, (227 * 1024) / smem));
+    int per_sm = 0;
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, dmx_frame_kernel<CPB, CSMODE>, 256, smem));
+    per_sm = std::max(per_sm, 1);
     int grid = (int)std::max<long long>(1, std::min<long long>(groups, (long long)sm_count * per_sm));
-    dmx_segment_kernel<CPB><<<grid, 256, smem, st>>>(a);
+    dmx_frame_kernel<CPB, CSMODE><<<grid, 256, smem, st>>>(a);
     ++g_launches;
     CUDA_TRY(cudaGetLastError());
     return DMX_OK;
@@ -851,10 +885,10 @@ static int launch_segment(const SegArgs& a, int sm_count, cudaStream_t st) {
 static int g_seg_cpb = 8;
 
 static int run_segment(Plan& p, DevPlan* d, long long batch, const double* params, const uint8_t* variants, double* out, cudaStream_t st) {
-    SegArgs a{};
-    a.nseg = p.nseg; a.n_rots = (int)p.rots.size(); a.n_params = p.n_params; a.n_slots = p.n_slots; a.n_terms = (int)p.e_w.size();
-    a.batch = batch; a.seg_pk = d->seg_pk; a.seg_w = d->seg_w; a.seg_rot = d->seg_rot; a.rots = d->rots; a.params = params;
-    a.variants = variants; a.slots = d->slots; a.labels = d->labels; a.coefs = d->coefs; a.e_src = d->e_src; a.e_w = d->e_w; a.out = out;
+    FrameArgs a{};
+    a.nseg = p.nseg; a.n_params = p.n_params; a.n_slots = p.n_slots; a.n_classes = (int)p.f_classes.size(); a.n_eterms = d->n_eterms;
+    a.batch = batch; a.w = d->f_w; a.segs = d->f_segs; a.classes = d->f_classes; a.init = d->f_init; a.eweight = d->f_eweight;
+    a.eslot = d->f_eslot; a.params = params; a.variants = variants; a.slots = d->slots; a.labels = d->labels; a.coefs = d->coefs; a.out = out;
     if (variants) {
         std::lock_guard<std::mutex> lock(d->wl_mu);
         if (d->wl_cap < batch) {
@@ -867,12 +901,12 @@ static int run_segment(Plan& p, DevPlan* d, long long batch, const double* param
         a.work_count = d->worklist;
         CUDA_TRY(cudaMemsetAsync(d->worklist, 0, sizeof(int), st));
     }
+    const int mode = p.f_classes.empty() ? 0 : (p.f_single_class ? 1 : 2);
     int rc;
-    switch (g_seg_cpb) {
-        case 2: rc = launch_segment<2>(a, d->sm_count, st); break;
-        case 4: rc = launch_segment<4>(a, d->sm_count, st); break;
-        case 16: rc = launch_segment<16>(a, d->sm_count, st); break;
-        default: rc = launch_segment<8>(a, d->sm_count, st); break;
+    if (g_seg_cpb == 4) {
+        rc = mode == 0 ? launch_frame<4, 0>(a, d->sm_count, st) : mode == 1 ? launch_frame<4, 1>(a, d->sm_count, st) : launch_frame<4, 2>(a, d->sm_count, st);
+    } else {
+        rc = mode == 0 ? launch_frame<8, 0>(a, d->sm_count, st) : mode == 1 ? launch_frame<8, 1>(a, d->sm_count, st) : launch_frame<8, 2>(a, d->sm_count, st);
     }
     if (rc) return rc;
     if (variants) {
@@ -930,7 +964,7 @@ int dmx_plan_set_option(dmx_plan* plan, const char* key, int value) {
         if (value < 4 || value > 7) return fail(DMX_ERR_INVALID, "tile_qubits must be in 4..7");
         plan->p.opt_tile_qubits = value;
     } else if (k == "segment_cpb") {
-        if (value != 2 && value != 4 && value != 8 && value != 16) return fail(DMX_ERR_INVALID, "segment_cpb must be 2, 4, 8 or 16");
+        if (value != 4 && value != 8) return fail(DMX_ERR_INVALID, "segment_cpb must be 4 or 8");
         g_seg_cpb = value;
     } else return fail(DMX_ERR_INVALID, "unknown option: " + k);
     return DMX_OK;

@@ -9,6 +9,7 @@
 #include <complex>
 #include <cstdio>
 #include <cstring>
+#include <functional>
 #include <map>
 #include <sstream>
 #include <stdexcept>
@@ -361,6 +362,16 @@ static void lower_ops(Plan& p) {
     p.info.canonical_flops_per_circuit = canon;
 }
 
+static int max_row_nnz(const std::vector<double>& m, int dim) {
+    int worst = 0;
+    for (int i = 0; i < dim; ++i) {
+        int nz = 0;
+        for (int j = 0; j < dim; ++j) nz += std::fabs(m[i * dim + j]) >= kTol;
+        worst = std::max(worst, nz);
+    }
+    return worst;
+}
+
 // gate+channel fusion: a fixed block is composed into the latest block on its qubits when that block
 // covers them; 1-qubit blocks are absorbed into the 2-qubit block that follows; fixed 1-qubit blocks
 // around a rotation are folded into its A/C/S matrices.
@@ -368,6 +379,15 @@ static void fuse_blocks(Plan& p) {
     const int n = p.n;
     std::vector<int> frontier(n, -1);
     std::vector<Block>& B = p.blocks;
+    // Small registers are candidates for the segment kernel, which needs every block to stay "2-sparse" (at most
+    // two non-zeros per row: Clifford x Pauli-noise x one Pauli rotation).  Fusing two such blocks can produce a
+    // denser matrix (rz . H . rz), so a fusion that would leave the 2-sparse class is skipped there.
+    const bool keep_sparse = p.opt_segments && n <= 4;
+    auto allowed = [&](const std::vector<double>& fused, int dim, const std::vector<double>& x, int dx, const std::vector<double>& y, int dy) {
+        if (!keep_sparse) return true;
+        if (max_row_nnz(x, dx) > 2 || max_row_nnz(y, dy) > 2) return true;  // already dense: nothing to protect
+        return max_row_nnz(fused, dim) <= 2;
+    };
     for (size_t i = 0; i < B.size(); ++i) {
         Block& b = B[i];
         const int dim = b.dim();
@@ -378,13 +398,15 @@ static void fuse_blocks(Plan& p) {
                 Block& f = B[f0];
                 bool covers = f.nq == 2 || b.nq == 1;
                 if (covers && f.kind == BK_FIXED) {
-                    if (f.nq == 2) f.M = matmul(embed16(b.M, b.nq, b.q, f.q[0], f.q[1]), f.M, 16);
-                    else f.M = matmul(b.M, f.M, 4);
-                    f.cls = classify(f.M, f.dim());
-                    b.dead = true;
-                    continue;
+                    std::vector<double> fused = f.nq == 2 ? matmul(embed16(b.M, b.nq, b.q, f.q[0], f.q[1]), f.M, 16) : matmul(b.M, f.M, 4);
+                    if (allowed(fused, f.dim(), f.M, f.dim(), b.M, dim)) {
+                        f.M = fused;
+                        f.cls = classify(f.M, f.dim());
+                        b.dead = true;
+                        continue;
+                    }
                 }
-                if (covers && f.kind == BK_ROT && b.nq == 1) {
+                if (covers && f.kind == BK_ROT && b.nq == 1 && (!keep_sparse || b.cls != CLS_DENSE)) {
                     f.A = matmul(b.M, f.A, 4); f.C = matmul(b.M, f.C, 4); f.S = matmul(b.M, f.S, 4);
                     b.dead = true;
                     continue;
@@ -392,21 +414,20 @@ static void fuse_blocks(Plan& p) {
             }
             if (b.nq == 2) {
                 // absorb fixed 1-qubit frontier blocks of either qubit
-                std::vector<double> pre = identity(16);
-                bool any = false;
                 for (int s = 0; s < 2; ++s) {
                     int f = frontier[b.q[s]];
                     if (f >= 0 && B[f].kind == BK_FIXED && B[f].nq == 1 && !B[f].dead) {
-                        pre = matmul(embed16(B[f].M, 1, B[f].q, b.q[0], b.q[1]), pre, 16);
+                        std::vector<double> fused = matmul(b.M, embed16(B[f].M, 1, B[f].q, b.q[0], b.q[1]), 16);
+                        if (!allowed(fused, 16, b.M, 16, B[f].M, 4)) continue;
+                        b.M = fused;
+                        b.cls = classify(b.M, 16);
                         B[f].dead = true;
-                        any = true;
                     }
                 }
-                if (any) { b.M = matmul(b.M, pre, 16); b.cls = classify(b.M, 16); }
             }
         } else if (b.kind == BK_ROT) {
             int f = frontier[b.q[0]];
-            if (f >= 0 && B[f].kind == BK_FIXED && B[f].nq == 1 && !B[f].dead) {
+            if (f >= 0 && B[f].kind == BK_FIXED && B[f].nq == 1 && !B[f].dead && (!keep_sparse || B[f].cls != CLS_DENSE)) {
                 b.A = matmul(b.A, B[f].M, 4); b.C = matmul(b.C, B[f].M, 4); b.S = matmul(b.S, B[f].M, 4);
                 B[f].dead = true;
             }
@@ -674,21 +695,57 @@ static bool build_segments(Plan& p, std::string& why) {
                 sg.src0.resize(SEG_E); sg.src1.resize(SEG_E); sg.active.resize(SEG_E);
                 sg.w0.resize(SEG_E); sg.w1.resize(SEG_E);
                 sg.rot_id = -2;
+                // Primary column per row.  The block is (monomial) x (one Pauli rotation) x (monomial): rows with one
+                // non-zero ("passive") fix an affine GF(2) map on the local codes; the rows with two non-zeros must be
+                // matched by the same affine map so that the primary sources form a group automorphism (needed for
+                // the constant-XOR partner structure of the fixed frame).  Two extensions exist (cos- or sin-term
+                // as primary); the first consistent one is taken.
+                int primary[16], nz1[16], nz2[16], cnt[16];
+                for (int a = 0; a < dim; ++a) {
+                    cnt[a] = 0; nz1[a] = nz2[a] = -1;
+                    for (int c = 0; c < dim; ++c)
+                        if (b.M[a * dim + c] != 0.0) { if (cnt[a] == 0) nz1[a] = c; else nz2[a] = c; ++cnt[a]; }
+                    if (cnt[a] > 2) { why = "dense fixed block (non-Clifford gate or non-Pauli channel)"; return false; }
+                }
+                bool ok_primary = false;
+                int a0 = -1;
+                for (int a = 0; a < dim; ++a) if (cnt[a] == 2) { a0 = a; break; }
+                if (a0 >= 0 && cnt[0] == 1) {
+                    for (int cand = 0; cand < 2 && !ok_primary; ++cand) {
+                        ok_primary = true;
+                        for (int a = 0; a < dim && ok_primary; ++a) {
+                            if (cnt[a] == 1) { primary[a] = nz1[a]; continue; }
+                            if (cnt[a] == 0) { ok_primary = false; break; }
+                            int d = a ^ a0;
+                            if (cnt[d] != 1) { ok_primary = false; break; }
+                            int pa = (cand == 0 ? nz1[a0] : nz2[a0]) ^ nz1[d] ^ nz1[0];
+                            if (pa != nz1[a] && pa != nz2[a]) { ok_primary = false; break; }
+                            primary[a] = pa;
+                        }
+                        if (ok_primary) {   // must be a permutation
+                            int seen = 0;
+                            for (int a = 0; a < dim; ++a) seen |= 1 << primary[a];
+                            ok_primary = seen == (1 << dim) - 1;
+                        }
+                    }
+                }
+                if (!ok_primary) { why = "2-sparse fixed block without a Pauli-rotation structure"; return false; }
                 for (int j = 0; j < SEG_E; ++j) {
                     int a = b.nq == 1 ? get_code(j, p0) : get_code(j, p0) * 4 + get_code(j, p1);
-                    int cols[2] = {a, a}, nnz = 0;
-                    double vals[2] = {0.0, 0.0};
+                    int cols[2] = {primary[a], primary[a]}, nnz = 0;
+                    double vals[2] = {b.M[a * dim + primary[a]], 0.0};
                     for (int c = 0; c < dim; ++c)
                         if (b.M[a * dim + c] != 0.0) {
-                            if (nnz == 2) { why = "dense fixed block (non-Clifford gate or non-Pauli channel)"; return false; }
-                            cols[nnz] = c; vals[nnz] = b.M[a * dim + c]; ++nnz;
+                            ++nnz;
+                            if (nnz > 2) { why = "dense fixed block (non-Clifford gate or non-Pauli channel)"; return false; }
+                            if (c != primary[a]) { cols[1] = c; vals[1] = b.M[a * dim + c]; }
                         }
                     int jj[2];
                     for (int t = 0; t < 2; ++t)
                         jj[t] = b.nq == 1 ? set_code(j, p0, cols[t]) : set_code(set_code(j, p0, cols[t] >> 2), p1, cols[t] & 3);
                     sg.src0[j] = (uint8_t)cur.src[jj[0]]; sg.w0[j] = vals[0] * cur.w[jj[0]];
                     sg.src1[j] = (uint8_t)cur.src[jj[1]]; sg.w1[j] = vals[1] * cur.w[jj[1]];
-                    sg.active[j] = nnz == 2;
+                    sg.active[j] = vals[1] != 0.0;
                 }
                 p.segs.push_back(std::move(sg));
                 cur.reset();
@@ -789,6 +846,158 @@ static bool build_segments(Plan& p, std::string& why) {
     return true;
 }
 
+// ---- fixed-frame conversion of the segment tables ----------------------------------------------------------
+
+static inline int parity8(unsigned v) { return __builtin_popcount(v) & 1; }
+
+// rows[r] = GF(2) functional giving bit r of the physical index; returns false if not invertible
+static bool gf2_invertible(const unsigned rows[8]) {
+    unsigned m[8];
+    for (int i = 0; i < 8; ++i) m[i] = rows[i];
+    int rank = 0;
+    for (int bit = 0; bit < 8 && rank < 8; ++bit) {
+        int piv = -1;
+        for (int i = rank; i < 8; ++i) if ((m[i] >> bit) & 1u) { piv = i; break; }
+        if (piv < 0) continue;
+        std::swap(m[rank], m[piv]);
+        for (int i = 0; i < 8; ++i) if (i != rank && ((m[i] >> bit) & 1u)) m[i] ^= m[rank];
+        ++rank;
+    }
+    return rank == 8;
+}
+
+static int gf2_rank(const std::vector<unsigned>& vecs) {
+    std::vector<unsigned> basis;
+    for (unsigned v : vecs) {
+        for (unsigned b : basis) v = std::min(v, v ^ b);
+        if (v) basis.push_back(v);
+    }
+    return (int)basis.size();
+}
+
+static bool build_frame(Plan& p, std::string& why) {
+    const int K = p.nseg;
+    std::vector<int> holder(SEG_E), nh(SEG_E);
+    for (int i = 0; i < SEG_E; ++i) holder[i] = i;
+    std::vector<double> w((size_t)K * SEG_E * 2, 0.0);
+    std::vector<unsigned> masks(K, 0u);
+    std::vector<uint8_t> labels((size_t)std::max(p.n_slots, 1) * SEG_E, 0);
+    auto place_labels = [&](int stage) {
+        for (int s = 0; s < p.n_slots; ++s)
+            if (p.slots[s].seg == stage)
+                for (int i = 0; i < SEG_E; ++i) labels[(size_t)s * SEG_E + holder[i]] = p.slots[s].label[i];
+    };
+    for (int k = 0; k < K; ++k) {
+        const Segment& sg = p.segs[k];
+        place_labels(k);
+        std::vector<char> used(SEG_E, 0);
+        int mask = -1;
+        for (int j = 0; j < SEG_E; ++j) {
+            int t = holder[sg.src0[j]];
+            if (used[t]) { why = "segment primary sources are not a permutation"; return false; }
+            used[t] = 1;
+            nh[j] = t;
+            w[((size_t)k * SEG_E + t) * 2] = sg.w0[j];
+            if (sg.active[j] && sg.w1[j] != 0.0) {
+                int partner = holder[sg.src1[j]];
+                int m = t ^ partner;
+                if (mask < 0) mask = m;
+                else if (mask != m) { why = "rotation partners are not related by a constant XOR mask"; return false; }
+                w[((size_t)k * SEG_E + t) * 2 + 1] = sg.w1[j];
+            }
+        }
+        masks[k] = mask < 0 ? 0u : (unsigned)mask;
+        holder = nh;
+    }
+    place_labels(K);
+    // energy weights per thread
+    std::vector<double> ew(SEG_E, 0.0);
+    for (size_t t = 0; t < p.e_w.size(); ++t) ew[holder[p.e_src[t]]] += p.e_w[t];
+
+    // GF(2) relabelling: three functionals (warp bits) that annihilate as many xor masks as possible
+    std::vector<unsigned> chosen;
+    {
+        std::map<unsigned, int> freq;
+        for (unsigned m : masks) if (m) ++freq[m];
+        std::vector<std::pair<int, unsigned>> order;
+        for (auto& kv : freq) order.push_back({-kv.second, kv.first});
+        std::sort(order.begin(), order.end());
+        for (auto& o : order) {
+            std::vector<unsigned> trial = chosen;
+            trial.push_back(o.second);
+            if (gf2_rank(trial) <= 5) chosen = trial;
+        }
+    }
+    unsigned rows[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    {
+        // annihilator of span(chosen): all f with parity(f & m) == 0 for every chosen m
+        std::vector<unsigned> ann;
+        for (unsigned f = 1; f < 256; ++f) {
+            bool ok = true;
+            for (unsigned m : chosen) if (parity8(f & m)) { ok = false; break; }
+            if (ok) ann.push_back(f);
+        }
+        std::vector<unsigned> picked;
+        for (unsigned f : ann) {
+            std::vector<unsigned> trial = picked;
+            trial.push_back(f);
+            if (gf2_rank(trial) == (int)trial.size()) picked = trial;
+            if (picked.size() == 3) break;
+        }
+        if (picked.size() < 3) { why = "internal: annihilator too small"; return false; }
+        rows[5] = picked[0]; rows[6] = picked[1]; rows[7] = picked[2];
+        int filled = 0;
+        for (unsigned f = 1; f < 256 && filled < 5; ++f) {
+            std::vector<unsigned> trial = {rows[5], rows[6], rows[7]};
+            for (int i = 0; i < filled; ++i) trial.push_back(rows[i]);
+            trial.push_back(f);
+            if (gf2_rank(trial) == (int)trial.size()) rows[filled++] = f;
+        }
+        if (filled < 5 || !gf2_invertible(rows)) { why = "internal: relabelling not invertible"; return false; }
+    }
+    auto phys = [&](unsigned t) {
+        unsigned pidx = 0;
+        for (int r = 0; r < 8; ++r) pidx |= (unsigned)parity8(rows[r] & t) << r;
+        return pidx;
+    };
+    p.fsegs.assign(K, FrameSeg());
+    p.f_w.assign((size_t)K * SEG_E * 2, 0.0);
+    p.f_init.assign(SEG_E, 0.0);
+    p.f_eweight.assign(SEG_E, 0.0);
+    p.f_labels.assign((size_t)std::max(p.n_slots, 1) * SEG_E, 0);
+    for (unsigned t = 0; t < (unsigned)SEG_E; ++t) {
+        unsigned q = phys(t);
+        p.f_init[q] = (t & 0xAAu) ? 0.0 : 1.0;
+        p.f_eweight[q] = ew[t];
+        for (int k = 0; k < K; ++k) {
+            p.f_w[((size_t)k * SEG_E + q) * 2] = w[((size_t)k * SEG_E + t) * 2];
+            p.f_w[((size_t)k * SEG_E + q) * 2 + 1] = w[((size_t)k * SEG_E + t) * 2 + 1];
+        }
+        for (int s = 0; s < p.n_slots; ++s) p.f_labels[(size_t)s * SEG_E + q] = labels[(size_t)s * SEG_E + t];
+    }
+    // rotation classes: (param, scale, offset); with offset == 0 the sign of scale folds into w1 (sin is odd)
+    p.f_classes.clear();
+    for (int k = 0; k < K; ++k) {
+        FrameSeg& fs = p.fsegs[k];
+        fs.xor_mask = (int)phys(masks[k]);     // linear map: phys(t ^ m) = phys(t) ^ phys(m)
+        fs.use_shfl = (fs.xor_mask >> 5) == 0;
+        const int rid = p.segs[k].rot_id;
+        if (rid < 0) { fs.cs_sel = -2; continue; }
+        RotInfo ri = p.rots[rid];
+        double sign = 1.0;
+        if (ri.offset == 0.0 && ri.scale < 0.0) { sign = -1.0; ri.scale = -ri.scale; }
+        int cls = -1;
+        for (size_t c = 0; c < p.f_classes.size(); ++c)
+            if (p.f_classes[c].param == ri.param && p.f_classes[c].scale == ri.scale && p.f_classes[c].offset == ri.offset) cls = (int)c;
+        if (cls < 0) { cls = (int)p.f_classes.size(); p.f_classes.push_back(ri); }
+        fs.cs_sel = cls;
+        if (sign < 0)
+            for (int q = 0; q < SEG_E; ++q) p.f_w[((size_t)k * SEG_E + q) * 2 + 1] = -p.f_w[((size_t)k * SEG_E + q) * 2 + 1];
+    }
+    p.f_single_class = p.f_classes.size() <= 1;
+    return true;
+}
+
 // ---- top level ------------------------------------------------------------------------------------------
 
 void lower_plan(Plan& p) {
@@ -820,6 +1029,7 @@ void lower_plan(Plan& p) {
     p.seg_eligible = false;
     if (p.opt_segments && p.n <= SEG_N) {
         p.seg_eligible = build_segments(p, p.seg_reason);
+        if (p.seg_eligible) p.seg_eligible = build_frame(p, p.seg_reason);
         if (p.seg_eligible) p.path = 1;
     } else if (p.n <= SEG_N) {
         p.seg_reason = "disabled by option";
@@ -837,8 +1047,11 @@ void lower_plan(Plan& p) {
     in.state_bytes = (int64_t)(8.0 * N);
     const double io = 8.0 * p.n_params + (double)p.n_slots + 8.0;
     if (p.path == 1) {
+        int smem_segs = 0;
+        for (const FrameSeg& fs : p.fsegs) smem_segs += !fs.use_shfl;
         in.flops_per_circuit = (p.nseg * 4.0 + 1.0) * SEG_E + 2.0 * p.e_w.size();
-        in.smem_bytes_per_circuit = p.nseg * SEG_E * (8.0 + 12.0);
+        // per circuit: smem-exchange segments move 8 B out + 8 B in per coefficient; the energy stage a few terms
+        in.smem_bytes_per_circuit = smem_segs * SEG_E * 16.0 + 16.0 * p.e_w.size();
         in.hbm_bytes_per_circuit = io;
     } else {
         double fl = 0;
@@ -919,6 +1132,27 @@ std::string dump_plan(const Plan& p) {
             os << "seg " << k << " rot=" << s.rot_id;
             dump_ints(os, "src0", s.src0); dump_ints(os, "src1", s.src1); dump_ints(os, "active", s.active);
             dump_vec(os, "w0", s.w0); dump_vec(os, "w1", s.w1);
+            os << "\n";
+        }
+        for (int k = 0; k < p.nseg; ++k) {
+            os << "fseg " << k << " mask=" << p.fsegs[k].xor_mask << " shfl=" << p.fsegs[k].use_shfl << " cs=" << p.fsegs[k].cs_sel;
+            std::vector<double> wk(p.f_w.begin() + (size_t)k * 512, p.f_w.begin() + (size_t)(k + 1) * 512);
+            dump_vec(os, "w", wk);
+            os << "\n";
+        }
+        os << "frame single_class=" << p.f_single_class;
+        dump_vec(os, "init", p.f_init);
+        dump_vec(os, "eweight", p.f_eweight);
+        os << "\n";
+        for (size_t c = 0; c < p.f_classes.size(); ++c) {
+            os << "fclass " << c << " param=" << p.f_classes[c].param;
+            dump_vec(os, "scale", {p.f_classes[c].scale}); dump_vec(os, "offset", {p.f_classes[c].offset});
+            os << "\n";
+        }
+        for (int sl = 0; sl < p.n_slots; ++sl) {
+            os << "flabel " << sl;
+            std::vector<uint8_t> lb(p.f_labels.begin() + (size_t)sl * 256, p.f_labels.begin() + (size_t)(sl + 1) * 256);
+            dump_ints(os, "label", lb);
             os << "\n";
         }
         os << "estage";

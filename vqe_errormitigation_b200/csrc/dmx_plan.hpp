@@ -83,6 +83,17 @@ struct Segment {
     int rot_id = -1;                          // -1: pure monomial (no local op)
 };
 
+// Fixed-frame form of the segment tables (what the kernel executes).  Thread t keeps "its" Pauli coefficient
+// for the whole circuit (the permutations of the Clifford gates are folded into a relabelling), so a segment is
+//   r[t] <- cm * w0[t] * r[t] + sm * w1[t] * r[t ^ xor_mask]
+// with (cm, sm) = (cos, sin) of the segment's rotation class, (1, 1) for constant blocks.  Threads are relabelled
+// by a GF(2)-linear map so that as many xor masks as possible stay inside a warp (register shuffle, no smem).
+struct FrameSeg {
+    int xor_mask = 0;   // physical thread index mask
+    int use_shfl = 1;   // mask has no warp bits -> __shfl_xor_sync; else shared-memory exchange
+    int cs_sel = -2;    // >= 0: rotation class index; -2: constant coefficients (cm = sm = 1)
+};
+
 struct SlotInfo {
     int nq = 1;
     int seg = 0;                  // segment whose INPUT index space the labels refer to (n_segments = energy stage)
@@ -120,6 +131,14 @@ struct Plan {
     std::vector<SlotInfo> slots;
     bool seg_eligible = false;
     std::string seg_reason;
+    // fixed-frame tables (physical thread order)
+    std::vector<FrameSeg> fsegs;
+    std::vector<double> f_w;          // [nseg][256][2] = (w0, w1)
+    std::vector<double> f_init;       // [256]
+    std::vector<double> f_eweight;    // [256] energy weight of the coefficient held by thread t
+    std::vector<uint8_t> f_labels;    // [n_slots][256]
+    std::vector<RotInfo> f_classes;   // distinct (param, scale, offset) rotation classes
+    int f_single_class = 0;           // 1: every rotation segment uses class 0 (kept in registers)
 
     dmx_plan_info info{};
 
