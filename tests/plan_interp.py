@@ -14,7 +14,8 @@ def _nums(s, typ=float):
 
 
 def parse(dump: str) -> dict:
-    plan = {"blocks": [], "passes": [], "devops": [], "segs": [], "slots": {}, "rots": [], "fsegs": [], "fclasses": [], "flabels": {}}
+    plan = {"blocks": [], "passes": [], "phases": [], "sweeps": [], "mus": [], "chains": [], "factors": [], "segs": [], "slots": {},
+            "rots": [], "fsegs": [], "fclasses": [], "flabels": {}}
     for line in dump.splitlines():
         if not line.strip():
             continue
@@ -29,7 +30,7 @@ def parse(dump: str) -> dict:
             else:
                 pos.append(t)
         if head == "plan":
-            for k in ("n", "params", "path", "tile_k", "nseg"):
+            for k in ("n", "params", "path", "tile_k", "nseg", "cpb"):
                 plan[k] = int(kv[k])
             plan["n_slots"] = int(kv["slots"])
         elif head == "block":
@@ -45,9 +46,17 @@ def parse(dump: str) -> dict:
                     b[k] = float(kv[k])
             plan["blocks"].append(b)
         elif head == "pass":
-            plan["passes"].append({"first": int(kv["first"]), "nops": int(kv["nops"]), "tile": _nums(kv["tile"], int), "rots": _nums(kv["rots"], int)})
-        elif head == "devop":
-            plan["devops"].append({k: int(kv[k]) for k in ("kind", "p0", "p1", "coef", "a0", "a1", "a2")})
+            plan["passes"].append({"first_phase": int(kv["first_phase"]), "nphases": int(kv["nphases"]), "tile": _nums(kv["tile"], int)})
+        elif head == "phase":
+            plan["phases"].append({k: int(kv[k]) for k in ("first_sweep", "nsweeps", "first_chain", "nchains")})
+        elif head == "sweep":
+            plan["sweeps"].append({k: int(kv[k]) for k in ("p0", "p1", "first_mu", "nmu", "lperm", "lcoef", "lsrc", "sperm", "scoef", "sdst")})
+        elif head == "mu":
+            plan["mus"].append({k: int(kv[k]) for k in ("kind", "a0", "a1", "a2", "a3")})
+        elif head == "chain":
+            plan["chains"].append({"first": int(kv["first"]), "n": int(kv["n"])})
+        elif head == "factor":
+            plan["factors"].append({"kind": int(kv["kind"]), "coef": int(kv["coef"]), "rot": int(kv["rot"])})
         elif head == "" and "coefs" in kv:
             plan["coefs"] = _nums(kv["coefs"])
         elif head == "terms":
@@ -117,80 +126,106 @@ def energy(plan, r) -> float:
 
 
 def run_devops(plan, params=None, variants=None) -> np.ndarray:
-    """Interpret the device op table pass by pass (tile-local bit positions -> global positions)."""
+    """Interpret the device program (passes -> phases -> sweeps -> micro-ops) as dmx_tile_kernel executes it."""
     n = plan["n"]
-    r = init_state(n)
     cf = plan["coefs"]
-    E = 4 ** n
+    pad = 2 if n == 1 else 0
+    nbits = 2 * n + pad
+    E = 1 << nbits
     idx = np.arange(E)
+    r = np.zeros(E)
+    r[np.arange(4 ** n) << pad] = init_state(n)
+
+    def chain_matrix(ch):
+        M = np.eye(4)
+        for f in plan["factors"][ch["first"]:ch["first"] + ch["n"]]:
+            if f["kind"] == 0:
+                F = cf[f["coef"]:f["coef"] + 16].reshape(4, 4)
+            else:
+                rot = plan["rots"][f["rot"]]
+                th = rot["scale"] * params[rot["param"]] + rot["offset"]
+                acs = cf[f["coef"]:f["coef"] + 48].reshape(3, 4, 4)
+                F = acs[0] + np.cos(th) * acs[1] + np.sin(th) * acs[2]
+            M = F @ M
+        return M
+
     for ps in plan["passes"]:
         tile = list(ps["tile"])
         k = len(tile)
-        # local position p of tile qubit i is 2*(k-1-i); global position 2*(n-1-q)
-        gpos = {2 * (k - 1 - i): 2 * (n - 1 - q) for i, q in enumerate(tile)}
-        for op in plan["devops"][ps["first"]:ps["first"] + ps["nops"]]:
-            kind = op["kind"]
-            g0 = gpos[op["p0"]]
-            c0 = (idx >> g0) & 3
-            if kind in (0, 1, 2, 3, 7):
-                if kind == 0:
-                    r = r * cf[op["coef"] + c0]
-                elif kind == 1:
-                    src_code = (op["a0"] >> (2 * c0)) & 3
-                    src = (idx & ~(3 << g0)) | (src_code << g0)
-                    r = cf[op["coef"] + c0] * r[src]
-                else:
-                    if kind == 2:
-                        M = cf[op["coef"]:op["coef"] + 16].reshape(4, 4)
-                    elif kind == 3:
-                        rot = plan["rots"][ps["rots"][op["a0"]]]
-                        assert ps["rots"][op["a0"]] == op["a2"]
-                        th = rot["scale"] * params[rot["param"]] + rot["offset"]
-                        acs = cf[op["coef"]:op["coef"] + 48].reshape(3, 4, 4)
-                        M = acs[0] + np.cos(th) * acs[1] + np.sin(th) * acs[2]
-                    else:
-                        v = 0 if variants is None else int(variants[op["a0"]])
-                        if v == 0:
-                            continue
-                        M = cf[op["coef"] + 16 * v: op["coef"] + 16 * v + 16].reshape(4, 4)
-                    new = np.zeros_like(r)
-                    for b in range(4):
-                        src = (idx & ~(3 << g0)) | (b << g0)
-                        new += M[c0, b] * r[src]
-                    r = new
-            else:
-                g1 = gpos[op["p1"]]
-                c1 = (idx >> g1) & 3
+        if n == 1:
+            gpos = {2: 2, 0: 0}
+        else:
+            gpos = {2 * (k - 1 - i): 2 * (n - 1 - q) for i, q in enumerate(tile)}
+        for ph in plan["phases"][ps["first_phase"]:ps["first_phase"] + ps["nphases"]]:
+            mats = [chain_matrix(c) for c in plan["chains"][ph["first_chain"]:ph["first_chain"] + ph["nchains"]]]
+            for sw in plan["sweeps"][ph["first_sweep"]:ph["first_sweep"] + ph["nsweeps"]]:
+                g0, g1 = gpos[sw["p0"]], gpos[sw["p1"]]
+                c0, c1 = (idx >> g0) & 3, (idx >> g1) & 3
                 loc = c0 * 4 + c1
                 clear = idx & ~(3 << g0) & ~(3 << g1)
 
-                def dense(M, r):
-                    new = np.zeros_like(r)
-                    for b in range(16):
-                        src = clear | ((b >> 2) << g0) | ((b & 3) << g1)
-                        new += M[loc, b] * r[src]
+                def at(code):
+                    return clear | ((code >> 2) << g0) | ((code & 3) << g1)
+
+                if sw["lperm"]:
+                    src = np.array([(sw["lsrc"] >> (4 * int(e))) & 15 for e in range(16)])[loc]
+                    v = cf[sw["lcoef"] + loc] * r[at(src)]
+                else:
+                    v = r.copy()
+
+                def side(v, M, a_side, unital):
+                    if unital:
+                        assert M[0, 0] == 1 and not M[0, 1:].any() and not M[1:, 0].any()
+                    new = np.zeros_like(v)
+                    for b in range(4):
+                        srcidx = (idx & ~(3 << (g0 if a_side else g1))) | (b << (g0 if a_side else g1))
+                        new += M[(c0 if a_side else c1), b] * v[srcidx]
                     return new
 
-                if kind == 4:
-                    r = r * cf[op["coef"] + loc]
-                elif kind == 5:
-                    pk = (op["a0"] & 0xFFFFFFFF) | ((op["a1"] & 0xFFFFFFFF) << 32)
-                    s = np.array([(pk >> (4 * int(e))) & 15 for e in loc])
-                    src = clear | ((s >> 2) << g0) | ((s & 3) << g1)
-                    r = cf[op["coef"] + loc] * r[src]
-                elif kind == 6:
-                    r = dense(cf[op["coef"]:op["coef"] + 256].reshape(16, 16), r)
-                else:
-                    v = 0 if variants is None else int(variants[op["a0"]])
-                    if v == 0:
-                        continue
-                    tab = cf[op["coef"]:op["coef"] + 256].reshape(16, 4, 4)
-                    r = dense(np.kron(tab[v >> 4], tab[v & 15]), r)
-                    if op["a2"] == 1:
-                        r = r * cf[op["a1"] + loc]
+                def dense(v, M):
+                    new = np.zeros_like(v)
+                    for b in range(16):
+                        new += M[loc, b] * v[at(np.full_like(loc, b))]
+                    return new
+
+                for m in plan["mus"][sw["first_mu"]:sw["first_mu"] + sw["nmu"]]:
+                    kind = m["kind"]
+                    if kind in (0, 1):
+                        v = side(v, mats[m["a0"]], kind == 0, m["a3"])
+                    elif kind in (2, 3):
+                        v = side(v, cf[m["a0"]:m["a0"] + 16].reshape(4, 4), kind == 2, m["a3"])
+                    elif kind == 4:
+                        v = v * cf[m["a0"] + c0]
+                    elif kind == 5:
+                        v = v * cf[m["a0"] + c1]
+                    elif kind == 6:
+                        v = v * cf[m["a0"] + loc]
+                    elif kind == 7:
+                        v = dense(v, cf[m["a0"]:m["a0"] + 256].reshape(16, 16))
                     else:
-                        r = dense(cf[op["a1"]:op["a1"] + 256].reshape(16, 16), r)
-    return r
+                        var = 0 if variants is None else int(variants[m["a0"]])
+                        if var == 0:
+                            continue
+                        tab = cf[m["a1"]:m["a1"] + 256].reshape(16, 4, 4)
+                        if kind == 8:
+                            v = side(v, tab[var & 15], True, 0)
+                        elif kind == 9:
+                            v = side(v, tab[var & 15], False, 0)
+                        else:
+                            v = side(v, tab[var >> 4], True, 0)
+                            v = side(v, tab[var & 15], False, 0)
+                            if m["a3"] == 1:
+                                v = v * cf[m["a2"] + loc]
+                            else:
+                                v = dense(v, cf[m["a2"]:m["a2"] + 256].reshape(16, 16))
+                if sw["sperm"]:
+                    dst = np.array([(sw["sdst"] >> (4 * int(e))) & 15 for e in range(16)])[loc]
+                    out = np.zeros_like(v)
+                    out[at(dst)] = cf[sw["scoef"] + dst] * v
+                    r = out
+                else:
+                    r = v
+    return r[np.arange(4 ** n) << pad]
 
 
 def run_segments(plan, params=None, variants=None):

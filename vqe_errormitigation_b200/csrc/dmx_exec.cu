@@ -52,17 +52,19 @@ struct BitRun {
 };
 
 struct TileArgs {
-    const DevOp* ops;
-    int n_ops;
+    const SweepDev* sweeps;
+    const MicroOp* mus;
+    const ChainDev* chains;
+    const ChainFactor* factors;
+    const Phase* phases;
+    int first_phase, n_phases, max_chains;
     const double* coefs;
     const RotInfo* rots;
-    const int* pass_rots;  // global rot ids evaluated in this pass
-    int n_rots;
     const double* params;
     int n_params;
     const uint8_t* variants;
     int n_slots;
-    int n, k, cpb;
+    int n, k, cpb, pad;         // pad: extra low index bits of the tile (2 when n == 1: virtual idle qubit)
     long long batch;
     const int* worklist;        // optional indirection: circuit id = worklist[i], count in *work_count
     const int* work_count;
@@ -89,7 +91,9 @@ __device__ __forceinline__ unsigned insert2(unsigned g, int p) {  // open a 2-bi
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// tile kernel
+// tile kernel: the Pauli vector (or one tile of it) lives in shared memory; a pass is a list of sweeps, each
+// sweep = load a 16-coefficient group (all codes of a qubit pair) into registers, apply the fused micro-ops,
+// store.  Monomial two-qubit blocks ride on the load / store addressing.
 // ---------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void mat4_apply(const double* __restrict__ M, double& v0, double& v1, double& v2, double& v3) {
     double n0 = M[0] * v0 + M[1] * v1 + M[2] * v2 + M[3] * v3;
@@ -99,15 +103,58 @@ __device__ __forceinline__ void mat4_apply(const double* __restrict__ M, double&
     v0 = n0; v1 = n1; v2 = n2; v3 = n3;
 }
 
+// unital, trace-preserving 1-qubit map: row 0 = column 0 = e0, only the 3x3 block acts
+__device__ __forceinline__ void mat3_apply(const double* __restrict__ M, double& v1, double& v2, double& v3) {
+    double n1 = M[5] * v1 + M[6] * v2 + M[7] * v3;
+    double n2 = M[9] * v1 + M[10] * v2 + M[11] * v3;
+    double n3 = M[13] * v1 + M[14] * v2 + M[15] * v3;
+    v1 = n1; v2 = n2; v3 = n3;
+}
+
+__device__ __forceinline__ void side_a(double (&v)[16], const double* __restrict__ M, bool unital) {
+    if (unital) {
+#pragma unroll
+        for (int c1 = 0; c1 < 4; ++c1) mat3_apply(M, v[4 + c1], v[8 + c1], v[12 + c1]);
+    } else {
+#pragma unroll
+        for (int c1 = 0; c1 < 4; ++c1) mat4_apply(M, v[c1], v[4 + c1], v[8 + c1], v[12 + c1]);
+    }
+}
+
+__device__ __forceinline__ void side_b(double (&v)[16], const double* __restrict__ M, bool unital) {
+    if (unital) {
+#pragma unroll
+        for (int c0 = 0; c0 < 4; ++c0) mat3_apply(M, v[4 * c0 + 1], v[4 * c0 + 2], v[4 * c0 + 3]);
+    } else {
+#pragma unroll
+        for (int c0 = 0; c0 < 4; ++c0) mat4_apply(M, v[4 * c0], v[4 * c0 + 1], v[4 * c0 + 2], v[4 * c0 + 3]);
+    }
+}
+
+__device__ __forceinline__ void dense16(double (&v)[16], const double* __restrict__ M) {
+    double nv[16];
+#pragma unroll
+    for (int r = 0; r < 16; ++r) {
+        double s = 0.0;
+#pragma unroll
+        for (int c = 0; c < 16; ++c) s += M[r * 16 + c] * v[c];
+        nv[r] = s;
+    }
+#pragma unroll
+    for (int e = 0; e < 16; ++e) v[e] = nv[e];
+}
+
 extern __shared__ __align__(16) double dmx_smem[];
 
+template <int G>
 __global__ void __launch_bounds__(512) dmx_tile_kernel(const TileArgs a) {
     double* tile = dmx_smem;
     const int tid = threadIdx.x, nthr = blockDim.x;
-    const int kbits = 2 * a.k;
-    const unsigned tile_elems = 1u << kbits;
-    const unsigned E = (unsigned)a.cpb << kbits;
-    double* cs = tile + E;  // [cpb][n_rots][2]
+    const int tbits = 2 * a.k + a.pad;               // index bits of one circuit's tile
+    const unsigned tile_elems = 1u << tbits;
+    const unsigned E = (unsigned)a.cpb << tbits;
+    const unsigned NG = E >> 4;
+    double* mats = tile + E;                         // [cpb][max_chains][16]
     const bool streaming = a.k < a.n;
 
     long long total = a.batch;
@@ -122,7 +169,6 @@ __global__ void __launch_bounds__(512) dmx_tile_kernel(const TileArgs a) {
     }
 
     for (long long grp = blockIdx.x; grp < ngroups; grp += gridDim.x) {
-        // circuit ids handled by this CTA iteration
         long long c_first;
         unsigned tile_base = 0;
         if (streaming) {
@@ -148,147 +194,154 @@ __global__ void __launch_bounds__(512) dmx_tile_kernel(const TileArgs a) {
                 }
             }
         } else {
-            for (unsigned e = tid; e < E; e += nthr) tile[e] = ((e & (tile_elems - 1)) & 0xAAAAAAAAu) ? 0.0 : 1.0;
-        }
-        // ---- per-circuit rotation angles ----
-        for (int i = tid; i < a.cpb * a.n_rots; i += nthr) {
-            int c = i / a.n_rots, r = i - c * a.n_rots;
-            long long ci = c_first + c;
-            double sv = 0.0, cv = 1.0;
-            if (ci < total) {
-                long long b = a.worklist ? a.worklist[ci] : ci + a.circuit_offset;
-                RotInfo ri = a.rots[a.pass_rots[r]];
-                double theta = ri.scale * a.params[b * a.n_params + ri.param] + ri.offset;
-                sincos(theta, &sv, &cv);
+            const unsigned padmask = (1u << a.pad) - 1u;
+            for (unsigned e = tid; e < E; e += nthr) {
+                unsigned loc = e & (tile_elems - 1);
+                tile[e] = ((loc & padmask) || ((loc >> a.pad) & 0xAAAAAAAAu)) ? 0.0 : 1.0;
             }
-            cs[2 * i] = cv;
-            cs[2 * i + 1] = sv;
         }
-        __syncthreads();
 
-        // ---- op loop ----
-        for (int oi = 0; oi < a.n_ops; ++oi) {
-            const DevOp op = a.ops[oi];
-            const double* __restrict__ cf = a.coefs + op.coef;
-            if (op.kind <= DK_ROT1 || op.kind == DK_VAR1) {
-                const int p = op.p0;
-                const unsigned G = E >> 2;
-                for (unsigned g = tid; g < G; g += nthr) {
-                    unsigned base = insert2(g, p);
-                    double v0 = tile[base], v1 = tile[base | (1u << p)], v2 = tile[base | (2u << p)], v3 = tile[base | (3u << p)];
-                    switch (op.kind) {
-                        case DK_DIAG1:
-                            v0 *= cf[0]; v1 *= cf[1]; v2 *= cf[2]; v3 *= cf[3];
-                            break;
-                        case DK_MONO1: {
-                            double in[4] = {v0, v1, v2, v3};
-                            unsigned pk = (unsigned)op.a0;
-                            // 2-bit source codes; select without dynamic register indexing
-                            auto pick = [&](unsigned s) { return s == 0 ? in[0] : (s == 1 ? in[1] : (s == 2 ? in[2] : in[3])); };
-                            v0 = cf[0] * pick(pk & 3u);
-                            v1 = cf[1] * pick((pk >> 2) & 3u);
-                            v2 = cf[2] * pick((pk >> 4) & 3u);
-                            v3 = cf[3] * pick((pk >> 6) & 3u);
-                            break;
-                        }
-                        case DK_MAT1:
-                            mat4_apply(cf, v0, v1, v2, v3);
-                            break;
-                        case DK_ROT1: {
-                            int c = (int)(base >> kbits);
-                            double cv = cs[2 * (c * a.n_rots + op.a0)], sv = cs[2 * (c * a.n_rots + op.a0) + 1];
-                            double M[16];
+        for (int ph = 0; ph < a.n_phases; ++ph) {
+            const Phase phase = a.phases[a.first_phase + ph];
+            // ---- per-circuit chain matrices (products of rotations / fixed 1-qubit blocks) ----
+            __syncthreads();   // previous phase's sweeps are done with the chain table
+            for (int i = tid; i < a.cpb * phase.n_chains; i += nthr) {
+                const int c = i / phase.n_chains, chn = i - c * phase.n_chains;
+                const long long ci = c_first + c;
+                double M[16];
 #pragma unroll
-                            for (int e = 0; e < 16; ++e) M[e] = cf[e] + cv * cf[16 + e] + sv * cf[32 + e];
-                            mat4_apply(M, v0, v1, v2, v3);
-                            break;
+                for (int e = 0; e < 16; ++e) M[e] = (e % 5 == 0) ? 1.0 : 0.0;
+                if (ci < total) {
+                    const long long b = a.worklist ? a.worklist[ci] : ci + a.circuit_offset;
+                    const ChainDev ch = a.chains[phase.first_chain + chn];
+                    for (int f = 0; f < ch.n_factors; ++f) {
+                        const ChainFactor fa = a.factors[ch.first_factor + f];
+                        const double* __restrict__ cf = a.coefs + fa.coef;
+                        double F[16];
+                        if (fa.kind == 0) {
+#pragma unroll
+                            for (int e = 0; e < 16; ++e) F[e] = cf[e];
+                        } else {
+                            const RotInfo ri = a.rots[fa.rot_id];
+                            double sv, cv;
+                            sincos(ri.scale * a.params[b * a.n_params + ri.param] + ri.offset, &sv, &cv);
+#pragma unroll
+                            for (int e = 0; e < 16; ++e) F[e] = cf[e] + cv * cf[16 + e] + sv * cf[32 + e];
                         }
-                        default: {  // DK_VAR1
-                            long long ci = c_first + (long long)(base >> kbits);
-                            if (a.variants && ci < total) {
-                                long long b = a.worklist ? a.worklist[ci] : ci + a.circuit_offset;
-                                unsigned idx = a.variants[b * a.n_slots + op.a0];
-                                if (idx) mat4_apply(cf + 16 * (idx & 15u), v0, v1, v2, v3);
-                            }
-                            break;
-                        }
+                        double T[16];
+#pragma unroll
+                        for (int r = 0; r < 4; ++r)
+#pragma unroll
+                            for (int cc = 0; cc < 4; ++cc)
+                                T[r * 4 + cc] = F[r * 4] * M[cc] + F[r * 4 + 1] * M[4 + cc] + F[r * 4 + 2] * M[8 + cc] + F[r * 4 + 3] * M[12 + cc];
+#pragma unroll
+                        for (int e = 0; e < 16; ++e) M[e] = T[e];
                     }
-                    tile[base] = v0; tile[base | (1u << p)] = v1; tile[base | (2u << p)] = v2; tile[base | (3u << p)] = v3;
                 }
-            } else {
-                const int p0 = op.p0, p1 = op.p1;
-                const int pa = p0 < p1 ? p0 : p1, pb = p0 < p1 ? p1 : p0;
-                const unsigned G = E >> 4;
-                for (unsigned g = tid; g < G; g += nthr) {
-                    unsigned base = insert2(insert2(g, pa), pb);
-                    double v[16];
+                double* dst = mats + (size_t)(c * a.max_chains + chn) * 16;
 #pragma unroll
-                    for (int c0 = 0; c0 < 4; ++c0)
-#pragma unroll
-                        for (int c1 = 0; c1 < 4; ++c1) v[c0 * 4 + c1] = tile[base | ((unsigned)c0 << p0) | ((unsigned)c1 << p1)];
-                    if (op.kind == DK_DIAG2) {
-#pragma unroll
-                        for (int e = 0; e < 16; ++e) v[e] *= cf[e];
-                    } else if (op.kind == DK_MONO2) {
-                        unsigned long long pk = ((unsigned long long)(unsigned)op.a1 << 32) | (unsigned)op.a0;
-#pragma unroll
-                        for (int e = 0; e < 16; ++e) {
-                            unsigned s = (unsigned)(pk >> (4 * e)) & 15u;
-                            v[e] = cf[e] * tile[base | ((s >> 2) << p0) | ((s & 3u) << p1)];
-                        }
-                    } else if (op.kind == DK_MAT2) {
-                        double nv[16];
-#pragma unroll
-                        for (int r = 0; r < 16; ++r) {
-                            double s = 0.0;
-#pragma unroll
-                            for (int c = 0; c < 16; ++c) s += cf[r * 16 + c] * v[c];
-                            nv[r] = s;
-                        }
-#pragma unroll
-                        for (int e = 0; e < 16; ++e) v[e] = nv[e];
-                    } else {  // DK_VAR2
-                        long long ci = c_first + (long long)(base >> kbits);
-                        unsigned idx = 0;
-                        if (a.variants && ci < total) {
-                            long long b = a.worklist ? a.worklist[ci] : ci + a.circuit_offset;
-                            idx = a.variants[b * a.n_slots + op.a0];
-                        }
-                        if (idx) {
-                            const double* Ma = cf + 16 * (idx >> 4);
-                            const double* Mb = cf + 16 * (idx & 15u);
-#pragma unroll
-                            for (int c1 = 0; c1 < 4; ++c1) mat4_apply(Ma, v[c1], v[4 + c1], v[8 + c1], v[12 + c1]);
-#pragma unroll
-                            for (int c0 = 0; c0 < 4; ++c0) mat4_apply(Mb, v[4 * c0], v[4 * c0 + 1], v[4 * c0 + 2], v[4 * c0 + 3]);
-                            const double* cc = a.coefs + op.a1;
-                            if (op.a2 == CLS_DIAG) {
-#pragma unroll
-                                for (int e = 0; e < 16; ++e) v[e] *= cc[e];
-                            } else {
-                                double nv[16];
-#pragma unroll
-                                for (int r = 0; r < 16; ++r) {
-                                    double s = 0.0;
-#pragma unroll
-                                    for (int c = 0; c < 16; ++c) s += cc[r * 16 + c] * v[c];
-                                    nv[r] = s;
-                                }
-#pragma unroll
-                                for (int e = 0; e < 16; ++e) v[e] = nv[e];
-                            }
-                        }
-                    }
-                    // MONO2 read its sources straight from the tile: all reads of this group are done
-                    // (each thread owns its whole 16-element group), so the in-place write is safe.
-#pragma unroll
-                    for (int c0 = 0; c0 < 4; ++c0)
-#pragma unroll
-                        for (int c1 = 0; c1 < 4; ++c1) tile[base | ((unsigned)c0 << p0) | ((unsigned)c1 << p1)] = v[c0 * 4 + c1];
-                }
+                for (int e = 0; e < 16; ++e) dst[e] = M[e];
             }
             __syncthreads();
+
+            for (int si = 0; si < phase.n_sweeps; ++si) {
+                const SweepDev sw = a.sweeps[phase.first_sweep + si];
+                const int p0 = sw.p0, p1 = sw.p1;
+                const int pa = p0 < p1 ? p0 : p1, pb = p0 < p1 ? p1 : p0;
+                double v[G][16];
+                unsigned base[G];
+#pragma unroll
+                for (int i = 0; i < G; ++i) {
+                    const unsigned g = tid + i * nthr;
+                    base[i] = insert2(insert2(g < NG ? g : 0u, pa), pb);
+                    if (sw.load_perm) {
+                        const unsigned long long pk = ((unsigned long long)sw.lsrc_hi << 32) | sw.lsrc_lo;
+                        const double* __restrict__ lc = a.coefs + sw.lcoef;
+#pragma unroll
+                        for (int e = 0; e < 16; ++e) {
+                            const unsigned s = (unsigned)(pk >> (4 * e)) & 15u;
+                            v[i][e] = lc[e] * tile[base[i] | ((s >> 2) << p0) | ((s & 3u) << p1)];
+                        }
+                    } else {
+#pragma unroll
+                        for (int e = 0; e < 16; ++e) v[i][e] = tile[base[i] | ((unsigned)(e >> 2) << p0) | ((unsigned)(e & 3) << p1)];
+                    }
+                }
+                for (int mi = 0; mi < sw.n_mu; ++mi) {
+                    const MicroOp m = a.mus[sw.first_mu + mi];
+#pragma unroll
+                    for (int i = 0; i < G; ++i) {
+                        const int c = (int)(base[i] >> tbits);
+                        switch (m.kind) {
+                            case MU_CHAIN_A: side_a(v[i], mats + (size_t)(c * a.max_chains + m.a0) * 16, m.a3 != 0); break;
+                            case MU_CHAIN_B: side_b(v[i], mats + (size_t)(c * a.max_chains + m.a0) * 16, m.a3 != 0); break;
+                            case MU_FIX_A: side_a(v[i], a.coefs + m.a0, m.a3 != 0); break;
+                            case MU_FIX_B: side_b(v[i], a.coefs + m.a0, m.a3 != 0); break;
+                            case MU_DIAG_A: {
+                                const double* __restrict__ d = a.coefs + m.a0;
+#pragma unroll
+                                for (int e = 0; e < 16; ++e) v[i][e] *= d[e >> 2];
+                                break;
+                            }
+                            case MU_DIAG_B: {
+                                const double* __restrict__ d = a.coefs + m.a0;
+#pragma unroll
+                                for (int e = 0; e < 16; ++e) v[i][e] *= d[e & 3];
+                                break;
+                            }
+                            case MU_DIAG2: {
+                                const double* __restrict__ d = a.coefs + m.a0;
+#pragma unroll
+                                for (int e = 0; e < 16; ++e) v[i][e] *= d[e];
+                                break;
+                            }
+                            case MU_MAT2: dense16(v[i], a.coefs + m.a0); break;
+                            default: {   // variant micro-ops
+                                const long long ci = c_first + c;
+                                unsigned idx = 0;
+                                if (a.variants && ci < total) {
+                                    const long long b = a.worklist ? a.worklist[ci] : ci + a.circuit_offset;
+                                    idx = a.variants[b * a.n_slots + m.a0];
+                                }
+                                if (!idx) break;
+                                if (m.kind == MU_VAR_A) side_a(v[i], a.coefs + m.a1 + 16 * (idx & 15u), false);
+                                else if (m.kind == MU_VAR_B) side_b(v[i], a.coefs + m.a1 + 16 * (idx & 15u), false);
+                                else {
+                                    side_a(v[i], a.coefs + m.a1 + 16 * (idx >> 4), false);
+                                    side_b(v[i], a.coefs + m.a1 + 16 * (idx & 15u), false);
+                                    const double* __restrict__ cc = a.coefs + m.a2;
+                                    if (m.a3 == CLS_DIAG) {
+#pragma unroll
+                                        for (int e = 0; e < 16; ++e) v[i][e] *= cc[e];
+                                    } else {
+                                        dense16(v[i], cc);
+                                    }
+                                }
+                                break;
+                            }
+                        }
+                    }
+                }
+#pragma unroll
+                for (int i = 0; i < G; ++i) {
+                    if (tid + i * nthr >= NG) continue;
+                    if (sw.store_perm) {
+                        const unsigned long long pk = ((unsigned long long)sw.sdst_hi << 32) | sw.sdst_lo;
+                        const double* __restrict__ sc = a.coefs + sw.scoef;
+#pragma unroll
+                        for (int e = 0; e < 16; ++e) {
+                            const unsigned d = (unsigned)(pk >> (4 * e)) & 15u;
+                            tile[base[i] | ((d >> 2) << p0) | ((d & 3u) << p1)] = sc[d] * v[i][e];
+                        }
+                    } else {
+#pragma unroll
+                        for (int e = 0; e < 16; ++e) tile[base[i] | ((unsigned)(e >> 2) << p0) | ((unsigned)(e & 3) << p1)] = v[i][e];
+                    }
+                }
+                __syncthreads();
+            }
         }
+        __syncthreads();
 
         // ---- epilogue ----
         if (streaming) {
@@ -305,9 +358,9 @@ __global__ void __launch_bounds__(512) dmx_tile_kernel(const TileArgs a) {
             for (int c = warp; c < a.cpb; c += nwarps) {
                 long long ci = c_first + c;
                 if (ci >= total) continue;
-                const double* r = tile + ((unsigned)c << kbits);
+                const double* r = tile + ((unsigned)c << tbits);
                 double e = 0.0;
-                for (int t = lane; t < a.n_terms; t += 32) e += a.term_coef[t] * r[a.term_idx[t]];
+                for (int t = lane; t < a.n_terms; t += 32) e += a.term_coef[t] * r[a.term_idx[t] << a.pad];
 #pragma unroll
                 for (int off = 16; off > 0; off >>= 1) e += __shfl_xor_sync(0xffffffffu, e, off);
                 if (lane == 0) {
@@ -316,9 +369,11 @@ __global__ void __launch_bounds__(512) dmx_tile_kernel(const TileArgs a) {
                 }
             }
         } else if (a.epilogue == 2) {
+            const unsigned padmask = (1u << a.pad) - 1u;
             for (unsigned e = tid; e < E; e += nthr) {
-                long long ci = c_first + (e >> kbits);
-                if (ci < total) a.out[(ci << kbits) + (e & (tile_elems - 1))] = tile[e];
+                long long ci = c_first + (e >> tbits);
+                unsigned loc = e & (tile_elems - 1);
+                if (ci < total && !(loc & padmask)) a.out[(ci << (2 * a.n)) + (loc >> a.pad)] = tile[e];
             }
         }
         __syncthreads();
@@ -635,11 +690,13 @@ __global__ void dmx_fp64_fma_kernel(double* out, int iters) {
 // ---------------------------------------------------------------------------------------------------------
 struct DevPlan {
     int device = -1;
-    DevOp* ops = nullptr;
+    SweepDev* sweeps = nullptr;
+    MicroOp* mus = nullptr;
+    ChainDev* chains = nullptr;
+    ChainFactor* factors = nullptr;
+    Phase* phases = nullptr;
     double* coefs = nullptr;
     RotInfo* rots = nullptr;
-    int* pass_rots = nullptr;          // concatenated
-    std::vector<int> pass_rot_off;
     uint32_t* term_idx = nullptr;
     double* term_coef = nullptr;
     // segment (fixed frame)
@@ -682,7 +739,14 @@ static int ensure_device(Plan& p, DevPlan** out) {
     DevPlan* d = new DevPlan();
     d->device = dev;
     CUDA_TRY(cudaDeviceGetAttribute(&d->sm_count, cudaDevAttrMultiProcessorCount, dev));
-    CUDA_TRY(upload(&d->ops, p.dev_ops));
+    {
+        auto nonempty = [](auto v) { if (v.empty()) v.resize(1); return v; };
+        CUDA_TRY(upload(&d->sweeps, nonempty(p.sweeps)));
+        CUDA_TRY(upload(&d->mus, nonempty(p.mus)));
+        CUDA_TRY(upload(&d->chains, nonempty(p.chains)));
+        CUDA_TRY(upload(&d->factors, nonempty(p.factors)));
+        CUDA_TRY(upload(&d->phases, nonempty(p.phases)));
+    }
     {
         std::vector<double> c = p.coefs;
         if (c.empty()) c.push_back(0.0);
@@ -693,13 +757,6 @@ static int ensure_device(Plan& p, DevPlan** out) {
         if (r.empty()) r.push_back(RotInfo{0, 0, 0.0, 0.0});
         CUDA_TRY(upload(&d->rots, r));
     }
-    std::vector<int> pr;
-    for (const Pass& ps : p.passes) {
-        d->pass_rot_off.push_back((int)pr.size());
-        pr.insert(pr.end(), ps.rot_ids.begin(), ps.rot_ids.end());
-    }
-    if (pr.empty()) pr.push_back(0);
-    CUDA_TRY(upload(&d->pass_rots, pr));
     CUDA_TRY(upload(&d->term_idx, p.term_idx));
     CUDA_TRY(upload(&d->term_coef, p.term_coef));
     if (p.seg_eligible) {
@@ -741,7 +798,8 @@ static int ensure_device(Plan& p, DevPlan** out) {
 static void free_device(Plan& p) {
     DevPlan* d = (DevPlan*)p.dev;
     if (!d) return;
-    cudaFree(d->ops); cudaFree(d->coefs); cudaFree(d->rots); cudaFree(d->pass_rots); cudaFree(d->term_idx); cudaFree(d->term_coef);
+    cudaFree(d->sweeps); cudaFree(d->mus); cudaFree(d->chains); cudaFree(d->factors); cudaFree(d->phases);
+    cudaFree(d->coefs); cudaFree(d->rots); cudaFree(d->term_idx); cudaFree(d->term_coef);
     cudaFree(d->f_w); cudaFree(d->f_segs); cudaFree(d->f_classes); cudaFree(d->f_init); cudaFree(d->f_eweight); cudaFree(d->f_eslot);
     cudaFree(d->slots); cudaFree(d->labels); cudaFree(d->worklist);
     if (d->h_stage) cudaFreeHost(d->h_stage);
@@ -773,29 +831,27 @@ static void make_runs(const std::vector<int>& qubits, int n, BitRun* runs, int* 
     *n_runs = count;
 }
 
-static int tile_threads(unsigned elems) { return elems >= 16384 ? 512 : 256; }
-
-static int tile_cpb(int n) {
-    int cpb = 1;
-    while ((cpb << (2 * n)) < 4096) cpb <<= 1;
-    return cpb;
+static int pass_max_chains(const Plan& p, const Pass& ps) {
+    int m = 1;
+    for (int i = 0; i < ps.n_phases; ++i) m = std::max(m, p.phases[ps.first_phase + i].n_chains);
+    return m;
 }
 
-static size_t tile_smem(int k, int cpb, int n_rots) {
-    return ((size_t)cpb << (2 * k)) * 8 + (size_t)cpb * std::max(n_rots, 1) * 16;
-}
-
-static int launch_tile(const TileArgs& a, int grid, int threads, size_t smem, cudaStream_t st) {
+static int launch_tile(const TileArgs& a, int grid, int threads, int groups_per_thread, size_t smem, cudaStream_t st) {
     static std::mutex mu;
-    static size_t configured = 0;
+    static size_t configured[2] = {0, 0};
+    const int gi = groups_per_thread == 2 ? 1 : 0;
     {
         std::lock_guard<std::mutex> lock(mu);
-        if (smem > configured) {
-            CUDA_TRY(cudaFuncSetAttribute(dmx_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max(smem, (size_t)48 * 1024)));
-            configured = std::max(smem, (size_t)48 * 1024);
+        if (smem > configured[gi]) {
+            const int want = (int)std::max(smem, (size_t)48 * 1024);
+            if (gi) CUDA_TRY(cudaFuncSetAttribute(dmx_tile_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, want));
+            else CUDA_TRY(cudaFuncSetAttribute(dmx_tile_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, want));
+            configured[gi] = want;
         }
     }
-    dmx_tile_kernel<<<grid, threads, smem, st>>>(a);
+    if (gi) dmx_tile_kernel<2><<<grid, threads, smem, st>>>(a);
+    else dmx_tile_kernel<1><<<grid, threads, smem, st>>>(a);
     ++g_launches;
     CUDA_TRY(cudaGetLastError());
     return DMX_OK;
@@ -803,24 +859,39 @@ static int launch_tile(const TileArgs& a, int grid, int threads, size_t smem, cu
 
 enum OutMode { OUT_ENERGY = 1, OUT_PAULI = 2 };
 
+static void tile_geometry(unsigned elems, int* threads, int* gpt) {
+    const unsigned ng = elems >> 4;
+    if (ng > 512) { *threads = 512; *gpt = 2; }
+    else if (ng > 256) { *threads = 512; *gpt = 1; }
+    else { *threads = 256; *gpt = 1; }
+}
+
+static void fill_common(TileArgs& a, Plan& p, DevPlan* d, const Pass& ps, const double* params, const uint8_t* variants) {
+    a.sweeps = d->sweeps; a.mus = d->mus; a.chains = d->chains; a.factors = d->factors; a.phases = d->phases;
+    a.first_phase = ps.first_phase; a.n_phases = ps.n_phases; a.max_chains = pass_max_chains(p, ps);
+    a.coefs = d->coefs; a.rots = d->rots; a.params = params; a.n_params = p.n_params; a.variants = variants; a.n_slots = p.n_slots;
+    a.n = p.n;
+}
+
 // Whole-state-in-smem execution (n <= 7).  worklist != nullptr: run only the listed circuits (energy only).
 static int run_tile_single(Plan& p, DevPlan* d, long long batch, const double* params, const uint8_t* variants, double* out,
                            int mode, const int* worklist, const int* work_count, cudaStream_t st) {
     const Pass& ps = p.passes[0];
     TileArgs a{};
-    a.ops = d->ops; a.n_ops = ps.n_ops; a.coefs = d->coefs; a.rots = d->rots; a.pass_rots = d->pass_rots;
-    a.n_rots = (int)ps.rot_ids.size(); a.params = params; a.n_params = p.n_params; a.variants = variants; a.n_slots = p.n_slots;
-    a.n = p.n; a.k = p.n; a.cpb = tile_cpb(p.n); a.batch = batch; a.worklist = worklist; a.work_count = work_count;
+    fill_common(a, p, d, ps, params, variants);
+    a.pad = p.n == 1 ? 2 : 0;
+    a.k = p.n; a.cpb = p.cpb; a.batch = batch; a.worklist = worklist; a.work_count = work_count;
     a.epilogue = mode; a.term_idx = d->term_idx; a.term_coef = d->term_coef; a.n_terms = (int)p.term_idx.size(); a.out = out;
-    const unsigned E = (unsigned)a.cpb << (2 * p.n);
-    const int threads = tile_threads(E);
-    const size_t smem = tile_smem(p.n, a.cpb, a.n_rots);
-    if (smem > 227 * 1024) return fail(DMX_ERR_UNSUPPORTED, "tile does not fit shared memory (too many rotations in one pass)");
+    const unsigned E = (unsigned)a.cpb << (2 * p.n + a.pad);
+    int threads, gpt;
+    tile_geometry(E, &threads, &gpt);
+    const size_t smem = (size_t)E * 8 + (size_t)a.cpb * a.max_chains * 128;
+    if (smem > 227 * 1024) return fail(DMX_ERR_UNSUPPORTED, "tile does not fit shared memory");
     long long groups = (batch + a.cpb - 1) / a.cpb;
     int per_sm = (int)std::max<size_t>(1, std::min<size_t>(2048 / threads, (227 * 1024) / std::max<size_t>(smem, 1)));
     long long cap = (long long)d->sm_count * per_sm;
     int grid = (int)std::max<long long>(1, std::min(groups, cap));
-    return launch_tile(a, grid, threads, smem, st);
+    return launch_tile(a, grid, threads, gpt, smem, st);
 }
 
 // Streaming execution (n > tile_k): state[chunk][4^n] in `state`; all passes over one chunk of circuits.
@@ -829,10 +900,8 @@ static int run_streaming(Plan& p, DevPlan* d, long long chunk, long long circuit
     for (size_t pi = 0; pi < p.passes.size(); ++pi) {
         const Pass& ps = p.passes[pi];
         TileArgs a{};
-        a.ops = d->ops + ps.first_op; a.n_ops = ps.n_ops; a.coefs = d->coefs; a.rots = d->rots;
-        a.pass_rots = d->pass_rots + d->pass_rot_off[pi]; a.n_rots = (int)ps.rot_ids.size();
-        a.params = params; a.n_params = p.n_params; a.variants = variants; a.n_slots = p.n_slots;
-        a.n = p.n; a.k = (int)ps.tile_q.size(); a.cpb = 1; a.batch = chunk; a.state = state; a.circuit_offset = circuit_offset;
+        fill_common(a, p, d, ps, params, variants);
+        a.k = (int)ps.tile_q.size(); a.cpb = 1; a.pad = 0; a.batch = chunk; a.state = state; a.circuit_offset = circuit_offset;
         a.load = pi > 0; a.store = 1;
         std::vector<int> others;
         {
@@ -845,12 +914,13 @@ static int run_streaming(Plan& p, DevPlan* d, long long chunk, long long circuit
             make_runs(others, p.n, a.oruns, &a.n_oruns);
         } catch (const std::exception& e) { return fail(DMX_ERR_UNSUPPORTED, e.what()); }
         const unsigned E = 1u << (2 * a.k);
-        const int threads = tile_threads(E);
-        const size_t smem = tile_smem(a.k, 1, a.n_rots);
+        int threads, gpt;
+        tile_geometry(E, &threads, &gpt);
+        const size_t smem = (size_t)E * 8 + (size_t)a.max_chains * 128;
         if (smem > 227 * 1024) return fail(DMX_ERR_UNSUPPORTED, "tile does not fit shared memory");
         long long groups = chunk << (2 * (p.n - a.k));
         int grid = (int)std::min<long long>(groups, 1LL << 30);
-        int rc = launch_tile(a, grid, threads, smem, st);
+        int rc = launch_tile(a, grid, threads, gpt, smem, st);
         if (rc) return rc;
     }
     return DMX_OK;

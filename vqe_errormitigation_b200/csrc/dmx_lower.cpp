@@ -481,94 +481,308 @@ static void mono_tables(const std::vector<double>& M, int dim, std::vector<doubl
             }
 }
 
-static DevOp emit_block(Plan& p, CoefCache& cc, const Block& b, const std::vector<int>& local_pos, int rot_ord) {
-    DevOp d{};
-    d.p0 = local_pos[b.q[0]];
-    d.p1 = b.nq == 2 ? local_pos[b.q[1]] : 0;
-    const int dim = b.dim();
-    if (b.kind == BK_FIXED) {
-        if (b.cls == CLS_DIAG || b.cls == CLS_IDENT) {
-            std::vector<double> dg(dim);
-            for (int i = 0; i < dim; ++i) dg[i] = b.M[i * dim + i];
-            d.kind = b.nq == 1 ? DK_DIAG1 : DK_DIAG2;
-            d.coef = cc.get(p, dg);
-        } else if (b.cls == CLS_MONO) {
-            std::vector<double> sc;
-            uint64_t packed;
-            mono_tables(b.M, dim, sc, packed);
-            d.kind = b.nq == 1 ? DK_MONO1 : DK_MONO2;
-            d.coef = cc.get(p, sc);
-            d.a0 = (int32_t)(packed & 0xffffffffu);
-            d.a1 = (int32_t)(packed >> 32);
-        } else {
-            d.kind = b.nq == 1 ? DK_MAT1 : DK_MAT2;
-            d.coef = cc.get(p, b.M);
-        }
-    } else if (b.kind == BK_ROT) {
-        std::vector<double> acs;
-        acs.insert(acs.end(), b.A.begin(), b.A.end());
-        acs.insert(acs.end(), b.C.begin(), b.C.end());
-        acs.insert(acs.end(), b.S.begin(), b.S.end());
-        d.kind = DK_ROT1;
-        d.coef = cc.get(p, acs);
-        d.a0 = rot_ord;
-        d.a2 = b.rot_id;
-    } else {
-        d.a0 = b.slot;
-        if (b.nq == 1) {
-            // T[idx] = cond * B_idx, T[0] unused (identity correction is skipped)
-            std::vector<double> T(16 * 16);
-            for (int k = 0; k < 16; ++k) {
-                std::vector<double> Bk(b.tab.begin() + 16 * k, b.tab.begin() + 16 * (k + 1));
-                auto t = matmul(b.cond, Bk, 4);
-                std::copy(t.begin(), t.end(), T.begin() + 16 * k);
+static bool is_unital3(const std::vector<double>& m) {
+    if (m[0] != 1.0) return false;
+    for (int j = 1; j < 4; ++j) if (m[j] != 0.0 || m[4 * j] != 0.0) return false;
+    return true;
+}
+
+static int plan_cpb(int n) {
+    if (n >= 6) return 1;
+    int cpb = 1;
+    while ((cpb << (2 * n)) < 4096 && cpb < 16) cpb <<= 1;
+    return cpb;
+}
+
+// Builds the sweeps of one pass from its blocks (`order`: block ids in a valid order).  Blocks are re-ordered
+// within the pass (they only need to respect the per-qubit program order) so that a sweep over a qubit pair
+// collects as many blocks as possible.
+struct SweepBuilder {
+    Plan& p;
+    CoefCache& cc;
+    const std::vector<int>& local_pos;
+    const std::vector<int>& tile_q;
+    int chain_cap;
+    Phase phase{};
+    double flops = 0.0, sweeps_elems = 0.0;
+
+    SweepBuilder(Plan& plan, CoefCache& cache, const std::vector<int>& lp, const std::vector<int>& tq)
+        : p(plan), cc(cache), local_pos(lp), tile_q(tq) {
+        chain_cap = std::max(8, 128 / p.cpb);
+        phase.first_sweep = (int)p.sweeps.size();
+        phase.first_chain = (int)p.chains.size();
+    }
+
+    // ---- one open sweep ----
+    int qa = -1, qb = -1;
+    std::vector<MicroOp> mus;
+    std::vector<ChainDev> new_chains;
+    std::vector<ChainFactor> new_factors;
+    std::vector<int> pendA, pendB;   // pending 1-qubit blocks per side
+    SweepDev sw{};
+    bool open = false;
+
+    void start(int a, int b) {
+        qa = a; qb = b; mus.clear(); new_chains.clear(); new_factors.clear(); pendA.clear(); pendB.clear();
+        sw = SweepDev{};
+        open = true;
+    }
+
+    static MicroOp mu(int kind, int a0 = 0, int a1 = 0, int a2 = 0, int a3 = 0) {
+        MicroOp m{};
+        m.kind = kind; m.a0 = a0; m.a1 = a1; m.a2 = a2; m.a3 = a3;
+        return m;
+    }
+
+    void flush_side(std::vector<int>& pend, bool sideA) {
+        if (pend.empty()) return;
+        // split at variant blocks; runs of FIXED/ROT blocks become one chain (or a fixed matrix)
+        size_t i = 0;
+        while (i < pend.size()) {
+            const Block& b0 = p.blocks[pend[i]];
+            if (b0.kind == BK_VAR) {
+                std::vector<double> T(16 * 16);
+                for (int k = 0; k < 16; ++k) {
+                    std::vector<double> Bk(b0.tab.begin() + 16 * k, b0.tab.begin() + 16 * (k + 1));
+                    auto t = matmul(b0.cond, Bk, 4);
+                    std::copy(t.begin(), t.end(), T.begin() + 16 * k);
+                }
+                mus.push_back(mu(sideA ? MU_VAR_A : MU_VAR_B, b0.slot, cc.get(p, T)));
+                ++i;
+                continue;
             }
-            d.kind = DK_VAR1;
-            d.coef = cc.get(p, T);
-        } else {
-            d.kind = DK_VAR2;
-            d.coef = cc.get(p, b.tab);
+            size_t j = i;
+            bool any_rot = false;
+            while (j < pend.size() && p.blocks[pend[j]].kind != BK_VAR) { any_rot |= p.blocks[pend[j]].kind == BK_ROT; ++j; }
+            if (!any_rot) {
+                std::vector<double> M = identity(4);
+                for (size_t t = i; t < j; ++t) M = matmul(p.blocks[pend[t]].M, M, 4);
+                int cls = classify(M, 4);
+                if (cls == CLS_DIAG || cls == CLS_IDENT) {
+                    std::vector<double> dg = {M[0], M[5], M[10], M[15]};
+                    if (cls != CLS_IDENT) mus.push_back(mu(sideA ? MU_DIAG_A : MU_DIAG_B, cc.get(p, dg)));
+                } else {
+                    mus.push_back(mu(sideA ? MU_FIX_A : MU_FIX_B, cc.get(p, M), 0, 0, is_unital3(M)));
+                }
+            } else {
+                ChainDev ch{(int)new_factors.size(), 0};
+                bool unital = true;
+                for (size_t t = i; t < j; ++t) {
+                    const Block& b = p.blocks[pend[t]];
+                    ChainFactor f{};
+                    if (b.kind == BK_ROT) {
+                        std::vector<double> acs;
+                        acs.insert(acs.end(), b.A.begin(), b.A.end());
+                        acs.insert(acs.end(), b.C.begin(), b.C.end());
+                        acs.insert(acs.end(), b.S.begin(), b.S.end());
+                        f.kind = 1; f.coef = cc.get(p, acs); f.rot_id = b.rot_id;
+                        unital = unital && is_unital3(b.A);
+                        for (int e = 0; e < 4; ++e)
+                            if (b.C[e] != 0.0 || b.S[e] != 0.0 || b.C[4 * e] != 0.0 || b.S[4 * e] != 0.0) unital = false;
+                    } else {
+                        f.kind = 0; f.coef = cc.get(p, b.M); f.rot_id = -1;
+                        unital = unital && is_unital3(b.M);
+                    }
+                    new_factors.push_back(f);
+                    ++ch.n_factors;
+                }
+                mus.push_back(mu(sideA ? MU_CHAIN_A : MU_CHAIN_B, (int)new_chains.size(), 0, 0, unital));
+                new_chains.push_back(ch);
+            }
+            i = j;
+        }
+        pend.clear();
+    }
+
+    std::vector<double> oriented(const Block& b) const {   // 16x16 of a 2q block in (qa,qb) order
+        return (b.q[0] == qa) ? b.M : swap_qubits(b.M);
+    }
+
+    void add_two_qubit(const Block& b) {
+        flush_side(pendA, true);
+        flush_side(pendB, false);
+        if (b.kind == BK_VAR) {
+            // variant tables are in the block's own (q0,q1) order: the sweep is oriented accordingly by the caller
             std::vector<double> cond = b.cond;
             int cls = classify(cond, 16);
-            d.a2 = cls;
+            MicroOp m = mu(MU_VAR2, b.slot, cc.get(p, b.tab));
             if (cls == CLS_DIAG || cls == CLS_IDENT) {
                 std::vector<double> dg(16);
                 for (int i = 0; i < 16; ++i) dg[i] = cond[i * 16 + i];
-                d.a1 = cc.get(p, dg);
-                d.a2 = CLS_DIAG;
+                m.a2 = cc.get(p, dg); m.a3 = CLS_DIAG;
             } else {
-                d.a1 = cc.get(p, cond);
-                d.a2 = CLS_DENSE;
+                m.a2 = cc.get(p, cond); m.a3 = CLS_DENSE;
             }
+            mus.push_back(m);
+            return;
+        }
+        std::vector<double> M = oriented(b);
+        int cls = classify(M, 16);
+        if (cls == CLS_DIAG || cls == CLS_IDENT) {
+            std::vector<double> dg(16);
+            for (int i = 0; i < 16; ++i) dg[i] = M[i * 16 + i];
+            mus.push_back(mu(MU_DIAG2, cc.get(p, dg)));
+        } else {
+            mus.push_back(mu(MU_MAT2, cc.get(p, M)));
         }
     }
-    return d;
-}
 
-// flops / smem bytes actually executed per element for one block (tile kernel)
-static double block_flops_per_elem(const Block& b) {
-    if (b.kind == BK_FIXED) {
-        if (b.cls == CLS_DIAG || b.cls == CLS_MONO) return 1.0;
-        return b.nq == 1 ? 7.0 : 31.0;
+    void set_perm(const Block& b, bool at_load) {
+        std::vector<double> M = oriented(b), sc;
+        classify(M, 16);
+        uint64_t packed;
+        mono_tables(M, 16, sc, packed);   // out[a] = sc[a] * in[src[a]]
+        if (at_load) {
+            sw.load_perm = 1; sw.lcoef = cc.get(p, sc);
+            sw.lsrc_lo = (uint32_t)(packed & 0xffffffffu); sw.lsrc_hi = (uint32_t)(packed >> 32);
+        } else {
+            uint64_t dst = 0;
+            for (int a = 0; a < 16; ++a) { uint64_t src = (packed >> (4 * a)) & 15u; dst |= (uint64_t)a << (4 * src); }
+            sw.store_perm = 1; sw.scoef = cc.get(p, sc);
+            sw.sdst_lo = (uint32_t)(dst & 0xffffffffu); sw.sdst_hi = (uint32_t)(dst >> 32);
+        }
     }
-    if (b.kind == BK_ROT) return 7.0 + 8.0;
-    return 0.0;
-}
+
+    void close() {
+        if (!open) return;
+        flush_side(pendA, true);
+        flush_side(pendB, false);
+        open = false;
+        if (mus.empty() && !sw.load_perm && !sw.store_perm) return;
+        if ((int)(p.chains.size() - phase.first_chain + new_chains.size()) > chain_cap && p.sweeps.size() > (size_t)phase.first_sweep) end_phase();
+        const int chain_base = (int)p.chains.size() - phase.first_chain;
+        const int factor_base = (int)p.factors.size();
+        for (ChainDev ch : new_chains) { ch.first_factor += factor_base; p.chains.push_back(ch); }
+        p.factors.insert(p.factors.end(), new_factors.begin(), new_factors.end());
+        for (MicroOp& m : mus)
+            if (m.kind == MU_CHAIN_A || m.kind == MU_CHAIN_B) m.a0 += chain_base;
+        sw.p0 = local_pos[qa]; sw.p1 = local_pos[qb];
+        sw.first_mu = (int)p.mus.size(); sw.n_mu = (int)mus.size();
+        p.mus.insert(p.mus.end(), mus.begin(), mus.end());
+        p.sweeps.push_back(sw);
+        // cost model (per element of the state): one smem read + write; flops by micro-op
+        sweeps_elems += 1.0;
+        for (const MicroOp& m : mus) {
+            switch (m.kind) {
+                case MU_CHAIN_A: case MU_CHAIN_B: case MU_FIX_A: case MU_FIX_B: flops += m.a3 ? 15.0 / 4 : 28.0 / 4; break;
+                case MU_DIAG_A: case MU_DIAG_B: case MU_DIAG2: flops += 1.0; break;
+                case MU_MAT2: flops += 31.0; break;
+                default: break;
+            }
+        }
+        flops += (sw.load_perm ? 1.0 : 0.0) + (sw.store_perm ? 1.0 : 0.0);
+    }
+
+    void end_phase() {
+        phase.n_sweeps = (int)p.sweeps.size() - phase.first_sweep;
+        phase.n_chains = (int)p.chains.size() - phase.first_chain;
+        if (phase.n_sweeps > 0) p.phases.push_back(phase);
+        phase.first_sweep = (int)p.sweeps.size();
+        phase.first_chain = (int)p.chains.size();
+    }
+
+    void run(const std::vector<int>& order) {
+        const int n = std::max(p.n, 2);
+        std::vector<std::vector<int>> qq(n);
+        std::vector<size_t> head(n, 0);
+        for (int bi : order) {
+            qq[p.blocks[bi].q[0]].push_back(bi);
+            if (p.blocks[bi].nq == 2) qq[p.blocks[bi].q[1]].push_back(bi);
+        }
+        auto front = [&](int q) { return head[q] < qq[q].size() ? qq[q][head[q]] : -1; };
+        auto ready = [&](int bi) {
+            const Block& b = p.blocks[bi];
+            for (int s = 0; s < b.nq; ++s) if (front(b.q[s]) != bi) return false;
+            return true;
+        };
+        auto pop = [&](int bi) {
+            const Block& b = p.blocks[bi];
+            for (int s = 0; s < b.nq; ++s) ++head[b.q[s]];
+        };
+        size_t remaining = order.size();
+        while (remaining > 0) {
+            // earliest ready block opens the sweep
+            int b0 = -1;
+            for (int q = 0; q < n; ++q) { int f = front(q); if (f >= 0 && ready(f) && (b0 < 0 || f < b0)) b0 = f; }
+            if (b0 < 0) throw std::runtime_error("sweep builder: no ready block");
+            const Block& first = p.blocks[b0];
+            int a = first.q[0], b = first.nq == 2 ? first.q[1] : -1;
+            if (b < 0) {
+                // partner: the other qubit of the next two-qubit block on this qubit's queue (if resident), else a neighbour
+                for (size_t t = head[a]; t < qq[a].size() && b < 0; ++t) {
+                    const Block& nb = p.blocks[qq[a][t]];
+                    if (nb.nq == 2) b = nb.q[0] == a ? nb.q[1] : nb.q[0];
+                }
+                if (b < 0)
+                    for (int q : tile_q) if (q != a) { b = q; if (q > a) break; }
+                if (b < 0) throw std::runtime_error("sweep builder: single-qubit tile");
+            }
+            start(a, b);
+            bool closed = false;
+            while (!closed) {
+                bool progress = false;
+                // 1) every ready one-qubit block on either side
+                for (int side = 0; side < 2; ++side) {
+                    int q = side == 0 ? qa : qb;
+                    while (true) {
+                        int f = front(q);
+                        if (f < 0 || p.blocks[f].nq != 1) break;
+                        (side == 0 ? pendA : pendB).push_back(f);
+                        pop(f); --remaining; progress = true;
+                    }
+                }
+                // 2) a ready two-qubit block on exactly this pair
+                int f = front(qa);
+                if (f >= 0 && p.blocks[f].nq == 2 && ready(f)) {
+                    const Block& blk = p.blocks[f];
+                    bool same_pair = (blk.q[0] == qa && blk.q[1] == qb) || (blk.q[0] == qb && blk.q[1] == qa);
+                    if (same_pair) {
+                        bool mono = blk.kind == BK_FIXED && blk.cls == CLS_MONO;
+                        if (blk.kind == BK_VAR && blk.q[0] != qa) {
+                            // variant tables are oriented (q0,q1): only usable when the sweep has the same orientation
+                            if (mus.empty() && pendA.empty() && pendB.empty() && !sw.load_perm) { std::swap(qa, qb); }
+                            else { close(); closed = true; continue; }
+                        }
+                        if (mono) {
+                            bool empty = mus.empty() && pendA.empty() && pendB.empty() && !sw.load_perm;
+                            if (empty) { set_perm(blk, true); pop(f); --remaining; progress = true; }
+                            else { flush_side(pendA, true); flush_side(pendB, false); set_perm(blk, false); pop(f); --remaining; close(); closed = true; continue; }
+                        } else {
+                            add_two_qubit(blk);
+                            pop(f); --remaining; progress = true;
+                        }
+                    }
+                }
+                if (!progress) { close(); closed = true; }
+            }
+        }
+        close();
+        end_phase();
+    }
+};
 
 static void schedule_single_pass(Plan& p) {
     CoefCache cc;
     std::vector<int> local_pos(p.n);
     Pass pass;
+    std::vector<int> order;
     for (int q = 0; q < p.n; ++q) { pass.tile_q.push_back(q); local_pos[q] = code_pos(p.n, q); }
-    pass.first_op = 0;
-    for (const Block& b : p.blocks) {
-        int ord = -1;
-        if (b.kind == BK_ROT) { ord = (int)pass.rot_ids.size(); pass.rot_ids.push_back(b.rot_id); }
-        p.dev_ops.push_back(emit_block(p, cc, b, local_pos, ord));
+    for (size_t i = 0; i < p.blocks.size(); ++i) order.push_back((int)i);
+    pass.first_phase = (int)p.phases.size();
+    if (p.n == 1) {
+        // a single qubit has no pair: the tile gets a virtual idle qubit below it (tile index = code << 2);
+        // the execution layer runs such plans with k = 2 and reads / writes the coefficients at stride 4
+        local_pos[0] = 2;
+        local_pos.push_back(0);
+        pass.tile_q.push_back(1);
     }
-    pass.n_ops = (int)p.dev_ops.size();
+    SweepBuilder sb(p, cc, local_pos, pass.tile_q);
+    sb.run(order);
+    pass.n_phases = (int)p.phases.size() - pass.first_phase;
     p.passes.push_back(pass);
     p.tile_k = p.n;
+    p.info.flops_per_circuit = sb.flops * std::pow(4.0, p.n);
+    p.info.smem_bytes_per_circuit = sb.sweeps_elems * 16.0 * std::pow(4.0, p.n);
 }
 
 // DAG-greedy pass builder for n > tile_k: the two lowest qubits stay resident (128-byte runs in HBM),
@@ -578,8 +792,6 @@ static void schedule_streaming(Plan& p) {
     p.tile_k = k;
     CoefCache cc;
     const size_t nb = p.blocks.size();
-    std::vector<char> done(nb, 0);
-    // per-qubit ordered list of blocks
     std::vector<std::vector<int>> chain(n);
     for (size_t i = 0; i < nb; ++i) {
         chain[p.blocks[i].q[0]].push_back((int)i);
@@ -587,6 +799,7 @@ static void schedule_streaming(Plan& p) {
     }
     std::vector<size_t> head(n, 0);
     size_t remaining = nb;
+    double flops = 0.0, sweeps = 0.0;
     while (remaining > 0) {
         std::vector<char> in_tile(n, 0);
         int count = 0;
@@ -616,7 +829,6 @@ static void schedule_streaming(Plan& p) {
                 if (!in_tile[b.q[s]]) { in_tile[b.q[s]] = 1; ++count; }
                 ++head[b.q[s]];
             }
-            done[best] = 1;
             --remaining;
             order.push_back(best);
         }
@@ -627,16 +839,16 @@ static void schedule_streaming(Plan& p) {
         std::vector<int> local_pos(n, -1);
         for (int q = 0; q < n; ++q) if (in_tile[q]) pass.tile_q.push_back(q);
         for (size_t i = 0; i < pass.tile_q.size(); ++i) local_pos[pass.tile_q[i]] = 2 * ((int)pass.tile_q.size() - 1 - (int)i);
-        pass.first_op = (int)p.dev_ops.size();
-        for (int bi : order) {
-            const Block& b = p.blocks[bi];
-            int ord = -1;
-            if (b.kind == BK_ROT) { ord = (int)pass.rot_ids.size(); pass.rot_ids.push_back(b.rot_id); }
-            p.dev_ops.push_back(emit_block(p, cc, b, local_pos, ord));
-        }
-        pass.n_ops = (int)p.dev_ops.size() - pass.first_op;
+        pass.first_phase = (int)p.phases.size();
+        SweepBuilder sb(p, cc, local_pos, pass.tile_q);
+        sb.run(order);
+        pass.n_phases = (int)p.phases.size() - pass.first_phase;
+        flops += sb.flops;
+        sweeps += sb.sweeps_elems;
         p.passes.push_back(std::move(pass));
     }
+    p.info.flops_per_circuit = flops * std::pow(4.0, n);
+    p.info.smem_bytes_per_circuit = sweeps * 16.0 * std::pow(4.0, n);
 }
 
 // ---- segment tables (path 1) --------------------------------------------------------------------------
@@ -1002,7 +1214,9 @@ static bool build_frame(Plan& p, std::string& why) {
 
 void lower_plan(Plan& p) {
     if (p.n < 1 || p.n > DMX_MAX_QUBITS) throw std::runtime_error("n_qubits out of range");
-    p.blocks.clear(); p.rots.clear(); p.dev_ops.clear(); p.coefs.clear(); p.passes.clear();
+    p.blocks.clear(); p.rots.clear(); p.mus.clear(); p.sweeps.clear(); p.factors.clear(); p.chains.clear(); p.phases.clear();
+    p.coefs.clear(); p.passes.clear();
+    p.cpb = plan_cpb(p.n);
     p.segs.clear(); p.slots.clear(); p.term_idx.clear(); p.term_coef.clear();
     std::memset(&p.info, 0, sizeof(p.info));
     lower_ops(p);
@@ -1025,6 +1239,7 @@ void lower_plan(Plan& p) {
         for (uint32_t idx : order) { p.term_idx.push_back(idx); p.term_coef.push_back(acc[idx]); }
     }
     if (p.n <= 7) schedule_single_pass(p); else schedule_streaming(p);
+    const double tile_flops = p.info.flops_per_circuit, tile_smem = p.info.smem_bytes_per_circuit;
     p.path = p.n <= 7 ? 0 : 2;
     p.seg_eligible = false;
     if (p.opt_segments && p.n <= SEG_N) {
@@ -1054,10 +1269,8 @@ void lower_plan(Plan& p) {
         in.smem_bytes_per_circuit = smem_segs * SEG_E * 16.0 + 16.0 * p.e_w.size();
         in.hbm_bytes_per_circuit = io;
     } else {
-        double fl = 0;
-        for (const Block& b : p.blocks) fl += block_flops_per_elem(b) * N;
-        in.flops_per_circuit = fl + 2.0 * p.term_idx.size();
-        in.smem_bytes_per_circuit = 16.0 * N * p.blocks.size();
+        in.flops_per_circuit = tile_flops + 2.0 * p.term_idx.size();
+        in.smem_bytes_per_circuit = tile_smem;
         // streaming: every pass reads and writes the state once, except the first (init in smem, no read)
         in.hbm_bytes_per_circuit = io + (p.path == 2 ? (2.0 * p.passes.size() - 1.0) * 8.0 * N : 0.0);
     }
@@ -1090,7 +1303,7 @@ static void dump_ints(std::ostringstream& os, const char* name, const std::vecto
 std::string dump_plan(const Plan& p) {
     std::ostringstream os;
     os << "plan n=" << p.n << " params=" << p.n_params << " slots=" << p.n_slots << " path=" << p.path
-       << " tile_k=" << p.tile_k << " blocks=" << p.blocks.size() << " passes=" << p.passes.size()
+       << " tile_k=" << p.tile_k << " cpb=" << p.cpb << " blocks=" << p.blocks.size() << " passes=" << p.passes.size()
        << " nseg=" << (p.seg_eligible ? p.nseg : 0) << " seg_reason=\"" << p.seg_reason << "\"\n";
     for (size_t i = 0; i < p.blocks.size(); ++i) {
         const Block& b = p.blocks[i];
@@ -1107,16 +1320,26 @@ std::string dump_plan(const Plan& p) {
     }
     for (size_t i = 0; i < p.passes.size(); ++i) {
         const Pass& ps = p.passes[i];
-        os << "pass " << i << " first=" << ps.first_op << " nops=" << ps.n_ops;
+        os << "pass " << i << " first_phase=" << ps.first_phase << " nphases=" << ps.n_phases;
         dump_ints(os, "tile", ps.tile_q);
-        dump_ints(os, "rots", ps.rot_ids);
         os << "\n";
     }
-    for (size_t i = 0; i < p.dev_ops.size(); ++i) {
-        const DevOp& d = p.dev_ops[i];
-        os << "devop " << i << " kind=" << d.kind << " p0=" << d.p0 << " p1=" << d.p1 << " coef=" << d.coef
-           << " a0=" << d.a0 << " a1=" << d.a1 << " a2=" << d.a2 << "\n";
+    for (size_t i = 0; i < p.phases.size(); ++i)
+        os << "phase " << i << " first_sweep=" << p.phases[i].first_sweep << " nsweeps=" << p.phases[i].n_sweeps
+           << " first_chain=" << p.phases[i].first_chain << " nchains=" << p.phases[i].n_chains << "\n";
+    for (size_t i = 0; i < p.sweeps.size(); ++i) {
+        const SweepDev& w = p.sweeps[i];
+        os << "sweep " << i << " p0=" << w.p0 << " p1=" << w.p1 << " first_mu=" << w.first_mu << " nmu=" << w.n_mu
+           << " lperm=" << w.load_perm << " lcoef=" << w.lcoef << " lsrc=" << (((unsigned long long)w.lsrc_hi << 32) | w.lsrc_lo)
+           << " sperm=" << w.store_perm << " scoef=" << w.scoef << " sdst=" << (((unsigned long long)w.sdst_hi << 32) | w.sdst_lo) << "\n";
     }
+    for (size_t i = 0; i < p.mus.size(); ++i)
+        os << "mu " << i << " kind=" << p.mus[i].kind << " a0=" << p.mus[i].a0 << " a1=" << p.mus[i].a1 << " a2=" << p.mus[i].a2
+           << " a3=" << p.mus[i].a3 << "\n";
+    for (size_t i = 0; i < p.chains.size(); ++i)
+        os << "chain " << i << " first=" << p.chains[i].first_factor << " n=" << p.chains[i].n_factors << "\n";
+    for (size_t i = 0; i < p.factors.size(); ++i)
+        os << "factor " << i << " kind=" << p.factors[i].kind << " coef=" << p.factors[i].coef << " rot=" << p.factors[i].rot_id << "\n";
     dump_vec(os, "coefs", p.coefs);
     os << "\n";
     {

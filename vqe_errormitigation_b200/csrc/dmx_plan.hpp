@@ -48,20 +48,51 @@ struct Block {
 
 // ---- device-facing tables -------------------------------------------------------------------------
 
-enum DevKind : int32_t {
-    DK_DIAG1 = 0, DK_MONO1 = 1, DK_MAT1 = 2, DK_ROT1 = 3,
-    DK_DIAG2 = 4, DK_MONO2 = 5, DK_MAT2 = 6,
-    DK_VAR1 = 7, DK_VAR2 = 8
+// A tile pass is executed as a list of SWEEPS.  One sweep walks the tile once: every thread loads a group of 16
+// coefficients (all codes of a qubit pair (A,B), the other codes fixed) into registers, applies a list of
+// micro-ops to it and stores it back — so several fused blocks cost ONE shared-memory round trip.  A monomial
+// two-qubit block (Clifford gate x Pauli noise) at the start / end of a sweep is folded into the load / store
+// addressing (permutation) plus 16 scales.
+enum MuKind : int32_t {
+    MU_CHAIN_A = 0, MU_CHAIN_B = 1,  // per-circuit 4x4 from the chain table (product of rotations / fixed 1q blocks)
+    MU_FIX_A = 2, MU_FIX_B = 3,      // fixed 4x4 from the coefficient table
+    MU_DIAG_A = 4, MU_DIAG_B = 5,    // 4 scales
+    MU_DIAG2 = 6,                    // 16 scales
+    MU_MAT2 = 7,                     // dense 16x16
+    MU_VAR_A = 8, MU_VAR_B = 9,      // variant slot on one qubit: 16 precomposed 4x4 (noise-after-correction included)
+    MU_VAR2 = 10                     // variant slot on the pair: kron(B[a], B[b]) then the conditional block
 };
 
-struct DevOp {        // 32 bytes, read through the constant/L1 path by every thread
+struct MicroOp {      // 32 bytes
     int32_t kind;
-    int32_t p0, p1;   // tile-local bit position of the code of q0 / q1 (p1 unused for 1q)
-    int32_t coef;     // offset into the coefficient table (doubles)
-    int32_t a0;       // MONO1/2: packed source codes (low word); ROT1: rot ordinal in pass; VAR: slot
-    int32_t a1;       // MONO2: packed source codes (high word); VAR: offset of cond coefficients
-    int32_t a2;       // VAR: cond class (MatClass); ROT1: rot_id (global)
-    int32_t a3;       // reserved
+    int32_t a0;       // CHAIN: slot in the phase's chain table; FIX/DIAG/MAT2: coefficient offset; VAR: variant slot
+    int32_t a1;       // VAR: coefficient offset of the matrix table
+    int32_t a2;       // VAR2: coefficient offset of the conditional block
+    int32_t a3;       // VAR2: class of the conditional block (CLS_DIAG / CLS_DENSE); CHAIN/FIX: 1 = unital 3x3 form
+    int32_t pad[3];
+};
+
+struct SweepDev {     // 48 bytes
+    int32_t p0, p1;           // tile-local bit positions of the codes of qubit A and qubit B
+    int32_t first_mu, n_mu;
+    int32_t load_perm, lcoef; // load: v[a] = coef[lcoef + a] * tile[src code lsrc[a]]
+    int32_t store_perm, scoef;// store: tile[dst code sdst[b]] = coef[scoef + sdst[b]] * v[b]
+    uint32_t lsrc_lo, lsrc_hi, sdst_lo, sdst_hi;  // 16 x 4-bit codes
+};
+
+struct ChainFactor {  // one factor of a per-circuit 1-qubit matrix product (applied in order)
+    int32_t kind;     // 0: fixed (16 coefficients), 1: rotation (48 coefficients A, C, S)
+    int32_t coef;
+    int32_t rot_id;   // global rotation id (kind 1)
+    int32_t pad;
+};
+
+struct ChainDev {
+    int32_t first_factor, n_factors;
+};
+
+struct Phase {        // sweeps that share one chain table (bounded shared memory)
+    int32_t first_sweep, n_sweeps, first_chain, n_chains;
 };
 
 struct RotInfo {      // per global rotation id
@@ -70,10 +101,9 @@ struct RotInfo {      // per global rotation id
     double scale, offset;
 };
 
-struct Pass {         // one sweep over the state with `tile_q` resident
+struct Pass {         // one pass over the state with `tile_q` resident
     std::vector<int> tile_q;          // resident qubits, ascending qubit index
-    int first_op = 0, n_ops = 0;      // range in Plan::dev_ops
-    std::vector<int> rot_ids;         // rotations evaluated in this pass (ordinal = position)
+    int first_phase = 0, n_phases = 0;
 };
 
 // Segment kernel tables (n padded to 4 qubits: 256 elements).
@@ -115,7 +145,12 @@ struct Plan {
     // lowered program
     std::vector<Block> blocks;
     std::vector<RotInfo> rots;
-    std::vector<DevOp> dev_ops;
+    std::vector<MicroOp> mus;
+    std::vector<SweepDev> sweeps;
+    std::vector<ChainFactor> factors;
+    std::vector<ChainDev> chains;
+    std::vector<Phase> phases;
+    int cpb = 1;            // circuits per CTA when the whole state is resident (n <= 5)
     std::vector<double> coefs;
     std::vector<Pass> passes;
     int path = 0;           // 0 tile (single pass, state in smem), 1 segment, 2 streaming
