@@ -1,0 +1,67 @@
+"""Test double: runs a CircuitProgram's op table through the C oracle (oracle/dm_oracle.c) instead of the GPU.
+
+Used ONLY by CPU tests of the host logic (circuit construction, QP bookkeeping, optimiser drivers).  The product
+has no such path: without this monkeypatch every CircuitProgram method raises on a machine without CUDA."""
+from __future__ import annotations
+
+import numpy as np
+
+from oracle import c_oracle as CO
+from oracle import dm_oracle as O
+from vqe_errormitigation_b200 import engine
+
+
+def _batch(self, params, variants, batch):
+    sizes = set()
+    p = v = None
+    if params is not None and self.n_params:
+        p = np.ascontiguousarray(np.asarray(params, np.float64).reshape(-1, self.n_params))
+        sizes.add(p.shape[0])
+    if variants is not None:
+        v = np.ascontiguousarray(np.asarray(variants, np.uint8).reshape(-1, self.n_slots))
+        sizes.add(v.shape[0])
+    if batch is not None:
+        sizes.add(batch)
+    if not sizes:
+        sizes = {1}
+    assert len(sizes) == 1
+    return p, v, sizes.pop()
+
+
+def _energies_host(self, params=None, variants=None, batch=None):
+    p, v, B = _batch(self, params, variants, batch)
+    return CO.energy_batch(self.n_qubits, self.ops, self.pool, self.hamiltonian, params=p, variants=v, batch=B,
+                           n_params=self.n_params, n_slots=self.n_slots, threads=2)
+
+
+def _density(self, params=None, variants=None, *, batch=None):
+    p, v, B = _batch(self, params, variants, batch)
+    return np.stack([CO.density(self.n_qubits, self.ops, self.pool, params=None if p is None else p[b],
+                                variants=None if v is None else v[b]) for b in range(B)])
+
+
+def _probabilities(self, params=None, variants=None, *, batch=None, renormalise=True, as_tensor=False):
+    rho = _density(self, params, variants, batch=batch)
+    return np.stack([O.probabilities(r, renormalise) for r in rho])
+
+
+class _FakeTensor:
+    def __init__(self, arr):
+        self._a = arr
+
+    def cpu(self):
+        return self
+
+    def numpy(self):
+        return self._a
+
+
+def _energies(self, params=None, variants=None, *, batch=None, out=None, workspace_states=None):
+    return _FakeTensor(_energies_host(self, params, variants, batch))
+
+
+def install(monkeypatch):
+    monkeypatch.setattr(engine.CircuitProgram, "energies_host", _energies_host)
+    monkeypatch.setattr(engine.CircuitProgram, "energies", _energies)
+    monkeypatch.setattr(engine.CircuitProgram, "density", _density)
+    monkeypatch.setattr(engine.CircuitProgram, "probabilities", _probabilities)

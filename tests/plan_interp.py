@@ -50,7 +50,10 @@ def parse(dump: str) -> dict:
         elif head == "phase":
             plan["phases"].append({k: int(kv[k]) for k in ("first_sweep", "nsweeps", "first_chain", "nchains")})
         elif head == "sweep":
-            plan["sweeps"].append({k: int(kv[k]) for k in ("p0", "p1", "first_mu", "nmu", "lperm", "lcoef", "lsrc", "sperm", "scoef", "sdst")})
+            sw = {k: int(kv[k]) for k in ("p0", "p1", "first_mu", "nmu", "lperm", "lcoef", "sperm", "scoef")}
+            sw["lmask"] = _nums(kv["lmask"], int)
+            sw["smask"] = _nums(kv["smask"], int)
+            plan["sweeps"].append(sw)
         elif head == "mu":
             plan["mus"].append({k: int(kv[k]) for k in ("kind", "a0", "a1", "a2", "a3")})
         elif head == "chain":
@@ -167,10 +170,23 @@ def run_devops(plan, params=None, variants=None) -> np.ndarray:
                 def at(code):
                     return clear | ((code >> 2) << g0) | ((code & 3) << g1)
 
+                # tile-local XOR masks -> global index masks (bit positions of the pair only)
+                def gmask(m):
+                    out = 0
+                    for lp, gp in ((sw["p0"], g0), (sw["p1"], g1)):
+                        out |= ((int(m) >> lp) & 3) << gp
+                    return out
+
+                def xor_index(masks):
+                    x = np.zeros_like(idx)
+                    for j in range(4):
+                        x ^= np.where((loc >> j) & 1, gmask(masks[j]), 0)
+                    return clear ^ x
+
                 if sw["lperm"]:
-                    src = np.array([(sw["lsrc"] >> (4 * int(e))) & 15 for e in range(16)])[loc]
-                    v = cf[sw["lcoef"] + loc] * r[at(src)]
+                    v = cf[sw["lcoef"] + loc] * r[xor_index(sw["lmask"])]
                 else:
+                    assert np.array_equal(xor_index(sw["lmask"]), idx)
                     v = r.copy()
 
                 def side(v, M, a_side, unital):
@@ -219,11 +235,11 @@ def run_devops(plan, params=None, variants=None) -> np.ndarray:
                             else:
                                 v = dense(v, cf[m["a2"]:m["a2"] + 256].reshape(16, 16))
                 if sw["sperm"]:
-                    dst = np.array([(sw["sdst"] >> (4 * int(e))) & 15 for e in range(16)])[loc]
                     out = np.zeros_like(v)
-                    out[at(dst)] = cf[sw["scoef"] + dst] * v
+                    out[xor_index(sw["smask"])] = cf[sw["scoef"] + loc] * v
                     r = out
                 else:
+                    assert np.array_equal(xor_index(sw["smask"]), idx)
                     r = v
     return r[np.arange(4 ** n) << pad]
 

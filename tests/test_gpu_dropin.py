@@ -1,0 +1,170 @@
+"""GPU tests of the reference-shaped call surface (QPU / CPU / IErrorMitigationManager / DensityMatrixSimulator /
+QP_QEM_lib) and of size-independent properties at BASELINE.json's full batch sizes."""
+import numpy as np
+import pytest
+
+from oracle import c_oracle as CO
+from oracle import dm_oracle as O
+from workloads import ALPHA_STAR, build_program, h2_golden, h2_ops, h2_terms
+from vqe_errormitigation_b200 import cirq_compat as cirq
+from vqe_errormitigation_b200 import qp_qem_lib as Q
+from vqe_errormitigation_b200.data_containers.helper_interfaces.i_noise_wrapper import INoiseModel, INoiseWrapper
+from vqe_errormitigation_b200.data_containers.model_hydrogen import HydrogenAnsatz
+from vqe_errormitigation_b200.error_mitigation import IErrorMitigationManager, SingleQubitPauliChannel, TwoQubitDepolarizingChannel, TwoQubitPauliChannel
+from vqe_errormitigation_b200.processors.processor_classic import CPU
+from vqe_errormitigation_b200.processors.processor_quantum import QPU
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-10
+
+
+def test_qpu_single_evaluation_and_simulator_facade():
+    w = HydrogenAnsatz()
+    n_w = INoiseWrapper(w, INoiseModel([cirq.depolarize(1e-3)], [TwoQubitDepolarizingChannel(1e-3)], "d"))
+    circuit = n_w.get_noisy_circuit()
+    for alpha, want in ((0.0, -1.0380841518615922), (ALPHA_STAR, -1.0559477031919418)):
+        got = QPU.get_simulated_noisy_expectation_value(n_w, circuit, cirq.ParamResolver({"alpha0": alpha}))
+        assert abs(got - want) < TOL
+    w.operator_parameters["alpha0"] = 0.2
+    resolved = QPU.get_resolved_circuit(circuit, w.operator_parameters)
+    rho = cirq.DensityMatrixSimulator().simulate(resolved).final_density_matrix
+    ref = O.simulate(4, O.from_circuit(resolved, w.qubits)[1])
+    assert rho.dtype == np.complex128 and np.max(np.abs(rho - ref)) < TOL
+    rho32 = cirq.DensityMatrixSimulator(dtype=np.complex64).simulate(resolved).final_density_matrix
+    assert rho32.dtype == np.complex64
+    # run(): terminal measurements, histogram of the first qubit
+    meas = resolved.copy()
+    meas.append(cirq.measure(w.qubits[0], key="M"))
+    np.random.seed(5)
+    res = cirq.DensityMatrixSimulator().run(meas, repetitions=20000)
+    p0 = O.probabilities(ref).reshape(2, 8).sum(axis=1)[0]
+    assert abs(res.histogram(key="M")[0] / 20000 - p0) < 5 * np.sqrt(p0 * (1 - p0) / 20000)
+
+
+def test_measure_observable_converges_to_exact_expectation():
+    """Sampled energy (5 circuits, shot histograms) -> infinite-shot value computed by the oracle on the same circuits."""
+    w = HydrogenAnsatz()
+    model = INoiseModel([cirq.depolarize(2e-3)], [TwoQubitDepolarizingChannel(2e-3)], "d")
+    n_w = INoiseWrapper(w, model)
+    w.operator_parameters["alpha0"] = ALPHA_STAR
+    base = QPU.get_resolved_circuit(n_w.get_noisy_circuit(), w.operator_parameters)
+    func, cost = n_w.observable_measurement()
+    assert cost == 5
+    np.random.seed(1)
+    shots = 200000
+    got = func(base, model.get_operators, shots)
+    # exact: Z/ZZ terms from the base circuit (+ identity gates with noise on every qubit), XXYY-type terms from rotated circuits
+    from vqe_errormitigation_b200.openfermion_compat import jordan_wigner
+    ham = jordan_wigner(w.molecule.get_molecular_hamiltonian())
+    exact = 0.0
+    basis = w.pauli_basis_map()
+    for term, coeff in ham.terms.items():
+        if len(term) == 0:
+            exact += coeff.real if hasattr(coeff, "real") else coeff
+            continue
+        c = base.copy()
+        if len(term) == 4:
+            c.append([(basis[p](w.qubits[q], 1), model.get_operators(w.qubits[q])) for q, p in term])
+        else:
+            for q in range(4):
+                c.append([cirq.I(w.qubits[q]), model.get_operators(w.qubits[q])])
+        rho = O.simulate(4, O.from_circuit(c, w.qubits)[1])
+        zmask = sum(1 << (3 - q) for q, _ in term)
+        par = np.array([bin(i & zmask).count("1") % 2 for i in range(16)])
+        exact += complex(coeff).real * float(np.sum(np.where(par == 0, 1, -1) * O.probabilities(rho)))
+    assert abs(got - exact) < 6 * 0.6 / np.sqrt(shots)
+
+
+def test_error_mitigation_manager_gpu_matches_oracle_values():
+    w = HydrogenAnsatz()
+    w.operator_parameters["alpha0"] = ALPHA_STAR
+    p = 1e-4
+    model = INoiseModel([SingleQubitPauliChannel(p, p, 6 * p)], [TwoQubitPauliChannel(p, p, 6 * p)], "asym")
+    n_w = INoiseWrapper(w, model)
+    clean = QPU.get_resolved_circuit(n_w.get_clean_circuit(), w.operator_parameters)
+    mgr = IErrorMitigationManager(clean, model, QPU.get_hamiltonian_objective_operator(w))
+    np.random.seed(7)
+    mgr.set_identifier_range(10000)
+    values, mu = mgr.get_mu_effective(error_mitigation=True, density_representation=True)
+    prog = mgr._variant_program()
+    assert prog.info["path"] == 1
+    want = CO.energy_batch(4, prog.ops, prog.pool, prog.hamiltonian, variants=mgr._rows, n_slots=prog.n_slots, threads=4)
+    signs, weights = mgr._signs_and_weights(mgr._rows)
+    ref_mu = float(np.sum(signs * np.prod(weights) * want * mgr._counts) / mgr._counts.sum())
+    assert abs(mu - ref_mu) < TOL and len(values) == 10000
+    fci = h2_golden()["molecules"]["0.7414"]["fci_energy"]
+    _, noisy = mgr.get_mu_effective(error_mitigation=False, density_representation=True)
+    assert abs(noisy - (-1.03136128530326)) < TOL                  # golden, SURVEY App. A.4 row 3
+    assert abs(mu - fci) < 0.35 * abs(noisy - fci)
+    # sampled objective (IWaveFunction): statistical sanity only
+    np.random.seed(8)
+    mu_s = CPU.get_mitigated_expectation(clean, model, 20000, w, meas_reps=50)
+    # 4000 identifiers; the estimator's spread is dominated by the sign fluctuations: sigma ~ 0.87 / sqrt(4000) = 0.014
+    assert abs(mu_s - fci) < 0.07
+
+
+def test_batched_lockstep_optimiser_on_gpu():
+    w = HydrogenAnsatz()
+    n_w = INoiseWrapper(w, INoiseModel([cirq.depolarize(1e-3)], [TwoQubitDepolarizingChannel(1e-3)], "d"))
+    x0s = np.array([[0.0], [0.05], [-0.03], [0.02]])   # same basin (the landscape is periodic with several minima)
+    funs, xs = CPU.get_batched_optimized_states(n_w, x0s, max_cpu_iter=40)
+    grid = CPU.get_batched_energies(n_w, np.linspace(-0.05, 0.08, 2601).reshape(-1, 1))
+    assert np.all(np.abs(funs - grid.min()) < 1e-6) and np.all(np.abs(xs[:, 0] - xs[0, 0]) < 2e-3)
+    single, _ = CPU.get_custom_optimized_state(n_w, max_cpu_iter=40, max_qpu_iter=1, use_density=True)
+    assert abs(single - funs[0]) < 1e-6
+
+
+def test_swap_test_seven_qubits():
+    q = cirq.LineQubit.range(7)
+    circuit = Q.swap_circuit(3, q)
+    rho = cirq.DensityMatrixSimulator().simulate(circuit).final_density_matrix
+    ref = O.simulate(7, O.from_circuit(circuit, q)[1])
+    assert np.max(np.abs(rho - ref)) < TOL
+    assert abs(2 * np.real(np.trace(rho[:64, :64])) - 1 - 0.5) < 1e-12          # ideal SWAP-test value (reference: 0.4999999404 in c64)
+    noisy = Q.noisy_circuit(circuit, "depolarize", 1e-3)
+    rho_n = cirq.DensityMatrixSimulator().simulate(noisy).final_density_matrix
+    ref_n = O.simulate(7, O.from_circuit(noisy, q)[1])
+    assert np.max(np.abs(rho_n - ref_n)) < TOL
+    np.random.seed(3)
+    s = Q.QPSamp(circuit, "depolarize", 1e-3)
+    ideal, noisy_v, mitigated = s.run_experiment(meas_reps=4000, sample_reps=4000, stat_reps=1, verbose=False)[0]
+    exact_noisy = 2 * np.real(np.trace(ref_n[:64, :64])) - 1
+    assert abs(ideal - 0.5) < 0.06 and abs(noisy_v - exact_noisy) < 0.06
+    assert abs(mitigated - 0.5) < abs(exact_noisy - 0.5) + 0.03
+
+
+def test_full_size_properties():
+    """BASELINE sizes: 65,536-circuit sweep and 1e6 variant rows — properties that do not need the oracle."""
+    import torch
+    terms = h2_terms()
+    n1, n2 = [O.depolarize(1e-3)], [O.two_qubit_depolarize(1e-3)]
+    B = 65536
+    alphas = torch.linspace(-0.5, 0.5, B, dtype=torch.float64, device="cuda").reshape(-1, 1)
+    # trace preservation: H = identity -> exactly Tr(rho) = 1 for every circuit
+    ident = (np.array([0], np.uint32), np.array([0], np.uint32), np.array([1.0]))
+    tr = build_program(h2_ops(n1, n2), 4, ident).energies(alphas).cpu().numpy()
+    assert np.max(np.abs(tr - 1.0)) < 1e-13
+    # linearity in H: E[H] = sum of single-term programs; and batch-order independence
+    prog = build_program(h2_ops(n1, n2), 4, terms)
+    e = prog.energies(alphas).cpu().numpy()
+    acc = np.zeros(B)
+    for t in range(len(terms[2])):
+        one = (terms[0][t:t + 1], terms[1][t:t + 1], terms[2][t:t + 1])
+        acc += build_program(h2_ops(n1, n2), 4, one).energies(alphas).cpu().numpy()
+    assert np.max(np.abs(acc - e)) < 1e-12
+    perm = torch.randperm(B, device="cuda")
+    assert np.array_equal(prog.energies(alphas[perm]).cpu().numpy(), e[perm.cpu().numpy()])
+    # periodicity: the circuit depends on alpha through rz(+-2 alpha) -> period pi
+    assert np.max(np.abs(prog.energies(alphas + np.pi).cpu().numpy() - e)) < 1e-11
+    # 1e6 variant rows: all-identity rows equal the plain noisy energy; rows are independent of their neighbours
+    from test_gpu_parity import qp_noisy_variant_program
+    vprog, gates = qp_noisy_variant_program(n1, n2, terms)
+    rows = torch.zeros((1_000_000, 122), dtype=torch.uint8, device="cuda")
+    hot = torch.arange(0, 1_000_000, 1000, device="cuda")
+    rows[hot, 5] = 2
+    ev = vprog.energies(None, rows).cpu().numpy()
+    base = ev[1]
+    mask = np.ones(1_000_000, bool)
+    mask[hot.cpu().numpy()] = False
+    assert np.all(ev[mask] == base) and abs(base - (-1.0559477031919418)) < TOL
+    assert np.all(ev[~mask] == ev[0]) and abs(ev[0] - base) > 1e-6

@@ -441,8 +441,9 @@ class CCXPowGate(ThreeQubitGate):
     def _decompose_(self, qubits):
         """Textbook 6-CNOT Toffoli (cirq's own sequence is not available offline; same unitary)."""
         c0, c1, t = qubits
-        return [H(t), CNOT(c1, t), T(t) ** -1, CNOT(c0, t), T(t), CNOT(c1, t), T(t) ** -1, CNOT(c0, t), T(c1), T(t),
-                H(t), CNOT(c0, c1), T(c0), T(c1) ** -1, CNOT(c0, c1)]
+        tdg = T ** -1
+        return [H(t), CNOT(c1, t), tdg(t), CNOT(c0, t), T(t), CNOT(c1, t), tdg(t), CNOT(c0, t), T(c1), T(t),
+                H(t), CNOT(c0, c1), T(c0), tdg(c1), CNOT(c0, c1)]
 
     def __str__(self):
         return "TOFFOLI"

@@ -90,6 +90,25 @@ __device__ __forceinline__ unsigned insert2(unsigned g, int p) {  // open a 2-bi
     return ((g >> p) << (p + 2)) | (g & ((1u << p) - 1u));
 }
 
+// Bank swizzle of the tile in shared memory: position = index with its low 4 bits (the 8-byte bank pair inside a
+// 128-byte line) XORed by a GF(2)-linear hash of the higher bits.  The hash columns were searched offline so that
+// for EVERY choice of qubit-pair positions the 32 lanes of a warp (which walk the five lowest free index bits)
+// cover all 16 bank pairs twice — the conflict-free optimum for 8-byte accesses.  Linear => swz(a ^ b) = swz(a) ^ swz(b),
+// so the XOR addressing below works on swizzled masks directly.
+__device__ __forceinline__ unsigned swz(unsigned i) {
+    const unsigned M0 = (1u << 4) | (1u << 5) | (1u << 7) | (1u << 9) | (1u << 10);
+    const unsigned M1 = (1u << 5) | (1u << 6) | (1u << 9) | (1u << 11) | (1u << 12) | (1u << 13);
+    const unsigned M2 = (1u << 5) | (1u << 6) | (1u << 8) | (1u << 9) | (1u << 11) | (1u << 12);
+    const unsigned M3 = (1u << 4) | (1u << 5) | (1u << 6) | (1u << 7) | (1u << 10) | (1u << 12) | (1u << 13);
+    const unsigned h = (__popc(i & M0) & 1u) | ((__popc(i & M1) & 1u) << 1) | ((__popc(i & M2) & 1u) << 2) | ((__popc(i & M3) & 1u) << 3);
+    return i ^ h;
+}
+
+// tile index of register e (bits zB, xB, zA, xA) = base ^ XOR of the masks of its set bits
+#define DMX_XADDR(base, m, e) ((base) ^ (((e) & 1) ? (m)[0] : 0u) ^ (((e) & 2) ? (m)[1] : 0u) ^ (((e) & 4) ? (m)[2] : 0u) ^ (((e) & 8) ? (m)[3] : 0u))
+// same with BYTE offsets into the tile (masks pre-shifted by 3): one LOP3 per access, no index scaling
+#define DMX_TILE_AT(tile_bytes, off) (*reinterpret_cast<double*>((tile_bytes) + (off)))
+
 // ---------------------------------------------------------------------------------------------------------
 // tile kernel: the Pauli vector (or one tile of it) lives in shared memory; a pass is a list of sweeps, each
 // sweep = load a 16-coefficient group (all codes of a qubit pair) into registers, apply the fused micro-ops,
@@ -178,26 +197,50 @@ __global__ void __launch_bounds__(512) dmx_tile_kernel(const TileArgs a) {
             c_first = grp * a.cpb;
         }
         // ---- load / init ----
+        // Element pairs t = 2*tid + j*2*nthr: the per-thread part (2*tid) and the per-iteration part (warp-uniform)
+        // occupy disjoint bits, and both the tile->global bit map and the swizzle are bitwise-linear, so the address
+        // arithmetic per element is one OR / XOR with hoisted values.
+        const unsigned pair_stride = 2u * nthr;                 // power of two
+        const unsigned g_thr = streaming ? map_bits(2u * tid, a.truns, a.n_truns) : 0u;
+        const unsigned s_thr = swz(2u * tid);
         if (streaming) {
             double* st = a.state + (c_first << (2 * a.n));
             if (a.load) {
-                for (unsigned i = tid; i < tile_elems / 2; i += nthr) {
-                    unsigned t = 2 * i;
-                    unsigned g = map_bits(t, a.truns, a.n_truns) | tile_base;
-                    double2 v = *reinterpret_cast<const double2*>(st + g);
-                    *reinterpret_cast<double2*>(tile + t) = v;
+                // batches of 8 independent 16-byte loads per thread keep enough bytes in flight to cover HBM latency
+                for (unsigned tj0 = 0; tj0 < tile_elems; tj0 += 8u * pair_stride) {
+                    double2 v[8];
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        const unsigned tj = tj0 + u * pair_stride;
+                        if (2u * tid + tj < tile_elems) {
+                            const unsigned g = g_thr | map_bits(tj, a.truns, a.n_truns) | tile_base;
+                            v[u] = __ldcs(reinterpret_cast<const double2*>(st + g));
+                        }
+                    }
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        const unsigned tj = tj0 + u * pair_stride;
+                        if (2u * tid + tj < tile_elems) {
+                            const unsigned sp = s_thr ^ swz(tj);
+                            tile[sp] = v[u].x;
+                            tile[sp ^ 1u] = v[u].y;
+                        }
+                    }
                 }
             } else {
-                for (unsigned t = tid; t < tile_elems; t += nthr) {
-                    unsigned g = map_bits(t, a.truns, a.n_truns) | tile_base;
-                    tile[t] = (g & 0xAAAAAAAAu) ? 0.0 : 1.0;
+                for (unsigned tj = 0; tj < tile_elems; tj += pair_stride) {
+                    if (2u * tid + tj >= tile_elems) break;
+                    const unsigned g = g_thr | map_bits(tj, a.truns, a.n_truns) | tile_base;
+                    const unsigned sp = s_thr ^ swz(tj);
+                    tile[sp] = (g & 0xAAAAAAAAu) ? 0.0 : 1.0;
+                    tile[sp ^ 1u] = ((g | 1u) & 0xAAAAAAAAu) ? 0.0 : 1.0;
                 }
             }
         } else {
             const unsigned padmask = (1u << a.pad) - 1u;
             for (unsigned e = tid; e < E; e += nthr) {
                 unsigned loc = e & (tile_elems - 1);
-                tile[e] = ((loc & padmask) || ((loc >> a.pad) & 0xAAAAAAAAu)) ? 0.0 : 1.0;
+                tile[swz(e)] = ((loc & padmask) || ((loc >> a.pad) & 0xAAAAAAAAu)) ? 0.0 : 1.0;
             }
         }
 
@@ -249,29 +292,30 @@ __global__ void __launch_bounds__(512) dmx_tile_kernel(const TileArgs a) {
                 const int p0 = sw.p0, p1 = sw.p1;
                 const int pa = p0 < p1 ? p0 : p1, pb = p0 < p1 ? p1 : p0;
                 double v[G][16];
-                unsigned base[G];
+                unsigned base[G], sbase[G];
+                unsigned lm[4], sm[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) { lm[j] = swz(sw.lmask[j]) << 3; sm[j] = swz(sw.smask[j]) << 3; }
+                char* const tile_bytes = reinterpret_cast<char*>(tile);
 #pragma unroll
                 for (int i = 0; i < G; ++i) {
                     const unsigned g = tid + i * nthr;
                     base[i] = insert2(insert2(g < NG ? g : 0u, pa), pb);
+                    sbase[i] = swz(base[i]) << 3;
                     if (sw.load_perm) {
-                        const unsigned long long pk = ((unsigned long long)sw.lsrc_hi << 32) | sw.lsrc_lo;
                         const double* __restrict__ lc = a.coefs + sw.lcoef;
 #pragma unroll
-                        for (int e = 0; e < 16; ++e) {
-                            const unsigned s = (unsigned)(pk >> (4 * e)) & 15u;
-                            v[i][e] = lc[e] * tile[base[i] | ((s >> 2) << p0) | ((s & 3u) << p1)];
-                        }
+                        for (int e = 0; e < 16; ++e) v[i][e] = lc[e] * DMX_TILE_AT(tile_bytes, DMX_XADDR(sbase[i], lm, e));
                     } else {
 #pragma unroll
-                        for (int e = 0; e < 16; ++e) v[i][e] = tile[base[i] | ((unsigned)(e >> 2) << p0) | ((unsigned)(e & 3) << p1)];
+                        for (int e = 0; e < 16; ++e) v[i][e] = DMX_TILE_AT(tile_bytes, DMX_XADDR(sbase[i], lm, e));
                     }
                 }
                 for (int mi = 0; mi < sw.n_mu; ++mi) {
                     const MicroOp m = a.mus[sw.first_mu + mi];
 #pragma unroll
                     for (int i = 0; i < G; ++i) {
-                        const int c = (int)(base[i] >> tbits);
+                        const int c = a.cpb == 1 ? 0 : (int)(base[i] >> tbits);
                         switch (m.kind) {
                             case MU_CHAIN_A: side_a(v[i], mats + (size_t)(c * a.max_chains + m.a0) * 16, m.a3 != 0); break;
                             case MU_CHAIN_B: side_b(v[i], mats + (size_t)(c * a.max_chains + m.a0) * 16, m.a3 != 0); break;
@@ -326,16 +370,12 @@ __global__ void __launch_bounds__(512) dmx_tile_kernel(const TileArgs a) {
                 for (int i = 0; i < G; ++i) {
                     if (tid + i * nthr >= NG) continue;
                     if (sw.store_perm) {
-                        const unsigned long long pk = ((unsigned long long)sw.sdst_hi << 32) | sw.sdst_lo;
                         const double* __restrict__ sc = a.coefs + sw.scoef;
 #pragma unroll
-                        for (int e = 0; e < 16; ++e) {
-                            const unsigned d = (unsigned)(pk >> (4 * e)) & 15u;
-                            tile[base[i] | ((d >> 2) << p0) | ((d & 3u) << p1)] = sc[d] * v[i][e];
-                        }
+                        for (int e = 0; e < 16; ++e) DMX_TILE_AT(tile_bytes, DMX_XADDR(sbase[i], sm, e)) = sc[e] * v[i][e];
                     } else {
 #pragma unroll
-                        for (int e = 0; e < 16; ++e) tile[base[i] | ((unsigned)(e >> 2) << p0) | ((unsigned)(e & 3) << p1)] = v[i][e];
+                        for (int e = 0; e < 16; ++e) DMX_TILE_AT(tile_bytes, DMX_XADDR(sbase[i], sm, e)) = v[i][e];
                     }
                 }
                 __syncthreads();
@@ -347,10 +387,11 @@ __global__ void __launch_bounds__(512) dmx_tile_kernel(const TileArgs a) {
         if (streaming) {
             if (a.store) {
                 double* st = a.state + (c_first << (2 * a.n));
-                for (unsigned i = tid; i < tile_elems / 2; i += nthr) {
-                    unsigned t = 2 * i;
-                    unsigned g = map_bits(t, a.truns, a.n_truns) | tile_base;
-                    *reinterpret_cast<double2*>(st + g) = *reinterpret_cast<const double2*>(tile + t);
+                for (unsigned tj = 0; tj < tile_elems; tj += pair_stride) {
+                    if (2u * tid + tj >= tile_elems) break;
+                    const unsigned g = g_thr | map_bits(tj, a.truns, a.n_truns) | tile_base;
+                    const unsigned sp = s_thr ^ swz(tj);
+                    *reinterpret_cast<double2*>(st + g) = make_double2(tile[sp], tile[sp ^ 1u]);
                 }
             }
         } else if (a.epilogue == 1) {
@@ -358,9 +399,9 @@ __global__ void __launch_bounds__(512) dmx_tile_kernel(const TileArgs a) {
             for (int c = warp; c < a.cpb; c += nwarps) {
                 long long ci = c_first + c;
                 if (ci >= total) continue;
-                const double* r = tile + ((unsigned)c << tbits);
+                const unsigned cbase = (unsigned)c << tbits;
                 double e = 0.0;
-                for (int t = lane; t < a.n_terms; t += 32) e += a.term_coef[t] * r[a.term_idx[t] << a.pad];
+                for (int t = lane; t < a.n_terms; t += 32) e += a.term_coef[t] * tile[swz(cbase | (a.term_idx[t] << a.pad))];
 #pragma unroll
                 for (int off = 16; off > 0; off >>= 1) e += __shfl_xor_sync(0xffffffffu, e, off);
                 if (lane == 0) {
@@ -373,7 +414,7 @@ __global__ void __launch_bounds__(512) dmx_tile_kernel(const TileArgs a) {
             for (unsigned e = tid; e < E; e += nthr) {
                 long long ci = c_first + (e >> tbits);
                 unsigned loc = e & (tile_elems - 1);
-                if (ci < total && !(loc & padmask)) a.out[(ci << (2 * a.n)) + (loc >> a.pad)] = tile[e];
+                if (ci < total && !(loc & padmask)) a.out[(ci << (2 * a.n)) + (loc >> a.pad)] = tile[swz(e)];
             }
         }
         __syncthreads();

@@ -627,19 +627,41 @@ struct SweepBuilder {
         }
     }
 
-    void set_perm(const Block& b, bool at_load) {
-        std::vector<double> M = oriented(b), sc;
-        classify(M, 16);
-        uint64_t packed;
-        mono_tables(M, 16, sc, packed);   // out[a] = sc[a] * in[src[a]]
+    static uint32_t code_offset(int code, int p0, int p1) { return ((uint32_t)(code >> 2) << p0) | ((uint32_t)(code & 3) << p1); }
+
+    // monomial 16x16: out[a] = sc[a] * in[src[a]]; usable as an addressing permutation only when src is GF(2)-linear
+    static bool linear_perm(const std::vector<double>& M, int src[16], double sc[16]) {
+        for (int a = 0; a < 16; ++a) {
+            src[a] = -1;
+            for (int c = 0; c < 16; ++c)
+                if (M[a * 16 + c] != 0.0) { src[a] = c; sc[a] = M[a * 16 + c]; }
+            if (src[a] < 0) return false;
+        }
+        for (int a = 0; a < 16; ++a)
+            for (int c = 0; c < 16; ++c)
+                if (src[a ^ c] != (src[a] ^ src[c])) return false;
+        return true;
+    }
+
+    void set_perm(const std::vector<double>& M, bool at_load) {
+        int src[16];
+        double sc[16];
+        linear_perm(M, src, sc);
+        const int p0 = local_pos[qa], p1 = local_pos[qb];
         if (at_load) {
-            sw.load_perm = 1; sw.lcoef = cc.get(p, sc);
-            sw.lsrc_lo = (uint32_t)(packed & 0xffffffffu); sw.lsrc_hi = (uint32_t)(packed >> 32);
+            // v[e] = sc[e] * tile[code src[e]]
+            sw.load_perm = 1;
+            sw.lcoef = cc.get(p, std::vector<double>(sc, sc + 16));
+            for (int j = 0; j < 4; ++j) sw.lmask[j] = code_offset(src[1 << j], p0, p1);
         } else {
-            uint64_t dst = 0;
-            for (int a = 0; a < 16; ++a) { uint64_t src = (packed >> (4 * a)) & 15u; dst |= (uint64_t)a << (4 * src); }
-            sw.store_perm = 1; sw.scoef = cc.get(p, sc);
-            sw.sdst_lo = (uint32_t)(dst & 0xffffffffu); sw.sdst_hi = (uint32_t)(dst >> 32);
+            // out[a] = sc[a] * v[src[a]]  <=>  register e goes to code dst[e] = src^-1[e] with scale sc[dst[e]]
+            int dst[16];
+            for (int a = 0; a < 16; ++a) dst[src[a]] = a;
+            std::vector<double> se(16);
+            for (int e = 0; e < 16; ++e) se[e] = sc[dst[e]];
+            sw.store_perm = 1;
+            sw.scoef = cc.get(p, se);
+            for (int j = 0; j < 4; ++j) sw.smask[j] = code_offset(dst[1 << j], p0, p1);
         }
     }
 
@@ -657,6 +679,11 @@ struct SweepBuilder {
         for (MicroOp& m : mus)
             if (m.kind == MU_CHAIN_A || m.kind == MU_CHAIN_B) m.a0 += chain_base;
         sw.p0 = local_pos[qa]; sw.p1 = local_pos[qb];
+        for (int j = 0; j < 4; ++j) {
+            const uint32_t unit = code_offset(1 << j, sw.p0, sw.p1);
+            if (!sw.load_perm) sw.lmask[j] = unit;
+            if (!sw.store_perm) sw.smask[j] = unit;
+        }
         sw.first_mu = (int)p.mus.size(); sw.n_mu = (int)mus.size();
         p.mus.insert(p.mus.end(), mus.begin(), mus.end());
         p.sweeps.push_back(sw);
@@ -738,6 +765,14 @@ struct SweepBuilder {
                     bool same_pair = (blk.q[0] == qa && blk.q[1] == qb) || (blk.q[0] == qb && blk.q[1] == qa);
                     if (same_pair) {
                         bool mono = blk.kind == BK_FIXED && blk.cls == CLS_MONO;
+                        std::vector<double> Mo;
+                        if (mono) {
+                            Mo = oriented(blk);
+                            classify(Mo, 16);
+                            int src_[16];
+                            double sc_[16];
+                            mono = linear_perm(Mo, src_, sc_);   // non-Clifford monomials fall back to a dense micro-op
+                        }
                         if (blk.kind == BK_VAR && blk.q[0] != qa) {
                             // variant tables are oriented (q0,q1): only usable when the sweep has the same orientation
                             if (mus.empty() && pendA.empty() && pendB.empty() && !sw.load_perm) { std::swap(qa, qb); }
@@ -745,8 +780,8 @@ struct SweepBuilder {
                         }
                         if (mono) {
                             bool empty = mus.empty() && pendA.empty() && pendB.empty() && !sw.load_perm;
-                            if (empty) { set_perm(blk, true); pop(f); --remaining; progress = true; }
-                            else { flush_side(pendA, true); flush_side(pendB, false); set_perm(blk, false); pop(f); --remaining; close(); closed = true; continue; }
+                            if (empty) { set_perm(Mo, true); pop(f); --remaining; progress = true; }
+                            else { flush_side(pendA, true); flush_side(pendB, false); set_perm(Mo, false); pop(f); --remaining; close(); closed = true; continue; }
                         } else {
                             add_two_qubit(blk);
                             pop(f); --remaining; progress = true;
@@ -1330,8 +1365,9 @@ std::string dump_plan(const Plan& p) {
     for (size_t i = 0; i < p.sweeps.size(); ++i) {
         const SweepDev& w = p.sweeps[i];
         os << "sweep " << i << " p0=" << w.p0 << " p1=" << w.p1 << " first_mu=" << w.first_mu << " nmu=" << w.n_mu
-           << " lperm=" << w.load_perm << " lcoef=" << w.lcoef << " lsrc=" << (((unsigned long long)w.lsrc_hi << 32) | w.lsrc_lo)
-           << " sperm=" << w.store_perm << " scoef=" << w.scoef << " sdst=" << (((unsigned long long)w.sdst_hi << 32) | w.sdst_lo) << "\n";
+           << " lperm=" << w.load_perm << " lcoef=" << w.lcoef << " sperm=" << w.store_perm << " scoef=" << w.scoef
+           << " lmask=" << w.lmask[0] << "," << w.lmask[1] << "," << w.lmask[2] << "," << w.lmask[3]
+           << " smask=" << w.smask[0] << "," << w.smask[1] << "," << w.smask[2] << "," << w.smask[3] << "\n";
     }
     for (size_t i = 0; i < p.mus.size(); ++i)
         os << "mu " << i << " kind=" << p.mus[i].kind << " a0=" << p.mus[i].a0 << " a1=" << p.mus[i].a1 << " a2=" << p.mus[i].a2

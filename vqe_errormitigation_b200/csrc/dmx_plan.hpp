@@ -72,12 +72,15 @@ struct MicroOp {      // 32 bytes
     int32_t pad[3];
 };
 
-struct SweepDev {     // 48 bytes
+// Register e of a group holds local code e = 4*code(A) + code(B); its bits are (zB, xB, zA, xA).  Clifford
+// permutations are GF(2)-linear on those 4 bits, so the tile index of register e is base ^ XOR_{j in bits(e)} mask[j]:
+// identity addressing and any monomial block use the same code path (4 masks), one LOP3 per element.
+struct SweepDev {     // 64 bytes
     int32_t p0, p1;           // tile-local bit positions of the codes of qubit A and qubit B
     int32_t first_mu, n_mu;
-    int32_t load_perm, lcoef; // load: v[a] = coef[lcoef + a] * tile[src code lsrc[a]]
-    int32_t store_perm, scoef;// store: tile[dst code sdst[b]] = coef[scoef + sdst[b]] * v[b]
-    uint32_t lsrc_lo, lsrc_hi, sdst_lo, sdst_hi;  // 16 x 4-bit codes
+    int32_t load_perm, lcoef; // load:  v[e] = coef[lcoef + e] * tile[base ^ X_l(e)]      (scale skipped when !load_perm)
+    int32_t store_perm, scoef;// store: tile[base ^ X_s(e)] = coef[scoef + e] * v[e]
+    uint32_t lmask[4], smask[4];
 };
 
 struct ChainFactor {  // one factor of a per-circuit 1-qubit matrix product (applied in order)
