@@ -281,6 +281,7 @@ def main():
     torch.cuda.set_device(local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # keep stdout to the single JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     wl = WORKLOADS[args.workload]()
     prog, B = wl["prog"], wl["batch"]
