@@ -273,3 +273,98 @@ def test_golden_fixture_energies():
     rows = np.array([c["identifier"] for c in gold["variant_cases"]], np.uint8)
     got = prog.energies(None, torch.tensor(rows)).cpu().numpy()
     assert np.max(np.abs(got - np.array([c["energy"] for c in gold["variant_cases"]]))) < TOL
+
+
+def _pauli_exponential_ops(n, string_qubits, paulis, sign, name, noise1, noise2):
+    """One UCCSD-style Pauli-exponential block (i_wave_function.py:176-189): basis change, CNOT ladder,
+    rz(2*sign*theta) on the last qubit, reverse ladder, inverse basis change — noise after every gate."""
+    ops = []
+
+    def gate(qs, m):
+        ops.append(("u", qs, m))
+        for kr in (noise1 if len(qs) == 1 else noise2):
+            ops.append(("k", qs, kr))
+
+    for q, p in zip(string_qubits, paulis):
+        if p != "Z":
+            gate((q,), O.H if p == "X" else O.rx(-np.pi / 2))
+    for a, b in zip(string_qubits[:-1], string_qubits[1:]):
+        gate((a, b), O.CNOT)
+    ops.append(("r", (string_qubits[-1],), (2, name, 2.0 * sign, 0.0)))
+    for kr in noise1:
+        ops.append(("k", (string_qubits[-1],), kr))
+    for a, b in reversed(list(zip(string_qubits[:-1], string_qubits[1:]))):
+        gate((a, b), O.CNOT)
+    for q, p in zip(string_qubits, paulis):
+        if p != "Z":
+            gate((q,), O.H if p == "X" else O.rx(np.pi / 2))
+    return ops
+
+
+def _large_circuit(n, rng, n_blocks=3):
+    n1, n2 = [O.depolarize(1e-3)], [O.two_qubit_depolarize(1e-3)]
+    ops = []
+    for q in range(4):                                     # HF-like initial state on the first four qubits
+        ops += [("u", (q,), O.rx(np.pi)), ("k", (q,), n1[0])]
+    for q in range(n):
+        ops += [("r", (q,), (1, f"y{q}", 1.0, 0.0)), ("k", (q,), n1[0]), ("r", (q,), (2, f"z{q}", 1.0, 0.0)), ("k", (q,), n1[0])]
+    for q in range(n - 1):
+        ops += [("u", (q, q + 1), O.CNOT), ("k", (q, q + 1), n2[0])]
+    for blk in range(n_blocks):                            # double-excitation style strings of weight 4 .. 8
+        wgt = int(rng.integers(4, 9))
+        qs = sorted(int(v) for v in rng.choice(n, wgt, replace=False))
+        paulis = [str(rng.choice(["X", "Y"])) for _ in qs]
+        ops += _pauli_exponential_ops(n, qs, paulis, float(rng.choice([-1.0, 1.0])), f"a{blk}", n1, n2)
+    return ops
+
+
+def test_ten_qubit_register_against_c_oracle():
+    """BASELINE config 4/5 shapes at reduced depth on 10 qubits: hardware-efficient layer + LiH-like Pauli-exponential
+    blocks, depolarizing noise after every gate, 60 Pauli terms — streaming kernel vs the C oracle."""
+    from oracle import c_oracle as CO
+    torch = torch_cuda()
+    n = 10
+    rng = np.random.default_rng(510)
+    ops = _large_circuit(n, rng)
+    terms = random_hamiltonian(rng, n, 60)
+    prog = build_program(ops, n, terms)
+    assert prog.info["path"] == 2
+    params = rng.uniform(-1.0, 1.0, size=(2, prog.n_params))
+    got = prog.energies(torch.tensor(params), workspace_states=2).cpu().numpy()
+    want = CO.energy_batch(n, prog.ops, prog.pool, terms, params=params, n_params=prog.n_params, threads=4)
+    assert np.max(np.abs(got - want)) < TOL
+
+
+def test_twelve_qubit_register():
+    """12 qubits (rho would be 4096^2 complex128 = 256 MiB; the engine's state is 128 MiB): a light circuit against the
+    C oracle, then the full LiH-like shape through two different tilings (7 and 5 resident qubits -> different pass
+    decompositions must agree) and trace preservation."""
+    from oracle import c_oracle as CO
+    torch = torch_cuda()
+    n = 12
+    rng = np.random.default_rng(512)
+    light = [("u", (0,), O.rx(np.pi)), ("k", (0,), O.depolarize(1e-2)), ("r", (11,), (1, "a", 1.0, 0.0)), ("k", (11,), O.bit_flip(2e-2)),
+             ("u", (0, 11), O.CNOT), ("r", (5,), (0, "b", 1.0, 0.3)), ("u", (5, 6), O.CNOT), ("k", (6,), O.amplitude_damp(0.05)),
+             ("u", (6,), O.H), ("k", (6,), O.asymmetric_depolarize(0.01, 0.02, 0.03))]
+    # Pauli strings supported on the touched qubits {0, 5, 6, 11} so that the expectation is not trivially zero
+    sub = random_hamiltonian(rng, 4, 40)
+    spread = lambda m: sum(((int(m) >> (3 - i)) & 1) << (n - 1 - q) for i, q in enumerate((0, 5, 6, 11)))
+    light_terms = (np.array([spread(m) for m in sub[0]], np.uint32), np.array([spread(m) for m in sub[1]], np.uint32), sub[2])
+    terms = random_hamiltonian(rng, n, 40)
+    prog = build_program(light, n, light_terms)
+    params = rng.uniform(-1.0, 1.0, size=(1, prog.n_params))
+    got = prog.energies(torch.tensor(params), workspace_states=1).cpu().numpy()
+    want = CO.energy_batch(n, prog.ops, prog.pool, light_terms, params=params, n_params=prog.n_params, threads=1)
+    assert abs(want[0]) > 1e-2 and np.max(np.abs(got - want)) < TOL
+    ops = _large_circuit(n, rng, n_blocks=4)
+    p7 = build_program(ops, n, terms, tile_qubits=7)
+    p5 = build_program(ops, n, terms, tile_qubits=5)
+    assert p7.info["n_passes"] < p5.info["n_passes"]
+    params = rng.uniform(-1.0, 1.0, size=(2, p7.n_params))
+    cols5 = [p7.param_names.index(nm) for nm in p5.param_names]
+    e7 = p7.energies(torch.tensor(params), workspace_states=2).cpu().numpy()
+    e5 = p5.energies(torch.tensor(params[:, cols5]), workspace_states=2).cpu().numpy()
+    assert np.max(np.abs(e7 - e5)) < 1e-12
+    ident = (np.array([0], np.uint32), np.array([0], np.uint32), np.array([1.0]))
+    tr = build_program(ops, n, ident).energies(torch.tensor(params), workspace_states=2).cpu().numpy()
+    assert np.max(np.abs(tr - 1.0)) < 1e-12
