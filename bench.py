@@ -125,7 +125,7 @@ def workload_hea10():
             if code in (2, 3):
                 zs[t] |= bit
     terms = (xs, zs, rng.normal(size=n_terms))
-    prog = engine.CircuitProgram(b, hamiltonian=terms)
+    prog = engine.CircuitProgram(b, hamiltonian=terms, options=dict(PLAN_OPTIONS))
 
     def make_inputs(rank: int, seed_offset: int = 0):
         r = np.random.default_rng(20260103 + rank)

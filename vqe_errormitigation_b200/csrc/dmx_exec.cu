@@ -13,16 +13,19 @@
 //   dmx_qp_reduce_*     deterministic two-stage reduction of the QP-weighted estimator.
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <atomic>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <map>
 #include <mutex>
 #include <stdexcept>
 #include <string>
 #include <vector>
 
 #include "dmx_plan.hpp"
+#include "dmx_stream.cuh"
 
 using namespace dmx;
 
@@ -759,6 +762,15 @@ struct DevPlan {
     std::mutex mu;       // host-buffer API staging (held for the whole dmx_energy_batch_host call)
     std::mutex wl_mu;    // worklist (re)allocation only — never held across a launch that may take `mu`
     int sm_count = 148;
+    // streaming passes in the form dmx_stream_kernel executes (dmx_stream.cuh); !ok -> generic dmx_tile_kernel
+    struct PassX {
+        bool ok = false;
+        void* tables = nullptr;      // device: [SweepX x n_sweeps][MuX x n_mus]
+        double* coefs = nullptr;     // device: pass-local fixed coefficients
+        int n_sweeps = 0, n_mus = 0, n_coefs = 0, first_chain = 0, n_chains = 0;
+        size_t smem = 0;
+    };
+    std::vector<PassX> passx;
 };
 
 template <class T>
@@ -771,6 +783,89 @@ static cudaError_t upload(T** dst, const std::vector<T>& src) {
 }
 
 static std::mutex g_upload_mu;
+
+// Streaming passes -> tables of dmx_stream_kernel.  A pass qualifies when its tile has 6 or 7 qubits, it holds no
+// variant micro-ops and its tables fit shared memory beside the tile.
+static cudaError_t build_stream_tables(const Plan& p, DevPlan* d) {
+    d->passx.assign(p.passes.size(), DevPlan::PassX{});
+    if (p.path != 2) return cudaSuccess;
+    for (size_t pi = 0; pi < p.passes.size(); ++pi) {
+        const Pass& ps = p.passes[pi];
+        DevPlan::PassX& px = d->passx[pi];
+        const int k = (int)ps.tile_q.size();
+        if (k != 6 && k != 7) continue;
+        const int threads = k == 7 ? 512 : 128;
+        if (ps.n_phases < 1) continue;
+        px.first_chain = p.phases[ps.first_phase].first_chain;
+        px.n_chains = 0;
+        for (int ph = 0; ph < ps.n_phases; ++ph) px.n_chains += p.phases[ps.first_phase + ph].n_chains;
+        std::vector<SweepX> sx;
+        std::vector<MuX> mx;
+        std::vector<double> lc;                       // pass-local coefficient table
+        std::map<std::pair<int, int>, int> where;     // (global offset, length) -> local offset
+        auto local = [&](int off, int len) {
+            auto key = std::make_pair(off, len);
+            auto it = where.find(key);
+            if (it != where.end()) return it->second;
+            int at = (int)lc.size();
+            lc.insert(lc.end(), p.coefs.begin() + off, p.coefs.begin() + off + len);
+            where.emplace(key, at);
+            return at;
+        };
+        bool ok = true;
+        for (int ph = 0; ph < ps.n_phases && ok; ++ph) {
+            const Phase& phase = p.phases[ps.first_phase + ph];
+            for (int si = 0; si < phase.n_sweeps && ok; ++si) {
+                const SweepDev& sw = p.sweeps[phase.first_sweep + si];
+                SweepX x{};
+                x.pa = std::min(sw.p0, sw.p1); x.pb = std::max(sw.p0, sw.p1);
+                x.first_mu = (int)mx.size(); x.n_mu = sw.n_mu;
+                x.lscale = sw.load_perm ? px.n_chains * 16 + local(sw.lcoef, 16) : -1;
+                x.sscale = sw.store_perm ? px.n_chains * 16 + local(sw.scoef, 16) : -1;
+                x.gtop = swz_hd(insert2_hd(insert2_hd((unsigned)threads, x.pa), x.pb)) << 3;
+                auto S = [](uint32_t m) { return swz_hd(m) << 3; };
+                for (int c = 0; c < 4; ++c) {
+                    x.lB[c] = ((c & 1) ? S(sw.lmask[0]) : 0u) ^ ((c & 2) ? S(sw.lmask[1]) : 0u);
+                    x.lA[c] = ((c & 1) ? S(sw.lmask[2]) : 0u) ^ ((c & 2) ? S(sw.lmask[3]) : 0u);
+                    x.sB[c] = ((c & 1) ? S(sw.smask[0]) : 0u) ^ ((c & 2) ? S(sw.smask[1]) : 0u);
+                    x.sA[c] = ((c & 1) ? S(sw.smask[2]) : 0u) ^ ((c & 2) ? S(sw.smask[3]) : 0u);
+                }
+                for (int mi = 0; mi < sw.n_mu && ok; ++mi) {
+                    const MicroOp& m = p.mus[sw.first_mu + mi];
+                    MuX y{};
+                    y.kind = m.kind;
+                    switch (m.kind) {
+                        case MU_CHAIN_A: case MU_CHAIN_B:
+                            y.off = (phase.first_chain + m.a0 - px.first_chain) * 16; y.unital = m.a3; break;
+                        case MU_FIX_A: case MU_FIX_B:
+                            y.off = px.n_chains * 16 + local(m.a0, 16); y.unital = m.a3; break;
+                        case MU_DIAG_A: case MU_DIAG_B: y.off = px.n_chains * 16 + local(m.a0, 4); break;
+                        case MU_DIAG2: y.off = px.n_chains * 16 + local(m.a0, 16); break;
+                        case MU_MAT2: y.off = px.n_chains * 16 + local(m.a0, 256); break;
+                        default: ok = false; break;     // variant micro-ops: generic kernel
+                    }
+                    mx.push_back(y);
+                }
+                sx.push_back(x);
+            }
+        }
+        if (!ok) continue;
+        px.n_sweeps = (int)sx.size(); px.n_mus = (int)mx.size(); px.n_coefs = (int)lc.size();
+        const size_t n_cf = ((size_t)px.n_chains * 16 + lc.size() + 1) & ~(size_t)1;
+        px.smem = ((size_t)32 * threads + n_cf) * 8 + sx.size() * sizeof(SweepX) + mx.size() * sizeof(MuX);
+        if (px.smem > (k == 7 ? 227u : 56u) * 1024) continue;       // k = 6: keep four CTAs per SM
+        std::vector<char> blob(sx.size() * sizeof(SweepX) + mx.size() * sizeof(MuX) + 16);
+        std::memcpy(blob.data(), sx.data(), sx.size() * sizeof(SweepX));
+        std::memcpy(blob.data() + sx.size() * sizeof(SweepX), mx.data(), mx.size() * sizeof(MuX));
+        cudaError_t e = upload((char**)&px.tables, blob);
+        if (e != cudaSuccess) return e;
+        if (lc.empty()) lc.push_back(0.0);
+        e = upload(&px.coefs, lc);
+        if (e != cudaSuccess) return e;
+        px.ok = true;
+    }
+    return cudaSuccess;
+}
 
 static int ensure_device(Plan& p, DevPlan** out) {
     std::lock_guard<std::mutex> lock(g_upload_mu);
@@ -831,6 +926,7 @@ static int ensure_device(Plan& p, DevPlan** out) {
         CUDA_TRY(upload(&d->slots, sl));
         CUDA_TRY(upload(&d->labels, lab));
     }
+    CUDA_TRY(build_stream_tables(p, d));
     p.dev = d;
     *out = d;
     return DMX_OK;
@@ -843,6 +939,7 @@ static void free_device(Plan& p) {
     cudaFree(d->coefs); cudaFree(d->rots); cudaFree(d->term_idx); cudaFree(d->term_coef);
     cudaFree(d->f_w); cudaFree(d->f_segs); cudaFree(d->f_classes); cudaFree(d->f_init); cudaFree(d->f_eweight); cudaFree(d->f_eslot);
     cudaFree(d->slots); cudaFree(d->labels); cudaFree(d->worklist);
+    for (auto& px : d->passx) { cudaFree(px.tables); cudaFree(px.coefs); }
     if (d->h_stage) cudaFreeHost(d->h_stage);
     if (d->d_stage) cudaFree(d->d_stage);
     if (d->stream) cudaStreamDestroy(d->stream);
@@ -935,36 +1032,112 @@ static int run_tile_single(Plan& p, DevPlan* d, long long batch, const double* p
     return launch_tile(a, grid, threads, gpt, smem, st);
 }
 
+static int g_stream_kernel = 1;        // option "stream_kernel": 0 -> generic dmx_tile_kernel for every pass
+static long long g_stream_chunk = 0;   // option "stream_chunk": circuits per pass launch (0: auto, ~64 MiB of states stay in L2)
+
+template <int THREADS>
+static int launch_stream(const StreamArgs& a, long long grid, size_t smem, cudaStream_t st) {
+    static std::mutex mu;
+    static size_t configured = 0;
+    {
+        std::lock_guard<std::mutex> lock(mu);
+        if (smem > configured) {
+            const int want = (int)std::max(smem, (size_t)48 * 1024);
+            CUDA_TRY(cudaFuncSetAttribute(dmx_stream_kernel<THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, want));
+            CUDA_TRY(cudaFuncSetAttribute(dmx_stream_kernel<THREADS>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+            configured = want;
+        }
+    }
+    dmx_stream_kernel<THREADS><<<(unsigned)grid, THREADS, smem, st>>>(a);
+    ++g_launches;
+    CUDA_TRY(cudaGetLastError());
+    return DMX_OK;
+}
+
+static unsigned map_runs_host(unsigned v, const BitRun* runs, int n) {
+    unsigned g = 0;
+    for (int i = 0; i < n; ++i) g |= ((v >> runs[i].lshift) & ((1u << runs[i].width) - 1u)) << runs[i].gshift;
+    return g;
+}
+
 // Streaming execution (n > tile_k): state[chunk][4^n] in `state`; all passes over one chunk of circuits.
 static int run_streaming(Plan& p, DevPlan* d, long long chunk, long long circuit_offset, const double* params, const uint8_t* variants,
                          double* state, cudaStream_t st) {
-    for (size_t pi = 0; pi < p.passes.size(); ++pi) {
+    const int total_chains = (int)p.chains.size();
+    bool any_x = false;
+    for (const auto& px : d->passx) any_x |= px.ok && g_stream_kernel;
+    double* chainmats = nullptr;
+    if (any_x && total_chains > 0) {
+        // per-circuit chain matrices of every pass, computed once (stream-ordered scratch: plans may run on several streams)
+        CUDA_TRY(cudaMallocAsync((void**)&chainmats, (size_t)chunk * total_chains * 128, st));
+        const long long items = chunk * total_chains;
+        dmx_chain_kernel<<<(unsigned)((items + 127) / 128), 128, 0, st>>>(d->chains, d->factors, d->coefs, d->rots, params, p.n_params,
+                                                                          total_chains, chunk, circuit_offset, chainmats);
+        ++g_launches;
+        CUDA_TRY(cudaGetLastError());
+    }
+    int rc = DMX_OK;
+    for (size_t pi = 0; pi < p.passes.size() && rc == DMX_OK; ++pi) {
         const Pass& ps = p.passes[pi];
-        TileArgs a{};
-        fill_common(a, p, d, ps, params, variants);
-        a.k = (int)ps.tile_q.size(); a.cpb = 1; a.pad = 0; a.batch = chunk; a.state = state; a.circuit_offset = circuit_offset;
-        a.load = pi > 0; a.store = 1;
+        const int k = (int)ps.tile_q.size();
         std::vector<int> others;
         {
             std::vector<char> in(p.n, 0);
             for (int q : ps.tile_q) in[q] = 1;
             for (int q = 0; q < p.n; ++q) if (!in[q]) others.push_back(q);
         }
+        BitRun truns[8], oruns[8];
+        int n_truns = 0, n_oruns = 0;
         try {
-            make_runs(ps.tile_q, p.n, a.truns, &a.n_truns);
-            make_runs(others, p.n, a.oruns, &a.n_oruns);
-        } catch (const std::exception& e) { return fail(DMX_ERR_UNSUPPORTED, e.what()); }
+            make_runs(ps.tile_q, p.n, truns, &n_truns);
+            make_runs(others, p.n, oruns, &n_oruns);
+        } catch (const std::exception& e) { rc = fail(DMX_ERR_UNSUPPORTED, e.what()); break; }
+        const long long groups = chunk << (2 * (p.n - k));
+        if (groups >= (1LL << 31)) { rc = fail(DMX_ERR_UNSUPPORTED, "streaming chunk too large for one launch"); break; }
+        const DevPlan::PassX& px = d->passx[pi];
+        if (px.ok && g_stream_kernel) {
+            StreamArgs a{};
+            a.sweeps = (const SweepX*)px.tables;
+            a.mus = (const MuX*)((const char*)px.tables + (size_t)px.n_sweeps * sizeof(SweepX));
+            a.coefs = px.coefs; a.chainmats = chainmats;
+            a.n_sweeps = px.n_sweeps; a.n_mus = px.n_mus; a.n_coefs = px.n_coefs;
+            a.total_chains = total_chains; a.first_chain = px.first_chain; a.n_chains = px.n_chains;
+            a.n = p.n; a.k = k; a.load = pi > 0; a.state = state;
+            a.n_truns_l = a.n_truns_s = n_truns; a.n_oruns_l = a.n_oruns_s = n_oruns;
+            for (int i = 0; i < 8; ++i) {
+                const int t[3] = {truns[i].lshift, truns[i].gshift, truns[i].width}, o[3] = {oruns[i].lshift, oruns[i].gshift, oruns[i].width};
+                for (int c = 0; c < 3; ++c) {
+                    a.truns_l[i][c] = a.truns_s[i][c] = i < n_truns ? t[c] : 0;
+                    a.oruns_l[i][c] = a.oruns_s[i][c] = i < n_oruns ? o[c] : 0;
+                }
+            }
+            const unsigned threads = k == 7 ? 512u : 128u;
+            for (unsigned j = 0; j < 16; ++j) {
+                a.giter_l[j] = a.giter_s[j] = map_runs_host(j * 2u * threads, truns, n_truns);
+                a.siter[j] = swz_hd(j * 2u * threads);
+            }
+            a.init_mask = 0xAAAAAAAAu;
+            rc = k == 7 ? launch_stream<512>(a, groups, px.smem, st) : launch_stream<128>(a, groups, px.smem, st);
+            continue;
+        }
+        TileArgs a{};
+        fill_common(a, p, d, ps, params, variants);
+        a.k = k; a.cpb = 1; a.pad = 0; a.batch = chunk; a.state = state; a.circuit_offset = circuit_offset;
+        a.load = pi > 0; a.store = 1;
+        a.n_truns = n_truns; a.n_oruns = n_oruns;
+        for (int i = 0; i < 8; ++i) { a.truns[i] = truns[i]; a.oruns[i] = oruns[i]; }
         const unsigned E = 1u << (2 * a.k);
         int threads, gpt;
         tile_geometry(E, &threads, &gpt);
         const size_t smem = (size_t)E * 8 + (size_t)a.max_chains * 128;
-        if (smem > 227 * 1024) return fail(DMX_ERR_UNSUPPORTED, "tile does not fit shared memory");
-        long long groups = chunk << (2 * (p.n - a.k));
-        int grid = (int)std::min<long long>(groups, 1LL << 30);
-        int rc = launch_tile(a, grid, threads, gpt, smem, st);
-        if (rc) return rc;
+        if (smem > 227 * 1024) { rc = fail(DMX_ERR_UNSUPPORTED, "tile does not fit shared memory"); break; }
+        rc = launch_tile(a, (int)groups, threads, gpt, smem, st);
     }
-    return DMX_OK;
+    if (chainmats) {
+        cudaError_t e = cudaFreeAsync(chainmats, st);
+        if (rc == DMX_OK && e != cudaSuccess) rc = fail(DMX_ERR_CUDA, std::string("cudaFreeAsync: ") + cudaGetErrorString(e));
+    }
+    return rc;
 }
 
 template <int CPB, int CSMODE>
@@ -1074,6 +1247,11 @@ int dmx_plan_set_option(dmx_plan* plan, const char* key, int value) {
     else if (k == "tile_qubits") {
         if (value < 4 || value > 7) return fail(DMX_ERR_INVALID, "tile_qubits must be in 4..7");
         plan->p.opt_tile_qubits = value;
+    } else if (k == "stream_kernel") {
+        g_stream_kernel = value != 0;
+    } else if (k == "stream_chunk") {
+        if (value < 0) return fail(DMX_ERR_INVALID, "stream_chunk must be >= 0");
+        g_stream_chunk = value;
     } else if (k == "segment_cpb") {
         if (value != 4 && value != 8) return fail(DMX_ERR_INVALID, "segment_cpb must be 4 or 8");
         g_seg_cpb = value;
@@ -1146,6 +1324,9 @@ static int energy_impl(dmx_plan* plan, int64_t batch, const double* d_params, co
     const size_t sb = (size_t)p.info.state_bytes;
     long long chunk = (long long)(workspace_bytes / sb);
     if (!d_workspace || chunk < 1) return fail(DMX_ERR_INVALID, "workspace too small: need dmx_workspace_bytes()");
+    // all passes run over one sub-chunk before the next starts: ~64 MiB of states stay resident in the 126 MB L2
+    const long long sub = g_stream_chunk > 0 ? g_stream_chunk : std::max<long long>(1, (long long)((64u << 20) / sb));
+    chunk = std::min(chunk, sub);
     for (long long off = 0; off < batch; off += chunk) {
         long long cur = std::min<long long>(chunk, batch - off);
         rc = run_streaming(p, d, cur, off, d_params, d_variants, (double*)d_workspace, st);

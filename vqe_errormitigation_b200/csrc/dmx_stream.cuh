@@ -1,0 +1,344 @@
+// dmx_stream.cuh — streaming pass kernel for n > tile_k (BASELINE configs 4-5: 10..14 qubits).
+//
+// One CTA owns one tile (4^k Pauli coefficients, k = 6 or 7 resident qubits) of one circuit for one pass:
+//     global -> shared (16-byte loads, whole tile in flight) -> sweeps -> global.
+// Every thread keeps 2 groups x 16 coefficients in registers during a sweep, so THREADS = 4^k / 32 and the whole
+// tile is register-resident while the micro-ops run; shared memory is only the exchange medium between sweeps.
+// Compared with the generic dmx_tile_kernel this kernel
+//   * reads per-circuit chain matrices (products of rotations / fixed one-qubit blocks) that dmx_chain_kernel
+//     computed ONCE per (circuit, pass) instead of once per tile,
+//   * keeps every table of the pass (sweeps, micro-ops, coefficients) in shared memory,
+//   * addresses the tile with one 3-input XOR per access (per-sweep masks precombined on the host).
+// k = 6 tiles are 32 KiB: four CTAs share an SM, so the HBM phases of one tile overlap the sweeps of the others.
+#pragma once
+#include <cstdint>
+
+#include "dmx_plan.hpp"
+
+namespace dmx {
+
+struct SweepX {               // 96 bytes, host-built (one per sweep of a pass)
+    int32_t pa, pb;           // tile bit positions of the two resident codes, pa < pb
+    int32_t first_mu, n_mu;   // pass-local micro-op range
+    int32_t lscale, sscale;   // offsets into the pass coefficient area (16 scales) or -1
+    uint32_t gtop;            // swizzled byte offset separating a thread's two groups
+    int32_t pad;
+    uint32_t lA[4], lB[4];    // load : byte offset of register e = lA[e >> 2] ^ lB[e & 3]   (swizzled, pre-shifted)
+    uint32_t sA[4], sB[4];    // store: same
+};
+
+struct MuX {                  // 16 bytes
+    int32_t kind;             // MuKind (CHAIN_* and FIX_* share a code path: `off` points at a 4x4 either way)
+    int32_t off;              // offset (doubles) into the pass coefficient area [chain matrices | fixed coefficients]
+    int32_t unital;           // 4x4: row 0 = column 0 = e0 -> only the 3x3 block acts
+    int32_t pad;
+};
+
+struct StreamArgs {
+    const SweepX* sweeps;
+    const MuX* mus;
+    const double* coefs;          // fixed coefficient table of the plan
+    const double* chainmats;      // [chunk][total_chains][16]
+    int n_sweeps, n_mus, n_coefs;
+    int total_chains, first_chain, n_chains;
+    int n, k;
+    int load, pad0;
+    double* state;                // [chunk][4^n]
+    // tile <-> global index maps (load side / store side: a pass may write the state in a different qubit order)
+    int n_truns_l, n_oruns_l, n_truns_s, n_oruns_s;
+    int truns_l[8][3], oruns_l[8][3], truns_s[8][3], oruns_s[8][3];   // (lshift, gshift, width)
+    uint32_t giter_l[16], giter_s[16];   // global index contribution of staging iteration j (element pair j * 2 * THREADS)
+    uint32_t siter[16];                  // swizzled tile index of the same
+    uint32_t init_mask;                  // first pass: coefficient is 1 when (global index & init_mask) == 0
+};
+
+__host__ __device__ __forceinline__ unsigned parity32(unsigned v) {
+#ifdef __CUDA_ARCH__
+    return __popc(v) & 1u;
+#else
+    return (unsigned)__builtin_popcount(v) & 1u;
+#endif
+}
+
+// Same bank swizzle as dmx_tile_kernel (see dmx_exec.cu): GF(2)-linear, touches only the low 4 index bits.
+__host__ __device__ __forceinline__ unsigned swz_hd(unsigned i) {
+    const unsigned M0 = (1u << 4) | (1u << 5) | (1u << 7) | (1u << 9) | (1u << 10);
+    const unsigned M1 = (1u << 5) | (1u << 6) | (1u << 9) | (1u << 11) | (1u << 12) | (1u << 13);
+    const unsigned M2 = (1u << 5) | (1u << 6) | (1u << 8) | (1u << 9) | (1u << 11) | (1u << 12);
+    const unsigned M3 = (1u << 4) | (1u << 5) | (1u << 6) | (1u << 7) | (1u << 10) | (1u << 12) | (1u << 13);
+    const unsigned h = parity32(i & M0) | (parity32(i & M1) << 1) | (parity32(i & M2) << 2) | (parity32(i & M3) << 3);
+    return i ^ h;
+}
+
+__host__ __device__ __forceinline__ unsigned insert2_hd(unsigned g, int p) { return ((g >> p) << (p + 2)) | (g & ((1u << p) - 1u)); }
+
+}  // namespace dmx
+
+#ifdef __CUDACC__
+
+namespace dmx {
+
+__device__ __forceinline__ unsigned map_runs(unsigned v, const int (*runs)[3], int n) {
+    unsigned g = 0;
+    for (int i = 0; i < n; ++i) g |= ((v >> runs[i][0]) & ((1u << runs[i][2]) - 1u)) << runs[i][1];
+    return g;
+}
+
+// ---- per-circuit chain matrices, once per (circuit, chain) ---------------------------------------------------
+__global__ void dmx_chain_kernel(const ChainDev* __restrict__ chains, const ChainFactor* __restrict__ factors,
+                                 const double* __restrict__ coefs, const RotInfo* __restrict__ rots,
+                                 const double* __restrict__ params, int n_params, int total_chains, long long chunk,
+                                 long long circuit_offset, double* __restrict__ out) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= chunk * total_chains) return;
+    const long long c = i / total_chains;
+    const int chn = (int)(i - c * total_chains);
+    const long long b = c + circuit_offset;
+    double M[16];
+#pragma unroll
+    for (int e = 0; e < 16; ++e) M[e] = (e % 5 == 0) ? 1.0 : 0.0;
+    const ChainDev ch = chains[chn];
+    for (int f = 0; f < ch.n_factors; ++f) {
+        const ChainFactor fa = factors[ch.first_factor + f];
+        const double* __restrict__ cf = coefs + fa.coef;
+        double F[16];
+        if (fa.kind == 0) {
+#pragma unroll
+            for (int e = 0; e < 16; ++e) F[e] = cf[e];
+        } else {
+            const RotInfo ri = rots[fa.rot_id];
+            double sv, cv;
+            sincos(ri.scale * params[b * n_params + ri.param] + ri.offset, &sv, &cv);
+#pragma unroll
+            for (int e = 0; e < 16; ++e) F[e] = cf[e] + cv * cf[16 + e] + sv * cf[32 + e];
+        }
+        double T[16];
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+#pragma unroll
+            for (int cc = 0; cc < 4; ++cc)
+                T[r * 4 + cc] = F[r * 4] * M[cc] + F[r * 4 + 1] * M[4 + cc] + F[r * 4 + 2] * M[8 + cc] + F[r * 4 + 3] * M[12 + cc];
+#pragma unroll
+        for (int e = 0; e < 16; ++e) M[e] = T[e];
+    }
+    double2* dst = reinterpret_cast<double2*>(out + i * 16);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) dst[e] = make_double2(M[2 * e], M[2 * e + 1]);
+}
+
+// ---- register-level micro-ops on the two groups of a thread --------------------------------------------------
+// group element e = 4 * code(A) + code(B)
+template <int SA, int SB>   // strides of the acted-on code (SA) and the spectator code (SB) in e
+__device__ __forceinline__ void apply3(double (&v)[16], const double* __restrict__ M) {
+    const double m5 = M[5], m6 = M[6], m7 = M[7], m9 = M[9], m10 = M[10], m11 = M[11], m13 = M[13], m14 = M[14], m15 = M[15];
+#pragma unroll
+    for (int s = 0; s < 4; ++s) {
+        const double a = v[SA + s * SB], b = v[2 * SA + s * SB], c = v[3 * SA + s * SB];
+        v[SA + s * SB] = m5 * a + m6 * b + m7 * c;
+        v[2 * SA + s * SB] = m9 * a + m10 * b + m11 * c;
+        v[3 * SA + s * SB] = m13 * a + m14 * b + m15 * c;
+    }
+}
+
+template <int SA, int SB>
+__device__ __forceinline__ void apply4(double (&v)[16], const double* __restrict__ M) {
+    double m[16];
+#pragma unroll
+    for (int e = 0; e < 16; ++e) m[e] = M[e];
+#pragma unroll
+    for (int s = 0; s < 4; ++s) {
+        const double a = v[s * SB], b = v[SA + s * SB], c = v[2 * SA + s * SB], d = v[3 * SA + s * SB];
+        v[s * SB] = m[0] * a + m[1] * b + m[2] * c + m[3] * d;
+        v[SA + s * SB] = m[4] * a + m[5] * b + m[6] * c + m[7] * d;
+        v[2 * SA + s * SB] = m[8] * a + m[9] * b + m[10] * c + m[11] * d;
+        v[3 * SA + s * SB] = m[12] * a + m[13] * b + m[14] * c + m[15] * d;
+    }
+}
+
+// Both groups get the same matrix: the coefficients are loaded from shared memory once.
+template <int SA, int SB>
+__device__ __forceinline__ void apply3x2(double (&v0)[16], double (&v1)[16], const double* __restrict__ M) {
+    const double m5 = M[5], m6 = M[6], m7 = M[7], m9 = M[9], m10 = M[10], m11 = M[11], m13 = M[13], m14 = M[14], m15 = M[15];
+#pragma unroll
+    for (int s = 0; s < 4; ++s) {
+        {
+            const double a = v0[SA + s * SB], b = v0[2 * SA + s * SB], c = v0[3 * SA + s * SB];
+            v0[SA + s * SB] = m5 * a + m6 * b + m7 * c;
+            v0[2 * SA + s * SB] = m9 * a + m10 * b + m11 * c;
+            v0[3 * SA + s * SB] = m13 * a + m14 * b + m15 * c;
+        }
+        {
+            const double a = v1[SA + s * SB], b = v1[2 * SA + s * SB], c = v1[3 * SA + s * SB];
+            v1[SA + s * SB] = m5 * a + m6 * b + m7 * c;
+            v1[2 * SA + s * SB] = m9 * a + m10 * b + m11 * c;
+            v1[3 * SA + s * SB] = m13 * a + m14 * b + m15 * c;
+        }
+    }
+}
+
+__device__ __forceinline__ void dense16x(double (&v)[16], const double* __restrict__ M) {
+    double nv[16];
+#pragma unroll
+    for (int r = 0; r < 16; ++r) {
+        double s = 0.0;
+#pragma unroll
+        for (int c = 0; c < 16; ++c) s += M[r * 16 + c] * v[c];
+        nv[r] = s;
+    }
+#pragma unroll
+    for (int e = 0; e < 16; ++e) v[e] = nv[e];
+}
+
+extern __shared__ __align__(16) double dmx_stream_smem[];
+
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS, THREADS == 512 ? 1 : 4) dmx_stream_kernel(const __grid_constant__ StreamArgs a) {
+    constexpr int NITER = 16;                               // 4^k / (2 * THREADS) staging iterations (k = 6: 128 thr, k = 7: 512 thr)
+    const unsigned E = 32u * THREADS;                       // tile elements
+    double* tile = dmx_stream_smem;
+    double* cf = tile + E;                                  // [n_chains*16 chain matrices | n_coefs fixed coefficients]
+    const int n_cf = a.n_chains * 16 + a.n_coefs;
+    SweepX* sws = reinterpret_cast<SweepX*>(cf + ((n_cf + 1) & ~1));
+    MuX* mus = reinterpret_cast<MuX*>(sws + a.n_sweeps);
+    char* const tb = reinterpret_cast<char*>(tile);
+    const int tid = threadIdx.x;
+
+    const unsigned tiles_per_circuit = 1u << (2 * (a.n - a.k));
+    const long long circuit = blockIdx.x / tiles_per_circuit;
+    const unsigned tile_id = blockIdx.x % tiles_per_circuit;
+    double* const st = a.state + (circuit << (2 * a.n));
+
+    // ---- pass tables -> shared memory ----
+    {
+        const double* cm = a.chainmats + ((size_t)circuit * a.total_chains + a.first_chain) * 16;
+        for (int i = tid; i < a.n_chains * 16; i += THREADS) cf[i] = cm[i];
+        for (int i = tid; i < a.n_coefs; i += THREADS) cf[a.n_chains * 16 + i] = a.coefs[i];
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(a.sweeps);
+        uint32_t* dst = reinterpret_cast<uint32_t*>(sws);
+        const int nw = a.n_sweeps * (int)(sizeof(SweepX) / 4) + a.n_mus * (int)(sizeof(MuX) / 4);   // mus follow the sweeps in both places
+        for (int i = tid; i < nw; i += THREADS) dst[i] = src[i];
+    }
+
+    // ---- tile load / init ----
+    const unsigned s_thr = swz_hd(2u * tid);
+    if (a.load) {
+        const unsigned gbase = map_runs(2u * tid, a.truns_l, a.n_truns_l) | map_runs(tile_id, a.oruns_l, a.n_oruns_l);
+        double2 x[NITER];
+#pragma unroll
+        for (int j = 0; j < NITER; ++j) x[j] = __ldcs(reinterpret_cast<const double2*>(st + (gbase | a.giter_l[j])));
+#pragma unroll
+        for (int j = 0; j < NITER; ++j) {
+            const unsigned sp = s_thr ^ a.siter[j];
+            const bool flip = sp & 1u;       // the pair (i, i+1) stays adjacent under the swizzle, possibly swapped
+            *reinterpret_cast<double2*>(tile + (sp & ~1u)) = flip ? make_double2(x[j].y, x[j].x) : x[j];
+        }
+    } else {
+        const unsigned gbase = map_runs(2u * tid, a.truns_s, a.n_truns_s) | map_runs(tile_id, a.oruns_s, a.n_oruns_s);
+#pragma unroll
+        for (int j = 0; j < NITER; ++j) {
+            const unsigned g = gbase | a.giter_s[j];     // the initial state is symmetric under qubit relabelling: any order works
+            const unsigned sp = s_thr ^ a.siter[j];
+            const double e0 = (g & a.init_mask) ? 0.0 : 1.0, e1 = ((g | 1u) & a.init_mask) ? 0.0 : 1.0;
+            const bool flip = sp & 1u;
+            *reinterpret_cast<double2*>(tile + (sp & ~1u)) = flip ? make_double2(e1, e0) : make_double2(e0, e1);
+        }
+    }
+    __syncthreads();
+
+    // ---- sweeps ----
+    for (int si = 0; si < a.n_sweeps; ++si) {
+        const SweepX& sw = sws[si];
+        const unsigned sb0 = swz_hd(insert2_hd(insert2_hd((unsigned)tid, sw.pa), sw.pb)) << 3;
+        const unsigned sb1 = sb0 ^ sw.gtop;
+        double v0[16], v1[16];
+        {
+            unsigned mA[4], mB[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { mA[j] = sw.lA[j]; mB[j] = sw.lB[j]; }
+#pragma unroll
+            for (int e = 0; e < 16; ++e) {
+                const unsigned off = mA[e >> 2] ^ mB[e & 3];
+                v0[e] = *reinterpret_cast<const double*>(tb + (sb0 ^ off));
+                v1[e] = *reinterpret_cast<const double*>(tb + (sb1 ^ off));
+            }
+            if (sw.lscale >= 0) {
+                const double* __restrict__ lc = cf + sw.lscale;
+#pragma unroll
+                for (int e = 0; e < 16; ++e) { const double s = lc[e]; v0[e] *= s; v1[e] *= s; }
+            }
+        }
+        for (int mi = 0; mi < sw.n_mu; ++mi) {
+            const MuX m = mus[sw.first_mu + mi];
+            const double* __restrict__ M = cf + m.off;
+            switch (m.kind) {
+                case MU_CHAIN_A: case MU_FIX_A:
+                    if (m.unital) apply3x2<4, 1>(v0, v1, M);
+                    else { apply4<4, 1>(v0, M); apply4<4, 1>(v1, M); }
+                    break;
+                case MU_CHAIN_B: case MU_FIX_B:
+                    if (m.unital) apply3x2<1, 4>(v0, v1, M);
+                    else { apply4<1, 4>(v0, M); apply4<1, 4>(v1, M); }
+                    break;
+                case MU_DIAG_A: {
+                    const double d0 = M[0], d1 = M[1], d2 = M[2], d3 = M[3];
+#pragma unroll
+                    for (int s = 0; s < 4; ++s) {
+                        v0[s] *= d0; v0[4 + s] *= d1; v0[8 + s] *= d2; v0[12 + s] *= d3;
+                        v1[s] *= d0; v1[4 + s] *= d1; v1[8 + s] *= d2; v1[12 + s] *= d3;
+                    }
+                    break;
+                }
+                case MU_DIAG_B: {
+                    const double d0 = M[0], d1 = M[1], d2 = M[2], d3 = M[3];
+#pragma unroll
+                    for (int s = 0; s < 4; ++s) {
+                        v0[4 * s] *= d0; v0[4 * s + 1] *= d1; v0[4 * s + 2] *= d2; v0[4 * s + 3] *= d3;
+                        v1[4 * s] *= d0; v1[4 * s + 1] *= d1; v1[4 * s + 2] *= d2; v1[4 * s + 3] *= d3;
+                    }
+                    break;
+                }
+                case MU_DIAG2:
+#pragma unroll
+                    for (int e = 0; e < 16; ++e) { const double s = M[e]; v0[e] *= s; v1[e] *= s; }
+                    break;
+                default:   // MU_MAT2
+                    dense16x(v0, M);
+                    dense16x(v1, M);
+                    break;
+            }
+        }
+        {
+            unsigned mA[4], mB[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { mA[j] = sw.sA[j]; mB[j] = sw.sB[j]; }
+            if (sw.sscale >= 0) {
+                const double* __restrict__ sc = cf + sw.sscale;
+#pragma unroll
+                for (int e = 0; e < 16; ++e) { const double s = sc[e]; v0[e] *= s; v1[e] *= s; }
+            }
+#pragma unroll
+            for (int e = 0; e < 16; ++e) {
+                const unsigned off = mA[e >> 2] ^ mB[e & 3];
+                *reinterpret_cast<double*>(tb + (sb0 ^ off)) = v0[e];
+                *reinterpret_cast<double*>(tb + (sb1 ^ off)) = v1[e];
+            }
+        }
+        __syncthreads();
+    }
+
+    // ---- tile store ----
+    {
+        const unsigned gbase = map_runs(2u * tid, a.truns_s, a.n_truns_s) | map_runs(tile_id, a.oruns_s, a.n_oruns_s);
+#pragma unroll
+        for (int j = 0; j < NITER; ++j) {
+            const unsigned sp = s_thr ^ a.siter[j];
+            const double2 x = *reinterpret_cast<const double2*>(tile + (sp & ~1u));
+            const bool flip = sp & 1u;
+            *reinterpret_cast<double2*>(st + (gbase | a.giter_s[j])) = flip ? make_double2(x.y, x.x) : x;
+        }
+    }
+}
+
+}  // namespace dmx
+
+#endif  // __CUDACC__
