@@ -102,6 +102,9 @@ typedef struct dmx_plan_info {
     double smem_bytes_per_circuit;/* shared-memory bytes moved per circuit */
     double canonical_flops_per_circuit; /* SURVEY.md §8d cost model (complex rho) for the same circuit */
     double canonical_hbm_bytes_per_circuit;
+    int64_t workspace_bytes_per_state; /* streaming path: workspace the engine needs per circuit in flight
+                                          (state_bytes, or 2 * state_bytes when passes re-order the qubits and
+                                          therefore ping-pong between two buffers); 0 otherwise */
 } dmx_plan_info;
 
 int dmx_version(void);

@@ -46,7 +46,9 @@ def parse(dump: str) -> dict:
                     b[k] = float(kv[k])
             plan["blocks"].append(b)
         elif head == "pass":
-            plan["passes"].append({"first_phase": int(kv["first_phase"]), "nphases": int(kv["nphases"]), "tile": _nums(kv["tile"], int)})
+            plan["passes"].append({"first_phase": int(kv["first_phase"]), "nphases": int(kv["nphases"]), "tile": _nums(kv["tile"], int),
+                                   "pos_in": _nums(kv["pos_in"], int) if "pos_in" in kv else None,
+                                   "pos_out": _nums(kv["pos_out"], int) if "pos_out" in kv else None})
         elif head == "phase":
             plan["phases"].append({k: int(kv[k]) for k in ("first_sweep", "nsweeps", "first_chain", "nchains")})
         elif head == "sweep":

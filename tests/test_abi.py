@@ -32,7 +32,7 @@ def test_header_symbols_exported_and_bound():
 
 def test_struct_layout_matches_header():
     assert C.sizeof(_lib.DmxOp) == 56
-    assert C.sizeof(_lib.DmxPlanInfo) == 10 * 4 + 8 + 5 * 8
+    assert C.sizeof(_lib.DmxPlanInfo) == 10 * 4 + 8 + 5 * 8 + 8
 
 
 def test_error_codes_and_messages():

@@ -143,15 +143,31 @@ def test_streaming_schedule_partitions_all_blocks():
             ops += [("u", (q, q + 1), O.CNOT), ("k", (q, q + 1), O.two_qubit_depolarize(1e-3))]
     rng = np.random.default_rng(1)
     terms = random_hamiltonian(rng, n, 5)
-    for tile in (4, 5, 7):
-        prog = build_program(ops, n, terms, tile_qubits=tile)
+    for tile, remap in ((4, 1), (5, 1), (7, 0), (6, 1), (7, 1)):
+        prog = build_program(ops, n, terms, tile_qubits=tile, remap=remap)
         plan = PI.parse(prog.dump())
         assert prog.info["path"] == 2
         assert sum(p["nphases"] for p in plan["passes"]) == len(plan["phases"])
         assert sum(ph["nsweeps"] for ph in plan["phases"]) == len(plan["sweeps"])
         assert len(plan["sweeps"]) < len(plan["blocks"])     # several fused blocks per shared-memory round trip
-        for p in plan["passes"]:
-            assert len(p["tile"]) == tile and n - 1 in p["tile"] and n - 2 in p["tile"]
+        if remap and tile >= 6:
+            # remapping scheduler: consecutive tiles share the two qubits that sit lowest in the layout between them,
+            # layouts chain from pass to pass and the last pass restores the standard order
+            std = [n - 1 - q for q in range(n)]
+            passes = plan["passes"]
+            assert list(passes[-1]["pos_out"]) == std
+            for a, b in zip(passes[:-1], passes[1:]):
+                assert list(a["pos_out"]) == list(b["pos_in"])
+                low = [q for q in range(n) if a["pos_out"][q] < 2]
+                assert len(low) == 2 and all(q in a["tile"] and q in b["tile"] for q in low)
+            for p in passes:
+                assert len(p["tile"]) == tile and sorted(p["pos_out"]) == list(range(n))
+                tile_pos = [p["pos_out"][q] for q in p["tile"]]
+                assert tile_pos == sorted(tile_pos, reverse=True)      # tile-local order = order of the stored layout
+        else:
+            for p in plan["passes"]:
+                assert p["pos_in"] is None
+                assert len(p["tile"]) == tile and n - 1 in p["tile"] and n - 2 in p["tile"]
         vals = rng.uniform(-1, 1, size=prog.n_params)
         r = PI.run_devops(plan, vals)
         rho = O.simulate(n, resolve(ops, prog.param_names, vals))

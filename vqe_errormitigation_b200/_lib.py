@@ -35,7 +35,7 @@ class DmxPlanInfo(C.Structure):
                 ("path", C.c_int32), ("n_terms", C.c_int32), ("state_bytes", C.c_int64),
                 ("flops_per_circuit", C.c_double), ("hbm_bytes_per_circuit", C.c_double),
                 ("smem_bytes_per_circuit", C.c_double), ("canonical_flops_per_circuit", C.c_double),
-                ("canonical_hbm_bytes_per_circuit", C.c_double)]
+                ("canonical_hbm_bytes_per_circuit", C.c_double), ("workspace_bytes_per_state", C.c_int64)]
 
     def as_dict(self):
         return {name: getattr(self, name) for name, _ in self._fields_}

@@ -765,7 +765,9 @@ struct DevPlan {
     // streaming passes in the form dmx_stream_kernel executes (dmx_stream.cuh); !ok -> generic dmx_tile_kernel
     struct PassX {
         bool ok = false;
-        void* tables = nullptr;      // device: [SweepX x n_sweeps][MuX x n_mus]
+        std::vector<SweepX> sweeps;  // travel in the kernel parameters
+        std::vector<MuX> mus;
+        bool general = false;        // needs the 4x4 / dense micro-ops
         double* coefs = nullptr;     // device: pass-local fixed coefficients
         int n_sweeps = 0, n_mus = 0, n_coefs = 0, first_chain = 0, n_chains = 0;
         size_t smem = 0;
@@ -795,8 +797,8 @@ static cudaError_t build_stream_tables(const Plan& p, DevPlan* d) {
         const int k = (int)ps.tile_q.size();
         if (k != 6 && k != 7) continue;
         const int threads = k == 7 ? 512 : 128;
-        if (ps.n_phases < 1) continue;
-        px.first_chain = p.phases[ps.first_phase].first_chain;
+        if (ps.n_phases > 0 && !pass_stream_eligible(p, ps)) continue;
+        px.first_chain = ps.n_phases > 0 ? p.phases[ps.first_phase].first_chain : 0;
         px.n_chains = 0;
         for (int ph = 0; ph < ps.n_phases; ++ph) px.n_chains += p.phases[ps.first_phase + ph].n_chains;
         std::vector<SweepX> sx;
@@ -807,6 +809,7 @@ static cudaError_t build_stream_tables(const Plan& p, DevPlan* d) {
             auto key = std::make_pair(off, len);
             auto it = where.find(key);
             if (it != where.end()) return it->second;
+            if (lc.size() & 1) lc.push_back(0.0);     // 16-byte alignment of every table
             int at = (int)lc.size();
             lc.insert(lc.end(), p.coefs.begin() + off, p.coefs.begin() + off + len);
             where.emplace(key, at);
@@ -836,12 +839,12 @@ static cudaError_t build_stream_tables(const Plan& p, DevPlan* d) {
                     y.kind = m.kind;
                     switch (m.kind) {
                         case MU_CHAIN_A: case MU_CHAIN_B:
-                            y.off = (phase.first_chain + m.a0 - px.first_chain) * 16; y.unital = m.a3; break;
+                            y.off = (phase.first_chain + m.a0 - px.first_chain) * 16; y.unital = m.a3; px.general |= !m.a3; break;
                         case MU_FIX_A: case MU_FIX_B:
-                            y.off = px.n_chains * 16 + local(m.a0, 16); y.unital = m.a3; break;
+                            y.off = px.n_chains * 16 + local(m.a0, 16); y.unital = m.a3; px.general |= !m.a3; break;
                         case MU_DIAG_A: case MU_DIAG_B: y.off = px.n_chains * 16 + local(m.a0, 4); break;
                         case MU_DIAG2: y.off = px.n_chains * 16 + local(m.a0, 16); break;
-                        case MU_MAT2: y.off = px.n_chains * 16 + local(m.a0, 256); break;
+                        case MU_MAT2: y.off = px.n_chains * 16 + local(m.a0, 256); px.general = true; break;
                         default: ok = false; break;     // variant micro-ops: generic kernel
                     }
                     mx.push_back(y);
@@ -849,18 +852,13 @@ static cudaError_t build_stream_tables(const Plan& p, DevPlan* d) {
                 sx.push_back(x);
             }
         }
-        if (!ok) continue;
+        if (!ok || sx.size() > (size_t)STREAM_MAX_SWEEPS || mx.size() > (size_t)STREAM_MAX_MUS) continue;
         px.n_sweeps = (int)sx.size(); px.n_mus = (int)mx.size(); px.n_coefs = (int)lc.size();
-        const size_t n_cf = ((size_t)px.n_chains * 16 + lc.size() + 1) & ~(size_t)1;
-        px.smem = ((size_t)32 * threads + n_cf) * 8 + sx.size() * sizeof(SweepX) + mx.size() * sizeof(MuX);
+        px.smem = ((size_t)32 * threads + (size_t)px.n_chains * 16 + lc.size() + 2) * 8;
         if (px.smem > (k == 7 ? 227u : 56u) * 1024) continue;       // k = 6: keep four CTAs per SM
-        std::vector<char> blob(sx.size() * sizeof(SweepX) + mx.size() * sizeof(MuX) + 16);
-        std::memcpy(blob.data(), sx.data(), sx.size() * sizeof(SweepX));
-        std::memcpy(blob.data() + sx.size() * sizeof(SweepX), mx.data(), mx.size() * sizeof(MuX));
-        cudaError_t e = upload((char**)&px.tables, blob);
-        if (e != cudaSuccess) return e;
+        px.sweeps = sx; px.mus = mx;
         if (lc.empty()) lc.push_back(0.0);
-        e = upload(&px.coefs, lc);
+        cudaError_t e = upload(&px.coefs, lc);
         if (e != cudaSuccess) return e;
         px.ok = true;
     }
@@ -939,7 +937,7 @@ static void free_device(Plan& p) {
     cudaFree(d->coefs); cudaFree(d->rots); cudaFree(d->term_idx); cudaFree(d->term_coef);
     cudaFree(d->f_w); cudaFree(d->f_segs); cudaFree(d->f_classes); cudaFree(d->f_init); cudaFree(d->f_eweight); cudaFree(d->f_eslot);
     cudaFree(d->slots); cudaFree(d->labels); cudaFree(d->worklist);
-    for (auto& px : d->passx) { cudaFree(px.tables); cudaFree(px.coefs); }
+    for (auto& px : d->passx) cudaFree(px.coefs);
     if (d->h_stage) cudaFreeHost(d->h_stage);
     if (d->d_stage) cudaFree(d->d_stage);
     if (d->stream) cudaStreamDestroy(d->stream);
@@ -1035,7 +1033,7 @@ static int run_tile_single(Plan& p, DevPlan* d, long long batch, const double* p
 static int g_stream_kernel = 1;        // option "stream_kernel": 0 -> generic dmx_tile_kernel for every pass
 static long long g_stream_chunk = 0;   // option "stream_chunk": circuits per pass launch (0: auto, ~64 MiB of states stay in L2)
 
-template <int THREADS>
+template <int THREADS, bool GENERAL>
 static int launch_stream(const StreamArgs& a, long long grid, size_t smem, cudaStream_t st) {
     static std::mutex mu;
     static size_t configured = 0;
@@ -1043,12 +1041,12 @@ static int launch_stream(const StreamArgs& a, long long grid, size_t smem, cudaS
         std::lock_guard<std::mutex> lock(mu);
         if (smem > configured) {
             const int want = (int)std::max(smem, (size_t)48 * 1024);
-            CUDA_TRY(cudaFuncSetAttribute(dmx_stream_kernel<THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, want));
-            CUDA_TRY(cudaFuncSetAttribute(dmx_stream_kernel<THREADS>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+            CUDA_TRY(cudaFuncSetAttribute(dmx_stream_kernel<THREADS, GENERAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, want));
+            CUDA_TRY(cudaFuncSetAttribute(dmx_stream_kernel<THREADS, GENERAL>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
             configured = want;
         }
     }
-    dmx_stream_kernel<THREADS><<<(unsigned)grid, THREADS, smem, st>>>(a);
+    dmx_stream_kernel<THREADS, GENERAL><<<(unsigned)grid, THREADS, smem, st>>>(a);
     ++g_launches;
     CUDA_TRY(cudaGetLastError());
     return DMX_OK;
@@ -1061,8 +1059,11 @@ static unsigned map_runs_host(unsigned v, const BitRun* runs, int n) {
 }
 
 // Streaming execution (n > tile_k): state[chunk][4^n] in `state`; all passes over one chunk of circuits.
+// Remapped plans ping-pong between `state` and `state2` (a tile's load and store address sets differ, so a pass cannot
+// run in place); the last pass always lands in `state`.
 static int run_streaming(Plan& p, DevPlan* d, long long chunk, long long circuit_offset, const double* params, const uint8_t* variants,
-                         double* state, cudaStream_t st) {
+                         double* state, double* state2, cudaStream_t st) {
+    if (p.remapped && !state2) return fail(DMX_ERR_INVALID, "remapped plan needs a second state buffer");
     const int total_chains = (int)p.chains.size();
     bool any_x = false;
     for (const auto& px : d->passx) any_x |= px.ok && g_stream_kernel;
@@ -1088,38 +1089,60 @@ static int run_streaming(Plan& p, DevPlan* d, long long chunk, long long circuit
         }
         BitRun truns[8], oruns[8];
         int n_truns = 0, n_oruns = 0;
+        const long long groups = chunk << (2 * (p.n - k));
+        if (groups >= (1LL << 31)) { rc = fail(DMX_ERR_UNSUPPORTED, "streaming chunk too large for one launch"); break; }
+        const DevPlan::PassX& px = d->passx[pi];
+        if (!ps.pos_in.empty() && !(px.ok && g_stream_kernel)) { rc = fail(DMX_ERR_STATE, "remapped plan needs the stream kernel"); break; }
+        if (px.ok && g_stream_kernel) {
+            StreamArgs a{};
+            std::copy(px.sweeps.begin(), px.sweeps.end(), a.sweeps);
+            std::copy(px.mus.begin(), px.mus.end(), a.mus);
+            a.coefs = px.coefs; a.chainmats = chainmats;
+            a.n_sweeps = px.n_sweeps; a.n_mus = px.n_mus; a.n_coefs = px.n_coefs;
+            a.total_chains = total_chains; a.first_chain = px.first_chain; a.n_chains = px.n_chains;
+            a.n = p.n; a.k = k; a.load = pi > 0;
+            {
+                const size_t last = p.passes.size() - 1;
+                double* bufs[2] = {state, p.remapped ? state2 : state};
+                a.dst = bufs[(last - pi) & 1];
+                a.src = bufs[(last - pi + 1) & 1];
+            }
+            std::vector<int> std_pos(p.n);
+            for (int q = 0; q < p.n; ++q) std_pos[q] = p.n - 1 - q;
+            const unsigned threads = k == 7 ? 512u : 128u;
+            auto side = [&](const std::vector<int>& pos, int& n_gruns, int& n_oruns, int (*gruns)[3], int (*uruns)[3], int (*oruns)[3],
+                            uint32_t* giter, uint32_t* siter, uint32_t& pbit) {
+                std::vector<int> tq = ps.tile_q;                  // tile_q[i] sits at tile bits 2*(k-1-i)
+                std::vector<int> tl(p.n, -1);
+                for (int i = 0; i < k; ++i) tl[tq[i]] = k - 1 - i;
+                std::sort(tq.begin(), tq.end(), [&](int x, int y) { return pos[x] < pos[y]; });
+                n_gruns = k;
+                for (int i = 0; i < k; ++i) {
+                    gruns[i][0] = 2 * i; gruns[i][1] = 2 * pos[tq[i]]; gruns[i][2] = 2;
+                    uruns[i][0] = 2 * i; uruns[i][1] = 2 * tl[tq[i]]; uruns[i][2] = 2;
+                }
+                n_oruns = (int)others.size();
+                for (int i = 0; i < n_oruns; ++i) { oruns[i][0] = 2 * i; oruns[i][1] = 2 * pos[others[i]]; oruns[i][2] = 2; }
+                auto dep = [&](unsigned v, int (*runs)[3]) {
+                    unsigned g = 0;
+                    for (int i = 0; i < k; ++i) g |= ((v >> runs[i][0]) & 3u) << runs[i][1];
+                    return g;
+                };
+                for (unsigned j = 0; j < 16; ++j) { giter[j] = dep(j * 2u * threads, gruns); siter[j] = swz_hd(dep(j * 2u * threads, uruns)); }
+                pbit = swz_hd(dep(1u, uruns));
+            };
+            if ((int)others.size() > 8) { rc = fail(DMX_ERR_UNSUPPORTED, "more than 8 non-resident qubits"); break; }
+            side(ps.pos_in.empty() ? std_pos : ps.pos_in, a.n_gruns_l, a.n_oruns_l, a.gruns_l, a.uruns_l, a.oruns_l, a.giter_l, a.siter_l, a.pbit_l);
+            side(ps.pos_out.empty() ? std_pos : ps.pos_out, a.n_gruns_s, a.n_oruns_s, a.gruns_s, a.uruns_s, a.oruns_s, a.giter_s, a.siter_s, a.pbit_s);
+            a.init_mask = 0xAAAAAAAAu;
+            if (k == 7) rc = px.general ? launch_stream<512, true>(a, groups, px.smem, st) : launch_stream<512, false>(a, groups, px.smem, st);
+            else rc = px.general ? launch_stream<128, true>(a, groups, px.smem, st) : launch_stream<128, false>(a, groups, px.smem, st);
+            continue;
+        }
         try {
             make_runs(ps.tile_q, p.n, truns, &n_truns);
             make_runs(others, p.n, oruns, &n_oruns);
         } catch (const std::exception& e) { rc = fail(DMX_ERR_UNSUPPORTED, e.what()); break; }
-        const long long groups = chunk << (2 * (p.n - k));
-        if (groups >= (1LL << 31)) { rc = fail(DMX_ERR_UNSUPPORTED, "streaming chunk too large for one launch"); break; }
-        const DevPlan::PassX& px = d->passx[pi];
-        if (px.ok && g_stream_kernel) {
-            StreamArgs a{};
-            a.sweeps = (const SweepX*)px.tables;
-            a.mus = (const MuX*)((const char*)px.tables + (size_t)px.n_sweeps * sizeof(SweepX));
-            a.coefs = px.coefs; a.chainmats = chainmats;
-            a.n_sweeps = px.n_sweeps; a.n_mus = px.n_mus; a.n_coefs = px.n_coefs;
-            a.total_chains = total_chains; a.first_chain = px.first_chain; a.n_chains = px.n_chains;
-            a.n = p.n; a.k = k; a.load = pi > 0; a.state = state;
-            a.n_truns_l = a.n_truns_s = n_truns; a.n_oruns_l = a.n_oruns_s = n_oruns;
-            for (int i = 0; i < 8; ++i) {
-                const int t[3] = {truns[i].lshift, truns[i].gshift, truns[i].width}, o[3] = {oruns[i].lshift, oruns[i].gshift, oruns[i].width};
-                for (int c = 0; c < 3; ++c) {
-                    a.truns_l[i][c] = a.truns_s[i][c] = i < n_truns ? t[c] : 0;
-                    a.oruns_l[i][c] = a.oruns_s[i][c] = i < n_oruns ? o[c] : 0;
-                }
-            }
-            const unsigned threads = k == 7 ? 512u : 128u;
-            for (unsigned j = 0; j < 16; ++j) {
-                a.giter_l[j] = a.giter_s[j] = map_runs_host(j * 2u * threads, truns, n_truns);
-                a.siter[j] = swz_hd(j * 2u * threads);
-            }
-            a.init_mask = 0xAAAAAAAAu;
-            rc = k == 7 ? launch_stream<512>(a, groups, px.smem, st) : launch_stream<128>(a, groups, px.smem, st);
-            continue;
-        }
         TileArgs a{};
         fill_common(a, p, d, ps, params, variants);
         a.k = k; a.cpb = 1; a.pad = 0; a.batch = chunk; a.state = state; a.circuit_offset = circuit_offset;
@@ -1247,6 +1270,8 @@ int dmx_plan_set_option(dmx_plan* plan, const char* key, int value) {
     else if (k == "tile_qubits") {
         if (value < 4 || value > 7) return fail(DMX_ERR_INVALID, "tile_qubits must be in 4..7");
         plan->p.opt_tile_qubits = value;
+    } else if (k == "remap") {
+        plan->p.opt_remap = value != 0;
     } else if (k == "stream_kernel") {
         g_stream_kernel = value != 0;
     } else if (k == "stream_chunk") {
@@ -1300,7 +1325,7 @@ size_t dmx_workspace_bytes(const dmx_plan* plan, int64_t batch) {
     if (!plan || !plan->p.finalized || batch <= 0) return 0;
     if (plan->p.path != 2) return 0;
     // at least one state; more lets several circuits share a launch (caller may pass any multiple)
-    return (size_t)plan->p.info.state_bytes * (size_t)std::min<int64_t>(batch, 64);
+    return (size_t)plan->p.info.workspace_bytes_per_state * (size_t)std::min<int64_t>(batch, 64);
 }
 
 static int check_exec(dmx_plan* plan, int64_t batch, const double* d_params, const void* out) {
@@ -1322,14 +1347,14 @@ static int energy_impl(dmx_plan* plan, int64_t batch, const double* d_params, co
     if (p.path == 1) return run_segment(p, d, batch, d_params, d_variants, d_energy, st);
     if (p.path == 0) return run_tile_single(p, d, batch, d_params, d_variants, d_energy, OUT_ENERGY, nullptr, nullptr, st);
     const size_t sb = (size_t)p.info.state_bytes;
-    long long chunk = (long long)(workspace_bytes / sb);
-    if (!d_workspace || chunk < 1) return fail(DMX_ERR_INVALID, "workspace too small: need dmx_workspace_bytes()");
-    // all passes run over one sub-chunk before the next starts: ~64 MiB of states stay resident in the 126 MB L2
-    const long long sub = g_stream_chunk > 0 ? g_stream_chunk : std::max<long long>(1, (long long)((64u << 20) / sb));
-    chunk = std::min(chunk, sub);
+    const long long cap = (long long)(workspace_bytes / (size_t)p.info.workspace_bytes_per_state);
+    if (!d_workspace || cap < 1) return fail(DMX_ERR_INVALID, "workspace too small: need dmx_workspace_bytes()");
+    double* const state2 = p.remapped ? (double*)((char*)d_workspace + (size_t)cap * sb) : nullptr;
+    // circuits per pass launch: large enough to fill the GPU for several waves ("stream_chunk" overrides)
+    long long chunk = std::min<long long>(cap, g_stream_chunk > 0 ? g_stream_chunk : 64);
     for (long long off = 0; off < batch; off += chunk) {
         long long cur = std::min<long long>(chunk, batch - off);
-        rc = run_streaming(p, d, cur, off, d_params, d_variants, (double*)d_workspace, st);
+        rc = run_streaming(p, d, cur, off, d_params, d_variants, (double*)d_workspace, state2, st);
         if (rc) return rc;
         int threads = 128;
         long long warps = cur;
@@ -1360,8 +1385,12 @@ int dmx_pauli_batch(dmx_plan* plan, int64_t batch, const double* d_params, const
     if (batch == 0) return DMX_OK;
     cudaStream_t st = (cudaStream_t)stream;
     if (p.n <= 7) return run_tile_single(p, d, batch, d_params, d_variants, d_pauli, OUT_PAULI, nullptr, nullptr, st);
-    // streaming: the output buffer is the state buffer
-    return run_streaming(p, d, batch, 0, d_params, d_variants, d_pauli, st);
+    // streaming: the output buffer is the state buffer (remapped plans need a scratch twin for the ping-pong)
+    double* twin = nullptr;
+    if (p.remapped) CUDA_TRY(cudaMallocAsync((void**)&twin, (size_t)batch * (size_t)p.info.state_bytes, st));
+    rc = run_streaming(p, d, batch, 0, d_params, d_variants, d_pauli, twin, st);
+    if (twin) cudaFreeAsync(twin, st);
+    return rc;
 }
 
 int dmx_density_batch(dmx_plan* plan, int64_t batch, const double* d_params, const uint8_t* d_variants, double* d_rho,
@@ -1429,7 +1458,7 @@ int dmx_energy_batch_host(dmx_plan* plan, int64_t batch, const double* h_params,
     auto align = [](size_t v) { return (v + 255) & ~(size_t)255; };
     const size_t pb = align((size_t)batch * p.n_params * 8), vb = h_variants ? align((size_t)batch * p.n_slots) : 0, eb = align((size_t)batch * 8);
     size_t ws = 0;
-    if (p.path == 2) ws = (size_t)p.info.state_bytes * (size_t)std::min<int64_t>(batch, 16);
+    if (p.path == 2) ws = (size_t)p.info.workspace_bytes_per_state * (size_t)std::min<int64_t>(batch, 64);
     const size_t hneed = pb + vb + eb, dneed = hneed + ws;
     if (d->h_cap < hneed) {
         if (d->h_stage) CUDA_TRY(cudaFreeHost(d->h_stage));

@@ -886,6 +886,212 @@ static void schedule_streaming(Plan& p) {
     p.info.smem_bytes_per_circuit = sweeps * 16.0 * std::pow(4.0, n);
 }
 
+bool pass_stream_eligible(const Plan& p, const Pass& ps) {
+    const int k = (int)ps.tile_q.size();
+    if (k != 6 && k != 7) return false;
+    int n_sweeps = 0, n_mus = 0, n_chains = 0;
+    for (int ph = 0; ph < ps.n_phases; ++ph) {
+        const Phase& phase = p.phases[ps.first_phase + ph];
+        n_chains += phase.n_chains;
+        for (int si = 0; si < phase.n_sweeps; ++si) {
+            const SweepDev& sw = p.sweeps[phase.first_sweep + si];
+            ++n_sweeps;
+            n_mus += sw.n_mu;
+            for (int mi = 0; mi < sw.n_mu; ++mi)
+                if (p.mus[sw.first_mu + mi].kind > MU_MAT2) return false;      // variant micro-ops
+        }
+    }
+    if (n_sweeps > STREAM_MAX_SWEEPS || n_mus > STREAM_MAX_MUS) return false;
+    return (size_t)n_chains * 128 + p.coefs.size() * 8 <= (k == 7 ? 90u : 20u) * 1024;
+}
+
+// Remapping pass builder (see Pass::pos_in / pos_out).  Same DAG-greedy block selection as schedule_streaming, but no
+// qubit is pinned: a pass only has to share two qubits with its predecessor; they become the two lowest positions of
+// the layout the predecessor stores (and this pass loads), so every tile is made of >= 128-byte runs on both sides.
+static void schedule_streaming_remap(Plan& p) {
+    const int n = p.n, k = std::min(p.opt_tile_qubits, n);
+    p.tile_k = k;
+    const size_t nb = p.blocks.size();
+    std::vector<std::vector<int>> chain(n);
+    for (size_t i = 0; i < nb; ++i) {
+        chain[p.blocks[i].q[0]].push_back((int)i);
+        if (p.blocks[i].nq == 2) chain[p.blocks[i].q[1]].push_back((int)i);
+    }
+    std::vector<size_t> head(n, 0);
+    size_t remaining = nb;
+    std::vector<std::vector<char>> tiles;
+    std::vector<std::vector<int>> orders;
+    std::vector<char> prev(n, 0);
+    bool have_prev = false;
+    const int BIG = 1 << 30;
+    auto pending = [&](const std::vector<size_t>& h, int q) { return h[q] < chain[q].size() ? chain[q][h[q]] : BIG; };
+
+    // earliest-first growth of a tile from `seeds` (the original greedy), then fill up to k qubits
+    auto grow = [&](std::vector<char> in_tile, int first_block) {
+        std::vector<size_t> h = head;
+        int count = 0;
+        for (int q = 0; q < n; ++q) count += in_tile[q];
+        auto take = [&](int i) {
+            const Block& b = p.blocks[i];
+            for (int s = 0; s < b.nq; ++s) {
+                if (!in_tile[b.q[s]]) { in_tile[b.q[s]] = 1; ++count; }
+                ++h[b.q[s]];
+            }
+        };
+        if (first_block >= 0) take(first_block);
+        while (true) {
+            int best = -1;
+            for (int q0 = 0; q0 < n; ++q0) {
+                if (h[q0] >= chain[q0].size()) continue;
+                int i = chain[q0][h[q0]];
+                if (best >= 0 && i >= best) continue;
+                const Block& b = p.blocks[i];
+                bool ready = true;
+                int need = 0;
+                for (int s = 0; s < b.nq; ++s) {
+                    int q = b.q[s];
+                    if (h[q] >= chain[q].size() || chain[q][h[q]] != i) ready = false;
+                    if (!in_tile[q]) ++need;
+                }
+                if (!ready || count + need > k) continue;
+                best = i;
+            }
+            if (best < 0) break;
+            take(best);
+        }
+        // fill: qubits of the previous tile first (they can be the shared low pair), then the most urgent ones
+        std::vector<int> cand;
+        for (int q = 0; q < n; ++q) if (!in_tile[q]) cand.push_back(q);
+        std::stable_sort(cand.begin(), cand.end(), [&](int a, int b) {
+            const int pa = have_prev && prev[a] ? 0 : 1, pb = have_prev && prev[b] ? 0 : 1;
+            if (pa != pb) return pa < pb;
+            return pending(h, a) < pending(h, b);
+        });
+        for (int q : cand) { if (count >= k) break; in_tile[q] = 1; ++count; }
+        return in_tile;
+    };
+    // everything a fixed tile can execute: ready blocks whose qubits are all resident, to closure
+    auto absorb = [&](const std::vector<char>& in_tile, std::vector<size_t>& h, std::vector<int>& order) {
+        h = head; order.clear();
+        while (true) {
+            int best = -1;
+            for (int q0 = 0; q0 < n; ++q0) {
+                if (!in_tile[q0] || h[q0] >= chain[q0].size()) continue;
+                int i = chain[q0][h[q0]];
+                if (best >= 0 && i >= best) continue;
+                const Block& b = p.blocks[i];
+                bool ok = true;
+                for (int s = 0; s < b.nq; ++s) {
+                    int q = b.q[s];
+                    if (!in_tile[q] || h[q] >= chain[q].size() || chain[q][h[q]] != i) ok = false;
+                }
+                if (ok) best = i;
+            }
+            if (best < 0) break;
+            const Block& b = p.blocks[best];
+            for (int s = 0; s < b.nq; ++s) ++h[b.q[s]];
+            order.push_back(best);
+        }
+    };
+    while (remaining > 0) {
+        // candidate tiles: the earliest-first greedy, the same forced to start at every qubit's pending block, every
+        // window of k adjacent qubits; the one that executes the most work wins (it must share two qubits with the
+        // previous tile)
+        std::vector<std::vector<char>> cands;
+        cands.push_back(grow(std::vector<char>(n, 0), -1));
+        for (int q = 0; q < n; ++q) {
+            if (head[q] >= chain[q].size()) continue;
+            const int i = chain[q][head[q]];
+            const Block& b = p.blocks[i];
+            bool ready = true;
+            for (int s = 0; s < b.nq; ++s) if (chain[b.q[s]][head[b.q[s]]] != i) ready = false;
+            if (ready) cands.push_back(grow(std::vector<char>(n, 0), i));
+        }
+        for (int a = 0; a + k <= n; ++a) {
+            std::vector<char> t(n, 0);
+            for (int q = a; q < a + k; ++q) t[q] = 1;
+            cands.push_back(t);
+        }
+        if (have_prev) {   // tiles seeded with two qubits of the previous tile always qualify
+            std::vector<int> pq;
+            for (int q = 0; q < n; ++q) if (prev[q]) pq.push_back(q);
+            std::stable_sort(pq.begin(), pq.end(), [&](int a, int b) { return pending(head, a) < pending(head, b); });
+            std::vector<char> t(n, 0);
+            t[pq[0]] = t[pq[1]] = 1;
+            cands.push_back(grow(t, -1));
+        }
+        size_t best_work = 0;
+        int best_shared = -1;
+        std::vector<char> best_tile;
+        std::vector<size_t> best_h;
+        std::vector<int> best_order;
+        for (const auto& t : cands) {
+            int shared = 0;
+            for (int q = 0; q < n; ++q) shared += t[q] && prev[q];
+            if (have_prev && shared < 2) continue;
+            std::vector<size_t> h;
+            std::vector<int> order;
+            absorb(t, h, order);
+            if (order.size() > best_work || (order.size() == best_work && shared > best_shared)) {
+                best_work = order.size(); best_shared = shared; best_tile = t; best_h = h; best_order = order;
+            }
+        }
+        if (best_work == 0) throw std::runtime_error("streaming scheduler made no progress");
+        head = best_h; remaining -= best_work;
+        tiles.push_back(best_tile); orders.push_back(best_order);
+        prev = best_tile; have_prev = true;
+    }
+    if (n >= 2 && !(tiles.back()[n - 1] && tiles.back()[n - 2])) {
+        // no room in the last tile: one transpose-only pass restores the standard order
+        std::vector<char> t(n, 0);
+        int count = 0;
+        t[n - 1] = t[n - 2] = 1; count = 2;
+        for (int q = 0; q < n && count < k; ++q) if (!t[q] && tiles.back()[q]) { t[q] = 1; ++count; }
+        for (int q = n - 1; q >= 0 && count < k; --q) if (!t[q]) { t[q] = 1; ++count; }
+        tiles.push_back(t); orders.push_back({});
+    }
+    // layouts
+    const size_t L = tiles.size();
+    std::vector<std::vector<int>> pos(L + 1, std::vector<int>(n));
+    for (int q = 0; q < n; ++q) pos[L][q] = n - 1 - q;
+    pos[0] = pos[L];
+    for (size_t pi = 1; pi < L; ++pi) {
+        std::vector<int> seq;   // qubits by ascending position
+        int got = 0;
+        for (int q = 0; q < n && got < 2; ++q) if (tiles[pi - 1][q] && tiles[pi][q]) { seq.push_back(q); ++got; }
+        if (got < 2) throw std::runtime_error("remap scheduler: consecutive tiles share fewer than two qubits");
+        std::vector<char> used(n, 0);
+        for (int q : seq) used[q] = 1;
+        for (int q = n - 1; q >= 0; --q) if (!used[q] && tiles[pi][q]) { seq.push_back(q); used[q] = 1; }   // this pass's tile is contiguous
+        for (int q = n - 1; q >= 0; --q) if (!used[q]) { seq.push_back(q); used[q] = 1; }
+        for (int i = 0; i < n; ++i) pos[pi][seq[i]] = i;
+    }
+    CoefCache cc;
+    double flops = 0.0, sweeps = 0.0;
+    for (size_t pi = 0; pi < L; ++pi) {
+        Pass pass;
+        pass.pos_in = pos[pi]; pass.pos_out = pos[pi + 1];
+        std::vector<int> tq;
+        for (int q = 0; q < n; ++q) if (tiles[pi][q]) tq.push_back(q);
+        // tile-local order = order of the layout this pass stores (the store side walks the tile linearly)
+        std::sort(tq.begin(), tq.end(), [&](int a, int b) { return pass.pos_out[a] > pass.pos_out[b]; });
+        pass.tile_q = tq;
+        std::vector<int> local_pos(n, -1);
+        for (size_t i = 0; i < tq.size(); ++i) local_pos[tq[i]] = 2 * ((int)tq.size() - 1 - (int)i);
+        pass.first_phase = (int)p.phases.size();
+        if (!orders[pi].empty()) {
+            SweepBuilder sb(p, cc, local_pos, pass.tile_q);
+            sb.run(orders[pi]);
+            flops += sb.flops;
+            sweeps += sb.sweeps_elems;
+        }
+        pass.n_phases = (int)p.phases.size() - pass.first_phase;
+        p.passes.push_back(std::move(pass));
+    }
+    p.info.flops_per_circuit = flops * std::pow(4.0, n);
+    p.info.smem_bytes_per_circuit = sweeps * 16.0 * std::pow(4.0, n);
+}
+
 // ---- segment tables (path 1) --------------------------------------------------------------------------
 
 static const int SEG_N = 4, SEG_E = 256;
@@ -1251,6 +1457,7 @@ void lower_plan(Plan& p) {
     if (p.n < 1 || p.n > DMX_MAX_QUBITS) throw std::runtime_error("n_qubits out of range");
     p.blocks.clear(); p.rots.clear(); p.mus.clear(); p.sweeps.clear(); p.factors.clear(); p.chains.clear(); p.phases.clear();
     p.coefs.clear(); p.passes.clear();
+    p.remapped = false;
     p.cpb = plan_cpb(p.n);
     p.segs.clear(); p.slots.clear(); p.term_idx.clear(); p.term_coef.clear();
     std::memset(&p.info, 0, sizeof(p.info));
@@ -1273,7 +1480,20 @@ void lower_plan(Plan& p) {
         }
         for (uint32_t idx : order) { p.term_idx.push_back(idx); p.term_coef.push_back(acc[idx]); }
     }
-    if (p.n <= 7) schedule_single_pass(p); else schedule_streaming(p);
+    if (p.n <= 7) schedule_single_pass(p);
+    else {
+        bool remapped = false;
+        if (p.opt_remap && p.opt_tile_qubits >= 6) {
+            schedule_streaming_remap(p);
+            remapped = true;
+            for (const Pass& ps : p.passes) remapped = remapped && (ps.n_phases == 0 || pass_stream_eligible(p, ps));
+            if (!remapped) {   // the generic tile kernel only knows the standard layout: re-plan with pinned low qubits
+                p.mus.clear(); p.sweeps.clear(); p.factors.clear(); p.chains.clear(); p.phases.clear(); p.coefs.clear(); p.passes.clear();
+            }
+        }
+        if (!remapped) schedule_streaming(p);
+        p.remapped = remapped;
+    }
     const double tile_flops = p.info.flops_per_circuit, tile_smem = p.info.smem_bytes_per_circuit;
     p.path = p.n <= 7 ? 0 : 2;
     p.seg_eligible = false;
@@ -1295,6 +1515,7 @@ void lower_plan(Plan& p) {
     in.path = p.path;
     in.n_terms = (int)p.term_idx.size();
     in.state_bytes = (int64_t)(8.0 * N);
+    in.workspace_bytes_per_state = p.path == 2 ? in.state_bytes * (p.remapped ? 2 : 1) : 0;
     const double io = 8.0 * p.n_params + (double)p.n_slots + 8.0;
     if (p.path == 1) {
         int smem_segs = 0;
@@ -1357,6 +1578,7 @@ std::string dump_plan(const Plan& p) {
         const Pass& ps = p.passes[i];
         os << "pass " << i << " first_phase=" << ps.first_phase << " nphases=" << ps.n_phases;
         dump_ints(os, "tile", ps.tile_q);
+        if (!ps.pos_in.empty()) { dump_ints(os, "pos_in", ps.pos_in); dump_ints(os, "pos_out", ps.pos_out); }
         os << "\n";
     }
     for (size_t i = 0; i < p.phases.size(); ++i)

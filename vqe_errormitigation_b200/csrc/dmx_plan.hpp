@@ -105,8 +105,13 @@ struct RotInfo {      // per global rotation id
 };
 
 struct Pass {         // one pass over the state with `tile_q` resident
-    std::vector<int> tile_q;          // resident qubits, ascending qubit index
+    std::vector<int> tile_q;          // resident qubits by DESCENDING tile-local position (tile_q[i] sits at bits 2*(k-1-i))
     int first_phase = 0, n_phases = 0;
+    // Global layout of the state in HBM before (pos_in) and after (pos_out) this pass: pos[q] = position of qubit q
+    // (its code occupies index bits 2*pos, 2*pos+1).  Empty = standard order pos[q] = n-1-q.  The remapping scheduler
+    // lets every pass store the state in the order the NEXT pass wants to load it: only two qubits shared by
+    // consecutive passes have to sit at the low positions (128-byte runs), instead of pinning qubits n-1, n-2 forever.
+    std::vector<int> pos_in, pos_out;
 };
 
 // Segment kernel tables (n padded to 4 qubits: 256 elements).
@@ -142,7 +147,7 @@ struct Plan {
     std::vector<double> pool;
     std::vector<uint32_t> hx, hz;
     std::vector<double> hc;
-    int opt_fuse = 1, opt_segments = 1, opt_tile_qubits = 7;
+    int opt_fuse = 1, opt_segments = 1, opt_tile_qubits = 7, opt_remap = 1;
     bool finalized = false;
 
     // lowered program
@@ -157,6 +162,7 @@ struct Plan {
     std::vector<double> coefs;
     std::vector<Pass> passes;
     int path = 0;           // 0 tile (single pass, state in smem), 1 segment, 2 streaming
+    bool remapped = false;  // streaming passes re-order the qubits in HBM (Pass::pos_in/pos_out): two state buffers
     int tile_k = 0;
     // energy terms in the engine's index space
     std::vector<uint32_t> term_idx;
@@ -186,6 +192,9 @@ struct Plan {
 
 // host-only lowering: ops -> blocks -> dev_ops/passes (+ segment tables).  Throws std::runtime_error.
 void lower_plan(Plan& p);
+// limits of dmx_stream_kernel's parameter tables (dmx_stream.cuh) and the check both layers use
+constexpr int STREAM_MAX_SWEEPS = 48, STREAM_MAX_MUS = 96;
+bool pass_stream_eligible(const Plan& p, const Pass& ps);
 std::string dump_plan(const Plan& p);
 
 // helpers shared with exec

@@ -7,7 +7,8 @@
 // Compared with the generic dmx_tile_kernel this kernel
 //   * reads per-circuit chain matrices (products of rotations / fixed one-qubit blocks) that dmx_chain_kernel
 //     computed ONCE per (circuit, pass) instead of once per tile,
-//   * keeps every table of the pass (sweeps, micro-ops, coefficients) in shared memory,
+//   * takes the sweep / micro-op tables of the pass as kernel parameters (constant bank) and keeps its coefficients
+//     in shared memory,
 //   * addresses the tile with one 3-input XOR per access (per-sweep masks precombined on the host).
 // k = 6 tiles are 32 KiB: four CTAs share an SM, so the HBM phases of one tile overlap the sweeps of the others.
 #pragma once
@@ -35,20 +36,26 @@ struct MuX {                  // 16 bytes
 };
 
 struct StreamArgs {
-    const SweepX* sweeps;
-    const MuX* mus;
-    const double* coefs;          // fixed coefficient table of the plan
+    // the sweep and micro-op tables of the pass travel in the kernel parameters (constant bank, uniform loads)
+    SweepX sweeps[STREAM_MAX_SWEEPS];
+    MuX mus[STREAM_MAX_MUS];
+    const double* coefs;          // pass-local fixed coefficient table
     const double* chainmats;      // [chunk][total_chains][16]
     int n_sweeps, n_mus, n_coefs;
     int total_chains, first_chain, n_chains;
     int n, k;
     int load, pad0;
-    double* state;                // [chunk][4^n]
-    // tile <-> global index maps (load side / store side: a pass may write the state in a different qubit order)
-    int n_truns_l, n_oruns_l, n_truns_s, n_oruns_s;
-    int truns_l[8][3], oruns_l[8][3], truns_s[8][3], oruns_s[8][3];   // (lshift, gshift, width)
-    uint32_t giter_l[16], giter_s[16];   // global index contribution of staging iteration j (element pair j * 2 * THREADS)
-    uint32_t siter[16];                  // swizzled tile index of the same
+    const double* src;            // [chunk][4^n] state before the pass (layout pos_in)
+    double* dst;                  // state after the pass (layout pos_out); == src unless the pass re-orders the qubits
+    // Staging maps, one set per side (a pass may store the state in a different qubit order than it loaded it).
+    // A side enumerates the tile's elements in the order of their GLOBAL addresses: u = 2 * tid + j * 2 * THREADS;
+    // gruns deposit the bits of u (and oruns those of the tile id) into the global index, uruns into the tile index.
+    int n_gruns_l, n_oruns_l, n_gruns_s, n_oruns_s;
+    int gruns_l[8][3], uruns_l[8][3], oruns_l[8][3];   // (source shift, destination shift, width)
+    int gruns_s[8][3], uruns_s[8][3], oruns_s[8][3];
+    uint32_t giter_l[16], giter_s[16];   // global index contribution of staging iteration j
+    uint32_t siter_l[16], siter_s[16];   // swizzled tile index of the same
+    uint32_t pbit_l, pbit_s;             // swizzled tile offset between the two elements of a 16-byte global chunk
     uint32_t init_mask;                  // first pass: coefficient is 1 when (global index & init_mask) == 0
 };
 
@@ -158,7 +165,9 @@ __device__ __forceinline__ void apply4(double (&v)[16], const double* __restrict
 // Both groups get the same matrix: the coefficients are loaded from shared memory once.
 template <int SA, int SB>
 __device__ __forceinline__ void apply3x2(double (&v0)[16], double (&v1)[16], const double* __restrict__ M) {
-    const double m5 = M[5], m6 = M[6], m7 = M[7], m9 = M[9], m10 = M[10], m11 = M[11], m13 = M[13], m14 = M[14], m15 = M[15];
+    const double2* __restrict__ M2 = reinterpret_cast<const double2*>(M);    // 4x4 tables are 16-byte aligned
+    const double2 r1a = M2[2], r1b = M2[3], r2a = M2[4], r2b = M2[5], r3a = M2[6], r3b = M2[7];
+    const double m5 = r1a.y, m6 = r1b.x, m7 = r1b.y, m9 = r2a.y, m10 = r2b.x, m11 = r2b.y, m13 = r3a.y, m14 = r3b.x, m15 = r3b.y;
 #pragma unroll
     for (int s = 0; s < 4; ++s) {
         {
@@ -191,63 +200,59 @@ __device__ __forceinline__ void dense16x(double (&v)[16], const double* __restri
 
 extern __shared__ __align__(16) double dmx_stream_smem[];
 
-template <int THREADS>
+// GENERAL = false: unital one-qubit maps (3x3) and diagonal blocks only — every circuit built from rotations, Clifford
+// gates and Pauli-type noise; GENERAL = true adds non-unital 4x4 maps (amplitude damping) and dense two-qubit blocks.
+template <int THREADS, bool GENERAL>
 __global__ void __launch_bounds__(THREADS, THREADS == 512 ? 1 : 4) dmx_stream_kernel(const __grid_constant__ StreamArgs a) {
     constexpr int NITER = 16;                               // 4^k / (2 * THREADS) staging iterations (k = 6: 128 thr, k = 7: 512 thr)
     const unsigned E = 32u * THREADS;                       // tile elements
     double* tile = dmx_stream_smem;
     double* cf = tile + E;                                  // [n_chains*16 chain matrices | n_coefs fixed coefficients]
-    const int n_cf = a.n_chains * 16 + a.n_coefs;
-    SweepX* sws = reinterpret_cast<SweepX*>(cf + ((n_cf + 1) & ~1));
-    MuX* mus = reinterpret_cast<MuX*>(sws + a.n_sweeps);
     char* const tb = reinterpret_cast<char*>(tile);
     const int tid = threadIdx.x;
 
     const unsigned tiles_per_circuit = 1u << (2 * (a.n - a.k));
     const long long circuit = blockIdx.x / tiles_per_circuit;
     const unsigned tile_id = blockIdx.x % tiles_per_circuit;
-    double* const st = a.state + (circuit << (2 * a.n));
+    const double* const st_in = a.src + (circuit << (2 * a.n));
+    double* const st = a.dst + (circuit << (2 * a.n));
 
     // ---- pass tables -> shared memory ----
     {
         const double* cm = a.chainmats + ((size_t)circuit * a.total_chains + a.first_chain) * 16;
         for (int i = tid; i < a.n_chains * 16; i += THREADS) cf[i] = cm[i];
         for (int i = tid; i < a.n_coefs; i += THREADS) cf[a.n_chains * 16 + i] = a.coefs[i];
-        const uint32_t* src = reinterpret_cast<const uint32_t*>(a.sweeps);
-        uint32_t* dst = reinterpret_cast<uint32_t*>(sws);
-        const int nw = a.n_sweeps * (int)(sizeof(SweepX) / 4) + a.n_mus * (int)(sizeof(MuX) / 4);   // mus follow the sweeps in both places
-        for (int i = tid; i < nw; i += THREADS) dst[i] = src[i];
     }
 
     // ---- tile load / init ----
-    const unsigned s_thr = swz_hd(2u * tid);
     if (a.load) {
-        const unsigned gbase = map_runs(2u * tid, a.truns_l, a.n_truns_l) | map_runs(tile_id, a.oruns_l, a.n_oruns_l);
+        const unsigned gbase = map_runs(2u * tid, a.gruns_l, a.n_gruns_l) | map_runs(tile_id, a.oruns_l, a.n_oruns_l);
+        const unsigned s_thr = swz_hd(map_runs(2u * tid, a.uruns_l, a.n_gruns_l));
         double2 x[NITER];
 #pragma unroll
-        for (int j = 0; j < NITER; ++j) x[j] = __ldcs(reinterpret_cast<const double2*>(st + (gbase | a.giter_l[j])));
+        for (int j = 0; j < NITER; ++j) x[j] = *reinterpret_cast<const double2*>(st_in + (gbase | a.giter_l[j]));
 #pragma unroll
         for (int j = 0; j < NITER; ++j) {
-            const unsigned sp = s_thr ^ a.siter[j];
-            const bool flip = sp & 1u;       // the pair (i, i+1) stays adjacent under the swizzle, possibly swapped
-            *reinterpret_cast<double2*>(tile + (sp & ~1u)) = flip ? make_double2(x[j].y, x[j].x) : x[j];
+            const unsigned sp = s_thr ^ a.siter_l[j];
+            tile[sp] = x[j].x;
+            tile[sp ^ a.pbit_l] = x[j].y;
         }
     } else {
-        const unsigned gbase = map_runs(2u * tid, a.truns_s, a.n_truns_s) | map_runs(tile_id, a.oruns_s, a.n_oruns_s);
+        const unsigned gbase = map_runs(2u * tid, a.gruns_s, a.n_gruns_s) | map_runs(tile_id, a.oruns_s, a.n_oruns_s);
+        const unsigned s_thr = swz_hd(map_runs(2u * tid, a.uruns_s, a.n_gruns_s));
 #pragma unroll
         for (int j = 0; j < NITER; ++j) {
-            const unsigned g = gbase | a.giter_s[j];     // the initial state is symmetric under qubit relabelling: any order works
-            const unsigned sp = s_thr ^ a.siter[j];
-            const double e0 = (g & a.init_mask) ? 0.0 : 1.0, e1 = ((g | 1u) & a.init_mask) ? 0.0 : 1.0;
-            const bool flip = sp & 1u;
-            *reinterpret_cast<double2*>(tile + (sp & ~1u)) = flip ? make_double2(e1, e0) : make_double2(e0, e1);
+            const unsigned g = gbase | a.giter_s[j];     // |0..0><0..0| is symmetric under qubit relabelling: any layout works
+            const unsigned sp = s_thr ^ a.siter_s[j];
+            tile[sp] = (g & a.init_mask) ? 0.0 : 1.0;
+            tile[sp ^ a.pbit_s] = ((g | 1u) & a.init_mask) ? 0.0 : 1.0;
         }
     }
     __syncthreads();
 
     // ---- sweeps ----
     for (int si = 0; si < a.n_sweeps; ++si) {
-        const SweepX& sw = sws[si];
+        const SweepX& sw = a.sweeps[si];
         const unsigned sb0 = swz_hd(insert2_hd(insert2_hd((unsigned)tid, sw.pa), sw.pb)) << 3;
         const unsigned sb1 = sb0 ^ sw.gtop;
         double v0[16], v1[16];
@@ -262,21 +267,21 @@ __global__ void __launch_bounds__(THREADS, THREADS == 512 ? 1 : 4) dmx_stream_ke
                 v1[e] = *reinterpret_cast<const double*>(tb + (sb1 ^ off));
             }
             if (sw.lscale >= 0) {
-                const double* __restrict__ lc = cf + sw.lscale;
+                const double2* __restrict__ lc = reinterpret_cast<const double2*>(cf + sw.lscale);
 #pragma unroll
-                for (int e = 0; e < 16; ++e) { const double s = lc[e]; v0[e] *= s; v1[e] *= s; }
+                for (int e = 0; e < 8; ++e) { const double2 s = lc[e]; v0[2 * e] *= s.x; v1[2 * e] *= s.x; v0[2 * e + 1] *= s.y; v1[2 * e + 1] *= s.y; }
             }
         }
         for (int mi = 0; mi < sw.n_mu; ++mi) {
-            const MuX m = mus[sw.first_mu + mi];
+            const MuX m = a.mus[sw.first_mu + mi];
             const double* __restrict__ M = cf + m.off;
             switch (m.kind) {
                 case MU_CHAIN_A: case MU_FIX_A:
-                    if (m.unital) apply3x2<4, 1>(v0, v1, M);
+                    if (!GENERAL || m.unital) apply3x2<4, 1>(v0, v1, M);
                     else { apply4<4, 1>(v0, M); apply4<4, 1>(v1, M); }
                     break;
                 case MU_CHAIN_B: case MU_FIX_B:
-                    if (m.unital) apply3x2<1, 4>(v0, v1, M);
+                    if (!GENERAL || m.unital) apply3x2<1, 4>(v0, v1, M);
                     else { apply4<1, 4>(v0, M); apply4<1, 4>(v1, M); }
                     break;
                 case MU_DIAG_A: {
@@ -297,13 +302,14 @@ __global__ void __launch_bounds__(THREADS, THREADS == 512 ? 1 : 4) dmx_stream_ke
                     }
                     break;
                 }
-                case MU_DIAG2:
+                case MU_DIAG2: {
+                    const double2* __restrict__ M2 = reinterpret_cast<const double2*>(M);
 #pragma unroll
-                    for (int e = 0; e < 16; ++e) { const double s = M[e]; v0[e] *= s; v1[e] *= s; }
+                    for (int e = 0; e < 8; ++e) { const double2 s = M2[e]; v0[2 * e] *= s.x; v1[2 * e] *= s.x; v0[2 * e + 1] *= s.y; v1[2 * e + 1] *= s.y; }
                     break;
+                }
                 default:   // MU_MAT2
-                    dense16x(v0, M);
-                    dense16x(v1, M);
+                    if (GENERAL) { dense16x(v0, M); dense16x(v1, M); }
                     break;
             }
         }
@@ -312,9 +318,9 @@ __global__ void __launch_bounds__(THREADS, THREADS == 512 ? 1 : 4) dmx_stream_ke
 #pragma unroll
             for (int j = 0; j < 4; ++j) { mA[j] = sw.sA[j]; mB[j] = sw.sB[j]; }
             if (sw.sscale >= 0) {
-                const double* __restrict__ sc = cf + sw.sscale;
+                const double2* __restrict__ sc = reinterpret_cast<const double2*>(cf + sw.sscale);
 #pragma unroll
-                for (int e = 0; e < 16; ++e) { const double s = sc[e]; v0[e] *= s; v1[e] *= s; }
+                for (int e = 0; e < 8; ++e) { const double2 s = sc[e]; v0[2 * e] *= s.x; v1[2 * e] *= s.x; v0[2 * e + 1] *= s.y; v1[2 * e + 1] *= s.y; }
             }
 #pragma unroll
             for (int e = 0; e < 16; ++e) {
@@ -328,13 +334,12 @@ __global__ void __launch_bounds__(THREADS, THREADS == 512 ? 1 : 4) dmx_stream_ke
 
     // ---- tile store ----
     {
-        const unsigned gbase = map_runs(2u * tid, a.truns_s, a.n_truns_s) | map_runs(tile_id, a.oruns_s, a.n_oruns_s);
+        const unsigned gbase = map_runs(2u * tid, a.gruns_s, a.n_gruns_s) | map_runs(tile_id, a.oruns_s, a.n_oruns_s);
+        const unsigned s_thr = swz_hd(map_runs(2u * tid, a.uruns_s, a.n_gruns_s));
 #pragma unroll
         for (int j = 0; j < NITER; ++j) {
-            const unsigned sp = s_thr ^ a.siter[j];
-            const double2 x = *reinterpret_cast<const double2*>(tile + (sp & ~1u));
-            const bool flip = sp & 1u;
-            *reinterpret_cast<double2*>(st + (gbase | a.giter_s[j])) = flip ? make_double2(x.y, x.x) : x;
+            const unsigned sp = s_thr ^ a.siter_s[j];
+            *reinterpret_cast<double2*>(st + (gbase | a.giter_s[j])) = make_double2(tile[sp], tile[sp ^ a.pbit_s]);
         }
     }
 }

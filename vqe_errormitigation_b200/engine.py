@@ -254,7 +254,7 @@ class CircuitProgram:
         nbytes = 0
         if self.info["path"] == 2:
             states = workspace_states if workspace_states else min(B, 64)
-            nbytes = int(self.info["state_bytes"]) * states
+            nbytes = int(self.info["workspace_bytes_per_state"]) * states
         ws = self._ws(torch, dev, nbytes)
         stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
         check(self._lib.dmx_energy_batch(self._handle, B, self._ptr(p_t), self._ptr(v_t), self._ptr(out), self._ptr(ws), nbytes, stream))
