@@ -110,7 +110,7 @@ def _hea_builder(n: int, depth: int, p: float = 1e-3):
 
 def workload_hea10():
     from vqe_errormitigation_b200 import engine
-    n, depth, B = 10, 20, 256
+    n, depth, B = 10, 20, 4096
     b = _hea_builder(n, depth)
     rng = np.random.default_rng(20260104)
     n_terms = 100
@@ -125,17 +125,130 @@ def workload_hea10():
             if code in (2, 3):
                 zs[t] |= bit
     terms = (xs, zs, rng.normal(size=n_terms))
-    prog = engine.CircuitProgram(b, hamiltonian=terms, options=dict(PLAN_OPTIONS))
+    prog = engine.CircuitProgram(b, hamiltonian=terms, options={"tile_qubits": 6, **PLAN_OPTIONS})
 
     def make_inputs(rank: int, seed_offset: int = 0):
         r = np.random.default_rng(20260103 + rank)
         return r.uniform(-np.pi, np.pi, size=(B, prog.n_params)), None
 
-    return dict(name=f"synthetic 10-qubit hardware-efficient ansatz depth 20, noise on every gate, batch {B} per step (BASELINE configs[3], sub-batch of 4096)",
-                prog=prog, batch=B, make_inputs=make_inputs, terms=terms)
+    # SURVEY.md §8d canonical traffic: one read + one write of complex128 rho per layer = depth * 32 B * 4^n
+    return dict(name=f"synthetic 10-qubit hardware-efficient ansatz depth 20, noise on every gate, batch {B} per step (BASELINE configs[3])",
+                prog=prog, batch=B, make_inputs=make_inputs, terms=terms, canonical_bytes=depth * 32.0 * 4.0 ** n,
+                cpu_sample=16)
 
 
-WORKLOADS = {"h2_sweep": workload_h2_sweep, "h2_qem": workload_h2_qem, "hea10": workload_hea10}
+def _lih_like(n: int = 12, n_occ: int = 4, p: float = 1e-3, n_terms: int = 631, max_excitations=None):
+    """SURVEY.md §8d config 5 (the reference has no LiH data): 12 spin orbitals, HF state rx(pi) on q0..q3, every
+    spin-conserving single (16) and double (76) excitation as Pauli-exponential blocks emitted by the rule of
+    i_wave_function.py:158-189 (basis change, CNOT ladder, rz(2*sign*theta), un-ladder, inverse basis change), noise
+    after every gate; one parameter per excitation.  Hamiltonian: 631 seeded number-conserving JW-shaped terms."""
+    from vqe_errormitigation_b200 import cirq_compat as cirq, engine
+    from vqe_errormitigation_b200.error_mitigation import TwoQubitDepolarizingChannel
+    rng = np.random.default_rng(20260105)
+    b = engine.ProgramBuilder(n)
+    dep1 = cirq.channel(cirq.depolarize(p))
+    dep2 = cirq.channel(TwoQubitDepolarizingChannel(p))
+    cnot = cirq.unitary(cirq.CNOT)
+    had = cirq.unitary(cirq.H)
+    rxm, rxp = cirq.unitary(cirq.rx(-np.pi / 2)), cirq.unitary(cirq.rx(np.pi / 2))
+
+    def gate(qs, m):
+        b.add_unitary(list(qs), m)
+        b.add_kraus(list(qs), dep1 if len(qs) == 1 else dep2)
+
+    for q in range(n_occ):
+        gate((q,), cirq.unitary(cirq.rx(np.pi)))
+    occ, virt = list(range(n_occ)), list(range(n_occ, n))
+    singles = [(i, a) for i in occ for a in virt if (i - a) % 2 == 0]
+    doubles = [(i, j, a, c) for x, i in enumerate(occ) for j in occ[x + 1:] for y, a in enumerate(virt) for c in virt[y + 1:]
+               if (i % 2) + (j % 2) == (a % 2) + (c % 2)]
+    excitations = [("s", e) for e in singles] + [("d", e) for e in doubles]
+    order = rng.permutation(len(excitations))
+    if max_excitations is not None:
+        order = order[:max_excitations]
+    n_blocks = 0
+
+    def exponential(string, sign, name):
+        nonlocal n_blocks
+        qs = [q for q, _ in string]
+        for q, pl in string:
+            if pl == "X":
+                gate((q,), had)
+            elif pl == "Y":
+                gate((q,), rxm)
+        for a, c in zip(qs[:-1], qs[1:]):
+            gate((a, c), cnot)
+        b.add_rotation(qs[-1], 2, name, 2.0 * sign)
+        b.add_kraus([qs[-1]], dep1)
+        for a, c in reversed(list(zip(qs[:-1], qs[1:]))):
+            gate((a, c), cnot)
+        for q, pl in string:
+            if pl == "X":
+                gate((q,), had)
+            elif pl == "Y":
+                gate((q,), rxp)
+        n_blocks += 1
+
+    for k in order:
+        kind, e = excitations[k]
+        name = f"t{k}"
+        if kind == "s":
+            i, a = e
+            zs = [(q, "Z") for q in range(i + 1, a)]
+            exponential([(i, "X")] + zs + [(a, "Y")], +1.0, name)
+            exponential([(i, "Y")] + zs + [(a, "X")], -1.0, name)
+        else:
+            i, j, a, c = e
+            z1 = [(q, "Z") for q in range(i + 1, j)]
+            z2 = [(q, "Z") for q in range(a + 1, c)]
+            for pat, sg in (("XXXY", 1), ("XXYX", 1), ("XYXX", -1), ("YXXX", -1), ("YYYX", -1), ("YYXY", -1), ("YXYY", 1), ("XYYY", 1)):
+                exponential([(i, pat[0])] + z1 + [(j, pat[1]), (a, pat[2])] + z2 + [(c, pat[3])], float(sg), name)
+    # Hamiltonian terms (x mask / z mask, qubit 0 = most significant bit)
+    bit = lambda q: 1 << (n - 1 - q)
+    terms = {(0, 0)}
+    for q in range(n):
+        terms.add((0, bit(q)))
+    for q in range(n):
+        for r in range(q + 1, n):
+            terms.add((0, bit(q) | bit(r)))
+    hop = [(q, r) for q in range(n) for r in range(q + 2, n, 2)]
+    for q, r in hop:
+        zz = sum(bit(t) for t in range(q + 1, r))
+        terms.add((bit(q) | bit(r), zz))                       # X Z..Z X
+        terms.add((bit(q) | bit(r), zz | bit(q) | bit(r)))     # Y Z..Z Y
+    quads = [(q0, q1, q2, q3) for q0 in range(n) for q1 in range(q0 + 1, n) for q2 in range(q1 + 1, n) for q3 in range(q2 + 1, n)]
+    for qi in rng.permutation(len(quads)):
+        if len(terms) >= n_terms:
+            break
+        q0, q1, q2, q3 = quads[qi]
+        zz = sum(bit(t) for t in range(q0 + 1, q1)) | sum(bit(t) for t in range(q2 + 1, q3))
+        xm = bit(q0) | bit(q1) | bit(q2) | bit(q3)
+        for ys in ((), (q0, q1), (q0, q2), (q0, q3), (q1, q2), (q1, q3), (q2, q3), (q0, q1, q2, q3)):
+            if len(terms) < n_terms:
+                terms.add((xm, zz | sum(bit(t) for t in ys)))
+    tl = sorted(terms)
+    ham = (np.array([t[0] for t in tl], np.uint32), np.array([t[1] for t in tl], np.uint32), rng.normal(scale=0.1, size=len(tl)))
+    return b, ham, n_blocks
+
+
+def workload_lih12():
+    from vqe_errormitigation_b200 import engine
+    n, B = 12, 8
+    b, terms, n_blocks = _lih_like(n)
+    prog = engine.CircuitProgram(b, hamiltonian=terms, options={"tile_qubits": 6, **PLAN_OPTIONS})
+
+    def make_inputs(rank: int, seed_offset: int = 0):
+        r = np.random.default_rng(20260106 + rank)
+        return r.normal(scale=0.1, size=(B, prog.n_params)), None
+
+    # SURVEY.md §8d canonical traffic: one pass (read + write of complex128 rho) per Pauli-exponential block
+    return dict(name=f"synthetic LiH-like 12-qubit UCCSD ansatz ({n_blocks} Pauli-exponential blocks, noise on every gate, "
+                     f"{len(terms[2])} Pauli terms), {B} optimiser chains per GPU per step (BASELINE configs[4]; no LiH data in the reference)",
+                prog=prog, batch=B, make_inputs=make_inputs, terms=terms, canonical_bytes=n_blocks * 32.0 * 4.0 ** n,
+                cpu_sample=0, cpu_ops_fraction=0.002)
+
+
+WORKLOADS = {"h2_sweep": workload_h2_sweep, "h2_qem": workload_h2_qem, "hea10": workload_hea10, "lih12": workload_lih12}
 
 
 # ---------------------------------------------------------------------------------------------------------
@@ -204,17 +317,34 @@ def measured_peaks():
 
 
 def cpu_port_rate(wl, sample: int, threads: int = 0, rank: int = 0):
-    """Time the C restatement of the reference algorithm on `sample` circuits of the workload."""
+    """Time the C restatement of the reference algorithm on `sample` circuits of the workload.  Workloads whose single
+    circuit takes the CPU many minutes (12 qubits: rho is 256 MiB, 25k ops) set `cpu_ops_fraction`: only that leading
+    fraction of the op list is evolved (one identity term as the observable) and the rate is scaled to the whole list."""
     from oracle import c_oracle
     prog = wl["prog"]
     params, variants = wl["make_inputs"](rank)
+    ops, terms, scale = prog.ops, wl["terms"], 1.0
+    frac = wl.get("cpu_ops_fraction")
+    if frac:
+        m = max(8, int(len(ops) * frac))
+        ops, scale = ops[:m], m / len(ops)
+        terms = (np.zeros(1, np.uint32), np.zeros(1, np.uint32), np.ones(1))
+        reps = -(-sample // len(params))
+        params = np.tile(params, (reps, 1))
     p = params[:sample] if params is not None else None
     v = variants[:sample] if variants is not None else None
     t0 = time.perf_counter()
-    c_oracle.energy_batch(prog.n_qubits, prog.ops, prog.pool, wl["terms"], params=p, variants=v, batch=sample,
+    c_oracle.energy_batch(prog.n_qubits, ops, prog.pool, terms, params=p, variants=v, batch=sample,
                           n_params=prog.n_params, n_slots=prog.n_slots, threads=threads)
     dt = time.perf_counter() - t0
-    return sample / dt, dt
+    return sample * scale / dt, dt
+
+
+def cpu_sample_note(wl, sample):
+    if wl.get("cpu_ops_fraction"):
+        return (f"{sample} circuits x the first {wl['cpu_ops_fraction']:.2%} of the op list, rate scaled to the whole list "
+                f"(a full 12-qubit circuit takes the CPU port tens of minutes)")
+    return f"{sample} circuits of the workload"
 
 
 def run_reference(args, wl):
@@ -222,9 +352,13 @@ def run_reference(args, wl):
     from oracle import c_oracle
     cores = c_oracle.max_threads()
     # calibrate so the whole run stays within ~2 minutes
-    rate0, _ = cpu_port_rate(wl, min(64, wl["batch"]), threads=cores)
+    probe = min(64, wl["batch"]) if not wl.get("cpu_ops_fraction") else cores
+    rate0, dt0 = cpu_port_rate(wl, probe, threads=cores)
     budget_s = 90.0
-    sample = int(max(16, min(wl["batch"], rate0 * budget_s / max(args.steps + args.warmup, 1))))
+    if wl.get("cpu_ops_fraction"):
+        sample = cores
+    else:
+        sample = int(max(min(16, wl["batch"]), min(wl["batch"], probe / dt0 * budget_s / max(args.steps + args.warmup, 1))))
     for _ in range(args.warmup):
         cpu_port_rate(wl, sample, threads=cores)
     t_total = 0.0
@@ -237,7 +371,7 @@ def run_reference(args, wl):
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": wl["name"], "sample_per_step": sample},
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
-                             "sample": f"{sample} circuits of the workload per step, {args.steps} steps (oracle/dm_oracle.c, pthreads)"},
+                             "sample": f"{cpu_sample_note(wl, sample)} per step, {args.steps} steps (oracle/dm_oracle.c, pthreads)"},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
 
@@ -292,11 +426,15 @@ def main():
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         from oracle import c_oracle
         cores = c_oracle.max_threads()
-        r1, _ = cpu_port_rate(wl, min(32, B), threads=cores)
-        sample = int(max(32, min(B, r1 * 12.0)))
+        if wl.get("cpu_ops_fraction"):
+            sample = cores
+        else:
+            probe = min(32, B, max(cores, 1))
+            _, dt1 = cpu_port_rate(wl, probe, threads=cores)
+            sample = int(max(probe, min(B, probe / dt1 * 12.0)))
         rate, dt = cpu_port_rate(wl, sample, threads=cores)
         cpu_baseline = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
-                        "sample": f"first {sample} circuits of the workload, {dt:.1f} s, C restatement of cirq's per-op "
+                        "sample": f"{cpu_sample_note(wl, sample)}, {dt:.1f} s, C restatement of cirq's per-op "
                                   f"density-matrix algorithm (oracle/dm_oracle.c) on {cores} threads"}
 
     params_h, variants_h = wl["make_inputs"](rank)
@@ -367,17 +505,32 @@ def main():
     # ---- roofline of the dominant kernel -----------------------------------------------------------------------------
     ms_per_step = dev_ms_max / args.steps
     kernel_s = ms_per_step * 1e-3
-    path = {0: "dmx_tile_kernel", 1: "dmx_segment_kernel", 2: "dmx_tile_kernel (streaming passes)"}[info["path"]]
+    path = {0: "dmx_tile_kernel", 1: "dmx_frame_kernel", 2: "dmx_stream_kernel (streaming passes)"}[info["path"]]
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
     if os.path.exists(tpath):
         with open(tpath) as fh:
             traffic = json.load(fh).get(args.workload)
     if info["path"] == 2:
-        ach = info["hbm_bytes_per_circuit"] * B / kernel_s / 1e9
+        # algorithmic bytes = SURVEY.md §8d canonical traffic (complex128 rho, one read + write per layer / block);
+        # the engine's own traffic (real Pauli vector, fused passes) is reported beside it
+        canon = wl.get("canonical_bytes") or info["canonical_hbm_bytes_per_circuit"]
+        ach = canon * B / kernel_s / 1e9
+        sm_clock = (clocks.summary()["sm_mhz"] or 1965.0) * 1e6
+        smem_peak = 148 * 128 * sm_clock / 1e9
         roofline = {"bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
                     "traffic": traffic, "kernel": path, "peak_source": hbm_src,
-                    "algorithmic_bytes_per_circuit": info["hbm_bytes_per_circuit"]}
+                    "algorithmic_bytes_per_circuit": canon,
+                    "algorithmic_model": "SURVEY.md 8d: 32 B x 4^n per layer (HEA) / per Pauli-exponential block (UCCSD)",
+                    "executed": {"hbm_bytes_per_circuit": info["hbm_bytes_per_circuit"],
+                                 "hbm_gbs": info["hbm_bytes_per_circuit"] * B / kernel_s / 1e9,
+                                 "smem_bytes_per_circuit": info["smem_bytes_per_circuit"],
+                                 "smem_gbs": info["smem_bytes_per_circuit"] * B / kernel_s / 1e9,
+                                 "smem_frac": info["smem_bytes_per_circuit"] * B / kernel_s / 1e9 / smem_peak,
+                                 "fp64_tflops": info["flops_per_circuit"] * B / kernel_s / 1e12,
+                                 "fp64_frac": info["flops_per_circuit"] * B / kernel_s / 1e12 / fp64_peak,
+                                 "note": "the binding resource is the shared-memory exchange between sweeps "
+                                         "(148 SM x 128 B/clk at the sampled clock), then HBM"}}
     else:
         ach = info["flops_per_circuit"] * B / kernel_s / 1e12
         sm_clock = (clocks.summary()["sm_mhz"] or 1965.0) * 1e6

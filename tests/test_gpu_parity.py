@@ -205,8 +205,11 @@ def test_qp_variants_match_oracle(options):
         assert abs(got[b] - want) < TOL, (b, got[b], want)
 
 
-@pytest.mark.parametrize("n,tile", [(8, 7), (8, 5), (9, 6), (9, 4)])
-def test_streaming_matches_oracle(n, tile):
+@pytest.mark.parametrize("n,tile,remap", [(8, 7, 1), (8, 7, 0), (8, 5, 1), (9, 6, 1), (9, 6, 0), (9, 4, 1), (10, 6, 1)])
+def test_streaming_matches_oracle(n, tile, remap):
+    """Streaming passes (state in HBM) against the numpy oracle: dmx_stream_kernel with the remapping scheduler (two state
+    buffers, per-pass qubit order) and with pinned low qubits (in place), the generic tile kernel for tiles below 6 qubits;
+    dense two-qubit and non-unital (amplitude damping) micro-ops ride along."""
     torch = torch_cuda()
     rng = np.random.default_rng(300 + n + tile)
     ops = []
@@ -223,8 +226,9 @@ def test_streaming_matches_oracle(n, tile):
     ops.append(("k", (1,), O.amplitude_damp(0.01)))
     terms = random_hamiltonian(rng, n, 30)
     ham = O.pauli_terms_to_matrix(n, *terms)
-    prog = build_program(ops, n, terms, tile_qubits=tile)
+    prog = build_program(ops, n, terms, tile_qubits=tile, remap=remap)
     assert prog.info["path"] == 2 and prog.info["n_passes"] >= 2
+    assert prog.info["workspace_bytes_per_state"] == prog.info["state_bytes"] * (2 if remap and tile >= 6 else 1)
     B = 3
     params = rng.uniform(-np.pi, np.pi, size=(B, prog.n_params))
     en = prog.energies(torch.tensor(params), workspace_states=2).cpu().numpy()

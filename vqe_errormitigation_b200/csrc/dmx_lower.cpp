@@ -987,7 +987,7 @@ static void schedule_streaming_remap(Plan& p) {
                 }
                 if (ok) best = i;
             }
-            if (best < 0) break;
+            if (best < 0 || (int)order.size() >= STREAM_MAX_BLOCKS) break;   // the kernel's parameter tables are bounded
             const Block& b = p.blocks[best];
             for (int s = 0; s < b.nq; ++s) ++h[b.q[s]];
             order.push_back(best);

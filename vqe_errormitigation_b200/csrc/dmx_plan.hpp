@@ -147,7 +147,7 @@ struct Plan {
     std::vector<double> pool;
     std::vector<uint32_t> hx, hz;
     std::vector<double> hc;
-    int opt_fuse = 1, opt_segments = 1, opt_tile_qubits = 7, opt_remap = 1;
+    int opt_fuse = 1, opt_segments = 1, opt_tile_qubits = 6, opt_remap = 1;
     bool finalized = false;
 
     // lowered program
@@ -193,7 +193,7 @@ struct Plan {
 // host-only lowering: ops -> blocks -> dev_ops/passes (+ segment tables).  Throws std::runtime_error.
 void lower_plan(Plan& p);
 // limits of dmx_stream_kernel's parameter tables (dmx_stream.cuh) and the check both layers use
-constexpr int STREAM_MAX_SWEEPS = 48, STREAM_MAX_MUS = 96;
+constexpr int STREAM_MAX_SWEEPS = 128, STREAM_MAX_MUS = 128, STREAM_MAX_BLOCKS = 120;   // sweeps, micro-ops <= blocks of a pass
 bool pass_stream_eligible(const Plan& p, const Pass& ps);
 std::string dump_plan(const Plan& p);
 
