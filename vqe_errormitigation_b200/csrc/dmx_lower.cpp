@@ -886,6 +886,30 @@ static void schedule_streaming(Plan& p) {
     p.info.smem_bytes_per_circuit = sweeps * 16.0 * std::pow(4.0, n);
 }
 
+// image of tile index bit `bit` in the 4-bit bank-pair index under the swizzle of dmx_stream.cuh / dmx_exec.cu
+static unsigned swz_col(int bit) {
+    const unsigned M[4] = {(1u << 4) | (1u << 5) | (1u << 7) | (1u << 9) | (1u << 10),
+                           (1u << 5) | (1u << 6) | (1u << 9) | (1u << 11) | (1u << 12) | (1u << 13),
+                           (1u << 5) | (1u << 6) | (1u << 8) | (1u << 9) | (1u << 11) | (1u << 12),
+                           (1u << 4) | (1u << 5) | (1u << 6) | (1u << 7) | (1u << 10) | (1u << 12) | (1u << 13)};
+    unsigned v = bit < 4 ? 1u << bit : 0u;
+    for (int i = 0; i < 4; ++i) if ((M[i] >> bit) & 1u) v ^= 1u << i;
+    return v;
+}
+
+static int gf2_rank4(unsigned v[4]) {
+    int rank = 0;
+    for (int bit = 0; bit < 4; ++bit) {
+        int piv = -1;
+        for (int i = rank; i < 4; ++i) if ((v[i] >> bit) & 1u) { piv = i; break; }
+        if (piv < 0) continue;
+        std::swap(v[rank], v[piv]);
+        for (int i = 0; i < 4; ++i) if (i != rank && ((v[i] >> bit) & 1u)) v[i] ^= v[rank];
+        ++rank;
+    }
+    return rank;
+}
+
 bool pass_stream_eligible(const Plan& p, const Pass& ps) {
     const int k = (int)ps.tile_q.size();
     if (k != 6 && k != 7) return false;
@@ -1073,8 +1097,33 @@ static void schedule_streaming_remap(Plan& p) {
         pass.pos_in = pos[pi]; pass.pos_out = pos[pi + 1];
         std::vector<int> tq;
         for (int q = 0; q < n; ++q) if (tiles[pi][q]) tq.push_back(q);
-        // tile-local order = order of the layout this pass stores (the store side walks the tile linearly)
+        // Tile-local order.  The staging loops walk the tile in the order of the GLOBAL addresses of each side, so the
+        // 16 lanes of a half-warp differ in four tile bits that depend on where the three lowest-positioned tile qubits
+        // of that side sit inside the tile.  Shared-memory accesses are conflict-free iff those four bits map to
+        // linearly independent bank-pair indices under the swizzle: search the orders for one that does so on both sides
+        // (default: the order of the stored layout).
         std::sort(tq.begin(), tq.end(), [&](int a, int b) { return pass.pos_out[a] > pass.pos_out[b]; });
+        {
+            const int kk = (int)tq.size();
+            auto side_rank = [&](const std::vector<int>& order, const std::vector<int>& ps) {
+                std::vector<int> tl(n, -1);
+                for (int i = 0; i < kk; ++i) tl[order[i]] = kk - 1 - i;
+                std::vector<int> byp = order;
+                std::sort(byp.begin(), byp.end(), [&](int a, int b) { return ps[a] < ps[b]; });
+                unsigned v[4] = {swz_col(2 * tl[byp[0]] + 1), swz_col(2 * tl[byp[1]]), swz_col(2 * tl[byp[1]] + 1), swz_col(2 * tl[byp[2]])};
+                return gf2_rank4(v);
+            };
+            std::vector<int> best = tq, cand = tq;
+            int best_score = (pi > 0 ? side_rank(tq, pass.pos_in) : 4) + side_rank(tq, pass.pos_out);
+            std::sort(cand.begin(), cand.end());
+            if (best_score < 8 && kk >= 3) {
+                do {
+                    const int sc = (pi > 0 ? side_rank(cand, pass.pos_in) : 4) + side_rank(cand, pass.pos_out);
+                    if (sc > best_score) { best_score = sc; best = cand; if (sc == 8) break; }
+                } while (std::next_permutation(cand.begin(), cand.end()));
+            }
+            tq = best;
+        }
         pass.tile_q = tq;
         std::vector<int> local_pos(n, -1);
         for (size_t i = 0; i < tq.size(); ++i) local_pos[tq[i]] = 2 * ((int)tq.size() - 1 - (int)i);
