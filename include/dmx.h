@@ -174,6 +174,17 @@ int dmx_pauli_batch(dmx_plan* plan, int64_t batch, const double* d_params, const
 int dmx_qp_reduce(const double* d_values, const double* d_weights, const int32_t* d_counts, int64_t batch,
                   double* d_out3, void* stream);
 
+/* Device-side draw of QP circuit variants — replaces the host loop of QuasiCircuitIdentifier._get_identifiers
+ * (src/error_mitigation.py:309-335: per gate np.random.choice(len(qp), p=|qp|/sum|qp|); sign = sign prod qp[idx],
+ * :321-323) and IErrorMitigationManager.set_identifier_range (:484-489) when 1e5..1e6 samples are wanted.
+ * qp [n_slots][stride] (host): the quasi-probabilities of every gate slot, n_choices[s] <= min(stride, 256) valid
+ * entries per row.  RNG: Philox4x32-10, counter (sample, slot), key = seed; sample b of this call is global sample
+ * first_sample + b, so ranks drawing disjoint ranges of one stream need no communication.
+ * d_variants [batch][n_slots] uint8, d_signs [batch] in {-1, 0, +1}.  Statistical (not bitwise) parity with numpy's
+ * generator; bit-exact against the numpy Philox restatement in tests/philox_ref.py. */
+int dmx_qp_sample_variants(int n_slots, const int32_t* n_choices, const double* qp, int stride, uint64_t seed,
+                           uint64_t first_sample, int64_t batch, uint8_t* d_variants, double* d_signs, void* stream);
+
 /* Same as dmx_energy_batch but with HOST buffers: copies params/variants in, runs, copies energies
  * out, and waits.  This is the call a non-CUDA-aware host (the reference's Python) binds. */
 int dmx_energy_batch_host(dmx_plan* plan, int64_t batch, const double* h_params, const uint8_t* h_variants,

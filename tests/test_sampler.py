@@ -1,0 +1,77 @@
+"""Device-side QP variant sampler (dmx_qp_sample_variants) — the device twin of QuasiCircuitIdentifier._get_identifiers
+(reference src/error_mitigation.py:309-335).  CPU: the numpy restatement of its RNG against the published Philox4x32-10
+known answers.  GPU: bit-exact equality with that restatement, the sampled distribution, the sign rule, rank slicing and
+the device-resident mitigated estimator."""
+import numpy as np
+import pytest
+
+import philox_ref as P
+
+
+def test_philox_reference_known_answers():
+    """Random123 kat_vectors for philox4x32-10 (counter, key -> output)."""
+    kat = [((0, 0, 0, 0), 0, (0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8)),
+           ((0xffffffff,) * 4, 0xffffffffffffffff, (0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd)),
+           ((0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344), (0x299f31d0 << 32) | 0xa4093822, (0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1))]
+    for ctr, key, want in kat:
+        got = P.philox4x32_10(*[[c] for c in ctr], key)
+        assert tuple(int(g[0]) for g in got) == want
+
+
+def test_reference_sampler_distribution_and_sign_rule():
+    qps = [np.array([1.2, -0.1, 0.0, -0.1]), np.array([0.5, 0.5]), np.linspace(-1, 1, 16)]
+    rows, signs = P.sample_variants(qps, 200000, seed=7)
+    for s, qp in enumerate(qps):
+        p = np.abs(qp) / np.abs(qp).sum()
+        freq = np.bincount(rows[:, s], minlength=len(qp)) / rows.shape[0]
+        assert np.max(np.abs(freq - p)) < 5e-3
+        assert freq[p == 0].sum() == 0                      # zero-probability entries are never drawn
+    want = np.prod([np.sign(qp[rows[:, s]]) for s, qp in enumerate(qps)], axis=0)
+    assert np.array_equal(signs, want)
+    # slices of one stream: first_sample offsets reproduce the same samples
+    rows2, signs2 = P.sample_variants(qps, 1000, seed=7, first_sample=5000)
+    assert np.array_equal(rows2, rows[5000:6000]) and np.array_equal(signs2, signs[5000:6000])
+
+
+@pytest.mark.gpu
+def test_device_sampler_is_bit_exact_with_reference():
+    import torch
+    from vqe_errormitigation_b200 import engine
+    rng = np.random.default_rng(11)
+    qps = [rng.normal(size=k) for k in (16, 256, 16, 2, 1, 256, 16)] + [np.array([1.3, -0.1, -0.1, -0.1] + [0.0] * 12)]
+    for batch, seed, first in ((1, 0, 0), (4097, 123456789012345, 0), (1000, 5, (1 << 33) + 17)):
+        dv, ds = engine.qp_sample_variants(qps, batch, seed, first_sample=first)
+        rv, rs = P.sample_variants(qps, batch, seed, first_sample=first)
+        assert np.array_equal(dv.cpu().numpy(), rv)
+        assert np.array_equal(ds.cpu().numpy(), rs)
+
+
+@pytest.mark.gpu
+def test_device_resident_mitigation_estimator():
+    """get_mu_effective_sampled: sampler + batched variant evaluation + reduction on the device equal the same estimator
+    assembled on the host from the reference-sampler's rows, and the mitigated value moves towards the noiseless one."""
+    import torch
+    from vqe_errormitigation_b200 import cirq_compat as cirq, engine
+    from vqe_errormitigation_b200.data_containers.helper_interfaces.i_noise_wrapper import INoiseModel, INoiseWrapper
+    from vqe_errormitigation_b200.data_containers.model_hydrogen import HydrogenAnsatz
+    from vqe_errormitigation_b200.error_mitigation import IErrorMitigationManager, TwoQubitDepolarizingChannel
+    from vqe_errormitigation_b200.processors.processor_quantum import QPU
+    w = HydrogenAnsatz()
+    w.operator_parameters["alpha0"] = 0.014133516193216759
+    noise = INoiseModel([cirq.depolarize(2e-3)], [TwoQubitDepolarizingChannel(2e-3)], "d")
+    n_w = INoiseWrapper(w, noise)
+    clean = QPU.get_resolved_circuit(n_w.get_clean_circuit(), w.operator_parameters)
+    mgr = IErrorMitigationManager(clean, noise, QPU.get_hamiltonian_objective_operator(w))
+    N, seed = 40000, 20260102
+    mean, stderr, n = mgr.get_mu_effective_sampled(N, seed)
+    assert n == N
+    qps = mgr._qp_matrix()
+    rows, signs = P.sample_variants(qps, N, seed)
+    scale = float(np.prod([np.sum(np.abs(q)) for q in qps]))
+    values = mgr._variant_program().energies(None, torch.tensor(rows)).cpu().numpy()
+    want = np.mean(signs * scale * values)
+    assert abs(mean - want) < 1e-10
+    assert abs(stderr - np.std(signs * scale * values) / np.sqrt(N)) < 1e-9
+    ideal = QPU.get_simulated_noisy_expectation_value(w, clean, cirq.ParamResolver({}))
+    noisy = QPU.get_simulated_noisy_expectation_value(n_w, QPU.get_resolved_circuit(n_w.get_noisy_circuit(), w.operator_parameters), cirq.ParamResolver({}))
+    assert abs(mean - ideal) < 6 * stderr + 1e-4 and abs(mean - ideal) < abs(noisy - ideal)

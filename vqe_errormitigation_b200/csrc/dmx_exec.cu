@@ -730,6 +730,55 @@ __global__ void dmx_fp64_fma_kernel(double* out, int iters) {
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// QP variant sampler: Philox4x32-10 counter RNG, one warp per sample, lanes over gate slots.
+// counter = (sample index lo, sample index hi, slot, 0), key = seed  ->  u in [0,1) from 53 random bits;
+// idx = first entry of the slot's cumulative |qp| table with cdf > u (np.random.choice(p=|qp|/sum|qp|),
+// src/error_mitigation.py:326-335); sign = sign prod qp[idx] (:321-323).
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void philox4x32_10(unsigned (&c)[4], unsigned k0, unsigned k1) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const unsigned hi0 = __umulhi(0xD2511F53u, c[0]), lo0 = 0xD2511F53u * c[0];
+        const unsigned hi1 = __umulhi(0xCD9E8D57u, c[2]), lo1 = 0xCD9E8D57u * c[2];
+        const unsigned n0 = hi1 ^ c[1] ^ k0, n2 = hi0 ^ c[3] ^ k1;
+        c[0] = n0; c[1] = lo1; c[2] = n2; c[3] = lo0;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+}
+
+__global__ void dmx_qp_sample_kernel(int n_slots, const int* __restrict__ n_choices, const double* __restrict__ cdf,
+                                     const unsigned char* __restrict__ sgn /* 0: +, 1: -, 2: zero */, int stride,
+                                     unsigned long long seed, unsigned long long first_sample, long long batch,
+                                     unsigned char* __restrict__ variants, double* __restrict__ signs) {
+    const int lane = threadIdx.x & 31;
+    const long long b = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (b >= batch) return;
+    const unsigned long long gidx = first_sample + (unsigned long long)b;
+    int neg = 0, zero = 0;
+    for (int s = lane; s < n_slots; s += 32) {
+        unsigned c[4] = {(unsigned)gidx, (unsigned)(gidx >> 32), (unsigned)s, 0u};
+        philox4x32_10(c, (unsigned)seed, (unsigned)(seed >> 32));
+        const double u = (double)((((unsigned long long)c[0] << 32) | c[1]) >> 11) * (1.0 / 9007199254740992.0);
+        const double* __restrict__ row = cdf + (size_t)s * stride;
+        int lo = 0, hi = n_choices[s] - 1;          // first index with row[idx] > u (row[last] = 1)
+        while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if (row[mid] > u) hi = mid; else lo = mid + 1;
+        }
+        variants[b * n_slots + s] = (unsigned char)lo;
+        const int sg = sgn[(size_t)s * stride + lo];
+        neg ^= sg == 1;
+        zero |= sg == 2;
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        neg ^= __shfl_xor_sync(0xffffffffu, neg, off);
+        zero |= __shfl_xor_sync(0xffffffffu, zero, off);
+    }
+    if (lane == 0) signs[b] = zero ? 0.0 : (neg ? -1.0 : 1.0);
+}
+
+// ---------------------------------------------------------------------------------------------------------
 // device mirror of a plan
 // ---------------------------------------------------------------------------------------------------------
 struct DevPlan {
@@ -1442,6 +1491,44 @@ int dmx_qp_reduce(const double* d_values, const double* d_weights, const int32_t
     dmx_qp_reduce_stage2<<<1, 32, 0, st>>>(partial[dev], d_out3);
     g_launches += 2;
     CUDA_TRY(cudaGetLastError());
+    return DMX_OK;
+}
+
+int dmx_qp_sample_variants(int n_slots, const int32_t* n_choices, const double* qp, int stride, uint64_t seed, uint64_t first_sample,
+                           int64_t batch, uint8_t* d_variants, double* d_signs, void* stream) {
+    if (n_slots < 1 || !n_choices || !qp || stride < 1 || batch < 0 || !d_variants || !d_signs) return fail(DMX_ERR_INVALID, "bad arguments");
+    std::vector<double> cdf((size_t)n_slots * stride, 1.0);
+    std::vector<unsigned char> sg((size_t)n_slots * stride, 0);
+    for (int s = 0; s < n_slots; ++s) {
+        const int K = n_choices[s];
+        if (K < 1 || K > stride || K > 256) return fail(DMX_ERR_INVALID, "n_choices must be in 1..min(stride, 256)");
+        const double* row = qp + (size_t)s * stride;
+        double total = 0.0;
+        for (int i = 0; i < K; ++i) total += std::fabs(row[i]);
+        if (!(total > 0.0)) return fail(DMX_ERR_INVALID, "quasi-probability row sums to zero");
+        double acc = 0.0;
+        for (int i = 0; i < K; ++i) {
+            acc += std::fabs(row[i]) / total;
+            cdf[(size_t)s * stride + i] = i == K - 1 ? 1.0 : acc;
+            sg[(size_t)s * stride + i] = row[i] == 0.0 ? 2 : (row[i] < 0.0 ? 1 : 0);
+        }
+    }
+    if (batch == 0) return DMX_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t cb = cdf.size() * 8, sb = sg.size(), nb = (size_t)n_slots * 4;
+    char* d = nullptr;
+    CUDA_TRY(cudaMallocAsync((void**)&d, cb + nb + sb, st));
+    // pageable sources: the copies complete with respect to the host before returning, so the vectors may go away
+    CUDA_TRY(cudaMemcpyAsync(d, cdf.data(), cb, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(d + cb, n_choices, nb, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(d + cb + nb, sg.data(), sb, cudaMemcpyHostToDevice, st));
+    const int threads = 256;
+    const long long grid = (batch * 32 + threads - 1) / threads;
+    dmx_qp_sample_kernel<<<(unsigned)grid, threads, 0, st>>>(n_slots, (const int*)(d + cb), (const double*)d, (const unsigned char*)(d + cb + nb),
+                                                             stride, seed, first_sample, batch, d_variants, d_signs);
+    ++g_launches;
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaFreeAsync(d, st));
     return DMX_OK;
 }
 

@@ -327,6 +327,36 @@ def qp_reduce(values, weights, counts=None):
     return out
 
 
+def pack_qp_tables(qps: Sequence[np.ndarray]) -> Tuple[np.ndarray, np.ndarray]:
+    """Row-padded table [S, max K] + valid lengths, the host-side input of dmx_qp_sample_variants (pack once, reuse)."""
+    S = len(qps)
+    stride = max(len(q) for q in qps)
+    table = np.zeros((S, stride), np.float64)
+    n_choices = np.zeros(S, np.int32)
+    for s, q in enumerate(qps):
+        table[s, :len(q)] = np.asarray(q, np.float64)
+        n_choices[s] = len(q)
+    return table, n_choices
+
+
+def qp_sample_variants(qps, batch: int, seed: int, first_sample: int = 0):
+    """Draw ``batch`` QP circuit variants on the device (``dmx_qp_sample_variants``): per gate slot an index with
+    probability |qp|/sum|qp| and the sample's sign — the device twin of QuasiCircuitIdentifier._get_identifiers
+    (reference error_mitigation.py:309-335).  Returns (variants uint8 [batch, S], signs float64 [batch]) CUDA tensors."""
+    torch = _require_cuda()
+    lib = _lib.load()
+    table, n_choices = qps if isinstance(qps, tuple) else pack_qp_tables(qps)
+    S, stride = table.shape
+    dev = torch.device("cuda", torch.cuda.current_device())
+    variants = torch.empty((batch, S), dtype=torch.uint8, device=dev)
+    signs = torch.empty(batch, dtype=torch.float64, device=dev)
+    stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    check(lib.dmx_qp_sample_variants(S, n_choices.ctypes.data_as(C.POINTER(C.c_int32)), table.ctypes.data_as(C.POINTER(C.c_double)),
+                                     stride, C.c_uint64(seed), C.c_uint64(first_sample), batch, C.c_void_p(variants.data_ptr()),
+                                     C.c_void_p(signs.data_ptr()), stream))
+    return variants, signs
+
+
 def measure_fp64_peak() -> float:
     _require_cuda()
     lib = _lib.load()
