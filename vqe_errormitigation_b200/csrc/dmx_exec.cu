@@ -93,19 +93,8 @@ __device__ __forceinline__ unsigned insert2(unsigned g, int p) {  // open a 2-bi
     return ((g >> p) << (p + 2)) | (g & ((1u << p) - 1u));
 }
 
-// Bank swizzle of the tile in shared memory: position = index with its low 4 bits (the 8-byte bank pair inside a
-// 128-byte line) XORed by a GF(2)-linear hash of the higher bits.  The hash columns were searched offline so that
-// for EVERY choice of qubit-pair positions the 32 lanes of a warp (which walk the five lowest free index bits)
-// cover all 16 bank pairs twice — the conflict-free optimum for 8-byte accesses.  Linear => swz(a ^ b) = swz(a) ^ swz(b),
-// so the XOR addressing below works on swizzled masks directly.
-__device__ __forceinline__ unsigned swz(unsigned i) {
-    const unsigned M0 = (1u << 4) | (1u << 5) | (1u << 7) | (1u << 9) | (1u << 10);
-    const unsigned M1 = (1u << 5) | (1u << 6) | (1u << 9) | (1u << 11) | (1u << 12) | (1u << 13);
-    const unsigned M2 = (1u << 5) | (1u << 6) | (1u << 8) | (1u << 9) | (1u << 11) | (1u << 12);
-    const unsigned M3 = (1u << 4) | (1u << 5) | (1u << 6) | (1u << 7) | (1u << 10) | (1u << 12) | (1u << 13);
-    const unsigned h = (__popc(i & M0) & 1u) | ((__popc(i & M1) & 1u) << 1) | ((__popc(i & M2) & 1u) << 2) | ((__popc(i & M3) & 1u) << 3);
-    return i ^ h;
-}
+// bank swizzle of the tile in shared memory (dmx_plan.hpp: SWZ_M)
+__device__ __forceinline__ unsigned swz(unsigned i) { return swz_hd(i); }
 
 // tile index of register e (bits zB, xB, zA, xA) = base ^ XOR of the masks of its set bits
 #define DMX_XADDR(base, m, e) ((base) ^ (((e) & 1) ? (m)[0] : 0u) ^ (((e) & 2) ? (m)[1] : 0u) ^ (((e) & 4) ? (m)[2] : 0u) ^ (((e) & 8) ? (m)[3] : 0u))

@@ -888,12 +888,8 @@ static void schedule_streaming(Plan& p) {
 
 // image of tile index bit `bit` in the 4-bit bank-pair index under the swizzle of dmx_stream.cuh / dmx_exec.cu
 static unsigned swz_col(int bit) {
-    const unsigned M[4] = {(1u << 4) | (1u << 5) | (1u << 7) | (1u << 9) | (1u << 10),
-                           (1u << 5) | (1u << 6) | (1u << 9) | (1u << 11) | (1u << 12) | (1u << 13),
-                           (1u << 5) | (1u << 6) | (1u << 8) | (1u << 9) | (1u << 11) | (1u << 12),
-                           (1u << 4) | (1u << 5) | (1u << 6) | (1u << 7) | (1u << 10) | (1u << 12) | (1u << 13)};
     unsigned v = bit < 4 ? 1u << bit : 0u;
-    for (int i = 0; i < 4; ++i) if ((M[i] >> bit) & 1u) v ^= 1u << i;
+    for (int i = 0; i < 4; ++i) if ((SWZ_M[i] >> bit) & 1u) v ^= 1u << i;
     return v;
 }
 

@@ -197,6 +197,13 @@ constexpr int STREAM_MAX_SWEEPS = 128, STREAM_MAX_MUS = 128, STREAM_MAX_BLOCKS =
 bool pass_stream_eligible(const Plan& p, const Pass& ps);
 std::string dump_plan(const Plan& p);
 
+// Bank swizzle of a tile in shared memory: position = index with its low 4 bits (the 8-byte bank pair inside a 128-byte
+// line) XORed by a GF(2)-linear hash of the higher bits; bit i of the hash = parity(index & SWZ_M[i]).  The masks were
+// searched offline (tools/search_swizzle.py) so that for EVERY choice of two or three resident-code positions in tiles
+// of 5..7 qubits the 16 lanes of a half-warp — which walk the four lowest remaining index bits — hit 16 distinct bank
+// pairs, and so do the linear staging loops: conflict-free 8-byte accesses.  Linear => swz(a ^ b) = swz(a) ^ swz(b).
+constexpr unsigned SWZ_M[4] = {0x1750u, 0x2aa0u, 0x1160u, 0x0ad0u};
+
 // helpers shared with exec
 inline int code_pos(int n, int q) { return 2 * (n - 1 - q); }
 uint32_t pauli_index(int n, uint32_t xmask, uint32_t zmask);

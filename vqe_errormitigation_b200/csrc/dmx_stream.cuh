@@ -67,15 +67,12 @@ __host__ __device__ __forceinline__ unsigned parity32(unsigned v) {
 #endif
 }
 
-// Same bank swizzle as dmx_tile_kernel (see dmx_exec.cu): GF(2)-linear, touches only the low 4 index bits.
+// bank swizzle (masks: dmx_plan.hpp)
 __host__ __device__ __forceinline__ unsigned swz_hd(unsigned i) {
-    const unsigned M0 = (1u << 4) | (1u << 5) | (1u << 7) | (1u << 9) | (1u << 10);
-    const unsigned M1 = (1u << 5) | (1u << 6) | (1u << 9) | (1u << 11) | (1u << 12) | (1u << 13);
-    const unsigned M2 = (1u << 5) | (1u << 6) | (1u << 8) | (1u << 9) | (1u << 11) | (1u << 12);
-    const unsigned M3 = (1u << 4) | (1u << 5) | (1u << 6) | (1u << 7) | (1u << 10) | (1u << 12) | (1u << 13);
-    const unsigned h = parity32(i & M0) | (parity32(i & M1) << 1) | (parity32(i & M2) << 2) | (parity32(i & M3) << 3);
+    const unsigned h = parity32(i & 0x1750u) | (parity32(i & 0x2aa0u) << 1) | (parity32(i & 0x1160u) << 2) | (parity32(i & 0x0ad0u) << 3);
     return i ^ h;
 }
+static_assert(SWZ_M[0] == 0x1750u && SWZ_M[1] == 0x2aa0u && SWZ_M[2] == 0x1160u && SWZ_M[3] == 0x0ad0u, "swizzle masks out of sync");
 
 __host__ __device__ __forceinline__ unsigned insert2_hd(unsigned g, int p) { return ((g >> p) << (p + 2)) | (g & ((1u << p) - 1u)); }
 
