@@ -14,7 +14,7 @@ def _nums(s, typ=float):
 
 
 def parse(dump: str) -> dict:
-    plan = {"blocks": [], "passes": [], "phases": [], "sweeps": [], "mus": [], "chains": [], "factors": [], "segs": [], "slots": {},
+    plan = {"blocks": [], "passes": [], "phases": [], "sweeps": [], "sweeps3": [], "mus": [], "chains": [], "factors": [], "segs": [], "slots": {},
             "rots": [], "fsegs": [], "fclasses": [], "flabels": {}}
     for line in dump.splitlines():
         if not line.strip():
@@ -56,6 +56,11 @@ def parse(dump: str) -> dict:
             sw["lmask"] = _nums(kv["lmask"], int)
             sw["smask"] = _nums(kv["smask"], int)
             plan["sweeps"].append(sw)
+        elif head == "sweep3":
+            sw = {k: int(kv[k]) for k in ("p0", "p1", "p2", "first_mu", "nmu", "lperm", "lcoef", "sperm", "scoef")}
+            sw["lmask"] = _nums(kv["lmask"], int)
+            sw["smask"] = _nums(kv["smask"], int)
+            plan["sweeps3"].append(sw)
         elif head == "mu":
             plan["mus"].append({k: int(kv[k]) for k in ("kind", "a0", "a1", "a2", "a3")})
         elif head == "chain":
@@ -163,6 +168,10 @@ def run_devops(plan, params=None, variants=None) -> np.ndarray:
             gpos = {2 * (k - 1 - i): 2 * (n - 1 - q) for i, q in enumerate(tile)}
         for ph in plan["phases"][ps["first_phase"]:ps["first_phase"] + ps["nphases"]]:
             mats = [chain_matrix(c) for c in plan["chains"][ph["first_chain"]:ph["first_chain"] + ph["nchains"]]]
+            if plan["sweeps3"]:
+                for sw in plan["sweeps3"][ph["first_sweep"]:ph["first_sweep"] + ph["nsweeps"]]:
+                    r = _run_sweep3(plan, sw, mats, gpos, r, idx)
+                continue
             for sw in plan["sweeps"][ph["first_sweep"]:ph["first_sweep"] + ph["nsweeps"]]:
                 g0, g1 = gpos[sw["p0"]], gpos[sw["p1"]]
                 c0, c1 = (idx >> g0) & 3, (idx >> g1) & 3
@@ -244,6 +253,71 @@ def run_devops(plan, params=None, variants=None) -> np.ndarray:
                     assert np.array_equal(xor_index(sw["smask"]), idx)
                     r = v
     return r[np.arange(4 ** n) << pad]
+
+
+def _run_sweep3(plan, sw, mats, gpos, r, idx):
+    """One triple sweep as dmx_stream3_kernel executes it: register e = 16*code(A) + 4*code(B) + code(C)."""
+    cf = plan["coefs"]
+    lp = (sw["p0"], sw["p1"], sw["p2"])
+    g = [gpos[x] for x in lp]
+    codes = [(idx >> gg) & 3 for gg in g]
+    loc = codes[0] * 16 + codes[1] * 4 + codes[2]
+    clear = idx & ~(3 << g[0]) & ~(3 << g[1]) & ~(3 << g[2])
+
+    def gmask(m):
+        out = 0
+        for l, gg in zip(lp, g):
+            out |= ((int(m) >> l) & 3) << gg
+        return out
+
+    def xor_index(masks):
+        x = np.zeros_like(idx)
+        for j in range(6):
+            x ^= np.where((loc >> j) & 1, gmask(masks[j]), 0)
+        return clear ^ x
+
+    if sw["lperm"]:
+        v = cf[sw["lcoef"] + loc] * r[xor_index(sw["lmask"])]
+    else:
+        assert np.array_equal(xor_index(sw["lmask"]), idx)
+        v = r.copy()
+
+    def one(v, M, slot, unital):
+        if unital:
+            assert M[0, 0] == 1 and not M[0, 1:].any() and not M[1:, 0].any()
+        new = np.zeros_like(v)
+        for b in range(4):
+            new += M[codes[slot], b] * v[(idx & ~(3 << g[slot])) | (b << g[slot])]
+        return new
+
+    pairs = ((0, 1), (0, 2), (1, 2))
+    for m in plan["mus"][sw["first_mu"]:sw["first_mu"] + sw["nmu"]]:
+        kind = m["kind"]
+        if kind == 16:
+            M = mats[m["a0"]] if m["a2"] else cf[m["a0"]:m["a0"] + 16].reshape(4, 4)
+            v = one(v, M, m["a1"], m["a3"])
+        elif kind == 17:
+            v = v * cf[m["a0"] + codes[m["a1"]]]
+        elif kind == 18:
+            s0, s1 = pairs[m["a1"]]
+            v = v * cf[m["a0"] + codes[s0] * 4 + codes[s1]]
+        elif kind == 19:
+            s0, s1 = pairs[m["a1"]]
+            M = cf[m["a0"]:m["a0"] + 256].reshape(16, 16)
+            l2 = codes[s0] * 4 + codes[s1]
+            new = np.zeros_like(v)
+            for b in range(16):
+                src = (idx & ~(3 << g[s0]) & ~(3 << g[s1])) | ((b >> 2) << g[s0]) | ((b & 3) << g[s1])
+                new += M[l2, b] * v[src]
+            v = new
+        else:
+            raise ValueError(f"unexpected micro-op kind {kind} in a triple sweep")
+    if sw["sperm"]:
+        out = np.zeros_like(v)
+        out[xor_index(sw["smask"])] = cf[sw["scoef"] + loc] * v
+        return out
+    assert np.array_equal(xor_index(sw["smask"]), idx)
+    return v
 
 
 def run_segments(plan, params=None, variants=None):

@@ -9,7 +9,7 @@ import pytest
 
 import plan_interp as PI
 from oracle import dm_oracle as O
-from test_gpu_parity import qp_noisy_variant_program, random_circuit, random_hamiltonian, resolve
+from test_gpu_parity import qp_noisy_variant_program, random_circuit, random_hamiltonian, random_unitary, resolve
 from workloads import ALPHA_STAR, GOLDEN, build_program, h2_ops, h2_terms
 
 TOL = 1e-11
@@ -143,13 +143,20 @@ def test_streaming_schedule_partitions_all_blocks():
             ops += [("u", (q, q + 1), O.CNOT), ("k", (q, q + 1), O.two_qubit_depolarize(1e-3))]
     rng = np.random.default_rng(1)
     terms = random_hamiltonian(rng, n, 5)
-    for tile, remap in ((4, 1), (5, 1), (7, 0), (6, 1), (7, 1)):
-        prog = build_program(ops, n, terms, tile_qubits=tile, remap=remap)
+    n_pair_sweeps = None
+    for tile, remap, triples in ((4, 1, 1), (5, 1, 1), (7, 0, 1), (6, 1, 0), (7, 1, 0), (6, 1, 1), (7, 1, 1)):
+        prog = build_program(ops, n, terms, tile_qubits=tile, remap=remap, triples=triples)
         plan = PI.parse(prog.dump())
         assert prog.info["path"] == 2
         assert sum(p["nphases"] for p in plan["passes"]) == len(plan["phases"])
-        assert sum(ph["nsweeps"] for ph in plan["phases"]) == len(plan["sweeps"])
-        assert len(plan["sweeps"]) < len(plan["blocks"])     # several fused blocks per shared-memory round trip
+        sweeps = plan["sweeps3"] if (remap and triples and tile >= 6) else plan["sweeps"]
+        assert sum(ph["nsweeps"] for ph in plan["phases"]) == len(sweeps)
+        assert len(sweeps) < len(plan["blocks"])     # several fused blocks per shared-memory round trip
+        if tile == 7 and remap:
+            if not triples:
+                n_pair_sweeps = len(sweeps)
+            else:
+                assert len(sweeps) < 0.75 * n_pair_sweeps        # a CNOT chain advances two links per triple sweep
         if remap and tile >= 6:
             # remapping scheduler: consecutive tiles share the two qubits that sit lowest in the layout between them,
             # layouts chain from pass to pass and the last pass restores the standard order
@@ -170,3 +177,48 @@ def test_streaming_schedule_partitions_all_blocks():
         r = PI.run_devops(plan, vals)
         rho = O.simulate(n, resolve(ops, prog.param_names, vals))
         assert abs(PI.energy(plan, r) - O.energy_sparse(rho, O.pauli_terms_to_matrix(n, *terms))) < TOL
+
+
+def _clifford_mix_circuit(rng, n, depth):
+    """Random mix that exercises every branch of the triple-sweep builder: Clifford gates with Pauli noise (monomial blocks:
+    load / store permutations), rotations (chains), dense one- and two-qubit maps, non-unital noise, diagonal two-qubit noise."""
+    cz = np.diag([1, 1, 1, -1]).astype(complex)
+    swap = np.eye(4)[[0, 2, 1, 3]].astype(complex)
+    ops = []
+    for _ in range(depth):
+        kind = int(rng.integers(0, 10))
+        a, b = (int(v) for v in rng.choice(n, 2, replace=False))
+        if kind == 0:
+            ops += [("u", (a,), O.H), ("k", (a,), O.depolarize(1e-2))]
+        elif kind == 1:
+            ops += [("u", (a,), O.rx(np.pi / 2 * int(rng.integers(1, 4)))), ("k", (a,), O.bit_flip(2e-2))]
+        elif kind in (2, 3):
+            ops += [("u", (a, b), O.CNOT), ("k", (a, b), O.two_qubit_depolarize(1e-2))]
+        elif kind == 4:
+            ops += [("u", (a, b), cz if rng.integers(2) else swap), ("k", (a, b), O.two_qubit_pauli_channel(1e-2, 2e-2, 3e-2))]
+        elif kind in (5, 6):
+            ops += [("r", (a,), (int(rng.integers(3)), f"t{int(rng.integers(4))}", float(rng.normal()), float(rng.normal()))),
+                    ("k", (a,), O.depolarize(1e-2))]
+        elif kind == 7:
+            ops.append(("k", (a, b), O.two_qubit_depolarize(3e-2)))            # diagonal two-qubit block on its own
+        elif kind == 8:
+            ops.append(("u", (a, b), random_unitary(rng, 4)))
+        else:
+            ops.append(("k", (a,), O.amplitude_damp(0.05)))
+    return ops
+
+
+@pytest.mark.parametrize("seed,tile", [(1, 6), (2, 7), (3, 6), (4, 7)])
+def test_triple_sweep_lowering_random_clifford_mix(seed, tile):
+    n = 8
+    rng = np.random.default_rng(800 + seed)
+    ops = _clifford_mix_circuit(rng, n, 70)
+    terms = random_hamiltonian(rng, n, 12)
+    prog = build_program(ops, n, terms, tile_qubits=tile)
+    plan = PI.parse(prog.dump())
+    assert prog.info["path"] == 2 and plan["sweeps3"] and not plan["sweeps"]
+    assert any(sw["lperm"] or sw["sperm"] for sw in plan["sweeps3"])
+    vals = rng.uniform(-1, 1, size=prog.n_params)
+    rho = O.simulate(n, resolve(ops, prog.param_names, vals))
+    want = O.energy_sparse(rho, O.pauli_terms_to_matrix(n, *terms))
+    assert abs(PI.energy(plan, PI.run_devops(plan, vals)) - want) < TOL

@@ -804,6 +804,7 @@ struct DevPlan {
     struct PassX {
         bool ok = false;
         std::vector<SweepX> sweeps;  // travel in the kernel parameters
+        std::vector<SweepX3> sweeps3; // triple-sweep plans
         std::vector<MuX> mus;
         bool general = false;        // needs the 4x4 / dense micro-ops
         double* coefs = nullptr;     // device: pass-local fixed coefficients
@@ -854,7 +855,46 @@ static cudaError_t build_stream_tables(const Plan& p, DevPlan* d) {
             return at;
         };
         bool ok = true;
-        for (int ph = 0; ph < ps.n_phases && ok; ++ph) {
+        std::vector<SweepX3> sx3;
+        for (int ph = 0; ph < ps.n_phases && ok && p.triples; ++ph) {
+            const Phase& phase = p.phases[ps.first_phase + ph];
+            for (int si = 0; si < phase.n_sweeps && ok; ++si) {
+                const Sweep3& sw = p.sweeps3[phase.first_sweep + si];
+                SweepX3 x{};
+                int sorted[3] = {sw.p[0], sw.p[1], sw.p[2]};
+                std::sort(sorted, sorted + 3);
+                for (int j = 0; j < 3; ++j) x.p[j] = sorted[j];
+                x.first_mu = (int)mx.size(); x.n_mu = sw.n_mu;
+                x.lscale = sw.load_perm ? px.n_chains * 16 + local(sw.lcoef, 64) : -1;
+                x.sscale = sw.store_perm ? px.n_chains * 16 + local(sw.scoef, 64) : -1;
+                auto S = [](uint32_t m) { return swz_hd(m) << 3; };
+                for (int c = 0; c < 4; ++c) {       // register bits (zC, xC, zB, xB, zA, xA) = masks 0..5
+                    x.lC[c] = ((c & 1) ? S(sw.lmask[0]) : 0u) ^ ((c & 2) ? S(sw.lmask[1]) : 0u);
+                    x.lB[c] = ((c & 1) ? S(sw.lmask[2]) : 0u) ^ ((c & 2) ? S(sw.lmask[3]) : 0u);
+                    x.lA[c] = ((c & 1) ? S(sw.lmask[4]) : 0u) ^ ((c & 2) ? S(sw.lmask[5]) : 0u);
+                    x.sC[c] = ((c & 1) ? S(sw.smask[0]) : 0u) ^ ((c & 2) ? S(sw.smask[1]) : 0u);
+                    x.sB[c] = ((c & 1) ? S(sw.smask[2]) : 0u) ^ ((c & 2) ? S(sw.smask[3]) : 0u);
+                    x.sA[c] = ((c & 1) ? S(sw.smask[4]) : 0u) ^ ((c & 2) ? S(sw.smask[5]) : 0u);
+                }
+                for (int mi = 0; mi < sw.n_mu && ok; ++mi) {
+                    const MicroOp& m = p.mus[sw.first_mu + mi];
+                    MuX y{};
+                    y.kind = m.kind; y.pad = m.a1;
+                    switch (m.kind) {
+                        case MU3_MAT:
+                            y.off = m.a2 ? (phase.first_chain + m.a0 - px.first_chain) * 16 : px.n_chains * 16 + local(m.a0, 16);
+                            y.unital = m.a3; px.general |= !m.a3; break;
+                        case MU3_DIAG: y.off = px.n_chains * 16 + local(m.a0, 4); break;
+                        case MU3_DIAG2: y.off = px.n_chains * 16 + local(m.a0, 16); break;
+                        case MU3_MAT2: y.off = px.n_chains * 16 + local(m.a0, 256); px.general = true; break;
+                        default: ok = false; break;
+                    }
+                    mx.push_back(y);
+                }
+                sx3.push_back(x);
+            }
+        }
+        for (int ph = 0; ph < ps.n_phases && ok && !p.triples; ++ph) {
             const Phase& phase = p.phases[ps.first_phase + ph];
             for (int si = 0; si < phase.n_sweeps && ok; ++si) {
                 const SweepDev& sw = p.sweeps[phase.first_sweep + si];
@@ -890,11 +930,11 @@ static cudaError_t build_stream_tables(const Plan& p, DevPlan* d) {
                 sx.push_back(x);
             }
         }
-        if (!ok || sx.size() > (size_t)STREAM_MAX_SWEEPS || mx.size() > (size_t)STREAM_MAX_MUS) continue;
-        px.n_sweeps = (int)sx.size(); px.n_mus = (int)mx.size(); px.n_coefs = (int)lc.size();
+        if (!ok || sx.size() + sx3.size() > (size_t)STREAM_MAX_SWEEPS || mx.size() > (size_t)STREAM_MAX_MUS) continue;
+        px.n_sweeps = (int)(sx.size() + sx3.size()); px.n_mus = (int)mx.size(); px.n_coefs = (int)lc.size();
         px.smem = ((size_t)32 * threads + (size_t)px.n_chains * 16 + lc.size() + 2) * 8;
         if (px.smem > (k == 7 ? 227u : 56u) * 1024) continue;       // k = 6: keep four CTAs per SM
-        px.sweeps = sx; px.mus = mx;
+        px.sweeps = sx; px.sweeps3 = sx3; px.mus = mx;
         if (lc.empty()) lc.push_back(0.0);
         cudaError_t e = upload(&px.coefs, lc);
         if (e != cudaSuccess) return e;
@@ -1090,6 +1130,25 @@ static int launch_stream(const StreamArgs& a, long long grid, size_t smem, cudaS
     return DMX_OK;
 }
 
+template <int THREADS, bool GENERAL>
+static int launch_stream3(const StreamArgs3& a, long long grid, size_t smem, cudaStream_t st) {
+    static std::mutex mu;
+    static size_t configured = 0;
+    {
+        std::lock_guard<std::mutex> lock(mu);
+        if (smem > configured) {
+            const int want = (int)std::max(smem, (size_t)48 * 1024);
+            CUDA_TRY(cudaFuncSetAttribute(dmx_stream3_kernel<THREADS, GENERAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, want));
+            CUDA_TRY(cudaFuncSetAttribute(dmx_stream3_kernel<THREADS, GENERAL>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+            configured = want;
+        }
+    }
+    dmx_stream3_kernel<THREADS, GENERAL><<<(unsigned)grid, THREADS, smem, st>>>(a);
+    ++g_launches;
+    CUDA_TRY(cudaGetLastError());
+    return DMX_OK;
+}
+
 static unsigned map_runs_host(unsigned v, const BitRun* runs, int n) {
     unsigned g = 0;
     for (int i = 0; i < n; ++i) g |= ((v >> runs[i].lshift) & ((1u << runs[i].width) - 1u)) << runs[i].gshift;
@@ -1132,49 +1191,60 @@ static int run_streaming(Plan& p, DevPlan* d, long long chunk, long long circuit
         const DevPlan::PassX& px = d->passx[pi];
         if (!ps.pos_in.empty() && !(px.ok && g_stream_kernel)) { rc = fail(DMX_ERR_STATE, "remapped plan needs the stream kernel"); break; }
         if (px.ok && g_stream_kernel) {
-            StreamArgs a{};
-            std::copy(px.sweeps.begin(), px.sweeps.end(), a.sweeps);
-            std::copy(px.mus.begin(), px.mus.end(), a.mus);
-            a.coefs = px.coefs; a.chainmats = chainmats;
-            a.n_sweeps = px.n_sweeps; a.n_mus = px.n_mus; a.n_coefs = px.n_coefs;
-            a.total_chains = total_chains; a.first_chain = px.first_chain; a.n_chains = px.n_chains;
-            a.n = p.n; a.k = k; a.load = pi > 0;
-            {
+            if ((int)others.size() > 8) { rc = fail(DMX_ERR_UNSUPPORTED, "more than 8 non-resident qubits"); break; }
+            std::vector<int> std_pos(p.n);
+            for (int q = 0; q < p.n; ++q) std_pos[q] = p.n - 1 - q;
+            // fields shared by StreamArgs (pair sweeps) and StreamArgs3 (triple sweeps)
+            auto fill = [&](auto& a, unsigned threads, unsigned niter) {
+                std::copy(px.mus.begin(), px.mus.end(), a.mus);
+                a.coefs = px.coefs; a.chainmats = chainmats;
+                a.n_sweeps = px.n_sweeps; a.n_mus = px.n_mus; a.n_coefs = px.n_coefs;
+                a.total_chains = total_chains; a.first_chain = px.first_chain; a.n_chains = px.n_chains;
+                a.n = p.n; a.k = k; a.load = pi > 0;
                 const size_t last = p.passes.size() - 1;
                 double* bufs[2] = {state, p.remapped ? state2 : state};
                 a.dst = bufs[(last - pi) & 1];
                 a.src = bufs[(last - pi + 1) & 1];
-            }
-            std::vector<int> std_pos(p.n);
-            for (int q = 0; q < p.n; ++q) std_pos[q] = p.n - 1 - q;
-            const unsigned threads = k == 7 ? 512u : 128u;
-            auto side = [&](const std::vector<int>& pos, int& n_gruns, int& n_oruns, int (*gruns)[3], int (*uruns)[3], int (*oruns)[3],
-                            uint32_t* giter, uint32_t* siter, uint32_t& pbit) {
-                std::vector<int> tq = ps.tile_q;                  // tile_q[i] sits at tile bits 2*(k-1-i)
-                std::vector<int> tl(p.n, -1);
-                for (int i = 0; i < k; ++i) tl[tq[i]] = k - 1 - i;
-                std::sort(tq.begin(), tq.end(), [&](int x, int y) { return pos[x] < pos[y]; });
-                n_gruns = k;
-                for (int i = 0; i < k; ++i) {
-                    gruns[i][0] = 2 * i; gruns[i][1] = 2 * pos[tq[i]]; gruns[i][2] = 2;
-                    uruns[i][0] = 2 * i; uruns[i][1] = 2 * tl[tq[i]]; uruns[i][2] = 2;
-                }
-                n_oruns = (int)others.size();
-                for (int i = 0; i < n_oruns; ++i) { oruns[i][0] = 2 * i; oruns[i][1] = 2 * pos[others[i]]; oruns[i][2] = 2; }
-                auto dep = [&](unsigned v, int (*runs)[3]) {
-                    unsigned g = 0;
-                    for (int i = 0; i < k; ++i) g |= ((v >> runs[i][0]) & 3u) << runs[i][1];
-                    return g;
+                auto side = [&](const std::vector<int>& pos, int& n_gruns, int& n_oruns, int (*gruns)[3], int (*uruns)[3], int (*oruns)[3],
+                                uint32_t* giter, uint32_t* siter, uint32_t& pbit) {
+                    std::vector<int> tq = ps.tile_q;                  // tile_q[i] sits at tile bits 2*(k-1-i)
+                    std::vector<int> tl(p.n, -1);
+                    for (int i = 0; i < k; ++i) tl[tq[i]] = k - 1 - i;
+                    std::sort(tq.begin(), tq.end(), [&](int x, int y) { return pos[x] < pos[y]; });
+                    n_gruns = k;
+                    for (int i = 0; i < k; ++i) {
+                        gruns[i][0] = 2 * i; gruns[i][1] = 2 * pos[tq[i]]; gruns[i][2] = 2;
+                        uruns[i][0] = 2 * i; uruns[i][1] = 2 * tl[tq[i]]; uruns[i][2] = 2;
+                    }
+                    n_oruns = (int)others.size();
+                    for (int i = 0; i < n_oruns; ++i) { oruns[i][0] = 2 * i; oruns[i][1] = 2 * pos[others[i]]; oruns[i][2] = 2; }
+                    auto dep = [&](unsigned v, int (*runs)[3]) {
+                        unsigned g = 0;
+                        for (int i = 0; i < k; ++i) g |= ((v >> runs[i][0]) & 3u) << runs[i][1];
+                        return g;
+                    };
+                    for (unsigned jj = 0; jj < niter; ++jj) { giter[jj] = dep(jj * 2u * threads, gruns); siter[jj] = swz_hd(dep(jj * 2u * threads, uruns)); }
+                    pbit = swz_hd(dep(1u, uruns));
                 };
-                for (unsigned j = 0; j < 16; ++j) { giter[j] = dep(j * 2u * threads, gruns); siter[j] = swz_hd(dep(j * 2u * threads, uruns)); }
-                pbit = swz_hd(dep(1u, uruns));
+                side(ps.pos_in.empty() ? std_pos : ps.pos_in, a.n_gruns_l, a.n_oruns_l, a.gruns_l, a.uruns_l, a.oruns_l, a.giter_l, a.siter_l, a.pbit_l);
+                side(ps.pos_out.empty() ? std_pos : ps.pos_out, a.n_gruns_s, a.n_oruns_s, a.gruns_s, a.uruns_s, a.oruns_s, a.giter_s, a.siter_s, a.pbit_s);
+                a.init_mask = 0xAAAAAAAAu;
             };
-            if ((int)others.size() > 8) { rc = fail(DMX_ERR_UNSUPPORTED, "more than 8 non-resident qubits"); break; }
-            side(ps.pos_in.empty() ? std_pos : ps.pos_in, a.n_gruns_l, a.n_oruns_l, a.gruns_l, a.uruns_l, a.oruns_l, a.giter_l, a.siter_l, a.pbit_l);
-            side(ps.pos_out.empty() ? std_pos : ps.pos_out, a.n_gruns_s, a.n_oruns_s, a.gruns_s, a.uruns_s, a.oruns_s, a.giter_s, a.siter_s, a.pbit_s);
-            a.init_mask = 0xAAAAAAAAu;
-            if (k == 7) rc = px.general ? launch_stream<512, true>(a, groups, px.smem, st) : launch_stream<512, false>(a, groups, px.smem, st);
-            else rc = px.general ? launch_stream<128, true>(a, groups, px.smem, st) : launch_stream<128, false>(a, groups, px.smem, st);
+            if (p.triples) {
+                static thread_local StreamArgs3 a3;      // ~19 KB of kernel parameters: keep it off the stack
+                a3 = StreamArgs3{};
+                std::copy(px.sweeps3.begin(), px.sweeps3.end(), a3.sweeps);
+                fill(a3, k == 7 ? 256u : 64u, 32u);
+                if (k == 7) rc = px.general ? launch_stream3<256, true>(a3, groups, px.smem, st) : launch_stream3<256, false>(a3, groups, px.smem, st);
+                else rc = px.general ? launch_stream3<64, true>(a3, groups, px.smem, st) : launch_stream3<64, false>(a3, groups, px.smem, st);
+            } else {
+                static thread_local StreamArgs a2;
+                a2 = StreamArgs{};
+                std::copy(px.sweeps.begin(), px.sweeps.end(), a2.sweeps);
+                fill(a2, k == 7 ? 512u : 128u, 16u);
+                if (k == 7) rc = px.general ? launch_stream<512, true>(a2, groups, px.smem, st) : launch_stream<512, false>(a2, groups, px.smem, st);
+                else rc = px.general ? launch_stream<128, true>(a2, groups, px.smem, st) : launch_stream<128, false>(a2, groups, px.smem, st);
+            }
             continue;
         }
         try {
@@ -1310,6 +1380,8 @@ int dmx_plan_set_option(dmx_plan* plan, const char* key, int value) {
         plan->p.opt_tile_qubits = value;
     } else if (k == "remap") {
         plan->p.opt_remap = value != 0;
+    } else if (k == "triples") {
+        plan->p.opt_triples = value != 0;
     } else if (k == "stream_kernel") {
         g_stream_kernel = value != 0;
     } else if (k == "stream_chunk") {

@@ -796,6 +796,288 @@ struct SweepBuilder {
     }
 };
 
+// Triple-sweep builder (see Sweep3 in dmx_plan.hpp).  A sweep is  [monomial blocks]* [general blocks]* [monomial blocks]*
+// on three tile qubits: the leading / trailing monomials are composed into the load / store permutation, everything
+// between runs on the 64 register-resident coefficients.  Only FIXED and ROT blocks (no variant slots).
+struct TripleBuilder {
+    Plan& p;
+    CoefCache& cc;
+    const std::vector<int>& local_pos;
+    const std::vector<int>& tile_q;
+    Phase phase{};
+    double flops = 0.0, sweeps_elems = 0.0;
+
+    TripleBuilder(Plan& plan, CoefCache& cache, const std::vector<int>& lp, const std::vector<int>& tq)
+        : p(plan), cc(cache), local_pos(lp), tile_q(tq) {
+        phase.first_sweep = (int)p.sweeps3.size();
+        phase.first_chain = (int)p.chains.size();
+    }
+
+    struct Mono {            // out[a] = sc[a] * in[src[a]] on the 64 codes of the triple
+        int src[64];
+        double sc[64];
+        bool trivial = true;
+        Mono() { for (int a = 0; a < 64; ++a) { src[a] = a; sc[a] = 1.0; } }
+        void then(const Mono& m) {      // apply m after this
+            int ns[64];
+            double nc[64];
+            for (int a = 0; a < 64; ++a) { ns[a] = src[m.src[a]]; nc[a] = m.sc[a] * sc[m.src[a]]; }
+            for (int a = 0; a < 64; ++a) { src[a] = ns[a]; sc[a] = nc[a]; }
+            trivial = false;
+        }
+    };
+
+    int T[3] = {-1, -1, -1};
+    int slot_of(int q) const { for (int s = 0; s < 3; ++s) if (T[s] == q) return s; return -1; }
+    static int shift(int slot) { return 4 - 2 * slot; }
+
+    // block -> monomial on the 64 codes (false when the block is not a GF(2)-linear signed permutation x scales)
+    bool as_mono(const Block& b, Mono& out) const {
+        if (b.kind != BK_FIXED || (b.cls != CLS_MONO && b.cls != CLS_DIAG && b.cls != CLS_IDENT)) return false;
+        const int dim = b.dim();
+        std::vector<int> src(dim, -1);
+        std::vector<double> sc(dim, 0.0);
+        for (int a = 0; a < dim; ++a) {
+            for (int c = 0; c < dim; ++c)
+                if (b.M[a * dim + c] != 0.0) { if (src[a] >= 0) return false; src[a] = c; sc[a] = b.M[a * dim + c]; }
+            if (src[a] < 0) return false;
+        }
+        for (int a = 0; a < dim; ++a)
+            for (int c = 0; c < dim; ++c)
+                if (src[a ^ c] != (src[a] ^ src[c])) return false;
+        out = Mono();
+        out.trivial = false;
+        if (b.nq == 1) {
+            const int sh = shift(slot_of(b.q[0]));
+            for (int a = 0; a < 64; ++a) {
+                const int c = (a >> sh) & 3;
+                out.src[a] = (a & ~(3 << sh)) | (src[c] << sh);
+                out.sc[a] = sc[c];
+            }
+        } else {
+            const int s0 = shift(slot_of(b.q[0])), s1 = shift(slot_of(b.q[1]));
+            for (int a = 0; a < 64; ++a) {
+                const int c = (((a >> s0) & 3) << 2) | ((a >> s1) & 3);
+                const int sv = src[c];
+                out.src[a] = (a & ~(3 << s0) & ~(3 << s1)) | ((sv >> 2) << s0) | ((sv & 3) << s1);
+                out.sc[a] = sc[c];
+            }
+        }
+        return true;
+    }
+
+    static MicroOp mu(int kind, int a0 = 0, int a1 = 0, int a2 = 0, int a3 = 0) {
+        MicroOp m{};
+        m.kind = kind; m.a0 = a0; m.a1 = a1; m.a2 = a2; m.a3 = a3;
+        return m;
+    }
+
+    std::vector<MicroOp> mus;
+    std::vector<ChainDev> new_chains;
+    std::vector<ChainFactor> new_factors;
+    std::vector<int> pend[3];
+
+    void flush_slot(int slot) {
+        std::vector<int>& pd = pend[slot];
+        if (pd.empty()) return;
+        bool any_rot = false;
+        for (int bi : pd) any_rot |= p.blocks[bi].kind == BK_ROT;
+        if (!any_rot) {
+            std::vector<double> M = identity(4);
+            for (int bi : pd) M = matmul(p.blocks[bi].M, M, 4);
+            const int cls = classify(M, 4);
+            if (cls == CLS_DIAG || cls == CLS_IDENT) {
+                if (cls != CLS_IDENT) { mus.push_back(mu(MU3_DIAG, cc.get(p, {M[0], M[5], M[10], M[15]}), slot)); flops += 1.0; }
+            } else {
+                const bool un = is_unital3(M);
+                mus.push_back(mu(MU3_MAT, cc.get(p, M), slot, 0, un));
+                flops += un ? 15.0 / 4 : 28.0 / 4;
+            }
+        } else {
+            ChainDev ch{(int)new_factors.size(), 0};
+            bool unital = true;
+            for (int bi : pd) {
+                const Block& b = p.blocks[bi];
+                ChainFactor f{};
+                if (b.kind == BK_ROT) {
+                    std::vector<double> acs;
+                    acs.insert(acs.end(), b.A.begin(), b.A.end());
+                    acs.insert(acs.end(), b.C.begin(), b.C.end());
+                    acs.insert(acs.end(), b.S.begin(), b.S.end());
+                    f.kind = 1; f.coef = cc.get(p, acs); f.rot_id = b.rot_id;
+                    unital = unital && is_unital3(b.A);
+                    for (int e = 0; e < 4; ++e)
+                        if (b.C[e] != 0.0 || b.S[e] != 0.0 || b.C[4 * e] != 0.0 || b.S[4 * e] != 0.0) unital = false;
+                } else {
+                    f.kind = 0; f.coef = cc.get(p, b.M); f.rot_id = -1;
+                    unital = unital && is_unital3(b.M);
+                }
+                new_factors.push_back(f);
+                ++ch.n_factors;
+            }
+            mus.push_back(mu(MU3_MAT, (int)new_chains.size(), slot, 1, unital));
+            new_chains.push_back(ch);
+            flops += unital ? 15.0 / 4 : 28.0 / 4;
+        }
+        pd.clear();
+    }
+
+    uint32_t code_offset(int code) const {
+        return ((uint32_t)((code >> 4) & 3) << local_pos[T[0]]) | ((uint32_t)((code >> 2) & 3) << local_pos[T[1]]) |
+               ((uint32_t)(code & 3) << local_pos[T[2]]);
+    }
+
+    void emit(const Mono& lp, const Mono& sp) {
+        for (int s = 0; s < 3; ++s) flush_slot(s);
+        if (mus.empty() && lp.trivial && sp.trivial) return;
+        Sweep3 sw{};
+        for (int s = 0; s < 3; ++s) sw.p[s] = local_pos[T[s]];
+        const int chain_base = (int)p.chains.size() - phase.first_chain;
+        const int factor_base = (int)p.factors.size();
+        for (ChainDev ch : new_chains) { ch.first_factor += factor_base; p.chains.push_back(ch); }
+        p.factors.insert(p.factors.end(), new_factors.begin(), new_factors.end());
+        for (MicroOp& m : mus)
+            if (m.kind == MU3_MAT && m.a2) m.a0 += chain_base;
+        for (int j = 0; j < 6; ++j) { sw.lmask[j] = code_offset(1 << j); sw.smask[j] = code_offset(1 << j); }
+        if (!lp.trivial) {
+            sw.load_perm = 1;
+            sw.lcoef = cc.get(p, std::vector<double>(lp.sc, lp.sc + 64));
+            for (int j = 0; j < 6; ++j) sw.lmask[j] = code_offset(lp.src[1 << j]);
+            flops += 1.0;
+        }
+        if (!sp.trivial) {
+            // out[a] = sc[a] * v[src[a]]  <=>  register e goes to code dst[e] = src^-1[e] with scale sc[dst[e]]
+            int dst[64];
+            for (int a = 0; a < 64; ++a) dst[sp.src[a]] = a;
+            std::vector<double> se(64);
+            for (int e = 0; e < 64; ++e) se[e] = sp.sc[dst[e]];
+            sw.store_perm = 1;
+            sw.scoef = cc.get(p, se);
+            for (int j = 0; j < 6; ++j) sw.smask[j] = code_offset(dst[1 << j]);
+            flops += 1.0;
+        }
+        sw.first_mu = (int)p.mus.size(); sw.n_mu = (int)mus.size();
+        p.mus.insert(p.mus.end(), mus.begin(), mus.end());
+        p.sweeps3.push_back(sw);
+        sweeps_elems += 1.0;
+        mus.clear(); new_chains.clear(); new_factors.clear();
+    }
+
+    void run(const std::vector<int>& order) {
+        const int n = p.n;
+        std::vector<std::vector<int>> qq(n);
+        std::vector<size_t> head(n, 0);
+        std::vector<char> resident(n, 0);
+        for (int q : tile_q) resident[q] = 1;
+        for (int bi : order) {
+            const Block& b = p.blocks[bi];
+            if (b.kind == BK_VAR) throw std::runtime_error("triple sweeps do not take variant blocks");
+            qq[b.q[0]].push_back(bi);
+            if (b.nq == 2) qq[b.q[1]].push_back(bi);
+        }
+        auto front = [&](int q) { return head[q] < qq[q].size() ? qq[q][head[q]] : -1; };
+        auto ready = [&](int bi) {
+            const Block& b = p.blocks[bi];
+            for (int s = 0; s < b.nq; ++s) if (front(b.q[s]) != bi) return false;
+            return true;
+        };
+        auto pop = [&](int bi) {
+            const Block& b = p.blocks[bi];
+            for (int s = 0; s < b.nq; ++s) ++head[b.q[s]];
+        };
+        size_t remaining = order.size();
+        while (remaining > 0) {
+            int b0 = -1;
+            for (int q = 0; q < n; ++q) { int f = front(q); if (f >= 0 && ready(f) && (b0 < 0 || f < b0)) b0 = f; }
+            if (b0 < 0) throw std::runtime_error("triple builder: no ready block");
+            // ---- choose the triple: the opening block's qubits, then partners along the pending two-qubit blocks ----
+            int nt = 0;
+            T[0] = T[1] = T[2] = -1;
+            T[nt++] = p.blocks[b0].q[0];
+            if (p.blocks[b0].nq == 2) T[nt++] = p.blocks[b0].q[1];
+            bool grew = true;
+            while (nt < 3 && grew) {
+                grew = false;
+                int best_q = -1, best_i = 1 << 30;
+                for (int s = 0; s < nt; ++s)
+                    for (size_t t = head[T[s]]; t < qq[T[s]].size(); ++t) {
+                        const Block& nb = p.blocks[qq[T[s]][t]];
+                        if (nb.nq != 2) continue;
+                        const int partner = nb.q[0] == T[s] ? nb.q[1] : nb.q[0];
+                        if (slot_of(partner) >= 0) continue;
+                        if (qq[T[s]][t] < best_i) { best_i = qq[T[s]][t]; best_q = partner; }
+                        break;
+                    }
+                if (best_q >= 0) { T[nt++] = best_q; grew = true; }
+            }
+            while (nt < 3) {     // spectators: resident qubits with the most urgent pending work, else any
+                int best_q = -1, best_i = 1 << 30;
+                for (int q : tile_q) {
+                    if (slot_of(q) >= 0) continue;
+                    const int f = front(q) >= 0 ? front(q) : (1 << 30) - 1;
+                    if (f < best_i) { best_i = f; best_q = q; }
+                }
+                if (best_q < 0) throw std::runtime_error("triple builder: tile has fewer than three qubits");
+                T[nt++] = best_q;
+            }
+            // ---- absorb ----
+            Mono lp, sp;
+            int stage = 0;     // 0: load permutation, 1: body, 2: store permutation
+            while (true) {
+                int bi = -1;
+                for (int s = 0; s < 3; ++s) {
+                    const int f = front(T[s]);
+                    if (f < 0 || !ready(f) || (bi >= 0 && f >= bi)) continue;
+                    const Block& b = p.blocks[f];
+                    bool inside = true;
+                    for (int t = 0; t < b.nq; ++t) inside = inside && slot_of(b.q[t]) >= 0;
+                    if (!inside) continue;
+                    Mono m;
+                    const bool mono = as_mono(b, m);
+                    if (stage == 2 && !mono) continue;          // only monomials ride on the store permutation
+                    bi = f;
+                }
+                if (bi < 0) break;
+                const Block& b = p.blocks[bi];
+                Mono m;
+                const bool mono = as_mono(b, m);
+                if (stage == 0) {
+                    if (mono) { lp.then(m); pop(bi); --remaining; continue; }
+                    stage = 1;
+                }
+                if (stage == 1) {
+                    if (b.nq == 1) { pend[slot_of(b.q[0])].push_back(bi); pop(bi); --remaining; continue; }
+                    if (mono && b.cls == CLS_MONO) { stage = 2; }
+                    else {
+                        int s0 = slot_of(b.q[0]), s1 = slot_of(b.q[1]);
+                        std::vector<double> M = b.M;
+                        if (s0 > s1) { M = swap_qubits(M); std::swap(s0, s1); }
+                        flush_slot(s0); flush_slot(s1);
+                        const int pair = s0 == 0 ? (s1 == 1 ? 0 : 1) : 2;
+                        const int cls = classify(M, 16);
+                        if (cls == CLS_DIAG || cls == CLS_IDENT) {
+                            std::vector<double> dg(16);
+                            for (int i = 0; i < 16; ++i) dg[i] = M[i * 16 + i];
+                            if (cls != CLS_IDENT) { mus.push_back(mu(MU3_DIAG2, cc.get(p, dg), pair)); flops += 1.0; }
+                        } else {
+                            mus.push_back(mu(MU3_MAT2, cc.get(p, M), pair));
+                            flops += 31.0;
+                        }
+                        pop(bi); --remaining;
+                        continue;
+                    }
+                }
+                // stage 2
+                sp.then(m); pop(bi); --remaining;
+            }
+            emit(lp, sp);
+        }
+        phase.n_sweeps = (int)p.sweeps3.size() - phase.first_sweep;
+        phase.n_chains = (int)p.chains.size() - phase.first_chain;
+        if (phase.n_sweeps > 0) p.phases.push_back(phase);
+    }
+};
+
 static void schedule_single_pass(Plan& p) {
     CoefCache cc;
     std::vector<int> local_pos(p.n);
@@ -910,19 +1192,45 @@ bool pass_stream_eligible(const Plan& p, const Pass& ps) {
     const int k = (int)ps.tile_q.size();
     if (k != 6 && k != 7) return false;
     int n_sweeps = 0, n_mus = 0, n_chains = 0;
+    std::map<int, int> tables;      // pass-local fixed coefficient tables: offset -> length
     for (int ph = 0; ph < ps.n_phases; ++ph) {
         const Phase& phase = p.phases[ps.first_phase + ph];
         n_chains += phase.n_chains;
         for (int si = 0; si < phase.n_sweeps; ++si) {
-            const SweepDev& sw = p.sweeps[phase.first_sweep + si];
             ++n_sweeps;
-            n_mus += sw.n_mu;
-            for (int mi = 0; mi < sw.n_mu; ++mi)
-                if (p.mus[sw.first_mu + mi].kind > MU_MAT2) return false;      // variant micro-ops
+            int first_mu, n_mu;
+            if (p.triples) {
+                const Sweep3& sw = p.sweeps3[phase.first_sweep + si];
+                first_mu = sw.first_mu; n_mu = sw.n_mu;
+                if (sw.load_perm) tables[sw.lcoef] = 64;
+                if (sw.store_perm) tables[sw.scoef] = 64;
+            } else {
+                const SweepDev& sw = p.sweeps[phase.first_sweep + si];
+                first_mu = sw.first_mu; n_mu = sw.n_mu;
+                if (sw.load_perm) tables[sw.lcoef] = 16;
+                if (sw.store_perm) tables[sw.scoef] = 16;
+            }
+            n_mus += n_mu;
+            for (int mi = 0; mi < n_mu; ++mi) {
+                const MicroOp& m = p.mus[first_mu + mi];
+                switch (m.kind) {
+                    case MU_CHAIN_A: case MU_CHAIN_B: break;
+                    case MU_FIX_A: case MU_FIX_B: case MU_DIAG2: tables[m.a0] = 16; break;
+                    case MU_DIAG_A: case MU_DIAG_B: tables[m.a0] = 4; break;
+                    case MU_MAT2: tables[m.a0] = 256; break;
+                    case MU3_MAT: if (!m.a2) tables[m.a0] = 16; break;
+                    case MU3_DIAG: tables[m.a0] = 4; break;
+                    case MU3_DIAG2: tables[m.a0] = 16; break;
+                    case MU3_MAT2: tables[m.a0] = 256; break;
+                    default: return false;      // variant micro-ops
+                }
+            }
         }
     }
     if (n_sweeps > STREAM_MAX_SWEEPS || n_mus > STREAM_MAX_MUS) return false;
-    return (size_t)n_chains * 128 + p.coefs.size() * 8 <= (k == 7 ? 90u : 20u) * 1024;
+    size_t coefs = 0;
+    for (const auto& t : tables) coefs += (size_t)((t.second + 1) & ~1);
+    return (size_t)n_chains * 128 + coefs * 8 <= (k == 7 ? 90u : 20u) * 1024;
 }
 
 // Remapping pass builder (see Pass::pos_in / pos_out).  Same DAG-greedy block selection as schedule_streaming, but no
@@ -1125,10 +1433,17 @@ static void schedule_streaming_remap(Plan& p) {
         for (size_t i = 0; i < tq.size(); ++i) local_pos[tq[i]] = 2 * ((int)tq.size() - 1 - (int)i);
         pass.first_phase = (int)p.phases.size();
         if (!orders[pi].empty()) {
-            SweepBuilder sb(p, cc, local_pos, pass.tile_q);
-            sb.run(orders[pi]);
-            flops += sb.flops;
-            sweeps += sb.sweeps_elems;
+            if (p.triples) {
+                TripleBuilder sb(p, cc, local_pos, pass.tile_q);
+                sb.run(orders[pi]);
+                flops += sb.flops;
+                sweeps += sb.sweeps_elems;
+            } else {
+                SweepBuilder sb(p, cc, local_pos, pass.tile_q);
+                sb.run(orders[pi]);
+                flops += sb.flops;
+                sweeps += sb.sweeps_elems;
+            }
         }
         pass.n_phases = (int)p.phases.size() - pass.first_phase;
         p.passes.push_back(std::move(pass));
@@ -1502,7 +1817,7 @@ void lower_plan(Plan& p) {
     if (p.n < 1 || p.n > DMX_MAX_QUBITS) throw std::runtime_error("n_qubits out of range");
     p.blocks.clear(); p.rots.clear(); p.mus.clear(); p.sweeps.clear(); p.factors.clear(); p.chains.clear(); p.phases.clear();
     p.coefs.clear(); p.passes.clear();
-    p.remapped = false;
+    p.remapped = false; p.triples = false; p.sweeps3.clear();
     p.cpb = plan_cpb(p.n);
     p.segs.clear(); p.slots.clear(); p.term_idx.clear(); p.term_coef.clear();
     std::memset(&p.info, 0, sizeof(p.info));
@@ -1529,11 +1844,15 @@ void lower_plan(Plan& p) {
     else {
         bool remapped = false;
         if (p.opt_remap && p.opt_tile_qubits >= 6) {
+            bool has_var = false;
+            for (const Block& b : p.blocks) has_var = has_var || b.kind == BK_VAR;
+            p.triples = p.opt_triples && !has_var;
             schedule_streaming_remap(p);
             remapped = true;
             for (const Pass& ps : p.passes) remapped = remapped && (ps.n_phases == 0 || pass_stream_eligible(p, ps));
             if (!remapped) {   // the generic tile kernel only knows the standard layout: re-plan with pinned low qubits
-                p.mus.clear(); p.sweeps.clear(); p.factors.clear(); p.chains.clear(); p.phases.clear(); p.coefs.clear(); p.passes.clear();
+                p.mus.clear(); p.sweeps.clear(); p.sweeps3.clear(); p.factors.clear(); p.chains.clear(); p.phases.clear(); p.coefs.clear(); p.passes.clear();
+                p.triples = false;
             }
         }
         if (!remapped) schedule_streaming(p);
@@ -1635,6 +1954,15 @@ std::string dump_plan(const Plan& p) {
            << " lperm=" << w.load_perm << " lcoef=" << w.lcoef << " sperm=" << w.store_perm << " scoef=" << w.scoef
            << " lmask=" << w.lmask[0] << "," << w.lmask[1] << "," << w.lmask[2] << "," << w.lmask[3]
            << " smask=" << w.smask[0] << "," << w.smask[1] << "," << w.smask[2] << "," << w.smask[3] << "\n";
+    }
+    for (size_t i = 0; i < p.sweeps3.size(); ++i) {
+        const Sweep3& w = p.sweeps3[i];
+        os << "sweep3 " << i << " p0=" << w.p[0] << " p1=" << w.p[1] << " p2=" << w.p[2] << " first_mu=" << w.first_mu << " nmu=" << w.n_mu
+           << " lperm=" << w.load_perm << " lcoef=" << w.lcoef << " sperm=" << w.store_perm << " scoef=" << w.scoef << " lmask=";
+        for (int j = 0; j < 6; ++j) os << (j ? "," : "") << w.lmask[j];
+        os << " smask=";
+        for (int j = 0; j < 6; ++j) os << (j ? "," : "") << w.smask[j];
+        os << "\n";
     }
     for (size_t i = 0; i < p.mus.size(); ++i)
         os << "mu " << i << " kind=" << p.mus[i].kind << " a0=" << p.mus[i].a0 << " a1=" << p.mus[i].a1 << " a2=" << p.mus[i].a2

@@ -83,6 +83,25 @@ struct SweepDev {     // 64 bytes
     uint32_t lmask[4], smask[4];
 };
 
+// Triple sweeps (streaming plans executed by dmx_stream3_kernel): a thread holds all 64 codes of THREE tile qubits
+// (slots A, B, C; register e = 16*code(A) + 4*code(B) + code(C), bits zC,xC,zB,xB,zA,xA), so a CNOT chain advances two
+// links per shared-memory round trip.  Leading / trailing monomial blocks (Clifford gate x Pauli noise, one- or
+// two-qubit) are composed into ONE load / store permutation (6 XOR masks + 64 scales).
+enum Mu3Kind : int32_t {
+    MU3_MAT = 16,    // 4x4 on slot a1: a2 = 1 -> per-circuit chain a0 (phase-relative), else fixed coefficients at a0; a3 = unital
+    MU3_DIAG = 17,   // 4 scales at a0 on slot a1
+    MU3_DIAG2 = 18,  // 16 scales at a0 on slot pair a1 (0: AB, 1: AC, 2: BC), index = 4*code(first) + code(second)
+    MU3_MAT2 = 19    // dense 16x16 at a0 on slot pair a1
+};
+
+struct Sweep3 {       // 88 bytes
+    int32_t p[3];             // tile-local bit positions of the codes of slots A, B, C
+    int32_t first_mu, n_mu;
+    int32_t load_perm, lcoef; // load:  v[e] = coef[lcoef + e] * tile[base ^ X_l(e)]   (64 scales; skipped when !load_perm)
+    int32_t store_perm, scoef;// store: tile[base ^ X_s(e)] = coef[scoef + e] * v[e]
+    uint32_t lmask[6], smask[6];
+};
+
 struct ChainFactor {  // one factor of a per-circuit 1-qubit matrix product (applied in order)
     int32_t kind;     // 0: fixed (16 coefficients), 1: rotation (48 coefficients A, C, S)
     int32_t coef;
@@ -147,7 +166,7 @@ struct Plan {
     std::vector<double> pool;
     std::vector<uint32_t> hx, hz;
     std::vector<double> hc;
-    int opt_fuse = 1, opt_segments = 1, opt_tile_qubits = 6, opt_remap = 1;
+    int opt_fuse = 1, opt_segments = 1, opt_tile_qubits = 6, opt_remap = 1, opt_triples = 1;
     bool finalized = false;
 
     // lowered program
@@ -155,6 +174,8 @@ struct Plan {
     std::vector<RotInfo> rots;
     std::vector<MicroOp> mus;
     std::vector<SweepDev> sweeps;
+    std::vector<Sweep3> sweeps3;    // used instead of `sweeps` when `triples` (Phase::first_sweep indexes this table)
+    bool triples = false;
     std::vector<ChainFactor> factors;
     std::vector<ChainDev> chains;
     std::vector<Phase> phases;

@@ -59,6 +59,36 @@ struct StreamArgs {
     uint32_t init_mask;                  // first pass: coefficient is 1 when (global index & init_mask) == 0
 };
 
+// ---- triple sweeps (dmx_stream3_kernel) -------------------------------------------------------------------
+struct SweepX3 {              // 128 bytes
+    int32_t p[3];             // tile bit positions of the three resident codes, ascending (for the group base)
+    int32_t first_mu, n_mu;
+    int32_t lscale, sscale;   // offsets into the pass coefficient area (64 scales) or -1
+    int32_t pad;
+    uint32_t lA[4], lB[4], lC[4];   // load : byte offset of register e = lA[e >> 4] ^ lB[(e >> 2) & 3] ^ lC[e & 3]
+    uint32_t sA[4], sB[4], sC[4];   // store: same
+};
+
+struct StreamArgs3 {
+    SweepX3 sweeps[STREAM_MAX_SWEEPS];
+    MuX mus[STREAM_MAX_MUS];      // MuX::pad carries the slot (0..2) or slot pair (0: AB, 1: AC, 2: BC)
+    const double* coefs;
+    const double* chainmats;
+    int n_sweeps, n_mus, n_coefs;
+    int total_chains, first_chain, n_chains;
+    int n, k;
+    int load, pad0;
+    const double* src;
+    double* dst;
+    int n_gruns_l, n_oruns_l, n_gruns_s, n_oruns_s;
+    int gruns_l[8][3], uruns_l[8][3], oruns_l[8][3];
+    int gruns_s[8][3], uruns_s[8][3], oruns_s[8][3];
+    uint32_t giter_l[32], giter_s[32];
+    uint32_t siter_l[32], siter_s[32];
+    uint32_t pbit_l, pbit_s;
+    uint32_t init_mask;
+};
+
 __host__ __device__ __forceinline__ unsigned parity32(unsigned v) {
 #ifdef __CUDA_ARCH__
     return __popc(v) & 1u;
@@ -330,6 +360,199 @@ __global__ void __launch_bounds__(THREADS, THREADS == 512 ? 1 : 4) dmx_stream_ke
     }
 
     // ---- tile store ----
+    {
+        const unsigned gbase = map_runs(2u * tid, a.gruns_s, a.n_gruns_s) | map_runs(tile_id, a.oruns_s, a.n_oruns_s);
+        const unsigned s_thr = swz_hd(map_runs(2u * tid, a.uruns_s, a.n_gruns_s));
+#pragma unroll
+        for (int j = 0; j < NITER; ++j) {
+            const unsigned sp = s_thr ^ a.siter_s[j];
+            *reinterpret_cast<double2*>(st + (gbase | a.giter_s[j])) = make_double2(tile[sp], tile[sp ^ a.pbit_s]);
+        }
+    }
+}
+
+// ---- triple-sweep kernel: 64 coefficients (three resident codes) per thread -----------------------------------
+// THREADS = 4^k / 64 (k = 6: 64 threads, four CTAs per SM; k = 7: 256 threads).  Register e = 16*code(A) + 4*code(B) + code(C).
+template <int S>   // stride of the acted-on code in e: 16 (slot A), 4 (slot B), 1 (slot C)
+__device__ __forceinline__ int spectator_offset(int t) {     // t = 0..15 enumerates the other two codes
+    return S == 16 ? t : (S == 4 ? ((t >> 2) * 16 + (t & 3)) : t * 4);
+}
+
+template <int S>
+__device__ __forceinline__ void apply3_64(double (&v)[64], const double* __restrict__ M) {
+    const double2* __restrict__ M2 = reinterpret_cast<const double2*>(M);
+    const double2 r1a = M2[2], r1b = M2[3], r2a = M2[4], r2b = M2[5], r3a = M2[6], r3b = M2[7];
+    const double m5 = r1a.y, m6 = r1b.x, m7 = r1b.y, m9 = r2a.y, m10 = r2b.x, m11 = r2b.y, m13 = r3a.y, m14 = r3b.x, m15 = r3b.y;
+#pragma unroll
+    for (int t = 0; t < 16; ++t) {
+        const int o = spectator_offset<S>(t);
+        const double x = v[o + S], y = v[o + 2 * S], z = v[o + 3 * S];
+        v[o + S] = m5 * x + m6 * y + m7 * z;
+        v[o + 2 * S] = m9 * x + m10 * y + m11 * z;
+        v[o + 3 * S] = m13 * x + m14 * y + m15 * z;
+    }
+}
+
+template <int S>
+__device__ __forceinline__ void apply4_64(double (&v)[64], const double* __restrict__ M) {
+#pragma unroll
+    for (int t = 0; t < 16; ++t) {
+        const int o = spectator_offset<S>(t);
+        const double w = v[o], x = v[o + S], y = v[o + 2 * S], z = v[o + 3 * S];
+        v[o] = M[0] * w + M[1] * x + M[2] * y + M[3] * z;
+        v[o + S] = M[4] * w + M[5] * x + M[6] * y + M[7] * z;
+        v[o + 2 * S] = M[8] * w + M[9] * x + M[10] * y + M[11] * z;
+        v[o + 3 * S] = M[12] * w + M[13] * x + M[14] * y + M[15] * z;
+    }
+}
+
+template <int S>
+__device__ __forceinline__ void diag1_64(double (&v)[64], const double* __restrict__ d) {
+    const double d0 = d[0], d1 = d[1], d2 = d[2], d3 = d[3];
+#pragma unroll
+    for (int t = 0; t < 16; ++t) {
+        const int o = spectator_offset<S>(t);
+        v[o] *= d0; v[o + S] *= d1; v[o + 2 * S] *= d2; v[o + 3 * S] *= d3;
+    }
+}
+
+// pair 0: (A,B), 1: (A,C), 2: (B,C); local index = 4 * code(first) + code(second)
+template <int PAIR>
+__device__ __forceinline__ int pair_index(int e) { return PAIR == 0 ? (e >> 2) : (PAIR == 1 ? ((e >> 4) * 4 + (e & 3)) : (e & 15)); }
+template <int PAIR>
+__device__ __forceinline__ int pair_element(int l, int spect) {   // inverse of pair_index for spectator code `spect`
+    return PAIR == 0 ? (l * 4 + spect) : (PAIR == 1 ? ((l >> 2) * 16 + spect * 4 + (l & 3)) : (spect * 16 + l));
+}
+
+template <int PAIR>
+__device__ __forceinline__ void diag2_64(double (&v)[64], const double* __restrict__ d) {
+    const double2* __restrict__ d2 = reinterpret_cast<const double2*>(d);
+    double c[16];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { const double2 t = d2[i]; c[2 * i] = t.x; c[2 * i + 1] = t.y; }
+#pragma unroll
+    for (int e = 0; e < 64; ++e) v[e] *= c[pair_index<PAIR>(e)];
+}
+
+template <int PAIR>
+__device__ __forceinline__ void dense2_64(double (&v)[64], const double* __restrict__ M) {
+#pragma unroll
+    for (int sp = 0; sp < 4; ++sp) {
+        double nv[16];
+#pragma unroll
+        for (int r = 0; r < 16; ++r) {
+            double acc = 0.0;
+#pragma unroll
+            for (int c = 0; c < 16; ++c) acc += M[r * 16 + c] * v[pair_element<PAIR>(c, sp)];
+            nv[r] = acc;
+        }
+#pragma unroll
+        for (int r = 0; r < 16; ++r) v[pair_element<PAIR>(r, sp)] = nv[r];
+    }
+}
+
+template <int THREADS, bool GENERAL>
+__global__ void __launch_bounds__(THREADS, THREADS == 256 ? 1 : 4) dmx_stream3_kernel(const __grid_constant__ StreamArgs3 a) {
+    constexpr int NITER = 32;                               // 4^k / (2 * THREADS)
+    const unsigned E = 64u * THREADS;
+    double* tile = dmx_stream_smem;
+    double* cf = tile + E;                                  // [n_chains*16 chain matrices | n_coefs fixed coefficients]
+    char* const tb = reinterpret_cast<char*>(tile);
+    const int tid = threadIdx.x;
+
+    const unsigned tiles_per_circuit = 1u << (2 * (a.n - a.k));
+    const long long circuit = blockIdx.x / tiles_per_circuit;
+    const unsigned tile_id = blockIdx.x % tiles_per_circuit;
+    const double* const st_in = a.src + (circuit << (2 * a.n));
+    double* const st = a.dst + (circuit << (2 * a.n));
+
+    {
+        const double* cm = a.chainmats + ((size_t)circuit * a.total_chains + a.first_chain) * 16;
+        for (int i = tid; i < a.n_chains * 16; i += THREADS) cf[i] = cm[i];
+        for (int i = tid; i < a.n_coefs; i += THREADS) cf[a.n_chains * 16 + i] = a.coefs[i];
+    }
+
+    if (a.load) {
+        const unsigned gbase = map_runs(2u * tid, a.gruns_l, a.n_gruns_l) | map_runs(tile_id, a.oruns_l, a.n_oruns_l);
+        const unsigned s_thr = swz_hd(map_runs(2u * tid, a.uruns_l, a.n_gruns_l));
+        double2 x[NITER];
+#pragma unroll
+        for (int j = 0; j < NITER; ++j) x[j] = *reinterpret_cast<const double2*>(st_in + (gbase | a.giter_l[j]));
+#pragma unroll
+        for (int j = 0; j < NITER; ++j) {
+            const unsigned sp = s_thr ^ a.siter_l[j];
+            tile[sp] = x[j].x;
+            tile[sp ^ a.pbit_l] = x[j].y;
+        }
+    } else {
+        const unsigned gbase = map_runs(2u * tid, a.gruns_s, a.n_gruns_s) | map_runs(tile_id, a.oruns_s, a.n_oruns_s);
+        const unsigned s_thr = swz_hd(map_runs(2u * tid, a.uruns_s, a.n_gruns_s));
+#pragma unroll
+        for (int j = 0; j < NITER; ++j) {
+            const unsigned g = gbase | a.giter_s[j];
+            const unsigned sp = s_thr ^ a.siter_s[j];
+            tile[sp] = (g & a.init_mask) ? 0.0 : 1.0;
+            tile[sp ^ a.pbit_s] = ((g | 1u) & a.init_mask) ? 0.0 : 1.0;
+        }
+    }
+    __syncthreads();
+
+    for (int si = 0; si < a.n_sweeps; ++si) {
+        const SweepX3& sw = a.sweeps[si];
+        const unsigned sb = swz_hd(insert2_hd(insert2_hd(insert2_hd((unsigned)tid, sw.p[0]), sw.p[1]), sw.p[2])) << 3;
+        double v[64];
+        {
+#pragma unroll
+            for (int e = 0; e < 64; ++e) {
+                const unsigned off = sw.lA[e >> 4] ^ sw.lB[(e >> 2) & 3] ^ sw.lC[e & 3];
+                v[e] = *reinterpret_cast<const double*>(tb + (sb ^ off));
+            }
+            if (sw.lscale >= 0) {
+                const double2* __restrict__ lc = reinterpret_cast<const double2*>(cf + sw.lscale);
+#pragma unroll
+                for (int e = 0; e < 32; ++e) { const double2 s = lc[e]; v[2 * e] *= s.x; v[2 * e + 1] *= s.y; }
+            }
+        }
+        for (int mi = 0; mi < sw.n_mu; ++mi) {
+            const MuX m = a.mus[sw.first_mu + mi];
+            const double* __restrict__ M = cf + m.off;
+            const int which = m.pad;
+            switch (m.kind) {
+                case MU3_MAT:
+                    if (!GENERAL || m.unital) {
+                        if (which == 0) apply3_64<16>(v, M); else if (which == 1) apply3_64<4>(v, M); else apply3_64<1>(v, M);
+                    } else {
+                        if (which == 0) apply4_64<16>(v, M); else if (which == 1) apply4_64<4>(v, M); else apply4_64<1>(v, M);
+                    }
+                    break;
+                case MU3_DIAG:
+                    if (which == 0) diag1_64<16>(v, M); else if (which == 1) diag1_64<4>(v, M); else diag1_64<1>(v, M);
+                    break;
+                case MU3_DIAG2:
+                    if (which == 0) diag2_64<0>(v, M); else if (which == 1) diag2_64<1>(v, M); else diag2_64<2>(v, M);
+                    break;
+                default:   // MU3_MAT2
+                    if (GENERAL) {
+                        if (which == 0) dense2_64<0>(v, M); else if (which == 1) dense2_64<1>(v, M); else dense2_64<2>(v, M);
+                    }
+                    break;
+            }
+        }
+        {
+            if (sw.sscale >= 0) {
+                const double2* __restrict__ sc = reinterpret_cast<const double2*>(cf + sw.sscale);
+#pragma unroll
+                for (int e = 0; e < 32; ++e) { const double2 s = sc[e]; v[2 * e] *= s.x; v[2 * e + 1] *= s.y; }
+            }
+#pragma unroll
+            for (int e = 0; e < 64; ++e) {
+                const unsigned off = sw.sA[e >> 4] ^ sw.sB[(e >> 2) & 3] ^ sw.sC[e & 3];
+                *reinterpret_cast<double*>(tb + (sb ^ off)) = v[e];
+            }
+        }
+        __syncthreads();
+    }
+
     {
         const unsigned gbase = map_runs(2u * tid, a.gruns_s, a.n_gruns_s) | map_runs(tile_id, a.oruns_s, a.n_oruns_s);
         const unsigned s_thr = swz_hd(map_runs(2u * tid, a.uruns_s, a.n_gruns_s));
