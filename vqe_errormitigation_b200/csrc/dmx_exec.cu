@@ -805,6 +805,7 @@ struct DevPlan {
         bool ok = false;
         std::vector<SweepX> sweeps;  // travel in the kernel parameters
         std::vector<SweepX3> sweeps3; // triple-sweep plans
+        std::vector<double> cfix;     // triple-sweep plans: permutation scale tables for the kernel parameters
         std::vector<MuX> mus;
         bool general = false;        // needs the 4x4 / dense micro-ops
         double* coefs = nullptr;     // device: pass-local fixed coefficients
@@ -856,6 +857,21 @@ static cudaError_t build_stream_tables(const Plan& p, DevPlan* d) {
         };
         bool ok = true;
         std::vector<SweepX3> sx3;
+        std::vector<double> cfix;
+        std::map<int, int> cfix_where;
+        auto scale_table = [&](int off) {      // 64 scales: constant bank while it has room, else shared memory
+            auto it = cfix_where.find(off);
+            if (it != cfix_where.end()) return it->second;
+            int at;
+            if (cfix.size() + 64 <= (size_t)STREAM3_CFIX) {
+                at = (int)cfix.size();
+                cfix.insert(cfix.end(), p.coefs.begin() + off, p.coefs.begin() + off + 64);
+            } else {
+                at = -(px.n_chains * 16 + local(off, 64)) - 2;
+            }
+            cfix_where.emplace(off, at);
+            return at;
+        };
         for (int ph = 0; ph < ps.n_phases && ok && p.triples; ++ph) {
             const Phase& phase = p.phases[ps.first_phase + ph];
             for (int si = 0; si < phase.n_sweeps && ok; ++si) {
@@ -865,8 +881,8 @@ static cudaError_t build_stream_tables(const Plan& p, DevPlan* d) {
                 std::sort(sorted, sorted + 3);
                 for (int j = 0; j < 3; ++j) x.p[j] = sorted[j];
                 x.first_mu = (int)mx.size(); x.n_mu = sw.n_mu;
-                x.lscale = sw.load_perm ? px.n_chains * 16 + local(sw.lcoef, 64) : -1;
-                x.sscale = sw.store_perm ? px.n_chains * 16 + local(sw.scoef, 64) : -1;
+                x.lscale = sw.load_perm ? scale_table(sw.lcoef) : -1;
+                x.sscale = sw.store_perm ? scale_table(sw.scoef) : -1;
                 auto S = [](uint32_t m) { return swz_hd(m) << 3; };
                 for (int c = 0; c < 4; ++c) {       // register bits (zC, xC, zB, xB, zA, xA) = masks 0..5
                     x.lC[c] = ((c & 1) ? S(sw.lmask[0]) : 0u) ^ ((c & 2) ? S(sw.lmask[1]) : 0u);
@@ -934,7 +950,7 @@ static cudaError_t build_stream_tables(const Plan& p, DevPlan* d) {
         px.n_sweeps = (int)(sx.size() + sx3.size()); px.n_mus = (int)mx.size(); px.n_coefs = (int)lc.size();
         px.smem = ((size_t)32 * threads + (size_t)px.n_chains * 16 + lc.size() + 2) * 8;
         if (px.smem > (k == 7 ? 227u : 56u) * 1024) continue;       // k = 6: keep four CTAs per SM
-        px.sweeps = sx; px.sweeps3 = sx3; px.mus = mx;
+        px.sweeps = sx; px.sweeps3 = sx3; px.mus = mx; px.cfix = cfix;
         if (lc.empty()) lc.push_back(0.0);
         cudaError_t e = upload(&px.coefs, lc);
         if (e != cudaSuccess) return e;
@@ -1234,6 +1250,7 @@ static int run_streaming(Plan& p, DevPlan* d, long long chunk, long long circuit
                 static thread_local StreamArgs3 a3;      // ~19 KB of kernel parameters: keep it off the stack
                 a3 = StreamArgs3{};
                 std::copy(px.sweeps3.begin(), px.sweeps3.end(), a3.sweeps);
+                std::copy(px.cfix.begin(), px.cfix.end(), a3.cfix);
                 fill(a3, k == 7 ? 256u : 64u, 32u);
                 if (k == 7) rc = px.general ? launch_stream3<256, true>(a3, groups, px.smem, st) : launch_stream3<256, false>(a3, groups, px.smem, st);
                 else rc = px.general ? launch_stream3<64, true>(a3, groups, px.smem, st) : launch_stream3<64, false>(a3, groups, px.smem, st);

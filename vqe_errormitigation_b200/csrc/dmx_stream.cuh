@@ -63,15 +63,20 @@ struct StreamArgs {
 struct SweepX3 {              // 128 bytes
     int32_t p[3];             // tile bit positions of the three resident codes, ascending (for the group base)
     int32_t first_mu, n_mu;
-    int32_t lscale, sscale;   // offsets into the pass coefficient area (64 scales) or -1
+    int32_t lscale, sscale;   // 64 scales: >= 0 offset into StreamArgs3::cfix (constant bank), <= -2 offset -(v+2) into the
+                              // shared-memory coefficient area, -1 none
     int32_t pad;
     uint32_t lA[4], lB[4], lC[4];   // load : byte offset of register e = lA[e >> 4] ^ lB[(e >> 2) & 3] ^ lC[e & 3]
     uint32_t sA[4], sB[4], sC[4];   // store: same
 };
 
+constexpr int STREAM3_CFIX = 1536;   // doubles of permutation scale tables carried in the kernel parameters
+
 struct StreamArgs3 {
     SweepX3 sweeps[STREAM_MAX_SWEEPS];
     MuX mus[STREAM_MAX_MUS];      // MuX::pad carries the slot (0..2) or slot pair (0: AB, 1: AC, 2: BC)
+    double cfix[STREAM3_CFIX];    // scale tables of the load / store permutations: read through the constant cache, so they
+                                  // do not compete with the tile exchange for the shared-memory pipe
     const double* coefs;
     const double* chainmats;
     int n_sweeps, n_mus, n_coefs;
@@ -502,13 +507,19 @@ __global__ void __launch_bounds__(THREADS, THREADS == 256 ? 1 : 4) dmx_stream3_k
         const unsigned sb = swz_hd(insert2_hd(insert2_hd(insert2_hd((unsigned)tid, sw.p[0]), sw.p[1]), sw.p[2])) << 3;
         double v[64];
         {
+            // address of register e = (sb ^ lC[c]) ^ (lA[a] ^ lB[b]): 4 per-thread bases x 16 uniform offsets, one XOR per access
+            unsigned ab[16], sc[4];
 #pragma unroll
-            for (int e = 0; e < 64; ++e) {
-                const unsigned off = sw.lA[e >> 4] ^ sw.lB[(e >> 2) & 3] ^ sw.lC[e & 3];
-                v[e] = *reinterpret_cast<const double*>(tb + (sb ^ off));
-            }
+            for (int i = 0; i < 16; ++i) ab[i] = sw.lA[i >> 2] ^ sw.lB[i & 3];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) sc[c] = sb ^ sw.lC[c];
+#pragma unroll
+            for (int e = 0; e < 64; ++e) v[e] = *reinterpret_cast<const double*>(tb + (sc[e & 3] ^ ab[e >> 2]));
             if (sw.lscale >= 0) {
-                const double2* __restrict__ lc = reinterpret_cast<const double2*>(cf + sw.lscale);
+#pragma unroll
+                for (int e = 0; e < 64; ++e) v[e] *= a.cfix[sw.lscale + e];
+            } else if (sw.lscale <= -2) {
+                const double2* __restrict__ lc = reinterpret_cast<const double2*>(cf - (sw.lscale + 2));
 #pragma unroll
                 for (int e = 0; e < 32; ++e) { const double2 s = lc[e]; v[2 * e] *= s.x; v[2 * e + 1] *= s.y; }
             }
@@ -540,15 +551,20 @@ __global__ void __launch_bounds__(THREADS, THREADS == 256 ? 1 : 4) dmx_stream3_k
         }
         {
             if (sw.sscale >= 0) {
-                const double2* __restrict__ sc = reinterpret_cast<const double2*>(cf + sw.sscale);
 #pragma unroll
-                for (int e = 0; e < 32; ++e) { const double2 s = sc[e]; v[2 * e] *= s.x; v[2 * e + 1] *= s.y; }
-            }
+                for (int e = 0; e < 64; ++e) v[e] *= a.cfix[sw.sscale + e];
+            } else if (sw.sscale <= -2) {
+                const double2* __restrict__ sc2 = reinterpret_cast<const double2*>(cf - (sw.sscale + 2));
 #pragma unroll
-            for (int e = 0; e < 64; ++e) {
-                const unsigned off = sw.sA[e >> 4] ^ sw.sB[(e >> 2) & 3] ^ sw.sC[e & 3];
-                *reinterpret_cast<double*>(tb + (sb ^ off)) = v[e];
+                for (int e = 0; e < 32; ++e) { const double2 s = sc2[e]; v[2 * e] *= s.x; v[2 * e + 1] *= s.y; }
             }
+            unsigned ab[16], sc[4];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) ab[i] = sw.sA[i >> 2] ^ sw.sB[i & 3];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) sc[c] = sb ^ sw.sC[c];
+#pragma unroll
+            for (int e = 0; e < 64; ++e) *reinterpret_cast<double*>(tb + (sc[e & 3] ^ ab[e >> 2])) = v[e];
         }
         __syncthreads();
     }
