@@ -1019,6 +1019,16 @@ static int ensure_device(Plan& p, DevPlan** out) {
         CUDA_TRY(upload(&d->labels, lab));
     }
     CUDA_TRY(build_stream_tables(p, d));
+    {
+        // stream-ordered scratch (chain matrices, sampler tables) comes from the device's default pool: keep freed blocks
+        // cached instead of returning them to the driver at every synchronisation
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+            unsigned long long keep = ~0ull;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        }
+        (void)cudaGetLastError();
+    }
     p.dev = d;
     *out = d;
     return DMX_OK;
@@ -1175,15 +1185,15 @@ static unsigned map_runs_host(unsigned v, const BitRun* runs, int n) {
 // Remapped plans ping-pong between `state` and `state2` (a tile's load and store address sets differ, so a pass cannot
 // run in place); the last pass always lands in `state`.
 static int run_streaming(Plan& p, DevPlan* d, long long chunk, long long circuit_offset, const double* params, const uint8_t* variants,
-                         double* state, double* state2, cudaStream_t st) {
+                         double* state, double* state2, cudaStream_t st, double* chain_scratch = nullptr) {
     if (p.remapped && !state2) return fail(DMX_ERR_INVALID, "remapped plan needs a second state buffer");
     const int total_chains = (int)p.chains.size();
     bool any_x = false;
     for (const auto& px : d->passx) any_x |= px.ok && g_stream_kernel;
-    double* chainmats = nullptr;
+    double* chainmats = chain_scratch;
     if (any_x && total_chains > 0) {
         // per-circuit chain matrices of every pass, computed once (stream-ordered scratch: plans may run on several streams)
-        CUDA_TRY(cudaMallocAsync((void**)&chainmats, (size_t)chunk * total_chains * 128, st));
+        if (!chainmats) CUDA_TRY(cudaMallocAsync((void**)&chainmats, (size_t)chunk * total_chains * 128, st));
         const long long items = chunk * total_chains;
         dmx_chain_kernel<<<(unsigned)((items + 127) / 128), 128, 0, st>>>(d->chains, d->factors, d->coefs, d->rots, params, p.n_params,
                                                                           total_chains, chunk, circuit_offset, chainmats);
@@ -1281,7 +1291,7 @@ static int run_streaming(Plan& p, DevPlan* d, long long chunk, long long circuit
         if (smem > 227 * 1024) { rc = fail(DMX_ERR_UNSUPPORTED, "tile does not fit shared memory"); break; }
         rc = launch_tile(a, (int)groups, threads, gpt, smem, st);
     }
-    if (chainmats) {
+    if (chainmats && !chain_scratch) {
         cudaError_t e = cudaFreeAsync(chainmats, st);
         if (rc == DMX_OK && e != cudaSuccess) rc = fail(DMX_ERR_CUDA, std::string("cudaFreeAsync: ") + cudaGetErrorString(e));
     }
@@ -1479,9 +1489,12 @@ static int energy_impl(dmx_plan* plan, int64_t batch, const double* d_params, co
     double* const state2 = p.remapped ? (double*)((char*)d_workspace + (size_t)cap * sb) : nullptr;
     // circuits per pass launch: large enough to fill the GPU for several waves ("stream_chunk" overrides)
     long long chunk = std::min<long long>(cap, g_stream_chunk > 0 ? g_stream_chunk : 64);
+    double* chain_scratch = nullptr;
+    if (!p.chains.empty()) CUDA_TRY(cudaMallocAsync((void**)&chain_scratch, (size_t)chunk * p.chains.size() * 128, st));
+    struct Release { double* ptr; cudaStream_t st; ~Release() { if (ptr) cudaFreeAsync(ptr, st); } } release{chain_scratch, st};
     for (long long off = 0; off < batch; off += chunk) {
         long long cur = std::min<long long>(chunk, batch - off);
-        rc = run_streaming(p, d, cur, off, d_params, d_variants, (double*)d_workspace, state2, st);
+        rc = run_streaming(p, d, cur, off, d_params, d_variants, (double*)d_workspace, state2, st, chain_scratch);
         if (rc) return rc;
         int threads = 128;
         long long warps = cur;
