@@ -530,7 +530,8 @@ def main():
     # ---- roofline of the dominant kernel -----------------------------------------------------------------------------
     ms_per_step = dev_ms_max / args.steps
     kernel_s = ms_per_step * 1e-3
-    path = {0: "dmx_tile_kernel", 1: "dmx_frame_kernel", 2: "dmx_stream_kernel (streaming passes)"}[info["path"]]
+    path = {0: "dmx_tile_kernel", 1: "dmx_frame32_kernel (dmx_frame_kernel when more than 32 coefficients are live)",
+            2: "dmx_stream3_kernel (streaming passes)"}[info["path"]]
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
     if os.path.exists(tpath):

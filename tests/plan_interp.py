@@ -81,6 +81,10 @@ def parse(dump: str) -> dict:
             plan["single_class"] = int(kv["single_class"])
             plan["f_init"] = _nums(kv["init"])
             plan["f_eweight"] = _nums(kv["eweight"])
+        elif head == "f32":
+            plan["f32"] = {"n": int(kv["n"]), "orig": _nums(kv["orig"], int), "init": _nums(kv["init"]), "eweight": _nums(kv["eweight"]), "segs": []}
+        elif head == "f32seg":
+            plan["f32"]["segs"].append({"partner": _nums(kv["partner"], int), "w": _nums(kv["w"]).reshape(32, 2)})
         elif head == "fclass":
             plan["fclasses"].append({"param": int(kv["param"]), "scale": float(kv["scale"]), "offset": float(kv["offset"])})
         elif head == "flabel":
@@ -363,6 +367,53 @@ def run_segments(plan, params=None, variants=None):
         else:
             r = a
     return float(np.dot(plan["e_w"], r[plan["e_src"]]))
+
+
+def run_frame32(plan, params=None, variants=None):
+    """Interpret the liveness-compacted frame tables as dmx_frame32_kernel does (array index = lane)."""
+    f32 = plan.get("f32")
+    if f32 is None:
+        return None
+    cf = plan["coefs"]
+    orig = np.asarray(f32["orig"])
+    r = f32["init"].copy()
+    act = []
+    if variants is not None:
+        for s, v in enumerate(variants):
+            v = int(v)
+            if v == 0 or s not in plan["slots"] or plan["slots"][s]["seg"] < 0:
+                continue
+            sl = plan["slots"][s]
+            if not (int(sl["diag_ok"][v >> 5]) >> (v & 31)) & 1:
+                return None
+            act.append((s, v))
+    nseg = plan["nseg"]
+    for k in range(nseg + 1):
+        for s, v in act:
+            sl = plan["slots"][s]
+            if sl["seg"] != k:
+                continue
+            lab = np.where(orig >= 0, plan["flabels"][s][np.maximum(orig, 0)], 0)
+            tb = sl["tab"]
+            if sl["nq"] == 1:
+                f = cf[tb + v * 4 + lab]
+            else:
+                f = cf[tb + (v >> 4) * 4 + (lab >> 2)] * cf[tb + (v & 15) * 4 + (lab & 3)] * cf[tb + 64 + lab]
+            r = r * f
+        if k == nseg:
+            break
+        fs, seg = plan["fsegs"][k], f32["segs"][k]
+        other = r[np.asarray(seg["partner"]) & 31]
+        if fs["cs"] >= 0:
+            cl = plan["fclasses"][fs["cs"]]
+            th = cl["scale"] * params[cl["param"]] + cl["offset"]
+            cm, sm = np.cos(th), np.sin(th)
+        else:
+            cm = sm = 1.0
+        w0, w1 = seg["w"][:, 0], seg["w"][:, 1]
+        cme = np.where((np.asarray(seg["partner"]) & 0x80) != 0, cm, 1.0)     # bit 7: the rotation moves this coefficient
+        r = cme * (w0 * r) + sm * (w1 * other)
+    return float(np.dot(f32["eweight"], r))
 
 
 def run_frame(plan, params=None, variants=None):

@@ -47,6 +47,10 @@ def test_h2_lowering(noise, options):
         if plan["nseg"]:
             assert abs(PI.run_segments(plan, [a]) - want) < TOL
             assert abs(PI.run_frame(plan, [a]) - want) < TOL
+            if noise != "ampdamp":
+                assert plan["f32"]["n"] <= 24              # noisy / clean H2: at most 24 of 256 coefficients matter
+            if "f32" in plan:
+                assert abs(PI.run_frame32(plan, [a]) - want) < TOL
 
 
 def test_frame_relabelling_keeps_h2_exchanges_inside_warps():
@@ -62,6 +66,7 @@ def test_frame_mixed_axes_random_clifford_rotation_circuits():
     several rotation classes) reproduce the oracle."""
     rng = np.random.default_rng(77)
     cliff1 = [O.H, O.rx(np.pi / 2), O.rx(-np.pi / 2), O.rx(np.pi), O.rz(np.pi / 2), O.X, O.Z]
+    n_compact = 0
     for trial in range(6):
         n = int(rng.integers(2, 5))
         ops = []
@@ -86,6 +91,10 @@ def test_frame_mixed_axes_random_clifford_rotation_circuits():
         vals = rng.normal(size=max(prog.n_params, 1))
         want = O.energy_sparse(O.simulate(n, resolve(ops, prog.param_names, vals)), O.pauli_terms_to_matrix(n, *terms))
         assert abs(PI.run_frame(plan, vals) - want) < TOL
+        if "f32" in plan:
+            n_compact += 1
+            assert abs(PI.run_frame32(plan, vals) - want) < TOL
+    assert n_compact >= 1
 
 
 def test_canonical_cost_model_matches_survey():
@@ -130,6 +139,7 @@ def test_variant_lowering_against_golden():
         else:
             assert abs(seg - case["energy"]) < TOL
             assert abs(frame - case["energy"]) < TOL
+            assert abs(PI.run_frame32(plan, None, v) - case["energy"]) < TOL
     assert general >= 1
 
 

@@ -583,6 +583,156 @@ __global__ void __launch_bounds__(256) dmx_frame_kernel(const FrameArgs a) {
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// compact frame kernel ("frame32"): liveness analysis on the host (dmx_lower.cpp::build_frame32) shows that only a few of
+// the 256 Pauli coefficients can both be reached from |0..0> and reach a Hamiltonian term (noisy H2 UCCSD: 23).  When at
+// most 32 can, one WARP carries CPB circuits: lane l owns coefficient orig[l], the partner of a segment comes from
+// __shfl_sync(r, partner[k][l]), the energy is a warp butterfly.  No shared-memory exchange, no block barrier; warps of a
+// CTA run independent circuit groups.
+// ---------------------------------------------------------------------------------------------------------
+struct Frame32Args {
+    int nseg, n_params, n_slots, n_classes;
+    long long batch;
+    const double2* w;             // [nseg][32] (w0, w1)
+    const unsigned char* partner; // [nseg][32] partner lane | 0x80 (rotation moves this coefficient)
+    const int* cs_sel;            // [nseg] rotation class or < 0 (constant coefficients)
+    const RotInfo* classes;
+    const double* init;           // [32]
+    const double* eweight;        // [32]
+    const int* orig;              // [32] frame index (labels are indexed by it), -1 idle
+    const double* params;
+    const uint8_t* variants;
+    const SlotDev* slots;
+    const uint8_t* labels;        // [n_slots][256]
+    const double* coefs;
+    double* out;
+    int* worklist;
+    int* work_count;
+};
+
+template <int CPB, int CSMODE>
+__global__ void __launch_bounds__(256) dmx_frame32_kernel(const Frame32Args a) {
+    const int NC = a.n_classes > 0 ? a.n_classes : 1;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // per-warp shared memory: (cos, sin) table for CSMODE 2, active variant entries
+    double2* cs = reinterpret_cast<double2*>(dmx_smem) + (size_t)warp * CPB * NC;
+    unsigned* act = reinterpret_cast<unsigned*>(reinterpret_cast<double2*>(dmx_smem) + (size_t)8 * CPB * NC) + (size_t)warp * CPB * (SEG_MAXACT + 1);
+    int* nact = reinterpret_cast<int*>(act + CPB * SEG_MAXACT);
+    const long long ngroups = (a.batch + CPB - 1) / CPB;
+    const long long gwarp = (long long)blockIdx.x * 8 + warp, nwarps = (long long)gridDim.x * 8;
+    const double init = a.init[lane];
+    const double ew = a.eweight[lane];
+    const int p = a.orig[lane] < 0 ? 0 : a.orig[lane];
+
+    for (long long grp = gwarp; grp < ngroups; grp += nwarps) {
+        const long long b0 = grp * CPB;
+        double2 csr[CPB];
+        if (CSMODE == 1) {
+            double sv = 0.0, cv = 1.0;
+            if (lane < CPB && b0 + lane < a.batch) {
+                const RotInfo ri = a.classes[0];
+                sincos(ri.scale * a.params[(b0 + lane) * a.n_params + ri.param] + ri.offset, &sv, &cv);
+            }
+#pragma unroll
+            for (int c = 0; c < CPB; ++c) csr[c] = make_double2(__shfl_sync(0xffffffffu, cv, c), __shfl_sync(0xffffffffu, sv, c));
+        } else {
+#pragma unroll
+            for (int c = 0; c < CPB; ++c) csr[c] = make_double2(1.0, 1.0);
+            if (CSMODE == 2) {
+                __syncwarp();
+                for (int i = lane; i < CPB * NC; i += 32) {
+                    const int c = i / NC, cl = i - c * NC;
+                    double sv = 0.0, cv = 1.0;
+                    if (b0 + c < a.batch) {
+                        const RotInfo ri = a.classes[cl];
+                        sincos(ri.scale * a.params[(b0 + c) * a.n_params + ri.param] + ri.offset, &sv, &cv);
+                    }
+                    cs[i] = make_double2(cv, sv);
+                }
+                __syncwarp();
+            }
+        }
+        bool have_act = false;
+        if (a.variants) {
+            __syncwarp();
+            for (int c = 0; c < CPB; ++c) {
+                int count = 0;
+                bool general = false;
+                if (b0 + c < a.batch) {
+                    const uint8_t* row = a.variants + (b0 + c) * a.n_slots;
+                    for (int s0 = 0; s0 < a.n_slots; s0 += 32) {
+                        const int s = s0 + lane;
+                        unsigned idx = s < a.n_slots ? row[s] : 0u;
+                        if (idx && a.slots[s].seg < 0) idx = 0;
+                        const bool nz = idx != 0;
+                        if (nz && !((a.slots[s].diag_ok[idx >> 5] >> (idx & 31)) & 1u)) general = true;
+                        const unsigned m = __ballot_sync(0xffffffffu, nz);
+                        const int pos = count + __popc(m & ((1u << lane) - 1u));
+                        if (nz && pos < SEG_MAXACT) act[c * SEG_MAXACT + pos] = ((unsigned)s << 8) | idx;
+                        count += __popc(m);
+                    }
+                    general = __any_sync(0xffffffffu, general) || count > SEG_MAXACT;
+                }
+                if (lane == 0) {
+                    nact[c] = general ? -1 : count;
+                    if (general) a.worklist[atomicAdd(a.work_count, 1)] = (int)(b0 + c);
+                }
+                have_act = have_act || general || count > 0;
+            }
+            __syncwarp();
+        }
+
+        double r[CPB];
+#pragma unroll
+        for (int c = 0; c < CPB; ++c) r[c] = init;
+
+        for (int k = 0; k <= a.nseg; ++k) {
+            if (have_act) {
+#pragma unroll
+                for (int c = 0; c < CPB; ++c) {
+                    const int na = nact[c];
+                    for (int e = 0; e < na; ++e) {
+                        const unsigned ent = act[c * SEG_MAXACT + e];
+                        const int s = ent >> 8;
+                        const unsigned idx = ent & 255u;
+                        const SlotDev sd = a.slots[s];
+                        if (sd.seg != k) continue;
+                        const unsigned lab = a.labels[s * 256 + p];
+                        const double* t = a.coefs + sd.tab_off;
+                        const double f = sd.nq == 1 ? t[idx * 4 + lab]
+                                                    : t[(idx >> 4) * 4 + (lab >> 2)] * t[(idx & 15u) * 4 + (lab & 3u)] * t[64 + lab];
+                        r[c] *= f;
+                    }
+                }
+            }
+            if (k == a.nseg) break;
+            const int sel = a.cs_sel[k];
+            const double2 wk = a.w[k * 32 + lane];
+            const unsigned pb = a.partner[k * 32 + lane];
+            const bool active = pb & 0x80u;
+            const int src = pb & 31u;
+#pragma unroll
+            for (int c = 0; c < CPB; ++c) {
+                const double other = __shfl_sync(0xffffffffu, r[c], src);
+                double2 v;
+                if (sel < 0) v = make_double2(1.0, 1.0);
+                else if (CSMODE == 1) v = csr[c];
+                else v = cs[c * NC + sel];
+                const double cm = active ? v.x : 1.0;
+                r[c] = cm * (wk.x * r[c]) + v.y * (wk.y * other);
+            }
+        }
+        // energy: fixed butterfly over the 32 lanes (deterministic), lane c writes circuit c
+#pragma unroll
+        for (int c = 0; c < CPB; ++c) {
+            double e = ew * r[c];
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) e += __shfl_xor_sync(0xffffffffu, e, off);
+            if (lane == c && b0 + c < a.batch && !(a.variants && nact[c] < 0)) a.out[b0 + c] = e;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
 // small kernels
 // ---------------------------------------------------------------------------------------------------------
 __global__ void dmx_energy_kernel(const double* __restrict__ state, int n, long long batch, const uint32_t* __restrict__ term_idx,
@@ -789,6 +939,8 @@ struct DevPlan {
     double* f_eweight = nullptr;
     int* f_eslot = nullptr;
     int n_eterms = 0, n_smem_segs = 0;
+    // compact frame (frame32)
+    double2* g_w = nullptr; unsigned char* g_partner = nullptr; int* g_cs_sel = nullptr; double* g_init = nullptr; double* g_ew = nullptr; int* g_orig = nullptr;
     SlotDev* slots = nullptr;
     uint8_t* labels = nullptr;
     int* worklist = nullptr;           // capacity wl_cap (+ counter at the end)
@@ -1017,6 +1169,20 @@ static int ensure_device(Plan& p, DevPlan** out) {
         }
         CUDA_TRY(upload(&d->slots, sl));
         CUDA_TRY(upload(&d->labels, lab));
+        if (p.f32_n > 0) {
+            std::vector<double2> gw((size_t)K * 32, make_double2(0, 0));
+            std::vector<int> sel(K, -2);
+            for (int k = 0; k < p.nseg; ++k) {
+                sel[k] = p.fsegs[k].cs_sel;
+                for (int l = 0; l < 32; ++l) gw[(size_t)k * 32 + l] = make_double2(p.f32_w[((size_t)k * 32 + l) * 2], p.f32_w[((size_t)k * 32 + l) * 2 + 1]);
+            }
+            CUDA_TRY(upload(&d->g_w, gw));
+            CUDA_TRY(upload(&d->g_partner, p.f32_partner));
+            CUDA_TRY(upload(&d->g_cs_sel, sel));
+            CUDA_TRY(upload(&d->g_init, p.f32_init));
+            CUDA_TRY(upload(&d->g_ew, p.f32_eweight));
+            CUDA_TRY(upload(&d->g_orig, p.f32_orig));
+        }
     }
     CUDA_TRY(build_stream_tables(p, d));
     {
@@ -1041,6 +1207,7 @@ static void free_device(Plan& p) {
     cudaFree(d->coefs); cudaFree(d->rots); cudaFree(d->term_idx); cudaFree(d->term_coef);
     cudaFree(d->f_w); cudaFree(d->f_segs); cudaFree(d->f_classes); cudaFree(d->f_init); cudaFree(d->f_eweight); cudaFree(d->f_eslot);
     cudaFree(d->slots); cudaFree(d->labels); cudaFree(d->worklist);
+    cudaFree(d->g_w); cudaFree(d->g_partner); cudaFree(d->g_cs_sel); cudaFree(d->g_init); cudaFree(d->g_ew); cudaFree(d->g_orig);
     for (auto& px : d->passx) cudaFree(px.coefs);
     if (d->h_stage) cudaFreeHost(d->h_stage);
     if (d->d_stage) cudaFree(d->d_stage);
@@ -1324,7 +1491,33 @@ static int launch_frame(const FrameArgs& a, int sm_count, cudaStream_t st) {
     return DMX_OK;
 }
 
+template <int CPB, int CSMODE>
+static int launch_frame32(const Frame32Args& a, int sm_count, cudaStream_t st) {
+    const int NC = a.n_classes > 0 ? a.n_classes : 1;
+    const size_t smem = (size_t)8 * CPB * NC * 16 + (size_t)8 * CPB * (SEG_MAXACT + 1) * 4 + 16;
+    if (smem > 200 * 1024) return fail(DMX_ERR_UNSUPPORTED, "frame32 kernel: tables do not fit shared memory");
+    static std::mutex mu;
+    static size_t configured = 0;
+    {
+        std::lock_guard<std::mutex> lock(mu);
+        if (smem > configured) {
+            CUDA_TRY(cudaFuncSetAttribute(dmx_frame32_kernel<CPB, CSMODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max(smem, (size_t)48 * 1024)));
+            configured = std::max(smem, (size_t)48 * 1024);
+        }
+    }
+    const long long groups = (a.batch + CPB - 1) / CPB;
+    int per_sm = 0;
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, dmx_frame32_kernel<CPB, CSMODE>, 256, smem));
+    per_sm = std::max(per_sm, 1);
+    const int grid = (int)std::max<long long>(1, std::min<long long>((groups + 7) / 8, (long long)sm_count * per_sm));
+    dmx_frame32_kernel<CPB, CSMODE><<<grid, 256, smem, st>>>(a);
+    ++g_launches;
+    CUDA_TRY(cudaGetLastError());
+    return DMX_OK;
+}
+
 static int g_seg_cpb = 8;
+static int g_frame32 = 1;      // option "frame32": 0 -> always the 256-thread frame kernel
 
 static int run_segment(Plan& p, DevPlan* d, long long batch, const double* params, const uint8_t* variants, double* out, cudaStream_t st) {
     FrameArgs a{};
@@ -1345,6 +1538,20 @@ static int run_segment(Plan& p, DevPlan* d, long long batch, const double* param
     }
     const int mode = p.f_classes.empty() ? 0 : (p.f_single_class ? 1 : 2);
     int rc;
+    if (p.f32_n > 0 && g_frame32) {
+        Frame32Args g{};
+        g.nseg = p.nseg; g.n_params = p.n_params; g.n_slots = p.n_slots; g.n_classes = (int)p.f_classes.size(); g.batch = batch;
+        g.w = d->g_w; g.partner = d->g_partner; g.cs_sel = d->g_cs_sel; g.classes = d->f_classes; g.init = d->g_init; g.eweight = d->g_ew;
+        g.orig = d->g_orig; g.params = params; g.variants = variants; g.slots = d->slots; g.labels = d->labels; g.coefs = d->coefs;
+        g.out = out; g.worklist = a.worklist; g.work_count = a.work_count;
+        if (g_seg_cpb == 4)
+            rc = mode == 0 ? launch_frame32<4, 0>(g, d->sm_count, st) : mode == 1 ? launch_frame32<4, 1>(g, d->sm_count, st) : launch_frame32<4, 2>(g, d->sm_count, st);
+        else
+            rc = mode == 0 ? launch_frame32<8, 0>(g, d->sm_count, st) : mode == 1 ? launch_frame32<8, 1>(g, d->sm_count, st) : launch_frame32<8, 2>(g, d->sm_count, st);
+        if (rc) return rc;
+        if (variants) rc = run_tile_single(p, d, batch, params, variants, out, OUT_ENERGY, d->worklist + 1, d->worklist, st);
+        return rc;
+    }
     if (g_seg_cpb == 4) {
         rc = mode == 0 ? launch_frame<4, 0>(a, d->sm_count, st) : mode == 1 ? launch_frame<4, 1>(a, d->sm_count, st) : launch_frame<4, 2>(a, d->sm_count, st);
     } else {
@@ -1414,6 +1621,8 @@ int dmx_plan_set_option(dmx_plan* plan, const char* key, int value) {
     } else if (k == "stream_chunk") {
         if (value < 0) return fail(DMX_ERR_INVALID, "stream_chunk must be >= 0");
         g_stream_chunk = value;
+    } else if (k == "frame32") {
+        g_frame32 = value != 0;
     } else if (k == "segment_cpb") {
         if (value != 4 && value != 8) return fail(DMX_ERR_INVALID, "segment_cpb must be 4 or 8");
         g_seg_cpb = value;

@@ -1688,6 +1688,61 @@ static int gf2_rank(const std::vector<unsigned>& vecs) {
     return (int)basis.size();
 }
 
+// Liveness of the fixed-frame program: forward (reachable from the initial state) and backward (able to reach an energy
+// term) over the segments; a coefficient outside both can be dropped without changing Tr(rho H).  Variant slots only scale
+// coefficients (diagonal corrections), so the analysis holds for every variant row the frame kernel accepts.
+static void build_frame32(Plan& p) {
+    p.f32_n = 0;
+    const int K = p.nseg;
+    std::vector<std::vector<char>> fwd(K + 1, std::vector<char>(SEG_E, 0)), need(K + 1, std::vector<char>(SEG_E, 0));
+    for (int t = 0; t < SEG_E; ++t) { fwd[0][t] = p.f_init[t] != 0.0; need[K][t] = p.f_eweight[t] != 0.0; }
+    auto w0 = [&](int k, int t) { return p.f_w[((size_t)k * SEG_E + t) * 2]; };
+    auto w1 = [&](int k, int t) { return p.f_w[((size_t)k * SEG_E + t) * 2 + 1]; };
+    for (int k = 0; k < K; ++k)
+        for (int t = 0; t < SEG_E; ++t) {
+            const int u = t ^ p.fsegs[k].xor_mask;
+            fwd[k + 1][t] = (w0(k, t) != 0.0 && fwd[k][t]) || (w1(k, t) != 0.0 && fwd[k][u]);
+        }
+    for (int k = K - 1; k >= 0; --k)
+        for (int t = 0; t < SEG_E; ++t) {
+            if (!need[k + 1][t]) continue;
+            if (w0(k, t) != 0.0) need[k][t] = 1;
+            if (w1(k, t) != 0.0) need[k][t ^ p.fsegs[k].xor_mask] = 1;
+        }
+    std::vector<int> lane_of(SEG_E, -1), orig;
+    for (int t = 0; t < SEG_E; ++t) {
+        bool live = false;
+        for (int k = 0; k <= K; ++k) live = live || (fwd[k][t] && need[k][t]);
+        if (live) { lane_of[t] = (int)orig.size(); orig.push_back(t); }
+    }
+    if (orig.empty() || orig.size() > 32) return;
+    p.f32_n = (int)orig.size();
+    orig.resize(32, -1);
+    p.f32_orig = orig;
+    p.f32_partner.assign((size_t)std::max(K, 1) * 32, 0);
+    p.f32_w.assign((size_t)std::max(K, 1) * 64, 0.0);
+    p.f32_init.assign(32, 0.0);
+    p.f32_eweight.assign(32, 0.0);
+    for (int l = 0; l < 32; ++l) {
+        const int t = orig[l];
+        for (int k = 0; k < K; ++k) p.f32_partner[(size_t)k * 32 + l] = (uint8_t)l;
+        if (t < 0) continue;
+        p.f32_init[l] = p.f_init[t];
+        p.f32_eweight[l] = p.f_eweight[t];
+        for (int k = 0; k < K; ++k) {
+            const int u = t ^ p.fsegs[k].xor_mask;
+            p.f32_w[((size_t)k * 32 + l) * 2] = w0(k, t);
+            // bit 7: the rotation moves this coefficient (it takes the cos factor) even when its partner is outside the
+            // live set — such a partner is either zero at this stage or feeds a coefficient nothing needs
+            if (w1(k, t) != 0.0) p.f32_partner[(size_t)k * 32 + l] |= 0x80;
+            if (w1(k, t) != 0.0 && lane_of[u] >= 0) {
+                p.f32_w[((size_t)k * 32 + l) * 2 + 1] = w1(k, t);
+                p.f32_partner[(size_t)k * 32 + l] = (uint8_t)(lane_of[u] | 0x80);
+            }
+        }
+    }
+}
+
 static bool build_frame(Plan& p, std::string& why) {
     const int K = p.nseg;
     std::vector<int> holder(SEG_E), nh(SEG_E);
@@ -1808,6 +1863,7 @@ static bool build_frame(Plan& p, std::string& why) {
             for (int q = 0; q < SEG_E; ++q) p.f_w[((size_t)k * SEG_E + q) * 2 + 1] = -p.f_w[((size_t)k * SEG_E + q) * 2 + 1];
     }
     p.f_single_class = p.f_classes.size() <= 1;
+    build_frame32(p);
     return true;
 }
 
@@ -1817,7 +1873,7 @@ void lower_plan(Plan& p) {
     if (p.n < 1 || p.n > DMX_MAX_QUBITS) throw std::runtime_error("n_qubits out of range");
     p.blocks.clear(); p.rots.clear(); p.mus.clear(); p.sweeps.clear(); p.factors.clear(); p.chains.clear(); p.phases.clear();
     p.coefs.clear(); p.passes.clear();
-    p.remapped = false; p.triples = false; p.sweeps3.clear();
+    p.remapped = false; p.triples = false; p.sweeps3.clear(); p.f32_n = 0;
     p.cpb = plan_cpb(p.n);
     p.segs.clear(); p.slots.clear(); p.term_idx.clear(); p.term_coef.clear();
     std::memset(&p.info, 0, sizeof(p.info));
@@ -1884,7 +1940,8 @@ void lower_plan(Plan& p) {
     if (p.path == 1) {
         int smem_segs = 0;
         for (const FrameSeg& fs : p.fsegs) smem_segs += !fs.use_shfl;
-        in.flops_per_circuit = (p.nseg * 4.0 + 1.0) * SEG_E + 2.0 * p.e_w.size();
+        // the compact frame kernel executes the segments on 32 lanes per circuit instead of 256 threads
+        in.flops_per_circuit = (p.nseg * 4.0 + 1.0) * (p.f32_n > 0 ? 32.0 : (double)SEG_E) + 2.0 * p.e_w.size();
         // per circuit: smem-exchange segments move 8 B out + 8 B in per coefficient; the energy stage a few terms
         in.smem_bytes_per_circuit = smem_segs * SEG_E * 16.0 + 16.0 * p.e_w.size();
         in.hbm_bytes_per_circuit = io;
@@ -1998,6 +2055,19 @@ std::string dump_plan(const Plan& p) {
         dump_vec(os, "init", p.f_init);
         dump_vec(os, "eweight", p.f_eweight);
         os << "\n";
+        if (p.f32_n > 0) {
+            os << "f32 n=" << p.f32_n;
+            dump_ints(os, "orig", p.f32_orig);
+            dump_vec(os, "init", p.f32_init);
+            dump_vec(os, "eweight", p.f32_eweight);
+            os << "\n";
+            for (int k = 0; k < p.nseg; ++k) {
+                os << "f32seg " << k;
+                dump_ints(os, "partner", std::vector<int>(p.f32_partner.begin() + (size_t)k * 32, p.f32_partner.begin() + (size_t)(k + 1) * 32));
+                dump_vec(os, "w", std::vector<double>(p.f32_w.begin() + (size_t)k * 64, p.f32_w.begin() + (size_t)(k + 1) * 64));
+                os << "\n";
+            }
+        }
         for (size_t c = 0; c < p.f_classes.size(); ++c) {
             os << "fclass " << c << " param=" << p.f_classes[c].param;
             dump_vec(os, "scale", {p.f_classes[c].scale}); dump_vec(os, "offset", {p.f_classes[c].offset});

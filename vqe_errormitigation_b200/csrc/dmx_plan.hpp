@@ -204,6 +204,14 @@ struct Plan {
     std::vector<uint8_t> f_labels;    // [n_slots][256]
     std::vector<RotInfo> f_classes;   // distinct (param, scale, offset) rotation classes
     int f_single_class = 0;           // 1: every rotation segment uses class 0 (kept in registers)
+    // Compact frame ("frame32"): only the Pauli coefficients that are both reachable from |0..0> and able to influence a
+    // Hamiltonian term are ever non-trivial (noisy H2 UCCSD: 23 of 256).  When at most 32 are, one WARP carries a circuit:
+    // lane l owns coefficient f32_orig[l]; the partner of a segment comes from __shfl_sync(r, f32_partner[k][l]).
+    int f32_n = 0;                    // live coefficients (0: compact form not available)
+    std::vector<int> f32_orig;        // [32] frame index of the lane's coefficient (-1: idle lane)
+    std::vector<uint8_t> f32_partner; // [nseg][32]: partner lane | 0x80 when the segment's rotation moves the coefficient
+    std::vector<double> f32_w;        // [nseg][32][2]
+    std::vector<double> f32_init, f32_eweight;   // [32]
 
     dmx_plan_info info{};
 
