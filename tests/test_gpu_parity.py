@@ -80,6 +80,17 @@ def test_batch_sizes_and_host_api():
         want = oracle_energy(h2_ops([O.depolarize(1e-3)], [O.two_qubit_depolarize(1e-3)], alpha=a[i, 0]), 4, ham)
         assert abs(dev[i] - want) < TOL
     assert prog.energies(torch.zeros(0, 1, dtype=torch.float64)).numel() == 0
+    # host-buffer call, pipelined in chunks (three streams): ragged batch, pageable and page-locked buffers
+    from vqe_errormitigation_b200 import engine
+    B = 70001
+    a = rng.normal(0, 0.3, size=(B, 1))
+    dev = prog.energies(torch.tensor(a)).cpu().numpy()
+    assert np.max(np.abs(prog.energies_host(a) - dev)) < 1e-13
+    ap, out = engine.pinned_empty(a.shape), engine.pinned_empty(B)
+    ap[...] = a
+    out[...] = np.nan
+    res = prog.energies_host(ap, out=out)
+    assert res is out and np.max(np.abs(out - dev)) < 1e-13
 
 
 def random_unitary(rng, d):

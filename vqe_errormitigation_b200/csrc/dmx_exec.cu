@@ -617,6 +617,15 @@ __global__ void __launch_bounds__(256) dmx_frame32_kernel(const Frame32Args a) {
     double2* cs = reinterpret_cast<double2*>(dmx_smem) + (size_t)warp * CPB * NC;
     unsigned* act = reinterpret_cast<unsigned*>(reinterpret_cast<double2*>(dmx_smem) + (size_t)8 * CPB * NC) + (size_t)warp * CPB * (SEG_MAXACT + 1);
     int* nact = reinterpret_cast<int*>(act + CPB * SEG_MAXACT);
+    // segment tables -> shared memory once per CTA (every warp walks them for every circuit group)
+    double2* sw = reinterpret_cast<double2*>(reinterpret_cast<unsigned*>(reinterpret_cast<double2*>(dmx_smem) + (size_t)8 * CPB * NC) +
+                                             (size_t)8 * CPB * (SEG_MAXACT + 1) + 4);
+    sw = reinterpret_cast<double2*>((reinterpret_cast<uintptr_t>(sw) + 15) & ~(uintptr_t)15);
+    unsigned char* spart = reinterpret_cast<unsigned char*>(sw + (size_t)a.nseg * 32);
+    int* ssel = reinterpret_cast<int*>(spart + (size_t)a.nseg * 32);
+    for (int i = threadIdx.x; i < a.nseg * 32; i += 256) { sw[i] = a.w[i]; spart[i] = a.partner[i]; }
+    for (int i = threadIdx.x; i < a.nseg; i += 256) ssel[i] = a.cs_sel[i];
+    __syncthreads();
     const long long ngroups = (a.batch + CPB - 1) / CPB;
     const long long gwarp = (long long)blockIdx.x * 8 + warp, nwarps = (long long)gridDim.x * 8;
     const double init = a.init[lane];
@@ -705,20 +714,25 @@ __global__ void __launch_bounds__(256) dmx_frame32_kernel(const Frame32Args a) {
                 }
             }
             if (k == a.nseg) break;
-            const int sel = a.cs_sel[k];
-            const double2 wk = a.w[k * 32 + lane];
-            const unsigned pb = a.partner[k * 32 + lane];
+            const int sel = ssel[k];
+            const double2 wk = sw[k * 32 + lane];
+            const unsigned pb = spart[k * 32 + lane];
             const bool active = pb & 0x80u;
             const int src = pb & 31u;
+            if (sel < 0) {          // constant-coefficient segment (resolved rotation): weights carry cos / sin already
 #pragma unroll
-            for (int c = 0; c < CPB; ++c) {
-                const double other = __shfl_sync(0xffffffffu, r[c], src);
-                double2 v;
-                if (sel < 0) v = make_double2(1.0, 1.0);
-                else if (CSMODE == 1) v = csr[c];
-                else v = cs[c * NC + sel];
-                const double cm = active ? v.x : 1.0;
-                r[c] = cm * (wk.x * r[c]) + v.y * (wk.y * other);
+                for (int c = 0; c < CPB; ++c) {
+                    const double other = __shfl_sync(0xffffffffu, r[c], src);
+                    r[c] = wk.x * r[c] + wk.y * other;
+                }
+            } else {
+#pragma unroll
+                for (int c = 0; c < CPB; ++c) {
+                    const double other = __shfl_sync(0xffffffffu, r[c], src);
+                    const double2 v = CSMODE == 1 ? csr[c] : cs[c * NC + sel];
+                    const double cm = active ? v.x : 1.0;
+                    r[c] = cm * (wk.x * r[c]) + v.y * (wk.y * other);
+                }
             }
         }
         // energy: fixed butterfly over the 32 lanes (deterministic), lane c writes circuit c
@@ -946,7 +960,9 @@ struct DevPlan {
     int* worklist = nullptr;           // capacity wl_cap (+ counter at the end)
     long long wl_cap = 0;
     // host-buffer API staging
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr, s_in = nullptr, s_out = nullptr;   // host-buffer API: compute / copy-in / copy-out
+    static constexpr int MAX_CHUNKS = 8;
+    cudaEvent_t ev_in[MAX_CHUNKS] = {}, ev_k[MAX_CHUNKS] = {};
     void* h_stage = nullptr; size_t h_cap = 0;
     void* d_stage = nullptr; size_t d_cap = 0;
     std::mutex mu;       // host-buffer API staging (held for the whole dmx_energy_batch_host call)
@@ -1211,7 +1227,10 @@ static void free_device(Plan& p) {
     for (auto& px : d->passx) cudaFree(px.coefs);
     if (d->h_stage) cudaFreeHost(d->h_stage);
     if (d->d_stage) cudaFree(d->d_stage);
-    if (d->stream) cudaStreamDestroy(d->stream);
+    if (d->stream) {
+        cudaStreamDestroy(d->stream); cudaStreamDestroy(d->s_in); cudaStreamDestroy(d->s_out);
+        for (int i = 0; i < DevPlan::MAX_CHUNKS; ++i) { cudaEventDestroy(d->ev_in[i]); cudaEventDestroy(d->ev_k[i]); }
+    }
     delete d;
     p.dev = nullptr;
 }
@@ -1301,6 +1320,7 @@ static int run_tile_single(Plan& p, DevPlan* d, long long batch, const double* p
     return launch_tile(a, grid, threads, gpt, smem, st);
 }
 
+static int64_t g_host_chunk_rows = 32768;   // option "host_chunk_rows": rows per pipeline chunk of dmx_energy_batch_host
 static int g_stream_kernel = 1;        // option "stream_kernel": 0 -> generic dmx_tile_kernel for every pass
 static long long g_stream_chunk = 0;   // option "stream_chunk": circuits per pass launch (0: auto, ~64 MiB of states stay in L2)
 
@@ -1494,7 +1514,7 @@ static int launch_frame(const FrameArgs& a, int sm_count, cudaStream_t st) {
 template <int CPB, int CSMODE>
 static int launch_frame32(const Frame32Args& a, int sm_count, cudaStream_t st) {
     const int NC = a.n_classes > 0 ? a.n_classes : 1;
-    const size_t smem = (size_t)8 * CPB * NC * 16 + (size_t)8 * CPB * (SEG_MAXACT + 1) * 4 + 16;
+    const size_t smem = (size_t)8 * CPB * NC * 16 + (size_t)8 * CPB * (SEG_MAXACT + 1) * 4 + 48 + (size_t)a.nseg * (32 * 16 + 32 + 4);
     if (smem > 200 * 1024) return fail(DMX_ERR_UNSUPPORTED, "frame32 kernel: tables do not fit shared memory");
     static std::mutex mu;
     static size_t configured = 0;
@@ -1621,6 +1641,9 @@ int dmx_plan_set_option(dmx_plan* plan, const char* key, int value) {
     } else if (k == "stream_chunk") {
         if (value < 0) return fail(DMX_ERR_INVALID, "stream_chunk must be >= 0");
         g_stream_chunk = value;
+    } else if (k == "host_chunk_rows") {
+        if (value < 1024) return fail(DMX_ERR_INVALID, "host_chunk_rows must be >= 1024");
+        g_host_chunk_rows = value;
     } else if (k == "frame32") {
         g_frame32 = value != 0;
     } else if (k == "segment_cpb") {
@@ -1832,6 +1855,17 @@ int dmx_qp_sample_variants(int n_slots, const int32_t* n_choices, const double* 
     return DMX_OK;
 }
 
+static bool is_pinned_host(const void* ptr) {
+    if (!ptr) return true;
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, ptr) != cudaSuccess) { (void)cudaGetLastError(); return false; }
+    return at.type == cudaMemoryTypeHost;
+}
+
+// Host-buffer call.  The batch is cut into chunks that flow through three streams — H2D of chunk i+1, the kernels of chunk i
+// and the D2H of chunk i-1 overlap — so the call costs about max(copy in, compute, copy out) instead of their sum.  Buffers
+// that are already page-locked (cudaHostAlloc / cudaHostRegister, e.g. torch pinned tensors) are used in place; pageable
+// ones go through the plan's pinned staging buffer.
 int dmx_energy_batch_host(dmx_plan* plan, int64_t batch, const double* h_params, const uint8_t* h_variants, double* h_energy) {
     int rc = check_exec(plan, batch, h_params, h_energy);
     if (rc) return rc;
@@ -1841,12 +1875,22 @@ int dmx_energy_batch_host(dmx_plan* plan, int64_t batch, const double* h_params,
     if (rc) return rc;
     if (batch == 0) return DMX_OK;
     std::lock_guard<std::mutex> lock(d->mu);
-    if (!d->stream) CUDA_TRY(cudaStreamCreateWithFlags(&d->stream, cudaStreamNonBlocking));
+    if (!d->stream) {
+        CUDA_TRY(cudaStreamCreateWithFlags(&d->stream, cudaStreamNonBlocking));
+        CUDA_TRY(cudaStreamCreateWithFlags(&d->s_in, cudaStreamNonBlocking));
+        CUDA_TRY(cudaStreamCreateWithFlags(&d->s_out, cudaStreamNonBlocking));
+        for (int i = 0; i < DevPlan::MAX_CHUNKS; ++i) {
+            CUDA_TRY(cudaEventCreateWithFlags(&d->ev_in[i], cudaEventDisableTiming));
+            CUDA_TRY(cudaEventCreateWithFlags(&d->ev_k[i], cudaEventDisableTiming));
+        }
+    }
+    const size_t prow = h_params ? (size_t)p.n_params * 8 : 0, vrow = h_variants ? (size_t)p.n_slots : 0;
     auto align = [](size_t v) { return (v + 255) & ~(size_t)255; };
-    const size_t pb = align((size_t)batch * p.n_params * 8), vb = h_variants ? align((size_t)batch * p.n_slots) : 0, eb = align((size_t)batch * 8);
+    const size_t pb = align((size_t)batch * prow), vb = align((size_t)batch * vrow), eb = align((size_t)batch * 8);
     size_t ws = 0;
     if (p.path == 2) ws = (size_t)p.info.workspace_bytes_per_state * (size_t)std::min<int64_t>(batch, 64);
-    const size_t hneed = pb + vb + eb, dneed = hneed + ws;
+    const bool pin_in = is_pinned_host(h_params) && is_pinned_host(h_variants), pin_out = is_pinned_host(h_energy);
+    const size_t hneed = (pin_in ? 0 : pb + vb) + (pin_out ? 0 : eb), dneed = pb + vb + eb + ws;
     if (d->h_cap < hneed) {
         if (d->h_stage) CUDA_TRY(cudaFreeHost(d->h_stage));
         d->h_stage = nullptr; d->h_cap = 0;
@@ -1861,16 +1905,33 @@ int dmx_energy_batch_host(dmx_plan* plan, int64_t batch, const double* h_params,
     }
     char* hs = (char*)d->h_stage;
     char* ds = (char*)d->d_stage;
-    if (pb) std::memcpy(hs, h_params, (size_t)batch * p.n_params * 8);
-    if (vb) std::memcpy(hs + pb, h_variants, (size_t)batch * p.n_slots);
-    if (pb + vb) CUDA_TRY(cudaMemcpyAsync(ds, hs, pb + vb, cudaMemcpyHostToDevice, d->stream));
-    // the mutex is released around nothing: the staging buffers belong to this call until the sync below
-    rc = energy_impl(plan, batch, pb ? (const double*)ds : nullptr, vb ? (const uint8_t*)(ds + pb) : nullptr, (double*)(ds + pb + vb),
-                     ws ? ds + hneed : nullptr, ws, d->stream);
-    if (rc) return rc;
-    CUDA_TRY(cudaMemcpyAsync(hs + pb + vb, ds + pb + vb, (size_t)batch * 8, cudaMemcpyDeviceToHost, d->stream));
-    CUDA_TRY(cudaStreamSynchronize(d->stream));
-    std::memcpy(h_energy, hs + pb + vb, (size_t)batch * 8);
+    const char* src_p = pin_in ? (const char*)h_params : hs;
+    const char* src_v = pin_in ? (const char*)h_variants : hs + pb;
+    char* dst_e = pin_out ? (char*)h_energy : hs + (pin_in ? 0 : pb + vb);
+    // small-state plans: pipeline in up to MAX_CHUNKS chunks; streaming plans are long-running, one chunk
+    int n_chunks = 1;
+    if (p.path != 2) n_chunks = (int)std::max<int64_t>(1, std::min<int64_t>(DevPlan::MAX_CHUNKS, batch / g_host_chunk_rows));
+    const int64_t per = ((batch + n_chunks - 1) / n_chunks + 7) & ~(int64_t)7;
+    for (int c = 0; c < n_chunks; ++c) {
+        const int64_t lo = (int64_t)c * per, cnt = std::min<int64_t>(per, batch - lo);
+        if (cnt <= 0) { n_chunks = c; break; }
+        if (!pin_in) {
+            if (prow) std::memcpy(hs + lo * prow, (const char*)h_params + lo * prow, (size_t)cnt * prow);
+            if (vrow) std::memcpy(hs + pb + lo * vrow, (const char*)h_variants + lo * vrow, (size_t)cnt * vrow);
+        }
+        if (prow) CUDA_TRY(cudaMemcpyAsync(ds + lo * prow, src_p + lo * prow, (size_t)cnt * prow, cudaMemcpyHostToDevice, d->s_in));
+        if (vrow) CUDA_TRY(cudaMemcpyAsync(ds + pb + lo * vrow, src_v + lo * vrow, (size_t)cnt * vrow, cudaMemcpyHostToDevice, d->s_in));
+        CUDA_TRY(cudaEventRecord(d->ev_in[c], d->s_in));
+        CUDA_TRY(cudaStreamWaitEvent(d->stream, d->ev_in[c], 0));
+        rc = energy_impl(plan, cnt, prow ? (const double*)(ds + lo * prow) : nullptr, vrow ? (const uint8_t*)(ds + pb + lo * vrow) : nullptr,
+                         (double*)(ds + pb + vb) + lo, ws ? ds + pb + vb + eb : nullptr, ws, d->stream);
+        if (rc) { cudaStreamSynchronize(d->stream); cudaStreamSynchronize(d->s_in); cudaStreamSynchronize(d->s_out); return rc; }
+        CUDA_TRY(cudaEventRecord(d->ev_k[c], d->stream));
+        CUDA_TRY(cudaStreamWaitEvent(d->s_out, d->ev_k[c], 0));
+        CUDA_TRY(cudaMemcpyAsync(dst_e + lo * 8, ds + pb + vb + lo * 8, (size_t)cnt * 8, cudaMemcpyDeviceToHost, d->s_out));
+    }
+    CUDA_TRY(cudaStreamSynchronize(d->s_out));
+    if (!pin_out) std::memcpy(h_energy, dst_e, (size_t)batch * 8);
     return DMX_OK;
 }
 

@@ -260,8 +260,10 @@ class CircuitProgram:
         check(self._lib.dmx_energy_batch(self._handle, B, self._ptr(p_t), self._ptr(v_t), self._ptr(out), self._ptr(ws), nbytes, stream))
         return out
 
-    def energies_host(self, params: Optional[np.ndarray] = None, variants: Optional[np.ndarray] = None, batch: Optional[int] = None) -> np.ndarray:
-        """Host-buffer call (``dmx_energy_batch_host``): numpy in, numpy out, copies included."""
+    def energies_host(self, params: Optional[np.ndarray] = None, variants: Optional[np.ndarray] = None, batch: Optional[int] = None,
+                      out: Optional[np.ndarray] = None) -> np.ndarray:
+        """Host-buffer call (``dmx_energy_batch_host``): numpy in, numpy out, copies included.  Page-locked arrays
+        (``engine.pinned_empty``) are copied from / into in place; pageable ones go through a pinned staging buffer."""
         _require_cuda()
         sizes = set()
         p = v = None
@@ -277,7 +279,10 @@ class CircuitProgram:
         if len(sizes) != 1:
             raise ValueError(f"inconsistent batch sizes {sorted(sizes)}")
         B = sizes.pop()
-        out = np.empty(B, np.float64)
+        if out is None:
+            out = np.empty(B, np.float64)
+        elif out.dtype != np.float64 or out.size != B or not out.flags.c_contiguous:
+            raise ValueError("out must be a contiguous float64 array of the batch size")
         check(self._lib.dmx_energy_batch_host(self._handle, B, p.ctypes.data_as(C.c_void_p) if p is not None else None,
                                               v.ctypes.data_as(C.c_void_p) if v is not None else None, out.ctypes.data_as(C.c_void_p)))
         return out
@@ -325,6 +330,18 @@ def qp_reduce(values, weights, counts=None):
     check(lib.dmx_qp_reduce(C.c_void_p(values.data_ptr()), C.c_void_p(weights.data_ptr()), c_ptr, values.numel(),
                             C.c_void_p(out.data_ptr()), stream))
     return out
+
+
+def pinned_empty(shape, dtype=np.float64) -> np.ndarray:
+    """Page-locked numpy array (a view of a pinned torch tensor): the host-buffer API copies from / into it without staging."""
+    torch = _require_cuda()
+    t = torch.empty(tuple(np.atleast_1d(shape)), dtype=getattr(torch, np.dtype(dtype).name), pin_memory=True)
+    arr = t.numpy()
+    _PINNED_KEEPALIVE[arr.__array_interface__["data"][0]] = t
+    return arr
+
+
+_PINNED_KEEPALIVE: Dict[int, object] = {}
 
 
 def pack_qp_tables(qps: Sequence[np.ndarray]) -> Tuple[np.ndarray, np.ndarray]:
