@@ -3,11 +3,16 @@
 // Kernels (all FP64, no tensor cores — SURVEY.md §2.1):
 //   dmx_tile_kernel     Pauli-vector tile resident in shared memory; interprets the fused block list of one
 //                       pass (DIAG/MONO/MAT/ROT/VAR on 1 or 2 qubits).  n <= 7: whole circuit in one launch
-//                       (several circuits per CTA for small n), fused Tr(rho H) epilogue.  n > 7: one tile of a
-//                       streaming pass (coalesced 16-byte loads/stores of 128-byte runs).
-//   dmx_frame_kernel    n <= 4, Clifford + Pauli-noise (+ rotations) circuits: thread-per-Pauli-coefficient in a
-//                       fixed frame; a segment is r <- cm*w0*r + sm*w1*r[t^mask] with the partner fetched by a
-//                       warp shuffle (or one shared-memory exchange when the mask crosses warps).
+//                       (several circuits per CTA for small n), fused Tr(rho H) epilogue.  n > 7: fallback for
+//                       streaming passes the stream kernels do not take (variant slots, tiles below 6 qubits).
+//   dmx_stream3_kernel / dmx_stream_kernel / dmx_chain_kernel (dmx_stream.cuh)
+//                       n > 7: one tile of a streaming pass, triple (64 coefficients per thread) or pair sweeps.
+//   dmx_frame32_kernel  n <= 4, Clifford + Pauli-noise (+ rotations) circuits whose live coefficient set fits a warp
+//                       (noisy H2: 23 of 256): warp-per-circuit, partner by indexed shuffle, no barriers.
+//   dmx_frame_kernel    same circuit class, any live set: thread-per-Pauli-coefficient in a fixed frame; a segment
+//                       is r <- cm*w0*r + sm*w1*r[t^mask] with the partner fetched by a warp shuffle (or one
+//                       shared-memory exchange when the mask crosses warps).
+//   dmx_qp_sample_kernel  Philox4x32-10 draw of QP circuit variants.
 //   dmx_energy_kernel   gather-dot Tr(rho H) on a state in global memory (streaming path).
 //   dmx_pauli_to_rho / dmx_pauli_to_diag   output converters (final_density_matrix, run() probabilities).
 //   dmx_qp_reduce_*     deterministic two-stage reduction of the QP-weighted estimator.
@@ -1360,12 +1365,6 @@ static int launch_stream3(const StreamArgs3& a, long long grid, size_t smem, cud
     ++g_launches;
     CUDA_TRY(cudaGetLastError());
     return DMX_OK;
-}
-
-static unsigned map_runs_host(unsigned v, const BitRun* runs, int n) {
-    unsigned g = 0;
-    for (int i = 0; i < n; ++i) g |= ((v >> runs[i].lshift) & ((1u << runs[i].width) - 1u)) << runs[i].gshift;
-    return g;
 }
 
 // Streaming execution (n > tile_k): state[chunk][4^n] in `state`; all passes over one chunk of circuits.

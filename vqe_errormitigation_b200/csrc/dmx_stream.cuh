@@ -1,9 +1,11 @@
-// dmx_stream.cuh — streaming pass kernel for n > tile_k (BASELINE configs 4-5: 10..14 qubits).
+// dmx_stream.cuh — streaming pass kernels for n > tile_k (BASELINE configs 4-5: 10..14 qubits).
 //
 // One CTA owns one tile (4^k Pauli coefficients, k = 6 or 7 resident qubits) of one circuit for one pass:
 //     global -> shared (16-byte loads, whole tile in flight) -> sweeps -> global.
-// Every thread keeps 2 groups x 16 coefficients in registers during a sweep, so THREADS = 4^k / 32 and the whole
-// tile is register-resident while the micro-ops run; shared memory is only the exchange medium between sweeps.
+// dmx_stream3_kernel (default): every thread keeps the 64 coefficients of THREE resident codes in registers during a
+// sweep (THREADS = 4^k / 64); dmx_stream_kernel: 2 groups x 16 coefficients of a code pair (THREADS = 4^k / 32).  Either
+// way the whole tile is register-resident while the micro-ops run; shared memory is only the exchange medium between
+// sweeps.
 // Compared with the generic dmx_tile_kernel this kernel
 //   * reads per-circuit chain matrices (products of rotations / fixed one-qubit blocks) that dmx_chain_kernel
 //     computed ONCE per (circuit, pass) instead of once per tile,
@@ -167,18 +169,7 @@ __global__ void dmx_chain_kernel(const ChainDev* __restrict__ chains, const Chai
 
 // ---- register-level micro-ops on the two groups of a thread --------------------------------------------------
 // group element e = 4 * code(A) + code(B)
-template <int SA, int SB>   // strides of the acted-on code (SA) and the spectator code (SB) in e
-__device__ __forceinline__ void apply3(double (&v)[16], const double* __restrict__ M) {
-    const double m5 = M[5], m6 = M[6], m7 = M[7], m9 = M[9], m10 = M[10], m11 = M[11], m13 = M[13], m14 = M[14], m15 = M[15];
-#pragma unroll
-    for (int s = 0; s < 4; ++s) {
-        const double a = v[SA + s * SB], b = v[2 * SA + s * SB], c = v[3 * SA + s * SB];
-        v[SA + s * SB] = m5 * a + m6 * b + m7 * c;
-        v[2 * SA + s * SB] = m9 * a + m10 * b + m11 * c;
-        v[3 * SA + s * SB] = m13 * a + m14 * b + m15 * c;
-    }
-}
-
+// SA / SB: strides of the acted-on code and of the spectator code in e
 template <int SA, int SB>
 __device__ __forceinline__ void apply4(double (&v)[16], const double* __restrict__ M) {
     double m[16];
