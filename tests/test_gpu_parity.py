@@ -383,3 +383,34 @@ def test_twelve_qubit_register():
     ident = (np.array([0], np.uint32), np.array([0], np.uint32), np.array([1.0]))
     tr = build_program(ops, n, ident).energies(torch.tensor(params), workspace_states=2).cpu().numpy()
     assert np.max(np.abs(tr - 1.0)) < 1e-12
+
+
+@pytest.mark.parametrize("tile", [6, 7])
+def test_eleven_qubit_long_range_circuit_against_c_oracle(tile):
+    """Random long-range CNOTs, Clifford gates, rotations, Pauli and amplitude-damping noise on 11 qubits: remapped passes
+    with arbitrary (non-adjacent) tiles, triple sweeps with composed permutations, general micro-ops — vs the C oracle."""
+    from oracle import c_oracle as CO
+    torch = torch_cuda()
+    n = 11
+    rng = np.random.default_rng(1100 + tile)
+    ops = []
+    for _ in range(120):
+        a, b = (int(v) for v in rng.choice(n, 2, replace=False))
+        kind = int(rng.integers(0, 5))
+        if kind == 0:
+            ops += [("u", (a, b), O.CNOT), ("k", (a, b), O.two_qubit_depolarize(1e-2))]
+        elif kind == 1:
+            ops += [("r", (a,), (int(rng.integers(3)), f"t{int(rng.integers(6))}", 1.0, 0.0)), ("k", (a,), O.depolarize(1e-2))]
+        elif kind == 2:
+            ops += [("u", (a,), O.H), ("k", (a,), O.bit_flip(1e-2))]
+        elif kind == 3:
+            ops.append(("k", (a,), O.amplitude_damp(0.02)))
+        else:
+            ops.append(("u", (a, b), random_unitary(rng, 4)))
+    terms = random_hamiltonian(rng, n, 50)
+    prog = build_program(ops, n, terms, tile_qubits=tile)
+    assert prog.info["path"] == 2 and prog.info["workspace_bytes_per_state"] == 2 * prog.info["state_bytes"]
+    params = rng.uniform(-1.0, 1.0, size=(3, prog.n_params))
+    got = prog.energies(torch.tensor(params)).cpu().numpy()
+    want = CO.energy_batch(n, prog.ops, prog.pool, terms, params=params, n_params=prog.n_params, threads=3)
+    assert np.max(np.abs(got - want)) < TOL

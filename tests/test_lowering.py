@@ -232,3 +232,38 @@ def test_triple_sweep_lowering_random_clifford_mix(seed, tile):
     rho = O.simulate(n, resolve(ops, prog.param_names, vals))
     want = O.energy_sparse(rho, O.pauli_terms_to_matrix(n, *terms))
     assert abs(PI.energy(plan, PI.run_devops(plan, vals)) - want) < TOL
+
+
+@pytest.mark.parametrize("n,tile", [(11, 6), (13, 7), (14, 6)])
+def test_remap_scheduler_invariants_on_wide_registers(n, tile):
+    """Planning only (no state is built): random long-range Clifford + rotation circuits on 11..14 qubits keep the
+    scheduler's invariants — every block scheduled once, layouts chain, shared low pair resident on both sides."""
+    rng = np.random.default_rng(1400 + n)
+    ops = []
+    for _ in range(150):
+        a, b = (int(v) for v in rng.choice(n, 2, replace=False))
+        kind = int(rng.integers(0, 4))
+        if kind == 0:
+            ops += [("u", (a, b), O.CNOT), ("k", (a, b), O.two_qubit_depolarize(1e-2))]
+        elif kind == 1:
+            ops += [("r", (a,), (int(rng.integers(3)), f"t{int(rng.integers(6))}", 1.0, 0.0)), ("k", (a,), O.depolarize(1e-2))]
+        elif kind == 2:
+            ops += [("u", (a,), O.H), ("k", (a,), O.bit_flip(1e-2))]
+        else:
+            ops.append(("k", (a,), O.amplitude_damp(0.02)))
+    terms = random_hamiltonian(rng, n, 7)
+    prog = build_program(ops, n, terms, tile_qubits=tile)
+    plan = PI.parse(prog.dump())
+    assert prog.info["path"] == 2 and prog.info["workspace_bytes_per_state"] == 2 * prog.info["state_bytes"]
+    passes = plan["passes"]
+    assert list(passes[-1]["pos_out"]) == [n - 1 - q for q in range(n)]
+    for a, b in zip(passes[:-1], passes[1:]):
+        assert list(a["pos_out"]) == list(b["pos_in"])
+        low = [q for q in range(n) if a["pos_out"][q] < 2]
+        assert all(q in a["tile"] and q in b["tile"] for q in low)
+    assert all(len(p["tile"]) == tile for p in passes)
+    assert sum(ph["nsweeps"] for ph in plan["phases"]) == len(plan["sweeps3"])
+    # every micro-op of a triple sweep is one of the four triple kinds; chains are referenced exactly once
+    assert all(m["kind"] in (16, 17, 18, 19) for m in plan["mus"])
+    n_chain_refs = sum(1 for m in plan["mus"] if m["kind"] == 16 and m["a2"])
+    assert n_chain_refs == len(plan["chains"])

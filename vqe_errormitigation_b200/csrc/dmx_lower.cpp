@@ -1903,8 +1903,12 @@ void lower_plan(Plan& p) {
             bool has_var = false;
             for (const Block& b : p.blocks) has_var = has_var || b.kind == BK_VAR;
             p.triples = p.opt_triples && !has_var;
-            schedule_streaming_remap(p);
-            remapped = true;
+            try {
+                schedule_streaming_remap(p);
+                remapped = true;
+            } catch (const std::runtime_error&) {
+                remapped = false;      // e.g. a builder limit: fall back to the pinned-qubit scheduler below
+            }
             for (const Pass& ps : p.passes) remapped = remapped && (ps.n_phases == 0 || pass_stream_eligible(p, ps));
             if (!remapped) {   // the generic tile kernel only knows the standard layout: re-plan with pinned low qubits
                 p.mus.clear(); p.sweeps.clear(); p.sweeps3.clear(); p.factors.clear(); p.chains.clear(); p.phases.clear(); p.coefs.clear(); p.passes.clear();
