@@ -614,7 +614,20 @@ struct Frame32Args {
     int* work_count;
 };
 
-template <int CPB, int CSMODE>
+// diagonal factor of variant entry `ent` for the coefficient whose frame index is p (kept out of line: it runs for a few
+// entries per row, inlining it into the unrolled circuit loop only bloats the instruction footprint)
+__device__ __noinline__ double frame32_variant_factor(const SlotDev* __restrict__ slots, const uint8_t* __restrict__ labels,
+                                                      const double* __restrict__ coefs, unsigned ent, int p) {
+    const int s = (ent >> 8) & 4095u;
+    const unsigned idx = ent & 255u;
+    const SlotDev sd = slots[s];
+    const unsigned lab = labels[s * 256 + p];
+    const double* t = coefs + sd.tab_off;
+    return sd.nq == 1 ? t[idx * 4 + lab] : t[(idx >> 4) * 4 + (lab >> 2)] * t[(idx & 15u) * 4 + (lab & 3u)] * t[64 + lab];
+}
+
+// VAR = false: plain parameter sweeps (no variant code, fewer registers); VAR = true: QP variant rows.
+template <int CPB, int CSMODE, bool VAR>
 __global__ void __launch_bounds__(256) dmx_frame32_kernel(const Frame32Args a) {
     const int NC = a.n_classes > 0 ? a.n_classes : 1;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -665,32 +678,56 @@ __global__ void __launch_bounds__(256) dmx_frame32_kernel(const Frame32Args a) {
                 __syncwarp();
             }
         }
-        bool have_act = false;
-        if (a.variants) {
+        // Variant rows: the non-identity entries of each row are compacted into act[c][] as (stage << 20 | slot << 8 | idx);
+        // stage_any has a bit per stage that holds at least one entry of some circuit of the group.
+        unsigned stage_any = 0u;
+        if (VAR) {
             __syncwarp();
-            for (int c = 0; c < CPB; ++c) {
-                int count = 0;
-                bool general = false;
-                if (b0 + c < a.batch) {
-                    const uint8_t* row = a.variants + (b0 + c) * a.n_slots;
-                    for (int s0 = 0; s0 < a.n_slots; s0 += 32) {
-                        const int s = s0 + lane;
-                        unsigned idx = s < a.n_slots ? row[s] : 0u;
-                        if (idx && a.slots[s].seg < 0) idx = 0;
-                        const bool nz = idx != 0;
-                        if (nz && !((a.slots[s].diag_ok[idx >> 5] >> (idx & 31)) & 1u)) general = true;
-                        const unsigned m = __ballot_sync(0xffffffffu, nz);
-                        const int pos = count + __popc(m & ((1u << lane) - 1u));
-                        if (nz && pos < SEG_MAXACT) act[c * SEG_MAXACT + pos] = ((unsigned)s << 8) | idx;
-                        count += __popc(m);
+            int count[CPB];
+            bool general[CPB];
+#pragma unroll
+            for (int c = 0; c < CPB; ++c) { count[c] = 0; general[c] = false; }
+            for (int s00 = 0; s00 < a.n_slots; s00 += 128) {
+                // all identifier bytes of the CPB rows first (CPB x 4 independent loads per lane), then the compaction
+                unsigned pk[CPB];
+#pragma unroll
+                for (int c = 0; c < CPB; ++c) {
+                    pk[c] = 0u;
+                    if (b0 + c < a.batch) {
+                        const uint8_t* row = a.variants + (b0 + c) * a.n_slots;
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const int s = s00 + 32 * j + lane;
+                            if (s < a.n_slots) pk[c] |= (unsigned)row[s] << (8 * j);
+                        }
                     }
-                    general = __any_sync(0xffffffffu, general) || count > SEG_MAXACT;
                 }
+#pragma unroll
+                for (int c = 0; c < CPB; ++c) {
+                    if (!__any_sync(0xffffffffu, pk[c] != 0u)) continue;       // identity row: nothing to record
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const int s = s00 + 32 * j + lane;
+                        unsigned idx = (pk[c] >> (8 * j)) & 255u;
+                        int seg = -1;
+                        if (idx) { seg = a.slots[s].seg; if (seg < 0) idx = 0; }     // slot not present in the circuit
+                        const bool nz = idx != 0;
+                        if (nz && !((a.slots[s].diag_ok[idx >> 5] >> (idx & 31)) & 1u)) general[c] = true;
+                        const unsigned m = __ballot_sync(0xffffffffu, nz);
+                        const int pos = count[c] + __popc(m & ((1u << lane) - 1u));
+                        if (nz && pos < SEG_MAXACT) act[c * SEG_MAXACT + pos] = ((unsigned)seg << 20) | ((unsigned)s << 8) | idx;
+                        stage_any |= __reduce_or_sync(0xffffffffu, nz ? (seg < 31 ? 1u << seg : 0x80000000u) : 0u);
+                        count[c] += __popc(m);
+                    }
+                }
+            }
+#pragma unroll
+            for (int c = 0; c < CPB; ++c) {
+                const bool gen = __any_sync(0xffffffffu, general[c]) || count[c] > SEG_MAXACT;
                 if (lane == 0) {
-                    nact[c] = general ? -1 : count;
-                    if (general) a.worklist[atomicAdd(a.work_count, 1)] = (int)(b0 + c);
+                    nact[c] = gen ? -1 : count[c];
+                    if (gen) a.worklist[atomicAdd(a.work_count, 1)] = (int)(b0 + c);
                 }
-                have_act = have_act || general || count > 0;
             }
             __syncwarp();
         }
@@ -700,21 +737,13 @@ __global__ void __launch_bounds__(256) dmx_frame32_kernel(const Frame32Args a) {
         for (int c = 0; c < CPB; ++c) r[c] = init;
 
         for (int k = 0; k <= a.nseg; ++k) {
-            if (have_act) {
+            if (VAR && ((stage_any >> (k < 31 ? k : 31)) & 1u)) {
 #pragma unroll
                 for (int c = 0; c < CPB; ++c) {
                     const int na = nact[c];
                     for (int e = 0; e < na; ++e) {
                         const unsigned ent = act[c * SEG_MAXACT + e];
-                        const int s = ent >> 8;
-                        const unsigned idx = ent & 255u;
-                        const SlotDev sd = a.slots[s];
-                        if (sd.seg != k) continue;
-                        const unsigned lab = a.labels[s * 256 + p];
-                        const double* t = a.coefs + sd.tab_off;
-                        const double f = sd.nq == 1 ? t[idx * 4 + lab]
-                                                    : t[(idx >> 4) * 4 + (lab >> 2)] * t[(idx & 15u) * 4 + (lab & 3u)] * t[64 + lab];
-                        r[c] *= f;
+                        if ((int)(ent >> 20) == k) r[c] *= frame32_variant_factor(a.slots, a.labels, a.coefs, ent, p);
                     }
                 }
             }
@@ -746,7 +775,7 @@ __global__ void __launch_bounds__(256) dmx_frame32_kernel(const Frame32Args a) {
             double e = ew * r[c];
 #pragma unroll
             for (int off = 16; off > 0; off >>= 1) e += __shfl_xor_sync(0xffffffffu, e, off);
-            if (lane == c && b0 + c < a.batch && !(a.variants && nact[c] < 0)) a.out[b0 + c] = e;
+            if (lane == c && b0 + c < a.batch && !(VAR && nact[c] < 0)) a.out[b0 + c] = e;
         }
     }
 }
@@ -1510,8 +1539,8 @@ static int launch_frame(const FrameArgs& a, int sm_count, cudaStream_t st) {
     return DMX_OK;
 }
 
-template <int CPB, int CSMODE>
-static int launch_frame32(const Frame32Args& a, int sm_count, cudaStream_t st) {
+template <int CPB, int CSMODE, bool VAR>
+static int launch_frame32_impl(const Frame32Args& a, int sm_count, cudaStream_t st) {
     const int NC = a.n_classes > 0 ? a.n_classes : 1;
     const size_t smem = (size_t)8 * CPB * NC * 16 + (size_t)8 * CPB * (SEG_MAXACT + 1) * 4 + 48 + (size_t)a.nseg * (32 * 16 + 32 + 4);
     if (smem > 200 * 1024) return fail(DMX_ERR_UNSUPPORTED, "frame32 kernel: tables do not fit shared memory");
@@ -1520,19 +1549,24 @@ static int launch_frame32(const Frame32Args& a, int sm_count, cudaStream_t st) {
     {
         std::lock_guard<std::mutex> lock(mu);
         if (smem > configured) {
-            CUDA_TRY(cudaFuncSetAttribute(dmx_frame32_kernel<CPB, CSMODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max(smem, (size_t)48 * 1024)));
+            CUDA_TRY(cudaFuncSetAttribute(dmx_frame32_kernel<CPB, CSMODE, VAR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max(smem, (size_t)48 * 1024)));
             configured = std::max(smem, (size_t)48 * 1024);
         }
     }
     const long long groups = (a.batch + CPB - 1) / CPB;
     int per_sm = 0;
-    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, dmx_frame32_kernel<CPB, CSMODE>, 256, smem));
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, dmx_frame32_kernel<CPB, CSMODE, VAR>, 256, smem));
     per_sm = std::max(per_sm, 1);
     const int grid = (int)std::max<long long>(1, std::min<long long>((groups + 7) / 8, (long long)sm_count * per_sm));
-    dmx_frame32_kernel<CPB, CSMODE><<<grid, 256, smem, st>>>(a);
+    dmx_frame32_kernel<CPB, CSMODE, VAR><<<grid, 256, smem, st>>>(a);
     ++g_launches;
     CUDA_TRY(cudaGetLastError());
     return DMX_OK;
+}
+
+template <int CPB, int CSMODE>
+static int launch_frame32(const Frame32Args& a, int sm_count, cudaStream_t st) {
+    return a.variants ? launch_frame32_impl<CPB, CSMODE, true>(a, sm_count, st) : launch_frame32_impl<CPB, CSMODE, false>(a, sm_count, st);
 }
 
 static int g_seg_cpb = 8;
@@ -1557,7 +1591,7 @@ static int run_segment(Plan& p, DevPlan* d, long long batch, const double* param
     }
     const int mode = p.f_classes.empty() ? 0 : (p.f_single_class ? 1 : 2);
     int rc;
-    if (p.f32_n > 0 && g_frame32) {
+    if (p.f32_n > 0 && g_frame32 && p.n_slots < 4096 && p.nseg < 4095) {
         Frame32Args g{};
         g.nseg = p.nseg; g.n_params = p.n_params; g.n_slots = p.n_slots; g.n_classes = (int)p.f_classes.size(); g.batch = batch;
         g.w = d->g_w; g.partner = d->g_partner; g.cs_sel = d->g_cs_sel; g.classes = d->f_classes; g.init = d->g_init; g.eweight = d->g_ew;
