@@ -1,5 +1,7 @@
 """GPU tests of the reference-shaped call surface (QPU / CPU / IErrorMitigationManager / DensityMatrixSimulator /
 QP_QEM_lib) and of size-independent properties at BASELINE.json's full batch sizes."""
+import os
+
 import numpy as np
 import pytest
 
@@ -168,3 +170,75 @@ def test_full_size_properties():
     mask[hot.cpu().numpy()] = False
     assert np.all(ev[mask] == base) and abs(base - (-1.0559477031919418)) < TOL
     assert np.all(ev[~mask] == ev[0]) and abs(ev[0] - base) > 1e-6
+
+
+def _stored(name):
+    import json
+    with open(os.path.join(os.path.dirname(__file__), "golden", "classic_minimisation.json")) as fh:
+        return json.load(fh)["files"][name]
+
+
+def test_swap_similarity_experiment_reproduces_reference_stored_run():
+    """visual_testing.similarity_plot_swap_circuit(overwrite=True) through the drop-in manager on the GPU, against the
+    run the reference stored (SWAP_Similarity_P0.0001_R100_C10000: 100 x (noisy, mitigated) from 10 000 circuits)."""
+    from vqe_errormitigation_b200 import experiments as E
+    rec = _stored("SWAP_Similarity_P0.0001_R100_C10000")
+    # deterministic (density) form: the exact noisy value, to 1e-10 of the oracle's (tests/test_oracle.py pins it at 0.45602391)
+    np.random.seed(11)
+    d = E.similarity_swap_circuit(prob=1e-4, measure_count=2, identifier_count=10000, density_representation=True)
+    assert abs(d.mu_ideal - 0.5) < 1e-12
+    # (the density branch traces against kron(eye, Z): Z on the LAST qubit - reference error_mitigation.py:381, SURVEY B.2)
+    q = cirq.LineQubit.range(7)
+    gates = [g for g in O.from_circuit(Q.swap_circuit(3, q, True), q)[1] if g[0] == "u"]
+    p = 1e-4
+    probs = O.probabilities(O.simulate(7, O.with_noise(gates, [O.asymmetric_depolarize(p, p, 6 * p)], [O.two_qubit_pauli_channel(p, p, 6 * p)])))
+    z_last = float(probs[0::2].sum() - probs[1::2].sum())
+    assert max(abs(v - z_last) for v in d.data_noisy.get_data) < TOL
+    assert abs(d.data_mitigated.get_mean - 0.5) < 0.02
+    # sampled form, as stored: same mean and same spread
+    reps = 40
+    d = E.similarity_swap_circuit(prob=1e-4, measure_count=reps, identifier_count=10000)
+    for got, ref in ((d.data_noisy, rec["data_noisy"]), (d.data_mitigated, rec["data_mitigated"])):
+        se = np.hypot(ref["std"] / np.sqrt(ref["n"]), ref["std"] / np.sqrt(reps))
+        assert abs(got.get_mean - ref["mean"]) < 4 * se, (got.get_mean, ref["mean"], se)
+        assert 0.6 * ref["std"] < got.get_std < 1.6 * ref["std"], (got.get_std, ref["std"])
+    assert abs(d.data_mitigated.get_mean - 0.5) < abs(d.data_noisy.get_mean - 0.5) / 4
+
+
+def test_hydrogen_similarity_experiment_against_reference_stored_run():
+    """visual_testing.similarity_plot_hydrogen_circuit(overwrite=True): per repetition a 10-iteration, 10 000-shot
+    COBYLA run on the noisy ansatz, then noisy / mitigated sampled energies from 10 000 // 5 identifier circuits.
+    Stored: noisy -1.02701 (sigma 0.0080), mitigated -1.13234 (sigma 0.0152), 100 repetitions.  The optimiser in the
+    loop is scipy's COBYLA (reference: scipy 1.5.2, here a later release), so the band is 5 combined standard errors."""
+    from vqe_errormitigation_b200 import experiments as E
+    rec = _stored("H2_Similarity_P0.0001_R100_C10000")
+    np.random.seed(12)
+    reps = 30
+    d = E.similarity_hydrogen_circuit(prob=1e-4, measure_count=reps, identifier_count=10000)
+    for got, ref in ((d.data_noisy, rec["data_noisy"]), (d.data_mitigated, rec["data_mitigated"])):
+        se = np.hypot(ref["std"] / np.sqrt(ref["n"]), ref["std"] / np.sqrt(reps))
+        assert abs(got.get_mean - ref["mean"]) < 5 * se, (got.get_mean, ref["mean"], se)
+        assert 0.5 * ref["std"] < got.get_std < 2.0 * ref["std"], (got.get_std, ref["std"])
+    assert abs(d.data_mitigated.get_mean - d.mu_ideal) < abs(d.data_noisy.get_mean - d.mu_ideal) / 4
+
+
+def test_calculate_minimisation_driver_end_to_end(tmp_path, monkeypatch):
+    """calculate_minimisation.__main__ (reference :74-88) on a reduced budget: containers written in the reference's
+    jsonpickle format and read back."""
+    from vqe_errormitigation_b200 import calculate_minimisation as CM
+    from vqe_errormitigation_b200 import experiments as E
+    from vqe_errormitigation_b200.data_containers.helper_interfaces.i_collection import IMeasurementCollection
+    monkeypatch.setattr(CM, "DATA_DIR", str(tmp_path / "classic_minimisation"))
+    monkeypatch.setattr(CM, "CPU_ITER", 3)
+    monkeypatch.setattr(CM, "QPU_ITER", 2000)
+    np.random.seed(5)
+    noise_space = [E.asymmetric_pauli_noise_model(p) for p in (0.0, 1e-4)]
+    collection = IMeasurementCollection(w=HydrogenAnsatz(), p_space=[.7414, 0.8], n_space=noise_space)
+    CM.calculate_and_write_collection(collection=collection, filename="H2_temptest6")
+    text = open(tmp_path / "classic_minimisation" / "H2_temptest6").read()
+    assert '"py/object": "src.data_containers.helper_interfaces.i_collection.IContainer"' in text
+    back = CM.read_object("H2_temptest6")
+    assert len(back) == 4 and [c.molecule_param for c in back] == [.7414, 0.8, .7414, 0.8]
+    assert abs(back[0].fci_value - (-1.1372701746571037)) < 1e-12 and abs(back[1].fci_value - (-1.13414767)) < 1e-8
+    for c in back:
+        assert len(c._optimized_exp_values) == 3 and -1.25 < c.measured_value < -0.95

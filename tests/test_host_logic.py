@@ -58,11 +58,15 @@ def test_circuit_earliest_strategy_value_equality_and_resolution():
 
 
 def test_cswap_decomposition_is_unitary_equivalent():
-    q = cirq.LineQubit.range(3)
-    dec = cirq.Circuit(cirq.CSWAP(q[0], q[1], q[2])._decompose_()).unitary()
-    want = cirq.unitary(cirq.CSWAP)
-    phase = dec[0, 0] / want[0, 0]
-    assert np.allclose(dec, phase * want)
+    # (control, target, target) positions -> form cirq 0.8.2 picks by adjacency, gate count
+    for xs, count in (((0, 1, 2), 21), ((0, 1, 4), 24), ((0, 2, 3), 21), ((0, 3, 6), 24), ((1, 0, 2), 24), ((5, 1, 2), 21)):
+        q = [cirq.LineQubit(x) for x in xs]
+        ops = cirq.CSWAP(*q)._decompose_()
+        assert len(ops) == count and all(len(op.qubits) <= 2 for op in ops)
+        dec = cirq.Circuit(ops).unitary()
+        want = cirq.Circuit([cirq.CSWAP(*q)]).unitary()
+        k = np.argmax(np.abs(want))
+        assert np.allclose(dec, dec.flat[k] / want.flat[k] * want)
 
 
 # ---- ansatz / noise construction ----------------------------------------------------------------------------------

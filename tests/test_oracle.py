@@ -166,3 +166,29 @@ def test_c_oracle_variants_match_numpy_oracle():
     got = CO.energy_batch(4, b.ops, b.pool(), terms, variants=rows, n_slots=122, threads=2)
     want = np.array([c["energy"] for c in gold["variant_cases"]])
     assert np.max(np.abs(got - want)) < 1e-13
+
+
+def test_swap_test_noisy_value_matches_reference_stored_run():
+    """The only reference-GENERATED noisy value without an optimiser in the loop: the 3+3-qubit SWAP test under
+    SingleQubit/TwoQubitPauliChannel(1e-4, 1e-4, 6e-4), 100 repetitions of 10 000 shots
+    (src/visual_testing.py:492-524 -> src/classic_minimisation/SWAP_Similarity_P0.0001_R100_C10000).  Its expectation
+    is <Z0> of the noisy circuit; the oracle's exact value must sit inside the stored run's standard error."""
+    import json
+    import os
+    from vqe_errormitigation_b200 import cirq_compat as cirq
+    from vqe_errormitigation_b200.qp_qem_lib import swap_circuit
+    q = cirq.LineQubit.range(7)
+    n, ops_all = O.from_circuit(swap_circuit(3, q, True), q)
+    gates = [g for g in ops_all if g[0] == "u"]          # get_updated_circuit puts no noise after the measurement (:540-543)
+    assert sum(len(g[1]) == 2 for g in gates) == 38 and sum(len(g[1]) == 1 for g in gates) == 39   # 3 x 24 + 5
+    p = 1e-4
+    ops = O.with_noise(gates, [O.asymmetric_depolarize(p, p, 6 * p)], [O.two_qubit_pauli_channel(p, p, 6 * p)])
+    probs = O.probabilities(O.simulate(n, ops))
+    z0 = float(probs[:64].sum() - probs[64:].sum())
+    assert abs(z0 - 0.45602390888719) < 1e-12
+    with open(os.path.join(os.path.dirname(__file__), "golden", "classic_minimisation.json")) as fh:
+        rec = json.load(fh)["files"]["SWAP_Similarity_P0.0001_R100_C10000"]["data_noisy"]
+    standard_error = rec["std"] / np.sqrt(rec["n"])
+    assert abs(z0 - rec["mean"]) < standard_error          # 0.456024 vs 0.456066 +- 0.00085
+    ideal = O.probabilities(O.simulate(n, gates))
+    assert abs(float(ideal[:64].sum() - ideal[64:].sum()) - 0.5) < 1e-13

@@ -27,9 +27,13 @@ class IContainer:
         self._molecular_parameter = m_param
 
     def get_measured_eigenvalue(self) -> float:
+        if not hasattr(self, "_optimized_exp_values"):      # files stored with the reference's earlier schema
+            return self._measured_eigenvalue                 # (src/classic_minimisation/H2_{bitflip,depolar}_*, H2_*semi*)
         return mean(self._optimized_exp_values)
 
     def get_measured_standard_deviation(self) -> float:
+        if not hasattr(self, "_optimized_exp_values"):
+            return getattr(self, "_measured_standard_deviation", 0)
         return stdev(self._optimized_exp_values) if len(self._optimized_exp_values) >= 2 else 0
 
     def get_fci_value(self) -> float:
