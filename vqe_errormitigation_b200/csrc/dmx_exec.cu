@@ -596,6 +596,7 @@ __global__ void __launch_bounds__(256) dmx_frame_kernel(const FrameArgs a) {
 // ---------------------------------------------------------------------------------------------------------
 struct Frame32Args {
     int nseg, n_params, n_slots, n_classes;
+    int any_const;                // some segment has cs_sel < 0
     long long batch;
     const double2* w;             // [nseg][32] (w0, w1)
     const unsigned char* partner; // [nseg][32] partner lane | 0x80 (rotation moves this coefficient)
@@ -627,20 +628,26 @@ __device__ __noinline__ double frame32_variant_factor(const SlotDev* __restrict_
 }
 
 // VAR = false: plain parameter sweeps (no variant code, fewer registers); VAR = true: QP variant rows.
+#ifndef DMX_F32_MINB
+#define DMX_F32_MINB 4       // 64 registers (no spills): four 256-thread CTAs per SM
+#endif
 template <int CPB, int CSMODE, bool VAR>
-__global__ void __launch_bounds__(256) dmx_frame32_kernel(const Frame32Args a) {
+__global__ void __launch_bounds__(256, DMX_F32_MINB) dmx_frame32_kernel(const Frame32Args a) {
     const int NC = a.n_classes > 0 ? a.n_classes : 1;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    // per-warp shared memory: (cos, sin) table for CSMODE 2, active variant entries
-    double2* cs = reinterpret_cast<double2*>(dmx_smem) + (size_t)warp * CPB * NC;
-    unsigned* act = reinterpret_cast<unsigned*>(reinterpret_cast<double2*>(dmx_smem) + (size_t)8 * CPB * NC) + (size_t)warp * CPB * (SEG_MAXACT + 1);
+    // Shared memory, carved by byte offsets from the one __shared__ base (no integer round trip on the pointers: the
+    // compiler must keep the address space, or every table read in the segment loop becomes a generic LD):
+    //   [0, A)  per-warp (cos, sin) table for CSMODE 2;  [A, B)  per-warp active variant entries + counts;
+    //   [B', ..) segment tables, staged once per CTA (every warp walks them for every circuit group)
+    unsigned char* const smem_base = reinterpret_cast<unsigned char*>(dmx_smem);
+    const unsigned off_act = 8u * CPB * NC * 16u;
+    const unsigned off_sw = (off_act + 8u * CPB * (SEG_MAXACT + 1) * 4u + 15u) & ~15u;
+    double2* cs = reinterpret_cast<double2*>(smem_base) + (size_t)warp * CPB * NC;
+    unsigned* act = reinterpret_cast<unsigned*>(smem_base + off_act) + (size_t)warp * CPB * (SEG_MAXACT + 1);
     int* nact = reinterpret_cast<int*>(act + CPB * SEG_MAXACT);
-    // segment tables -> shared memory once per CTA (every warp walks them for every circuit group)
-    double2* sw = reinterpret_cast<double2*>(reinterpret_cast<unsigned*>(reinterpret_cast<double2*>(dmx_smem) + (size_t)8 * CPB * NC) +
-                                             (size_t)8 * CPB * (SEG_MAXACT + 1) + 4);
-    sw = reinterpret_cast<double2*>((reinterpret_cast<uintptr_t>(sw) + 15) & ~(uintptr_t)15);
-    unsigned char* spart = reinterpret_cast<unsigned char*>(sw + (size_t)a.nseg * 32);
-    int* ssel = reinterpret_cast<int*>(spart + (size_t)a.nseg * 32);
+    double2* sw = reinterpret_cast<double2*>(smem_base + off_sw);
+    unsigned char* spart = smem_base + off_sw + (unsigned)a.nseg * 32u * 16u;
+    int* ssel = reinterpret_cast<int*>(smem_base + off_sw + (unsigned)a.nseg * 32u * 17u);
     for (int i = threadIdx.x; i < a.nseg * 32; i += 256) { sw[i] = a.w[i]; spart[i] = a.partner[i]; }
     for (int i = threadIdx.x; i < a.nseg; i += 256) ssel[i] = a.cs_sel[i];
     __syncthreads();
@@ -650,7 +657,12 @@ __global__ void __launch_bounds__(256) dmx_frame32_kernel(const Frame32Args a) {
     const double ew = a.eweight[lane];
     const int p = a.orig[lane] < 0 ? 0 : a.orig[lane];
 
-    for (long long grp = gwarp; grp < ngroups; grp += nwarps) {
+    // Every warp runs the same number of rounds (rows past the batch are predicated off at the loads and stores): with a
+    // trip count that depends only on kernel parameters the compiler can prove the warp converged and emits bare SHFLs
+    // (a warp-index-dependent bound costs a WARPSYNC + ENDCOLLECTIVE around every 64-bit shuffle).
+    const long long rounds = (ngroups + nwarps - 1) / nwarps;
+    for (long long it = 0; it < rounds; ++it) {
+        const long long grp = gwarp + it * nwarps;
         const long long b0 = grp * CPB;
         double2 csr[CPB];
         if (CSMODE == 1) {
@@ -736,6 +748,10 @@ __global__ void __launch_bounds__(256) dmx_frame32_kernel(const Frame32Args a) {
 #pragma unroll
         for (int c = 0; c < CPB; ++c) r[c] = init;
 
+        int sel_n = -1;
+        double2 wk_n = make_double2(1.0, 0.0);
+        unsigned pb_n = 0u;
+        if (a.nseg > 0) { sel_n = ssel[0]; wk_n = sw[lane]; pb_n = spart[lane]; }
         for (int k = 0; k <= a.nseg; ++k) {
             if (VAR && ((stage_any >> (k < 31 ? k : 31)) & 1u)) {
 #pragma unroll
@@ -748,34 +764,59 @@ __global__ void __launch_bounds__(256) dmx_frame32_kernel(const Frame32Args a) {
                 }
             }
             if (k == a.nseg) break;
-            const int sel = ssel[k];
-            const double2 wk = sw[k * 32 + lane];
-            const unsigned pb = spart[k * 32 + lane];
+            const int sel = sel_n;
+            const double2 wk = wk_n;
+            const unsigned pb = pb_n;
+            {   // tables of the next segment: in flight while this one computes
+                const int kn = k + 1 < a.nseg ? k + 1 : k;
+                sel_n = ssel[kn]; wk_n = sw[kn * 32 + lane]; pb_n = spart[kn * 32 + lane];
+            }
             const bool active = pb & 0x80u;
             const int src = pb & 31u;
-            if (sel < 0) {          // constant-coefficient segment (resolved rotation): weights carry cos / sin already
+            // sel < 0: constant-coefficient segment (resolved rotation) - the weights carry cos / sin already.  The test
+            // on `sel` (shared-memory data) must not become a branch around the shuffles, see `rounds` above: plans
+            // without such segments (a.any_const == 0, kernel parameter) skip it, the others use selects.
+            if (!a.any_const) {
 #pragma unroll
                 for (int c = 0; c < CPB; ++c) {
                     const double other = __shfl_sync(0xffffffffu, r[c], src);
-                    r[c] = wk.x * r[c] + wk.y * other;
-                }
-            } else {
-#pragma unroll
-                for (int c = 0; c < CPB; ++c) {
-                    const double other = __shfl_sync(0xffffffffu, r[c], src);
-                    const double2 v = CSMODE == 1 ? csr[c] : cs[c * NC + sel];
+                    const double2 v = CSMODE == 1 ? csr[c] : (CSMODE == 2 ? cs[c * NC + sel] : make_double2(1.0, 1.0));
                     const double cm = active ? v.x : 1.0;
                     r[c] = cm * (wk.x * r[c]) + v.y * (wk.y * other);
                 }
+            } else {
+                const bool rot = sel >= 0;
+#pragma unroll
+                for (int c = 0; c < CPB; ++c) {
+                    const double other = __shfl_sync(0xffffffffu, r[c], src);
+                    const double2 v = CSMODE == 1 ? csr[c] : (CSMODE == 2 ? cs[c * NC + (rot ? sel : 0)] : make_double2(1.0, 1.0));
+                    const double cm = (rot && active) ? v.x : 1.0, sm = rot ? v.y : 1.0;
+                    r[c] = cm * (wk.x * r[c]) + sm * (wk.y * other);
+                }
             }
         }
-        // energy: fixed butterfly over the 32 lanes (deterministic), lane c writes circuit c
+        // energy: transposed butterfly in a fixed order (deterministic).  Each step halves the number of circuits a lane
+        // carries: after offsets 16 / 8 / 4 the lane holds the partial sum of circuit (lane >> 2) (CPB = 8) over its 8-lane
+        // class, offsets 2 / 1 finish it; CPB - 1 + 2 shuffles instead of 5 CPB.
+        {
+            double e[CPB];
 #pragma unroll
-        for (int c = 0; c < CPB; ++c) {
-            double e = ew * r[c];
+            for (int c = 0; c < CPB; ++c) e[c] = ew * r[c];
+            int off = 16;
 #pragma unroll
-            for (int off = 16; off > 0; off >>= 1) e += __shfl_xor_sync(0xffffffffu, e, off);
-            if (lane == c && b0 + c < a.batch && !(VAR && nact[c] < 0)) a.out[b0 + c] = e;
+            for (int m = CPB / 2; m >= 1; m >>= 1, off >>= 1) {
+                const bool hi = lane & off;
+#pragma unroll
+                for (int j = 0; j < m; ++j) {
+                    const double keep = hi ? e[j + m] : e[j], send = hi ? e[j] : e[j + m];
+                    e[j] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+                }
+            }
+#pragma unroll
+            for (; off > 0; off >>= 1) e[0] += __shfl_xor_sync(0xffffffffu, e[0], off);
+            constexpr int LPC = 32 / CPB;           // lanes per circuit after the halving steps
+            const int c = lane / LPC;
+            if ((lane & (LPC - 1)) == 0 && b0 + c < a.batch && !(VAR && nact[c] < 0)) a.out[b0 + c] = e[0];
         }
     }
 }
@@ -1553,11 +1594,10 @@ static int launch_frame32_impl(const Frame32Args& a, int sm_count, cudaStream_t 
             configured = std::max(smem, (size_t)48 * 1024);
         }
     }
+    // one CTA per 8 circuit groups, no occupancy cap: measured faster than a persistent grid (H2 sweep 18.7 vs 20.6 us per
+    // 65 536 circuits) - the hardware scheduler balances the tail, and re-staging the 4 KB segment tables per CTA is cheap
     const long long groups = (a.batch + CPB - 1) / CPB;
-    int per_sm = 0;
-    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, dmx_frame32_kernel<CPB, CSMODE, VAR>, 256, smem));
-    per_sm = std::max(per_sm, 1);
-    const int grid = (int)std::max<long long>(1, std::min<long long>((groups + 7) / 8, (long long)sm_count * per_sm));
+    const int grid = (int)std::max<long long>(1, std::min<long long>((groups + 7) / 8, 0x7fffffffLL));
     dmx_frame32_kernel<CPB, CSMODE, VAR><<<grid, 256, smem, st>>>(a);
     ++g_launches;
     CUDA_TRY(cudaGetLastError());
@@ -1597,6 +1637,8 @@ static int run_segment(Plan& p, DevPlan* d, long long batch, const double* param
         g.w = d->g_w; g.partner = d->g_partner; g.cs_sel = d->g_cs_sel; g.classes = d->f_classes; g.init = d->g_init; g.eweight = d->g_ew;
         g.orig = d->g_orig; g.params = params; g.variants = variants; g.slots = d->slots; g.labels = d->labels; g.coefs = d->coefs;
         g.out = out; g.worklist = a.worklist; g.work_count = a.work_count;
+        g.any_const = 0;
+        for (int k = 0; k < p.nseg; ++k) g.any_const |= p.fsegs[k].cs_sel < 0;
         if (g_seg_cpb == 4)
             rc = mode == 0 ? launch_frame32<4, 0>(g, d->sm_count, st) : mode == 1 ? launch_frame32<4, 1>(g, d->sm_count, st) : launch_frame32<4, 2>(g, d->sm_count, st);
         else
