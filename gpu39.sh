@@ -1,0 +1,1 @@
+python tools/qem_breakdown.py 2>&1 | tail -6

@@ -178,10 +178,18 @@ int dmx_qp_reduce(const double* d_values, const double* d_weights, const int32_t
  * (src/error_mitigation.py:309-335: per gate np.random.choice(len(qp), p=|qp|/sum|qp|); sign = sign prod qp[idx],
  * :321-323) and IErrorMitigationManager.set_identifier_range (:484-489) when 1e5..1e6 samples are wanted.
  * qp [n_slots][stride] (host): the quasi-probabilities of every gate slot, n_choices[s] <= min(stride, 256) valid
- * entries per row.  RNG: Philox4x32-10, counter (sample, slot), key = seed; sample b of this call is global sample
- * first_sample + b, so ranks drawing disjoint ranges of one stream need no communication.
- * d_variants [batch][n_slots] uint8, d_signs [batch] in {-1, 0, +1}.  Statistical (not bitwise) parity with numpy's
- * generator; bit-exact against the numpy Philox restatement in tests/philox_ref.py. */
+ * entries per row.  RNG: Philox4x32-10, counter (sample lo, sample hi, slot / 4, 0), key = seed; slot s takes word
+ * s % 4 of the call as u = (word + 0.5) / 2^32 and draws the first index whose cumulative |qp| / sum|qp| exceeds u.
+ * Sample b of a call is global sample first_sample + b, so ranks drawing disjoint ranges of one stream need no
+ * communication.  d_variants [batch][n_slots] uint8, d_signs [batch] in {-1, 0, +1}.  Statistical (not bitwise)
+ * parity with numpy's generator; bit-exact against the numpy Philox restatement in tests/philox_ref.py.
+ * dmx_qp_sampler_create uploads the tables once (current device); dmx_qp_sampler_draw is one kernel launch on
+ * `stream`; dmx_qp_sample_variants = create + draw + synchronise + destroy. */
+typedef struct dmx_qp_sampler dmx_qp_sampler;
+int dmx_qp_sampler_create(int n_slots, const int32_t* n_choices, const double* qp, int stride, dmx_qp_sampler** out);
+int dmx_qp_sampler_draw(const dmx_qp_sampler* sampler, uint64_t seed, uint64_t first_sample, int64_t batch,
+                        uint8_t* d_variants, double* d_signs, void* stream);
+void dmx_qp_sampler_destroy(dmx_qp_sampler* sampler);
 int dmx_qp_sample_variants(int n_slots, const int32_t* n_choices, const double* qp, int stride, uint64_t seed,
                            uint64_t first_sample, int64_t batch, uint8_t* d_variants, double* d_signs, void* stream);
 

@@ -1,5 +1,6 @@
 """numpy restatement of the engine's variant sampler (dmx_qp_sample_kernel): Philox4x32-10 with counter
-(sample lo, sample hi, slot, 0) and key = seed, u = top 53 bits / 2^53, idx = first cdf entry > u.  Test infrastructure."""
+(sample lo, sample hi, slot // 4, 0) and key = seed; slot s takes word s % 4 as u = (word + 0.5) / 2^32,
+idx = first cdf entry > u.  Test infrastructure."""
 import numpy as np
 
 M0, M1 = np.uint64(0xD2511F53), np.uint64(0xCD9E8D57)
@@ -24,10 +25,12 @@ def sample_variants(qps, batch, seed, first_sample=0):
     rows = np.zeros((batch, S), np.uint8)
     neg = np.zeros(batch, np.int64)
     zero = np.zeros(batch, bool)
+    words = None
     for s, qp in enumerate(qps):
         qp = np.asarray(qp, np.float64)
-        r0, r1, _, _ = philox4x32_10(g & MASK, g >> np.uint64(32), np.full(batch, s, np.uint64), np.zeros(batch, np.uint64), seed)
-        u = (((r0 << np.uint64(32)) | r1) >> np.uint64(11)).astype(np.float64) * (1.0 / 9007199254740992.0)
+        if s % 4 == 0:
+            words = philox4x32_10(g & MASK, g >> np.uint64(32), np.full(batch, s // 4, np.uint64), np.zeros(batch, np.uint64), seed)
+        u = (words[s % 4].astype(np.float64) + 0.5) * (1.0 / 4294967296.0)
         total = np.sum(np.abs(qp))
         acc, cdf = 0.0, np.empty(len(qp))
         for i, v in enumerate(np.abs(qp)):      # same accumulation order as the C code

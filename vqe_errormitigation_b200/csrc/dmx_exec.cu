@@ -974,29 +974,53 @@ __device__ __forceinline__ void philox4x32_10(unsigned (&c)[4], unsigned k0, uns
     }
 }
 
-__global__ void dmx_qp_sample_kernel(int n_slots, const int* __restrict__ n_choices, const double* __restrict__ cdf,
+// One warp per sample.  One Philox call serves FOUR consecutive gate slots: counter (sample lo, sample hi, slot / 4, 0), key = seed,
+// slot s takes word s % 4 as u = (word + 0.5) / 2^32 and idx = first cdf entry > u (cdf[last] = 1).  Entry 0 (the identity
+// correction, probability ~ 1 - O(p)) is tested first; only the rare other draws run the binary search.
+__global__ void __launch_bounds__(256) dmx_qp_sample_kernel(int n_slots, const int* __restrict__ n_choices, const double* __restrict__ cdf,
                                      const unsigned char* __restrict__ sgn /* 0: +, 1: -, 2: zero */, int stride,
+                                     const double2* __restrict__ cdf0 /* [ceil(S/4)*2]: first cdf entry of every slot (padding: 2.0) */,
+                                     const unsigned* __restrict__ sgn0 /* [ceil(S/4)]: sign code of entry 0, 4 slots per word */,
                                      unsigned long long seed, unsigned long long first_sample, long long batch,
                                      unsigned char* __restrict__ variants, double* __restrict__ signs) {
     const int lane = threadIdx.x & 31;
     const long long b = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (b >= batch) return;
     const unsigned long long gidx = first_sample + (unsigned long long)b;
+    unsigned char* const out = variants + b * n_slots;
+    const bool aligned = ((b * n_slots) & 3) == 0;
     int neg = 0, zero = 0;
-    for (int s = lane; s < n_slots; s += 32) {
-        unsigned c[4] = {(unsigned)gidx, (unsigned)(gidx >> 32), (unsigned)s, 0u};
+    for (int g = lane; 4 * g < n_slots; g += 32) {
+        unsigned c[4] = {(unsigned)gidx, (unsigned)(gidx >> 32), (unsigned)g, 0u};
         philox4x32_10(c, (unsigned)seed, (unsigned)(seed >> 32));
-        const double u = (double)((((unsigned long long)c[0] << 32) | c[1]) >> 11) * (1.0 / 9007199254740992.0);
-        const double* __restrict__ row = cdf + (size_t)s * stride;
-        int lo = 0, hi = n_choices[s] - 1;          // first index with row[idx] > u (row[last] = 1)
-        while (lo < hi) {
-            const int mid = (lo + hi) >> 1;
-            if (row[mid] > u) hi = mid; else lo = mid + 1;
+        // entry 0 of the four slots from the compact tables (coalesced); the full rows (stride apart) only for other draws
+        const double2 fa = cdf0[2 * g], fb = cdf0[2 * g + 1];
+        const double first[4] = {fa.x, fa.y, fb.x, fb.y};
+        const unsigned s0 = sgn0[g];
+        unsigned packed = 0u;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int s = 4 * g + i;
+            const double u = ((double)c[i] + 0.5) * (1.0 / 4294967296.0);
+            int sg = (s0 >> (8 * i)) & 255u;
+            if (!(first[i] > u)) {             // never for the padding slots (first = 2)
+                const double* __restrict__ row = cdf + (size_t)s * stride;
+                int hi = n_choices[s] - 1, lo = hi > 0 ? 1 : 0;
+                while (lo < hi) {
+                    const int mid = (lo + hi) >> 1;
+                    if (row[mid] > u) hi = mid; else lo = mid + 1;
+                }
+                packed |= (unsigned)lo << (8 * i);
+                sg = sgn[(size_t)s * stride + lo];
+            }
+            neg ^= sg == 1;
+            zero |= sg == 2;
         }
-        variants[b * n_slots + s] = (unsigned char)lo;
-        const int sg = sgn[(size_t)s * stride + lo];
-        neg ^= sg == 1;
-        zero |= sg == 2;
+        if (aligned && 4 * g + 3 < n_slots) {
+            *reinterpret_cast<unsigned*>(out + 4 * g) = packed;
+        } else {
+            for (int i = 0; i < 4 && 4 * g + i < n_slots; ++i) out[4 * g + i] = (unsigned char)(packed >> (8 * i));
+        }
     }
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) {
@@ -1005,6 +1029,13 @@ __global__ void dmx_qp_sample_kernel(int n_slots, const int* __restrict__ n_choi
     }
     if (lane == 0) signs[b] = zero ? 0.0 : (neg ? -1.0 : 1.0);
 }
+
+// device tables of a QP sampler (dmx_qp_sampler_create): [cdf | first cdf entries | n_choices | first sign codes | sign codes]
+struct dmx_qp_sampler {
+    int n_slots = 0, stride = 0, device = -1;
+    char* d = nullptr;
+    size_t cb = 0, fb = 0, nb = 0, gb = 0;
+};
 
 // ---------------------------------------------------------------------------------------------------------
 // device mirror of a plan
@@ -1892,9 +1923,8 @@ int dmx_qp_reduce(const double* d_values, const double* d_weights, const int32_t
     return DMX_OK;
 }
 
-int dmx_qp_sample_variants(int n_slots, const int32_t* n_choices, const double* qp, int stride, uint64_t seed, uint64_t first_sample,
-                           int64_t batch, uint8_t* d_variants, double* d_signs, void* stream) {
-    if (n_slots < 1 || !n_choices || !qp || stride < 1 || batch < 0 || !d_variants || !d_signs) return fail(DMX_ERR_INVALID, "bad arguments");
+int dmx_qp_sampler_create(int n_slots, const int32_t* n_choices, const double* qp, int stride, dmx_qp_sampler** out) {
+    if (n_slots < 1 || !n_choices || !qp || stride < 1 || !out) return fail(DMX_ERR_INVALID, "bad arguments");
     std::vector<double> cdf((size_t)n_slots * stride, 1.0);
     std::vector<unsigned char> sg((size_t)n_slots * stride, 0);
     for (int s = 0; s < n_slots; ++s) {
@@ -1911,23 +1941,65 @@ int dmx_qp_sample_variants(int n_slots, const int32_t* n_choices, const double* 
             sg[(size_t)s * stride + i] = row[i] == 0.0 ? 2 : (row[i] < 0.0 ? 1 : 0);
         }
     }
+    const int groups = (n_slots + 3) / 4;
+    std::vector<double> first((size_t)groups * 4, 2.0);
+    std::vector<unsigned char> sg0((size_t)groups * 4, 0);
+    for (int s = 0; s < n_slots; ++s) { first[s] = cdf[(size_t)s * stride]; sg0[s] = sg[(size_t)s * stride]; }
+    auto* sm = new dmx_qp_sampler();
+    sm->n_slots = n_slots; sm->stride = stride;
+    sm->cb = cdf.size() * 8; sm->fb = first.size() * 8; sm->nb = (size_t)n_slots * 4; sm->gb = sg0.size();
+    sm->nb = (sm->nb + 15) & ~(size_t)15;
+    if (cudaGetDevice(&sm->device) != cudaSuccess || cudaMalloc((void**)&sm->d, sm->cb + sm->fb + sm->nb + sm->gb + sg.size()) != cudaSuccess ||
+        cudaMemcpy(sm->d, cdf.data(), sm->cb, cudaMemcpyHostToDevice) != cudaSuccess ||
+        cudaMemcpy(sm->d + sm->cb, first.data(), sm->fb, cudaMemcpyHostToDevice) != cudaSuccess ||
+        cudaMemcpy(sm->d + sm->cb + sm->fb, n_choices, (size_t)n_slots * 4, cudaMemcpyHostToDevice) != cudaSuccess ||
+        cudaMemcpy(sm->d + sm->cb + sm->fb + sm->nb, sg0.data(), sm->gb, cudaMemcpyHostToDevice) != cudaSuccess ||
+        cudaMemcpy(sm->d + sm->cb + sm->fb + sm->nb + sm->gb, sg.data(), sg.size(), cudaMemcpyHostToDevice) != cudaSuccess) {
+        const cudaError_t e = cudaGetLastError();
+        if (sm->d) cudaFree(sm->d);
+        delete sm;
+        return fail(DMX_ERR_CUDA, std::string("dmx_qp_sampler_create: ") + cudaGetErrorString(e));
+    }
+    *out = sm;
+    return DMX_OK;
+}
+
+void dmx_qp_sampler_destroy(dmx_qp_sampler* sampler) {
+    if (!sampler) return;
+    if (sampler->d) cudaFree(sampler->d);
+    delete sampler;
+}
+
+int dmx_qp_sampler_draw(const dmx_qp_sampler* sm, uint64_t seed, uint64_t first_sample, int64_t batch, uint8_t* d_variants,
+                        double* d_signs, void* stream) {
+    if (!sm || batch < 0 || (batch > 0 && (!d_variants || !d_signs))) return fail(DMX_ERR_INVALID, "bad arguments");
     if (batch == 0) return DMX_OK;
-    cudaStream_t st = (cudaStream_t)stream;
-    const size_t cb = cdf.size() * 8, sb = sg.size(), nb = (size_t)n_slots * 4;
-    char* d = nullptr;
-    CUDA_TRY(cudaMallocAsync((void**)&d, cb + nb + sb, st));
-    // pageable sources: the copies complete with respect to the host before returning, so the vectors may go away
-    CUDA_TRY(cudaMemcpyAsync(d, cdf.data(), cb, cudaMemcpyHostToDevice, st));
-    CUDA_TRY(cudaMemcpyAsync(d + cb, n_choices, nb, cudaMemcpyHostToDevice, st));
-    CUDA_TRY(cudaMemcpyAsync(d + cb + nb, sg.data(), sb, cudaMemcpyHostToDevice, st));
+    int dev = -1;
+    CUDA_TRY(cudaGetDevice(&dev));
+    if (dev != sm->device) return fail(DMX_ERR_STATE, "sampler tables live on another device");
     const int threads = 256;
     const long long grid = (batch * 32 + threads - 1) / threads;
-    dmx_qp_sample_kernel<<<(unsigned)grid, threads, 0, st>>>(n_slots, (const int*)(d + cb), (const double*)d, (const unsigned char*)(d + cb + nb),
-                                                             stride, seed, first_sample, batch, d_variants, d_signs);
+    if (grid >= (1LL << 31)) return fail(DMX_ERR_UNSUPPORTED, "batch too large for one launch");
+    const char* base = sm->d;
+    dmx_qp_sample_kernel<<<(unsigned)grid, threads, 0, (cudaStream_t)stream>>>(
+        sm->n_slots, (const int*)(base + sm->cb + sm->fb), (const double*)base, (const unsigned char*)(base + sm->cb + sm->fb + sm->nb + sm->gb),
+        sm->stride, (const double2*)(base + sm->cb), (const unsigned*)(base + sm->cb + sm->fb + sm->nb), seed, first_sample, batch, d_variants,
+        d_signs);
     ++g_launches;
     CUDA_TRY(cudaGetLastError());
-    CUDA_TRY(cudaFreeAsync(d, st));
     return DMX_OK;
+}
+
+int dmx_qp_sample_variants(int n_slots, const int32_t* n_choices, const double* qp, int stride, uint64_t seed, uint64_t first_sample,
+                           int64_t batch, uint8_t* d_variants, double* d_signs, void* stream) {
+    if (batch < 0 || !d_variants || !d_signs) return fail(DMX_ERR_INVALID, "bad arguments");
+    dmx_qp_sampler* sm = nullptr;
+    int rc = dmx_qp_sampler_create(n_slots, n_choices, qp, stride, &sm);
+    if (rc) return rc;
+    rc = dmx_qp_sampler_draw(sm, seed, first_sample, batch, d_variants, d_signs, stream);
+    if (rc == DMX_OK && batch > 0 && cudaStreamSynchronize((cudaStream_t)stream) != cudaSuccess) rc = fail(DMX_ERR_CUDA, "sampler launch failed");
+    dmx_qp_sampler_destroy(sm);
+    return rc;
 }
 
 static bool is_pinned_host(const void* ptr) {

@@ -356,22 +356,49 @@ def pack_qp_tables(qps: Sequence[np.ndarray]) -> Tuple[np.ndarray, np.ndarray]:
     return table, n_choices
 
 
+class QpSampler:
+    """Device-resident sampling tables of one circuit's quasi-probabilities (``dmx_qp_sampler_create``): built once,
+    every ``draw`` is a single kernel launch."""
+
+    def __init__(self, qps):
+        _require_cuda()
+        self._lib = _lib.load()
+        table, n_choices = qps if isinstance(qps, tuple) else pack_qp_tables(qps)
+        table = np.ascontiguousarray(table, np.float64)
+        n_choices = np.ascontiguousarray(n_choices, np.int32)
+        self.n_slots, stride = table.shape
+        handle = C.c_void_p()
+        check(self._lib.dmx_qp_sampler_create(self.n_slots, n_choices.ctypes.data_as(C.POINTER(C.c_int32)),
+                                              table.ctypes.data_as(C.POINTER(C.c_double)), stride, C.byref(handle)))
+        self._handle = handle
+
+    def draw(self, batch: int, seed: int, first_sample: int = 0):
+        """(variants uint8 [batch, S], signs float64 [batch]) CUDA tensors; sample b is global sample first_sample + b."""
+        torch = _require_cuda()
+        dev = torch.device("cuda", torch.cuda.current_device())
+        variants = torch.empty((batch, self.n_slots), dtype=torch.uint8, device=dev)
+        signs = torch.empty(batch, dtype=torch.float64, device=dev)
+        stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+        check(self._lib.dmx_qp_sampler_draw(self._handle, C.c_uint64(seed), C.c_uint64(first_sample), batch,
+                                            C.c_void_p(variants.data_ptr()), C.c_void_p(signs.data_ptr()), stream))
+        return variants, signs
+
+    def __del__(self):
+        handle, self._handle = getattr(self, "_handle", None), None
+        if handle:
+            try:
+                self._lib.dmx_qp_sampler_destroy(handle)
+            except Exception:  # noqa: BLE001 - interpreter shutdown
+                pass
+
+
 def qp_sample_variants(qps, batch: int, seed: int, first_sample: int = 0):
-    """Draw ``batch`` QP circuit variants on the device (``dmx_qp_sample_variants``): per gate slot an index with
-    probability |qp|/sum|qp| and the sample's sign — the device twin of QuasiCircuitIdentifier._get_identifiers
-    (reference error_mitigation.py:309-335).  Returns (variants uint8 [batch, S], signs float64 [batch]) CUDA tensors."""
-    torch = _require_cuda()
-    lib = _lib.load()
-    table, n_choices = qps if isinstance(qps, tuple) else pack_qp_tables(qps)
-    S, stride = table.shape
-    dev = torch.device("cuda", torch.cuda.current_device())
-    variants = torch.empty((batch, S), dtype=torch.uint8, device=dev)
-    signs = torch.empty(batch, dtype=torch.float64, device=dev)
-    stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
-    check(lib.dmx_qp_sample_variants(S, n_choices.ctypes.data_as(C.POINTER(C.c_int32)), table.ctypes.data_as(C.POINTER(C.c_double)),
-                                     stride, C.c_uint64(seed), C.c_uint64(first_sample), batch, C.c_void_p(variants.data_ptr()),
-                                     C.c_void_p(signs.data_ptr()), stream))
-    return variants, signs
+    """Draw ``batch`` QP circuit variants on the device: per gate slot an index with probability |qp|/sum|qp| and the
+    sample's sign — the device twin of QuasiCircuitIdentifier._get_identifiers (reference error_mitigation.py:309-335).
+    ``qps``: list of quasi-probability vectors, a packed (table, n_choices) pair, or a :class:`QpSampler` (reuse it when
+    drawing repeatedly).  Returns (variants uint8 [batch, S], signs float64 [batch]) CUDA tensors."""
+    sampler = qps if isinstance(qps, QpSampler) else QpSampler(qps)
+    return sampler.draw(batch, seed, first_sample)
 
 
 def measure_fp64_peak() -> float:

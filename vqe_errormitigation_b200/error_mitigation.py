@@ -589,12 +589,13 @@ class IErrorMitigationManager:
         lo, hi = parallel.shard_bounds(int(count), rank, world_size)
         if getattr(self, "_sampler_cache", None) is None:
             qps = self._qp_matrix()
-            self._sampler_cache = (engine.pack_qp_tables(qps), float(np.prod([np.sum(np.abs(qp)) for qp in qps])))
-        tables, scale = self._sampler_cache
+            self._sampler_cache = (engine.QpSampler(qps), float(np.prod([np.sum(np.abs(qp)) for qp in qps])))
+        sampler, scale = self._sampler_cache
         prog = self._variant_program()
-        variants, signs = engine.qp_sample_variants(tables, hi - lo, seed, first_sample=lo)
+        variants, signs = sampler.draw(hi - lo, seed, first_sample=lo)
         values = prog.energies(None, variants, batch=hi - lo)
-        mean, var, n = parallel.sharded_mean(values, signs * scale)
+        mean, var, n = parallel.sharded_mean(values, signs)      # the circuit's total cost is one scalar: applied once here
+        mean, var = scale * mean, scale * scale * var
         return mean, float(np.sqrt(max(var, 0.0) / n)) if n else float("nan"), int(n)
 
     def __str__(self):
