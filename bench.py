@@ -534,7 +534,11 @@ def main():
         h2d = (params_h.nbytes if params_h is not None else 0) + (variants_h.nbytes if variants_h is not None else 0)
         e2e = {"value": world * B * args.steps / float(te.item()), "unit": UNIT, "h2d_bytes_per_step": int(h2d),
                "d2h_bytes_per_step": int(B * 8), "api": "dmx_energy_batch_host (CircuitProgram.energies_host)",
-               "checksum": float(np.sum(res))}
+               "checksum": float(np.sum(res)),
+               "transfer": ("zero-copy: the kernel reads the parameters from and writes the energies to the mapped page-locked host "
+                            "buffers over PCIe (one launch + one synchronise per step)"
+                            if prog.info["path"] == 1 and variants_h is None and not any(o.startswith("host_zero_copy=0") for o in args.opt)
+                            else "cudaMemcpyAsync H2D / D2H from and to the page-locked host buffers, pipelined in chunks over three streams")}
 
     # ---- QEM only: the same estimate with the variants drawn on the device (no variant table crosses PCIe) ----------
     if e2e is not None and wl.get("sampled_step"):

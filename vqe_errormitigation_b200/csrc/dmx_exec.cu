@@ -1426,6 +1426,7 @@ static int run_tile_single(Plan& p, DevPlan* d, long long batch, const double* p
     return launch_tile(a, grid, threads, gpt, smem, st);
 }
 
+static int g_host_zero_copy = 1;   // option "host_zero_copy": small-state plans read / write mapped page-locked host buffers in place
 static int64_t g_host_chunk_rows = 32768;   // option "host_chunk_rows": rows per pipeline chunk of dmx_energy_batch_host
 static int g_stream_kernel = 1;        // option "stream_kernel": 0 -> generic dmx_tile_kernel for every pass
 static long long g_stream_chunk = 0;   // option "stream_chunk": circuits per pass launch (0: auto, ~64 MiB of states stay in L2)
@@ -1747,6 +1748,8 @@ int dmx_plan_set_option(dmx_plan* plan, const char* key, int value) {
     } else if (k == "stream_chunk") {
         if (value < 0) return fail(DMX_ERR_INVALID, "stream_chunk must be >= 0");
         g_stream_chunk = value;
+    } else if (k == "host_zero_copy") {
+        g_host_zero_copy = value != 0;
     } else if (k == "host_chunk_rows") {
         if (value < 1024) return fail(DMX_ERR_INVALID, "host_chunk_rows must be >= 1024");
         g_host_chunk_rows = value;
@@ -2009,6 +2012,15 @@ static bool is_pinned_host(const void* ptr) {
     return at.type == cudaMemoryTypeHost;
 }
 
+// device-visible alias of a page-locked host buffer (nullptr when the buffer is pageable or not mapped)
+static void* mapped_alias(const void* ptr) {
+    if (!ptr) return nullptr;
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, ptr) != cudaSuccess) { (void)cudaGetLastError(); return nullptr; }
+    return at.type == cudaMemoryTypeHost ? at.devicePointer : nullptr;
+}
+
+
 // Host-buffer call.  The batch is cut into chunks that flow through three streams — H2D of chunk i+1, the kernels of chunk i
 // and the D2H of chunk i-1 overlap — so the call costs about max(copy in, compute, copy out) instead of their sum.  Buffers
 // that are already page-locked (cudaHostAlloc / cudaHostRegister, e.g. torch pinned tensors) are used in place; pageable
@@ -2029,6 +2041,21 @@ int dmx_energy_batch_host(dmx_plan* plan, int64_t batch, const double* h_params,
         for (int i = 0; i < DevPlan::MAX_CHUNKS; ++i) {
             CUDA_TRY(cudaEventCreateWithFlags(&d->ev_in[i], cudaEventDisableTiming));
             CUDA_TRY(cudaEventCreateWithFlags(&d->ev_k[i], cudaEventDisableTiming));
+        }
+    }
+    // Zero-copy: a parameter sweep on a register-resident plan moves 8 B in and 8 B out per circuit, so two DMA copies
+    // and their stream hand-offs cost more than the kernel.  With mapped page-locked buffers the kernel reads the parameters
+    // and writes the energies over PCIe itself: one launch, one synchronise.  (Variant tables - 1 byte per gate and row,
+    // read lane-strided - stay on the DMA pipeline below.)
+    if (g_host_zero_copy && p.path == 1 && !h_variants) {
+        double* const e_dev = (double*)mapped_alias(h_energy);
+        const double* const p_dev = h_params ? (const double*)mapped_alias(h_params) : nullptr;
+        if (e_dev && (p_dev || !h_params)) {
+            rc = energy_impl(plan, batch, p_dev, nullptr, e_dev, nullptr, 0, d->stream);
+            const cudaError_t e = cudaStreamSynchronize(d->stream);
+            if (rc) return rc;
+            CUDA_TRY(e);
+            return DMX_OK;
         }
     }
     const size_t prow = h_params ? (size_t)p.n_params * 8 : 0, vrow = h_variants ? (size_t)p.n_slots : 0;
