@@ -89,8 +89,20 @@ def test_batch_sizes_and_host_api():
     ap, out = engine.pinned_empty(a.shape), engine.pinned_empty(B)
     ap[...] = a
     out[...] = np.nan
-    res = prog.energies_host(ap, out=out)
-    assert res is out and np.max(np.abs(out - dev)) < 1e-13
+    res = prog.energies_host(ap, out=out)            # page-locked in and out: zero-copy (the kernel works on the mapped buffers)
+    assert res is out and np.array_equal(out, dev)
+    out[...] = np.nan                                 # page-locked out, pageable in: DMA pipeline
+    assert np.array_equal(prog.energies_host(a, out=out), dev)
+    dma, _ = h2_program(host_zero_copy=0)             # the option is library-wide: restore it before leaving
+    try:
+        out[...] = np.nan
+        assert np.array_equal(dma.energies_host(ap, out=out), dev)
+    finally:
+        h2_program(host_zero_copy=1)
+    for small in (1, 7):                              # ragged CTA tails through the zero-copy path
+        sp, so = engine.pinned_empty((small, 1)), engine.pinned_empty(small)
+        sp[...] = a[:small]
+        assert np.array_equal(prog.energies_host(sp, out=so), dev[:small])
 
 
 def random_unitary(rng, d):

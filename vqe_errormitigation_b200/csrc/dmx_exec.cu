@@ -939,11 +939,19 @@ __global__ void dmx_qp_reduce_stage1(const double* __restrict__ v, const double*
 }
 
 __global__ void dmx_qp_reduce_stage2(const double* __restrict__ partial, double* __restrict__ out3) {
-    if (threadIdx.x < 3) {
-        double t = 0.0;
-        for (int k = 0; k < QP_BLOCKS; ++k) t += partial[k * 3 + threadIdx.x];
-        out3[threadIdx.x] = t;
+    // one warp, fixed order: lane l sums blocks l, l + 32, ...; then a butterfly
+    const int lane = threadIdx.x & 31;
+    double t[3] = {0.0, 0.0, 0.0};
+    for (int k = lane; k < QP_BLOCKS; k += 32) {
+#pragma unroll
+        for (int j = 0; j < 3; ++j) t[j] += partial[k * 3 + j];
     }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+#pragma unroll
+        for (int j = 0; j < 3; ++j) t[j] += __shfl_xor_sync(0xffffffffu, t[j], off);
+    }
+    if (lane < 3) out3[lane] = lane == 0 ? t[0] : (lane == 1 ? t[1] : t[2]);
 }
 
 __global__ void dmx_fp64_fma_kernel(double* out, int iters) {
