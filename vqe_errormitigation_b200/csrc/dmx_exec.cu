@@ -645,10 +645,21 @@ __global__ void __launch_bounds__(256, DMX_F32_MINB) dmx_frame32_kernel(const Fr
     double2* cs = reinterpret_cast<double2*>(smem_base) + (size_t)warp * CPB * NC;
     unsigned* act = reinterpret_cast<unsigned*>(smem_base + off_act) + (size_t)warp * CPB * (SEG_MAXACT + 1);
     int* nact = reinterpret_cast<int*>(act + CPB * SEG_MAXACT);
-    double2* sw = reinterpret_cast<double2*>(smem_base + off_sw);
-    unsigned char* spart = smem_base + off_sw + (unsigned)a.nseg * 32u * 16u;
-    int* ssel = reinterpret_cast<int*>(smem_base + off_sw + (unsigned)a.nseg * 32u * 17u);
-    for (int i = threadIdx.x; i < a.nseg * 32; i += 256) { sw[i] = a.w[i]; spart[i] = a.partner[i]; }
+    // Staged form of the weights: the own-coefficient factor of a segment is A = w0 * (moved by the rotation ? cos : 1).
+    // Kept as (wc, wk) with A = fma(wc, cos, wk) it needs no select in the segment loop (a select on a double is two
+    // FSELs per circuit and segment; ptxas also turns a predicated DMUL into DMUL + 2 FSEL).
+    double2* sw = reinterpret_cast<double2*>(smem_base + off_sw);                                   // [nseg][32] (wc, wk)
+    double* sw1 = reinterpret_cast<double*>(smem_base + off_sw + (unsigned)a.nseg * 32u * 16u);     // [nseg][32] w1
+    unsigned char* spart = smem_base + off_sw + (unsigned)a.nseg * 32u * 24u;
+    int* ssel = reinterpret_cast<int*>(smem_base + off_sw + (unsigned)a.nseg * 32u * 25u);
+    for (int i = threadIdx.x; i < a.nseg * 32; i += 256) {
+        const double2 w = a.w[i];
+        const unsigned char pbyte = a.partner[i];
+        const bool moved = (pbyte & 0x80u) && a.cs_sel[i >> 5] >= 0;
+        sw[i] = moved ? make_double2(w.x, 0.0) : make_double2(0.0, w.x);
+        sw1[i] = w.y;
+        spart[i] = pbyte;
+    }
     for (int i = threadIdx.x; i < a.nseg; i += 256) ssel[i] = a.cs_sel[i];
     __syncthreads();
     const long long ngroups = (a.batch + CPB - 1) / CPB;
@@ -749,9 +760,10 @@ __global__ void __launch_bounds__(256, DMX_F32_MINB) dmx_frame32_kernel(const Fr
         for (int c = 0; c < CPB; ++c) r[c] = init;
 
         int sel_n = -1;
-        double2 wk_n = make_double2(1.0, 0.0);
+        double2 wk_n = make_double2(0.0, 1.0);
+        double w1_n = 0.0;
         unsigned pb_n = 0u;
-        if (a.nseg > 0) { sel_n = ssel[0]; wk_n = sw[lane]; pb_n = spart[lane]; }
+        if (a.nseg > 0) { sel_n = ssel[0]; wk_n = sw[lane]; w1_n = sw1[lane]; pb_n = spart[lane]; }
         for (int k = 0; k <= a.nseg; ++k) {
             if (VAR && ((stage_any >> (k < 31 ? k : 31)) & 1u)) {
 #pragma unroll
@@ -766,32 +778,38 @@ __global__ void __launch_bounds__(256, DMX_F32_MINB) dmx_frame32_kernel(const Fr
             if (k == a.nseg) break;
             const int sel = sel_n;
             const double2 wk = wk_n;
+            const double w1 = w1_n;
             const unsigned pb = pb_n;
             {   // tables of the next segment: in flight while this one computes
                 const int kn = k + 1 < a.nseg ? k + 1 : k;
-                sel_n = ssel[kn]; wk_n = sw[kn * 32 + lane]; pb_n = spart[kn * 32 + lane];
+                sel_n = ssel[kn]; wk_n = sw[kn * 32 + lane]; w1_n = sw1[kn * 32 + lane]; pb_n = spart[kn * 32 + lane];
             }
-            const bool active = pb & 0x80u;
             const int src = pb & 31u;
             // sel < 0: constant-coefficient segment (resolved rotation) - the weights carry cos / sin already.  The test
             // on `sel` (shared-memory data) must not become a branch around the shuffles, see `rounds` above: plans
             // without such segments (a.any_const == 0, kernel parameter) skip it, the others use selects.
-            if (!a.any_const) {
+            if (CSMODE == 0) {          // no parameterised rotation at all (resolved circuits, QP variant batches)
+                const double w0 = wk.x + wk.y;
 #pragma unroll
                 for (int c = 0; c < CPB; ++c) {
                     const double other = __shfl_sync(0xffffffffu, r[c], src);
-                    const double2 v = CSMODE == 1 ? csr[c] : (CSMODE == 2 ? cs[c * NC + sel] : make_double2(1.0, 1.0));
-                    const double cm = active ? v.x : 1.0;
-                    r[c] = cm * (wk.x * r[c]) + v.y * (wk.y * other);
+                    r[c] = fma(w1, other, w0 * r[c]);
+                }
+            } else if (!a.any_const) {
+#pragma unroll
+                for (int c = 0; c < CPB; ++c) {
+                    const double other = __shfl_sync(0xffffffffu, r[c], src);
+                    const double2 v = CSMODE == 1 ? csr[c] : cs[c * NC + sel];
+                    r[c] = fma(v.y, w1 * other, fma(wk.x, v.x, wk.y) * r[c]);
                 }
             } else {
                 const bool rot = sel >= 0;
 #pragma unroll
                 for (int c = 0; c < CPB; ++c) {
                     const double other = __shfl_sync(0xffffffffu, r[c], src);
-                    const double2 v = CSMODE == 1 ? csr[c] : (CSMODE == 2 ? cs[c * NC + (rot ? sel : 0)] : make_double2(1.0, 1.0));
-                    const double cm = (rot && active) ? v.x : 1.0, sm = rot ? v.y : 1.0;
-                    r[c] = cm * (wk.x * r[c]) + sm * (wk.y * other);
+                    const double2 v = CSMODE == 1 ? csr[c] : cs[c * NC + (rot ? sel : 0)];
+                    const double sm = rot ? v.y : 1.0;          // wk.x = 0 on constant-coefficient segments: cos drops out
+                    r[c] = fma(sm, w1 * other, fma(wk.x, v.x, wk.y) * r[c]);
                 }
             }
         }
@@ -1623,7 +1641,7 @@ static int launch_frame(const FrameArgs& a, int sm_count, cudaStream_t st) {
 template <int CPB, int CSMODE, bool VAR>
 static int launch_frame32_impl(const Frame32Args& a, int sm_count, cudaStream_t st) {
     const int NC = a.n_classes > 0 ? a.n_classes : 1;
-    const size_t smem = (size_t)8 * CPB * NC * 16 + (size_t)8 * CPB * (SEG_MAXACT + 1) * 4 + 48 + (size_t)a.nseg * (32 * 16 + 32 + 4);
+    const size_t smem = (size_t)8 * CPB * NC * 16 + (size_t)8 * CPB * (SEG_MAXACT + 1) * 4 + 48 + (size_t)a.nseg * (32 * 24 + 32 + 4);
     if (smem > 200 * 1024) return fail(DMX_ERR_UNSUPPORTED, "frame32 kernel: tables do not fit shared memory");
     static std::mutex mu;
     static size_t configured = 0;
