@@ -73,6 +73,29 @@ def test_no_cpu_execution_path():
     assert rc == -3 and out[0] == 123.0
 
 
+def test_qp_sampler_argument_checks():
+    lib = _lib.load()
+    h = C.c_void_p()
+    n_choices = np.array([4, 2], np.int32)
+    table = np.array([[1.2, -0.1, 0.0, -0.1], [0.5, 0.5, 0.0, 0.0]])
+    nc, tb = n_choices.ctypes.data_as(C.POINTER(C.c_int32)), table.ctypes.data_as(C.POINTER(C.c_double))
+    assert lib.dmx_qp_sampler_create(0, nc, tb, 4, C.byref(h)) == -1
+    assert lib.dmx_qp_sampler_create(2, nc, tb, 4, None) == -1
+    bad = np.array([5, 2], np.int32)                                  # more choices than the row stride
+    assert lib.dmx_qp_sampler_create(2, bad.ctypes.data_as(C.POINTER(C.c_int32)), tb, 4, C.byref(h)) == -1
+    assert b"n_choices" in lib.dmx_last_error()
+    zero = np.zeros((2, 4))
+    assert lib.dmx_qp_sampler_create(2, nc, zero.ctypes.data_as(C.POINTER(C.c_double)), 4, C.byref(h)) == -1
+    assert b"sums to zero" in lib.dmx_last_error()
+    assert lib.dmx_qp_sampler_draw(None, 1, 0, 1, None, None, None) == -1
+    lib.dmx_qp_sampler_destroy(None)                                  # no-op
+    import torch
+    if not torch.cuda.is_available():                                 # valid tables, no device: reported, nothing drawn
+        assert lib.dmx_qp_sampler_create(2, nc, tb, 4, C.byref(h)) == -3
+        with pytest.raises(RuntimeError, match="no CPU path"):
+            engine.QpSampler([table[0], table[1, :2]])
+
+
 def test_plan_info_and_dump():
     prog = build_program(h2_ops([O.depolarize(1e-3)], [O.two_qubit_depolarize(1e-3)]), 4, h2_terms())
     info = prog.info
