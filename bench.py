@@ -480,6 +480,8 @@ def main():
     def step():
         prog.energies(params_d, variants_d, batch=B, out=out)
 
+    short_steps = prog.info["path"] != 2
+
     for _ in range(args.warmup):
         flush.zero_()
         step()
@@ -493,6 +495,11 @@ def main():
         torch.cuda.synchronize()
         wall0 = time.perf_counter()
         for i in range(args.steps):
+            if short_steps:
+                # a ~150 us device-side spin ahead of the flush lets the host run ahead, so that the start event, the
+                # launch and the end event of a microsecond-scale step are queued back to back (otherwise host jitter -
+                # eight ranks and their clock samplers share the CPU - leaks into the event interval)
+                torch.cuda._sleep(300_000)
             flush.zero_()                      # L2 flush between timed iterations (not inside the events)
             starts[i].record()
             step()
@@ -611,7 +618,7 @@ def main():
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic",
             "config": {"workload": wl["name"], "batch_per_gpu": B, "l2": "flushed (192 MiB memset) between timed steps",
-                       "timing": "CUDA events per step on the launch stream, summed; max over ranks",
+                       "timing": "CUDA events per step on the launch stream, summed; max over ranks" + ("; a device-side spin precedes each flush so the host queues ahead" if short_steps else ""),
                        "plan": {k: info[k] for k in ("path", "n_blocks", "n_segments", "n_passes", "tile_qubits", "n_terms")},
                        "wall_ms_incl_flush": 1e3 * wall},
             "clocks": clocks.summary(), "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
