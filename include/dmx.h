@@ -125,10 +125,20 @@ int dmx_plan_create(int n_qubits, int n_params, int n_slots, const dmx_op* ops, 
 int dmx_plan_set_hamiltonian(dmx_plan* plan, int n_terms, const uint32_t* xmask, const uint32_t* zmask,
                              const double* coeff);
 
-/* Planner options (before finalize).  key/value pairs; unknown keys -> DMX_ERR_INVALID.
- *   "fuse"      0/1   gate+channel block fusion (default 1)
- *   "segments"  0/1   allow the segment kernel when eligible (default 1)
- *   "tile_qubits" k   resident qubits per streaming tile, 4..7 (default 7)
+/* Options (before finalize).  key/value pairs; unknown keys -> DMX_ERR_INVALID.
+ * Per plan:
+ *   "fuse"         0/1  gate+channel block fusion (default 1)
+ *   "segments"     0/1  allow the segment / fixed-frame kernels when eligible (default 1)
+ *   "tile_qubits"  k    resident qubits per streaming tile, 4..7 (default 6)
+ *   "remap"        0/1  streaming: re-order the qubits in HBM between passes (default 1)
+ *   "triples"      0/1  streaming: three resident codes per thread instead of two (default 1)
+ * Library-wide execution switches (take effect for every plan of the process):
+ *   "stream_kernel"   0/1  0 = generic tile kernel for every streaming pass (default 1)
+ *   "stream_chunk"    n    circuits per streaming pass launch, 0 = automatic (default 0)
+ *   "frame32"         0/1  compact warp-per-circuit frame kernel when <= 32 coefficients are live (default 1)
+ *   "segment_cpb"     4|8  circuits per warp / thread of the frame kernels (default 8)
+ *   "host_zero_copy"  0/1  dmx_energy_batch_host works in place on mapped page-locked buffers (default 1)
+ *   "host_chunk_rows" n    rows per chunk of the dmx_energy_batch_host DMA pipeline, >= 1024 (default 32768)
  */
 int dmx_plan_set_option(dmx_plan* plan, const char* key, int value);
 

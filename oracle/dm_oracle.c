@@ -8,7 +8,8 @@
  * U rho U^dagger, mixtures/channels as sum_k K rho K^dagger, the energy is Re Tr(rho H) summed over Pauli
  * strings.  Nothing is fused or re-expressed: this is the per-operation work the reference's CPU path does,
  * minus Python dispatch.  Parity pinning: validated against dm_oracle.py (tests/test_oracle.py), which is
- * itself pinned on the reference's HF/FCI known answers; noisy energies are unpinned by the reference.
+ * itself pinned on the reference's HF/FCI known answers and on its stored noisy SWAP-test run (statistically);
+ * deterministic noisy energies are otherwise unpinned by the reference.
  *
  * The op table uses the same layout as include/dmx.h's dmx_op so the same circuit description can be handed
  * to both implementations; the struct is re-declared here on purpose (no shared code with the product).

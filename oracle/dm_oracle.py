@@ -17,12 +17,18 @@ and of the observable evaluation at the reference's call sites:
   * ``(H * rho).diagonal().sum().real`` with ndarray H = element-wise product —
     ``src/error_mitigation.py:377-383``.
 
-PARITY PINNING: the reference has no tests and publishes no golden vector for any noisy energy.  This
-oracle is pinned against everything that does exist (tests/test_oracle.py): the 30 (hf_energy, fci_energy)
-pairs stored in the reference's ``src/mol_data/H2_*.hdf5`` (noiseless E(alpha=0) = HF, min_alpha E = FCI =
-lambda_min(H)), analytic quasi-probability values, trace/Hermiticity invariants, and closed-form channel
-identities.  For noisy energies and mitigated estimators: **parity unpinned by the reference** — this
-restatement is the sole oracle there.
+PARITY PINNING: the reference has no tests and publishes no deterministic golden vector for a noisy energy.
+This oracle is pinned against everything that does exist (tests/test_oracle.py, tests/test_persistence.py):
+  * the 30 (hf_energy, fci_energy) pairs stored in the reference's ``src/mol_data/H2_*.hdf5`` (noiseless
+    E(alpha=0) = HF, min_alpha E = FCI = lambda_min(H)) and the per-bond-length FCI values the reference wrote into
+    ``src/classic_minimisation/H2_*semi_minimisation*``;
+  * the reference-GENERATED noisy SWAP-test run ``src/classic_minimisation/SWAP_Similarity_P0.0001_R100_C10000``
+    (100 x 10 000 shots, no optimiser in the loop): this oracle's exact noisy <Z0> = 0.4560239 sits inside the stored
+    mean's standard error (0.456066 +- 0.00085) — a statistical pin of the noise model, the op order and cirq's
+    Fredkin decomposition;
+  * analytic quasi-probability values, trace / Hermiticity invariants, closed-form channel identities.
+Beyond that — every other noisy energy and mitigated estimator to 1e-10 — **parity is unpinned by the reference**:
+this restatement is the sole oracle there.
 
 ``dtype=np.complex64`` reproduces the precision the reference actually runs at (cirq's default).
 """

@@ -1089,8 +1089,6 @@ struct DevPlan {
     double2* g_w = nullptr; unsigned char* g_partner = nullptr; int* g_cs_sel = nullptr; double* g_init = nullptr; double* g_ew = nullptr; int* g_orig = nullptr;
     SlotDev* slots = nullptr;
     uint8_t* labels = nullptr;
-    int* worklist = nullptr;           // capacity wl_cap (+ counter at the end)
-    long long wl_cap = 0;
     // host-buffer API staging
     cudaStream_t stream = nullptr, s_in = nullptr, s_out = nullptr;   // host-buffer API: compute / copy-in / copy-out
     static constexpr int MAX_CHUNKS = 8;
@@ -1098,7 +1096,6 @@ struct DevPlan {
     void* h_stage = nullptr; size_t h_cap = 0;
     void* d_stage = nullptr; size_t d_cap = 0;
     std::mutex mu;       // host-buffer API staging (held for the whole dmx_energy_batch_host call)
-    std::mutex wl_mu;    // worklist (re)allocation only — never held across a launch that may take `mu`
     int sm_count = 148;
     // streaming passes in the form dmx_stream_kernel executes (dmx_stream.cuh); !ok -> generic dmx_tile_kernel
     struct PassX {
@@ -1354,7 +1351,7 @@ static void free_device(Plan& p) {
     cudaFree(d->sweeps); cudaFree(d->mus); cudaFree(d->chains); cudaFree(d->factors); cudaFree(d->phases);
     cudaFree(d->coefs); cudaFree(d->rots); cudaFree(d->term_idx); cudaFree(d->term_coef);
     cudaFree(d->f_w); cudaFree(d->f_segs); cudaFree(d->f_classes); cudaFree(d->f_init); cudaFree(d->f_eweight); cudaFree(d->f_eslot);
-    cudaFree(d->slots); cudaFree(d->labels); cudaFree(d->worklist);
+    cudaFree(d->slots); cudaFree(d->labels);
     cudaFree(d->g_w); cudaFree(d->g_partner); cudaFree(d->g_cs_sel); cudaFree(d->g_init); cudaFree(d->g_ew); cudaFree(d->g_orig);
     for (auto& px : d->passx) cudaFree(px.coefs);
     if (d->h_stage) cudaFreeHost(d->h_stage);
@@ -1675,18 +1672,18 @@ static int run_segment(Plan& p, DevPlan* d, long long batch, const double* param
     a.nseg = p.nseg; a.n_params = p.n_params; a.n_slots = p.n_slots; a.n_classes = (int)p.f_classes.size(); a.n_eterms = d->n_eterms;
     a.batch = batch; a.w = d->f_w; a.segs = d->f_segs; a.classes = d->f_classes; a.init = d->f_init; a.eweight = d->f_eweight;
     a.eslot = d->f_eslot; a.params = params; a.variants = variants; a.slots = d->slots; a.labels = d->labels; a.coefs = d->coefs; a.out = out;
+    // worklist of rows that need the general path: per call and stream-ordered (a plan may run on several streams at once)
+    int* wl = nullptr;
     if (variants) {
-        std::lock_guard<std::mutex> lock(d->wl_mu);
-        if (d->wl_cap < batch) {
-            if (d->worklist) CUDA_TRY(cudaFree(d->worklist));
-            d->worklist = nullptr;
-            CUDA_TRY(cudaMalloc((void**)&d->worklist, (size_t)(batch + 1) * sizeof(int)));
-            d->wl_cap = batch;
-        }
-        a.worklist = d->worklist + 1;
-        a.work_count = d->worklist;
-        CUDA_TRY(cudaMemsetAsync(d->worklist, 0, sizeof(int), st));
+        CUDA_TRY(cudaMallocAsync((void**)&wl, (size_t)(batch + 1) * sizeof(int), st));
+        a.worklist = wl + 1;
+        a.work_count = wl;
+        CUDA_TRY(cudaMemsetAsync(wl, 0, sizeof(int), st));
     }
+    auto done = [&](int rc) {
+        if (wl) { const cudaError_t e = cudaFreeAsync(wl, st); if (rc == DMX_OK && e != cudaSuccess) rc = fail(DMX_ERR_CUDA, cudaGetErrorString(e)); }
+        return rc;
+    };
     const int mode = p.f_classes.empty() ? 0 : (p.f_single_class ? 1 : 2);
     int rc;
     if (p.f32_n > 0 && g_frame32 && p.n_slots < 4096 && p.nseg < 4095) {
@@ -1701,21 +1698,19 @@ static int run_segment(Plan& p, DevPlan* d, long long batch, const double* param
             rc = mode == 0 ? launch_frame32<4, 0>(g, d->sm_count, st) : mode == 1 ? launch_frame32<4, 1>(g, d->sm_count, st) : launch_frame32<4, 2>(g, d->sm_count, st);
         else
             rc = mode == 0 ? launch_frame32<8, 0>(g, d->sm_count, st) : mode == 1 ? launch_frame32<8, 1>(g, d->sm_count, st) : launch_frame32<8, 2>(g, d->sm_count, st);
-        if (rc) return rc;
-        if (variants) rc = run_tile_single(p, d, batch, params, variants, out, OUT_ENERGY, d->worklist + 1, d->worklist, st);
-        return rc;
+        if (rc == DMX_OK && variants) rc = run_tile_single(p, d, batch, params, variants, out, OUT_ENERGY, wl + 1, wl, st);
+        return done(rc);
     }
     if (g_seg_cpb == 4) {
         rc = mode == 0 ? launch_frame<4, 0>(a, d->sm_count, st) : mode == 1 ? launch_frame<4, 1>(a, d->sm_count, st) : launch_frame<4, 2>(a, d->sm_count, st);
     } else {
         rc = mode == 0 ? launch_frame<8, 0>(a, d->sm_count, st) : mode == 1 ? launch_frame<8, 1>(a, d->sm_count, st) : launch_frame<8, 2>(a, d->sm_count, st);
     }
-    if (rc) return rc;
-    if (variants) {
+    if (rc == DMX_OK && variants) {
         // circuits with non-diagonal correction ops (R-type / projector basis ops) take the general tile path
-        rc = run_tile_single(p, d, batch, params, variants, out, OUT_ENERGY, d->worklist + 1, d->worklist, st);
+        rc = run_tile_single(p, d, batch, params, variants, out, OUT_ENERGY, wl + 1, wl, st);
     }
-    return rc;
+    return done(rc);
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -1935,18 +1930,12 @@ int dmx_diag_batch(dmx_plan* plan, int64_t batch, const double* d_params, const 
 
 int dmx_qp_reduce(const double* d_values, const double* d_weights, const int32_t* d_counts, int64_t batch, double* d_out3, void* stream) {
     if (!d_values || !d_weights || !d_out3 || batch < 0) return fail(DMX_ERR_INVALID, "bad arguments");
-    static std::mutex mu;
-    static double* partial[64] = {nullptr};
-    int dev = 0;
-    CUDA_TRY(cudaGetDevice(&dev));
-    if (dev < 0 || dev >= 64) return fail(DMX_ERR_UNSUPPORTED, "device ordinal too large");
-    {
-        std::lock_guard<std::mutex> lock(mu);
-        if (!partial[dev]) CUDA_TRY(cudaMalloc((void**)&partial[dev], QP_BLOCKS * 3 * sizeof(double)));
-    }
     cudaStream_t st = (cudaStream_t)stream;
-    dmx_qp_reduce_stage1<<<QP_BLOCKS, QP_THREADS, 0, st>>>(d_values, d_weights, d_counts, batch, partial[dev]);
-    dmx_qp_reduce_stage2<<<1, 32, 0, st>>>(partial[dev], d_out3);
+    double* partial = nullptr;       // per call, stream-ordered: concurrent reductions on different streams do not share it
+    CUDA_TRY(cudaMallocAsync((void**)&partial, QP_BLOCKS * 3 * sizeof(double), st));
+    dmx_qp_reduce_stage1<<<QP_BLOCKS, QP_THREADS, 0, st>>>(d_values, d_weights, d_counts, batch, partial);
+    dmx_qp_reduce_stage2<<<1, 32, 0, st>>>(partial, d_out3);
+    CUDA_TRY(cudaFreeAsync(partial, st));
     g_launches += 2;
     CUDA_TRY(cudaGetLastError());
     return DMX_OK;
