@@ -228,6 +228,42 @@ def test_qp_variants_match_oracle(options):
         assert abs(got[b] - want) < TOL, (b, got[b], want)
 
 
+def test_one_plan_on_two_streams_concurrently():
+    """include/dmx.h: a finalized plan may be used from several streams at once (per-call worklist / reduction
+    scratch).  Two different variant tables - both with rows that take the general path - are evaluated and reduced on
+    two streams, interleaved, and must equal the results of running them one after the other."""
+    torch = torch_cuda()
+    from vqe_errormitigation_b200 import engine
+    terms = h2_terms()
+    n1, n2 = [O.depolarize(1e-3)], [O.two_qubit_depolarize(1e-3)]
+    prog, gates = qp_noisy_variant_program(n1, n2, terms)
+    arity = np.array([len(g[1]) for g in gates])
+    rng = np.random.default_rng(77)
+    B = 20000
+    tables = []
+    for t in range(2):
+        v = np.zeros((B, 122), np.uint8)
+        hot = rng.choice(B, B // 5, replace=False)
+        slot = rng.integers(0, 122, hot.size)
+        v[hot, slot] = np.where(arity[slot] == 1, rng.integers(1, 16, hot.size), rng.integers(1, 256, hot.size))   # incl. R / projector ops
+        tables.append(torch.tensor(v, device="cuda"))
+    weights = torch.ones(B, dtype=torch.float64, device="cuda")
+    want = [prog.energies(None, tb).clone() for tb in tables]
+    want_red = [engine.qp_reduce(w, weights).clone() for w in want]
+    torch.cuda.synchronize()
+    streams = [torch.cuda.Stream(), torch.cuda.Stream()]
+    outs = [[], []]
+    for _ in range(6):
+        for i, st in enumerate(streams):
+            with torch.cuda.stream(st):
+                e = prog.energies(None, tables[i])
+                outs[i].append((e, engine.qp_reduce(e, weights)))
+    torch.cuda.synchronize()
+    for i in range(2):
+        for e, red in outs[i]:
+            assert torch.equal(e, want[i]) and torch.equal(red, want_red[i])
+
+
 @pytest.mark.parametrize("n,tile,remap", [(8, 7, 1), (8, 7, 0), (8, 5, 1), (9, 6, 1), (9, 6, 0), (9, 4, 1), (10, 6, 1)])
 def test_streaming_matches_oracle(n, tile, remap):
     """Streaming passes (state in HBM) against the numpy oracle: dmx_stream_kernel with the remapping scheduler (two state
