@@ -467,6 +467,15 @@ def main():
         cpu_baseline = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
                         "sample": f"{cpu_sample_note(wl, sample)}, {dt:.1f} s, C restatement of cirq's per-op "
                                   f"density-matrix algorithm (oracle/dm_oracle.c) on {cores} threads"}
+        if not wl.get("cpu_ops_fraction"):
+            # the reference's own shapes: one process (CPU.get_custom_optimized_state) and its Pool(6)
+            # (MAX_MULTI_PROCESSING_COUNT, src/error_mitigation.py:14), ~2 s of work each
+            by = {str(cores): rate}
+            for th in (1, 6):
+                if th < cores:
+                    n_s = int(max(8, min(B, rate / cores * th * 2.0)))
+                    by[str(th)] = cpu_port_rate(wl, n_s, threads=th)[0]
+            cpu_baseline["by_threads"] = by
 
     params_h, variants_h = wl["make_inputs"](rank)
     params_d = torch.tensor(params_h, device="cuda") if params_h is not None else None
