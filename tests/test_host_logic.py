@@ -273,3 +273,28 @@ def test_molecular_data_from_reference_hdf5_if_present():
     packaged = of.MolecularData(description="0.7414", filename="/nonexistent/H2_0.7414").load()
     assert np.array_equal(m.two_body_integrals, packaged.two_body_integrals)
     assert np.array_equal(m.ccsd_double_amps, packaged.ccsd_double_amps)
+
+
+def test_experiment_and_demo_drivers_on_the_oracle_backend(monkeypatch, tmp_path, capsys):
+    """The compute halves of visual_testing.py's similarity experiments, main.custom_ansatz / get_log_experiment and the
+    calculate_minimisation driver, run end to end on CPU with the oracle standing in for the engine (reduced budgets)."""
+    from vqe_errormitigation_b200 import calculate_minimisation as CM
+    from vqe_errormitigation_b200 import experiments as E
+    from vqe_errormitigation_b200 import main as M
+    oracle_backend.install(monkeypatch)
+    np.random.seed(3)
+    fci = h2_golden()["molecules"]["0.7414"]["fci_energy"]
+    d = E.similarity_hydrogen_circuit(prob=1e-4, measure_count=2, identifier_count=2000, fixed_parameters=[ALPHA_STAR])
+    assert d._settings == "P0.0001_R2_C2000" and d.mu_ideal == -1.13727 and len(d.data_noisy.get_data) == 2
+    # 2000 // 5 identifiers: noisy ~ -1.031 (SURVEY App. A.4 row 3 plus measurement-basis noise), mitigated ~ FCI
+    assert abs(d.data_noisy.get_mean - (-1.031)) < 0.03 and abs(d.data_mitigated.get_mean - fci) < 0.08
+    monkeypatch.setattr(CM, "DATA_DIR", str(tmp_path / "classic_minimisation"))
+    CM.write_object(d, "H2_Similarity_" + d._settings)
+    back = CM.read_object("H2_Similarity_" + d._settings)
+    assert back.data_mitigated.get_data == d.data_mitigated.get_data and back.mu_ideal == d.mu_ideal
+    # main.custom_ansatz: bit + phase flip model, shot-based COBYLA (reference main.py:35-50) on a reduced budget
+    value, params = M.custom_ansatz(max_cpu_iter=3, max_qpu_iter=200, p=1e-3)
+    assert -1.3 < value < -0.9 and len(params) == 1
+    errors = M.get_log_experiment([10, 1000], expectation=0.5, experiment=lambda shots: 0.5 + 1.0 / shots, reps=2)
+    assert errors == {10: pytest.approx(0.1), 1000: pytest.approx(1e-3)}
+    capsys.readouterr()
