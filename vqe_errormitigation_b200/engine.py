@@ -22,10 +22,17 @@ from ._lib import DmxOp, DmxPlanInfo, check
 _AXIS = {0: "X", 1: "Y", 2: "Z"}
 
 
+_TORCH_WITH_CUDA = None
+
+
 def _require_cuda():
+    global _TORCH_WITH_CUDA
+    if _TORCH_WITH_CUDA is not None:        # a visible device does not go away: only the positive answer is cached
+        return _TORCH_WITH_CUDA
     import torch
     if not torch.cuda.is_available():
         raise RuntimeError("vqe_errormitigation_b200: no CUDA device visible — the density-matrix engine has no CPU path")
+    _TORCH_WITH_CUDA = torch
     return torch
 
 
@@ -265,26 +272,36 @@ class CircuitProgram:
         """Host-buffer call (``dmx_energy_batch_host``): numpy in, numpy out, copies included.  Page-locked arrays
         (``engine.pinned_empty``) are copied from / into in place; pageable ones go through a pinned staging buffer."""
         _require_cuda()
-        sizes = set()
         p = v = None
-        if params is not None:
-            p = np.ascontiguousarray(params, np.float64).reshape(-1, max(self.n_params, 1)) if self.n_params else None
-            if p is not None:
-                sizes.add(p.shape[0])
+        B = batch
+        if params is not None and self.n_params:
+            p = params if (type(params) is np.ndarray and params.dtype == np.float64 and params.flags.c_contiguous) \
+                else np.ascontiguousarray(params, np.float64)
+            if p.size % self.n_params:
+                raise ValueError(f"params has {p.size} entries, not a multiple of {self.n_params}")
+            rows = p.size // self.n_params
+            if B is not None and B != rows:
+                raise ValueError(f"inconsistent batch sizes {sorted({B, rows})}")
+            B = rows
         if variants is not None:
-            v = np.ascontiguousarray(variants, np.uint8).reshape(-1, self.n_slots)
-            sizes.add(v.shape[0])
-        if batch is not None:
-            sizes.add(batch)
-        if len(sizes) != 1:
-            raise ValueError(f"inconsistent batch sizes {sorted(sizes)}")
-        B = sizes.pop()
+            v = variants if (type(variants) is np.ndarray and variants.dtype == np.uint8 and variants.flags.c_contiguous) \
+                else np.ascontiguousarray(variants, np.uint8)
+            if self.n_slots == 0 or v.size % self.n_slots:
+                raise ValueError(f"variants has {v.size} entries, not a multiple of {self.n_slots}")
+            rows = v.size // self.n_slots
+            if B is not None and B != rows:
+                raise ValueError(f"inconsistent batch sizes {sorted({B, rows})}")
+            B = rows
+        if B is None:
+            raise ValueError("inconsistent batch sizes []")
         if out is None:
             out = np.empty(B, np.float64)
         elif out.dtype != np.float64 or out.size != B or not out.flags.c_contiguous:
             raise ValueError("out must be a contiguous float64 array of the batch size")
-        check(self._lib.dmx_energy_batch_host(self._handle, B, p.ctypes.data_as(C.c_void_p) if p is not None else None,
-                                              v.ctypes.data_as(C.c_void_p) if v is not None else None, out.ctypes.data_as(C.c_void_p)))
+        # raw addresses (ndarray.ctypes builds a helper object per access: several microseconds on a 40 us call)
+        check(self._lib.dmx_energy_batch_host(self._handle, B, p.__array_interface__["data"][0] if p is not None else None,
+                                              v.__array_interface__["data"][0] if v is not None else None,
+                                              out.__array_interface__["data"][0]))
         return out
 
     def pauli_vectors(self, params=None, variants=None, *, batch: Optional[int] = None):
