@@ -584,11 +584,13 @@ def main():
     kernel_s = ms_per_step * 1e-3
     path = {0: "dmx_tile_kernel", 1: "dmx_frame32_kernel (dmx_frame_kernel when more than 32 coefficients are live)",
             2: "dmx_stream3_kernel (streaming passes)"}[info["path"]]
-    traffic = None
+    traffic = ncu_util = None
     tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
     if os.path.exists(tpath):
         with open(tpath) as fh:
-            traffic = json.load(fh).get(args.workload)
+            recorded = json.load(fh)
+        traffic = recorded.get(args.workload)
+        ncu_util = recorded.get("_ncu", {}).get(args.workload)
     if info["path"] == 2:
         # algorithmic bytes = SURVEY.md §8d canonical traffic (complex128 rho, one read + write per layer / block);
         # the engine's own traffic (real Pauli vector, fused passes) is reported beside it
@@ -623,6 +625,8 @@ def main():
                     "smem": {"achieved_gbs": smem_ach, "peak_gbs": smem_peak, "frac": smem_ach / smem_peak,
                              "note": "shared-memory exchange bytes per circuit x rate vs 148 SM x 128 B/clk at the sampled SM clock"},
                     "hbm": {"achieved_gbs": info["hbm_bytes_per_circuit"] * B / kernel_s / 1e9, "peak_gbs": hbm_peak}}
+    if ncu_util:
+        roofline["ncu"] = ncu_util      # recorded capture (profiles/), not re-measured by this run
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic",
