@@ -298,3 +298,22 @@ def test_experiment_and_demo_drivers_on_the_oracle_backend(monkeypatch, tmp_path
     errors = M.get_log_experiment([10, 1000], expectation=0.5, experiment=lambda shots: 0.5 + 1.0 / shots, reps=2)
     assert errors == {10: pytest.approx(0.1), 1000: pytest.approx(1e-3)}
     capsys.readouterr()
+
+
+def test_remaining_experiment_loops_on_the_oracle_backend(monkeypatch, capsys):
+    """visual_testing.py's other experiment loops (density-vs-shots, repeated noisy optimisation, raw-vs-mitigated per noise
+    level) at toy budgets.  full_raw_vs_mitigation_per_noise hands an INoiseWrapper to the manager as its objective
+    (reference :761), which must be accepted like an IWaveFunction."""
+    from vqe_errormitigation_b200 import experiments as E
+    oracle_backend.install(monkeypatch)
+    np.random.seed(2)
+    err, spread, probs, reps = E.hamiltonian_density_vs_measure(prob_list=[1e-4], meas_reps=[10, 4000], count=6, max_iter=40)
+    assert err.shape == spread.shape == (1, 2) and probs == [1e-4] and reps == [10, 4000]
+    assert spread[0, 1] < spread[0, 0] and err[0, 1] < 0.02          # more shots: tighter, and close to Tr(rho H)
+    exp_list, opt_list, probs = E.circuit_parameter_optimization(prob_list=[1e-4], count=2, max_cpu_iter=10, max_qpu_iter=4000)
+    assert len(exp_list) == len(opt_list) == 1 and len(exp_list[0]) == 2 and all(-1.1 < v < -0.95 for v in exp_list[0])
+    assert all(abs(a) < 0.2 for a in opt_list[0])                    # COBYLA's halving steps end near alpha* = 0.0141
+    noisy, mitigated, probs = E.full_raw_vs_mitigation_per_noise(measure_count=1, identifier_count=2000, prob_list=[1e-4], max_cpu_iter=6)
+    fci = h2_golden()["molecules"]["0.7414"]["fci_energy"]
+    assert len(noisy) == len(mitigated) == 1 and abs(mitigated[0][0] - fci) < 0.12 and -1.1 < noisy[0][0] < -0.9
+    capsys.readouterr()

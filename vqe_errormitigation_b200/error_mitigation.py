@@ -17,7 +17,7 @@ import numpy as np
 from . import cirq_compat as cirq
 from . import engine
 from .data_containers.helper_interfaces.i_noise_wrapper import INoiseModel
-from .data_containers.helper_interfaces.i_wave_function import IWaveFunction
+from .data_containers.helper_interfaces.i_wave_function import IGeneralizedUCCSD, IWaveFunction
 
 MAX_MULTI_PROCESSING_COUNT = 6  # kept for API compatibility; the GPU batch replaces the process pool
 
@@ -501,7 +501,7 @@ class IErrorMitigationManager:
         hamiltonian = jordan_wigner(w.molecule.get_molecular_hamiltonian())
         qubits = w.qubits
         n = len(qubits)
-        to_z = w.pauli_basis_map()
+        to_z = IGeneralizedUCCSD.pauli_basis_map()      # static, like model_hydrogen.py:122: the objective may be an INoiseWrapper
         noise = self._noise_model.get_operators
         by_size: Dict[int, list] = {}
         for term in hamiltonian.terms:

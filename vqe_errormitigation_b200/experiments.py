@@ -9,7 +9,7 @@ it in the same jsonpickle format).
 """
 from __future__ import annotations
 
-from typing import Optional
+from typing import Optional, Sequence
 
 import numpy as np
 
@@ -77,3 +77,74 @@ def similarity_hydrogen_circuit(prob: float = 1e-4, measure_count: int = 100, id
         result_mitigated.append(manager.get_mu_effective(error_mitigation=True, density_representation=False, meas_reps=1)[1])
     settings = ISimilarityCollection.get_settings(probability=prob, measure_count=measure_count, identifier_count=identifier_count)
     return ISimilarityCollection(data_noisy=result_noisy, data_mitigated=result_mitigated, mu_ideal=mu_ideal, settings=settings)
+
+
+def hamiltonian_density_vs_measure(prob_list: Optional[Sequence[float]] = None, meas_reps: Optional[Sequence[int]] = None, count: int = 50,
+                                   max_iter: int = 1000):
+    """``hamiltonian_density_vs_measure`` (visual_testing.py:402-447): the deterministic Tr(rho H) of the noisy optimised
+    ansatz against ``count`` shot-based ``measure_observable`` energies per (noise level, shots).  Returns
+    (error[i, j] = |Tr(rho H) - mean|, spread[i, j] = std, prob_list, meas_reps); the reference's Pool(6) over the
+    ``count`` repetitions (:438-439) is a plain loop here — every repetition is five GPU evolutions."""
+    ansatz = HydrogenAnsatz()
+    result = CPU.get_optimized_state(w=ansatz, max_iter=max_iter)
+    parameters = ansatz.operator_parameters
+    parameters.update(v=result.optimal_parameters)       # (the reference passes r=result, which its IParameter rejects)
+    observable_process, _circuit_cost = ansatz.observable_measurement()
+    prob_list = [float(1 / shot) for shot in np.logspace(1, 4, 4)] if prob_list is None else list(prob_list)
+    meas_reps = [int(shot) for shot in np.logspace(0, 4, 10)] if meas_reps is None else list(meas_reps)
+    error_list = np.zeros((len(prob_list), len(meas_reps)))
+    error_var_list = np.zeros((len(prob_list), len(meas_reps)))
+    for i, prob in enumerate(prob_list):
+        noise_model = asymmetric_pauli_noise_model(prob)
+        noisy_ansatz = INoiseWrapper(ansatz, noise_model)
+        circuit = noisy_ansatz.get_noisy_circuit()
+        exp_fidelity = QPU.get_simulated_noisy_expectation_value(w=noisy_ansatz, r_c=circuit, r=parameters.get_resolved())
+        resolved_circuit = QPU.get_resolved_circuit(circuit, parameters)
+        for j, meas in enumerate(meas_reps):
+            exp_measure = np.array([observable_process(resolved_circuit, noise_model.get_operators, meas) for _ in range(count)])
+            error_list[i][j] = abs(exp_fidelity - np.mean(exp_measure))
+            error_var_list[i][j] = abs(np.std(exp_measure))
+    return error_list, error_var_list, prob_list, meas_reps
+
+
+def circuit_parameter_optimization(prob_list: Optional[Sequence[float]] = None, count: int = 20, max_cpu_iter: int = 10,
+                                   max_qpu_iter: int = 10000):
+    """``circuit_parameter_optimization(overwrite=True)`` (visual_testing.py:660-700): ``count`` independent shot-based
+    COBYLA runs per noise level.  Returns the tuple the reference stores as ``H2_Optimizing_Parameters_02``:
+    (exp_list, opt_list, prob_list)."""
+    ansatz = HydrogenAnsatz()
+    prob_list = np.flip(np.array([1 / shot for shot in np.logspace(2, 5, 14)])) if prob_list is None else np.asarray(prob_list, float)
+    exp_list, opt_list = [], []
+    for prob in prob_list:
+        noisy_ansatz = INoiseWrapper(w_class=ansatz, noise_model=asymmetric_pauli_noise_model(float(prob)))
+        results = [CPU.get_custom_optimized_state(n_w=noisy_ansatz, max_cpu_iter=max_cpu_iter, max_qpu_iter=max_qpu_iter) for _ in range(count)]
+        exp_list.append([value for value, _params in results])
+        opt_list.append([params[0] for _value, params in results])
+    return exp_list, opt_list, prob_list
+
+
+def full_raw_vs_mitigation_per_noise(measure_count: int, identifier_count: int, prob_list: Optional[Sequence[float]] = None,
+                                     max_cpu_iter: int = 10):
+    """``full_raw_vs_mitigation_per_noise(overwrite=True)`` (visual_testing.py:778-812, RawAndMitigatedClass :746-771): per
+    noise level ``measure_count`` x (noisy shot-based optimum, QP-mitigated energy at the optimised parameters).
+    Returns (exp_noisy_list, exp_mitig_list, prob_list) as stored in ``H2_Measure_Raw_vs_Mitigated``."""
+    ansatz = HydrogenAnsatz()
+    prob_list = np.flip(np.array([1 / shot for shot in np.logspace(3, 5, 5)])) if prob_list is None else np.asarray(prob_list, float)
+    exp_noisy_list, exp_mitig_list = [], []
+    for prob in prob_list:
+        noise_model = asymmetric_pauli_noise_model(float(prob))
+        noisy_ansatz = INoiseWrapper(w_class=ansatz, noise_model=noise_model)
+        circuit = noisy_ansatz.get_clean_circuit()
+        noisy, mitigated = [], []
+        for _ in range(measure_count):
+            exp_noisy_value, opt_params = CPU.get_custom_optimized_state(n_w=noisy_ansatz, max_cpu_iter=max_cpu_iter, max_qpu_iter=identifier_count)
+            ansatz_parameters = noisy_ansatz.operator_parameters
+            ansatz_parameters.update(v=opt_params)
+            circuit_noisy_param = QPU.get_resolved_circuit(c=circuit, p=ansatz_parameters)
+            manager = IErrorMitigationManager(clean_circuit=circuit_noisy_param, noise_model=noise_model, hamiltonian_objective=noisy_ansatz)
+            manager.set_identifier_range(identifier_count)
+            noisy.append(exp_noisy_value)
+            mitigated.append(manager.get_mu_effective(error_mitigation=True, density_representation=False, meas_reps=1)[1])
+        exp_noisy_list.append(noisy)
+        exp_mitig_list.append(mitigated)
+    return exp_noisy_list, exp_mitig_list, prob_list
