@@ -316,4 +316,12 @@ def test_remaining_experiment_loops_on_the_oracle_backend(monkeypatch, capsys):
     noisy, mitigated, probs = E.full_raw_vs_mitigation_per_noise(measure_count=1, identifier_count=2000, prob_list=[1e-4], max_cpu_iter=6)
     fci = h2_golden()["molecules"]["0.7414"]["fci_energy"]
     assert len(noisy) == len(mitigated) == 1 and abs(mitigated[0][0] - fci) < 0.12 and -1.1 < noisy[0][0] < -0.9
+    # bond-length sweeps: r = 0.0 has no molecular data and H2_1.8.hdf5 stops after the SCF step -> NaN rows (reference :983-986)
+    r, fci_e, hf_e, measured = E.hydrogen_fci_energy(atomic_distance_list=[0.0, 0.7, 1.8], repetitions=2, max_cpu_iter=8, max_qpu_iter=2000)
+    assert np.isnan(fci_e[0]) and np.isnan(fci_e[2]) and np.all(np.isnan(measured[0])) and np.all(np.isnan(measured[2]))
+    assert abs(fci_e[1] - h2_golden()["molecules"]["0.7"]["fci_energy"]) < 1e-12 and all(-1.2 < v < -0.9 for v in measured[1])
+    first = E.hydrogen_energy_spectrum(measure_count=1, identifier_count=1000, atomic_distance_list=[0.4, 1.0], max_cpu_iter=6)
+    more = E.hydrogen_energy_spectrum(measure_count=1, identifier_count=1000, atomic_distance_list=[0.4, 1.0], previous=first, max_cpu_iter=6)
+    assert [len(v) for v in more[0]] == [2, 2] and more[0][0][0] == first[0][0][0]          # resumed run extends the stored lists
+    assert abs(more[3][1] - h2_golden()["molecules"]["1.0"]["fci_energy"]) < 1e-12
     capsys.readouterr()

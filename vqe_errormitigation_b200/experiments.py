@@ -123,28 +123,77 @@ def circuit_parameter_optimization(prob_list: Optional[Sequence[float]] = None, 
     return exp_list, opt_list, prob_list
 
 
+def raw_and_mitigated(n_w: INoiseWrapper, noise_model: INoiseModel, max_qpu_iter: int, max_cpu_iter: int = 10):
+    """``RawAndMitigatedClass.process`` (visual_testing.py:746-771): shot-based noisy optimum, then the QP-mitigated energy
+    at the optimised parameters (objective = the noise wrapper itself, sampled ``measure_observable``)."""
+    exp_noisy_value, opt_params = CPU.get_custom_optimized_state(n_w=n_w, max_cpu_iter=max_cpu_iter, max_qpu_iter=max_qpu_iter)
+    ansatz_parameters = n_w.operator_parameters
+    ansatz_parameters.update(v=opt_params)
+    circuit_noisy_param = QPU.get_resolved_circuit(c=n_w.get_clean_circuit(), p=ansatz_parameters)
+    manager = IErrorMitigationManager(clean_circuit=circuit_noisy_param, noise_model=noise_model, hamiltonian_objective=n_w)
+    manager.set_identifier_range(max_qpu_iter)
+    exp_mitig_value = manager.get_mu_effective(error_mitigation=True, density_representation=False, meas_reps=1)[1]
+    return exp_noisy_value, exp_mitig_value
+
+
 def full_raw_vs_mitigation_per_noise(measure_count: int, identifier_count: int, prob_list: Optional[Sequence[float]] = None,
                                      max_cpu_iter: int = 10):
-    """``full_raw_vs_mitigation_per_noise(overwrite=True)`` (visual_testing.py:778-812, RawAndMitigatedClass :746-771): per
-    noise level ``measure_count`` x (noisy shot-based optimum, QP-mitigated energy at the optimised parameters).
-    Returns (exp_noisy_list, exp_mitig_list, prob_list) as stored in ``H2_Measure_Raw_vs_Mitigated``."""
+    """``full_raw_vs_mitigation_per_noise(overwrite=True)`` (visual_testing.py:778-812): per noise level ``measure_count``
+    x (noisy, mitigated).  Returns (exp_noisy_list, exp_mitig_list, prob_list) as stored in ``H2_Measure_Raw_vs_Mitigated``."""
     ansatz = HydrogenAnsatz()
     prob_list = np.flip(np.array([1 / shot for shot in np.logspace(3, 5, 5)])) if prob_list is None else np.asarray(prob_list, float)
     exp_noisy_list, exp_mitig_list = [], []
     for prob in prob_list:
         noise_model = asymmetric_pauli_noise_model(float(prob))
         noisy_ansatz = INoiseWrapper(w_class=ansatz, noise_model=noise_model)
-        circuit = noisy_ansatz.get_clean_circuit()
-        noisy, mitigated = [], []
-        for _ in range(measure_count):
-            exp_noisy_value, opt_params = CPU.get_custom_optimized_state(n_w=noisy_ansatz, max_cpu_iter=max_cpu_iter, max_qpu_iter=identifier_count)
-            ansatz_parameters = noisy_ansatz.operator_parameters
-            ansatz_parameters.update(v=opt_params)
-            circuit_noisy_param = QPU.get_resolved_circuit(c=circuit, p=ansatz_parameters)
-            manager = IErrorMitigationManager(clean_circuit=circuit_noisy_param, noise_model=noise_model, hamiltonian_objective=noisy_ansatz)
-            manager.set_identifier_range(identifier_count)
-            noisy.append(exp_noisy_value)
-            mitigated.append(manager.get_mu_effective(error_mitigation=True, density_representation=False, meas_reps=1)[1])
-        exp_noisy_list.append(noisy)
-        exp_mitig_list.append(mitigated)
+        results = [raw_and_mitigated(noisy_ansatz, noise_model, identifier_count, max_cpu_iter) for _ in range(measure_count)]
+        exp_noisy_list.append([noisy for noisy, _ in results])
+        exp_mitig_list.append([mitigated for _, mitigated in results])
     return exp_noisy_list, exp_mitig_list, prob_list
+
+
+def hydrogen_energy_spectrum(measure_count: int, identifier_count: int, atomic_distance_list: Optional[Sequence[float]] = None,
+                             previous=None, prob: float = 1e-4, max_cpu_iter: int = 10):
+    """``hydrogen_energy_spectrum(overwrite=True)`` (visual_testing.py:863-909): (noisy, mitigated) energies along the bond
+    length, ``measure_count`` repetitions per point; ``previous`` is an earlier result tuple to extend (the reference
+    re-reads ``H2_Full_Spectrum_C<n>`` and appends, :866-871).  Returns (exp_noisy_list, exp_mitig_list,
+    atomic_distance_list, fci_energy, hf_energy)."""
+    atomic_distance_list = np.linspace(.1, 2.8, 10) if atomic_distance_list is None else np.asarray(atomic_distance_list, float)
+    depth = len(atomic_distance_list)
+    exp_noisy_list = [list(v) for v in previous[0]] if previous else [[] for _ in range(depth)]
+    exp_mitig_list = [list(v) for v in previous[1]] if previous else [[] for _ in range(depth)]
+    noise_model = asymmetric_pauli_noise_model(prob)
+    fci_energy, hf_energy = [], []
+    for i, atomic_distance in enumerate(atomic_distance_list):
+        ansatz = HydrogenAnsatz(mol_param=round(float(atomic_distance), 2))
+        noisy_ansatz = INoiseWrapper(w_class=ansatz, noise_model=noise_model)
+        results = [raw_and_mitigated(noisy_ansatz, noise_model, identifier_count, max_cpu_iter) for _ in range(measure_count)]
+        exp_noisy_list[i].extend(noisy for noisy, _ in results)
+        exp_mitig_list[i].extend(mitigated for _, mitigated in results)
+        fci_energy.append(float(ansatz.molecule.fci_energy))
+        hf_energy.append(float(ansatz.molecule.hf_energy))
+    return exp_noisy_list, exp_mitig_list, atomic_distance_list, fci_energy, hf_energy
+
+
+def hydrogen_fci_energy(atomic_distance_list: Optional[Sequence[float]] = None, repetitions: int = 10, max_cpu_iter: int = 10,
+                        max_qpu_iter: int = 1000):
+    """``hydrogen_fci_energy(overwrite=True)`` (visual_testing.py:958-990): noiseless shot-based VQE energies along the bond
+    length.  Bond lengths without (complete) molecular data give NaN rows, like the reference's bare ``except`` (:983-986):
+    r = 0.0 has no hdf5 at all, ``H2_1.8.hdf5`` stops after the SCF step.  Returns (atomic_distance_list, fci_energy,
+    hf_energy, measured_energy)."""
+    atomic_distance_list = np.linspace(0.0, 3.0, 31) if atomic_distance_list is None else np.asarray(atomic_distance_list, float)
+    noise_model = asymmetric_pauli_noise_model(0)
+    fci_energy, hf_energy, measured_energy = [], [], []
+    for atomic_distance in atomic_distance_list:
+        try:
+            ansatz = HydrogenAnsatz(mol_param=round(float(atomic_distance), 2))
+            noisy_ansatz = INoiseWrapper(ansatz, noise_model)
+            energies = [CPU.get_custom_optimized_state(n_w=noisy_ansatz, max_cpu_iter=max_cpu_iter, max_qpu_iter=max_qpu_iter)[0]
+                        for _ in range(repetitions)]
+            fci, hf = float(ansatz.molecule.fci_energy), float(ansatz.molecule.hf_energy)
+        except (FileNotFoundError, TypeError, ValueError, KeyError):
+            energies, fci, hf = [float('NaN')] * repetitions, float('NaN'), float('NaN')
+        measured_energy.append(energies)
+        fci_energy.append(fci)
+        hf_energy.append(hf)
+    return atomic_distance_list, fci_energy, hf_energy, measured_energy
