@@ -39,11 +39,13 @@ def test_device_sampler_is_bit_exact_with_reference():
     from vqe_errormitigation_b200 import engine
     rng = np.random.default_rng(11)
     qps = [rng.normal(size=k) for k in (16, 256, 16, 2, 1, 256, 16)] + [np.array([1.3, -0.1, -0.1, -0.1] + [0.0] * 12)]
-    for batch, seed, first in ((1, 0, 0), (4097, 123456789012345, 0), (1000, 5, (1 << 33) + 17)):
-        dv, ds = engine.qp_sample_variants(qps, batch, seed, first_sample=first)
-        rv, rs = P.sample_variants(qps, batch, seed, first_sample=first)
-        assert np.array_equal(dv.cpu().numpy(), rv)
-        assert np.array_equal(ds.cpu().numpy(), rs)
+    odd = [np.array([0.7, -0.3]), np.array([1.0]), np.array([-2.0, 1.0, 0.5])]      # 3 slots x stride 3: sub-tables need padding to 16 B
+    for tables in (qps, odd, odd[:1], qps[:5]):
+        for batch, seed, first in ((1, 0, 0), (4097, 123456789012345, 0), (1000, 5, (1 << 33) + 17)):
+            dv, ds = engine.qp_sample_variants(tables, batch, seed, first_sample=first)
+            rv, rs = P.sample_variants(tables, batch, seed, first_sample=first)
+            assert np.array_equal(dv.cpu().numpy(), rv)
+            assert np.array_equal(ds.cpu().numpy(), rs)
 
 
 @pytest.mark.gpu

@@ -1965,10 +1965,10 @@ int dmx_qp_sampler_create(int n_slots, const int32_t* n_choices, const double* q
     for (int s = 0; s < n_slots; ++s) { first[s] = cdf[(size_t)s * stride]; sg0[s] = sg[(size_t)s * stride]; }
     auto* sm = new dmx_qp_sampler();
     sm->n_slots = n_slots; sm->stride = stride;
-    sm->cb = cdf.size() * 8; sm->fb = first.size() * 8; sm->nb = (size_t)n_slots * 4; sm->gb = sg0.size();
-    sm->nb = (sm->nb + 15) & ~(size_t)15;
+    // every sub-table starts 16-byte aligned (cdf0 is read as double2)
+    sm->cb = (cdf.size() * 8 + 15) & ~(size_t)15; sm->fb = first.size() * 8; sm->nb = ((size_t)n_slots * 4 + 15) & ~(size_t)15; sm->gb = sg0.size();
     if (cudaGetDevice(&sm->device) != cudaSuccess || cudaMalloc((void**)&sm->d, sm->cb + sm->fb + sm->nb + sm->gb + sg.size()) != cudaSuccess ||
-        cudaMemcpy(sm->d, cdf.data(), sm->cb, cudaMemcpyHostToDevice) != cudaSuccess ||
+        cudaMemcpy(sm->d, cdf.data(), cdf.size() * 8, cudaMemcpyHostToDevice) != cudaSuccess ||
         cudaMemcpy(sm->d + sm->cb, first.data(), sm->fb, cudaMemcpyHostToDevice) != cudaSuccess ||
         cudaMemcpy(sm->d + sm->cb + sm->fb, n_choices, (size_t)n_slots * 4, cudaMemcpyHostToDevice) != cudaSuccess ||
         cudaMemcpy(sm->d + sm->cb + sm->fb + sm->nb, sg0.data(), sm->gb, cudaMemcpyHostToDevice) != cudaSuccess ||
