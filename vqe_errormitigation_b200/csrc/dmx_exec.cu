@@ -1014,7 +1014,7 @@ __global__ void __launch_bounds__(256) dmx_qp_sample_kernel(int n_slots, const i
     if (b >= batch) return;
     const unsigned long long gidx = first_sample + (unsigned long long)b;
     unsigned char* const out = variants + b * n_slots;
-    const bool aligned = ((b * n_slots) & 3) == 0;
+    const bool aligned = (reinterpret_cast<unsigned long long>(out) & 3ull) == 0;      // this row's 4-slot words are word stores
     int neg = 0, zero = 0;
     for (int g = lane; 4 * g < n_slots; g += 32) {
         unsigned c[4] = {(unsigned)gidx, (unsigned)(gidx >> 32), (unsigned)g, 0u};
