@@ -1,0 +1,1 @@
+"""oracle package of the B200 density-matrix engine repository."""

@@ -1,0 +1,1 @@
+"""tests package of the B200 density-matrix engine repository."""

@@ -1,0 +1,1 @@
+"""data_containers package of the B200 density-matrix engine repository."""

@@ -1,49 +1,58 @@
-"""Named-parameter container (mirror of ``src/data_containers/helper_interfaces/i_parameter.py``)."""
+"""``IParameter``: the ordered name -> value table of an ansatz (API of
+``src/data_containers/helper_interfaces/i_parameter.py``).
+
+One table object is shared BY REFERENCE between an ansatz and its noise wrapper (the reference's
+``i_noise_wrapper.py:100`` hands the same object to both and callers rely on that aliasing), so every mutator works in
+place on the wrapped mapping and never rebinds it.
+"""
 from __future__ import annotations
 
-from typing import Dict, Sequence
+from typing import Dict, Iterator, Sequence
 
 from ... import cirq_compat as cirq
 
 
 class IParameter:
-    """Ordered ``name -> value`` mapping shared *by reference* between an ansatz and its noise wrapper
-    (reference: i_noise_wrapper.py:100 hands the same object to both, callers rely on that aliasing)."""
-
     def __init__(self, parameters: Dict[str, float]):
         self._p = parameters
 
+    # ---- mapping protocol --------------------------------------------------------------------------------
+    def __getitem__(self, name: str) -> float:
+        return self._p[name]
+
+    def __setitem__(self, name: str, value: float) -> None:
+        self._p[name] = value
+
+    def __iter__(self) -> Iterator[str]:
+        yield from self._p
+
+    def __len__(self) -> int:
+        return len(self._p)
+
+    def __str__(self) -> str:
+        return str(self._p)
+
+    def __add__(self, other: "IParameter") -> "IParameter":
+        """New table holding this one's entries followed by ``other``'s (``other`` wins on equal names)."""
+        combined = dict(self._p)
+        combined.update(other.get_dict())
+        return IParameter(combined)
+
+    # ---- reference API -------------------------------------------------------------------------------------
     def get_dict(self) -> Dict[str, float]:
+        """The wrapped mapping itself (not a copy)."""
         return self._p
 
     dict = property(get_dict)
 
     def get_resolved(self) -> cirq.ParamResolver:
-        """Reference: i_parameter.py:8-9 (cirq.ParamResolver over the dict)."""
+        """Resolver over the current values (reference :8-9)."""
         return cirq.ParamResolver(self._p)
 
-    def update(self, v: Sequence[float]):
-        if len(v) != len(self._p):
+    def update(self, v: Sequence[float]) -> None:
+        """Positional assignment of optimiser output, in the table's own order (reference :24-28)."""
+        names = list(self._p)
+        if len(names) != len(v):
             raise IndexError("Dimensions of optimized trial result does not correspond to IParameter")
-        for key, value in zip(list(self._p.keys()), v):
-            self._p[key] = value
-
-    def __iter__(self):
-        return iter(self._p)
-
-    def __len__(self):
-        return len(self._p)
-
-    def __str__(self):
-        return str(self._p)
-
-    def __getitem__(self, item: str):
-        return self._p[item]
-
-    def __setitem__(self, key: str, value: float):
-        self._p[key] = value
-
-    def __add__(self, other: "IParameter") -> "IParameter":
-        merged = dict(self._p)
-        merged.update(other.dict)
-        return IParameter(merged)
+        for name, value in zip(names, v):
+            self._p[name] = value

@@ -1,0 +1,1 @@
+"""moldata package of the B200 density-matrix engine repository."""

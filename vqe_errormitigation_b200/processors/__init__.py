@@ -1,0 +1,1 @@
+"""processors package of the B200 density-matrix engine repository."""
