@@ -1,0 +1,49 @@
+"""The bench.py JSON line: the committed round-1 records (profiles/, written by bench.py on the B200 box) carry every key
+of the driver's contract, and the reference arm's line has its own required shape.  CPU only."""
+import glob
+import json
+import os
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+BASE = ["metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline",
+        "dtype", "data", "config", "clocks", "e2e", "gpu_launches", "roofline"]
+
+
+def load(name):
+    with open(os.path.join(ROOT, "profiles", name)) as fh:
+        return json.load(fh)
+
+
+@pytest.mark.parametrize("name", ["r1_bench_h2_v10.json", "r1_bench_qem_v9.json", "r1_bench_hea10_v8.json", "r1_bench_lih12_v8.json",
+                                  "r1_bench_h2_n8_v8.json"])
+def test_record_has_contract_keys(name):
+    d = load(name)
+    assert [k for k in BASE if k not in d] == []
+    assert d["metric"] == "noisy_circuit_energy_evals_per_sec" and d["higher_is_better"] is True and d["scaling"] == "weak"
+    assert d["dtype"] == "f64" and d["data"] == "synthetic" and d["vs_baseline"] is None and "workload" in d["config"]
+    assert d["warmup"] >= 3 and d["gpu_launches"] >= d["steps"] and d["value"] > 0
+    assert {"value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step"} <= set(d["e2e"]) and d["e2e"]["value"] != d["value"]
+    assert {"bound", "achieved", "peak", "unit", "frac", "traffic"} <= set(d["roofline"])
+    assert abs(d["roofline"]["frac"] - d["roofline"]["achieved"] / d["roofline"]["peak"]) < 1e-12
+    assert {"sm_mhz", "sm_max_mhz", "reasons"} <= set(d["clocks"])
+    assert not set(d["clocks"]["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
+    if d.get("cpu_baseline"):            # rank 0 at N = 1, unless the run was started with --no-cpu-baseline
+        assert {"value", "unit", "cores", "kind", "sample"} <= set(d["cpu_baseline"]) and d["cpu_baseline"]["kind"] == "port"
+    assert name != "r1_bench_h2_v10.json" or d["cpu_baseline"]["by_threads"].keys() >= {"1", "6"}
+
+
+def test_reference_arm_record():
+    d = load("r1_bench_h2_reference_arm_v8.json")
+    assert d["impl"] == "reference" and d["metric"] == "noisy_circuit_energy_evals_per_sec"
+    assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert d["cpu_baseline"]["value"] == d["value"] and d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
+    h2 = load("r1_bench_h2_v10.json")
+    assert d["config"]["workload"] == h2["config"]["workload"]            # same workload on both arms
+
+
+def test_every_record_parses():
+    for path in glob.glob(os.path.join(ROOT, "profiles", "r1_bench_*.json")):
+        with open(path) as fh:
+            assert "value" in json.load(fh), path
