@@ -113,3 +113,53 @@ def test_new_schema_containers_and_arrays_round_trip(tmp_path, monkeypatch, caps
     assert again.data_mitigated.get_data == [0.5, 0.49] and again._settings == "P0.0001_R2_C10"
     with pytest.raises(FileNotFoundError):
         CM.read_object("missing")
+
+
+def test_random_nested_structures_round_trip():
+    """Property check of the codec on randomly nested lists / tuples / dicts / numpy scalars and arrays with shared
+    sub-objects: decode(encode(x)) rebuilds x (including aliasing) and re-encodes to the same text."""
+    rng = np.random.default_rng(5)
+
+    def make(depth, pool):
+        kind = rng.integers(0, 9 if depth < 3 else 6)
+        if kind == 0:
+            return float(rng.normal())
+        if kind == 1:
+            return int(rng.integers(-5, 5))
+        if kind == 2:
+            return [None, True, "text", float("inf")][rng.integers(0, 4)]
+        if kind == 3:
+            return rng.choice([np.float64, np.float32, np.int64, np.int32])(rng.integers(-100, 100))
+        if kind == 4:
+            return rng.normal(size=tuple(rng.integers(0, 4, size=rng.integers(0, 3)))).astype(rng.choice([np.float64, np.complex128, np.uint8]))
+        if kind == 5 and pool:
+            return pool[rng.integers(0, len(pool))]            # alias of an earlier list
+        if kind == 6:
+            out = [make(depth + 1, pool) for _ in range(rng.integers(0, 4))]
+            pool.append(out)
+            return out
+        if kind == 7:
+            return tuple(make(depth + 1, pool) for _ in range(rng.integers(0, 3)))
+        return {f"k{i}": make(depth + 1, pool) for i in range(rng.integers(0, 3))}
+
+    def same(a, b):
+        if isinstance(a, np.ndarray):
+            return isinstance(b, np.ndarray) and a.dtype == b.dtype and a.shape == b.shape and np.array_equal(a, b)
+        if isinstance(a, np.generic):
+            return type(a) is type(b) and a == b
+        if isinstance(a, (list, tuple)):
+            return type(a) is type(b) and len(a) == len(b) and all(same(x, y) for x, y in zip(a, b))
+        if isinstance(a, dict):
+            return isinstance(b, dict) and list(a) == list(b) and all(same(a[k], b[k]) for k in a)
+        return type(a) is type(b) and a == b
+
+    for _ in range(200):
+        value = [make(0, []) for _ in range(3)]
+        text = jp.encode(value)
+        back = jp.decode(text)
+        assert same(value, back)
+        assert jp.encode(back) == text
+    nan_box = IContainer.__new__(IContainer)
+    nan_box.__dict__.update(_molecular_parameter=0.7, _optimized_exp_values=[-1.0], _fci_value=None, _hf_value=None, _label="x")
+    again = jp.decode(jp.encode(nan_box, indent=4))
+    assert np.isnan(again.fci_value) and np.isnan(again.hf_value) and again.measured_std == 0 and again.measured_value == -1.0
