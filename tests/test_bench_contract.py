@@ -16,7 +16,7 @@ def load(name):
         return json.load(fh)
 
 
-@pytest.mark.parametrize("name", ["r1_bench_h2_v10.json", "r1_bench_qem_v9.json", "r1_bench_hea10_v8.json", "r1_bench_lih12_v8.json",
+@pytest.mark.parametrize("name", ["r1_bench_h2_v10.json", "r1_bench_qem_v10.json", "r1_bench_hea10_v8.json", "r1_bench_lih12_v8.json",
                                   "r1_bench_h2_n8_v8.json"])
 def test_record_has_contract_keys(name):
     d = load(name)
@@ -31,6 +31,7 @@ def test_record_has_contract_keys(name):
     assert not set(d["clocks"]["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
     if d.get("cpu_baseline"):            # rank 0 at N = 1, unless the run was started with --no-cpu-baseline
         assert {"value", "unit", "cores", "kind", "sample"} <= set(d["cpu_baseline"]) and d["cpu_baseline"]["kind"] == "port"
+    assert name != "r1_bench_qem_v10.json" or (d["dedup"]["unique_rows"] < d["dedup"]["rows"] and d["dedup"]["value"] > d["value"])
     assert name != "r1_bench_h2_v10.json" or d["cpu_baseline"]["by_threads"].keys() >= {"1", "6"}
 
 
