@@ -1,7 +1,8 @@
 #!/usr/bin/env python
 """Headline benchmark: noisy-circuit energy evaluations per second (BASELINE.json `metric`).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload h2_sweep|h2_qem|hea10|lih12] [--impl reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload h2_sweep|h2_qem|hea10|lih12]
+                    [--impl reference] [--no-also]
 
 Default workload = BASELINE.json configs[1]: H2 STO-3G 4-qubit UCCSD ansatz, depolarize(1e-3) after every 1-qubit
 gate and TwoQubitDepolarizingChannel(1e-3) after every CNOT, parameter sweep of 65,536 circuits per launch.  A
@@ -10,13 +11,20 @@ gate and TwoQubitDepolarizingChannel(1e-3) after every CNOT, parameter sweep of 
 (torchrun), the batch is weak-scaled (each rank owns its own 65,536 circuits), no data-path collective
 (independent circuits) — time is max over ranks.
 
+The default run also carries an `also` block: short runs of the other BASELINE configs (h2_qem = configs[2], hea10 =
+configs[3], lih12 = configs[4]) with their own value / ms_per_step / roofline / e2e, so every configuration is in the
+driver-run record.  Under `--gpus N` the h2_qem entry times the whole mitigated estimator INCLUDING its all-reduce.
+Every workload is checked against the oracle outside the timed region (`parity_max_abs_err`).
+
 `--impl reference` times the reference's CPU path for the same circuit: the repo's C restatement of cirq's
 density-matrix algorithm (oracle/dm_oracle.c, kind "port" — cirq/openfermion themselves are not installable
-here) on all host cores, on a bounded sample per step.
+here) on all host cores, on a bounded sample per step.  That arm builds its op table with the host-side builder only:
+libdmx.so is never loaded there.
 """
 from __future__ import annotations
 
 import argparse
+import hashlib
 import json
 import os
 import sys
@@ -33,22 +41,37 @@ UNIT = "circuits/s"
 
 
 # ---------------------------------------------------------------------------------------------------------
-# workloads (built through the repo's public API: HydrogenAnsatz + INoiseWrapper + QPU, or the op builder)
+# workloads.  Each returns the HOST-side description only (op-table builder, Hamiltonian terms, inputs); the plan
+# (libdmx) is created lazily by get_prog(), so `--impl reference` never maps the CUDA library.
 # ---------------------------------------------------------------------------------------------------------
 
 PLAN_OPTIONS = {}
 
 
-def workload_h2_sweep():
-    from vqe_errormitigation_b200 import cirq_compat as cirq
+def get_prog(wl):
+    if wl.get("_prog") is None:
+        from vqe_errormitigation_b200 import engine
+        wl["_prog"] = engine.CircuitProgram(wl["builder"], qubits=wl.get("qubits"), measurements=wl.get("measurements"),
+                                            hamiltonian=wl["terms"], options={**wl.get("options", {}), **PLAN_OPTIONS})
+    return wl["_prog"]
+
+
+def _h2_noisy(noise_1q, noise_2q, description, alpha=None):
     from vqe_errormitigation_b200.data_containers.helper_interfaces.i_noise_wrapper import INoiseModel, INoiseWrapper
     from vqe_errormitigation_b200.data_containers.model_hydrogen import HydrogenAnsatz
+    w = HydrogenAnsatz()
+    if alpha is not None:
+        w.operator_parameters["alpha0"] = alpha
+    noise = INoiseModel(noise_1q, noise_2q, description)
+    return w, noise, INoiseWrapper(w, noise)
+
+
+def workload_h2_sweep():
+    from vqe_errormitigation_b200 import cirq_compat as cirq, engine
     from vqe_errormitigation_b200.error_mitigation import TwoQubitDepolarizingChannel
     from vqe_errormitigation_b200.processors.processor_quantum import QPU
-    w = HydrogenAnsatz()
-    noise = INoiseModel([cirq.depolarize(1e-3)], [TwoQubitDepolarizingChannel(1e-3)], "depolarize p=1e-3")
-    n_w = INoiseWrapper(w, noise)
-    prog = QPU.compile_energy_program(n_w, n_w.get_noisy_circuit(), **PLAN_OPTIONS)
+    w, _noise, n_w = _h2_noisy([cirq.depolarize(1e-3)], [TwoQubitDepolarizingChannel(1e-3)], "depolarize p=1e-3")
+    builder, qubits, measurements, _lifted, _key = engine.lower_circuit(n_w.get_noisy_circuit(), w.qubits)
     B = 65536
 
     def make_inputs(rank: int, seed_offset: int = 0):
@@ -56,44 +79,38 @@ def workload_h2_sweep():
         p = -0.5 + (np.arange(B, dtype=np.float64) + 0.25 * rank) / (B - 1)
         return p.reshape(B, 1), None
 
-    return dict(name="H2 STO-3G 4q UCCSD, depolarize(1e-3) on every gate, 65536-circuit parameter sweep (BASELINE configs[1])",
-                prog=prog, batch=B, make_inputs=make_inputs, terms=QPU.get_hamiltonian_terms(w))
+    return dict(key="h2_sweep",
+                name="H2 STO-3G 4q UCCSD, depolarize(1e-3) on every gate, 65536-circuit parameter sweep (BASELINE configs[1])",
+                builder=builder, qubits=qubits, measurements=measurements, batch=B, make_inputs=make_inputs,
+                terms=QPU.get_hamiltonian_terms(w), parity_rows=[0, B // 2, B - 1])
 
 
 def workload_h2_qem():
     from vqe_errormitigation_b200 import cirq_compat as cirq
-    from vqe_errormitigation_b200.data_containers.helper_interfaces.i_noise_wrapper import INoiseModel, INoiseWrapper
-    from vqe_errormitigation_b200.data_containers.model_hydrogen import HydrogenAnsatz
     from vqe_errormitigation_b200.error_mitigation import IErrorMitigationManager, TwoQubitDepolarizingChannel
     from vqe_errormitigation_b200.processors.processor_quantum import QPU
-    w = HydrogenAnsatz()
-    w.operator_parameters["alpha0"] = 0.014133516193216759
-    noise = INoiseModel([cirq.bit_flip(1e-3), cirq.depolarize(1e-3)], [TwoQubitDepolarizingChannel(1e-3)], "bitflip+depolarize p=1e-3")
-    n_w = INoiseWrapper(w, noise)
+    w, noise, n_w = _h2_noisy([cirq.bit_flip(1e-3), cirq.depolarize(1e-3)], [TwoQubitDepolarizingChannel(1e-3)],
+                              "bitflip+depolarize p=1e-3", alpha=0.014133516193216759)
     clean = QPU.get_resolved_circuit(n_w.get_clean_circuit(), w.operator_parameters)
     mgr = IErrorMitigationManager(clean, noise, QPU.get_hamiltonian_objective_operator(w))
-    prog = mgr._variant_program()
+    builder, qubits, measurements = mgr.variant_builder()
     B = 1_000_000 // 8  # per-GPU shard of the 1e6-variant table (BASELINE configs[2] is quoted on 8 GPUs)
+    qps = mgr.quasi_probabilities()
 
     def make_inputs(rank: int, seed_offset: int = 0):
         state = np.random.get_state()
         np.random.seed(20260102 + rank)
-        qps = mgr._qp_matrix()
         rows = np.zeros((B, len(qps)), np.uint8)
         for s, qp in enumerate(qps):
             rows[:, s] = np.random.choice(len(qp), size=B, p=np.abs(qp) / np.sum(np.abs(qp)))
         np.random.set_state(state)
         return None, rows
 
-    qp_bytes = int(sum(len(q) for q in mgr._qp_matrix()) * 8)
-
-    def sampled_step(step: int):
-        # whole mitigated estimate on the device: QP tables in, (mean, stderr, N) out
-        return mgr.get_mu_effective_sampled(B * max(int(os.environ.get("WORLD_SIZE", "1")), 1), seed=20260102 + step)
-
-    return dict(name="H2 QP error mitigation: 125000 sampled variants per GPU (1e6 over 8), bit_flip+depolarize(1e-3) (BASELINE configs[2])",
-                prog=prog, batch=B, make_inputs=make_inputs, terms=mgr._observable_terms(4), sampled_step=sampled_step,
-                sampled_h2d=qp_bytes)
+    return dict(key="h2_qem",
+                name="H2 QP error mitigation: 125000 sampled variants per GPU (1e6 over 8), bit_flip+depolarize(1e-3) (BASELINE configs[2])",
+                builder=builder, qubits=qubits, measurements=measurements, batch=B, make_inputs=make_inputs,
+                terms=mgr.observable_terms(), manager=mgr, qp_bytes=int(sum(len(q) for q in qps) * 8),
+                parity_rows=[0, 1, 2, 3, B - 1])
 
 
 def _hea_builder(n: int, depth: int, p: float = 1e-3):
@@ -116,32 +133,38 @@ def _hea_builder(n: int, depth: int, p: float = 1e-3):
 
 
 def workload_hea10():
-    from vqe_errormitigation_b200 import engine
     n, depth, B = 10, 20, 4096
     b = _hea_builder(n, depth)
     rng = np.random.default_rng(20260104)
     n_terms = 100
-    xs, zs = np.zeros(n_terms, np.uint32), np.zeros(n_terms, np.uint32)
-    for t in range(n_terms):
+    # 100 DISTINCT Pauli strings of weight 1..4 (a repeated draw is drawn again: round 1 kept duplicates, which the plan
+    # merged into 95 terms)
+    seen = []
+    while len(seen) < n_terms:
+        x = z = 0
         wgt = rng.integers(1, 5)
         for q in rng.choice(n, wgt, replace=False):
             code = rng.integers(1, 4)
             bit = 1 << (n - 1 - int(q))
             if code in (1, 2):
-                xs[t] |= bit
+                x |= bit
             if code in (2, 3):
-                zs[t] |= bit
+                z |= bit
+        if (x, z) not in seen:
+            seen.append((x, z))
+    xs, zs = np.array([t[0] for t in seen], np.uint32), np.array([t[1] for t in seen], np.uint32)
     terms = (xs, zs, rng.normal(size=n_terms))
-    prog = engine.CircuitProgram(b, hamiltonian=terms, options={"tile_qubits": 6, **PLAN_OPTIONS})
+    n_params = len(b.param_names)
 
     def make_inputs(rank: int, seed_offset: int = 0):
         r = np.random.default_rng(20260103 + rank)
-        return r.uniform(-np.pi, np.pi, size=(B, prog.n_params)), None
+        return r.uniform(-np.pi, np.pi, size=(B, n_params)), None
 
     # SURVEY.md §8d canonical traffic: one read + one write of complex128 rho per layer = depth * 32 B * 4^n
-    return dict(name=f"synthetic 10-qubit hardware-efficient ansatz depth 20, noise on every gate, batch {B} per step (BASELINE configs[3])",
-                prog=prog, batch=B, make_inputs=make_inputs, terms=terms, canonical_bytes=depth * 32.0 * 4.0 ** n,
-                cpu_sample=16)
+    return dict(key="hea10",
+                name=f"synthetic 10-qubit hardware-efficient ansatz depth 20, noise on every gate, batch {B} per step (BASELINE configs[3])",
+                builder=b, batch=B, make_inputs=make_inputs, terms=terms, options={"tile_qubits": 6},
+                canonical_bytes=depth * 32.0 * 4.0 ** n, cpu_sample=16, golden="hea10", parity_rows=[0, 1])
 
 
 def _lih_like(n: int = 12, n_occ: int = 4, p: float = 1e-3, n_terms: int = 631, max_excitations=None):
@@ -239,23 +262,25 @@ def _lih_like(n: int = 12, n_occ: int = 4, p: float = 1e-3, n_terms: int = 631, 
 
 
 def workload_lih12():
-    from vqe_errormitigation_b200 import engine
     n, B = 12, 8
     b, terms, n_blocks = _lih_like(n)
-    prog = engine.CircuitProgram(b, hamiltonian=terms, options={"tile_qubits": 6, **PLAN_OPTIONS})
+    n_params = len(b.param_names)
 
     def make_inputs(rank: int, seed_offset: int = 0):
         r = np.random.default_rng(20260106 + rank)
-        return r.normal(scale=0.1, size=(B, prog.n_params)), None
+        return r.normal(scale=0.1, size=(B, n_params)), None
 
     # SURVEY.md §8d canonical traffic: one pass (read + write of complex128 rho) per Pauli-exponential block
-    return dict(name=f"synthetic LiH-like 12-qubit UCCSD ansatz ({n_blocks} Pauli-exponential blocks, noise on every gate, "
+    return dict(key="lih12",
+                name=f"synthetic LiH-like 12-qubit UCCSD ansatz ({n_blocks} Pauli-exponential blocks, noise on every gate, "
                      f"{len(terms[2])} Pauli terms), {B} optimiser chains per GPU per step (BASELINE configs[4]; no LiH data in the reference)",
-                prog=prog, batch=B, make_inputs=make_inputs, terms=terms, canonical_bytes=n_blocks * 32.0 * 4.0 ** n,
-                cpu_sample=0, cpu_ops_fraction=0.002)
+                builder=b, batch=B, make_inputs=make_inputs, terms=terms, options={"tile_qubits": 6},
+                canonical_bytes=n_blocks * 32.0 * 4.0 ** n, cpu_sample=0, cpu_ops_fraction=0.002, golden="lih12_full", parity_rows=[0])
 
 
 WORKLOADS = {"h2_sweep": workload_h2_sweep, "h2_qem": workload_h2_qem, "hea10": workload_hea10, "lih12": workload_lih12}
+ALSO = ("h2_qem", "hea10", "lih12")       # riders of the default run (BASELINE configs[2..4])
+ALSO_STEPS = {"h2_qem": 20, "hea10": 3, "lih12": 2}
 
 
 # ---------------------------------------------------------------------------------------------------------
@@ -263,13 +288,17 @@ WORKLOADS = {"h2_sweep": workload_h2_sweep, "h2_qem": workload_h2_qem, "hea10": 
 # ---------------------------------------------------------------------------------------------------------
 
 class ClockSampler:
-    """Samples SM clock + throttle reasons through NVML while the timed region runs."""
+    """Samples SM clock + throttle reasons through NVML while the timed region runs (rank 0 only: eight 2 ms pollers
+    sharing the host were part of what the end-to-end scaling lost in round 1)."""
 
-    def __init__(self, index: int):
+    def __init__(self, index: int, enabled: bool = True):
         self.samples, self.reasons = [], set()
         self._stop = threading.Event()
         self._thread = None
         self.max_mhz = None
+        self._nv = None
+        if not enabled:
+            return
         try:
             import pynvml
             pynvml.nvmlInit()
@@ -297,6 +326,7 @@ class ClockSampler:
             time.sleep(0.002)
 
     def __enter__(self):
+        self._stop.clear()
         if self._nv is not None:
             self._thread = threading.Thread(target=self._run, daemon=True)
             self._thread.start()
@@ -306,6 +336,7 @@ class ClockSampler:
         self._stop.set()
         if self._thread is not None:
             self._thread.join()
+            self._thread = None
 
     def summary(self):
         if not self.samples:
@@ -323,14 +354,27 @@ def measured_peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def pin_rank_to_cores(local_rank: int, world: int):
+    """One disjoint slice of the host cores per rank (round 1: eight ranks floated over the same cores and the fixed
+    launch + synchronise cost of the host call grew with N)."""
+    try:
+        cores = sorted(os.sched_getaffinity(0))
+        per = max(1, len(cores) // max(world, 1))
+        mine = cores[local_rank * per:(local_rank + 1) * per] or cores
+        os.sched_setaffinity(0, mine)
+        return len(mine)
+    except (AttributeError, OSError):
+        return None
+
+
 def cpu_port_rate(wl, sample: int, threads: int = 0, rank: int = 0):
     """Time the C restatement of the reference algorithm on `sample` circuits of the workload.  Workloads whose single
     circuit takes the CPU many minutes (12 qubits: rho is 256 MiB, 25k ops) set `cpu_ops_fraction`: only that leading
     fraction of the op list is evolved (one identity term as the observable) and the rate is scaled to the whole list."""
     from oracle import c_oracle
-    prog = wl["prog"]
+    b = wl["builder"]
     params, variants = wl["make_inputs"](rank)
-    ops, terms, scale = prog.ops, wl["terms"], 1.0
+    ops, terms, scale = list(b.ops), wl["terms"], 1.0
     frac = wl.get("cpu_ops_fraction")
     if frac:
         m = max(8, int(len(ops) * frac))
@@ -341,8 +385,8 @@ def cpu_port_rate(wl, sample: int, threads: int = 0, rank: int = 0):
     p = params[:sample] if params is not None else None
     v = variants[:sample] if variants is not None else None
     t0 = time.perf_counter()
-    c_oracle.energy_batch(prog.n_qubits, ops, prog.pool, terms, params=p, variants=v, batch=sample,
-                          n_params=prog.n_params, n_slots=prog.n_slots, threads=threads)
+    c_oracle.energy_batch(b.n_qubits, ops, b.pool(), terms, params=p, variants=v, batch=sample,
+                          n_params=len(b.param_names), n_slots=b.n_slots, threads=threads)
     dt = time.perf_counter() - t0
     return sample * scale / dt, dt
 
@@ -355,7 +399,7 @@ def cpu_sample_note(wl, sample):
 
 
 def run_reference(args, wl):
-    """--impl reference: CPU port on all host threads, bounded sample per step."""
+    """--impl reference: CPU port on all host threads, bounded sample per step.  Host-side builder only (no plan)."""
     from oracle import c_oracle
     cores = c_oracle.max_threads()
     # calibrate so the whole run stays within ~2 minutes
@@ -379,8 +423,335 @@ def run_reference(args, wl):
             "config": {"workload": wl["name"], "sample_per_step": sample},
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
                              "sample": f"{cpu_sample_note(wl, sample)} per step, {args.steps} steps (oracle/dm_oracle.c, pthreads)"},
-            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "native": "oracle/libdm_oracle.so only (the op table comes from the host-side ProgramBuilder; libdmx.so is not loaded)"}
     emit(line)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# parity (outside every timed region): the workload's own rows against the oracle
+# ---------------------------------------------------------------------------------------------------------
+
+def parity_check(wl, prog, params_h, variants_h, rank: int):
+    """max |gpu - oracle| over a few rows of THIS workload's inputs.  4-qubit workloads: the C oracle runs live.  The
+    streaming shapes: golden energies the same oracle produced for exactly these circuits and rows
+    (tests/golden/large_energies.json, tools/make_golden_large.py; a 10-qubit depth-20 circuit costs the oracle ~1 min,
+    the full 12-qubit one hours) - valid for rank 0's inputs, checked by a hash of the parameter rows."""
+    import torch
+    rows = [r for r in wl.get("parity_rows", [0]) if r < wl["batch"]]
+    p = params_h[rows] if params_h is not None else None
+    v = variants_h[rows] if variants_h is not None else None
+    got = prog.energies(torch.tensor(p, device="cuda") if p is not None else None,
+                        torch.tensor(v, device="cuda") if v is not None else None, batch=len(rows)).cpu().numpy()
+    b = wl["builder"]
+    if wl.get("golden"):
+        path = os.path.join(ROOT, "tests", "golden", "large_energies.json")
+        rec = None
+        if os.path.exists(path):
+            with open(path) as fh:
+                rec = json.load(fh).get(wl["golden"])
+        if rec is not None and rank == 0:
+            k = min(rec["rows"], len(rows))
+            if hashlib.sha256(np.ascontiguousarray(params_h[:rec["rows"]]).tobytes()).hexdigest() == rec["params_sha"] and rows[:k] == list(range(k)):
+                err = float(np.max(np.abs(got[:k] - np.array(rec["energies"][:k]))))
+                return err, f"{k} row(s) vs tests/golden/large_energies.json[{wl['golden']}] (C oracle on this exact circuit and these rows)"
+        return None, "no golden energies for this rank's rows (the oracle needs minutes to hours per circuit at this size)"
+    from oracle import c_oracle
+    want = c_oracle.energy_batch(b.n_qubits, list(b.ops), b.pool(), wl["terms"], params=p, variants=v, batch=len(rows),
+                                 n_params=len(b.param_names), n_slots=b.n_slots, threads=min(len(rows), 4))
+    return float(np.max(np.abs(got - want))), f"{len(rows)} rows vs the C oracle (oracle/dm_oracle.c), run live"
+
+
+# ---------------------------------------------------------------------------------------------------------
+# one workload on this rank (+ max over ranks)
+# ---------------------------------------------------------------------------------------------------------
+
+def run_workload(wl, ctx, steps: int, warmup: int, with_cpu_baseline: bool, with_e2e: bool):
+    import torch
+    import torch.distributed as dist
+    from vqe_errormitigation_b200 import engine
+    rank, local_rank, world, flush = ctx["rank"], ctx["local_rank"], ctx["world"], ctx["flush"]
+    clocks = ClockSampler(local_rank, enabled=rank == 0)
+    prog, B = get_prog(wl), wl["batch"]
+    info = prog.info
+
+    # ---- CPU baseline first (GPU idle), rank 0 at N=1 only -----------------------------------------------------
+    cpu_baseline = None
+    if with_cpu_baseline and rank == 0 and world == 1:
+        from oracle import c_oracle
+        cores = c_oracle.max_threads()
+        if wl.get("cpu_ops_fraction"):
+            sample = cores
+        else:
+            probe = min(32, B, max(cores, 1))
+            _, dt1 = cpu_port_rate(wl, probe, threads=cores)
+            sample = int(max(probe, min(B, probe / dt1 * 12.0)))
+        rate, dt = cpu_port_rate(wl, sample, threads=cores)
+        cpu_baseline = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
+                        "sample": f"{cpu_sample_note(wl, sample)}, {dt:.1f} s, C restatement of cirq's per-op "
+                                  f"density-matrix algorithm (oracle/dm_oracle.c) on {cores} threads"}
+        if not wl.get("cpu_ops_fraction"):
+            # the reference's own shapes (SURVEY §8d): one process (CPU.get_custom_optimized_state) and its Pool(6)
+            # (MAX_MULTI_PROCESSING_COUNT, src/error_mitigation.py:14), ~2 s of work each
+            by = {str(cores): rate}
+            for th in (1, 6):
+                if th < cores:
+                    n_s = int(max(8, min(B, rate / cores * th * 2.0)))
+                    by[str(th)] = cpu_port_rate(wl, n_s, threads=th)[0]
+            cpu_baseline["by_threads"] = by
+
+    params_h, variants_h = wl["make_inputs"](rank)
+    params_d = torch.tensor(params_h, device="cuda") if params_h is not None else None
+    variants_d = torch.tensor(variants_h, device="cuda") if variants_h is not None else None
+    out = torch.empty(B, dtype=torch.float64, device="cuda")
+
+    def step():
+        prog.energies(params_d, variants_d, batch=B, out=out)
+
+    short_steps = info["path"] != 2
+    for _ in range(warmup):
+        flush.zero_()
+        step()
+    torch.cuda.synchronize()
+    parity_err, parity_src = parity_check(wl, prog, params_h, variants_h, rank)
+    if world > 1:
+        dist.barrier()
+    starts = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
+    ends = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
+    launches0 = engine.launch_count()
+    with clocks:
+        torch.cuda.synchronize()
+        wall0 = time.perf_counter()
+        for i in range(steps):
+            if short_steps:
+                # a ~150 us device-side spin ahead of the flush lets the host run ahead, so that the start event, the
+                # launch and the end event of a microsecond-scale step are queued back to back (otherwise host jitter
+                # leaks into the event interval)
+                torch.cuda._sleep(300_000)
+            flush.zero_()                      # L2 flush between timed iterations (not inside the events)
+            starts[i].record()
+            step()
+            ends[i].record()
+        torch.cuda.synchronize()
+        wall = time.perf_counter() - wall0
+    launches = engine.launch_count() - launches0
+    if world > 1:
+        dist.barrier()
+    dev_ms = sum(s.elapsed_time(e) for s, e in zip(starts, ends))
+    t = torch.tensor([dev_ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dev_ms_max = float(t.item())
+    value = world * B * steps / (dev_ms_max * 1e-3)
+
+    def pinned(a):
+        if a is None:
+            return None
+        b = engine.pinned_empty(a.shape, a.dtype)
+        b[...] = a
+        return b
+
+    def timed(fn, n_steps, n_warm=3):
+        """Wall-clock seconds of n_steps calls (after n_warm untimed ones), max over ranks."""
+        for i in range(n_warm):
+            fn(10_000 + i)
+        if world > 1:
+            dist.barrier()
+        t0 = time.perf_counter()
+        for i in range(n_steps):
+            fn(i)
+        te = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        return float(te.item())
+
+    # ---- e2e: host buffers through the C ABI (H2D + kernels + D2H + sync inside the timed region) -----------------
+    e2e = None
+    mgr = wl.get("manager")
+    if with_e2e and mgr is None:
+        # Parameter batches: params[B, P] in page-locked host memory, energies[B] back into page-locked host memory.
+        # Register-resident plans (path 1) keep up to DEPTH batches in flight (dmx_energy_batch_host_async, each with its
+        # own result buffer; dmx_plan_host_sync after every DEPTH-th step) - the way a sweep or a lock-step optimiser
+        # driver calls it; streaming plans run one synchronous call per step.
+        depth = 4 if info["path"] == 1 else 1
+        params_p = pinned(params_h)
+        res = [engine.pinned_empty(B) for _ in range(depth)]
+
+        def host_step(i):
+            prog.energies_host(params_p, None, batch=B, out=res[i % depth], nowait=depth > 1)
+            if depth > 1 and (i + 1) % depth == 0:
+                prog.host_sync()
+
+        n_e2e = steps if depth == 1 else max(depth, (steps // depth) * depth)
+        e2e_s = timed(host_step, n_e2e, n_warm=depth if depth > 1 else 3)
+        prog.host_sync()
+        zero_copy = info["path"] == 1 and PLAN_OPTIONS.get("host_zero_copy", 1) != 0
+        e2e = {"value": world * B * n_e2e / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(params_h.nbytes), "d2h_bytes_per_step": int(B * 8),
+               "steps": n_e2e, "in_flight": depth,
+               "api": "CircuitProgram.energies_host = dmx_energy_batch_host" + (f"_async, dmx_plan_host_sync every {depth} steps" if depth > 1 else ""),
+               "checksum": float(np.sum(res[0])),
+               "transfer": ("zero-copy: the kernel reads the parameters from and writes the energies to the mapped page-locked host "
+                            "buffers over PCIe" if zero_copy else
+                            "cudaMemcpyAsync H2D / D2H from and to the page-locked host buffers, pipelined in chunks over three streams")}
+        if depth > 1:
+            # the strictly synchronous form (one call, one synchronise per step) beside it
+            sync_s = timed(lambda i: prog.energies_host(params_p, None, batch=B, out=res[0]), steps)
+            e2e["synchronous"] = {"value": world * B * steps / sync_s, "unit": UNIT, "api": "dmx_energy_batch_host, one synchronise per step"}
+    elif with_e2e:
+        # QEM: what the reference's own flow hands to its workers is the identifier -> count dictionary
+        # (error_mitigation.py:492-497): the UNIQUE rows of this rank's 125000 sampled identifiers and their counts, prepared
+        # outside the timed region (set_identifier_range is a separate call there too).  Timed: unique rows H2D, kernels,
+        # values D2H, weighted mean.
+        uniq, counts = np.unique(variants_h, axis=0, return_counts=True)
+        uniq_p, signs_u = pinned(uniq), mgr.variant_signs(uniq)
+        est = [None]
+
+        def host_step(i):
+            est[0] = mgr.evaluate_variants(uniq_p, signs_u, counts)
+        e2e_s = timed(host_step, steps)
+        e2e = {"value": world * B * steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(uniq.nbytes), "d2h_bytes_per_step": int(len(uniq) * 8),
+               "steps": steps, "api": "IErrorMitigationManager.evaluate_variants(unique rows, signs, counts) -> dmx_energy_batch_host",
+               "unique_rows": int(len(uniq)), "rows_represented": int(B), "mu": float(est[0][1]),
+               "transfer": "unique identifier rows + counts (the reference's dict) instead of the raw 125000 x 122 table"}
+        # the raw table through the same C-ABI call (round 1's e2e): PCIe-bound by the 15 MB table
+        raw_p, raw_out, n_raw = pinned(variants_h), engine.pinned_empty(B), max(3, steps // 4)
+        raw_s = timed(lambda i: prog.energies_host(None, raw_p, batch=B, out=raw_out), n_raw)
+        e2e["raw_table"] = {"value": world * B * n_raw / raw_s, "unit": UNIT, "h2d_bytes_per_step": int(variants_h.nbytes),
+                            "d2h_bytes_per_step": int(B * 8)}
+
+        # the whole estimator with the variants drawn ON the device; under --gpus N this block CONTAINS the all-reduce
+        def sampled(i):
+            est[0] = mgr.get_mu_effective_sampled(B * world, seed=20260102 + i)
+        samp_s = timed(sampled, steps)
+        e2e["device_sampling"] = {"value": world * B * steps / samp_s, "unit": UNIT, "h2d_bytes_per_step": int(wl["qp_bytes"]),
+                                  "d2h_bytes_per_step": 24,
+                                  "api": "IErrorMitigationManager.get_mu_effective_sampled (dmx_qp_sampler_draw + dmx_energy_batch + "
+                                         "dmx_qp_reduce + all-reduce of 3 doubles over NCCL when N > 1)",
+                                  "estimate": [float(est[0][0]), float(est[0][1]), int(est[0][2])]}
+
+    # ---- QEM: device-timed estimator (draw + evaluate + reduce + all-reduce inside CUDA events), per-N rate ---------
+    estimator = None
+    if mgr is not None:
+        from vqe_errormitigation_b200 import parallel
+        sampler = engine.QpSampler(mgr.quasi_probabilities())
+        lo, hi = parallel.shard_bounds(B * world, rank, world)
+
+        def est_step(seed):
+            variants, signs = sampler.draw(hi - lo, seed, first_sample=lo)
+            values = prog.energies(None, variants, batch=hi - lo)
+            return parallel.sharded_sums(values, signs)       # device tensor [3]; all-reduce on this stream when N > 1
+        for i in range(3):
+            est_step(100 + i)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        es = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
+        ee = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
+        for i in range(steps):
+            torch.cuda._sleep(300_000)
+            flush.zero_()
+            es[i].record()
+            sums = est_step(i)
+            ee[i].record()
+        torch.cuda.synchronize()
+        ms = torch.tensor([sum(a.elapsed_time(b) for a, b in zip(es, ee))], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        s0, _s1, n = (float(x) for x in sums.cpu())
+        estimator = {"value": world * B * steps / (float(ms.item()) * 1e-3), "unit": "variants/s", "ms_per_estimate": float(ms.item()) / steps,
+                     "contains": "Philox draw + variant evaluation + dmx_qp_reduce" + (" + NCCL all-reduce of 3 doubles" if world > 1 else ""),
+                     "timing": "CUDA events on the launch stream, max over ranks", "variants_per_estimate": int(B * world),
+                     "estimate": [mgr.total_cost() * s0 / n, int(n)]}
+
+    # ---- QEM: deduplicated device rate (SURVEY App. C.3) ---------------------------------------------------------
+    dedup = None
+    if variants_h is not None and world == 1 and with_e2e:
+        uniq = np.unique(variants_h, axis=0)
+        uniq_d = torch.tensor(uniq, device="cuda")
+        uout = torch.empty(len(uniq), dtype=torch.float64, device="cuda")
+        for _ in range(3):
+            prog.energies(None, uniq_d, batch=len(uniq), out=uout)
+        torch.cuda.synchronize()
+        us, ue = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t_ms = 0.0
+        for _ in range(steps):
+            torch.cuda._sleep(300_000)
+            flush.zero_()
+            us.record()
+            prog.energies(None, uniq_d, batch=len(uniq), out=uout)
+            ue.record()
+            torch.cuda.synchronize()
+            t_ms += us.elapsed_time(ue)
+        dedup = {"unique_rows": int(len(uniq)), "rows": int(B), "value": B * steps / (t_ms * 1e-3), "unit": UNIT,
+                 "note": "variants represented per second when only the distinct rows are evaluated (device time of the unique-row "
+                         "batch); the roofline fraction is defined on the raw rate"}
+
+    if rank != 0:
+        return None
+
+    # ---- roofline of the dominant kernel -----------------------------------------------------------------------------
+    ms_per_step = dev_ms_max / steps
+    kernel_s = ms_per_step * 1e-3
+    kern = {0: "dmx_tile_kernel", 1: "dmx_frame32_kernel (dmx_frame_kernel when more than 32 coefficients are live)",
+            2: "dmx_stream3_kernel / dmx_stream3b_kernel (streaming passes)"}[info["path"]]
+    traffic = ncu_util = None
+    tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+    if os.path.exists(tpath):
+        with open(tpath) as fh:
+            recorded = json.load(fh)
+        traffic = recorded.get(wl["key"])
+        ncu_util = recorded.get("_ncu", {}).get(wl["key"])
+    sm_clock = (clocks.summary()["sm_mhz"] or 1965.0) * 1e6
+    smem_peak = 148 * 128 * sm_clock / 1e9
+    fp64_peak, hbm_peak, hbm_src = ctx["fp64_peak"], ctx["hbm_peak"], ctx["hbm_src"]
+    if info["path"] == 2:
+        # `achieved` / `frac`: SURVEY.md §8d canonical traffic (complex128 rho, one read + write per layer / block) over
+        # the step time.  `frac_executed`: the bytes this engine really moves (real Pauli vector, fused passes) over the
+        # same time - how close the kernel itself runs to the HBM roof.
+        canon = wl.get("canonical_bytes") or info["canonical_hbm_bytes_per_circuit"]
+        ach = canon * B / kernel_s / 1e9
+        ex_gbs = info["hbm_bytes_per_circuit"] * B / kernel_s / 1e9
+        roofline = {"bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
+                    "traffic": traffic, "kernel": kern, "peak_source": hbm_src,
+                    "algorithmic_bytes_per_circuit": canon,
+                    "algorithmic_model": "SURVEY.md 8d: 32 B x 4^n per layer (HEA) / per Pauli-exponential block (UCCSD)",
+                    "frac_executed": ex_gbs / hbm_peak,
+                    "executed": {"hbm_bytes_per_circuit": info["hbm_bytes_per_circuit"], "hbm_gbs": ex_gbs, "hbm_frac": ex_gbs / hbm_peak,
+                                 "smem_bytes_per_circuit": info["smem_bytes_per_circuit"],
+                                 "smem_gbs": info["smem_bytes_per_circuit"] * B / kernel_s / 1e9,
+                                 "smem_frac": info["smem_bytes_per_circuit"] * B / kernel_s / 1e9 / smem_peak,
+                                 "fp64_tflops": info["flops_per_circuit"] * B / kernel_s / 1e12,
+                                 "fp64_frac": info["flops_per_circuit"] * B / kernel_s / 1e12 / fp64_peak,
+                                 "note": "the binding resource is the shared-memory exchange between sweeps "
+                                         "(148 SM x 128 B/clk at the sampled clock), then HBM"}}
+    else:
+        ach = info["flops_per_circuit"] * B / kernel_s / 1e12
+        smem_ach = info["smem_bytes_per_circuit"] * B / kernel_s / 1e9
+        roofline = {"bound": "fp64", "achieved": ach, "peak": fp64_peak, "unit": "TFLOP/s", "frac": ach / fp64_peak,
+                    "traffic": traffic, "kernel": kern,
+                    "peak_source": "FP64 FMA micro-benchmark run live (dmx_measure_fp64_peak); MEASURED_PEAKS.json has no FP64 figure",
+                    "executed_flops_per_circuit": info["flops_per_circuit"],
+                    "canonical_flops_per_circuit": info["canonical_flops_per_circuit"],
+                    "canonical_equiv_tflops": info["canonical_flops_per_circuit"] * B / kernel_s / 1e12,
+                    "smem": {"achieved_gbs": smem_ach, "peak_gbs": smem_peak, "frac": smem_ach / smem_peak,
+                             "note": "shared-memory exchange bytes per circuit x rate vs 148 SM x 128 B/clk at the sampled SM clock"},
+                    "hbm": {"achieved_gbs": info["hbm_bytes_per_circuit"] * B / kernel_s / 1e9, "peak_gbs": hbm_peak}}
+    if ncu_util:
+        roofline["ncu"] = ncu_util      # recorded capture (profiles/), not re-measured by this run
+    res = {"value": value, "unit": UNIT, "steps": steps, "warmup": warmup, "ms_per_step": ms_per_step,
+           "config": {"workload": wl["name"], "batch_per_gpu": B, "l2": "flushed (192 MiB memset) between timed steps",
+                      "timing": "CUDA events per step on the launch stream, summed; max over ranks" + ("; a device-side spin precedes each flush so the host queues ahead" if short_steps else ""),
+                      "plan": {k: info[k] for k in ("path", "n_blocks", "n_segments", "n_passes", "tile_qubits", "n_terms")},
+                      "wall_ms_incl_flush": 1e3 * wall},
+           "clocks": clocks.summary(), "parity_max_abs_err": parity_err, "parity_source": parity_src,
+           "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline}
+    if estimator:
+        res["estimator"] = estimator
+    if dedup:
+        res["dedup"] = dedup
+    if cpu_baseline:
+        res["cpu_baseline"] = cpu_baseline
+    return res
 
 
 # ---------------------------------------------------------------------------------------------------------
@@ -420,6 +791,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-also", action="store_true", help="skip the short runs of the other BASELINE configs")
     ap.add_argument("--opt", action="append", default=[], help="planner option key=value (dmx_plan_set_option)")
     args = ap.parse_args()
     for kv in args.opt:
@@ -437,6 +809,8 @@ def main():
         run_reference(args, WORKLOADS[args.workload]())
         return
 
+    cores_per_rank = pin_rank_to_cores(local_rank, world) if world > 1 else None
+
     import torch
     import torch.distributed as dist
     from vqe_errormitigation_b200 import engine
@@ -448,220 +822,41 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # keep stdout to the single JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    wl = WORKLOADS[args.workload]()
-    prog, B = wl["prog"], wl["batch"]
-    info = prog.info
-
-    # ---- CPU baseline first (GPU idle), rank 0 at N=1 only -----------------------------------------------------
-    cpu_baseline = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        from oracle import c_oracle
-        cores = c_oracle.max_threads()
-        if wl.get("cpu_ops_fraction"):
-            sample = cores
-        else:
-            probe = min(32, B, max(cores, 1))
-            _, dt1 = cpu_port_rate(wl, probe, threads=cores)
-            sample = int(max(probe, min(B, probe / dt1 * 12.0)))
-        rate, dt = cpu_port_rate(wl, sample, threads=cores)
-        cpu_baseline = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
-                        "sample": f"{cpu_sample_note(wl, sample)}, {dt:.1f} s, C restatement of cirq's per-op "
-                                  f"density-matrix algorithm (oracle/dm_oracle.c) on {cores} threads"}
-        if not wl.get("cpu_ops_fraction"):
-            # the reference's own shapes: one process (CPU.get_custom_optimized_state) and its Pool(6)
-            # (MAX_MULTI_PROCESSING_COUNT, src/error_mitigation.py:14), ~2 s of work each
-            by = {str(cores): rate}
-            for th in (1, 6):
-                if th < cores:
-                    n_s = int(max(8, min(B, rate / cores * th * 2.0)))
-                    by[str(th)] = cpu_port_rate(wl, n_s, threads=th)[0]
-            cpu_baseline["by_threads"] = by
-
-    params_h, variants_h = wl["make_inputs"](rank)
-    params_d = torch.tensor(params_h, device="cuda") if params_h is not None else None
-    variants_d = torch.tensor(variants_h, device="cuda") if variants_h is not None else None
-    out = torch.empty(B, dtype=torch.float64, device="cuda")
-    flush = torch.empty(192 * 1024 * 1024, dtype=torch.uint8, device="cuda")  # > 126 MB L2
-
-    fp64_peak = engine.measure_fp64_peak()
     hbm_peak, hbm_src = measured_peaks()
+    ctx = {"rank": rank, "local_rank": local_rank, "world": world,
+           "flush": torch.empty(192 * 1024 * 1024, dtype=torch.uint8, device="cuda"),     # > 126 MB L2
+           "fp64_peak": engine.measure_fp64_peak(), "hbm_peak": hbm_peak, "hbm_src": hbm_src}
 
-    def step():
-        prog.energies(params_d, variants_d, batch=B, out=out)
-
-    short_steps = prog.info["path"] != 2
-
-    for _ in range(args.warmup):
-        flush.zero_()
-        step()
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    starts = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
-    ends = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
-    launches0 = engine.launch_count()
-    with ClockSampler(local_rank) as clocks:
-        torch.cuda.synchronize()
-        wall0 = time.perf_counter()
-        for i in range(args.steps):
-            if short_steps:
-                # a ~150 us device-side spin ahead of the flush lets the host run ahead, so that the start event, the
-                # launch and the end event of a microsecond-scale step are queued back to back (otherwise host jitter -
-                # eight ranks and their clock samplers share the CPU - leaks into the event interval)
-                torch.cuda._sleep(300_000)
-            flush.zero_()                      # L2 flush between timed iterations (not inside the events)
-            starts[i].record()
-            step()
-            ends[i].record()
-        torch.cuda.synchronize()
-        wall = time.perf_counter() - wall0
-    launches = engine.launch_count() - launches0
-    if world > 1:
-        dist.barrier()
-    dev_ms = sum(s.elapsed_time(e) for s, e in zip(starts, ends))
-    t = torch.tensor([dev_ms], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    dev_ms_max = float(t.item())
-    value = world * B * args.steps / (dev_ms_max * 1e-3)
-
-    # ---- e2e: host buffers through the C ABI (H2D + kernels + D2H + sync inside the timed region) -----------------
-    e2e = None
-    if not args.no_e2e:
-        # inputs and result live in page-locked host memory (the contract's "pinned host memory")
-        def pinned(a):
-            if a is None:
-                return None
-            b = engine.pinned_empty(a.shape, a.dtype)
-            b[...] = a
-            return b
-        params_p, variants_p, res = pinned(params_h), pinned(variants_h), engine.pinned_empty(B)
-        for _ in range(3):
-            prog.energies_host(params_p, variants_p, batch=B, out=res)
-        if world > 1:
-            dist.barrier()
-        t0 = time.perf_counter()
-        for _ in range(args.steps):
-            prog.energies_host(params_p, variants_p, batch=B, out=res)
-        e2e_s = time.perf_counter() - t0
-        te = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
-        if world > 1:
-            dist.all_reduce(te, op=dist.ReduceOp.MAX)
-        h2d = (params_h.nbytes if params_h is not None else 0) + (variants_h.nbytes if variants_h is not None else 0)
-        e2e = {"value": world * B * args.steps / float(te.item()), "unit": UNIT, "h2d_bytes_per_step": int(h2d),
-               "d2h_bytes_per_step": int(B * 8), "api": "dmx_energy_batch_host (CircuitProgram.energies_host)",
-               "checksum": float(np.sum(res)),
-               "transfer": ("zero-copy: the kernel reads the parameters from and writes the energies to the mapped page-locked host "
-                            "buffers over PCIe (one launch + one synchronise per step)"
-                            if prog.info["path"] == 1 and variants_h is None and not any(o.startswith("host_zero_copy=0") for o in args.opt)
-                            else "cudaMemcpyAsync H2D / D2H from and to the page-locked host buffers, pipelined in chunks over three streams")}
-
-    # ---- QEM only: the same estimate with the variants drawn on the device (no variant table crosses PCIe) ----------
-    if e2e is not None and wl.get("sampled_step"):
-        for i in range(3):
-            wl["sampled_step"](1000 + i)
-        if world > 1:
-            dist.barrier()
-        t0 = time.perf_counter()
-        for i in range(args.steps):
-            est = wl["sampled_step"](i)
-        ts = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
-        if world > 1:
-            dist.all_reduce(ts, op=dist.ReduceOp.MAX)
-        e2e["device_sampling"] = {"value": world * B * args.steps / float(ts.item()), "unit": UNIT,
-                                  "h2d_bytes_per_step": int(wl["sampled_h2d"]), "d2h_bytes_per_step": 24,
-                                  "api": "IErrorMitigationManager.get_mu_effective_sampled (dmx_qp_sample_variants + "
-                                         "dmx_energy_batch + dmx_qp_reduce [+ 24-byte all-reduce])",
-                                  "estimate": [float(est[0]), float(est[1]), int(est[2])]}
-
-    # ---- QEM only: deduplicated rate - the reference evaluates each distinct identifier once and weights it
-    # by its count (error_mitigation.py:492-497); here: unique rows of this rank's table, found on the host outside the timing
-    dedup = None
-    if variants_h is not None and world == 1 and not args.no_e2e:
-        uniq = np.unique(variants_h, axis=0)
-        uniq_d = torch.tensor(uniq, device="cuda")
-        uout = torch.empty(len(uniq), dtype=torch.float64, device="cuda")
-        for _ in range(3):
-            prog.energies(None, uniq_d, batch=len(uniq), out=uout)
-        torch.cuda.synchronize()
-        us, ue = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        t_ms = 0.0
-        for _ in range(args.steps):
-            torch.cuda._sleep(300_000)
-            flush.zero_()
-            us.record()
-            prog.energies(None, uniq_d, batch=len(uniq), out=uout)
-            ue.record()
-            torch.cuda.synchronize()
-            t_ms += us.elapsed_time(ue)
-        dedup = {"unique_rows": int(len(uniq)), "rows": int(B), "value": B * args.steps / (t_ms * 1e-3), "unit": UNIT,
-                 "note": "variants represented per second when only the distinct rows are evaluated (device time of the unique-row "
-                         "batch; np.unique on the host not included); the roofline fraction is defined on the raw rate"}
-
-    if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
-        return
-
-    # ---- roofline of the dominant kernel -----------------------------------------------------------------------------
-    ms_per_step = dev_ms_max / args.steps
-    kernel_s = ms_per_step * 1e-3
-    path = {0: "dmx_tile_kernel", 1: "dmx_frame32_kernel (dmx_frame_kernel when more than 32 coefficients are live)",
-            2: "dmx_stream3_kernel (streaming passes)"}[info["path"]]
-    traffic = ncu_util = None
-    tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
-    if os.path.exists(tpath):
-        with open(tpath) as fh:
-            recorded = json.load(fh)
-        traffic = recorded.get(args.workload)
-        ncu_util = recorded.get("_ncu", {}).get(args.workload)
-    if info["path"] == 2:
-        # algorithmic bytes = SURVEY.md §8d canonical traffic (complex128 rho, one read + write per layer / block);
-        # the engine's own traffic (real Pauli vector, fused passes) is reported beside it
-        canon = wl.get("canonical_bytes") or info["canonical_hbm_bytes_per_circuit"]
-        ach = canon * B / kernel_s / 1e9
-        sm_clock = (clocks.summary()["sm_mhz"] or 1965.0) * 1e6
-        smem_peak = 148 * 128 * sm_clock / 1e9
-        roofline = {"bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
-                    "traffic": traffic, "kernel": path, "peak_source": hbm_src,
-                    "algorithmic_bytes_per_circuit": canon,
-                    "algorithmic_model": "SURVEY.md 8d: 32 B x 4^n per layer (HEA) / per Pauli-exponential block (UCCSD)",
-                    "executed": {"hbm_bytes_per_circuit": info["hbm_bytes_per_circuit"],
-                                 "hbm_gbs": info["hbm_bytes_per_circuit"] * B / kernel_s / 1e9,
-                                 "smem_bytes_per_circuit": info["smem_bytes_per_circuit"],
-                                 "smem_gbs": info["smem_bytes_per_circuit"] * B / kernel_s / 1e9,
-                                 "smem_frac": info["smem_bytes_per_circuit"] * B / kernel_s / 1e9 / smem_peak,
-                                 "fp64_tflops": info["flops_per_circuit"] * B / kernel_s / 1e12,
-                                 "fp64_frac": info["flops_per_circuit"] * B / kernel_s / 1e12 / fp64_peak,
-                                 "note": "the binding resource is the shared-memory exchange between sweeps "
-                                         "(148 SM x 128 B/clk at the sampled clock), then HBM"}}
-    else:
-        ach = info["flops_per_circuit"] * B / kernel_s / 1e12
-        sm_clock = (clocks.summary()["sm_mhz"] or 1965.0) * 1e6
-        smem_peak = 148 * 128 * sm_clock / 1e9
-        smem_ach = info["smem_bytes_per_circuit"] * B / kernel_s / 1e9
-        roofline = {"bound": "fp64", "achieved": ach, "peak": fp64_peak, "unit": "TFLOP/s", "frac": ach / fp64_peak,
-                    "traffic": traffic, "kernel": path,
-                    "peak_source": "FP64 FMA micro-benchmark run live (dmx_measure_fp64_peak); MEASURED_PEAKS.json has no FP64 figure",
-                    "executed_flops_per_circuit": info["flops_per_circuit"],
-                    "canonical_flops_per_circuit": info["canonical_flops_per_circuit"],
-                    "canonical_equiv_tflops": info["canonical_flops_per_circuit"] * B / kernel_s / 1e12,
-                    "smem": {"achieved_gbs": smem_ach, "peak_gbs": smem_peak, "frac": smem_ach / smem_peak,
-                             "note": "shared-memory exchange bytes per circuit x rate vs 148 SM x 128 B/clk at the sampled SM clock"},
-                    "hbm": {"achieved_gbs": info["hbm_bytes_per_circuit"] * B / kernel_s / 1e9, "peak_gbs": hbm_peak}}
-    if ncu_util:
-        roofline["ncu"] = ncu_util      # recorded capture (profiles/), not re-measured by this run
-    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
-            "data": "synthetic",
-            "config": {"workload": wl["name"], "batch_per_gpu": B, "l2": "flushed (192 MiB memset) between timed steps",
-                       "timing": "CUDA events per step on the launch stream, summed; max over ranks" + ("; a device-side spin precedes each flush so the host queues ahead" if short_steps else ""),
-                       "plan": {k: info[k] for k in ("path", "n_blocks", "n_segments", "n_passes", "tile_qubits", "n_terms")},
-                       "wall_ms_incl_flush": 1e3 * wall},
-            "clocks": clocks.summary(), "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
-            **({"dedup": dedup} if dedup else {}),
-            "cpu_baseline": cpu_baseline}
-    emit(line)
+    head = run_workload(WORKLOADS[args.workload](), ctx, args.steps, args.warmup,
+                        with_cpu_baseline=not args.no_cpu_baseline, with_e2e=not args.no_e2e)
+    also = {}
+    if args.workload == "h2_sweep" and not args.no_also:
+        for key in ALSO:
+            t0 = time.perf_counter()
+            try:
+                res = run_workload(WORKLOADS[key](), ctx, ALSO_STEPS[key], 3, with_cpu_baseline=False, with_e2e=not args.no_e2e)
+            except Exception as exc:  # noqa: BLE001 - a rider must not take the headline line down
+                if world > 1:
+                    raise                  # ranks must stay in step through the collectives
+                res = {"error": f"{type(exc).__name__}: {exc}"}
+            if res is not None:
+                res["wall_s"] = round(time.perf_counter() - t0, 2)
+                also[key] = res
+    if rank == 0:
+        line = {"metric": METRIC, "value": head["value"], "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": head["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+                "data": "synthetic", "config": head["config"], "clocks": head["clocks"],
+                "parity_max_abs_err": head["parity_max_abs_err"], "parity_source": head["parity_source"],
+                "e2e": head["e2e"], "gpu_launches": head["gpu_launches"], "roofline": head["roofline"]}
+        for k in ("estimator", "dedup"):
+            if k in head:
+                line[k] = head[k]
+        line["cpu_baseline"] = head.get("cpu_baseline")
+        if cores_per_rank:
+            line["config"]["host_cores_per_rank"] = cores_per_rank
+        if also:
+            line["also"] = also
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 

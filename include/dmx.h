@@ -16,7 +16,8 @@
  *   - there is no CPU execution path: without a CUDA device the execution calls fail with
  *     DMX_ERR_CUDA.  Plan construction/inspection is host-only work and needs no device.
  *   - a plan is immutable after dmx_plan_finalize(); it may be used from several host threads /
- *     streams concurrently (workspace is per call).
+ *     streams concurrently (workspace is per call).  Its device tables are uploaded to the device that is
+ *     current at the first execution call; executing it with another current device fails with DMX_ERR_STATE.
  */
 #ifndef DMX_H_
 #define DMX_H_
@@ -132,8 +133,10 @@ int dmx_plan_set_hamiltonian(dmx_plan* plan, int n_terms, const uint32_t* xmask,
  *   "tile_qubits"  k    resident qubits per streaming tile, 4..7 (default 6)
  *   "remap"        0/1  streaming: re-order the qubits in HBM between passes (default 1)
  *   "triples"      0/1  streaming: three resident codes per thread instead of two (default 1)
- * Library-wide execution switches (take effect for every plan of the process):
+ * Execution switches (also per plan - they are read from the plan at launch time, so one plan's setting never changes
+ * how another plan runs):
  *   "stream_kernel"   0/1  0 = generic tile kernel for every streaming pass (default 1)
+ *   "bulk"            0/1  streaming: cp.async.bulk + mbarrier tile staging, double-buffered persistent CTAs (default 1)
  *   "stream_chunk"    n    circuits per streaming pass launch, 0 = automatic (default 0)
  *   "frame32"         0/1  compact warp-per-circuit frame kernel when <= 32 coefficients are live (default 1)
  *   "segment_cpb"     4|8  circuits per warp / thread of the frame kernels (default 8)
@@ -177,7 +180,7 @@ int dmx_diag_batch(dmx_plan* plan, int64_t batch, const double* d_params, const 
 int dmx_pauli_batch(dmx_plan* plan, int64_t batch, const double* d_params, const uint8_t* d_variants,
                     double* d_pauli, void* d_workspace, size_t workspace_bytes, void* stream);
 
-/* d_out[3] = { sum_b w[b]*v[b], sum_b (w[b]*v[b])^2, sum_b |w[b]|>0 ? count[b] : 0 } with
+/* d_out[3] = { sum_b w[b]*v[b], sum_b (w[b]*v[b])^2, sum_b count[b] } with
  * w[b] = d_weights[b] (sign * prod(weights) * count) — the per-rank partial of np.mean at
  * src/error_mitigation.py:399,451; the 24-byte cross-GPU sum is the caller's all-reduce.
  * d_counts may be NULL (every row counts 1).  Deterministic (fixed reduction tree). */
@@ -207,6 +210,15 @@ int dmx_qp_sample_variants(int n_slots, const int32_t* n_choices, const double* 
  * out, and waits.  This is the call a non-CUDA-aware host (the reference's Python) binds. */
 int dmx_energy_batch_host(dmx_plan* plan, int64_t batch, const double* h_params, const uint8_t* h_variants,
                           double* h_energy);
+
+/* Asynchronous form for callers that keep several batches in flight (a lock-step optimiser driver, a sweep): queues the
+ * batch and returns; dmx_plan_host_sync waits for everything queued on the plan.  h_energy / h_params must stay valid and
+ * untouched until then.  Only page-locked, mapped buffers on register-resident plans run asynchronously (the kernel then
+ * reads / writes host memory itself); every other case executes synchronously inside the call, so the pair
+ * async + sync is always correct. */
+int dmx_energy_batch_host_async(dmx_plan* plan, int64_t batch, const double* h_params, const uint8_t* h_variants,
+                                double* h_energy);
+int dmx_plan_host_sync(dmx_plan* plan);
 
 /* ---- measurement helpers ---------------------------------------------------------------------------- */
 /* FP64 FMA micro-benchmark on the current device: returns achieved TFLOP/s (roofline denominator the

@@ -24,6 +24,7 @@ def load():
             raise ImportError(f"{_PATH} missing: run `make -C oracle` (or __graft_entry__.build())")
         _lib = C.CDLL(_PATH)
         _lib.orc_energy_batch.restype = C.c_int
+        _lib.orc_energy_batch_wide.restype = C.c_int
         _lib.orc_density.restype = C.c_int
         _lib.orc_max_threads.restype = C.c_int
     return _lib
@@ -42,7 +43,10 @@ def max_threads() -> int:
     return int(load().orc_max_threads())
 
 
-def energy_batch(n, ops, pool, terms, params=None, variants=None, batch=None, n_params=0, n_slots=0, threads=0) -> np.ndarray:
+def energy_batch(n, ops, pool, terms, params=None, variants=None, batch=None, n_params=0, n_slots=0, threads=0,
+                 wide=False) -> np.ndarray:
+    """``wide``: a few large circuits, one after the other, each split over ``threads`` OpenMP threads (instead of one
+    circuit per thread)."""
     lib = load()
     x, z, c = (np.ascontiguousarray(terms[0], np.uint32), np.ascontiguousarray(terms[1], np.uint32), np.ascontiguousarray(terms[2], np.float64))
     pool = np.ascontiguousarray(pool, np.float64)
@@ -52,7 +56,8 @@ def energy_batch(n, ops, pool, terms, params=None, variants=None, batch=None, n_
         batch = p.shape[0] if p is not None else v.shape[0]
     out = np.empty(batch, np.float64)
     arr = _convert_ops(ops)
-    rc = lib.orc_energy_batch(C.c_int(n), arr, C.c_int(len(ops)), pool.ctypes.data_as(C.c_void_p), C.c_int(len(c)),
+    fn = lib.orc_energy_batch_wide if wide else lib.orc_energy_batch
+    rc = fn(C.c_int(n), arr, C.c_int(len(ops)), pool.ctypes.data_as(C.c_void_p), C.c_int(len(c)),
                               x.ctypes.data_as(C.c_void_p), z.ctypes.data_as(C.c_void_p), c.ctypes.data_as(C.c_void_p),
                               p.ctypes.data_as(C.c_void_p) if p is not None else None, C.c_int(n_params),
                               v.ctypes.data_as(C.c_void_p) if v is not None else None, C.c_int(n_slots), C.c_int64(batch),

@@ -25,6 +25,11 @@
 
 typedef double complex cplx;
 
+/* > 1: the row loops of one circuit are split over this many OpenMP threads (orc_energy_batch_wide: a few LARGE
+ * circuits, e.g. 10-12 qubits in the parity tests); 1: serial inside a circuit (orc_energy_batch: one circuit per
+ * pthread).  Same arithmetic per element either way - every (row, column) group is written by exactly one thread. */
+static int g_wide = 1;
+
 typedef struct {
     int32_t kind, n_qubits, q0, q1, mat, n_mats, param, axis, slot;
     uint32_t flags;
@@ -37,6 +42,7 @@ enum { OP_UNITARY = 1, OP_KRAUS = 2, OP_ROTATION = 3, OP_VARIANT = 4, OP_MEASURE
 /* out = M applied to the row index bits (left) and conj(M) to the column bits (right): out = M rho M^dagger */
 static void conjugate_1q(int n, const cplx* rho, cplx* out, const cplx m[4], int q, int accumulate) {
     const int dim = 1 << n, bit = 1 << (n - 1 - q);
+#pragma omp parallel for schedule(static) num_threads(g_wide) if (g_wide > 1)
     for (int r = 0; r < dim; ++r) {
         if (r & bit) continue;
         for (int c = 0; c < dim; ++c) {
@@ -63,6 +69,7 @@ static void conjugate_1q(int n, const cplx* rho, cplx* out, const cplx m[4], int
 static void conjugate_2q(int n, const cplx* rho, cplx* out, const cplx m[16], int q0, int q1, int accumulate) {
     const int dim = 1 << n, b0 = 1 << (n - 1 - q0), b1 = 1 << (n - 1 - q1);
     const int off[4] = {0, b1, b0, b0 | b1}; /* local index = 2*bit(q0) + bit(q1) */
+#pragma omp parallel for schedule(static) num_threads(g_wide) if (g_wide > 1)
     for (int r = 0; r < dim; ++r) {
         if (r & (b0 | b1)) continue;
         for (int c = 0; c < dim; ++c) {
@@ -230,6 +237,17 @@ int orc_energy_batch(int n, const orc_op* ops, int n_ops, const double* pool, in
         for (int t = 0; t < started; ++t) pthread_join(th[t], NULL);
     }
     return atomic_load(&j.failed) ? -1 : 0;
+}
+
+/* A few large circuits: evolved one after the other, each with its row loops split over n_threads OpenMP threads. */
+int orc_energy_batch_wide(int n, const orc_op* ops, int n_ops, const double* pool, int n_terms, const uint32_t* xm, const uint32_t* zm,
+                          const double* coeff, const double* params, int n_params, const uint8_t* variants, int n_slots, int64_t batch,
+                          double* out, int n_threads) {
+    if (n_threads <= 0) n_threads = orc_max_threads();
+    g_wide = n_threads;
+    const int rc = orc_energy_batch(n, ops, n_ops, pool, n_terms, xm, zm, coeff, params, n_params, variants, n_slots, batch, out, 1);
+    g_wide = 1;
+    return rc;
 }
 
 /* Single circuit, full density matrix out (row-major complex128). */

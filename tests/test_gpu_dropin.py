@@ -88,7 +88,7 @@ def test_error_mitigation_manager_gpu_matches_oracle_values():
     np.random.seed(7)
     mgr.set_identifier_range(10000)
     values, mu = mgr.get_mu_effective(error_mitigation=True, density_representation=True)
-    prog = mgr._variant_program()
+    prog = mgr.variant_program()
     assert prog.info["path"] == 1
     want = CO.energy_batch(4, prog.ops, prog.pool, prog.hamiltonian, variants=mgr._rows, n_slots=prog.n_slots, threads=4)
     signs, weights = mgr._signs_and_weights(mgr._rows)

@@ -462,3 +462,171 @@ def test_eleven_qubit_long_range_circuit_against_c_oracle(tile):
     got = prog.energies(torch.tensor(params)).cpu().numpy()
     want = CO.energy_batch(n, prog.ops, prog.pool, terms, params=params, n_params=prog.n_params, threads=3)
     assert np.max(np.abs(got - want)) < TOL
+
+
+# ---- the BENCHMARKED shapes (bench.py workloads), against the C oracle -----------------------------------------------
+
+def _large_golden(key):
+    import json
+    import os
+    from workloads import GOLDEN
+    path = os.path.join(GOLDEN, "large_energies.json")
+    if not os.path.exists(path):
+        return None
+    with open(path) as fh:
+        return json.load(fh).get(key)
+
+
+def test_hea10_depth20_bench_workload_against_c_oracle():
+    """BASELINE configs[3] exactly as bench.workload_hea10 builds it (10 qubits, depth 20, 1160 ops, 100 Pauli terms, 18
+    remapped passes / 112 triple sweeps): rows 0-1 of the bench inputs against the C oracle run live (one circuit per
+    thread, ~1 min) and against the committed golden energies the same oracle produced (tools/make_golden_large.py)."""
+    import bench
+    from oracle import c_oracle as CO
+    torch = torch_cuda()
+    wl = bench.workload_hea10()
+    prog = bench.get_prog(wl)
+    assert prog.info["path"] == 2 and prog.info["n_passes"] >= 10 and prog.info["n_terms"] == 100 and len(prog.ops) == 1160
+    params = wl["make_inputs"](0)[0][:2]
+    got = prog.energies(torch.tensor(params), workspace_states=2).cpu().numpy()
+    want = CO.energy_batch(10, prog.ops, prog.pool, wl["terms"], params=params, n_params=prog.n_params, threads=2)
+    assert np.max(np.abs(got - want)) < TOL, (got, want)
+    gold = _large_golden("hea10")
+    assert gold is not None and np.max(np.abs(np.array(gold["energies"]) - want)) < 1e-12
+    # the same rows inside a full-size launch (64 circuits in flight per pass) give the same numbers
+    big = wl["make_inputs"](0)[0][:130]
+    e_big = prog.energies(torch.tensor(big)).cpu().numpy()
+    assert np.max(np.abs(e_big[:2] - got)) < 1e-13
+
+
+def test_lih12_26_blocks_against_c_oracle_golden():
+    """BASELINE configs[4] shape at 26 Pauli-exponential blocks (bench._lih_like(max_excitations=4): 12 qubits, 1084 ops,
+    631 Pauli terms) against golden energies from the C oracle (it needs ~7 min per 12-qubit row, so the values are
+    committed: tests/golden/large_energies.json, tools/make_golden_large.py), through tiles of 6 and 7 qubits."""
+    import bench
+    sys_path_tools()
+    from make_golden_large import lih12_26_inputs
+    from vqe_errormitigation_b200 import engine
+    torch = torch_cuda()
+    gold = _large_golden("lih12_26")
+    if gold is None:
+        pytest.skip("tests/golden/large_energies.json has no lih12_26 record")
+    b, terms, n_blocks = bench._lih_like(12, max_excitations=4)
+    assert n_blocks == 26 and len(b.ops) == gold["n_ops"]
+    params = lih12_26_inputs(len(b.param_names))
+    for tile in (6, 7):
+        prog = engine.CircuitProgram(b, hamiltonian=terms, options={"tile_qubits": tile})
+        assert prog.info["path"] == 2
+        got = prog.energies(torch.tensor(params), workspace_states=2).cpu().numpy()
+        assert np.max(np.abs(got - np.array(gold["energies"]))) < TOL, (tile, got, gold["energies"])
+
+
+def test_lih12_full_640_blocks_two_tilings_trace_and_golden():
+    """The full benchmarked LiH-like plan (640 blocks, 25 224 ops): tiles of 6 and 7 resident qubits give different pass
+    decompositions (547 vs 492 passes) that must agree; Tr(rho) = 1; and, when the golden record exists (the oracle needs
+    hours for this circuit), row 0 of the bench inputs matches it to 1e-10."""
+    import bench
+    from vqe_errormitigation_b200 import engine
+    torch = torch_cuda()
+    wl = bench.workload_lih12()
+    b, terms = wl["builder"], wl["terms"]
+    params = wl["make_inputs"](0)[0][:2]
+    p6 = engine.CircuitProgram(b, hamiltonian=terms, options={"tile_qubits": 6})
+    p7 = engine.CircuitProgram(b, hamiltonian=terms, options={"tile_qubits": 7})
+    assert p6.info["n_passes"] > p7.info["n_passes"] > 100
+    e6 = p6.energies(torch.tensor(params), workspace_states=2).cpu().numpy()
+    e7 = p7.energies(torch.tensor(params), workspace_states=2).cpu().numpy()
+    assert np.max(np.abs(e6 - e7)) < 1e-11, (e6, e7)
+    ident = (np.array([0], np.uint32), np.array([0], np.uint32), np.array([1.0]))
+    tr = engine.CircuitProgram(b, hamiltonian=ident, options={"tile_qubits": 6}).energies(torch.tensor(params[:1]), workspace_states=1).cpu().numpy()
+    assert abs(tr[0] - 1.0) < 1e-11
+    gold = _large_golden("lih12_full")
+    if gold is not None:
+        assert abs(e6[0] - gold["energies"][0]) < TOL and abs(e7[0] - gold["energies"][0]) < TOL
+
+
+def sys_path_tools():
+    import os
+    import sys
+    tools = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools")
+    if tools not in sys.path:
+        sys.path.insert(0, tools)
+
+
+def test_plan_options_are_per_plan():
+    """Execution switches are stored in the plan: turning the stream kernel off on one plan must not change
+    how another - already finalised - remapped plan runs."""
+    torch = torch_cuda()
+    rng = np.random.default_rng(77)
+    n = 8
+    ops = []
+    for q in range(n):
+        ops += [("r", (q,), (1, f"y{q}", 1.0, 0.0)), ("k", (q,), O.depolarize(1e-3))]
+    for q in range(n - 1):
+        ops += [("u", (q, q + 1), O.CNOT), ("k", (q, q + 1), O.two_qubit_depolarize(1e-3))]
+    terms = random_hamiltonian(rng, n, 10)
+    a = build_program(ops, n, terms)                                   # remapped, stream kernel
+    params = rng.uniform(-1, 1, size=(2, a.n_params))
+    want = a.energies(torch.tensor(params)).cpu().numpy()
+    b = build_program(ops, n, terms, stream_kernel=0, remap=0)           # generic tile kernel for every pass
+    got_b = b.energies(torch.tensor(params)).cpu().numpy()
+    got_a = a.energies(torch.tensor(params)).cpu().numpy()              # still runs (used to fail: "needs the stream kernel")
+    assert np.max(np.abs(got_b - want)) < 1e-12 and np.array_equal(got_a, want)
+
+
+def test_plan_is_bound_to_its_device():
+    torch = torch_cuda()
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    from vqe_errormitigation_b200._lib import DmxError
+    prog, _ = h2_program()
+    prog.energies(torch.zeros(1, 1, dtype=torch.float64, device="cuda:0"))
+    with torch.cuda.device(1):
+        with pytest.raises(DmxError):
+            prog.energies(torch.zeros(1, 1, dtype=torch.float64, device="cuda:1"))
+
+
+def test_async_host_call_matches_sync():
+    torch = torch_cuda()
+    from vqe_errormitigation_b200 import engine
+    prog, _ = h2_program()
+    B = 4099
+    p = engine.pinned_empty((B, 1))
+    p[:, 0] = np.linspace(-0.4, 0.4, B)
+    want = prog.energies_host(p)
+    outs = [engine.pinned_empty(B) for _ in range(3)]
+    for o in outs:
+        o[:] = 0
+        prog.energies_host(p, out=o, nowait=True)
+    prog.host_sync()
+    for o in outs:
+        assert np.array_equal(o, want)
+    # pageable buffers: the async entry point falls back to a synchronous call
+    q = np.linspace(-0.4, 0.4, 17).reshape(-1, 1)
+    assert np.allclose(prog.energies_host(q, nowait=True), prog.energies_host(q), atol=0, rtol=0)
+    prog.host_sync()
+
+
+def test_evaluate_variants_public_entry_point():
+    """IErrorMitigationManager.evaluate_variants: unique rows + counts on the host path and a device tensor
+    path give the same mitigated estimate as get_mu_effective on the same table."""
+    torch = torch_cuda()
+    from vqe_errormitigation_b200 import cirq_compat as cirq
+    from vqe_errormitigation_b200.data_containers.helper_interfaces.i_noise_wrapper import INoiseModel, INoiseWrapper
+    from vqe_errormitigation_b200.data_containers.model_hydrogen import HydrogenAnsatz
+    from vqe_errormitigation_b200.error_mitigation import IErrorMitigationManager, TwoQubitDepolarizingChannel
+    from vqe_errormitigation_b200.processors.processor_quantum import QPU
+    w = HydrogenAnsatz()
+    w.operator_parameters["alpha0"] = 0.0141
+    noise = INoiseModel([cirq.depolarize(2e-3)], [TwoQubitDepolarizingChannel(2e-3)], "dep")
+    n_w = INoiseWrapper(w, noise)
+    clean = QPU.get_resolved_circuit(n_w.get_clean_circuit(), w.operator_parameters)
+    mgr = IErrorMitigationManager(clean, noise, QPU.get_hamiltonian_objective_operator(w))
+    np.random.seed(5)
+    mgr.set_identifier_range(3000)
+    _vals, mu = mgr.get_mu_effective(True, True)
+    rows, counts = mgr._rows, mgr._counts
+    values_h, mu_h = mgr.evaluate_variants(rows, None, counts)
+    assert abs(mu_h - mu) < 1e-12 and values_h.shape == (len(rows),)
+    values_d, mu_d = mgr.evaluate_variants(torch.tensor(rows, device="cuda"), None, torch.tensor(counts, device="cuda"))
+    assert abs(mu_d - mu) < 1e-11 and np.max(np.abs(values_d.cpu().numpy() - values_h)) < 1e-13

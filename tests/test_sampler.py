@@ -67,10 +67,10 @@ def test_device_resident_mitigation_estimator():
     N, seed = 40000, 20260102
     mean, stderr, n = mgr.get_mu_effective_sampled(N, seed)
     assert n == N
-    qps = mgr._qp_matrix()
+    qps = mgr.quasi_probabilities()
     rows, signs = P.sample_variants(qps, N, seed)
     scale = float(np.prod([np.sum(np.abs(q)) for q in qps]))
-    values = mgr._variant_program().energies(None, torch.tensor(rows)).cpu().numpy()
+    values = mgr.variant_program().energies(None, torch.tensor(rows)).cpu().numpy()
     want = np.mean(signs * scale * values)
     assert abs(mean - want) < 1e-10
     assert abs(stderr - np.std(signs * scale * values) / np.sqrt(N)) < 1e-9

@@ -13,12 +13,12 @@ from vqe_errormitigation_b200 import engine, parallel
 
 wl = bench.workload_h2_qem()
 B = wl["batch"]
-step = wl["sampled_step"]
-mgr = step.__closure__[[c.cell_contents.__class__.__name__ for c in step.__closure__].index("IErrorMitigationManager")].cell_contents
+mgr = wl["manager"]
+step = lambda i: mgr.get_mu_effective_sampled(B, seed=20260102 + i)
 for i in range(3):
     step(i)
 sampler, scale = mgr._sampler_cache
-prog = mgr._variant_program()
+prog = mgr.variant_program()
 
 
 def timed(fn, reps=20):

@@ -71,6 +71,8 @@ EXPORTS = {
     "dmx_qp_sample_variants": (C.c_int, [C.c_int, C.POINTER(C.c_int32), C.POINTER(C.c_double), C.c_int, C.c_uint64, C.c_uint64,
                                          C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),
     "dmx_energy_batch_host": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "dmx_energy_batch_host_async": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "dmx_plan_host_sync": (C.c_int, [C.c_void_p]),
     "dmx_measure_fp64_peak": (C.c_int, [C.POINTER(C.c_double), C.c_void_p]),
 }
 

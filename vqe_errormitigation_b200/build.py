@@ -10,14 +10,16 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libdmx.so")
 SOURCES = ["dmx_exec.cu", "dmx_lower.cpp"]
-HEADERS = ["dmx_plan.hpp", os.path.join("..", "..", "include", "dmx.h")]
+PUBLIC_HEADER = os.path.join(HERE, "..", "include", "dmx.h")
 
 
 def _stale() -> bool:
+    """Any file under csrc/ (sources, .hpp, .cuh) or the public header newer than the library."""
     if not os.path.exists(OUT):
         return True
     t = os.path.getmtime(OUT)
-    return any(os.path.getmtime(os.path.join(CSRC, f)) > t for f in SOURCES + HEADERS)
+    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh", ".cpp", ".hpp", ".h"))] + [PUBLIC_HEADER]
+    return any(os.path.getmtime(f) > t for f in deps)
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
@@ -25,7 +27,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         return OUT
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
     cmd = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-           "-Xcompiler", "-fPIC", "-shared", "-cudart", "static", "-o", OUT] + SOURCES
+           "-Xcompiler", "-fPIC", "-shared", "-cudart", "static", "-o", OUT] + SOURCES + ["-ldl"]
     if verbose:
         cmd.insert(1, "-Xptxas")
         cmd.insert(2, "-v")

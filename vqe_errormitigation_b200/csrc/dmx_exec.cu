@@ -17,6 +17,7 @@
 //   dmx_pauli_to_rho / dmx_pauli_to_diag   output converters (final_density_matrix, run() probabilities).
 //   dmx_qp_reduce_*     deterministic two-stage reduction of the QP-weighted estimator.
 #include <cuda_runtime.h>
+#include <nvtx3/nvToolsExt.h>
 
 #include <algorithm>
 #include <atomic>
@@ -44,6 +45,12 @@ static int fail(int code, const std::string& msg) {
     g_last_error = msg;
     return code;
 }
+
+// NVTX range for the host-side phases (plan lowering, launch sequences, reductions): visible in nsys / ncu --nvtx
+struct NvtxRange {
+    explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
+};
 
 #define CUDA_TRY(expr)                                                                              \
     do {                                                                                            \
@@ -174,7 +181,10 @@ __global__ void __launch_bounds__(512) dmx_tile_kernel(const TileArgs a) {
     const bool streaming = a.k < a.n;
 
     long long total = a.batch;
-    if (a.work_count) total = *a.work_count;
+    if (a.work_count) {
+        asm volatile("griddepcontrol.wait;" ::: "memory");   // launched programmatically behind the frame kernel (launch_tile)
+        total = *a.work_count;
+    }
     long long ngroups;
     unsigned tiles_per_circuit = 1;
     if (streaming) {
@@ -985,7 +995,8 @@ __global__ void dmx_fp64_fma_kernel(double* out, int iters) {
 
 // ---------------------------------------------------------------------------------------------------------
 // QP variant sampler: Philox4x32-10 counter RNG, one warp per sample, lanes over gate slots.
-// counter = (sample index lo, sample index hi, slot, 0), key = seed  ->  u in [0,1) from 53 random bits;
+// counter = (sample index lo, sample index hi, slot / 4, 0), key = seed  ->  one 32-bit word per slot, u = (word + 0.5) / 2^32
+// (entries whose |qp| / sum|qp| is below ~2^-32 are therefore quantised away);
 // idx = first entry of the slot's cumulative |qp| table with cdf > u (np.random.choice(p=|qp|/sum|qp|),
 // src/error_mitigation.py:326-335); sign = sign prod qp[idx] (:321-323).
 // ---------------------------------------------------------------------------------------------------------
@@ -1256,13 +1267,34 @@ static cudaError_t build_stream_tables(const Plan& p, DevPlan* d) {
     return cudaSuccess;
 }
 
+static void free_devplan(DevPlan* d);
+
+static int upload_plan(Plan& p, DevPlan* d, int dev);
+
+// The plan's tables live on the device that was current at its first execution; a later call from another device would
+// hand kernels pointers of a different GPU, so it is refused (DMX_ERR_STATE).  A failed upload frees what it allocated.
 static int ensure_device(Plan& p, DevPlan** out) {
     std::lock_guard<std::mutex> lock(g_upload_mu);
-    if (p.dev) { *out = (DevPlan*)p.dev; return DMX_OK; }
     int dev = 0;
     CUDA_TRY(cudaGetDevice(&dev));
+    if (p.dev) {
+        DevPlan* d = (DevPlan*)p.dev;
+        if (d->device != dev)
+            return fail(DMX_ERR_STATE, "plan tables live on device " + std::to_string(d->device) + " but the current device is " +
+                                           std::to_string(dev) + " (a plan is bound to the device of its first execution)");
+        *out = d;
+        return DMX_OK;
+    }
     DevPlan* d = new DevPlan();
     d->device = dev;
+    const int rc = upload_plan(p, d, dev);
+    if (rc != DMX_OK) { free_devplan(d); return rc; }
+    p.dev = d;
+    *out = d;
+    return DMX_OK;
+}
+
+static int upload_plan(Plan& p, DevPlan* d, int dev) {
     CUDA_TRY(cudaDeviceGetAttribute(&d->sm_count, cudaDevAttrMultiProcessorCount, dev));
     {
         auto nonempty = [](auto v) { if (v.empty()) v.resize(1); return v; };
@@ -1340,13 +1372,15 @@ static int ensure_device(Plan& p, DevPlan** out) {
         }
         (void)cudaGetLastError();
     }
-    p.dev = d;
-    *out = d;
     return DMX_OK;
 }
 
 static void free_device(Plan& p) {
-    DevPlan* d = (DevPlan*)p.dev;
+    free_devplan((DevPlan*)p.dev);
+    p.dev = nullptr;
+}
+
+static void free_devplan(DevPlan* d) {
     if (!d) return;
     cudaFree(d->sweeps); cudaFree(d->mus); cudaFree(d->chains); cudaFree(d->factors); cudaFree(d->phases);
     cudaFree(d->coefs); cudaFree(d->rots); cudaFree(d->term_idx); cudaFree(d->term_coef);
@@ -1361,7 +1395,6 @@ static void free_device(Plan& p) {
         for (int i = 0; i < DevPlan::MAX_CHUNKS; ++i) { cudaEventDestroy(d->ev_in[i]); cudaEventDestroy(d->ev_k[i]); }
     }
     delete d;
-    p.dev = nullptr;
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -1405,7 +1438,19 @@ static int launch_tile(const TileArgs& a, int grid, int threads, int groups_per_
             configured[gi] = want;
         }
     }
-    if (gi) dmx_tile_kernel<2><<<grid, threads, smem, st>>>(a);
+    if (a.work_count) {
+        // Deferred-row launch behind a frame kernel: almost always the worklist is empty (Pauli-type noise has no R-type /
+        // projector corrections).  Programmatic dependent launch lets this grid start while the frame kernel still runs;
+        // the kernel waits (griddepcontrol.wait) before it reads the work count, so the ~4 us launch is off the critical path.
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3((unsigned)threads); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        if (gi) CUDA_TRY(cudaLaunchKernelEx(&cfg, dmx_tile_kernel<2>, a));
+        else CUDA_TRY(cudaLaunchKernelEx(&cfg, dmx_tile_kernel<1>, a));
+    } else if (gi) dmx_tile_kernel<2><<<grid, threads, smem, st>>>(a);
     else dmx_tile_kernel<1><<<grid, threads, smem, st>>>(a);
     ++g_launches;
     CUDA_TRY(cudaGetLastError());
@@ -1449,10 +1494,6 @@ static int run_tile_single(Plan& p, DevPlan* d, long long batch, const double* p
     return launch_tile(a, grid, threads, gpt, smem, st);
 }
 
-static int g_host_zero_copy = 1;   // option "host_zero_copy": small-state plans read / write mapped page-locked host buffers in place
-static int64_t g_host_chunk_rows = 32768;   // option "host_chunk_rows": rows per pipeline chunk of dmx_energy_batch_host
-static int g_stream_kernel = 1;        // option "stream_kernel": 0 -> generic dmx_tile_kernel for every pass
-static long long g_stream_chunk = 0;   // option "stream_chunk": circuits per pass launch (0: auto, ~64 MiB of states stay in L2)
 
 template <int THREADS, bool GENERAL>
 static int launch_stream(const StreamArgs& a, long long grid, size_t smem, cudaStream_t st) {
@@ -1497,10 +1538,11 @@ static int launch_stream3(const StreamArgs3& a, long long grid, size_t smem, cud
 // run in place); the last pass always lands in `state`.
 static int run_streaming(Plan& p, DevPlan* d, long long chunk, long long circuit_offset, const double* params, const uint8_t* variants,
                          double* state, double* state2, cudaStream_t st, double* chain_scratch = nullptr) {
+    NvtxRange nvtx("dmx:streaming_passes");
     if (p.remapped && !state2) return fail(DMX_ERR_INVALID, "remapped plan needs a second state buffer");
     const int total_chains = (int)p.chains.size();
     bool any_x = false;
-    for (const auto& px : d->passx) any_x |= px.ok && g_stream_kernel;
+    for (const auto& px : d->passx) any_x |= px.ok && p.opt_stream_kernel;
     double* chainmats = chain_scratch;
     if (any_x && total_chains > 0) {
         // per-circuit chain matrices of every pass, computed once (stream-ordered scratch: plans may run on several streams)
@@ -1526,8 +1568,8 @@ static int run_streaming(Plan& p, DevPlan* d, long long chunk, long long circuit
         const long long groups = chunk << (2 * (p.n - k));
         if (groups >= (1LL << 31)) { rc = fail(DMX_ERR_UNSUPPORTED, "streaming chunk too large for one launch"); break; }
         const DevPlan::PassX& px = d->passx[pi];
-        if (!ps.pos_in.empty() && !(px.ok && g_stream_kernel)) { rc = fail(DMX_ERR_STATE, "remapped plan needs the stream kernel"); break; }
-        if (px.ok && g_stream_kernel) {
+        if (!ps.pos_in.empty() && !(px.ok && p.opt_stream_kernel)) { rc = fail(DMX_ERR_STATE, "remapped plan needs the stream kernel"); break; }
+        if (px.ok && p.opt_stream_kernel) {
             if ((int)others.size() > 8) { rc = fail(DMX_ERR_UNSUPPORTED, "more than 8 non-resident qubits"); break; }
             std::vector<int> std_pos(p.n);
             for (int q = 0; q < p.n; ++q) std_pos[q] = p.n - 1 - q;
@@ -1664,8 +1706,6 @@ static int launch_frame32(const Frame32Args& a, int sm_count, cudaStream_t st) {
     return a.variants ? launch_frame32_impl<CPB, CSMODE, true>(a, sm_count, st) : launch_frame32_impl<CPB, CSMODE, false>(a, sm_count, st);
 }
 
-static int g_seg_cpb = 8;
-static int g_frame32 = 1;      // option "frame32": 0 -> always the 256-thread frame kernel
 
 static int run_segment(Plan& p, DevPlan* d, long long batch, const double* params, const uint8_t* variants, double* out, cudaStream_t st) {
     FrameArgs a{};
@@ -1686,7 +1726,7 @@ static int run_segment(Plan& p, DevPlan* d, long long batch, const double* param
     };
     const int mode = p.f_classes.empty() ? 0 : (p.f_single_class ? 1 : 2);
     int rc;
-    if (p.f32_n > 0 && g_frame32 && p.n_slots < 4096 && p.nseg < 4095) {
+    if (p.f32_n > 0 && p.opt_frame32 && p.n_slots < 4096 && p.nseg < 4095) {
         Frame32Args g{};
         g.nseg = p.nseg; g.n_params = p.n_params; g.n_slots = p.n_slots; g.n_classes = (int)p.f_classes.size(); g.batch = batch;
         g.w = d->g_w; g.partner = d->g_partner; g.cs_sel = d->g_cs_sel; g.classes = d->f_classes; g.init = d->g_init; g.eweight = d->g_ew;
@@ -1694,14 +1734,14 @@ static int run_segment(Plan& p, DevPlan* d, long long batch, const double* param
         g.out = out; g.worklist = a.worklist; g.work_count = a.work_count;
         g.any_const = 0;
         for (int k = 0; k < p.nseg; ++k) g.any_const |= p.fsegs[k].cs_sel < 0;
-        if (g_seg_cpb == 4)
+        if (p.opt_seg_cpb == 4)
             rc = mode == 0 ? launch_frame32<4, 0>(g, d->sm_count, st) : mode == 1 ? launch_frame32<4, 1>(g, d->sm_count, st) : launch_frame32<4, 2>(g, d->sm_count, st);
         else
             rc = mode == 0 ? launch_frame32<8, 0>(g, d->sm_count, st) : mode == 1 ? launch_frame32<8, 1>(g, d->sm_count, st) : launch_frame32<8, 2>(g, d->sm_count, st);
         if (rc == DMX_OK && variants) rc = run_tile_single(p, d, batch, params, variants, out, OUT_ENERGY, wl + 1, wl, st);
         return done(rc);
     }
-    if (g_seg_cpb == 4) {
+    if (p.opt_seg_cpb == 4) {
         rc = mode == 0 ? launch_frame<4, 0>(a, d->sm_count, st) : mode == 1 ? launch_frame<4, 1>(a, d->sm_count, st) : launch_frame<4, 2>(a, d->sm_count, st);
     } else {
         rc = mode == 0 ? launch_frame<8, 0>(a, d->sm_count, st) : mode == 1 ? launch_frame<8, 1>(a, d->sm_count, st) : launch_frame<8, 2>(a, d->sm_count, st);
@@ -1765,20 +1805,22 @@ int dmx_plan_set_option(dmx_plan* plan, const char* key, int value) {
     } else if (k == "triples") {
         plan->p.opt_triples = value != 0;
     } else if (k == "stream_kernel") {
-        g_stream_kernel = value != 0;
+        plan->p.opt_stream_kernel = value != 0;
     } else if (k == "stream_chunk") {
         if (value < 0) return fail(DMX_ERR_INVALID, "stream_chunk must be >= 0");
-        g_stream_chunk = value;
+        plan->p.opt_stream_chunk = value;
     } else if (k == "host_zero_copy") {
-        g_host_zero_copy = value != 0;
+        plan->p.opt_host_zero_copy = value != 0;
     } else if (k == "host_chunk_rows") {
         if (value < 1024) return fail(DMX_ERR_INVALID, "host_chunk_rows must be >= 1024");
-        g_host_chunk_rows = value;
+        plan->p.opt_host_chunk_rows = value;
     } else if (k == "frame32") {
-        g_frame32 = value != 0;
+        plan->p.opt_frame32 = value != 0;
     } else if (k == "segment_cpb") {
         if (value != 4 && value != 8) return fail(DMX_ERR_INVALID, "segment_cpb must be 4 or 8");
-        g_seg_cpb = value;
+        plan->p.opt_seg_cpb = value;
+    } else if (k == "bulk") {
+        plan->p.opt_bulk = value != 0;
     } else return fail(DMX_ERR_INVALID, "unknown option: " + k);
     return DMX_OK;
 }
@@ -1786,6 +1828,7 @@ int dmx_plan_set_option(dmx_plan* plan, const char* key, int value) {
 int dmx_plan_finalize(dmx_plan* plan) {
     if (!plan) return fail(DMX_ERR_INVALID, "plan is NULL");
     if (plan->p.finalized) return fail(DMX_ERR_STATE, "plan already finalized");
+    NvtxRange nvtx("dmx:plan_finalize");
     try {
         lower_plan(plan->p);
     } catch (const std::bad_alloc&) {
@@ -1837,6 +1880,7 @@ static int check_exec(dmx_plan* plan, int64_t batch, const double* d_params, con
 
 static int energy_impl(dmx_plan* plan, int64_t batch, const double* d_params, const uint8_t* d_variants, double* d_energy,
                        void* d_workspace, size_t workspace_bytes, cudaStream_t st) {
+    NvtxRange nvtx("dmx:energy_batch");
     Plan& p = plan->p;
     if (p.term_idx.empty()) return fail(DMX_ERR_STATE, "no Hamiltonian set");
     DevPlan* d;
@@ -1850,7 +1894,7 @@ static int energy_impl(dmx_plan* plan, int64_t batch, const double* d_params, co
     if (!d_workspace || cap < 1) return fail(DMX_ERR_INVALID, "workspace too small: need dmx_workspace_bytes()");
     double* const state2 = p.remapped ? (double*)((char*)d_workspace + (size_t)cap * sb) : nullptr;
     // circuits per pass launch: large enough to fill the GPU for several waves ("stream_chunk" overrides)
-    long long chunk = std::min<long long>(cap, g_stream_chunk > 0 ? g_stream_chunk : 64);
+    long long chunk = std::min<long long>(cap, p.opt_stream_chunk > 0 ? p.opt_stream_chunk : 64);
     double* chain_scratch = nullptr;
     if (!p.chains.empty()) CUDA_TRY(cudaMallocAsync((void**)&chain_scratch, (size_t)chunk * p.chains.size() * 128, st));
     struct Release { double* ptr; cudaStream_t st; ~Release() { if (ptr) cudaFreeAsync(ptr, st); } } release{chain_scratch, st};
@@ -1930,6 +1974,7 @@ int dmx_diag_batch(dmx_plan* plan, int64_t batch, const double* d_params, const 
 
 int dmx_qp_reduce(const double* d_values, const double* d_weights, const int32_t* d_counts, int64_t batch, double* d_out3, void* stream) {
     if (!d_values || !d_weights || !d_out3 || batch < 0) return fail(DMX_ERR_INVALID, "bad arguments");
+    NvtxRange nvtx("dmx:qp_reduce");
     cudaStream_t st = (cudaStream_t)stream;
     double* partial = nullptr;       // per call, stream-ordered: concurrent reductions on different streams do not share it
     CUDA_TRY(cudaMallocAsync((void**)&partial, QP_BLOCKS * 3 * sizeof(double), st));
@@ -2040,7 +2085,28 @@ static void* mapped_alias(const void* ptr) {
 // and the D2H of chunk i-1 overlap — so the call costs about max(copy in, compute, copy out) instead of their sum.  Buffers
 // that are already page-locked (cudaHostAlloc / cudaHostRegister, e.g. torch pinned tensors) are used in place; pageable
 // ones go through the plan's pinned staging buffer.
+static int energy_batch_host_impl(dmx_plan* plan, int64_t batch, const double* h_params, const uint8_t* h_variants, double* h_energy,
+                                  bool wait);
+
 int dmx_energy_batch_host(dmx_plan* plan, int64_t batch, const double* h_params, const uint8_t* h_variants, double* h_energy) {
+    return energy_batch_host_impl(plan, batch, h_params, h_variants, h_energy, true);
+}
+
+int dmx_energy_batch_host_async(dmx_plan* plan, int64_t batch, const double* h_params, const uint8_t* h_variants, double* h_energy) {
+    return energy_batch_host_impl(plan, batch, h_params, h_variants, h_energy, false);
+}
+
+int dmx_plan_host_sync(dmx_plan* plan) {
+    if (!plan) return fail(DMX_ERR_INVALID, "plan is NULL");
+    DevPlan* d = (DevPlan*)plan->p.dev;
+    if (!d || !d->stream) return DMX_OK;       // nothing was ever queued
+    std::lock_guard<std::mutex> lock(d->mu);
+    CUDA_TRY(cudaStreamSynchronize(d->stream));
+    return DMX_OK;
+}
+
+static int energy_batch_host_impl(dmx_plan* plan, int64_t batch, const double* h_params, const uint8_t* h_variants, double* h_energy,
+                                  bool wait) {
     int rc = check_exec(plan, batch, h_params, h_energy);
     if (rc) return rc;
     Plan& p = plan->p;
@@ -2048,6 +2114,7 @@ int dmx_energy_batch_host(dmx_plan* plan, int64_t batch, const double* h_params,
     rc = ensure_device(p, &d);
     if (rc) return rc;
     if (batch == 0) return DMX_OK;
+    NvtxRange nvtx("dmx:energy_batch_host");
     std::lock_guard<std::mutex> lock(d->mu);
     if (!d->stream) {
         CUDA_TRY(cudaStreamCreateWithFlags(&d->stream, cudaStreamNonBlocking));
@@ -2062,11 +2129,12 @@ int dmx_energy_batch_host(dmx_plan* plan, int64_t batch, const double* h_params,
     // and their stream hand-offs cost more than the kernel.  With mapped page-locked buffers the kernel reads the parameters
     // and writes the energies over PCIe itself: one launch, one synchronise.  (Variant tables - 1 byte per gate and row,
     // read lane-strided - stay on the DMA pipeline below.)
-    if (g_host_zero_copy && p.path == 1 && !h_variants) {
+    if (p.opt_host_zero_copy && p.path == 1 && !h_variants) {
         double* const e_dev = (double*)mapped_alias(h_energy);
         const double* const p_dev = h_params ? (const double*)mapped_alias(h_params) : nullptr;
         if (e_dev && (p_dev || !h_params)) {
             rc = energy_impl(plan, batch, p_dev, nullptr, e_dev, nullptr, 0, d->stream);
+            if (!wait) return rc;            // dmx_energy_batch_host_async: the caller collects with dmx_plan_host_sync
             const cudaError_t e = cudaStreamSynchronize(d->stream);
             if (rc) return rc;
             CUDA_TRY(e);
@@ -2099,7 +2167,7 @@ int dmx_energy_batch_host(dmx_plan* plan, int64_t batch, const double* h_params,
     char* dst_e = pin_out ? (char*)h_energy : hs + (pin_in ? 0 : pb + vb);
     // small-state plans: pipeline in up to MAX_CHUNKS chunks; streaming plans are long-running, one chunk
     int n_chunks = 1;
-    if (p.path != 2) n_chunks = (int)std::max<int64_t>(1, std::min<int64_t>(DevPlan::MAX_CHUNKS, batch / g_host_chunk_rows));
+    if (p.path != 2) n_chunks = (int)std::max<int64_t>(1, std::min<int64_t>(DevPlan::MAX_CHUNKS, batch / p.opt_host_chunk_rows));
     const int64_t per = ((batch + n_chunks - 1) / n_chunks + 7) & ~(int64_t)7;
     for (int c = 0; c < n_chunks; ++c) {
         const int64_t lo = (int64_t)c * per, cnt = std::min<int64_t>(per, batch - lo);

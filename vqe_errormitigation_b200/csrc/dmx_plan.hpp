@@ -167,6 +167,14 @@ struct Plan {
     std::vector<uint32_t> hx, hz;
     std::vector<double> hc;
     int opt_fuse = 1, opt_segments = 1, opt_tile_qubits = 6, opt_remap = 1, opt_triples = 1;
+    // execution switches (read at launch time from THIS plan; they used to be process-wide statics)
+    int opt_stream_kernel = 1;          // 0 -> generic dmx_tile_kernel for every streaming pass
+    long long opt_stream_chunk = 0;     // circuits per streaming pass launch (0: automatic)
+    int opt_host_zero_copy = 1;         // dmx_energy_batch_host works in place on mapped page-locked buffers
+    long long opt_host_chunk_rows = 32768;
+    int opt_frame32 = 1;                // compact warp-per-circuit frame kernel when <= 32 coefficients are live
+    int opt_seg_cpb = 8;                // circuits per warp / thread of the frame kernels
+    int opt_bulk = 1;                   // streaming: cp.async.bulk / mbarrier tile staging (dmx_stream3b_kernel)
     bool finalized = false;
 
     // lowered program

@@ -268,9 +268,11 @@ class CircuitProgram:
         return out
 
     def energies_host(self, params: Optional[np.ndarray] = None, variants: Optional[np.ndarray] = None, batch: Optional[int] = None,
-                      out: Optional[np.ndarray] = None) -> np.ndarray:
+                      out: Optional[np.ndarray] = None, nowait: bool = False) -> np.ndarray:
         """Host-buffer call (``dmx_energy_batch_host``): numpy in, numpy out, copies included.  Page-locked arrays
-        (``engine.pinned_empty``) are copied from / into in place; pageable ones go through a pinned staging buffer."""
+        (``engine.pinned_empty``) are copied from / into in place; pageable ones go through a pinned staging buffer.
+        ``nowait=True`` (``dmx_energy_batch_host_async``): the batch is queued and ``out`` is valid after
+        :meth:`host_sync` - several batches can then be in flight (pass page-locked ``params`` / ``out`` that stay alive)."""
         _require_cuda()
         p = v = None
         B = batch
@@ -299,10 +301,14 @@ class CircuitProgram:
         elif out.dtype != np.float64 or out.size != B or not out.flags.c_contiguous:
             raise ValueError("out must be a contiguous float64 array of the batch size")
         # raw addresses (ndarray.ctypes builds a helper object per access: several microseconds on a 40 us call)
-        check(self._lib.dmx_energy_batch_host(self._handle, B, p.__array_interface__["data"][0] if p is not None else None,
-                                              v.__array_interface__["data"][0] if v is not None else None,
-                                              out.__array_interface__["data"][0]))
+        fn = self._lib.dmx_energy_batch_host_async if nowait else self._lib.dmx_energy_batch_host
+        check(fn(self._handle, B, p.__array_interface__["data"][0] if p is not None else None,
+                 v.__array_interface__["data"][0] if v is not None else None, out.__array_interface__["data"][0]))
         return out
+
+    def host_sync(self):
+        """Wait for every ``energies_host(..., nowait=True)`` call queued on this program (``dmx_plan_host_sync``)."""
+        check(self._lib.dmx_plan_host_sync(self._handle))
 
     def pauli_vectors(self, params=None, variants=None, *, batch: Optional[int] = None):
         torch, dev, p_t, v_t, B = self._prep(params, variants, batch)
@@ -525,7 +531,12 @@ def program_for_circuit(resolved: cirq.Circuit, qubit_order=None, hamiltonian=No
     ham_key = None
     if hamiltonian is not None:
         ham_key = tuple(np.ascontiguousarray(a).tobytes() for a in hamiltonian)
-    full_key = (tuple(qubits), key, ham_key)
+    # a plan's device tables are bound to the device of its first execution (dmx.h): one cache entry per device
+    try:
+        device = _require_cuda().cuda.current_device()
+    except RuntimeError:       # host-only use (plan inspection in the CPU tests)
+        device = -1
+    full_key = (tuple(qubits), key, ham_key, device)
     prog = _PROGRAM_CACHE.get(full_key)
     if prog is None:
         prog = CircuitProgram(builder, qubits=qubits, measurements=measurements, hamiltonian=hamiltonian)

@@ -434,6 +434,16 @@ class IErrorMitigationManager:
         key = (tuple(tail_ops), with_hamiltonian, measure_all)
         if key in self._programs:
             return self._programs[key]
+        b, qubits, measurements = self.variant_builder(tail_ops)
+        ham = self._observable_terms(len(qubits)) if with_hamiltonian else None
+        prog = engine.CircuitProgram(b, qubits=qubits, measurements=measurements, hamiltonian=ham)
+        self._programs[key] = prog
+        return prog
+
+    def variant_builder(self, tail_ops=()):
+        """The op table of the variant family (host only, no plan is created): gate, noise, ``DMX_OP_VARIANT`` slot,
+        noise-if-slot-nonzero per gate of the clean circuit - the batched form of get_updated_circuit (reference :528-572).
+        Returns (ProgramBuilder, qubits, measurements)."""
         qubits = sorted(self.circuit.all_qubits())
         pos = {q: i for i, q in enumerate(qubits)}
         basis = list(BasisUnitarySet.get_basis_unitary_set())
@@ -461,10 +471,58 @@ class IErrorMitigationManager:
                 b.add_unitary(idx, cirq.unitary(op))
             else:
                 b.add_kraus(idx, cirq.channel(op))
-        ham = self._observable_terms(len(qubits)) if with_hamiltonian else None
-        prog = engine.CircuitProgram(b, qubits=qubits, measurements=measurements, hamiltonian=ham)
-        self._programs[key] = prog
-        return prog
+        return b, qubits, measurements
+
+    # ---- public batched surface (evaluate_variants) ---------------------------------------------------
+    def variant_program(self):
+        """The compiled plan of the variant family with the objective as its Hamiltonian (density representation)."""
+        return self._variant_program()
+
+    def quasi_probabilities(self) -> List[np.ndarray]:
+        """Quasi-probability vector of every gate slot, in variant-table column order."""
+        return self._qp_matrix()
+
+    def observable_terms(self):
+        """(xmask, zmask, coeff) of the objective the density path evaluates (reference :377-383)."""
+        return self._observable_terms(len(sorted(self.circuit.all_qubits())))
+
+    def total_cost(self) -> float:
+        """prod_g sum_i |qp_g[i]|: the scalar every sampled value is multiplied by (reference :399, `np.prod(weights)`)."""
+        return float(np.prod([np.sum(np.abs(qp)) for qp in self._qp_matrix()]))
+
+    def variant_signs(self, variants: np.ndarray) -> np.ndarray:
+        """sign prod_g qp_g[variants[b, g]] per row (reference :321-323)."""
+        return self._signs_and_weights(np.asarray(variants, np.uint8))[0]
+
+    def evaluate_variants(self, variants, signs=None, counts=None):
+        """Batched density-path evaluation of QP circuit variants: ``variants[B, S]`` (uint8 identifiers, one column per
+        gate of the clean circuit), optional ``signs[B]`` (default: computed from the quasi-probabilities) and ``counts[B]``
+        (multiplicity of each row; default 1).  Host arrays go through ``dmx_energy_batch_host`` (only the rows given are
+        shipped - pass UNIQUE rows + counts, the reference's own identifier -> count dictionary, :492-497); CUDA tensors
+        stay on the device (``dmx_energy_batch`` + ``dmx_qp_reduce`` + the cross-rank all-reduce of three doubles).
+        Returns (values[B] = Tr(rho_b H) un-weighted, mu = cost * sum(sign*count*value) / sum(count))."""
+        prog = self._variant_program()
+        scale = self.total_cost()
+        try:
+            import torch
+            on_device = isinstance(variants, torch.Tensor) and variants.is_cuda
+        except ImportError:   # pragma: no cover
+            on_device = False
+        if on_device:
+            from . import parallel
+            B = variants.shape[0]
+            values = prog.energies(None, variants, batch=B)
+            if signs is None:
+                signs = torch.as_tensor(self.variant_signs(variants.cpu().numpy()), device=variants.device)
+            w = signs if counts is None else signs * counts.to(torch.float64)
+            s0, _s1, n = (float(x) for x in parallel.sharded_sums(values, w, counts).cpu())
+            return values, scale * s0 / n if n else float("nan")
+        rows = np.ascontiguousarray(variants, np.uint8)
+        values = prog.energies_host(None, rows)
+        sg = self.variant_signs(rows) if signs is None else np.asarray(signs, np.float64)
+        cn = np.ones(rows.shape[0]) if counts is None else np.asarray(counts, np.float64)
+        total = float(np.sum(cn))
+        return values, scale * float(np.dot(sg * cn, values)) / total if total else float("nan")
 
     # ---- evaluation -----------------------------------------------------------------------------------------------
     def _measure_rows(self, rows: np.ndarray, counts: np.ndarray) -> np.ndarray:
@@ -561,7 +619,11 @@ class IErrorMitigationManager:
         self._error_mitigation = error_mitigation
         self._density_representation = density_representation
         self._meas_reps = meas_reps
+        from . import parallel
         if error_mitigation:
+            # rank 0's table wins: the identifiers were drawn from each process's own numpy RNG (set_identifier_range)
+            self._rows, self._counts = parallel.broadcast_table(self._rows, self._counts)
+            self._dict_cache = None
             rows, counts = self._rows, self._counts
             signs, weights = self._signs_and_weights(rows)
             scale = float(np.prod(weights))
@@ -571,7 +633,6 @@ class IErrorMitigationManager:
             signs, scale = np.ones(1), 1.0
         if rows.shape[0] == 0:
             return np.zeros(0), float("nan")
-        from . import parallel
         values = parallel.sharded_rows(lambda r, c: self._measure_rows(r, c), rows, counts)
         weighted = signs * scale * values
         results = np.repeat(weighted, counts)

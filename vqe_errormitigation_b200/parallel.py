@@ -50,18 +50,50 @@ def sharded_rows(fn: Callable[[np.ndarray, np.ndarray], np.ndarray], rows: np.nd
     return np.concatenate([g[:h - l].cpu().numpy() for g, (l, h) in zip(gathered, sizes)])
 
 
-def sharded_mean(values, weights, counts=None) -> Tuple[float, float, float]:
-    """(mean, variance, N) of w*v over all ranks from the three local sums (device tensors in, floats out).
-    Local sums come from dmx_qp_reduce; the cross-rank step is one all-reduce of 3 doubles."""
-    from . import engine
+def broadcast_table(rows: np.ndarray, counts: np.ndarray, src: int = 0) -> Tuple[np.ndarray, np.ndarray]:
+    """Make a (rows uint8 [R, S], counts int64 [R]) variant table identical on every rank: rank ``src``'s copy wins.
+    The host-side sampler (``IErrorMitigationManager.set_identifier_range``) draws from the process-local numpy RNG, so
+    without this step every rank would hold a different table - of a different length - and the sharded evaluation would
+    combine values of unrelated rows.  The reference has a single dict in one parent process (error_mitigation.py:484-497)."""
+    d = _dist()
+    if d is None or d.get_world_size() == 1:
+        return rows, counts
     import torch
+    device = torch.device("cuda", torch.cuda.current_device()) if d.get_backend() == "nccl" else torch.device("cpu")
+    shape = torch.tensor(list(rows.shape) if d.get_rank() == src else [0, 0], dtype=torch.int64, device=device)
+    d.broadcast(shape, src=src)
+    n_rows, n_cols = int(shape[0]), int(shape[1])
+    if d.get_rank() == src:
+        r_t = torch.as_tensor(np.ascontiguousarray(rows, np.uint8)).to(device)
+        c_t = torch.as_tensor(np.ascontiguousarray(counts, np.int64)).to(device)
+    else:
+        r_t = torch.empty((n_rows, n_cols), dtype=torch.uint8, device=device)
+        c_t = torch.empty(n_rows, dtype=torch.int64, device=device)
+    if n_rows:
+        d.broadcast(r_t, src=src)
+        d.broadcast(c_t, src=src)
+    return r_t.cpu().numpy(), c_t.cpu().numpy()
+
+
+def sharded_sums(values, weights, counts=None):
+    """Device tensor [3] = (sum w*v, sum (w*v)^2, N) over ALL ranks: dmx_qp_reduce locally, then one all-reduce of three
+    doubles (NCCL: on the current stream, nothing is copied to the host - the caller decides when to synchronise)."""
+    from . import engine
     local = engine.qp_reduce(values, weights, counts)
     d = _dist()
-    if d is not None:
+    if d is not None and d.get_world_size() > 1:
         if d.get_backend() != "nccl":
-            local = local.cpu()
-        d.all_reduce(local)
-    s0, s1, n = (float(x) for x in local.cpu())
+            host = local.cpu()
+            d.all_reduce(host)
+            local = host.to(local.device)
+        else:
+            d.all_reduce(local)
+    return local
+
+
+def sharded_mean(values, weights, counts=None) -> Tuple[float, float, float]:
+    """(mean, variance, N) of w*v over all ranks from the three sums of :func:`sharded_sums` (one 24-byte D2H read)."""
+    s0, s1, n = (float(x) for x in sharded_sums(values, weights, counts).cpu())
     mean = s0 / n if n else float("nan")
     var = s1 / n - mean * mean if n else float("nan")
     return mean, var, n

@@ -137,6 +137,10 @@ class CPU:
         return lockstep_minimize(batch_objective, x0s, max_cpu_iter, tol)
 
 
+class _BatchFailed(Exception):
+    """Raised inside a chain's objective after the coordinator's batched evaluation failed."""
+
+
 def lockstep_minimize(batch_objective: Callable[[np.ndarray], np.ndarray], x0s: np.ndarray, maxiter: int, tol: float = 1e-6,
                       method: str = "COBYLA") -> Tuple[np.ndarray, np.ndarray]:
     """Advance ``len(x0s)`` independent scipy optimiser chains together: every chain runs in its own thread and
@@ -148,6 +152,7 @@ def lockstep_minimize(batch_objective: Callable[[np.ndarray], np.ndarray], x0s: 
     alive = set(range(n_chains))
     results: List[Optional[optimize.OptimizeResult]] = [None] * n_chains
     errors: List[BaseException] = []
+    failed = threading.Event()
 
     def chain(c: int):
         def f(x):
@@ -156,9 +161,14 @@ def lockstep_minimize(batch_objective: Callable[[np.ndarray], np.ndarray], x0s: 
                 cond.notify_all()
                 while c not in answers:
                     cond.wait()
-                return answers.pop(c)
+                value = answers.pop(c)
+            if failed.is_set():
+                raise _BatchFailed()      # unwinds scipy's optimiser; the coordinator re-raises the real error
+            return value
         try:
             results[c] = optimize.minimize(fun=f, x0=x0s[c], method=method, options={"maxiter": maxiter}, tol=tol)
+        except _BatchFailed:
+            pass
         except BaseException as exc:  # noqa: BLE001 - propagated below
             errors.append(exc)
         finally:
@@ -177,7 +187,14 @@ def lockstep_minimize(batch_objective: Callable[[np.ndarray], np.ndarray], x0s: 
                 break
             ids = sorted(pending)
             xs = np.stack([pending.pop(c) for c in ids])
-        vals = np.asarray(batch_objective(xs), dtype=float)
+        try:
+            vals = np.asarray(batch_objective(xs), dtype=float)
+            if vals.shape != (len(ids),):
+                raise ValueError(f"batch_objective returned shape {vals.shape} for {len(ids)} requests")
+        except BaseException as exc:  # noqa: BLE001 - a failed batch must not leave the chains blocked in cond.wait()
+            errors.insert(0, exc)
+            vals = np.full(len(ids), np.nan)
+            failed.set()
         with cond:
             for c, v in zip(ids, vals):
                 answers[c] = float(v)
