@@ -23,11 +23,13 @@
 #include <atomic>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <mutex>
 #include <stdexcept>
 #include <string>
+#include <type_traits>
 #include <vector>
 
 #include "dmx_plan.hpp"
@@ -1119,6 +1121,11 @@ struct DevPlan {
         double* coefs = nullptr;     // device: pass-local fixed coefficients
         int n_sweeps = 0, n_mus = 0, n_coefs = 0, first_chain = 0, n_chains = 0;
         size_t smem = 0;
+        // Blackwell staging modes of dmx_stream3_kernel (dmx_stream.cuh: StreamLoadMode / StreamStoreMode)
+        int load_mode = LOAD_STAGED, store_mode = STORE_STAGED;
+        int first_lp[3] = {0, 0, 0}, first_tl[4] = {0, 0, 0, 0}, last_g[4] = {0, 0, 0, 0};
+        uint32_t first_A[4] = {}, first_B[4] = {}, first_C[4] = {}, last_A[4] = {}, last_B[4] = {}, last_C[4] = {};
+        uint32_t mbar_off = 0;
     };
     std::vector<PassX> passx;
 };
@@ -1257,12 +1264,88 @@ static cudaError_t build_stream_tables(const Plan& p, DevPlan* d) {
         if (!ok || sx.size() + sx3.size() > (size_t)STREAM_MAX_SWEEPS || mx.size() > (size_t)STREAM_MAX_MUS) continue;
         px.n_sweeps = (int)(sx.size() + sx3.size()); px.n_mus = (int)mx.size(); px.n_coefs = (int)lc.size();
         px.smem = ((size_t)32 * threads + (size_t)px.n_chains * 16 + lc.size() + 2) * 8;
+        px.mbar_off = (uint32_t)px.smem;      // 8-byte aligned by construction
+        px.smem += 16;
+        if (p.triples && !sx3.empty()) {
+            // First / last sweep of the pass in the LINEAR order of each side (tile qubits sorted by their position in
+            // pos_in / pos_out).  Register bits of a sweep = masks over tile-local index bits; both sides only permute bits.
+            std::vector<int> std_pos(p.n);
+            for (int q = 0; q < p.n; ++q) std_pos[q] = p.n - 1 - q;
+            const std::vector<int>& pin = ps.pos_in.empty() ? std_pos : ps.pos_in;
+            const std::vector<int>& pout = ps.pos_out.empty() ? std_pos : ps.pos_out;
+            // tile-local position (bit index of the code) of every tile qubit
+            std::vector<int> tl(p.n, -1);
+            for (int i = 0; i < k; ++i) tl[ps.tile_q[i]] = 2 * (k - 1 - i);
+            auto side = [&](const std::vector<int>& pos, const Sweep3& sw, const uint32_t* masks, bool store, uint32_t* A, uint32_t* B,
+                            uint32_t* C) -> bool {
+                std::vector<int> byp = ps.tile_q;                 // tile qubits by ascending position on this side
+                std::sort(byp.begin(), byp.end(), [&](int x, int y) { return pos[x] < pos[y]; });
+                std::vector<int> rank(p.n, -1);
+                for (int i = 0; i < k; ++i) rank[byp[i]] = i;
+                if (pos[byp[0]] != 0 || pos[byp[1]] != 1) return false;      // the side has no 128-byte runs
+                if (!store) for (int i = 0; i < k; ++i) if (pos[byp[i]] != i) return false;     // bulk / direct load: contiguous tile
+                int reg_q[3];
+                for (int j = 0; j < 3; ++j) {
+                    reg_q[j] = ps.tile_q[k - 1 - sw.p[j] / 2];
+                    if (rank[reg_q[j]] < 2) return false;   // a register-resident qubit sits in the low pair
+                }
+                auto is_reg = [&](int q) { return q == reg_q[0] || q == reg_q[1] || q == reg_q[2]; };
+                if (!store) {
+                    int r3[3] = {rank[reg_q[0]], rank[reg_q[1]], rank[reg_q[2]]};
+                    std::sort(r3, r3 + 3);
+                    for (int j = 0; j < 3; ++j) px.first_lp[j] = 2 * r3[j];
+                    int j = 0;
+                    for (int i = 0; i < k; ++i) if (!is_reg(byp[i])) px.first_tl[j++] = tl[byp[i]];   // thread bit pairs: load-linear order
+                } else {
+                    // thread identity of the last sweep = non-register qubits in tile-local order; coalescing needs its two
+                    // lowest ones to be the low pair of the store side
+                    std::vector<int> byt = ps.tile_q;
+                    std::sort(byt.begin(), byt.end(), [&](int x, int y) { return tl[x] < tl[y]; });
+                    int j = 0;
+                    for (int i = 0; i < k; ++i) if (!is_reg(byt[i])) { if (j < 2 && pos[byt[i]] > 1) return false; px.last_g[j++] = 2 * pos[byt[i]]; }
+                }
+                auto map_mask = [&](uint32_t m) {
+                    uint32_t out = 0;
+                    for (int t = 0; t < k; ++t)
+                        for (int b = 0; b < 2; ++b)
+                            if ((m >> (2 * t + b)) & 1u) {
+                                const int q = ps.tile_q[k - 1 - t];
+                                out |= 1u << (2 * (store ? pos[q] : rank[q]) + b);
+                            }
+                    return store ? out : out << 3;         // global element index / linear byte offset
+                };
+                uint32_t mm[6];
+                for (int j = 0; j < 6; ++j) mm[j] = map_mask(masks[j]);
+                for (int c = 0; c < 4; ++c) {       // register bits (zC, xC, zB, xB, zA, xA) = masks 0..5
+                    C[c] = ((c & 1) ? mm[0] : 0u) ^ ((c & 2) ? mm[1] : 0u);
+                    B[c] = ((c & 1) ? mm[2] : 0u) ^ ((c & 2) ? mm[3] : 0u);
+                    A[c] = ((c & 1) ? mm[4] : 0u) ^ ((c & 2) ? mm[5] : 0u);
+                }
+                return true;
+            };
+            const Sweep3& sw_first = p.sweeps3[p.phases[ps.first_phase].first_sweep];
+            const Phase& ph_last = p.phases[ps.first_phase + ps.n_phases - 1];
+            const Sweep3& sw_last = p.sweeps3[ph_last.first_sweep + ph_last.n_sweeps - 1];
+            if (pi > 0 && p.opt_bulk && side(pin, sw_first, sw_first.lmask, false, px.first_A, px.first_B, px.first_C))
+                px.load_mode = p.opt_bulk == 2 ? LOAD_DIRECT : LOAD_BULK;
+            if (p.opt_direct_store && side(pout, sw_last, sw_last.smask, true, px.last_A, px.last_B, px.last_C))
+                px.store_mode = STORE_DIRECT;
+        }
         if (px.smem > (k == 7 ? 227u : 56u) * 1024) continue;       // k = 6: keep four CTAs per SM
         px.sweeps = sx; px.sweeps3 = sx3; px.mus = mx; px.cfix = cfix;
         if (lc.empty()) lc.push_back(0.0);
         cudaError_t e = upload(&px.coefs, lc);
         if (e != cudaSuccess) return e;
         px.ok = true;
+    }
+    if (std::getenv("DMX_VERBOSE")) {
+        int n_ok = 0, n_bulk = 0, n_direct_l = 0, n_direct_s = 0;
+        for (const auto& px : d->passx) {
+            n_ok += px.ok; n_bulk += px.ok && px.load_mode == LOAD_BULK; n_direct_l += px.ok && px.load_mode == LOAD_DIRECT;
+            n_direct_s += px.ok && px.store_mode == STORE_DIRECT;
+        }
+        std::fprintf(stderr, "[dmx] streaming plan: %zu passes, %d on the stream kernel, tile load: %d bulk-async, %d direct; %d direct stores\n",
+                     d->passx.size(), n_ok, n_bulk, n_direct_l, n_direct_s);
     }
     return cudaSuccess;
 }
@@ -1580,6 +1663,18 @@ static int run_streaming(Plan& p, DevPlan* d, long long chunk, long long circuit
                 a.n_sweeps = px.n_sweeps; a.n_mus = px.n_mus; a.n_coefs = px.n_coefs;
                 a.total_chains = total_chains; a.first_chain = px.first_chain; a.n_chains = px.n_chains;
                 a.n = p.n; a.k = k; a.load = pi > 0;
+                if constexpr (std::is_same<std::decay_t<decltype(a)>, StreamArgs3>::value) {
+                    a.load_mode = pi > 0 ? px.load_mode : LOAD_INIT;
+                    a.store_mode = px.store_mode;
+                    for (int j = 0; j < 3; ++j) a.first_lp[j] = px.first_lp[j];
+                    for (int j = 0; j < 4; ++j) {
+                        a.first_tl[j] = px.first_tl[j]; a.last_g[j] = px.last_g[j];
+                        a.first_A[j] = px.first_A[j]; a.first_B[j] = px.first_B[j]; a.first_C[j] = px.first_C[j];
+                        a.last_A[j] = px.last_A[j]; a.last_B[j] = px.last_B[j]; a.last_C[j] = px.last_C[j];
+                    }
+                    a.mbar_off = px.mbar_off;
+                    a.tile_bytes = 8u << (2 * k);
+                }
                 const size_t last = p.passes.size() - 1;
                 double* bufs[2] = {state, p.remapped ? state2 : state};
                 a.dst = bufs[(last - pi) & 1];
@@ -1820,7 +1915,10 @@ int dmx_plan_set_option(dmx_plan* plan, const char* key, int value) {
         if (value != 4 && value != 8) return fail(DMX_ERR_INVALID, "segment_cpb must be 4 or 8");
         plan->p.opt_seg_cpb = value;
     } else if (k == "bulk") {
-        plan->p.opt_bulk = value != 0;
+        if (value < 0 || value > 2) return fail(DMX_ERR_INVALID, "bulk must be 0 (register staging), 1 (cp.async.bulk) or 2 (direct global loads)");
+        plan->p.opt_bulk = value;
+    } else if (k == "direct_store") {
+        plan->p.opt_direct_store = value != 0;
     } else return fail(DMX_ERR_INVALID, "unknown option: " + k);
     return DMX_OK;
 }

@@ -5,6 +5,7 @@
 //   path 2: streaming tile passes over a state kept in HBM/L2 (n > 7).
 // No CUDA in this file; it is exercised on CPU by tests/test_lowering.py through dmx_plan_dump().
 #include <algorithm>
+#include <array>
 #include <cmath>
 #include <complex>
 #include <cstdio>
@@ -828,6 +829,7 @@ struct TripleBuilder {
     };
 
     int T[3] = {-1, -1, -1};
+    std::vector<std::array<int, 3>>* record = nullptr;   // dry runs: the qubit triple of every emitted sweep
     int slot_of(int q) const { for (int s = 0; s < 3; ++s) if (T[s] == q) return s; return -1; }
     static int shift(int slot) { return 4 - 2 * slot; }
 
@@ -959,6 +961,7 @@ struct TripleBuilder {
         sw.first_mu = (int)p.mus.size(); sw.n_mu = (int)mus.size();
         p.mus.insert(p.mus.end(), mus.begin(), mus.end());
         p.sweeps3.push_back(sw);
+        if (record) record->push_back({T[0], T[1], T[2]});
         sweeps_elems += 1.0;
         mus.clear(); new_chains.clear(); new_factors.clear();
     }
@@ -1380,14 +1383,51 @@ static void schedule_streaming_remap(Plan& p) {
     }
     // layouts
     const size_t L = tiles.size();
+    // Triple sweeps: which qubits the FIRST and the LAST sweep of every pass hold in registers (a dry run of the sweep
+    // builder; the choice of triples does not depend on the layout).  The execution layer lets the first sweep read the
+    // tile where the bulk copy put it (global order) and the last sweep write its registers straight to global memory
+    // when neither of the two lowest-positioned qubits of that side is register-resident in that sweep: the 16 lanes of
+    // a half-warp then walk the 16 doubles of a 128-byte run (conflict-free shared-memory reads, full-line stores).
+    std::vector<std::array<int, 3>> first3(L, std::array<int, 3>{-1, -1, -1}), last3(L, std::array<int, 3>{-1, -1, -1});
+    if (p.opt_triples && k >= 3) {
+        for (size_t pi = 0; pi < L; ++pi) {
+            if (orders[pi].empty()) continue;
+            const size_t n_sw = p.sweeps3.size(), n_mu = p.mus.size(), n_ch = p.chains.size(), n_fa = p.factors.size(), n_ph = p.phases.size(),
+                         n_co = p.coefs.size();
+            std::vector<int> tq, lp(n, -1);
+            for (int q = 0; q < n; ++q) if (tiles[pi][q]) tq.push_back(q);
+            for (size_t i = 0; i < tq.size(); ++i) lp[tq[i]] = 2 * (int)i;
+            CoefCache scratch;
+            std::vector<std::array<int, 3>> rec;
+            {
+                TripleBuilder tb(p, scratch, lp, tq);
+                tb.record = &rec;
+                tb.run(orders[pi]);
+            }
+            p.sweeps3.resize(n_sw); p.mus.resize(n_mu); p.chains.resize(n_ch); p.factors.resize(n_fa); p.phases.resize(n_ph); p.coefs.resize(n_co);
+            if (!rec.empty()) { first3[pi] = rec.front(); last3[pi] = rec.back(); }
+        }
+    }
+    auto in3 = [](const std::array<int, 3>& t, int q) { return t[0] == q || t[1] == q || t[2] == q; };
     std::vector<std::vector<int>> pos(L + 1, std::vector<int>(n));
     for (int q = 0; q < n; ++q) pos[L][q] = n - 1 - q;
     pos[0] = pos[L];
     for (size_t pi = 1; pi < L; ++pi) {
         std::vector<int> seq;   // qubits by ascending position
-        int got = 0;
-        for (int q = 0; q < n && got < 2; ++q) if (tiles[pi - 1][q] && tiles[pi][q]) { seq.push_back(q); ++got; }
-        if (got < 2) throw std::runtime_error("remap scheduler: consecutive tiles share fewer than two qubits");
+        std::vector<int> shared;
+        for (int q = 0; q < n; ++q) if (tiles[pi - 1][q] && tiles[pi][q]) shared.push_back(q);
+        if (shared.size() < 2) throw std::runtime_error("remap scheduler: consecutive tiles share fewer than two qubits");
+        // the low pair: two shared qubits, preferably resident neither in the last sweep of the storing pass (2 points:
+        // direct stores save a shared-memory round trip) nor in the first sweep of the loading pass (1 point each side of
+        // the bulk-staged load); ties keep the lowest qubit numbers
+        int best_a = shared[0], best_b = shared[1], best_score = -1;
+        for (size_t i = 0; i < shared.size(); ++i)
+            for (size_t j = i + 1; j < shared.size(); ++j) {
+                const int a = shared[i], b = shared[j];
+                const int score = 2 * (!in3(last3[pi - 1], a) && !in3(last3[pi - 1], b)) + (!in3(first3[pi], a) && !in3(first3[pi], b));
+                if (score > best_score) { best_score = score; best_a = a; best_b = b; }
+            }
+        seq.push_back(best_a); seq.push_back(best_b);
         std::vector<char> used(n, 0);
         for (int q : seq) used[q] = 1;
         for (int q = n - 1; q >= 0; --q) if (!used[q] && tiles[pi][q]) { seq.push_back(q); used[q] = 1; }   // this pass's tile is contiguous
@@ -1417,13 +1457,56 @@ static void schedule_streaming_remap(Plan& p) {
                 unsigned v[4] = {swz_col(2 * tl[byp[0]] + 1), swz_col(2 * tl[byp[1]]), swz_col(2 * tl[byp[1]] + 1), swz_col(2 * tl[byp[2]])};
                 return gf2_rank4(v);
             };
+            // What an order is worth (see dmx_exec.cu::build_stream_tables for the matching run-time checks):
+            //  * direct store (the last sweep writes global memory from registers): the two lowest tile-local qubits outside
+            //    its triple must be the low pair of the stored layout - then the lanes of a half-warp walk one 128-byte run;
+            //  * bulk-staged load (first sweep reads the linear image): its threads hold the load-side low pair in their low
+            //    bits, so that sweep's store into the swizzled tile walks the tile-local bits of that pair - they must map
+            //    to four independent bank-pair bits;
+            //  * a side that stays on the register-staged path wants the old staging-loop criterion.
+            auto lowest_two_outside = [&](const std::vector<int>& order, const std::array<int, 3>& t3, const std::vector<int>& ps) {
+                int found = 0;
+                for (int i = kk - 1; i >= 0 && found < 2; --i) {       // order[i] sits at tile-local position kk-1-i
+                    const int q = order[i];
+                    if (in3(t3, q)) continue;
+                    if (ps[q] > 1) return false;
+                    ++found;
+                }
+                return found == 2;
+            };
+            auto low_pair_clear = [&](const std::array<int, 3>& t3, const std::vector<int>& ps) {
+                if (t3[0] < 0) return false;
+                int cnt = 0;
+                for (int q : tq) if (ps[q] <= 1) { if (in3(t3, q)) return false; ++cnt; }
+                return cnt == 2;
+            };
+            const bool store_ok = p.opt_triples && low_pair_clear(last3[pi], pass.pos_out);
+            bool load_ok = p.opt_triples && pi > 0 && low_pair_clear(first3[pi], pass.pos_in);
+            if (load_ok) for (int q : tq) if (pass.pos_in[q] >= kk) load_ok = false;      // contiguous tile only
+            auto bulk_rank = [&](const std::vector<int>& order) {
+                std::vector<int> tl(n, -1);
+                for (int i = 0; i < kk; ++i) tl[order[i]] = kk - 1 - i;
+                unsigned v[4];
+                int j = 0;
+                for (int q : order) if (pass.pos_in[q] <= 1) { v[j++] = swz_col(2 * tl[q]); v[j++] = swz_col(2 * tl[q] + 1); }
+                return gf2_rank4(v);
+            };
+            auto score_of = [&](const std::vector<int>& order) {
+                int sc = 0;
+                if (store_ok && lowest_two_outside(order, last3[pi], pass.pos_out)) sc += 100;
+                else sc += 5 * side_rank(order, pass.pos_out);
+                if (load_ok) sc += 10 * bulk_rank(order);
+                else sc += 5 * (pi > 0 ? side_rank(order, pass.pos_in) : 4);
+                return sc;
+            };
+            const int full_score = (store_ok ? 100 : 20) + (load_ok ? 40 : 20);
             std::vector<int> best = tq, cand = tq;
-            int best_score = (pi > 0 ? side_rank(tq, pass.pos_in) : 4) + side_rank(tq, pass.pos_out);
+            int best_score = score_of(tq);
             std::sort(cand.begin(), cand.end());
-            if (best_score < 8 && kk >= 3) {
+            if (best_score < full_score && kk >= 3) {
                 do {
-                    const int sc = (pi > 0 ? side_rank(cand, pass.pos_in) : 4) + side_rank(cand, pass.pos_out);
-                    if (sc > best_score) { best_score = sc; best = cand; if (sc == 8) break; }
+                    const int sc = score_of(cand);
+                    if (sc > best_score) { best_score = sc; best = cand; if (sc == full_score) break; }
                 } while (std::next_permutation(cand.begin(), cand.end()));
             }
             tq = best;

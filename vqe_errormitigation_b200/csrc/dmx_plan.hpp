@@ -174,7 +174,8 @@ struct Plan {
     long long opt_host_chunk_rows = 32768;
     int opt_frame32 = 1;                // compact warp-per-circuit frame kernel when <= 32 coefficients are live
     int opt_seg_cpb = 8;                // circuits per warp / thread of the frame kernels
-    int opt_bulk = 1;                   // streaming: cp.async.bulk / mbarrier tile staging (dmx_stream3b_kernel)
+    int opt_bulk = 1;                   // streaming tile load: 0 register staging, 1 cp.async.bulk + mbarrier, 2 direct global loads
+    int opt_direct_store = 1;           // streaming: the last sweep of a pass writes its registers straight to global memory
     bool finalized = false;
 
     // lowered program

@@ -94,7 +94,28 @@ struct StreamArgs3 {
     uint32_t siter_l[32], siter_s[32];
     uint32_t pbit_l, pbit_s;
     uint32_t init_mask;
+    // ---- Blackwell staging modes (dmx_stream3_kernel) ----
+    // load_mode  LOAD_STAGED: 16-byte global loads -> registers -> swizzled tile (the portable path above)
+    //            LOAD_BULK:   ONE cp.async.bulk of the whole tile (contiguous in the load-side layout) into shared memory,
+    //                         completion on an mbarrier; the first sweep reads that LINEAR (global-order) image directly
+    //            LOAD_DIRECT: the first sweep reads its registers straight from global memory (same linear addressing)
+    // store_mode STORE_DIRECT: the last sweep writes its registers straight to global memory in the store-side layout
+    // Both need the two lowest-positioned qubits of that side outside the sweep's register triple (the half-warp then
+    // walks a 128-byte run: conflict-free / fully coalesced); dmx_lower.cpp picks the layouts accordingly.
+    int load_mode, store_mode;
+    int first_lp[3];                     // first sweep: bit positions of its three codes in the LINEAR load image, ascending
+    int first_tl[4];                     // ... and where the thread's own bit pairs (non-register qubits in load-linear order)
+                                         // sit in the tile-local index: base of that sweep's store into the swizzled tile
+    int last_g[4];                       // last sweep: global bit position of the thread's j-th bit pair (non-register qubits
+                                         // in tile-local order) in the store-side layout
+    uint32_t first_A[4], first_B[4], first_C[4];   // linear BYTE offsets of register e = A[e >> 4] ^ B[(e >> 2) & 3] ^ C[e & 3]
+    uint32_t last_A[4], last_B[4], last_C[4];      // store side: GLOBAL element-index offsets of register e
+    uint32_t mbar_off;                   // byte offset of the mbarrier inside dynamic shared memory
+    uint32_t tile_bytes;
 };
+
+enum StreamLoadMode : int { LOAD_INIT = 0, LOAD_STAGED = 1, LOAD_BULK = 2, LOAD_DIRECT = 3 };
+enum StreamStoreMode : int { STORE_STAGED = 0, STORE_DIRECT = 1 };
 
 __host__ __device__ __forceinline__ unsigned parity32(unsigned v) {
 #ifdef __CUDA_ARCH__
@@ -119,10 +140,45 @@ __host__ __device__ __forceinline__ unsigned insert2_hd(unsigned g, int p) { ret
 
 namespace dmx {
 
+// bit pair j of v -> bit position pos[j] (four pairs: the thread index of a k <= 7 tile with three register-resident codes)
+__device__ __forceinline__ unsigned deposit_pairs(unsigned v, const int (&pos)[4]) {
+    return ((v & 3u) << pos[0]) | (((v >> 2) & 3u) << pos[1]) | (((v >> 4) & 3u) << pos[2]) | (((v >> 6) & 3u) << pos[3]);
+}
+
 __device__ __forceinline__ unsigned map_runs(unsigned v, const int (*runs)[3], int n) {
     unsigned g = 0;
     for (int i = 0; i < n; ++i) g |= ((v >> runs[i][0]) & ((1u << runs[i][2]) - 1u)) << runs[i][1];
     return g;
+}
+
+// ---- mbarrier + bulk async copy (sm_90+ PTX; SASS: SYNCS.* / UBLKCP) -----------------------------------------
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(unsigned bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");     // make the init visible to the async proxy
+}
+
+__device__ __forceinline__ void mbar_expect_tx(unsigned bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+
+// global -> shared bulk copy (16-byte aligned, size a multiple of 16); completes `bytes` transactions on the mbarrier
+__device__ __forceinline__ void bulk_g2s(unsigned dst, const void* src, unsigned bytes, unsigned bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+
+__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(bar), "r"(parity) : "memory");
 }
 
 // ---- per-circuit chain matrices, once per (circuit, chain) ---------------------------------------------------
@@ -462,13 +518,22 @@ __global__ void __launch_bounds__(THREADS, THREADS == 256 ? 1 : 4) dmx_stream3_k
     const double* const st_in = a.src + (circuit << (2 * a.n));
     double* const st = a.dst + (circuit << (2 * a.n));
 
+    // the tile of the load side is contiguous for LOAD_BULK / LOAD_DIRECT: tile_id supplies the upper index bits
+    const double* const tile_src = st_in + map_runs(tile_id, a.oruns_l, a.n_oruns_l);
+    const unsigned mbar = smem_u32(reinterpret_cast<char*>(dmx_stream_smem) + a.mbar_off);
+    if (a.load_mode == LOAD_BULK && tid == 0) {
+        // issued first: the 32 KB are in flight while the CTA stages its tables
+        mbar_init(mbar, 1);
+        mbar_expect_tx(mbar, a.tile_bytes);
+        bulk_g2s(smem_u32(tile), tile_src, a.tile_bytes, mbar);     // UBLKCP: the whole tile, one instruction
+    }
     {
         const double* cm = a.chainmats + ((size_t)circuit * a.total_chains + a.first_chain) * 16;
         for (int i = tid; i < a.n_chains * 16; i += THREADS) cf[i] = cm[i];
         for (int i = tid; i < a.n_coefs; i += THREADS) cf[a.n_chains * 16 + i] = a.coefs[i];
     }
 
-    if (a.load) {
+    if (a.load_mode == LOAD_STAGED) {
         const unsigned gbase = map_runs(2u * tid, a.gruns_l, a.n_gruns_l) | map_runs(tile_id, a.oruns_l, a.n_oruns_l);
         const unsigned s_thr = swz_hd(map_runs(2u * tid, a.uruns_l, a.n_gruns_l));
         double2 x[NITER];
@@ -480,7 +545,7 @@ __global__ void __launch_bounds__(THREADS, THREADS == 256 ? 1 : 4) dmx_stream3_k
             tile[sp] = x[j].x;
             tile[sp ^ a.pbit_l] = x[j].y;
         }
-    } else {
+    } else if (a.load_mode == LOAD_INIT) {
         const unsigned gbase = map_runs(2u * tid, a.gruns_s, a.n_gruns_s) | map_runs(tile_id, a.oruns_s, a.n_oruns_s);
         const unsigned s_thr = swz_hd(map_runs(2u * tid, a.uruns_s, a.n_gruns_s));
 #pragma unroll
@@ -492,12 +557,44 @@ __global__ void __launch_bounds__(THREADS, THREADS == 256 ? 1 : 4) dmx_stream3_k
         }
     }
     __syncthreads();
+    if (a.load_mode == LOAD_BULK) mbar_wait(mbar, 0);
 
     for (int si = 0; si < a.n_sweeps; ++si) {
         const SweepX3& sw = a.sweeps[si];
-        const unsigned sb = swz_hd(insert2_hd(insert2_hd(insert2_hd((unsigned)tid, sw.p[0]), sw.p[1]), sw.p[2])) << 3;
+        unsigned sb = swz_hd(insert2_hd(insert2_hd(insert2_hd((unsigned)tid, sw.p[0]), sw.p[1]), sw.p[2])) << 3;
         double v[64];
-        {
+        if (si == 0 && a.load_mode >= LOAD_BULK) {
+            // this thread holds the elements whose non-register qubits, taken in LOAD-LINEAR order, spell tid: that is the
+            // identity its store into the swizzled tile-local layout must use
+            sb = swz_hd(deposit_pairs((unsigned)tid, a.first_tl)) << 3;
+            // first sweep on the LINEAR image of the tile (what the bulk copy delivered, or global memory itself): the
+            // thread's non-register bits fill the remaining index bits in ascending order, so a half-warp walks the 16
+            // doubles of a 128-byte run
+            const unsigned lb = insert2_hd(insert2_hd(insert2_hd((unsigned)tid, a.first_lp[0]), a.first_lp[1]), a.first_lp[2]) << 3;
+            unsigned ab[16], sc[4];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) ab[i] = a.first_A[i >> 2] ^ a.first_B[i & 3];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) sc[c] = lb ^ a.first_C[c];
+            if (a.load_mode == LOAD_BULK) {
+#pragma unroll
+                for (int e = 0; e < 64; ++e) v[e] = *reinterpret_cast<const double*>(tb + (sc[e & 3] ^ ab[e >> 2]));
+            } else {
+                const char* const gsrc = reinterpret_cast<const char*>(tile_src);
+#pragma unroll
+                for (int e = 0; e < 64; ++e) v[e] = __ldcs(reinterpret_cast<const double*>(gsrc + (sc[e & 3] ^ ab[e >> 2])));
+            }
+            if (sw.lscale >= 0) {
+#pragma unroll
+                for (int e = 0; e < 64; ++e) v[e] *= a.cfix[sw.lscale + e];
+            } else if (sw.lscale <= -2) {
+                const double2* __restrict__ lc = reinterpret_cast<const double2*>(cf - (sw.lscale + 2));
+#pragma unroll
+                for (int e = 0; e < 32; ++e) { const double2 s = lc[e]; v[2 * e] *= s.x; v[2 * e + 1] *= s.y; }
+            }
+            // the sweep stores in the swizzled tile-local layout: every thread must have read the linear image first
+            if (a.load_mode == LOAD_BULK) __syncthreads();
+        } else {
             // address of register e = (sb ^ lC[c]) ^ (lA[a] ^ lB[b]): 4 per-thread bases x 16 uniform offsets, one XOR per access
             unsigned ab[16], sc[4];
 #pragma unroll
@@ -548,6 +645,18 @@ __global__ void __launch_bounds__(THREADS, THREADS == 256 ? 1 : 4) dmx_stream3_k
                 const double2* __restrict__ sc2 = reinterpret_cast<const double2*>(cf - (sw.sscale + 2));
 #pragma unroll
                 for (int e = 0; e < 32; ++e) { const double2 s = sc2[e]; v[2 * e] *= s.x; v[2 * e + 1] *= s.y; }
+            }
+            if (si == a.n_sweeps - 1 && a.store_mode == STORE_DIRECT) {
+                // last sweep: registers straight to global memory in the store-side layout (128-byte runs per half-warp)
+                const unsigned gb = deposit_pairs((unsigned)tid, a.last_g) | map_runs(tile_id, a.oruns_s, a.n_oruns_s);
+                unsigned ab[16], sc[4];
+#pragma unroll
+                for (int i = 0; i < 16; ++i) ab[i] = a.last_A[i >> 2] ^ a.last_B[i & 3];
+#pragma unroll
+                for (int c = 0; c < 4; ++c) sc[c] = gb ^ a.last_C[c];
+#pragma unroll
+                for (int e = 0; e < 64; ++e) st[sc[e & 3] ^ ab[e >> 2]] = v[e];
+                return;
             }
             unsigned ab[16], sc[4];
 #pragma unroll

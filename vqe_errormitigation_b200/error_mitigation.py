@@ -344,7 +344,10 @@ class IErrorMitigationManager:
         return self._dict_cache
 
     def _qp_matrix(self) -> List[np.ndarray]:
-        return [np.asarray(self._gate_lookup[op.gate], dtype=np.float64) for op in self._gate_ops]
+        # the lookup is fixed at construction; hashing 122 gate objects per call costs ~1 ms, so the list is built once
+        if getattr(self, "_qp_cache", None) is None:
+            self._qp_cache = [np.asarray(self._gate_lookup[op.gate], dtype=np.float64) for op in self._gate_ops]
+        return self._qp_cache
 
     def _signs_and_weights(self, rows: np.ndarray) -> Tuple[np.ndarray, List[float]]:
         qps = self._qp_matrix()
@@ -488,7 +491,9 @@ class IErrorMitigationManager:
 
     def total_cost(self) -> float:
         """prod_g sum_i |qp_g[i]|: the scalar every sampled value is multiplied by (reference :399, `np.prod(weights)`)."""
-        return float(np.prod([np.sum(np.abs(qp)) for qp in self._qp_matrix()]))
+        if getattr(self, "_cost_cache", None) is None:
+            self._cost_cache = float(np.prod([np.sum(np.abs(qp)) for qp in self._qp_matrix()]))
+        return self._cost_cache
 
     def variant_signs(self, variants: np.ndarray) -> np.ndarray:
         """sign prod_g qp_g[variants[b, g]] per row (reference :321-323)."""
