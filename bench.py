@@ -52,7 +52,8 @@ def get_prog(wl):
     if wl.get("_prog") is None:
         from vqe_errormitigation_b200 import engine
         wl["_prog"] = engine.CircuitProgram(wl["builder"], qubits=wl.get("qubits"), measurements=wl.get("measurements"),
-                                            hamiltonian=wl["terms"], options={**wl.get("options", {}), **PLAN_OPTIONS})
+                                            hamiltonian=wl["terms"], options={**wl.get("options", {}), **PLAN_OPTIONS},
+                                            coefficient_groups=wl.get("coefficient_groups"))
     return wl["_prog"]
 
 
@@ -83,6 +84,39 @@ def workload_h2_sweep():
                 name="H2 STO-3G 4q UCCSD, depolarize(1e-3) on every gate, 65536-circuit parameter sweep (BASELINE configs[1])",
                 builder=builder, qubits=qubits, measurements=measurements, batch=B, make_inputs=make_inputs,
                 terms=QPU.get_hamiltonian_terms(w), parity_rows=[0, B // 2, B - 1])
+
+
+BOND_LENGTHS = ["0.1", "0.2", "0.3", "0.4", "0.5", "0.6", "0.7", "0.7414", "0.8", "0.9", "1.0", "1.1", "1.2", "1.3", "1.4", "1.5", "1.6",
+                "1.7", "1.9", "2.0", "2.1", "2.2", "2.3", "2.4", "2.5", "2.6", "2.7", "2.8", "2.9", "3.0"]
+
+
+def workload_h2_bonds():
+    """Batch axes A x B of CPU.get_collection_ground_states (reference processor_classic.py:18-44): the 30 stored H2
+    geometries x optimiser chains in ONE launch - one plan, one Hamiltonian coefficient row per bond length
+    (dmx_plan_set_hamiltonian_groups), circuit b evaluated with row b % 30."""
+    from vqe_errormitigation_b200 import cirq_compat as cirq, engine
+    from vqe_errormitigation_b200.data_containers.helper_interfaces.i_parameter import IParameter
+    from vqe_errormitigation_b200.error_mitigation import TwoQubitDepolarizingChannel
+    from vqe_errormitigation_b200.processors.processor_quantum import QPU
+    w, _noise, n_w = _h2_noisy([cirq.depolarize(1e-3)], [TwoQubitDepolarizingChannel(1e-3)], "depolarize p=1e-3")
+    builder, qubits, measurements, _lifted, _key = engine.lower_circuit(n_w.get_noisy_circuit(), w.qubits)
+    group_terms = []
+    for r in BOND_LENGTHS:
+        w.update_molecule(IParameter({"r0": float(r)}))
+        group_terms.append(QPU.get_hamiltonian_terms(w))
+    assert all(np.array_equal(t[0], group_terms[0][0]) and np.array_equal(t[1], group_terms[0][1]) for t in group_terms)
+    B = 65536
+
+    def make_inputs(rank: int, seed_offset: int = 0):
+        p = -0.5 + (np.arange(B, dtype=np.float64) + 0.25 * rank) / (B - 1)
+        return p.reshape(B, 1), None
+
+    return dict(key="h2_bonds",
+                name="H2 4q UCCSD, depolarize(1e-3): 30 bond lengths x 2184 optimiser chains per launch (65536 circuits, one plan, "
+                     "one Hamiltonian coefficient row per bond length; batch axes of CPU.get_collection_ground_states)",
+                builder=builder, qubits=qubits, measurements=measurements, batch=B, make_inputs=make_inputs,
+                terms=group_terms[0], group_terms=group_terms, coefficient_groups=np.stack([t[2] for t in group_terms]),
+                make_groups=lambda rank: (np.arange(B, dtype=np.int32) + rank) % len(BOND_LENGTHS), parity_rows=[0, 1, 29, B // 2, B - 1])
 
 
 def workload_h2_qem():
@@ -278,9 +312,10 @@ def workload_lih12():
                 canonical_bytes=n_blocks * 32.0 * 4.0 ** n, cpu_sample=0, cpu_ops_fraction=0.002, golden="lih12_full", parity_rows=[0])
 
 
-WORKLOADS = {"h2_sweep": workload_h2_sweep, "h2_qem": workload_h2_qem, "hea10": workload_hea10, "lih12": workload_lih12}
-ALSO = ("h2_qem", "hea10", "lih12")       # riders of the default run (BASELINE configs[2..4])
-ALSO_STEPS = {"h2_qem": 20, "hea10": 3, "lih12": 2}
+WORKLOADS = {"h2_sweep": workload_h2_sweep, "h2_qem": workload_h2_qem, "hea10": workload_hea10, "lih12": workload_lih12,
+             "h2_bonds": workload_h2_bonds}
+ALSO = ("h2_qem", "hea10", "lih12", "h2_bonds")       # riders of the default run (BASELINE configs[2..4] + the A x B batch axes)
+ALSO_STEPS = {"h2_qem": 20, "hea10": 3, "lih12": 2, "h2_bonds": 20}
 
 
 # ---------------------------------------------------------------------------------------------------------
@@ -432,7 +467,7 @@ def run_reference(args, wl):
 # parity (outside every timed region): the workload's own rows against the oracle
 # ---------------------------------------------------------------------------------------------------------
 
-def parity_check(wl, prog, params_h, variants_h, rank: int):
+def parity_check(wl, prog, params_h, variants_h, rank: int, groups_h=None):
     """max |gpu - oracle| over a few rows of THIS workload's inputs.  4-qubit workloads: the C oracle runs live.  The
     streaming shapes: golden energies the same oracle produced for exactly these circuits and rows
     (tests/golden/large_energies.json, tools/make_golden_large.py; a 10-qubit depth-20 circuit costs the oracle ~1 min,
@@ -441,8 +476,10 @@ def parity_check(wl, prog, params_h, variants_h, rank: int):
     rows = [r for r in wl.get("parity_rows", [0]) if r < wl["batch"]]
     p = params_h[rows] if params_h is not None else None
     v = variants_h[rows] if variants_h is not None else None
+    g = groups_h[rows] if groups_h is not None else None
     got = prog.energies(torch.tensor(p, device="cuda") if p is not None else None,
-                        torch.tensor(v, device="cuda") if v is not None else None, batch=len(rows)).cpu().numpy()
+                        torch.tensor(v, device="cuda") if v is not None else None, batch=len(rows),
+                        groups=torch.tensor(g, device="cuda") if g is not None else None).cpu().numpy()
     b = wl["builder"]
     if wl.get("golden"):
         path = os.path.join(ROOT, "tests", "golden", "large_energies.json")
@@ -457,6 +494,10 @@ def parity_check(wl, prog, params_h, variants_h, rank: int):
                 return err, f"{k} row(s) vs tests/golden/large_energies.json[{wl['golden']}] (C oracle on this exact circuit and these rows)"
         return None, "no golden energies for this rank's rows (the oracle needs minutes to hours per circuit at this size)"
     from oracle import c_oracle
+    if g is not None:      # every row against the oracle with the Hamiltonian of its own coefficient group
+        want = np.array([c_oracle.energy_batch(b.n_qubits, list(b.ops), b.pool(), wl["group_terms"][int(gi)], params=p[i:i + 1], batch=1,
+                                               n_params=len(b.param_names), n_slots=b.n_slots, threads=1)[0] for i, gi in enumerate(g)])
+        return float(np.max(np.abs(got - want))), f"{len(rows)} rows vs the C oracle with each row's own Hamiltonian, run live"
     want = c_oracle.energy_batch(b.n_qubits, list(b.ops), b.pool(), wl["terms"], params=p, variants=v, batch=len(rows),
                                  n_params=len(b.param_names), n_slots=b.n_slots, threads=min(len(rows), 4))
     return float(np.max(np.abs(got - want))), f"{len(rows)} rows vs the C oracle (oracle/dm_oracle.c), run live"
@@ -501,19 +542,21 @@ def run_workload(wl, ctx, steps: int, warmup: int, with_cpu_baseline: bool, with
             cpu_baseline["by_threads"] = by
 
     params_h, variants_h = wl["make_inputs"](rank)
+    groups_h = np.ascontiguousarray(wl["make_groups"](rank), np.int32) if wl.get("make_groups") else None
     params_d = torch.tensor(params_h, device="cuda") if params_h is not None else None
     variants_d = torch.tensor(variants_h, device="cuda") if variants_h is not None else None
+    groups_d = torch.tensor(groups_h, device="cuda") if groups_h is not None else None
     out = torch.empty(B, dtype=torch.float64, device="cuda")
 
     def step():
-        prog.energies(params_d, variants_d, batch=B, out=out)
+        prog.energies(params_d, variants_d, batch=B, out=out, groups=groups_d)
 
     short_steps = info["path"] != 2
     for _ in range(warmup):
         flush.zero_()
         step()
     torch.cuda.synchronize()
-    parity_err, parity_src = parity_check(wl, prog, params_h, variants_h, rank)
+    parity_err, parity_src = parity_check(wl, prog, params_h, variants_h, rank, groups_h)
     if world > 1:
         dist.barrier()
     starts = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
@@ -573,12 +616,12 @@ def run_workload(wl, ctx, steps: int, warmup: int, with_cpu_baseline: bool, with
         # Register-resident plans (path 1) keep up to DEPTH batches in flight (dmx_energy_batch_host_async, each with its
         # own result buffer; dmx_plan_host_sync after every DEPTH-th step) - the way a sweep or a lock-step optimiser
         # driver calls it; streaming plans run one synchronous call per step.
-        depth = 4 if info["path"] == 1 else 1
-        params_p = pinned(params_h)
+        depth = 4 if info["path"] == 1 and groups_h is None else 1
+        params_p, groups_p = pinned(params_h), pinned(groups_h)
         res = [engine.pinned_empty(B) for _ in range(depth)]
 
         def host_step(i):
-            prog.energies_host(params_p, None, batch=B, out=res[i % depth], nowait=depth > 1)
+            prog.energies_host(params_p, None, batch=B, out=res[i % depth], nowait=depth > 1, groups=groups_p)
             if depth > 1 and (i + 1) % depth == 0:
                 prog.host_sync()
 
@@ -586,7 +629,8 @@ def run_workload(wl, ctx, steps: int, warmup: int, with_cpu_baseline: bool, with
         e2e_s = timed(host_step, n_e2e, n_warm=depth if depth > 1 else 3)
         prog.host_sync()
         zero_copy = info["path"] == 1 and PLAN_OPTIONS.get("host_zero_copy", 1) != 0
-        e2e = {"value": world * B * n_e2e / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(params_h.nbytes), "d2h_bytes_per_step": int(B * 8),
+        e2e = {"value": world * B * n_e2e / e2e_s, "unit": UNIT,
+               "h2d_bytes_per_step": int(params_h.nbytes + (groups_h.nbytes if groups_h is not None else 0)), "d2h_bytes_per_step": int(B * 8),
                "steps": n_e2e, "in_flight": depth,
                "api": "CircuitProgram.energies_host = dmx_energy_batch_host" + (f"_async, dmx_plan_host_sync every {depth} steps" if depth > 1 else ""),
                "checksum": float(np.sum(res[0])),

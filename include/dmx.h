@@ -126,6 +126,15 @@ int dmx_plan_create(int n_qubits, int n_params, int n_slots, const dmx_op* ops, 
 int dmx_plan_set_hamiltonian(dmx_plan* plan, int n_terms, const uint32_t* xmask, const uint32_t* zmask,
                              const double* coeff);
 
+/* Coefficient groups (optional, before finalize, after dmx_plan_set_hamiltonian): the same n_terms Pauli strings with
+ * n_groups different weight rows, coeff[n_groups][n_terms] in the term order of dmx_plan_set_hamiltonian.  The grouped
+ * execution calls let circuit b use row group[b].  This is the batch axis "bond lengths" of
+ * CPU.get_collection_ground_states (src/processors/processor_classic.py:18-44 loops noise models x bond lengths x
+ * restarts serially; IMeasurementCollection.get_wave_functions, src/data_containers/helper_interfaces/i_collection.py:56-78):
+ * every H2 geometry has the same 15 Jordan-Wigner strings with different coefficients, so 30 molecules x R restarts
+ * are ONE plan and ONE launch.  The un-grouped calls on such a plan use row 0. */
+int dmx_plan_set_hamiltonian_groups(dmx_plan* plan, int n_groups, const double* coeff);
+
 /* Options (before finalize).  key/value pairs; unknown keys -> DMX_ERR_INVALID.
  * Per plan:
  *   "fuse"         0/1  gate+channel block fusion (default 1)
@@ -164,6 +173,10 @@ size_t dmx_workspace_bytes(const dmx_plan* plan, int64_t batch);
  * rho is NOT renormalised (projector basis ops leave Tr rho < 1). */
 int dmx_energy_batch(dmx_plan* plan, int64_t batch, const double* d_params, const uint8_t* d_variants,
                      double* d_energy, void* d_workspace, size_t workspace_bytes, void* stream);
+
+/* As dmx_energy_batch with a coefficient row per circuit: d_group [B] int32 in [0, n_groups) (NULL: row 0). */
+int dmx_energy_batch_grouped(dmx_plan* plan, int64_t batch, const double* d_params, const uint8_t* d_variants,
+                             const int32_t* d_group, double* d_energy, void* d_workspace, size_t workspace_bytes, void* stream);
 
 /* d_rho [B, 2^n, 2^n] complex128: simulate(...).final_density_matrix. */
 int dmx_density_batch(dmx_plan* plan, int64_t batch, const double* d_params, const uint8_t* d_variants,
@@ -210,6 +223,10 @@ int dmx_qp_sample_variants(int n_slots, const int32_t* n_choices, const double* 
  * out, and waits.  This is the call a non-CUDA-aware host (the reference's Python) binds. */
 int dmx_energy_batch_host(dmx_plan* plan, int64_t batch, const double* h_params, const uint8_t* h_variants,
                           double* h_energy);
+
+/* Host-buffer call with a coefficient row per circuit (h_group [B] int32, NULL: row 0). */
+int dmx_energy_batch_host_grouped(dmx_plan* plan, int64_t batch, const double* h_params, const uint8_t* h_variants,
+                                  const int32_t* h_group, double* h_energy);
 
 /* Asynchronous form for callers that keep several batches in flight (a lock-step optimiser driver, a sweep): queues the
  * batch and returns; dmx_plan_host_sync waits for everything queued on the plan.  h_energy / h_params must stay valid and

@@ -242,3 +242,85 @@ def test_calculate_minimisation_driver_end_to_end(tmp_path, monkeypatch):
     assert abs(back[0].fci_value - (-1.1372701746571037)) < 1e-12 and abs(back[1].fci_value - (-1.13414767)) < 1e-8
     for c in back:
         assert len(c._optimized_exp_values) == 3 and -1.25 < c.measured_value < -0.95
+
+
+BOND_LENGTHS = [0.1, 0.2, 0.3, 0.4, 0.5, 0.6, 0.7, 0.7414, 0.8, 0.9, 1.0, 1.1, 1.2, 1.3, 1.4, 1.5, 1.6, 1.7, 1.9, 2.0, 2.1, 2.2, 2.3, 2.4,
+                2.5, 2.6, 2.7, 2.8, 2.9, 3.0]
+
+
+def test_grouped_energies_match_per_molecule_plans():
+    """Coefficient groups (dmx_plan_set_hamiltonian_groups / dmx_energy_batch_grouped): ONE noisy-H2 plan with one
+    coefficient row per bond length gives, row by row, the energies of 30 separate per-molecule plans and of the oracle -
+    on the device path, the host path (DMA pipeline and zero-copy) and through the frame32s sweep kernel."""
+    import torch
+    from workloads import h2_terms, h2_ops, build_program
+    from oracle import dm_oracle as O
+    from vqe_errormitigation_b200 import engine
+    keys = [format(r, "g") for r in BOND_LENGTHS]
+    terms = [h2_terms(k) for k in keys]
+    assert all(np.array_equal(t[0], terms[0][0]) and np.array_equal(t[1], terms[0][1]) for t in terms)      # same 15 strings
+    rows = np.stack([t[2] for t in terms])
+    n1, n2 = [O.depolarize(1e-3)], [O.two_qubit_depolarize(1e-3)]
+    b = engine.ProgramBuilder(4)
+    for kind, qs, pl in h2_ops(n1, n2):
+        if kind == "u":
+            b.add_unitary(qs, pl)
+        elif kind == "k":
+            b.add_kraus(qs, pl)
+        else:
+            b.add_rotation(qs[0], pl[0], pl[1], pl[2], pl[3])
+    rng = np.random.default_rng(4)
+    B = 4099
+    alphas = rng.uniform(-0.4, 0.4, size=(B, 1))
+    groups = rng.integers(0, len(keys), size=B).astype(np.int32)
+    for opts in ({}, {"frame32s": 8}, {"frame32": 0}, {"segments": 0}):
+        prog = engine.CircuitProgram(b, hamiltonian=terms[0], coefficient_groups=rows, options=opts)
+        got = prog.energies(torch.tensor(alphas, device="cuda"), groups=torch.tensor(groups, device="cuda")).cpu().numpy()
+        for g in (0, 7, 29):
+            single = build_program(h2_ops(n1, n2), 4, terms[g])
+            sel = np.flatnonzero(groups == g)
+            want = single.energies(torch.tensor(alphas[sel], device="cuda")).cpu().numpy()
+            assert np.max(np.abs(got[sel] - want)) < 1e-12, (opts, g)
+        i = 5
+        rho = O.simulate(4, O.with_noise(O.h2_gate_list(alphas[i, 0]), n1, n2))
+        assert abs(got[i] - O.energy_sparse(rho, O.pauli_terms_to_matrix(4, *terms[groups[i]]))) < 1e-10
+        host = prog.energies_host(alphas, groups=groups)                       # pageable buffers: DMA pipeline
+        assert np.max(np.abs(host - got)) < 1e-13
+        if not opts:
+            pa, pg, po = engine.pinned_empty((B, 1)), engine.pinned_empty(B, np.int32), engine.pinned_empty(B)
+            pa[...] = alphas
+            pg[...] = groups
+            prog.energies_host(pa, groups=pg, out=po)                           # page-locked: zero-copy
+            assert np.max(np.abs(po - got)) < 1e-13
+            assert np.max(np.abs(prog.energies(torch.tensor(alphas, device="cuda")).cpu().numpy() -
+                                 build_program(h2_ops(n1, n2), 4, terms[0]).energies(torch.tensor(alphas, device="cuda")).cpu().numpy())) < 1e-12
+
+
+def test_collection_ground_states_batched_reaches_fci_for_30_bond_lengths():
+    """CPU.get_collection_ground_states_batched: the noiseless minimisation of all 30 stored H2 geometries in lock-step
+    (one plan, 30 coefficient rows, one launch per optimiser round) lands on the FCI energies the reference stored for them
+    (src/classic_minimisation/H2_semi_minimisation `_fci_value`, equal to the hdf5 values) - SURVEY 8a row a12."""
+    from vqe_errormitigation_b200 import engine
+    from vqe_errormitigation_b200.data_containers.helper_interfaces.i_collection import IMeasurementCollection
+    collection = IMeasurementCollection(w=HydrogenAnsatz(), p_space=list(BOND_LENGTHS), n_space=[])
+    launches = engine.launch_count()
+    out = CPU.get_collection_ground_states_batched(collection, cpu_iter=2, max_evals=80, tol=1e-12)
+    used = engine.launch_count() - launches
+    assert len(out) == 30 and used <= 3 * 80                 # rounds, not chains x evaluations (60 chains x 80 = 4800)
+    from workloads import h2_golden
+    gold = h2_golden()["molecules"]
+    for c, r in zip(out, BOND_LENGTHS):
+        assert c.molecule_param == r and len(c._optimized_exp_values) == 2
+        fci = gold[format(r, "g")]["fci_energy"]
+        assert abs(c.fci_value - fci) < 1e-12
+        assert abs(c.measured_value - fci) < 1e-9, (r, c.measured_value, fci)
+    # a noisy model on top: still one plan per noise model, energies above FCI and below HF + noise penalty
+    from vqe_errormitigation_b200 import experiments as E
+    noisy = IMeasurementCollection(w=HydrogenAnsatz(), p_space=[0.7414, 1.0, 2.0], n_space=[E.asymmetric_pauli_noise_model(1e-4)])
+    res = CPU.get_collection_ground_states_batched(noisy, cpu_iter=1, max_evals=60, tol=1e-10)
+    for c in res:
+        assert c.fci_value < c.measured_value < c.fci_value + 0.2
+    single = CPU.get_custom_optimized_state(n_w=next(iter(IMeasurementCollection(w=HydrogenAnsatz(), p_space=[1.0],
+                                             n_space=[E.asymmetric_pauli_noise_model(1e-4)]).get_wave_functions()))[0],
+                                            max_cpu_iter=60, max_qpu_iter=0, use_density=True)[0]
+    assert abs(res[1].measured_value - single) < 1e-6

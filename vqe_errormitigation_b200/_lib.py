@@ -50,6 +50,7 @@ EXPORTS = {
                                   C.c_size_t, C.POINTER(C.c_void_p)]),
     "dmx_plan_set_hamiltonian": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32),
                                            C.POINTER(C.c_double)]),
+    "dmx_plan_set_hamiltonian_groups": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_double)]),
     "dmx_plan_set_option": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int]),
     "dmx_plan_finalize": (C.c_int, [C.c_void_p]),
     "dmx_plan_get_info": (C.c_int, [C.c_void_p, C.POINTER(DmxPlanInfo)]),
@@ -58,6 +59,8 @@ EXPORTS = {
     "dmx_workspace_bytes": (C.c_size_t, [C.c_void_p, C.c_int64]),
     "dmx_energy_batch": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                    C.c_size_t, C.c_void_p]),
+    "dmx_energy_batch_grouped": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                           C.c_size_t, C.c_void_p]),
     "dmx_density_batch": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                     C.c_size_t, C.c_void_p]),
     "dmx_diag_batch": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p,
@@ -71,6 +74,7 @@ EXPORTS = {
     "dmx_qp_sample_variants": (C.c_int, [C.c_int, C.POINTER(C.c_int32), C.POINTER(C.c_double), C.c_int, C.c_uint64, C.c_uint64,
                                          C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),
     "dmx_energy_batch_host": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "dmx_energy_batch_host_grouped": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "dmx_energy_batch_host_async": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),
     "dmx_plan_host_sync": (C.c_int, [C.c_void_p]),
     "dmx_measure_fp64_peak": (C.c_int, [C.POINTER(C.c_double), C.c_void_p]),

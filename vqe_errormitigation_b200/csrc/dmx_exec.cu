@@ -92,8 +92,9 @@ struct TileArgs {
     BitRun truns[8], oruns[8];
     int epilogue;               // 0 none, 1 energy, 2 copy state out
     const uint32_t* term_idx;
-    const double* term_coef;
+    const double* term_coef;    // [groups][n_terms]
     int n_terms;
+    const int* group;           // optional: circuit b uses coefficient row group[b] (row 0 when NULL)
     double* out;
 };
 
@@ -409,14 +410,13 @@ __global__ void __launch_bounds__(512) dmx_tile_kernel(const TileArgs a) {
                 long long ci = c_first + c;
                 if (ci >= total) continue;
                 const unsigned cbase = (unsigned)c << tbits;
+                const long long b = a.worklist ? a.worklist[ci] : ci;
+                const double* __restrict__ tc = a.term_coef + (a.group ? (size_t)a.group[b] * a.n_terms : 0);
                 double e = 0.0;
-                for (int t = lane; t < a.n_terms; t += 32) e += a.term_coef[t] * tile[swz(cbase | (a.term_idx[t] << a.pad))];
+                for (int t = lane; t < a.n_terms; t += 32) e += tc[t] * tile[swz(cbase | (a.term_idx[t] << a.pad))];
 #pragma unroll
                 for (int off = 16; off > 0; off >>= 1) e += __shfl_xor_sync(0xffffffffu, e, off);
-                if (lane == 0) {
-                    long long b = a.worklist ? a.worklist[ci] : ci;
-                    a.out[b] = e;
-                }
+                if (lane == 0) a.out[b] = e;
             }
         } else if (a.epilogue == 2) {
             const unsigned padmask = (1u << a.pad) - 1u;
@@ -449,7 +449,8 @@ struct FrameArgs {
     const int4* segs;           // [nseg] (xor_mask, use_shfl, cs_sel, 0)
     const RotInfo* classes;     // [n_classes]
     const double* init;         // [256]
-    const double* eweight;      // [256]
+    const double* eweight;      // [groups][256]
+    const int* group;           // optional coefficient row per circuit
     const int* eslot;           // [256] compact index of the thread's energy term or -1
     const double* params;
     const uint8_t* variants;
@@ -478,7 +479,6 @@ __global__ void __launch_bounds__(256) dmx_frame_kernel(const FrameArgs a) {
     const int p = threadIdx.x, warp = p >> 5, lane = p & 31;
     const long long ngroups = (a.batch + CPB - 1) / CPB;
     const double init = a.init[p];
-    const double ew = a.eweight[p];
     const int eslot = a.eslot[p];
 
     for (long long grp = blockIdx.x; grp < ngroups; grp += gridDim.x) {
@@ -584,7 +584,10 @@ __global__ void __launch_bounds__(256) dmx_frame_kernel(const FrameArgs a) {
         // circuit sums it in a fixed order
         if (eslot >= 0) {
 #pragma unroll
-            for (int c = 0; c < CPB; ++c) esm[c * epad + eslot] = ew * r[c];
+            for (int c = 0; c < CPB; ++c) {
+                const int g = (a.group && b0 + c < a.batch) ? a.group[b0 + c] : 0;
+                esm[c * epad + eslot] = a.eweight[g * 256 + p] * r[c];
+            }
         }
         __syncthreads();
         for (int c = warp; c < CPB; c += 8) {
@@ -615,7 +618,8 @@ struct Frame32Args {
     const int* cs_sel;            // [nseg] rotation class or < 0 (constant coefficients)
     const RotInfo* classes;
     const double* init;           // [32]
-    const double* eweight;        // [32]
+    const double* eweight;        // [groups][32]
+    const int* group;             // optional coefficient row per circuit
     const int* orig;              // [32] frame index (labels are indexed by it), -1 idle
     const double* params;
     const uint8_t* variants;
@@ -677,7 +681,7 @@ __global__ void __launch_bounds__(256, DMX_F32_MINB) dmx_frame32_kernel(const Fr
     const long long ngroups = (a.batch + CPB - 1) / CPB;
     const long long gwarp = (long long)blockIdx.x * 8 + warp, nwarps = (long long)gridDim.x * 8;
     const double init = a.init[lane];
-    const double ew = a.eweight[lane];
+    const double ew0 = a.eweight[lane];
     const int p = a.orig[lane] < 0 ? 0 : a.orig[lane];
 
     // Every warp runs the same number of rounds (rows past the batch are predicated off at the loads and stores): with a
@@ -830,8 +834,16 @@ __global__ void __launch_bounds__(256, DMX_F32_MINB) dmx_frame32_kernel(const Fr
         // class, offsets 2 / 1 finish it; CPB - 1 + 2 shuffles instead of 5 CPB.
         {
             double e[CPB];
+            if (a.group) {      // coefficient groups: the circuit's own row of energy weights (uniform branch on a kernel parameter)
 #pragma unroll
-            for (int c = 0; c < CPB; ++c) e[c] = ew * r[c];
+                for (int c = 0; c < CPB; ++c) {
+                    const int g = b0 + c < a.batch ? a.group[b0 + c] : 0;
+                    e[c] = a.eweight[g * 32 + lane] * r[c];
+                }
+            } else {
+#pragma unroll
+                for (int c = 0; c < CPB; ++c) e[c] = ew0 * r[c];
+            }
             int off = 16;
 #pragma unroll
             for (int m = CPB / 2; m >= 1; m >>= 1, off >>= 1) {
@@ -852,16 +864,110 @@ __global__ void __launch_bounds__(256, DMX_F32_MINB) dmx_frame32_kernel(const Fr
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// frame32, sweep form ("frame32s"): parameter sweeps of a plan with ONE rotation class and no variant table (the noisy
+// H2 UCCSD energy sweep, BASELINE configs[1]).  A warp owns 32 consecutive circuits: one coalesced 256-byte parameter
+// load, ONE sincos for all 32 lanes (the 8-circuit kernel above spends a third of its FP64 instructions on a sincos that
+// only 8 lanes use), then four rounds of 8 circuits through the segment tables (read through L1: no staging, no block
+// barrier), and one coalesced 256-byte store of the 32 energies.  Table entry per (segment, lane): (wc, wk, w1, partner).
+// ---------------------------------------------------------------------------------------------------------
+struct Frame32sArgs {
+    int nseg, n_params;
+    long long batch;
+    const double4* tab;           // [nseg][32]: x = wc, y = wk (own-coefficient factor = fma(wc, cos, wk)), z = w1, w = partner lane (bits)
+    RotInfo cls;                  // the single rotation class
+    const double* init;           // [32]
+    const double* eweight;        // [groups][32]
+    const int* group;             // optional coefficient row per circuit
+    const double* params;
+    double* out;
+};
+
+template <int CPB>      // circuits advanced together by one warp: 8 (four rounds per warp) or 16 (two rounds, twice the ILP)
+__global__ void __launch_bounds__(64) dmx_frame32s_kernel(const Frame32sArgs a) {
+    constexpr int NSUB = 32 / CPB, LPC = 32 / CPB;
+    const int lane = threadIdx.x & 31;
+
+    const long long w = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const long long b = w * 32 + lane;
+    // rows past the batch are predicated off at the load and the store: every warp runs the same instruction stream, so
+    // the shuffles need no convergence barrier
+    double sv = 0.0, cv = 1.0;
+    {
+        double theta = a.cls.offset;
+        if (b < a.batch) theta = fma(a.cls.scale, a.params[b * a.n_params + a.cls.param], a.cls.offset);
+        sincos(theta, &sv, &cv);
+    }
+    const double init = __ldg(a.init + lane);
+    const double ew0 = __ldg(a.eweight + lane);
+    const int g_lane = (a.group && b < a.batch) ? a.group[b] : 0;
+    double eout = 0.0;
+#pragma unroll 1
+    for (int sub = 0; sub < NSUB; ++sub) {
+        double2 csr[CPB];
+#pragma unroll
+        for (int c = 0; c < CPB; ++c) csr[c] = make_double2(__shfl_sync(0xffffffffu, cv, sub * CPB + c), __shfl_sync(0xffffffffu, sv, sub * CPB + c));
+        double r[CPB];
+#pragma unroll
+        for (int c = 0; c < CPB; ++c) r[c] = init;
+        const double2* const tab2 = reinterpret_cast<const double2*>(a.tab);
+        auto entry = [&](int k) {
+            const double2 lo = __ldg(tab2 + 2 * (k * 32 + lane)), hi = __ldg(tab2 + 2 * (k * 32 + lane) + 1);
+            return make_double4(lo.x, lo.y, hi.x, hi.y);
+        };
+        double4 t_n = a.nseg > 0 ? entry(0) : make_double4(0.0, 1.0, 0.0, 0.0);
+        for (int k = 0; k < a.nseg; ++k) {
+            const double4 t = t_n;
+            {   // next segment's entry: in flight while this one computes
+                const int kn = k + 1 < a.nseg ? k + 1 : k;
+                t_n = entry(kn);
+            }
+            const int src = __double2loint(t.w) & 31;
+#pragma unroll
+            for (int c = 0; c < CPB; ++c) {
+                const double other = __shfl_sync(0xffffffffu, r[c], src);
+                r[c] = fma(csr[c].y, t.z * other, fma(t.x, csr[c].x, t.y) * r[c]);
+            }
+        }
+        // energy: transposed butterfly (fixed order); afterwards lane 4 c holds the energy of circuit c of this round
+        double e[CPB];
+        if (a.group) {
+#pragma unroll
+            for (int c = 0; c < CPB; ++c) e[c] = __ldg(a.eweight + __shfl_sync(0xffffffffu, g_lane, sub * CPB + c) * 32 + lane) * r[c];
+        } else {
+#pragma unroll
+            for (int c = 0; c < CPB; ++c) e[c] = ew0 * r[c];
+        }
+        int off = 16;
+#pragma unroll
+        for (int m = CPB / 2; m >= 1; m >>= 1, off >>= 1) {
+            const bool hi = lane & off;
+#pragma unroll
+            for (int j = 0; j < m; ++j) {
+                const double keep = hi ? e[j + m] : e[j], send = hi ? e[j] : e[j + m];
+                e[j] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+            }
+        }
+#pragma unroll
+        for (; off > 0; off >>= 1) e[0] += __shfl_xor_sync(0xffffffffu, e[0], off);
+        const double mine = __shfl_sync(0xffffffffu, e[0], (lane & (CPB - 1)) * LPC);
+        if (lane / CPB == sub) eout = mine;
+    }
+    if (b < a.batch) a.out[b] = eout;
+}
+
+// ---------------------------------------------------------------------------------------------------------
 // small kernels
 // ---------------------------------------------------------------------------------------------------------
 __global__ void dmx_energy_kernel(const double* __restrict__ state, int n, long long batch, const uint32_t* __restrict__ term_idx,
-                                  const double* __restrict__ term_coef, int n_terms, double* __restrict__ out, long long out_offset) {
+                                  const double* __restrict__ term_coef, int n_terms, const int* __restrict__ group,
+                                  double* __restrict__ out, long long out_offset) {
     const int lane = threadIdx.x & 31;
     long long w = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (w >= batch) return;
     const double* r = state + (w << (2 * n));
+    const double* __restrict__ tc = term_coef + (group ? (size_t)group[out_offset + w] * n_terms : 0);
     double e = 0.0;
-    for (int t = lane; t < n_terms; t += 32) e += term_coef[t] * r[term_idx[t]];
+    for (int t = lane; t < n_terms; t += 32) e += tc[t] * r[term_idx[t]];
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) e += __shfl_xor_sync(0xffffffffu, e, off);
     if (lane == 0) out[out_offset + w] = e;
@@ -1099,6 +1205,7 @@ struct DevPlan {
     int* f_eslot = nullptr;
     int n_eterms = 0, n_smem_segs = 0;
     // compact frame (frame32)
+    double4* g_tab4 = nullptr;     // frame32s: (wc, wk, w1, partner) per (segment, lane)
     double2* g_w = nullptr; unsigned char* g_partner = nullptr; int* g_cs_sel = nullptr; double* g_init = nullptr; double* g_ew = nullptr; int* g_orig = nullptr;
     SlotDev* slots = nullptr;
     uint8_t* labels = nullptr;
@@ -1178,7 +1285,7 @@ static cudaError_t build_stream_tables(const Plan& p, DevPlan* d) {
             auto it = cfix_where.find(off);
             if (it != cfix_where.end()) return it->second;
             int at;
-            if (cfix.size() + 64 <= (size_t)STREAM3_CFIX) {
+            if (!p.opt_scale_smem && cfix.size() + 64 <= (size_t)STREAM3_CFIX) {
                 at = (int)cfix.size();
                 cfix.insert(cfix.end(), p.coefs.begin() + off, p.coefs.begin() + off + 64);
             } else {
@@ -1398,7 +1505,7 @@ static int upload_plan(Plan& p, DevPlan* d, int dev) {
         CUDA_TRY(upload(&d->rots, r));
     }
     CUDA_TRY(upload(&d->term_idx, p.term_idx));
-    CUDA_TRY(upload(&d->term_coef, p.term_coef));
+    CUDA_TRY(upload(&d->term_coef, p.term_coef_g));
     if (p.seg_eligible) {
         const int K = std::max(p.nseg, 1);
         std::vector<double2> w((size_t)K * 256, make_double2(0, 0));
@@ -1414,7 +1521,7 @@ static int upload_plan(Plan& p, DevPlan* d, int dev) {
         if (cl.empty()) cl.push_back(RotInfo{0, 0, 0.0, 0.0});
         CUDA_TRY(upload(&d->f_classes, cl));
         CUDA_TRY(upload(&d->f_init, p.f_init));
-        CUDA_TRY(upload(&d->f_eweight, p.f_eweight));
+        CUDA_TRY(upload(&d->f_eweight, p.f_eweight_g));
         std::vector<int> eslot(256, -1);
         int ne = 0;
         for (int j = 0; j < 256; ++j) if (p.f_eweight[j] != 0.0) eslot[j] = ne++;
@@ -1437,10 +1544,24 @@ static int upload_plan(Plan& p, DevPlan* d, int dev) {
                 for (int l = 0; l < 32; ++l) gw[(size_t)k * 32 + l] = make_double2(p.f32_w[((size_t)k * 32 + l) * 2], p.f32_w[((size_t)k * 32 + l) * 2 + 1]);
             }
             CUDA_TRY(upload(&d->g_w, gw));
+            {
+                std::vector<double4> t4((size_t)K * 32, make_double4(0.0, 1.0, 0.0, 0.0));
+                for (int k = 0; k < p.nseg; ++k)
+                    for (int l = 0; l < 32; ++l) {
+                        const unsigned char pb = p.f32_partner[(size_t)k * 32 + l];
+                        const bool moved = (pb & 0x80u) && p.fsegs[k].cs_sel >= 0;
+                        const double w0 = p.f32_w[((size_t)k * 32 + l) * 2], w1 = p.f32_w[((size_t)k * 32 + l) * 2 + 1];
+                        double pw;
+                        const long long bits = (long long)(pb & 31u);
+                        std::memcpy(&pw, &bits, sizeof(pw));
+                        t4[(size_t)k * 32 + l] = moved ? make_double4(w0, 0.0, w1, pw) : make_double4(0.0, w0, w1, pw);
+                    }
+                CUDA_TRY(upload(&d->g_tab4, t4));
+            }
             CUDA_TRY(upload(&d->g_partner, p.f32_partner));
             CUDA_TRY(upload(&d->g_cs_sel, sel));
             CUDA_TRY(upload(&d->g_init, p.f32_init));
-            CUDA_TRY(upload(&d->g_ew, p.f32_eweight));
+            CUDA_TRY(upload(&d->g_ew, p.f32_eweight_g));
             CUDA_TRY(upload(&d->g_orig, p.f32_orig));
         }
     }
@@ -1469,7 +1590,7 @@ static void free_devplan(DevPlan* d) {
     cudaFree(d->coefs); cudaFree(d->rots); cudaFree(d->term_idx); cudaFree(d->term_coef);
     cudaFree(d->f_w); cudaFree(d->f_segs); cudaFree(d->f_classes); cudaFree(d->f_init); cudaFree(d->f_eweight); cudaFree(d->f_eslot);
     cudaFree(d->slots); cudaFree(d->labels);
-    cudaFree(d->g_w); cudaFree(d->g_partner); cudaFree(d->g_cs_sel); cudaFree(d->g_init); cudaFree(d->g_ew); cudaFree(d->g_orig);
+    cudaFree(d->g_tab4); cudaFree(d->g_w); cudaFree(d->g_partner); cudaFree(d->g_cs_sel); cudaFree(d->g_init); cudaFree(d->g_ew); cudaFree(d->g_orig);
     for (auto& px : d->passx) cudaFree(px.coefs);
     if (d->h_stage) cudaFreeHost(d->h_stage);
     if (d->d_stage) cudaFree(d->d_stage);
@@ -1558,13 +1679,14 @@ static void fill_common(TileArgs& a, Plan& p, DevPlan* d, const Pass& ps, const 
 
 // Whole-state-in-smem execution (n <= 7).  worklist != nullptr: run only the listed circuits (energy only).
 static int run_tile_single(Plan& p, DevPlan* d, long long batch, const double* params, const uint8_t* variants, double* out,
-                           int mode, const int* worklist, const int* work_count, cudaStream_t st) {
+                           int mode, const int* worklist, const int* work_count, cudaStream_t st, const int* group = nullptr) {
     const Pass& ps = p.passes[0];
     TileArgs a{};
     fill_common(a, p, d, ps, params, variants);
     a.pad = p.n == 1 ? 2 : 0;
     a.k = p.n; a.cpb = p.cpb; a.batch = batch; a.worklist = worklist; a.work_count = work_count;
     a.epilogue = mode; a.term_idx = d->term_idx; a.term_coef = d->term_coef; a.n_terms = (int)p.term_idx.size(); a.out = out;
+    a.group = group;
     const unsigned E = (unsigned)a.cpb << (2 * p.n + a.pad);
     int threads, gpt;
     tile_geometry(E, &threads, &gpt);
@@ -1802,11 +1924,13 @@ static int launch_frame32(const Frame32Args& a, int sm_count, cudaStream_t st) {
 }
 
 
-static int run_segment(Plan& p, DevPlan* d, long long batch, const double* params, const uint8_t* variants, double* out, cudaStream_t st) {
+static int run_segment(Plan& p, DevPlan* d, long long batch, const double* params, const uint8_t* variants, double* out, cudaStream_t st,
+                       const int* group = nullptr) {
     FrameArgs a{};
     a.nseg = p.nseg; a.n_params = p.n_params; a.n_slots = p.n_slots; a.n_classes = (int)p.f_classes.size(); a.n_eterms = d->n_eterms;
     a.batch = batch; a.w = d->f_w; a.segs = d->f_segs; a.classes = d->f_classes; a.init = d->f_init; a.eweight = d->f_eweight;
     a.eslot = d->f_eslot; a.params = params; a.variants = variants; a.slots = d->slots; a.labels = d->labels; a.coefs = d->coefs; a.out = out;
+    a.group = group;
     // worklist of rows that need the general path: per call and stream-ordered (a plan may run on several streams at once)
     int* wl = nullptr;
     if (variants) {
@@ -1826,14 +1950,33 @@ static int run_segment(Plan& p, DevPlan* d, long long batch, const double* param
         g.nseg = p.nseg; g.n_params = p.n_params; g.n_slots = p.n_slots; g.n_classes = (int)p.f_classes.size(); g.batch = batch;
         g.w = d->g_w; g.partner = d->g_partner; g.cs_sel = d->g_cs_sel; g.classes = d->f_classes; g.init = d->g_init; g.eweight = d->g_ew;
         g.orig = d->g_orig; g.params = params; g.variants = variants; g.slots = d->slots; g.labels = d->labels; g.coefs = d->coefs;
-        g.out = out; g.worklist = a.worklist; g.work_count = a.work_count;
+        g.out = out; g.worklist = a.worklist; g.work_count = a.work_count; g.group = group;
         g.any_const = 0;
         for (int k = 0; k < p.nseg; ++k) g.any_const |= p.fsegs[k].cs_sel < 0;
+        // Measured on B200 (profiles/r2_frame32s_ab.txt): 14 warps per SM leave the issue slots idle at the BASELINE batch
+        // (65 536 circuits: 20.4 us against 18.6 us for the 8-circuit kernel with its 32 warps per SM), but from ~5e5
+        // circuits per launch the leaner instruction stream wins (2^20: 6.45e9 against 5.99e9 circuits/s, 2^22: 6.87e9
+        // against 6.27e9).  opt_frame32s: 0 never, 1 automatic (large batches), 8 / 16 always with that many circuits a round.
+        const bool sweep_form = p.opt_frame32s > 1 || (p.opt_frame32s == 1 && batch >= (1 << 19));
+        if (sweep_form && mode == 1 && !variants && !g.any_const) {
+            // parameter sweep with one rotation class: 32 circuits per warp (dmx_frame32s_kernel)
+            Frame32sArgs f{};
+            f.nseg = p.nseg; f.n_params = p.n_params; f.batch = batch; f.tab = d->g_tab4; f.cls = p.f_classes[0];
+            f.init = d->g_init; f.eweight = d->g_ew; f.group = group; f.params = params; f.out = out;
+            const long long warps = (batch + 31) / 32;
+            const long long grid = (warps + 1) / 2;
+            if (grid >= (1LL << 31)) return done(fail(DMX_ERR_UNSUPPORTED, "batch too large for one launch"));
+            if (p.opt_frame32s == 16) dmx_frame32s_kernel<16><<<(unsigned)grid, 64, 0, st>>>(f);
+            else dmx_frame32s_kernel<8><<<(unsigned)grid, 64, 0, st>>>(f);
+            ++g_launches;
+            CUDA_TRY(cudaGetLastError());
+            return done(DMX_OK);
+        }
         if (p.opt_seg_cpb == 4)
             rc = mode == 0 ? launch_frame32<4, 0>(g, d->sm_count, st) : mode == 1 ? launch_frame32<4, 1>(g, d->sm_count, st) : launch_frame32<4, 2>(g, d->sm_count, st);
         else
             rc = mode == 0 ? launch_frame32<8, 0>(g, d->sm_count, st) : mode == 1 ? launch_frame32<8, 1>(g, d->sm_count, st) : launch_frame32<8, 2>(g, d->sm_count, st);
-        if (rc == DMX_OK && variants) rc = run_tile_single(p, d, batch, params, variants, out, OUT_ENERGY, wl + 1, wl, st);
+        if (rc == DMX_OK && variants) rc = run_tile_single(p, d, batch, params, variants, out, OUT_ENERGY, wl + 1, wl, st, group);
         return done(rc);
     }
     if (p.opt_seg_cpb == 4) {
@@ -1843,7 +1986,7 @@ static int run_segment(Plan& p, DevPlan* d, long long batch, const double* param
     }
     if (rc == DMX_OK && variants) {
         // circuits with non-diagonal correction ops (R-type / projector basis ops) take the general tile path
-        rc = run_tile_single(p, d, batch, params, variants, out, OUT_ENERGY, wl + 1, wl, st);
+        rc = run_tile_single(p, d, batch, params, variants, out, OUT_ENERGY, wl + 1, wl, st, group);
     }
     return done(rc);
 }
@@ -1886,6 +2029,16 @@ int dmx_plan_set_hamiltonian(dmx_plan* plan, int n_terms, const uint32_t* xmask,
     return DMX_OK;
 }
 
+int dmx_plan_set_hamiltonian_groups(dmx_plan* plan, int n_groups, const double* coeff) {
+    if (!plan || n_groups < 1 || !coeff) return fail(DMX_ERR_INVALID, "bad coefficient-group arguments");
+    if (plan->p.finalized) return fail(DMX_ERR_STATE, "plan already finalized");
+    if (plan->p.hc.empty()) return fail(DMX_ERR_STATE, "set the Hamiltonian's Pauli strings first (dmx_plan_set_hamiltonian)");
+    if (n_groups > (1 << 20)) return fail(DMX_ERR_UNSUPPORTED, "too many coefficient groups");
+    plan->p.n_groups = n_groups;
+    plan->p.hgroups.assign(coeff, coeff + (size_t)n_groups * plan->p.hc.size());
+    return DMX_OK;
+}
+
 int dmx_plan_set_option(dmx_plan* plan, const char* key, int value) {
     if (!plan || !key) return fail(DMX_ERR_INVALID, "NULL argument");
     if (plan->p.finalized) return fail(DMX_ERR_STATE, "plan already finalized");
@@ -1917,6 +2070,11 @@ int dmx_plan_set_option(dmx_plan* plan, const char* key, int value) {
     } else if (k == "bulk") {
         if (value < 0 || value > 2) return fail(DMX_ERR_INVALID, "bulk must be 0 (register staging), 1 (cp.async.bulk) or 2 (direct global loads)");
         plan->p.opt_bulk = value;
+    } else if (k == "frame32s") {
+        if (value != 0 && value != 1 && value != 8 && value != 16) return fail(DMX_ERR_INVALID, "frame32s must be 0, 1 (= 8), 8 or 16");
+        plan->p.opt_frame32s = value;
+    } else if (k == "scale_smem") {
+        plan->p.opt_scale_smem = value != 0;
     } else if (k == "direct_store") {
         plan->p.opt_direct_store = value != 0;
     } else return fail(DMX_ERR_INVALID, "unknown option: " + k);
@@ -1977,7 +2135,7 @@ static int check_exec(dmx_plan* plan, int64_t batch, const double* d_params, con
 }
 
 static int energy_impl(dmx_plan* plan, int64_t batch, const double* d_params, const uint8_t* d_variants, double* d_energy,
-                       void* d_workspace, size_t workspace_bytes, cudaStream_t st) {
+                       void* d_workspace, size_t workspace_bytes, cudaStream_t st, const int* d_group = nullptr) {
     NvtxRange nvtx("dmx:energy_batch");
     Plan& p = plan->p;
     if (p.term_idx.empty()) return fail(DMX_ERR_STATE, "no Hamiltonian set");
@@ -1985,8 +2143,8 @@ static int energy_impl(dmx_plan* plan, int64_t batch, const double* d_params, co
     int rc = ensure_device(p, &d);
     if (rc) return rc;
     if (batch == 0) return DMX_OK;
-    if (p.path == 1) return run_segment(p, d, batch, d_params, d_variants, d_energy, st);
-    if (p.path == 0) return run_tile_single(p, d, batch, d_params, d_variants, d_energy, OUT_ENERGY, nullptr, nullptr, st);
+    if (p.path == 1) return run_segment(p, d, batch, d_params, d_variants, d_energy, st, d_group);
+    if (p.path == 0) return run_tile_single(p, d, batch, d_params, d_variants, d_energy, OUT_ENERGY, nullptr, nullptr, st, d_group);
     const size_t sb = (size_t)p.info.state_bytes;
     const long long cap = (long long)(workspace_bytes / (size_t)p.info.workspace_bytes_per_state);
     if (!d_workspace || cap < 1) return fail(DMX_ERR_INVALID, "workspace too small: need dmx_workspace_bytes()");
@@ -2003,7 +2161,7 @@ static int energy_impl(dmx_plan* plan, int64_t batch, const double* d_params, co
         int threads = 128;
         long long warps = cur;
         int grid = (int)((warps * 32 + threads - 1) / threads);
-        dmx_energy_kernel<<<grid, threads, 0, st>>>((const double*)d_workspace, p.n, cur, d->term_idx, d->term_coef, (int)p.term_idx.size(), d_energy, off);
+        dmx_energy_kernel<<<grid, threads, 0, st>>>((const double*)d_workspace, p.n, cur, d->term_idx, d->term_coef, (int)p.term_idx.size(), d_group, d_energy, off);
         ++g_launches;
         CUDA_TRY(cudaGetLastError());
     }
@@ -2015,6 +2173,14 @@ int dmx_energy_batch(dmx_plan* plan, int64_t batch, const double* d_params, cons
     int rc = check_exec(plan, batch, d_params, d_energy);
     if (rc) return rc;
     return energy_impl(plan, batch, d_params, d_variants, d_energy, d_workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+int dmx_energy_batch_grouped(dmx_plan* plan, int64_t batch, const double* d_params, const uint8_t* d_variants, const int32_t* d_group,
+                             double* d_energy, void* d_workspace, size_t workspace_bytes, void* stream) {
+    int rc = check_exec(plan, batch, d_params, d_energy);
+    if (rc) return rc;
+    if (d_group && plan->p.n_groups < 1) return fail(DMX_ERR_STATE, "plan has no coefficient groups (dmx_plan_set_hamiltonian_groups)");
+    return energy_impl(plan, batch, d_params, d_variants, d_energy, d_workspace, workspace_bytes, (cudaStream_t)stream, d_group);
 }
 
 int dmx_pauli_batch(dmx_plan* plan, int64_t batch, const double* d_params, const uint8_t* d_variants, double* d_pauli,
@@ -2184,7 +2350,13 @@ static void* mapped_alias(const void* ptr) {
 // that are already page-locked (cudaHostAlloc / cudaHostRegister, e.g. torch pinned tensors) are used in place; pageable
 // ones go through the plan's pinned staging buffer.
 static int energy_batch_host_impl(dmx_plan* plan, int64_t batch, const double* h_params, const uint8_t* h_variants, double* h_energy,
-                                  bool wait);
+                                  bool wait, const int32_t* h_group = nullptr);
+
+int dmx_energy_batch_host_grouped(dmx_plan* plan, int64_t batch, const double* h_params, const uint8_t* h_variants,
+                                  const int32_t* h_group, double* h_energy) {
+    if (h_group && plan && plan->p.n_groups < 1) return fail(DMX_ERR_STATE, "plan has no coefficient groups (dmx_plan_set_hamiltonian_groups)");
+    return energy_batch_host_impl(plan, batch, h_params, h_variants, h_energy, true, h_group);
+}
 
 int dmx_energy_batch_host(dmx_plan* plan, int64_t batch, const double* h_params, const uint8_t* h_variants, double* h_energy) {
     return energy_batch_host_impl(plan, batch, h_params, h_variants, h_energy, true);
@@ -2204,7 +2376,7 @@ int dmx_plan_host_sync(dmx_plan* plan) {
 }
 
 static int energy_batch_host_impl(dmx_plan* plan, int64_t batch, const double* h_params, const uint8_t* h_variants, double* h_energy,
-                                  bool wait) {
+                                  bool wait, const int32_t* h_group) {
     int rc = check_exec(plan, batch, h_params, h_energy);
     if (rc) return rc;
     Plan& p = plan->p;
@@ -2230,8 +2402,9 @@ static int energy_batch_host_impl(dmx_plan* plan, int64_t batch, const double* h
     if (p.opt_host_zero_copy && p.path == 1 && !h_variants) {
         double* const e_dev = (double*)mapped_alias(h_energy);
         const double* const p_dev = h_params ? (const double*)mapped_alias(h_params) : nullptr;
-        if (e_dev && (p_dev || !h_params)) {
-            rc = energy_impl(plan, batch, p_dev, nullptr, e_dev, nullptr, 0, d->stream);
+        const int* const g_dev = h_group ? (const int*)mapped_alias(h_group) : nullptr;
+        if (e_dev && (p_dev || !h_params) && (g_dev || !h_group)) {
+            rc = energy_impl(plan, batch, p_dev, nullptr, e_dev, nullptr, 0, d->stream, g_dev);
             if (!wait) return rc;            // dmx_energy_batch_host_async: the caller collects with dmx_plan_host_sync
             const cudaError_t e = cudaStreamSynchronize(d->stream);
             if (rc) return rc;
@@ -2242,10 +2415,11 @@ static int energy_batch_host_impl(dmx_plan* plan, int64_t batch, const double* h
     const size_t prow = h_params ? (size_t)p.n_params * 8 : 0, vrow = h_variants ? (size_t)p.n_slots : 0;
     auto align = [](size_t v) { return (v + 255) & ~(size_t)255; };
     const size_t pb = align((size_t)batch * prow), vb = align((size_t)batch * vrow), eb = align((size_t)batch * 8);
+    const size_t gb = h_group ? align((size_t)batch * 4) : 0;
     size_t ws = 0;
     if (p.path == 2) ws = (size_t)p.info.workspace_bytes_per_state * (size_t)std::min<int64_t>(batch, 64);
     const bool pin_in = is_pinned_host(h_params) && is_pinned_host(h_variants), pin_out = is_pinned_host(h_energy);
-    const size_t hneed = (pin_in ? 0 : pb + vb) + (pin_out ? 0 : eb), dneed = pb + vb + eb + ws;
+    const size_t hneed = (pin_in ? 0 : pb + vb) + (pin_out ? 0 : eb), dneed = pb + vb + eb + ws + gb;
     if (d->h_cap < hneed) {
         if (d->h_stage) CUDA_TRY(cudaFreeHost(d->h_stage));
         d->h_stage = nullptr; d->h_cap = 0;
@@ -2263,6 +2437,9 @@ static int energy_batch_host_impl(dmx_plan* plan, int64_t batch, const double* h
     const char* src_p = pin_in ? (const char*)h_params : hs;
     const char* src_v = pin_in ? (const char*)h_variants : hs + pb;
     char* dst_e = pin_out ? (char*)h_energy : hs + (pin_in ? 0 : pb + vb);
+    // coefficient rows: one small (pageable or pinned) copy ahead of the pipeline, ordered before every chunk on s_in
+    int* const d_grp = h_group ? (int*)(ds + pb + vb + eb + ws) : nullptr;
+    if (h_group) CUDA_TRY(cudaMemcpyAsync(d_grp, h_group, (size_t)batch * 4, cudaMemcpyHostToDevice, d->s_in));
     // small-state plans: pipeline in up to MAX_CHUNKS chunks; streaming plans are long-running, one chunk
     int n_chunks = 1;
     if (p.path != 2) n_chunks = (int)std::max<int64_t>(1, std::min<int64_t>(DevPlan::MAX_CHUNKS, batch / p.opt_host_chunk_rows));
@@ -2279,7 +2456,7 @@ static int energy_batch_host_impl(dmx_plan* plan, int64_t batch, const double* h
         CUDA_TRY(cudaEventRecord(d->ev_in[c], d->s_in));
         CUDA_TRY(cudaStreamWaitEvent(d->stream, d->ev_in[c], 0));
         rc = energy_impl(plan, cnt, prow ? (const double*)(ds + lo * prow) : nullptr, vrow ? (const uint8_t*)(ds + pb + lo * vrow) : nullptr,
-                         (double*)(ds + pb + vb) + lo, ws ? ds + pb + vb + eb : nullptr, ws, d->stream);
+                         (double*)(ds + pb + vb) + lo, ws ? ds + pb + vb + eb : nullptr, ws, d->stream, d_grp ? d_grp + lo : nullptr);
         if (rc) { cudaStreamSynchronize(d->stream); cudaStreamSynchronize(d->s_in); cudaStreamSynchronize(d->s_out); return rc; }
         CUDA_TRY(cudaEventRecord(d->ev_k[c], d->stream));
         CUDA_TRY(cudaStreamWaitEvent(d->s_out, d->ev_k[c], 0));

@@ -1731,11 +1731,12 @@ static bool build_segments(Plan& p, std::string& why) {
         if (!slot_seen[s]) { p.slots[s].seg = -1; p.slots[s].label.assign(SEG_E, 0); }
     // energy stage: E = sum_t c_t * w[idx_t] * r_in[src[idx_t]]
     const int shift = 2 * (SEG_N - p.n);
-    p.e_src.clear(); p.e_w.clear();
+    p.e_src.clear(); p.e_w.clear(); p.e_fac.clear();
     for (size_t t = 0; t < p.term_idx.size(); ++t) {
         int j = (int)(p.term_idx[t] << shift);
         p.e_src.push_back((uint8_t)cur.src[j]);
         p.e_w.push_back(p.term_coef[t] * cur.w[j]);
+        p.e_fac.push_back(cur.w[j]);
     }
     p.nseg = (int)p.segs.size();
     p.coefs.reserve(p.coefs.size());
@@ -1915,11 +1916,13 @@ static bool build_frame(Plan& p, std::string& why) {
     p.f_w.assign((size_t)K * SEG_E * 2, 0.0);
     p.f_init.assign(SEG_E, 0.0);
     p.f_eweight.assign(SEG_E, 0.0);
+    p.e_frame.assign(p.e_src.size(), -1);
     p.f_labels.assign((size_t)std::max(p.n_slots, 1) * SEG_E, 0);
     for (unsigned t = 0; t < (unsigned)SEG_E; ++t) {
         unsigned q = phys(t);
         p.f_init[q] = (t & 0xAAu) ? 0.0 : 1.0;
         p.f_eweight[q] = ew[t];
+        for (size_t te = 0; te < p.e_src.size(); ++te) if ((unsigned)holder[p.e_src[te]] == t) p.e_frame[te] = (int)q;
         for (int k = 0; k < K; ++k) {
             p.f_w[((size_t)k * SEG_E + q) * 2] = w[((size_t)k * SEG_E + t) * 2];
             p.f_w[((size_t)k * SEG_E + q) * 2 + 1] = w[((size_t)k * SEG_E + t) * 2 + 1];
@@ -1947,6 +1950,18 @@ static bool build_frame(Plan& p, std::string& why) {
     }
     p.f_single_class = p.f_classes.size() <= 1;
     build_frame32(p);
+    {   // per-group energy weights: linear in the coefficients, same routing as the base weights
+        const size_t T = p.term_idx.size(), G = (size_t)std::max(p.n_groups, 1);
+        p.f_eweight_g.assign(G * SEG_E, 0.0);
+        p.f32_eweight_g.assign(G * 32, 0.0);
+        for (size_t g = 0; g < G; ++g) {
+            for (size_t t = 0; t < T; ++t)
+                if (p.e_frame[t] >= 0) p.f_eweight_g[g * SEG_E + p.e_frame[t]] += p.term_coef_g[g * T + t] * p.e_fac[t];
+            if (p.f32_n > 0)
+                for (int l = 0; l < 32; ++l)
+                    if (p.f32_orig[l] >= 0) p.f32_eweight_g[g * 32 + l] = p.f_eweight_g[g * SEG_E + p.f32_orig[l]];
+        }
+    }
     return true;
 }
 
@@ -1978,6 +1993,24 @@ void lower_plan(Plan& p) {
             acc[idx] += p.hc[t];
         }
         for (uint32_t idx : order) { p.term_idx.push_back(idx); p.term_coef.push_back(acc[idx]); }
+        // coefficient groups: the same merge per row.  For a grouped plan the base coefficients only decide which Pauli
+        // coefficients are live (frame32 compaction), so they become sum_g |c_g| - non-zero wherever any row is.
+        const size_t T = p.term_idx.size(), G = (size_t)std::max(p.n_groups, 1);
+        p.term_coef_g.assign(G * T, 0.0);
+        if (p.n_groups > 0) {
+            std::map<uint32_t, size_t> at;
+            for (size_t t = 0; t < T; ++t) at[p.term_idx[t]] = t;
+            for (size_t g = 0; g < G; ++g)
+                for (size_t t = 0; t < p.hc.size(); ++t)
+                    p.term_coef_g[g * T + at[pauli_index(p.n, p.hx[t], p.hz[t])]] += p.hgroups[g * p.hc.size() + t];
+            for (size_t t = 0; t < T; ++t) {
+                double a = 0.0;
+                for (size_t g = 0; g < G; ++g) a += std::fabs(p.term_coef_g[g * T + t]);
+                p.term_coef[t] = a;
+            }
+        } else {
+            p.term_coef_g = p.term_coef;
+        }
     }
     if (p.n <= 7) schedule_single_pass(p);
     else {

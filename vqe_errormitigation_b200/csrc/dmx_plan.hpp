@@ -166,6 +166,10 @@ struct Plan {
     std::vector<double> pool;
     std::vector<uint32_t> hx, hz;
     std::vector<double> hc;
+    // Coefficient groups (dmx_plan_set_hamiltonian_groups): the same Pauli strings with n_groups different weight rows, e.g.
+    // one row per bond length; circuit b of a grouped call takes row group[b].  Input order [n_groups][hc.size()].
+    int n_groups = 0;
+    std::vector<double> hgroups;
     int opt_fuse = 1, opt_segments = 1, opt_tile_qubits = 6, opt_remap = 1, opt_triples = 1;
     // execution switches (read at launch time from THIS plan; they used to be process-wide statics)
     int opt_stream_kernel = 1;          // 0 -> generic dmx_tile_kernel for every streaming pass
@@ -173,8 +177,10 @@ struct Plan {
     int opt_host_zero_copy = 1;         // dmx_energy_batch_host works in place on mapped page-locked buffers
     long long opt_host_chunk_rows = 32768;
     int opt_frame32 = 1;                // compact warp-per-circuit frame kernel when <= 32 coefficients are live
+    int opt_frame32s = 1;               // one-rotation-class parameter sweeps: 32 circuits per warp (dmx_frame32s_kernel)
     int opt_seg_cpb = 8;                // circuits per warp / thread of the frame kernels
     int opt_bulk = 1;                   // streaming tile load: 0 register staging, 1 cp.async.bulk + mbarrier, 2 direct global loads
+    int opt_scale_smem = 0;             // streaming: permutation scale tables in shared memory (LDS.128) instead of the constant bank
     int opt_direct_store = 1;           // streaming: the last sweep of a pass writes its registers straight to global memory
     bool finalized = false;
 
@@ -197,6 +203,11 @@ struct Plan {
     // energy terms in the engine's index space
     std::vector<uint32_t> term_idx;
     std::vector<double> term_coef;
+    std::vector<double> term_coef_g;  // [max(n_groups, 1)][term_idx.size()]: what the tile / energy kernels read
+    std::vector<double> e_fac;        // segment path: e_w[t] = term_coef[t] * e_fac[t]
+    std::vector<int> e_frame;         // segment path: frame index (physical thread order) that holds term t at the energy stage
+    std::vector<double> f_eweight_g;  // [max(n_groups, 1)][256]
+    std::vector<double> f32_eweight_g;// [max(n_groups, 1)][32]
     // segment path
     int nseg = 0;
     std::vector<Segment> segs;

@@ -149,7 +149,10 @@ class ProgramBuilder:
 class CircuitProgram:
     """A finalized ``dmx_plan`` plus what the Python callers need (qubit order, parameter names, measurements)."""
 
-    def __init__(self, builder: ProgramBuilder, *, qubits=None, measurements=None, hamiltonian=None, options: Optional[dict] = None):
+    def __init__(self, builder: ProgramBuilder, *, qubits=None, measurements=None, hamiltonian=None, options: Optional[dict] = None,
+                 coefficient_groups: Optional[np.ndarray] = None):
+        """``coefficient_groups[G, T]``: G alternative weight rows for the T Pauli strings of ``hamiltonian`` (e.g. one row per
+        bond length); ``energies(..., groups=g[B])`` then lets circuit b use row g[b] (``dmx_plan_set_hamiltonian_groups``)."""
         lib = _lib.load()
         self._lib = lib
         self.n_qubits = builder.n_qubits
@@ -168,6 +171,7 @@ class CircuitProgram:
         check(lib.dmx_plan_create(self.n_qubits, self.n_params, self.n_slots, ops, len(builder.ops),
                                   pool.ctypes.data_as(C.POINTER(C.c_double)), pool.size, C.byref(self._handle)))
         self.has_hamiltonian = False
+        self.n_groups = 0
         try:
             if hamiltonian is not None:
                 x, z, c = hamiltonian
@@ -177,6 +181,13 @@ class CircuitProgram:
                 check(lib.dmx_plan_set_hamiltonian(self._handle, len(c), x.ctypes.data_as(C.POINTER(C.c_uint32)),
                                                    z.ctypes.data_as(C.POINTER(C.c_uint32)), c.ctypes.data_as(C.POINTER(C.c_double))))
                 self.has_hamiltonian = len(c) > 0
+                self.n_groups = 0
+                if coefficient_groups is not None:
+                    cg = np.ascontiguousarray(coefficient_groups, np.float64)
+                    if cg.ndim != 2 or cg.shape[1] != len(c):
+                        raise ValueError(f"coefficient_groups must have shape [G, {len(c)}]")
+                    check(lib.dmx_plan_set_hamiltonian_groups(self._handle, cg.shape[0], cg.ctypes.data_as(C.POINTER(C.c_double))))
+                    self.n_groups = cg.shape[0]
             for k, v in (options or {}).items():
                 check(lib.dmx_plan_set_option(self._handle, k.encode(), int(v)))
             check(lib.dmx_plan_finalize(self._handle))
@@ -249,8 +260,10 @@ class CircuitProgram:
     def _ptr(t):
         return C.c_void_p(t.data_ptr()) if t is not None else None
 
-    def energies(self, params=None, variants=None, *, batch: Optional[int] = None, out=None, workspace_states: Optional[int] = None):
-        """Re Tr(rho_b H) for every row; returns a CUDA float64 tensor [B] (async on the current stream)."""
+    def energies(self, params=None, variants=None, *, batch: Optional[int] = None, out=None, workspace_states: Optional[int] = None,
+                 groups=None):
+        """Re Tr(rho_b H) for every row; returns a CUDA float64 tensor [B] (async on the current stream).  ``groups[B]``
+        (int32): coefficient row of every circuit for programs built with ``coefficient_groups``."""
         if not self.has_hamiltonian:
             raise ValueError("program was built without a Hamiltonian")
         torch, dev, p_t, v_t, B = self._prep(params, variants, batch)
@@ -264,11 +277,18 @@ class CircuitProgram:
             nbytes = int(self.info["workspace_bytes_per_state"]) * states
         ws = self._ws(torch, dev, nbytes)
         stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+        if groups is not None:
+            g_t = torch.as_tensor(groups, device=dev).to(torch.int32).contiguous()
+            if g_t.numel() != B:
+                raise ValueError(f"groups has {g_t.numel()} entries for a batch of {B}")
+            check(self._lib.dmx_energy_batch_grouped(self._handle, B, self._ptr(p_t), self._ptr(v_t), self._ptr(g_t), self._ptr(out),
+                                                     self._ptr(ws), nbytes, stream))
+            return out
         check(self._lib.dmx_energy_batch(self._handle, B, self._ptr(p_t), self._ptr(v_t), self._ptr(out), self._ptr(ws), nbytes, stream))
         return out
 
     def energies_host(self, params: Optional[np.ndarray] = None, variants: Optional[np.ndarray] = None, batch: Optional[int] = None,
-                      out: Optional[np.ndarray] = None, nowait: bool = False) -> np.ndarray:
+                      out: Optional[np.ndarray] = None, nowait: bool = False, groups: Optional[np.ndarray] = None) -> np.ndarray:
         """Host-buffer call (``dmx_energy_batch_host``): numpy in, numpy out, copies included.  Page-locked arrays
         (``engine.pinned_empty``) are copied from / into in place; pageable ones go through a pinned staging buffer.
         ``nowait=True`` (``dmx_energy_batch_host_async``): the batch is queued and ``out`` is valid after
@@ -301,6 +321,15 @@ class CircuitProgram:
         elif out.dtype != np.float64 or out.size != B or not out.flags.c_contiguous:
             raise ValueError("out must be a contiguous float64 array of the batch size")
         # raw addresses (ndarray.ctypes builds a helper object per access: several microseconds on a 40 us call)
+        if groups is not None:
+            g = groups if (type(groups) is np.ndarray and groups.dtype == np.int32 and groups.flags.c_contiguous) \
+                else np.ascontiguousarray(groups, np.int32)
+            if g.size != B:
+                raise ValueError(f"groups has {g.size} entries for a batch of {B}")
+            check(self._lib.dmx_energy_batch_host_grouped(self._handle, B, p.__array_interface__["data"][0] if p is not None else None,
+                                                          v.__array_interface__["data"][0] if v is not None else None,
+                                                          g.__array_interface__["data"][0], out.__array_interface__["data"][0]))
+            return out
         fn = self._lib.dmx_energy_batch_host_async if nowait else self._lib.dmx_energy_batch_host
         check(fn(self._handle, B, p.__array_interface__["data"][0] if p is not None else None,
                  v.__array_interface__["data"][0] if v is not None else None, out.__array_interface__["data"][0]))

@@ -20,6 +20,7 @@ from ..data_containers.helper_interfaces.i_noise_wrapper import INoiseModel, INo
 from ..data_containers.helper_interfaces.i_parameter import IParameter
 from ..data_containers.helper_interfaces.i_wave_function import IWaveFunction
 from ..error_mitigation import IErrorMitigationManager
+from .. import engine
 from .processor_quantum import QPU
 
 
@@ -108,6 +109,64 @@ class CPU:
         _values, mu = manager.get_mu_effective(error_mitigation=True, density_representation=using_density, meas_reps=meas_reps)
         return mu
 
+    @staticmethod
+    def get_collection_ground_states_batched(collection: IMeasurementCollection, cpu_iter: int, qpu_iter: int = 0, max_evals: int = 60,
+                                             tol: float = 1e-9, x0_spread: float = 0.0, seed: int = 0) -> List[IContainer]:
+        """``get_collection_ground_states`` (reference :18-44: noise models x bond lengths x ``cpu_iter`` restarts, one
+        scipy run after the other) with the batch axes used: per noise model ONE plan - the noisy ansatz circuit - whose
+        Hamiltonian carries one coefficient row per bond length (every H2 geometry has the same Jordan-Wigner strings),
+        and (bond lengths x restarts) optimiser chains advanced in lock-step by :func:`lockstep_nelder_mead`, so every
+        optimiser round is one launch over all chains.  Objective: the deterministic Tr(rho H) the reference keeps at
+        :73-75 (``qpu_iter`` - shots per circuit of the sampled objective - is accepted for signature compatibility and
+        unused).  Restart j starts from the ansatz's current parameters plus ``x0_spread`` * N(0, 1) (restarts of a
+        deterministic objective from one point are identical).  Returns the reference's list of ``IContainer``."""
+        rng = np.random.default_rng(seed)
+        result: List[IContainer] = []
+        for channel in (collection.noise_model_space or [None]):
+            points = []         # (molecule parameters copy, molecule data, terms) per bond length
+            circuit = qubits = names = x_start = label = None
+            for value in collection.parameter_space:
+                w = collection._bind(value)
+                n_w = w if channel is None else INoiseWrapper(w, channel)
+                if circuit is None:
+                    label = "No Noise Model" if channel is None else channel.get_description()
+                    if channel is None:
+                        circuit = QPU.get_initial_state_circuit(w=w)
+                        circuit.append(w.operations(w.qubits))
+                    else:
+                        circuit = n_w.get_noisy_circuit()
+                    qubits, names = w.qubits, list(w.operator_parameters)
+                    x_start = np.fromiter(w.operator_parameters.dict.values(), dtype=float)
+                points.append((copy.deepcopy(w.molecule_parameters), w.molecule, QPU.get_hamiltonian_terms(w)))
+            # union of the Pauli strings, one coefficient row per bond length
+            strings: dict = {}
+            for _, _, (xs, zs, cs) in points:
+                for x, z in zip(xs, zs):
+                    strings.setdefault((int(x), int(z)), len(strings))
+            rows = np.zeros((len(points), len(strings)))
+            for g, (_, _, (xs, zs, cs)) in enumerate(points):
+                for x, z, c in zip(xs, zs, cs):
+                    rows[g, strings[(int(x), int(z))]] += c
+            keys = list(strings)
+            terms = (np.array([k[0] for k in keys], np.uint32), np.array([k[1] for k in keys], np.uint32), rows[0].copy())
+            builder, bq, measurements, _lifted, _key = engine.lower_circuit(circuit, qubits)
+            prog = engine.CircuitProgram(builder, qubits=bq, measurements=measurements, hamiltonian=terms, coefficient_groups=rows)
+            cols = [names.index(nm) for nm in prog.param_names]
+            G, R = len(points), max(int(cpu_iter), 1)
+            group_of_chain = np.repeat(np.arange(G, dtype=np.int32), R)
+            x0s = np.tile(x_start, (G * R, 1))
+            if x0_spread:
+                x0s = x0s + x0_spread * rng.standard_normal(x0s.shape)
+
+            def objective(xs: np.ndarray, chain_ids: np.ndarray) -> np.ndarray:
+                return prog.energies_host(np.ascontiguousarray(xs[:, cols]) if cols else None, batch=len(xs),
+                                          groups=np.ascontiguousarray(group_of_chain[chain_ids]))
+
+            fun, _x, _n = lockstep_nelder_mead_grouped(objective, x0s, max_evals=max_evals, tol=tol)
+            for g, (m_param, m_data, _) in enumerate(points):
+                result.append(IContainer(m_param=m_param, e_values=[float(v) for v in fun[g * R:(g + 1) * R]], m_data=m_data, label=label))
+        return result
+
     # ---- batched additions ----------------------------------------------------------------------------------------
     @staticmethod
     def get_batched_energies(n_w: IWaveFunction, params: np.ndarray, noisy: bool = True) -> np.ndarray:
@@ -135,6 +194,74 @@ class CPU:
             cols = [names.index(nm) for nm in prog.param_names]
             batch_objective = lambda xs: prog.energies_host(np.ascontiguousarray(xs[:, cols]))
         return lockstep_minimize(batch_objective, x0s, max_cpu_iter, tol)
+
+
+def lockstep_nelder_mead(batch_objective: Callable[[np.ndarray], np.ndarray], x0s: np.ndarray, max_evals: int, tol: float = 1e-6,
+                         initial_step: float = 0.05) -> Tuple[np.ndarray, np.ndarray, np.ndarray]:
+    """:func:`lockstep_nelder_mead_grouped` for an objective that does not need to know which chain a row belongs to."""
+    return lockstep_nelder_mead_grouped(lambda rows, _ids: batch_objective(rows), x0s, max_evals, tol, initial_step)
+
+
+def lockstep_nelder_mead_grouped(batch_objective: Callable[[np.ndarray, np.ndarray], np.ndarray], x0s: np.ndarray, max_evals: int,
+                                 tol: float = 1e-6, initial_step: float = 0.05) -> Tuple[np.ndarray, np.ndarray, np.ndarray]:
+    """Nelder-Mead for ``C`` independent chains, vectorised over the chains in numpy (no thread per chain): every round
+    of the algorithm - reflection, then expansion / contraction where a chain asks for one, then the shrink points - is
+    ONE call of ``batch_objective(rows[M, P], chain_ids[M]) -> values[M]``, i.e. one GPU launch however many chains there are (the
+    engine's batch of 65 536 circuits is 65 536 chains).  ``max_evals`` bounds the objective evaluations of every chain
+    (the meaning of ``max_cpu_iter`` / COBYLA's ``maxiter`` in the reference, processor_classic.py:88-92).  A chain stops
+    when its simplex has collapsed to ``tol`` in both value and position.  Returns (fun[C], x[C, P], evaluations[C])."""
+    x0s = np.atleast_2d(np.asarray(x0s, dtype=float))
+    C, P = x0s.shape
+    simplex = np.repeat(x0s[:, None, :], P + 1, axis=1)                  # [C, P+1, P]
+    for i in range(P):
+        step = np.where(x0s[:, i] != 0.0, initial_step * np.abs(x0s[:, i]), initial_step)
+        simplex[:, i + 1, i] += step
+    fvals = np.asarray(batch_objective(simplex.reshape(-1, P), np.repeat(np.arange(C), P + 1)), dtype=float).reshape(C, P + 1)
+    evals = np.full(C, P + 1)
+    active = np.ones(C, dtype=bool)
+    idx = np.arange(C)
+    while True:
+        order = np.argsort(fvals, axis=1, kind="stable")
+        fvals = np.take_along_axis(fvals, order, axis=1)
+        simplex = np.take_along_axis(simplex, order[:, :, None], axis=1)
+        spread_f = np.max(np.abs(fvals[:, 1:] - fvals[:, :1]), axis=1)
+        spread_x = np.max(np.abs(simplex[:, 1:, :] - simplex[:, :1, :]), axis=(1, 2))
+        active &= ~((spread_f <= tol) & (spread_x <= tol)) & (evals + 2 <= max_evals)
+        if not active.any():
+            break
+        a = idx[active]
+        centroid = simplex[a, :P, :].mean(axis=1)
+        worst = simplex[a, P, :]
+        xr = centroid + (centroid - worst)
+        fr = np.asarray(batch_objective(xr, a), dtype=float)
+        evals[a] += 1
+        f_best, f_second, f_worst = fvals[a, 0], fvals[a, P - 1] if P > 1 else fvals[a, 0], fvals[a, P]
+        expand = fr < f_best
+        accept = ~expand & (fr < f_second)
+        outside = ~expand & ~accept & (fr < f_worst)
+        inside = ~expand & ~accept & ~outside
+        second = expand | outside | inside
+        x2 = np.where(expand[:, None], centroid + 2.0 * (xr - centroid),
+                      np.where(outside[:, None], centroid + 0.5 * (xr - centroid), centroid - 0.5 * (centroid - worst)))
+        f2 = np.full(len(a), np.inf)
+        if second.any():
+            f2[second] = np.asarray(batch_objective(x2[second], a[second]), dtype=float)
+            evals[a[second]] += 1
+        new_x, new_f = worst.copy(), f_worst.copy()
+        take_r = accept | (expand & ~(f2 < fr)) | (outside & ~(f2 <= fr))
+        new_x[take_r], new_f[take_r] = xr[take_r], fr[take_r]
+        take_2 = (expand & (f2 < fr)) | (outside & (f2 <= fr)) | (inside & (f2 < f_worst))
+        new_x[take_2], new_f[take_2] = x2[take_2], f2[take_2]
+        simplex[a, P, :], fvals[a, P] = new_x, new_f
+        shrink = (outside & ~(f2 <= fr)) | (inside & ~(f2 < f_worst))
+        shrink &= evals[a] + P <= max_evals
+        if shrink.any():
+            sa = a[shrink]
+            simplex[sa, 1:, :] = simplex[sa, :1, :] + 0.5 * (simplex[sa, 1:, :] - simplex[sa, :1, :])
+            fvals[sa, 1:] = np.asarray(batch_objective(simplex[sa, 1:, :].reshape(-1, P), np.repeat(sa, P)), dtype=float).reshape(len(sa), P)
+            evals[sa] += P
+    best = np.argmin(fvals, axis=1)
+    return fvals[idx, best], simplex[idx, best, :], evals
 
 
 class _BatchFailed(Exception):
