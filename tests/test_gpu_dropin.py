@@ -256,7 +256,7 @@ def test_grouped_energies_match_per_molecule_plans():
     from workloads import h2_terms, h2_ops, build_program
     from oracle import dm_oracle as O
     from vqe_errormitigation_b200 import engine
-    keys = [format(r, "g") for r in BOND_LENGTHS]
+    keys = [str(r) for r in BOND_LENGTHS]
     terms = [h2_terms(k) for k in keys]
     assert all(np.array_equal(t[0], terms[0][0]) and np.array_equal(t[1], terms[0][1]) for t in terms)      # same 15 strings
     rows = np.stack([t[2] for t in terms])
@@ -311,7 +311,7 @@ def test_collection_ground_states_batched_reaches_fci_for_30_bond_lengths():
     gold = h2_golden()["molecules"]
     for c, r in zip(out, BOND_LENGTHS):
         assert c.molecule_param == r and len(c._optimized_exp_values) == 2
-        fci = gold[format(r, "g")]["fci_energy"]
+        fci = gold[str(r)]["fci_energy"]
         assert abs(c.fci_value - fci) < 1e-12
         assert abs(c.measured_value - fci) < 1e-9, (r, c.measured_value, fci)
     # a noisy model on top: still one plan per noise model, energies above FCI and below HF + noise penalty
