@@ -219,6 +219,18 @@ void dmx_qp_sampler_destroy(dmx_qp_sampler* sampler);
 int dmx_qp_sample_variants(int n_slots, const int32_t* n_choices, const double* qp, int stride, uint64_t seed,
                            uint64_t first_sample, int64_t batch, uint8_t* d_variants, double* d_signs, void* stream);
 
+/* Shot sampling on the device - the sampling half of DensityMatrixSimulator.run as the reference uses it
+ * (src/data_containers/model_hydrogen.py:132,155: evolve once, draw `repetitions` outcomes from |diag rho|, histogram) and the
+ * parity read-out of measure_observable (:103-112,136-166: expectation = 2 P(even parity on the term's qubits) - 1).
+ * d_probs [rows, dim] probability vectors (dmx_diag_batch output; dim = 2^n <= 128), `shots` draws per row (or
+ * d_row_shots[r] when that device array is given: meas_reps x count of a QP identifier, src/error_mitigation.py:386-388) from
+ * Philox4x32-10 (counter (shot / 4 lo, shot / 4 hi, row lo, row hi) with row = first_row + r, key = seed, word shot % 4 as
+ * u = (word + 0.5) / 2^32, outcome = first cumulative entry > u).  h_masks [n_masks] (host): bit n-1-q <-> qubit q; every
+ * mask is evaluated on the SAME shots.  d_expect [rows, n_masks].  Statistical parity with numpy's generator, bit-exact
+ * against the numpy Philox restatement in tests/philox_ref.py. */
+int dmx_shot_expectations(const double* d_probs, int64_t rows, int dim, int64_t shots, const int64_t* d_row_shots, const uint32_t* h_masks,
+                          int n_masks, uint64_t seed, uint64_t first_row, double* d_expect, void* stream);
+
 /* Same as dmx_energy_batch but with HOST buffers: copies params/variants in, runs, copies energies
  * out, and waits.  This is the call a non-CUDA-aware host (the reference's Python) binds. */
 int dmx_energy_batch_host(dmx_plan* plan, int64_t batch, const double* h_params, const uint8_t* h_variants,

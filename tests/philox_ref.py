@@ -42,3 +42,29 @@ def sample_variants(qps, batch, seed, first_sample=0):
         neg += qp[idx] < 0
         zero |= qp[idx] == 0
     return rows, np.where(zero, 0.0, np.where(neg % 2 == 1, -1.0, 1.0))
+
+
+def shot_expectations(probs, shots, masks, seed, first_row=0):
+    """numpy restatement of dmx_shot_expect_kernel: per row, shot s takes word s % 4 of Philox call (s // 4 lo, s // 4 hi,
+    row lo, row hi), outcome = first entry of cumsum(p) / sum(p) (last entry forced to 1) that exceeds u; every mask's
+    expectation 2 P(even parity) - 1 comes from the same shots."""
+    probs = np.asarray(probs, np.float64)
+    rows, dim = probs.shape
+    out = np.zeros((rows, len(masks)))
+    parity = np.array([[bin(i & int(m)).count("1") & 1 for i in range(dim)] for m in masks])
+    all_shots = np.broadcast_to(np.asarray(shots, np.int64), (rows,))
+    for r in range(rows):
+        shots = int(all_shots[r])
+        calls = (shots + 3) // 4
+        c = np.arange(calls, dtype=np.uint64)
+        row = np.uint64(first_row + r)
+        words = philox4x32_10(c & MASK, c >> np.uint64(32), np.full(calls, row & MASK, np.uint64), np.full(calls, row >> np.uint64(32), np.uint64), seed)
+        u = (np.stack(words, axis=1).reshape(-1)[:shots].astype(np.float64) + 0.5) * (1.0 / 4294967296.0)
+        cdf = np.cumsum(probs[r])
+        cdf = cdf / cdf[-1]
+        cdf[-1] = 1.0
+        outcome = np.minimum(np.searchsorted(cdf, u, side="right"), dim - 1)
+        hist = np.bincount(outcome, minlength=dim)
+        for j in range(len(masks)):
+            out[r, j] = 2.0 * (hist[parity[j] == 0].sum() / shots) - 1.0
+    return out

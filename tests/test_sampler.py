@@ -77,3 +77,91 @@ def test_device_resident_mitigation_estimator():
     ideal = QPU.get_simulated_noisy_expectation_value(w, clean, cirq.ParamResolver({}))
     noisy = QPU.get_simulated_noisy_expectation_value(n_w, QPU.get_resolved_circuit(n_w.get_noisy_circuit(), w.operator_parameters), cirq.ParamResolver({}))
     assert abs(mean - ideal) < 6 * stderr + 1e-4 and abs(mean - ideal) < abs(noisy - ideal)
+
+
+def test_reference_shot_sampler_statistics():
+    """numpy restatement of the device shot sampler (philox_ref.shot_expectations): parity expectations converge to the exact
+    values of the distribution, every mask is read from the same shots, rows use independent streams."""
+    rng = np.random.default_rng(3)
+    probs = rng.dirichlet(np.ones(16), size=3)
+    masks = [0b1000, 0b0100, 0b1100, 0b1111]
+    shots = 200000
+    got = P.shot_expectations(probs, shots, masks, seed=5)
+    for r in range(3):
+        for j, m in enumerate(masks):
+            sign = np.array([1 - 2 * (bin(i & m).count("1") & 1) for i in range(16)])
+            assert abs(got[r, j] - float(np.dot(sign, probs[r]))) < 5 / np.sqrt(shots)
+    # a deterministic distribution gives exact parities; first_row shifts the stream; per-row shot counts
+    delta = np.zeros((1, 16)); delta[0, 0b1010] = 1.0
+    assert P.shot_expectations(delta, 17, masks, seed=1).tolist() == [[-1.0, 1.0, -1.0, 1.0]]
+    a = P.shot_expectations(probs, 1000, masks, seed=9, first_row=1)
+    b = P.shot_expectations(probs[:1], 1000, masks, seed=9, first_row=1)
+    c = P.shot_expectations(np.concatenate([probs[:1], probs]), 1000, masks, seed=9)
+    assert np.array_equal(a[:1], b) and np.array_equal(c[1], b[0])       # row 1 of c: probs[0] on stream row 1, like b
+    d = P.shot_expectations(probs, np.array([10, 1000, 7]), masks, seed=9)
+    assert np.array_equal(d[1], P.shot_expectations(probs[1:2], 1000, masks, seed=9, first_row=1)[0])
+
+
+@pytest.mark.gpu
+def test_device_shot_sampler_is_bit_exact_with_reference():
+    import torch
+    from vqe_errormitigation_b200 import engine
+    rng = np.random.default_rng(21)
+    for dim, masks in ((16, [0b1000, 0b0001, 0b0110, 0b1111]), (128, [1, 64, 127, 0b1010101]), (2, [1])):
+        probs = rng.dirichlet(np.ones(dim) * 0.5, size=37)
+        probs[3] = 0.0
+        probs[3, dim - 1] = 1.0
+        for shots in (1, 10, 1001):
+            want = P.shot_expectations(probs, shots, masks, seed=1234567, first_row=5)
+            got = engine.shot_expectations(torch.tensor(probs, device="cuda"), shots, masks, 1234567, first_row=5).cpu().numpy()
+            assert np.array_equal(got, want), (dim, shots)
+        per_row = rng.integers(1, 500, size=37)
+        want = P.shot_expectations(probs, per_row, masks, seed=99)
+        got = engine.shot_expectations(torch.tensor(probs, device="cuda"), per_row, masks, 99).cpu().numpy()
+        assert np.array_equal(got, want)
+
+
+@pytest.mark.gpu
+def test_sampled_energy_program_batched_matches_exact_limit():
+    """SampledEnergyProgram (the five measurement circuits of measure_observable as one plan, shots on the device): the
+    batched sampled energies of several parameter rows converge to the exact sum_t w_t <P_t> of their own circuits, rows
+    are independent, and a fixed seed reproduces the numbers."""
+    import torch
+    from oracle import dm_oracle as O
+    from vqe_errormitigation_b200 import cirq_compat as cirq
+    from vqe_errormitigation_b200.data_containers.helper_interfaces.i_noise_wrapper import INoiseModel, INoiseWrapper
+    from vqe_errormitigation_b200.data_containers.helper_interfaces.i_wave_function import IGeneralizedUCCSD
+    from vqe_errormitigation_b200.data_containers.model_hydrogen import HydrogenAnsatz, SampledEnergyProgram
+    from vqe_errormitigation_b200.error_mitigation import TwoQubitDepolarizingChannel
+    from vqe_errormitigation_b200.openfermion_compat import jordan_wigner
+    from vqe_errormitigation_b200.processors.processor_quantum import QPU
+    w = HydrogenAnsatz()
+    model = INoiseModel([cirq.depolarize(2e-3)], [TwoQubitDepolarizingChannel(2e-3)], "d")
+    n_w = INoiseWrapper(w, model)
+    ham = jordan_wigner(w.molecule.get_molecular_hamiltonian())
+    prog = SampledEnergyProgram(n_w.get_noisy_circuit(), w.qubits, ham, model.get_operators, IGeneralizedUCCSD.pauli_basis_map())
+    assert prog.variant_rows.shape == (5, 4) and prog.prog.param_names == ["alpha0"]
+    alphas = np.array([[-0.2], [0.0141], [0.3]])
+    shots = 400000
+    got = prog.energies(alphas, shots, seed=11)
+    assert np.array_equal(got, prog.energies(alphas, shots, seed=11)) and not np.array_equal(got, prog.energies(alphas, shots, seed=12))
+    basis = w.pauli_basis_map()
+    for b, alpha in enumerate(alphas[:, 0]):
+        w.operator_parameters["alpha0"] = alpha
+        base = QPU.get_resolved_circuit(n_w.get_noisy_circuit(), w.operator_parameters)
+        exact = 0.0
+        for term, coeff in ham.terms.items():
+            if len(term) == 0:
+                exact += complex(coeff).real
+                continue
+            c = base.copy()
+            if len(term) == 4:
+                c.append([(basis[p](w.qubits[q], 1), model.get_operators(w.qubits[q])) for q, p in term])
+            else:
+                for q in range(4):
+                    c.append([cirq.I(w.qubits[q]), model.get_operators(w.qubits[q])])
+            rho = O.simulate(4, O.from_circuit(c, w.qubits)[1])
+            zmask = sum(1 << (3 - q) for q, _ in term)
+            par = np.array([bin(i & zmask).count("1") % 2 for i in range(16)])
+            exact += complex(coeff).real * float(np.sum(np.where(par == 0, 1, -1) * O.probabilities(rho)))
+        assert abs(got[b] - exact) < 6 * 0.6 / np.sqrt(shots), (b, got[b], exact)

@@ -73,6 +73,8 @@ EXPORTS = {
     "dmx_qp_sampler_destroy": (None, [C.c_void_p]),
     "dmx_qp_sample_variants": (C.c_int, [C.c_int, C.POINTER(C.c_int32), C.POINTER(C.c_double), C.c_int, C.c_uint64, C.c_uint64,
                                          C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "dmx_shot_expectations": (C.c_int, [C.c_void_p, C.c_int64, C.c_int, C.c_int64, C.c_void_p, C.POINTER(C.c_uint32), C.c_int, C.c_uint64, C.c_uint64,
+                                        C.c_void_p, C.c_void_p]),
     "dmx_energy_batch_host": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),
     "dmx_energy_batch_host_grouped": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "dmx_energy_batch_host_async": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),

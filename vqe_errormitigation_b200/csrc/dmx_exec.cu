@@ -1175,6 +1175,62 @@ __global__ void __launch_bounds__(256) dmx_qp_sample_kernel(int n_slots, const i
     if (lane == 0) signs[b] = zero ? 0.0 : (neg ? -1.0 : 1.0);
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Shot sampler (K4, sampled mode): DensityMatrixSimulator.run evolves once and draws `shots` computational-basis outcomes
+// from |diag rho| renormalised; measure_observable (src/data_containers/model_hydrogen.py:114-175) turns the histogram into
+// parity expectations 2 P(even) - 1.  One warp per row of probabilities: the cumulative distribution is built once in
+// shared memory (sequential double sum, like numpy.cumsum), the lanes draw the shots - Philox4x32-10, counter (shot / 4 lo,
+// shot / 4 hi, row lo, row hi), key = seed, word (shot % 4) as u = (word + 0.5) / 2^32, outcome = first cdf entry > u - into
+// a shared-memory histogram, and every requested parity mask is evaluated on that one histogram (the reference derives
+// all its Z / ZZ expectations from the same shots too).  Bit-exact against tests/philox_ref.py::shot_expectations.
+// ---------------------------------------------------------------------------------------------------------
+constexpr int SHOT_MAX_DIM = 128;      // 2^7 outcomes: every circuit the whole-state kernels handle
+
+__global__ void __launch_bounds__(128) dmx_shot_expect_kernel(const double* __restrict__ probs, long long rows, int dim, long long shots_all,
+                                                              const long long* __restrict__ row_shots, const unsigned* __restrict__ masks, int n_masks, unsigned long long seed,
+                                                              unsigned long long first_row, double* __restrict__ expect) {
+    __shared__ double cdf[4][SHOT_MAX_DIM];
+    __shared__ int hist[4][SHOT_MAX_DIM];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long r = (long long)blockIdx.x * 4 + warp;
+    if (r >= rows) return;
+    const double* __restrict__ p = probs + r * dim;
+    const long long shots = row_shots ? row_shots[r] : shots_all;
+    for (int i = lane; i < dim; i += 32) hist[warp][i] = 0;
+    if (lane == 0) {
+        double acc = 0.0;
+        for (int i = 0; i < dim; ++i) { acc += p[i]; cdf[warp][i] = acc; }
+        const double total = acc;
+        for (int i = 0; i < dim; ++i) cdf[warp][i] = cdf[warp][i] / total;
+        cdf[warp][dim - 1] = 1.0;
+    }
+    __syncwarp();
+    const unsigned long long row = first_row + (unsigned long long)r;
+    const long long calls = (shots + 3) / 4;
+    for (long long c = lane; c < calls; c += 32) {
+        unsigned w[4] = {(unsigned)c, (unsigned)((unsigned long long)c >> 32), (unsigned)row, (unsigned)(row >> 32)};
+        philox4x32_10(w, (unsigned)seed, (unsigned)(seed >> 32));
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            if (4 * c + j >= shots) break;
+            const double u = ((double)w[j] + 0.5) * (1.0 / 4294967296.0);
+            int lo = 0, hi = dim - 1;            // first index with cdf > u (cdf[dim - 1] = 1 > u)
+            while (lo < hi) {
+                const int mid = (lo + hi) >> 1;
+                if (cdf[warp][mid] > u) hi = mid; else lo = mid + 1;
+            }
+            atomicAdd(&hist[warp][lo], 1);
+        }
+    }
+    __syncwarp();
+    for (int m = lane; m < n_masks; m += 32) {
+        const unsigned mask = masks[m];
+        long long even = 0;
+        for (int i = 0; i < dim; ++i) if (!(__popc((unsigned)i & mask) & 1)) even += hist[warp][i];
+        expect[r * n_masks + m] = 2.0 * ((double)even / (double)shots) - 1.0;
+    }
+}
+
 // device tables of a QP sampler (dmx_qp_sampler_create): [cdf | first cdf entries | n_choices | first sign codes | sign codes]
 struct dmx_qp_sampler {
     int n_slots = 0, stride = 0, device = -1;
@@ -2327,6 +2383,27 @@ int dmx_qp_sample_variants(int n_slots, const int32_t* n_choices, const double* 
     if (rc == DMX_OK && batch > 0 && cudaStreamSynchronize((cudaStream_t)stream) != cudaSuccess) rc = fail(DMX_ERR_CUDA, "sampler launch failed");
     dmx_qp_sampler_destroy(sm);
     return rc;
+}
+
+int dmx_shot_expectations(const double* d_probs, int64_t rows, int dim, int64_t shots, const int64_t* d_row_shots, const uint32_t* h_masks,
+                          int n_masks, uint64_t seed, uint64_t first_row, double* d_expect, void* stream) {
+    if (!d_probs || !d_expect || !h_masks || rows < 0 || (!d_row_shots && shots < 1) || n_masks < 1 || n_masks > 4096)
+        return fail(DMX_ERR_INVALID, "bad arguments");
+    if (dim < 1 || dim > SHOT_MAX_DIM || (dim & (dim - 1))) return fail(DMX_ERR_UNSUPPORTED, "dim must be a power of two up to 128");
+    if (rows == 0) return DMX_OK;
+    NvtxRange nvtx("dmx:shot_expectations");
+    cudaStream_t st = (cudaStream_t)stream;
+    unsigned* d_masks = nullptr;
+    CUDA_TRY(cudaMallocAsync((void**)&d_masks, (size_t)n_masks * 4, st));
+    CUDA_TRY(cudaMemcpyAsync(d_masks, h_masks, (size_t)n_masks * 4, cudaMemcpyHostToDevice, st));
+    const long long grid = (rows + 3) / 4;
+    if (grid >= (1LL << 31)) { cudaFreeAsync(d_masks, st); return fail(DMX_ERR_UNSUPPORTED, "too many rows for one launch"); }
+    dmx_shot_expect_kernel<<<(unsigned)grid, 128, 0, st>>>(d_probs, rows, dim, shots, (const long long*)d_row_shots, d_masks, n_masks, seed, first_row, d_expect);
+    ++g_launches;
+    const cudaError_t e = cudaGetLastError();
+    CUDA_TRY(cudaFreeAsync(d_masks, st));
+    CUDA_TRY(e);
+    return DMX_OK;
 }
 
 static bool is_pinned_host(const void* ptr) {

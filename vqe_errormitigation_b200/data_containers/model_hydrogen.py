@@ -3,8 +3,9 @@
 ``observable_measurement`` returns the sampled-energy objective the reference's COBYLA loop minimises
 (``src/processors/processor_classic.py:77-92``): five measurement circuits (one computational-basis circuit
 for the Z / ZZ terms, one per XXYY-type term), shot histograms, parity probabilities, and the weighted sum
-over Hamiltonian terms (reference lines 83-177).  The five density-matrix evolutions run as one batch on the
-GPU; only the multinomial shot sampling stays on the host (it is defined by numpy's global RNG stream).
+over Hamiltonian terms (reference lines 83-177).  The five density-matrix evolutions are ONE plan and one launch
+(``SampledEnergyProgram``), the shots are drawn on the device (``dmx_shot_expectations``: Philox4x32-10 seeded from
+numpy's global RNG, so ``np.random.seed`` still fixes a run) and only the parity expectations return to the host.
 """
 from __future__ import annotations
 
@@ -56,35 +57,113 @@ class HydrogenAnsatz(IGeneralizedUCCSD):
             return float(np.mean(bits[:, columns].sum(axis=1) % 2 == 0))
 
         def measure_observable(base_circuit: cirq.Circuit, noise_wrapper: Callable, meas_reps: int) -> float:
-            # circuit for the one- and two-Z terms: identity "basis change" (+ its noise) on every Z_i
-            circuits = []
-            c01 = base_circuit.copy()
-            for term in by_size.get(1, []):
-                c01.append([(to_z_basis[p](qubits[q], 1), noise_wrapper(qubits[q])) for q, p in term])
-            c01.append(cirq.measure(q, key=f"Z{i}") for i, q in enumerate(qubits))
-            circuits.append(c01)
-            for term in by_size.get(4, []):
-                c02 = base_circuit.copy()
-                c02.append([(to_z_basis[p](qubits[q], 1), noise_wrapper(qubits[q])) for q, p in term])
-                c02.append(cirq.measure(q, key=f"{term[i][1]}{term[i][0]}") for i, q in enumerate(qubits))
-                circuits.append(c02)
-            shots = sample_circuits(circuits, meas_reps)
-
-            expectation = {(): 1.0}
-            z_bits = shots[0]
-            for i in range(n):
-                expectation[((i, "Z"),)] = 2 * parity_probability(z_bits, [i]) - 1
-            for i, j in itertools.combinations(range(n), 2):
-                expectation[((i, "Z"), (j, "Z"))] = 2 * parity_probability(z_bits, [i, j]) - 1
-            for term, bits in zip(by_size.get(4, []), shots[1:]):
-                expectation[term] = 2 * parity_probability(bits, list(range(n))) - 1
-            result = 0
-            for term in itertools.chain.from_iterable(by_size.values()):
-                if term in expectation:
-                    result += weight[term] * expectation[term]
-            return result
+            """Sampled energy of one resolved circuit (reference :114-175).  The five measurement circuits - Z basis, and
+            one per four-qubit XXYY-type term - are ONE plan: the base circuit plus a per-qubit variant slot holding the
+            basis-change gate (I / H / rx(-pi/2), each followed by its noise), so one launch evolves all five; the shots
+            are drawn on the device (``dmx_shot_expectations``) and only the parity expectations come back."""
+            prog = SampledEnergyProgram.for_circuit(base_circuit, qubits, hamiltonian, noise_wrapper, to_z_basis)
+            seed = int(np.random.randint(0, 2 ** 31 - 1))        # numpy's global RNG stays the source of randomness
+            return float(prog.energies(None, meas_reps, seed)[0])
 
         return measure_observable, 5
+
+
+class SampledEnergyProgram:
+    """``measure_observable`` (reference model_hydrogen.py:114-175) as a batched device program.
+
+    Plan = base circuit + one ``DMX_OP_VARIANT`` slot per qubit whose table holds the basis-change gates
+    (index 1: identity, 2: X -> Z basis, 3: Y -> Z basis; index 0 = qubit not measured through a gate) followed by the
+    noise ops "if the slot is non-zero".  Measurement circuit m of parameter row b is variant row m: M rows per parameter
+    row in one launch, |diag rho| for all of them, shots + parities on the device.  ``energies`` returns
+    sum_t w_t <P_t> per parameter row, the identity term included, exactly as the reference assembles it (:126,171-175):
+    Z and ZZ expectations all come from the shots of the Z-basis circuit, each four-qubit term from its own circuit."""
+
+    _cache: dict = {}
+
+    def __init__(self, circuit: cirq.Circuit, qubits, hamiltonian, noise_wrapper: Callable, to_z_basis):
+        from .. import engine
+        self.qubits = list(qubits)
+        n = self.n = len(self.qubits)
+        builder, bq, _meas, lifted, key = engine.lower_circuit(circuit, self.qubits, lift_numeric_rotations=True)
+        self.lifted = np.array(lifted, np.float64)
+        eye = np.eye(2, dtype=complex)
+        table = [eye, eye] + [cirq.unitary(to_z_basis[p](self.qubits[0], 1)) for p in ("X", "Y")] + [eye] * 12
+        code = {"Z": 1, "X": 2, "Y": 3}
+        for q in range(n):
+            slot = builder.add_variant([q], table)
+            for nop in noise_wrapper(self.qubits[q]):
+                builder.add_kraus([q], cirq.channel(nop), if_slot=slot)
+        self.prog = engine.CircuitProgram(builder, qubits=bq)
+        self.key = key
+        by_size: dict = {}
+        for term, coefficient in hamiltonian.terms.items():
+            by_size.setdefault(len(term), []).append(term)
+        # measurement circuits: variant rows + which (mask, weight) pairs are read from each
+        bit = lambda q: 1 << (n - 1 - q)
+        rows, reads = [], []
+        z_row = np.zeros(n, np.uint8)
+        for term in by_size.get(1, []):
+            for q, p in term:
+                z_row[q] = code[p]
+        z_reads = []
+        for i in range(n):
+            if ((i, "Z"),) in hamiltonian.terms:
+                z_reads.append((bit(i), complex(hamiltonian.terms[((i, "Z"),)]).real))
+        for i, j in itertools.combinations(range(n), 2):
+            t = ((i, "Z"), (j, "Z"))
+            if t in hamiltonian.terms:
+                z_reads.append((bit(i) | bit(j), complex(hamiltonian.terms[t]).real))
+        rows.append(z_row)
+        reads.append(z_reads)
+        for term in by_size.get(4, []):
+            row = np.zeros(n, np.uint8)
+            for q, p in term:
+                row[q] = code[p]
+            rows.append(row)
+            reads.append([((1 << n) - 1, complex(hamiltonian.terms[term]).real)])          # parity of ALL qubits (reference :160-166)
+        self.variant_rows = np.stack(rows)
+        self.identity = complex(hamiltonian.terms.get((), 0.0)).real
+        self.masks = sorted({m for rd in reads for m, _ in rd})
+        col = {m: i for i, m in enumerate(self.masks)}
+        self.weights = np.zeros((len(rows), len(self.masks)))
+        for m_i, rd in enumerate(reads):
+            for mask, wgt in rd:
+                self.weights[m_i, col[mask]] += wgt
+
+    @classmethod
+    def for_circuit(cls, circuit, qubits, hamiltonian, noise_wrapper, to_z_basis) -> "SampledEnergyProgram":
+        """Plan cache: resolved circuits that differ only in their rotation angles share one program (the COBYLA loop of
+        processor_classic.py:77-92 re-resolves the same circuit on every call)."""
+        from .. import engine
+        _b, _q, _m, lifted, key = engine.lower_circuit(circuit, list(qubits), lift_numeric_rotations=True)
+        noise_key = tuple(str(op) for q in qubits for op in noise_wrapper(q))
+        full = (key, noise_key, id(hamiltonian))
+        hit = cls._cache.get(full)
+        if hit is None:
+            hit = cls(circuit, qubits, hamiltonian, noise_wrapper, to_z_basis)
+            hit._hamiltonian = hamiltonian          # keeps id() stable for the cache key
+            if len(cls._cache) > 32:
+                cls._cache.clear()
+            cls._cache[full] = hit
+        hit.lifted = np.array(lifted, np.float64)
+        return hit
+
+    def energies(self, params: "np.ndarray | None", meas_reps: int, seed: int) -> np.ndarray:
+        """Sampled energies of ``params[B, P]`` (columns = ``self.prog.param_names``; None: the circuit's own numeric angles).
+        Row b, measurement circuit m draws its shots from Philox stream row ``b * M + m`` of ``seed``."""
+        import torch
+        from .. import engine
+        M = len(self.variant_rows)
+        if params is None:
+            params = self.lifted[None, :] if self.prog.n_params else None
+        B = 1 if params is None else len(params)
+        dev = torch.device("cuda", torch.cuda.current_device())
+        p_t = None if params is None else torch.as_tensor(np.repeat(np.asarray(params, np.float64), M, axis=0), device=dev)
+        v_t = torch.as_tensor(np.tile(self.variant_rows, (B, 1)), device=dev)
+        probs = self.prog.probabilities(p_t, v_t, batch=B * M, renormalise=True, as_tensor=True)
+        expect = engine.shot_expectations(probs, meas_reps, self.masks, seed)                    # [B * M, n_masks] on the device
+        w = torch.as_tensor(np.tile(self.weights, (B, 1)), device=dev)
+        return (expect * w).sum(dim=1).reshape(B, M).sum(dim=1).cpu().numpy() + self.identity
 
 
 def sample_circuits(circuits: List[cirq.Circuit], repetitions: int) -> List[np.ndarray]:

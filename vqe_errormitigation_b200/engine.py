@@ -453,6 +453,31 @@ def qp_sample_variants(qps, batch: int, seed: int, first_sample: int = 0):
     return sampler.draw(batch, seed, first_sample)
 
 
+def shot_expectations(probs, shots, masks: Sequence[int], seed: int, first_row: int = 0):
+    """Draw ``shots`` outcomes per row of ``probs[rows, 2^n]`` (CUDA tensor, e.g. ``CircuitProgram.probabilities(...,
+    as_tensor=True)``) on the device and return ``2 P(even parity on mask) - 1`` for every mask, all masks from the same
+    shots: CUDA float64 tensor [rows, len(masks)] (``dmx_shot_expectations``; the sampled half of cirq's ``run()`` plus the
+    parity read-out of ``measure_observable``, reference model_hydrogen.py:103-112,132-166).  ``shots``: one int, or one
+    count per row (array / tensor)."""
+    torch = _require_cuda()
+    lib = _lib.load()
+    probs = probs.contiguous()
+    rows, dim = probs.shape
+    m = np.ascontiguousarray(masks, np.uint32)
+    out = torch.empty((rows, len(m)), dtype=torch.float64, device=probs.device)
+    stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    per_row = None
+    if not isinstance(shots, (int, np.integer)):
+        per_row = torch.as_tensor(shots, device=probs.device).to(torch.int64).contiguous()
+        if per_row.numel() != rows:
+            raise ValueError(f"shots has {per_row.numel()} entries for {rows} rows")
+        shots = 0
+    check(lib.dmx_shot_expectations(C.c_void_p(probs.data_ptr()), rows, dim, int(shots), CircuitProgram._ptr(per_row),
+                                    m.ctypes.data_as(C.POINTER(C.c_uint32)), len(m),
+                                    C.c_uint64(int(seed)), C.c_uint64(int(first_row)), C.c_void_p(out.data_ptr()), stream))
+    return out
+
+
 def measure_fp64_peak() -> float:
     _require_cuda()
     lib = _lib.load()

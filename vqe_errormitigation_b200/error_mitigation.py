@@ -541,12 +541,18 @@ class IErrorMitigationManager:
         prog = self._variant_program(with_hamiltonian=False)
         if not prog.measurements:
             raise ValueError("Circuit has no measurements to sample.")
-        probs = prog.probabilities(None, rows, renormalise=True)
         key_pos = [m for m in prog.measurements if m[0] == "M"]
         if not key_pos:
             raise KeyError("M")
         n = prog.n_qubits
         measured = key_pos[0][1]
+        if len(measured) == 1:
+            # histogram('M')[0]: one measured qubit -> 2 p0 - 1 is the parity expectation of that qubit (reference :391-396);
+            # shots drawn on the device
+            probs = prog.probabilities(None, rows, renormalise=True, as_tensor=True)
+            seed = int(np.random.randint(0, 2 ** 31 - 1))
+            return engine.shot_expectations(probs, reps, [1 << (n - 1 - measured[0])], seed).cpu().numpy()[:, 0]
+        probs = prog.probabilities(None, rows, renormalise=True)
         states = np.arange(probs.shape[1])
         all_zero = np.ones(probs.shape[1], dtype=bool)
         for pos in measured:
@@ -569,8 +575,6 @@ class IErrorMitigationManager:
         by_size: Dict[int, list] = {}
         for term in hamiltonian.terms:
             by_size.setdefault(len(term), []).append(term)
-        rng = np.random.default_rng(np.random.randint(0, 2 ** 31 - 1))
-
         def tail(term_list):
             ops = []
             for term in term_list:
@@ -579,29 +583,28 @@ class IErrorMitigationManager:
                     ops.extend(noise(qubits[q]))
             return tuple(ops)
 
-        def parities(tail_ops):
-            prog = self._variant_program(tail_ops=tail_ops, with_hamiltonian=False)
-            probs = prog.probabilities(None, rows, renormalise=True)
-            counts = rng.multinomial(reps, probs / probs.sum(axis=1, keepdims=True))
-            return counts
+        seed = int(np.random.randint(0, 2 ** 31 - 1))
+        reps_t = np.asarray(reps, np.int64)
+        bitmask = lambda qs: sum(1 << (n - 1 - q) for q in qs)
+        stream_row = [0]
 
-        states = np.arange(1 << n)
-        bit = lambda q: (states >> (n - 1 - q)) & 1
-        z_counts = parities(tail(by_size.get(1, [])))
+        def expectations(tail_ops, masks):
+            """|diag rho| of every variant row with this measurement tail, shots and parities on the device
+            (dmx_shot_expectations); only [rows, len(masks)] doubles come back."""
+            prog = self._variant_program(tail_ops=tail_ops, with_hamiltonian=False)
+            probs = prog.probabilities(None, rows, renormalise=True, as_tensor=True)
+            out = engine.shot_expectations(probs, reps_t, masks, seed, first_row=stream_row[0]).cpu().numpy()
+            stream_row[0] += rows.shape[0]
+            return out
+
         total = np.full(rows.shape[0], 0.0)
         expectation = {(): np.ones(rows.shape[0])}
-        for i in range(n):
-            even = bit(i) == 0
-            expectation[((i, "Z"),)] = 2.0 * z_counts[:, even].sum(axis=1) / reps - 1.0
-        for i, j in it.combinations(range(n), 2):
-            even = (bit(i) ^ bit(j)) == 0
-            expectation[((i, "Z"), (j, "Z"))] = 2.0 * z_counts[:, even].sum(axis=1) / reps - 1.0
+        z_terms = [((i, "Z"),) for i in range(n)] + [((i, "Z"), (j, "Z")) for i, j in it.combinations(range(n), 2)]
+        z_exp = expectations(tail(by_size.get(1, [])), [bitmask([q for q, _ in t]) for t in z_terms])
+        for k, t in enumerate(z_terms):
+            expectation[t] = z_exp[:, k]
         for term in by_size.get(4, []):
-            c = parities(tail([term]))
-            par = np.zeros(1 << n, dtype=np.int64)
-            for q in range(n):
-                par ^= bit(q)
-            expectation[term] = 2.0 * c[:, par == 0].sum(axis=1) / reps - 1.0
+            expectation[term] = expectations(tail([term]), [bitmask(range(n))])[:, 0]
         for term, coefficient in hamiltonian.terms.items():
             if term in expectation:
                 total = total + complex(coefficient).real * expectation[term]
