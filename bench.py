@@ -147,6 +147,38 @@ def workload_h2_qem():
                 parity_rows=[0, 1, 2, 3, B - 1])
 
 
+def workload_swap7_qem():
+    """The reference's only > 4-qubit workload: QP error mitigation of the 7-qubit SWAP test (QP_QEM_lib.py:388-419 swap_circuit
+    with cirq 0.8.2's Fredkin decomposition; stored run src/classic_minimisation/SWAP_Similarity_P0.0001_R100_C10000, driver
+    visual_testing.py:492-524): asymmetric Pauli noise p = 1e-4, 10 000 sampled identifiers per estimate, observable Z on the
+    last qubit (error_mitigation.py:381).  Whole state (4^7 Pauli coefficients = 128 KiB) resident in one CTA's shared memory."""
+    from vqe_errormitigation_b200 import cirq_compat as cirq
+    from vqe_errormitigation_b200 import experiments as E
+    from vqe_errormitigation_b200.error_mitigation import IErrorMitigationManager
+    from vqe_errormitigation_b200.qp_qem_lib import swap_circuit
+    noise = E.asymmetric_pauli_noise_model(1e-4)
+    circuit = swap_circuit(3, cirq.LineQubit.range(7), True)
+    mgr = IErrorMitigationManager(clean_circuit=circuit, noise_model=noise, hamiltonian_objective=None)
+    builder, qubits, measurements = mgr.variant_builder()
+    B = 10_000
+    qps = mgr.quasi_probabilities()
+
+    def make_inputs(rank: int, seed_offset: int = 0):
+        state = np.random.get_state()
+        np.random.seed(20260108 + rank)
+        rows = np.zeros((B, len(qps)), np.uint8)
+        for s, qp in enumerate(qps):
+            rows[:, s] = np.random.choice(len(qp), size=B, p=np.abs(qp) / np.sum(np.abs(qp)))
+        np.random.set_state(state)
+        return None, rows
+
+    return dict(key="swap7_qem",
+                name="7-qubit SWAP-test QP error mitigation (reference QP_QEM_lib.swap_circuit, asymmetric Pauli noise p=1e-4): "
+                     "10000 sampled identifiers per estimate, whole 4^7 state in one CTA's shared memory",
+                builder=builder, qubits=qubits, measurements=measurements, batch=B, make_inputs=make_inputs,
+                terms=mgr.observable_terms(), manager=mgr, qp_bytes=int(sum(len(q) for q in qps) * 8), parity_rows=[0, 1, 2, B - 1])
+
+
 def _hea_builder(n: int, depth: int, p: float = 1e-3):
     from vqe_errormitigation_b200 import cirq_compat as cirq, engine
     from vqe_errormitigation_b200.error_mitigation import TwoQubitDepolarizingChannel
@@ -313,9 +345,10 @@ def workload_lih12():
 
 
 WORKLOADS = {"h2_sweep": workload_h2_sweep, "h2_qem": workload_h2_qem, "hea10": workload_hea10, "lih12": workload_lih12,
-             "h2_bonds": workload_h2_bonds}
-ALSO = ("h2_qem", "hea10", "lih12", "h2_bonds")       # riders of the default run (BASELINE configs[2..4] + the A x B batch axes)
-ALSO_STEPS = {"h2_qem": 20, "hea10": 3, "lih12": 2, "h2_bonds": 20}
+             "h2_bonds": workload_h2_bonds, "swap7_qem": workload_swap7_qem}
+# riders of the default run: BASELINE configs[2..4], the A x B batch axes, the reference's 7-qubit workload
+ALSO = ("h2_qem", "hea10", "lih12", "h2_bonds", "swap7_qem")
+ALSO_STEPS = {"h2_qem": 20, "hea10": 3, "lih12": 2, "h2_bonds": 20, "swap7_qem": 5}
 
 
 # ---------------------------------------------------------------------------------------------------------
@@ -681,9 +714,9 @@ def run_workload(wl, ctx, steps: int, warmup: int, with_cpu_baseline: bool, with
         lo, hi = parallel.shard_bounds(B * world, rank, world)
 
         def est_step(seed):
-            variants, signs = sampler.draw(hi - lo, seed, first_sample=lo)
-            values = prog.energies(None, variants, batch=hi - lo)
-            return parallel.sharded_sums(values, signs)       # device tensor [3]; all-reduce on this stream when N > 1
+            # draw + evaluate (distinct rows only where the circuit is expensive) + reduce; device tensor [3], all-reduced on
+            # this stream when N > 1
+            return mgr.sampled_sums(sampler, lo, hi, seed)
         for i in range(3):
             est_step(100 + i)
         torch.cuda.synchronize()
@@ -703,7 +736,8 @@ def run_workload(wl, ctx, steps: int, warmup: int, with_cpu_baseline: bool, with
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         s0, _s1, n = (float(x) for x in sums.cpu())
         estimator = {"value": world * B * steps / (float(ms.item()) * 1e-3), "unit": "variants/s", "ms_per_estimate": float(ms.item()) / steps,
-                     "contains": "Philox draw + variant evaluation + dmx_qp_reduce" + (" + NCCL all-reduce of 3 doubles" if world > 1 else ""),
+                     "contains": "Philox draw + " + ("device dedup (torch.unique) + " if info["path"] != 1 else "") + "variant evaluation + reduction"
+                                 + (" + NCCL all-reduce of 3 doubles" if world > 1 else ""),
                      "timing": "CUDA events on the launch stream, max over ranks", "variants_per_estimate": int(B * world),
                      "estimate": [mgr.total_cost() * s0 / n, int(n)]}
 

@@ -646,13 +646,43 @@ class IErrorMitigationManager:
         results = np.repeat(weighted, counts)
         return results, float(np.sum(weighted * counts) / np.sum(counts))
 
+    def sampled_sums(self, sampler, lo: int, hi: int, seed: int):
+        """Device tensor [3] = (sum sign*value, sum value^2, N) over the samples [lo, hi) of Philox stream ``seed`` on this
+        rank, all-reduced over the ranks of an initialised process group (NCCL: on the current stream, no host copy).
+        Circuits that do not run on the warp-per-circuit frame kernels (the 7-qubit SWAP test: 128 KiB of state and ~80
+        shared-memory sweeps per row) are deduplicated ON THE DEVICE first - the reference's identifier -> count dictionary
+        (:492-497): at p = 1e-4 about 300 of 10 000 sampled rows are distinct.  torch.unique is plumbing (a device sort of
+        the identifier rows); the evaluation of the distinct rows is the engine's launch."""
+        import torch
+        from . import parallel
+        prog = self._variant_program()
+        variants, signs = sampler.draw(hi - lo, seed, first_sample=lo)
+        if prog.info["path"] != 1 and hi > lo:
+            uniq, inverse, counts = torch.unique(variants, dim=0, return_inverse=True, return_counts=True)
+            signs_u = torch.zeros(uniq.shape[0], dtype=signs.dtype, device=signs.device).scatter_(0, inverse, signs)
+            values = prog.energies(None, uniq, batch=uniq.shape[0])
+            cf = counts.to(signs.dtype)
+            local = torch.stack([torch.sum(cf * signs_u * values), torch.sum(cf * (signs_u * values) ** 2), torch.sum(cf)])
+            d = parallel._dist()
+            if d is not None and d.get_world_size() > 1:
+                if d.get_backend() != "nccl":
+                    host = local.cpu()
+                    d.all_reduce(host)
+                    local = host.to(local.device)
+                else:
+                    d.all_reduce(local)
+            return local
+        values = prog.energies(None, variants, batch=hi - lo)
+        return parallel.sharded_sums(values, signs)
+
     def get_mu_effective_sampled(self, count: int, seed: int = 0) -> Tuple[float, float, int]:
         """Mitigated expectation from ``count`` variants drawn ON THE DEVICE (density representation): the sampler
         (engine.qp_sample_variants), the batched variant evaluation and the reduction never leave the GPU, so the only
         host traffic is the QP tables in and three doubles out.  Each rank of an initialised torch.distributed job draws
         its own slice [first, first + share) of one Philox stream; the estimator is all-reduced (24 bytes).
-        Returns (mean, standard error, N).  Same estimator as get_mu_effective(True, True) (reference :401-452)
-        without the dedup dictionary — duplicates are simply evaluated again."""
+        Returns (mean, standard error, N).  Same estimator as get_mu_effective(True, True) (reference :401-452); on the
+        frame kernels duplicates are simply evaluated again (cheaper than sorting them), larger circuits are deduplicated
+        on the device (:meth:`sampled_sums`)."""
         from . import engine, parallel
         rank, world_size = parallel.world()
         lo, hi = parallel.shard_bounds(int(count), rank, world_size)
@@ -660,10 +690,9 @@ class IErrorMitigationManager:
             qps = self._qp_matrix()
             self._sampler_cache = (engine.QpSampler(qps), float(np.prod([np.sum(np.abs(qp)) for qp in qps])))
         sampler, scale = self._sampler_cache
-        prog = self._variant_program()
-        variants, signs = sampler.draw(hi - lo, seed, first_sample=lo)
-        values = prog.energies(None, variants, batch=hi - lo)
-        mean, var, n = parallel.sharded_mean(values, signs)      # the circuit's total cost is one scalar: applied once here
+        s0, s1, n = (float(x) for x in self.sampled_sums(sampler, lo, hi, seed).cpu())
+        mean = s0 / n if n else float("nan")
+        var = s1 / n - mean * mean if n else float("nan")
         mean, var = scale * mean, scale * scale * var
         return mean, float(np.sqrt(max(var, 0.0) / n)) if n else float("nan"), int(n)
 
