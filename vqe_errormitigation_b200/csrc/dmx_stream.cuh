@@ -517,7 +517,9 @@ __global__ void __launch_bounds__(THREADS, THREADS == 256 ? 1 : 4) dmx_stream3_k
     const unsigned tile_id = blockIdx.x % tiles_per_circuit;
     const double* const st_in = a.src + (circuit << (2 * a.n));
     double* const st = a.dst + (circuit << (2 * a.n));
-
+    // (Measured and rejected, profiles/r2_stream3_experiments.txt: a per-thread index on the permutation scale tables turns
+    // ptxas' LDCU.64 + 2 IMAD.MOV per scale into one vector LDC.64, but the kernel then needs 255 registers and HEA-10 drops
+    // from 8 235 to 7 335 circuits/s; scale tables in shared memory - LDS.128 - lose 6 %.)
     // the tile of the load side is contiguous for LOAD_BULK / LOAD_DIRECT: tile_id supplies the upper index bits
     const double* const tile_src = st_in + map_runs(tile_id, a.oruns_l, a.n_oruns_l);
     const unsigned mbar = smem_u32(reinterpret_cast<char*>(dmx_stream_smem) + a.mbar_off);

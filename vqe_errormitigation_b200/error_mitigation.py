@@ -658,7 +658,7 @@ class IErrorMitigationManager:
         prog = self._variant_program()
         variants, signs = sampler.draw(hi - lo, seed, first_sample=lo)
         if prog.info["path"] != 1 and hi > lo:
-            uniq, inverse, counts = torch.unique(variants, dim=0, return_inverse=True, return_counts=True)
+            uniq, inverse, counts = _unique_rows(variants)
             signs_u = torch.zeros(uniq.shape[0], dtype=signs.dtype, device=signs.device).scatter_(0, inverse, signs)
             values = prog.energies(None, uniq, batch=uniq.shape[0])
             cf = counts.to(signs.dtype)
@@ -698,6 +698,29 @@ class IErrorMitigationManager:
 
     def __str__(self):
         return str(self._dict_identifiers)
+
+
+_ROW_HASH = None
+
+
+def _unique_rows(variants):
+    """(distinct rows, inverse, counts) of a uint8 CUDA tensor [B, S].  torch.unique(dim=0) sorts the rows lexicographically
+    (milliseconds for 10 000 x 77); a 64-bit multiplicative hash of every row and a 1-D unique of the keys is ~20x faster.
+    The grouping is verified against the rows themselves (one boolean comes back) and falls back to the exact sort on a
+    collision."""
+    import torch
+    global _ROW_HASH
+    B, S = variants.shape
+    if _ROW_HASH is None or _ROW_HASH.shape[0] < S or _ROW_HASH.device != variants.device:
+        g = torch.Generator().manual_seed(0x5eed)
+        _ROW_HASH = (torch.randint(-(2 ** 62), 2 ** 62, (max(S, 256),), generator=g, dtype=torch.int64) | 1).to(variants.device)
+    keys = (variants.to(torch.int64) * _ROW_HASH[:S]).sum(dim=1)
+    _uk, inverse, counts = torch.unique(keys, return_inverse=True, return_counts=True)
+    first = torch.zeros(counts.shape[0], dtype=torch.int64, device=variants.device).scatter_(0, inverse, torch.arange(B, device=variants.device))
+    uniq = variants[first]
+    if not bool((uniq[inverse] == variants).all()):
+        return torch.unique(variants, dim=0, return_inverse=True, return_counts=True)
+    return uniq, inverse, counts
 
 
 def reconstruct_from_basis(quasi_probabilities: List[float], basis_set: List[np.ndarray]) -> np.ndarray:
