@@ -540,7 +540,7 @@ def parity_check(wl, prog, params_h, variants_h, rank: int, groups_h=None):
 # one workload on this rank (+ max over ranks)
 # ---------------------------------------------------------------------------------------------------------
 
-def run_workload(wl, ctx, steps: int, warmup: int, with_cpu_baseline: bool, with_e2e: bool):
+def run_workload(wl, ctx, steps: int, warmup: int, with_cpu_baseline: bool, with_e2e: bool, cpu_budget_s: float = 12.0):
     import torch
     import torch.distributed as dist
     from vqe_errormitigation_b200 import engine
@@ -559,12 +559,12 @@ def run_workload(wl, ctx, steps: int, warmup: int, with_cpu_baseline: bool, with
         else:
             probe = min(32, B, max(cores, 1))
             _, dt1 = cpu_port_rate(wl, probe, threads=cores)
-            sample = int(max(probe, min(B, probe / dt1 * 12.0)))
+            sample = int(max(probe, min(B, probe / dt1 * cpu_budget_s)))
         rate, dt = cpu_port_rate(wl, sample, threads=cores)
         cpu_baseline = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
                         "sample": f"{cpu_sample_note(wl, sample)}, {dt:.1f} s, C restatement of cirq's per-op "
                                   f"density-matrix algorithm (oracle/dm_oracle.c) on {cores} threads"}
-        if not wl.get("cpu_ops_fraction"):
+        if not wl.get("cpu_ops_fraction") and cpu_budget_s >= 10.0:
             # the reference's own shapes: one process (CPU.get_custom_optimized_state) and its Pool(6)
             # (MAX_MULTI_PROCESSING_COUNT, src/error_mitigation.py:14), ~2 s of work each
             by = {str(cores): rate}
@@ -912,7 +912,8 @@ def main():
         for key in ALSO:
             t0 = time.perf_counter()
             try:
-                res = run_workload(WORKLOADS[key](), ctx, ALSO_STEPS[key], 3, with_cpu_baseline=False, with_e2e=not args.no_e2e)
+                res = run_workload(WORKLOADS[key](), ctx, ALSO_STEPS[key], 3, with_cpu_baseline=not args.no_cpu_baseline,
+                                   with_e2e=not args.no_e2e, cpu_budget_s=2.5)
             except Exception as exc:  # noqa: BLE001 - a rider must not take the headline line down
                 if world > 1:
                     raise                  # ranks must stay in step through the collectives

@@ -693,6 +693,9 @@ __global__ void __launch_bounds__(256, DMX_F32_MINB) dmx_frame32_kernel(const Fr
         const long long b0 = grp * CPB;
         double2 csr[CPB];
         if (CSMODE == 1) {
+            // (Measured and rejected, profiles/r2_frame32s_ab.txt: computing the CTA's 64 (cos, sin) pairs once by 64 fully
+            // populated threads ahead of the staging barrier - 18.6 -> 26.7 us per 65 536 circuits: the other six warps wait
+            // at the barrier behind a DRAM round trip plus a sincos, and the kernel spills at 64 registers.)
             double sv = 0.0, cv = 1.0;
             if (lane < CPB && b0 + lane < a.batch) {
                 const RotInfo ri = a.classes[0];
