@@ -612,6 +612,7 @@ __global__ void __launch_bounds__(256) dmx_frame_kernel(const FrameArgs a) {
 struct Frame32Args {
     int nseg, n_params, n_slots, n_classes;
     int any_const;                // some segment has cs_sel < 0
+    int stage_io;                 // parameters / energies are mapped HOST memory: move them as one block per CTA (see the kernel)
     long long batch;
     const double2* w;             // [nseg][32] (w0, w1)
     const unsigned char* partner; // [nseg][32] partner lane | 0x80 (rotation moves this coefficient)
@@ -677,6 +678,18 @@ __global__ void __launch_bounds__(256, DMX_F32_MINB) dmx_frame32_kernel(const Fr
         spart[i] = pbyte;
     }
     for (int i = threadIdx.x; i < a.nseg; i += 256) ssel[i] = a.cs_sel[i];
+    // Plain single-class sweeps on mapped host buffers (STAGE_IO): the CTA's 8 * CPB circuits of the first round are consecutive rows, so their
+    // parameters come in - and their energies go out - as one contiguous 8 * CPB * 8-byte block per CTA through shared memory
+    // (the `cs` area, unused in this mode) instead of one 64-byte request per warp.  It matters when the buffers are mapped
+    // host memory (dmx_energy_batch_host zero-copy): eight GPUs issuing 64-byte PCIe transactions saturate the host's
+    // transaction rate at ~1.1e10 circuits/s (profiles/r2_e2e_scaling_n8.txt).  Device-resident buffers keep the per-warp
+    // accesses: the extra block barrier costs 5 % there (18.6 -> 19.5 us per 65 536 circuits).
+    const bool STAGE_IO = CSMODE == 1 && !VAR && a.stage_io;
+    double* const io = reinterpret_cast<double*>(smem_base);                 // [8 * CPB] angles in, energies out
+    if (STAGE_IO && threadIdx.x < 8 * CPB) {
+        const long long b = (long long)blockIdx.x * 8 * CPB + threadIdx.x;
+        io[threadIdx.x] = b < a.batch ? a.params[b * a.n_params + a.classes[0].param] : 0.0;
+    }
     __syncthreads();
     const long long ngroups = (a.batch + CPB - 1) / CPB;
     const long long gwarp = (long long)blockIdx.x * 8 + warp, nwarps = (long long)gridDim.x * 8;
@@ -699,7 +712,8 @@ __global__ void __launch_bounds__(256, DMX_F32_MINB) dmx_frame32_kernel(const Fr
             double sv = 0.0, cv = 1.0;
             if (lane < CPB && b0 + lane < a.batch) {
                 const RotInfo ri = a.classes[0];
-                sincos(ri.scale * a.params[(b0 + lane) * a.n_params + ri.param] + ri.offset, &sv, &cv);
+                const double x = (STAGE_IO && it == 0) ? io[warp * CPB + lane] : a.params[(b0 + lane) * a.n_params + ri.param];
+                sincos(ri.scale * x + ri.offset, &sv, &cv);
             }
 #pragma unroll
             for (int c = 0; c < CPB; ++c) csr[c] = make_double2(__shfl_sync(0xffffffffu, cv, c), __shfl_sync(0xffffffffu, sv, c));
@@ -861,8 +875,17 @@ __global__ void __launch_bounds__(256, DMX_F32_MINB) dmx_frame32_kernel(const Fr
             for (; off > 0; off >>= 1) e[0] += __shfl_xor_sync(0xffffffffu, e[0], off);
             constexpr int LPC = 32 / CPB;           // lanes per circuit after the halving steps
             const int c = lane / LPC;
-            if ((lane & (LPC - 1)) == 0 && b0 + c < a.batch && !(VAR && nact[c] < 0)) a.out[b0 + c] = e[0];
+            if (STAGE_IO && it == 0) {
+                if ((lane & (LPC - 1)) == 0) io[warp * CPB + c] = e[0];       // every lane of the warp has read its angle by now
+            } else if ((lane & (LPC - 1)) == 0 && b0 + c < a.batch && !(VAR && nact[c] < 0)) {
+                a.out[b0 + c] = e[0];
+            }
         }
+    }
+    if (STAGE_IO) {
+        __syncthreads();
+        const long long b = (long long)blockIdx.x * 8 * CPB + threadIdx.x;
+        if (threadIdx.x < 8 * CPB && b < a.batch) a.out[b] = io[threadIdx.x];
     }
 }
 
@@ -1984,7 +2007,7 @@ static int launch_frame32(const Frame32Args& a, int sm_count, cudaStream_t st) {
 
 
 static int run_segment(Plan& p, DevPlan* d, long long batch, const double* params, const uint8_t* variants, double* out, cudaStream_t st,
-                       const int* group = nullptr) {
+                       const int* group = nullptr, bool host_mapped = false) {
     FrameArgs a{};
     a.nseg = p.nseg; a.n_params = p.n_params; a.n_slots = p.n_slots; a.n_classes = (int)p.f_classes.size(); a.n_eterms = d->n_eterms;
     a.batch = batch; a.w = d->f_w; a.segs = d->f_segs; a.classes = d->f_classes; a.init = d->f_init; a.eweight = d->f_eweight;
@@ -2012,6 +2035,7 @@ static int run_segment(Plan& p, DevPlan* d, long long batch, const double* param
         g.out = out; g.worklist = a.worklist; g.work_count = a.work_count; g.group = group;
         g.any_const = 0;
         for (int k = 0; k < p.nseg; ++k) g.any_const |= p.fsegs[k].cs_sel < 0;
+        g.stage_io = host_mapped ? 1 : 0;
         // Measured on B200 (profiles/r2_frame32s_ab.txt): 14 warps per SM leave the issue slots idle at the BASELINE batch
         // (65 536 circuits: 20.4 us against 18.6 us for the 8-circuit kernel with its 32 warps per SM), but from ~5e5
         // circuits per launch the leaner instruction stream wins (2^20: 6.45e9 against 5.99e9 circuits/s, 2^22: 6.87e9
@@ -2194,7 +2218,7 @@ static int check_exec(dmx_plan* plan, int64_t batch, const double* d_params, con
 }
 
 static int energy_impl(dmx_plan* plan, int64_t batch, const double* d_params, const uint8_t* d_variants, double* d_energy,
-                       void* d_workspace, size_t workspace_bytes, cudaStream_t st, const int* d_group = nullptr) {
+                       void* d_workspace, size_t workspace_bytes, cudaStream_t st, const int* d_group = nullptr, bool host_mapped = false) {
     NvtxRange nvtx("dmx:energy_batch");
     Plan& p = plan->p;
     if (p.term_idx.empty()) return fail(DMX_ERR_STATE, "no Hamiltonian set");
@@ -2202,7 +2226,7 @@ static int energy_impl(dmx_plan* plan, int64_t batch, const double* d_params, co
     int rc = ensure_device(p, &d);
     if (rc) return rc;
     if (batch == 0) return DMX_OK;
-    if (p.path == 1) return run_segment(p, d, batch, d_params, d_variants, d_energy, st, d_group);
+    if (p.path == 1) return run_segment(p, d, batch, d_params, d_variants, d_energy, st, d_group, host_mapped);
     if (p.path == 0) return run_tile_single(p, d, batch, d_params, d_variants, d_energy, OUT_ENERGY, nullptr, nullptr, st, d_group);
     const size_t sb = (size_t)p.info.state_bytes;
     const long long cap = (long long)(workspace_bytes / (size_t)p.info.workspace_bytes_per_state);
@@ -2484,7 +2508,7 @@ static int energy_batch_host_impl(dmx_plan* plan, int64_t batch, const double* h
         const double* const p_dev = h_params ? (const double*)mapped_alias(h_params) : nullptr;
         const int* const g_dev = h_group ? (const int*)mapped_alias(h_group) : nullptr;
         if (e_dev && (p_dev || !h_params) && (g_dev || !h_group)) {
-            rc = energy_impl(plan, batch, p_dev, nullptr, e_dev, nullptr, 0, d->stream, g_dev);
+            rc = energy_impl(plan, batch, p_dev, nullptr, e_dev, nullptr, 0, d->stream, g_dev, true);
             if (!wait) return rc;            // dmx_energy_batch_host_async: the caller collects with dmx_plan_host_sync
             const cudaError_t e = cudaStreamSynchronize(d->stream);
             if (rc) return rc;
