@@ -325,3 +325,80 @@ def test_remaining_experiment_loops_on_the_oracle_backend(monkeypatch, capsys):
     assert [len(v) for v in more[0]] == [2, 2] and more[0][0][0] == first[0][0][0]          # resumed run extends the stored lists
     assert abs(more[3][1] - h2_golden()["molecules"]["1.0"]["fci_energy"]) < 1e-12
     capsys.readouterr()
+
+
+def test_lockstep_nelder_mead_vectorised_over_chains():
+    """Every round of the batched Nelder-Mead is one objective call over all chains (no thread per chain): thousands of
+    chains cost a few hundred calls, each chain converges to the minimiser scipy finds, and the grouped form hands the
+    objective the chain ids."""
+    from scipy.optimize import minimize
+    from vqe_errormitigation_b200.processors.processor_classic import lockstep_nelder_mead, lockstep_nelder_mead_grouped
+    calls = [0]
+
+    def f(xs):
+        calls[0] += 1
+        return ((xs - np.array([1.5, -0.3])) ** 2).sum(axis=1) + 0.05 * np.sin(xs[:, 0]) ** 2
+
+    rng = np.random.default_rng(0)
+    x0 = rng.normal(scale=0.3, size=(3000, 2))
+    fun, x, n = lockstep_nelder_mead(f, x0, max_evals=400, tol=1e-10)
+    ref = minimize(lambda v: f(v[None, :])[0], np.zeros(2), method="Nelder-Mead", options={"xatol": 1e-10, "fatol": 1e-10})
+    assert calls[0] < 1000 and np.max(np.abs(fun - ref.fun)) < 1e-9 and np.max(np.abs(x - ref.x)) < 1e-4
+    assert n.max() <= 400 and n.min() > 20
+    # the evaluation budget is respected (the reference's max_cpu_iter = COBYLA maxiter, processor_classic.py:88-92)
+    fun10, _x, n10 = lockstep_nelder_mead(f, x0[:50], max_evals=10, tol=1e-12)
+    assert n10.max() <= 10 and np.all(fun10 <= f(x0[:50]) + 1e-15)
+    # one-dimensional chains with a per-chain target (the objective receives the chain ids)
+    target = np.linspace(-1, 1, 9)
+    fun1, x1, _ = lockstep_nelder_mead_grouped(lambda xs, ids: (xs[:, 0] - target[ids]) ** 2 + ids, np.zeros((9, 1)), 120, tol=1e-13)
+    assert np.max(np.abs(x1[:, 0] - target)) < 1e-6 and np.max(np.abs(fun1 - np.arange(9))) < 1e-12
+
+
+def test_lockstep_minimize_propagates_objective_failure():
+    """A batched objective that raises must not leave the chain threads blocked."""
+    import threading
+    from vqe_errormitigation_b200.processors.processor_classic import lockstep_minimize
+    calls = [0]
+
+    def bad(xs):
+        calls[0] += 1
+        if calls[0] == 3:
+            raise RuntimeError("boom")
+        return (xs ** 2).sum(axis=1)
+
+    before = threading.active_count()
+    with pytest.raises(RuntimeError, match="boom"):
+        lockstep_minimize(bad, np.ones((4, 2)), 50)
+    assert threading.active_count() == before
+
+
+def test_coefficient_groups_lowering():
+    """dmx_plan_set_hamiltonian_groups: host-only checks - shape validation, call order, and the plan still finalises on the
+    frame path with the union of the rows' non-zero pattern."""
+    from workloads import h2_ops, h2_terms
+    from oracle import dm_oracle as O
+    from vqe_errormitigation_b200 import engine
+    from vqe_errormitigation_b200._lib import DmxError
+    b = engine.ProgramBuilder(4)
+    for kind, qs, pl in h2_ops([O.depolarize(1e-3)], [O.two_qubit_depolarize(1e-3)]):
+        if kind == "u":
+            b.add_unitary(qs, pl)
+        elif kind == "k":
+            b.add_kraus(qs, pl)
+        else:
+            b.add_rotation(qs[0], pl[0], pl[1], pl[2], pl[3])
+    terms = h2_terms()
+    rows = np.stack([terms[2], 2.0 * terms[2], np.zeros_like(terms[2])])
+    rows[2, 0] = 1.0
+    prog = engine.CircuitProgram(b, hamiltonian=terms, coefficient_groups=rows)
+    assert prog.n_groups == 3 and prog.info["path"] == 1 and prog.info["n_terms"] == len(terms[2])
+    with pytest.raises(ValueError):
+        engine.CircuitProgram(b, hamiltonian=terms, coefficient_groups=rows[:, :5])
+    lib = engine._lib.load()
+    import ctypes as C
+    h = C.c_void_p()
+    ops = (engine.DmxOp * 1)()
+    assert lib.dmx_plan_create(1, 0, 0, ops, 0, None, 0, C.byref(h)) == 0
+    c = np.ones(1)
+    assert lib.dmx_plan_set_hamiltonian_groups(h, 1, c.ctypes.data_as(C.POINTER(C.c_double))) == -5      # strings first (DMX_ERR_STATE)
+    lib.dmx_plan_destroy(h)

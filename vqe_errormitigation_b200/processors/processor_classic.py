@@ -214,7 +214,7 @@ def lockstep_nelder_mead_grouped(batch_objective: Callable[[np.ndarray, np.ndarr
     C, P = x0s.shape
     simplex = np.repeat(x0s[:, None, :], P + 1, axis=1)                  # [C, P+1, P]
     for i in range(P):
-        step = np.where(x0s[:, i] != 0.0, initial_step * np.abs(x0s[:, i]), initial_step)
+        step = np.maximum(initial_step * np.abs(x0s[:, i]), initial_step)      # never a degenerate (near-zero) edge
         simplex[:, i + 1, i] += step
     fvals = np.asarray(batch_objective(simplex.reshape(-1, P), np.repeat(np.arange(C), P + 1)), dtype=float).reshape(C, P + 1)
     evals = np.full(C, P + 1)
