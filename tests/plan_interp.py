@@ -60,6 +60,11 @@ def parse(dump: str) -> dict:
             sw = {k: int(kv[k]) for k in ("p0", "p1", "p2", "first_mu", "nmu", "lperm", "lcoef", "sperm", "scoef")}
             sw["lmask"] = _nums(kv["lmask"], int)
             sw["smask"] = _nums(kv["smask"], int)
+            sw["wide"] = int(kv.get("wide", 0))
+            if sw["wide"]:
+                sw["lnvar"], sw["snvar"] = int(kv["lnvar"]), int(kv["snvar"])
+                for key in ("ltmask", "stmask", "lvmask", "svmask"):
+                    sw[key] = _nums(kv[key], int)
             plan["sweeps3"].append(sw)
         elif head == "mu":
             plan["mus"].append({k: int(kv[k]) for k in ("kind", "a0", "a1", "a2", "a3")})
@@ -259,10 +264,61 @@ def run_devops(plan, params=None, variants=None) -> np.ndarray:
     return r[np.arange(4 ** n) << pad]
 
 
+def _wide_side(sw, gpos, idx, loc, lp, masks, tmasks, vmasks, nvar, wide_side):
+    """Global index and scale-table row of every element for one side of a (possibly wide) triple sweep: the element held by
+    thread t in register e lives at tile index T(t) ^ X(e); T is the canonical placement of the thread's bits unless the side
+    is wide (then XOR_j t_j * tmask[j]); the scale-table variant is sum_j parity(t & vmask[j]) << j."""
+    tile_bits = sorted(gpos)                       # tile-local code positions (even), ascending
+    k = len(tile_bits)
+    # tile-local index of every global index
+    a = np.zeros_like(idx)
+    for l in tile_bits:
+        a |= ((idx >> gpos[l]) & 3) << l
+    outer = idx.copy()
+    for l in tile_bits:
+        outer &= ~(3 << gpos[l])
+    # thread index: the non-triple tile bits, compacted in ascending order
+    t = np.zeros_like(idx)
+    j = 0
+    for l in tile_bits:
+        if l in lp:
+            continue
+        t |= ((a >> l) & 3) << j
+        j += 2
+    ntb = 2 * (k - 3)
+    if wide_side:
+        base = np.zeros_like(idx)
+        for b in range(ntb):
+            base ^= np.where((t >> b) & 1, int(tmasks[b]), 0)
+    else:
+        base = a.copy()
+        for l in lp:
+            base &= ~(3 << l)
+    x = np.zeros_like(idx)
+    for b in range(6):
+        x ^= np.where((loc >> b) & 1, int(masks[b]), 0)
+    tile_idx = base ^ x
+    g = outer.copy()
+    for l in tile_bits:
+        g |= ((tile_idx >> l) & 3) << gpos[l]
+    var = np.zeros_like(idx)
+    if wide_side:
+        for b in range(nvar):
+            par = np.zeros_like(idx)
+            m = int(vmasks[b])
+            for bit in range(ntb):
+                if (m >> bit) & 1:
+                    par ^= (t >> bit) & 1
+            var |= par << b
+    return g, var
+
+
 def _run_sweep3(plan, sw, mats, gpos, r, idx):
     """One triple sweep as dmx_stream3_kernel executes it: register e = 16*code(A) + 4*code(B) + code(C)."""
     cf = plan["coefs"]
     lp = (sw["p0"], sw["p1"], sw["p2"])
+    if sw.get("wide"):
+        return _run_sweep3_wide(plan, sw, mats, gpos, r, idx)
     g = [gpos[x] for x in lp]
     codes = [(idx >> gg) & 3 for gg in g]
     loc = codes[0] * 16 + codes[1] * 4 + codes[2]
@@ -460,3 +516,29 @@ def run_frame(plan, params=None, variants=None):
         cme = np.where(w1 != 0.0, cm, 1.0)
         r = cme * (w0 * r) + sm * (w1 * other)
     return float(np.dot(plan["f_eweight"], r))
+
+
+def _run_sweep3_wide(plan, sw, mats, gpos, r, idx):
+    """A wide sweep = wide load (gather + variant scale table), the local body on canonical coordinates, wide store."""
+    cf = plan["coefs"]
+    lp = (sw["p0"], sw["p1"], sw["p2"])
+    g = [gpos[x] for x in lp]
+    codes = [(idx >> gg) & 3 for gg in g]
+    loc = codes[0] * 16 + codes[1] * 4 + codes[2]
+    if sw["lperm"]:
+        src, var = _wide_side(sw, gpos, idx, loc, lp, sw["lmask"], sw["ltmask"], sw["lvmask"], sw["lnvar"], sw["wide"] & 1)
+        assert len(np.unique(src)) == len(src)
+        v = cf[sw["lcoef"] + var * 64 + loc] * r[src]
+    else:
+        v = r.copy()
+    body = dict(sw)
+    body.update(lperm=0, sperm=0, wide=0, lmask=[1 << (lp[2] + 0), 1 << (lp[2] + 1), 1 << (lp[1] + 0), 1 << (lp[1] + 1), 1 << (lp[0] + 0), 1 << (lp[0] + 1)])
+    body["smask"] = body["lmask"]
+    v = _run_sweep3(plan, body, mats, gpos, v, idx)
+    if sw["sperm"]:
+        dst, var = _wide_side(sw, gpos, idx, loc, lp, sw["smask"], sw["stmask"], sw["svmask"], sw["snvar"], sw["wide"] & 2)
+        assert len(np.unique(dst)) == len(dst)
+        out = np.zeros_like(v)
+        out[dst] = cf[sw["scoef"] + var * 64 + loc] * v
+        return out
+    return v

@@ -267,3 +267,48 @@ def test_remap_scheduler_invariants_on_wide_registers(n, tile):
     assert all(m["kind"] in (16, 17, 18, 19) for m in plan["mus"])
     n_chain_refs = sum(1 for m in plan["mus"] if m["kind"] == 16 and m["a2"])
     assert n_chain_refs == len(plan["chains"])
+
+
+@pytest.mark.parametrize("seed,tile", [(1, 6), (2, 7), (3, 6), (4, 7), (5, 6)])
+def test_wide_monomial_sweeps_random_clifford_mix(seed, tile):
+    """Plan option "wide": leading / trailing Clifford x Pauli-noise blocks on ANY tile qubits ride on the exchange addressing
+    (thread-base masks) with thread-variant scale tables.  The interpreted program equals the oracle, fewer sweeps are needed
+    than with triple-local monomials, and some sweeps really are wide."""
+    n = 8
+    rng = np.random.default_rng(800 + seed)
+    ops = _clifford_mix_circuit(rng, n, 70)
+    terms = random_hamiltonian(rng, n, 12)
+    local = PI.parse(build_program(ops, n, terms, tile_qubits=tile, wide=0).dump())
+    prog = build_program(ops, n, terms, tile_qubits=tile, wide=1)
+    plan = PI.parse(prog.dump())
+    assert prog.info["path"] == 2 and plan["sweeps3"] and not plan["sweeps"]
+    assert any(sw["wide"] for sw in plan["sweeps3"]) and len(plan["sweeps3"]) < len(local["sweeps3"])
+    for sw in plan["sweeps3"]:
+        assert sw["wide"] in (0, 5, 6, 7) and (not sw["wide"] or (sw["lnvar"] <= 4 and sw["snvar"] <= 4))
+    vals = rng.uniform(-1, 1, size=prog.n_params)
+    rho = O.simulate(n, resolve(ops, prog.param_names, vals))
+    want = O.energy_sparse(rho, O.pauli_terms_to_matrix(n, *terms))
+    assert abs(PI.energy(plan, PI.run_devops(plan, vals)) - want) < TOL
+
+
+def test_wide_monomial_sweeps_hea_layers():
+    """The HEA shape of BASELINE configs[3] at 9 qubits / 2 layers: wide sweeps cut the shared-memory round trips."""
+    n = 9
+    ops = []
+    for layer in range(2):
+        for q in range(n):
+            ops += [("r", (q,), (1, f"y{layer}_{q}", 1.0, 0.0)), ("k", (q,), O.depolarize(1e-3)),
+                    ("r", (q,), (2, f"z{layer}_{q}", 1.0, 0.0)), ("k", (q,), O.depolarize(1e-3))]
+        for q in range(n - 1):
+            ops += [("u", (q, q + 1), O.CNOT), ("k", (q, q + 1), O.two_qubit_depolarize(1e-3))]
+    rng = np.random.default_rng(2)
+    terms = random_hamiltonian(rng, n, 8)
+    counts = {}
+    for wide in (0, 1):
+        prog = build_program(ops, n, terms, tile_qubits=6, wide=wide)
+        plan = PI.parse(prog.dump())
+        counts[wide] = len(plan["sweeps3"])
+        vals = rng.uniform(-1, 1, size=prog.n_params)
+        rho = O.simulate(n, resolve(ops, prog.param_names, vals))
+        assert abs(PI.energy(plan, PI.run_devops(plan, vals)) - O.energy_sparse(rho, O.pauli_terms_to_matrix(n, *terms))) < TOL
+    assert counts[1] < counts[0]

@@ -1385,9 +1385,70 @@ static cudaError_t build_stream_tables(const Plan& p, DevPlan* d) {
                 std::sort(sorted, sorted + 3);
                 for (int j = 0; j < 3; ++j) x.p[j] = sorted[j];
                 x.first_mu = (int)mx.size(); x.n_mu = sw.n_mu;
-                x.lscale = sw.load_perm ? scale_table(sw.lcoef) : -1;
-                x.sscale = sw.store_perm ? scale_table(sw.scoef) : -1;
                 auto S = [](uint32_t m) { return swz_hd(m) << 3; };
+                // variant tables of a wide side are indexed per thread: shared memory, never the constant bank
+                auto variant_table = [&](int off, int nvar) { return -(px.n_chains * 16 + local(off, 64 << nvar)) - 2; };
+                x.lscale = sw.load_perm ? ((sw.wide & 1) ? variant_table(sw.lcoef, sw.l_nvar) : scale_table(sw.lcoef)) : -1;
+                x.sscale = sw.store_perm ? ((sw.wide & 2) ? variant_table(sw.scoef, sw.s_nvar) : scale_table(sw.scoef)) : -1;
+                if (sw.wide) {
+                    // Both sides in mask form, over a re-labelled thread index: thread `tid` holds the canonical thread
+                    // coordinate t = XOR_j tid_j * u[j].  The lane vectors u[0..3] are chosen so that the four low tid bits map
+                    // to four independent bank-pair bits on BOTH sides (conflict-free 8-byte accesses per half-warp); the rest
+                    // completes the basis.  Canonical image of thread bit j on a side that is not wide: the j-th non-triple bit.
+                    const int NTB = 2 * (k - 3);
+                    uint32_t canon[8] = {}, TLm[8], TSm[8];
+                    {
+                        int j = 0;
+                        for (int pos = 0; pos < 2 * k; pos += 2)
+                            if (pos != sw.p[0] && pos != sw.p[1] && pos != sw.p[2]) { canon[j++] = 1u << pos; canon[j++] = 1u << (pos + 1); }
+                    }
+                    for (int j = 0; j < NTB; ++j) {
+                        TLm[j] = S((sw.wide & 1) ? sw.ltmask[j] : canon[j]);
+                        TSm[j] = S((sw.wide & 2) ? sw.stmask[j] : canon[j]);
+                    }
+                    auto image = [&](const uint32_t* Tm, unsigned u) { uint32_t v = 0; for (int j = 0; j < NTB; ++j) if ((u >> j) & 1u) v ^= Tm[j]; return v; };
+                    auto rank_of = [](std::vector<unsigned> v, unsigned mask) {
+                        for (auto& w : v) w &= mask;
+                        int rank = 0;
+                        for (int bit = 0; bit < 16; ++bit) {
+                            int piv = -1;
+                            for (size_t i = rank; i < v.size(); ++i) if ((v[i] >> bit) & 1u) { piv = (int)i; break; }
+                            if (piv < 0) continue;
+                            std::swap(v[rank], v[piv]);
+                            for (size_t i = 0; i < v.size(); ++i) if ((int)i != rank && ((v[i] >> bit) & 1u)) v[i] ^= v[rank];
+                            ++rank;
+                        }
+                        return rank;
+                    };
+                    std::vector<unsigned> u, bl, bs;       // chosen thread vectors and their bank-pair images per side
+                    for (int pass2 = 0; pass2 < 2 && u.size() < 4; ++pass2)
+                        for (unsigned c = 1; c < (1u << NTB) && u.size() < 4; ++c) {
+                            std::vector<unsigned> tu = u, tl = bl, ts = bs;
+                            tu.push_back(c); tl.push_back((image(TLm, c) >> 3) & 15u); ts.push_back((image(TSm, c) >> 3) & 15u);
+                            if (rank_of(tu, ~0u) != (int)tu.size()) continue;
+                            const bool full = rank_of(tl, 15u) == (int)tl.size() && rank_of(ts, 15u) == (int)ts.size();
+                            const bool half = rank_of(tl, 15u) == (int)tl.size() || rank_of(ts, 15u) == (int)ts.size();
+                            if (full || (pass2 == 1 && half)) { u = tu; bl = tl; bs = ts; }
+                        }
+                    for (unsigned c = 1; c < (1u << NTB) && (int)u.size() < NTB; ++c) {
+                        std::vector<unsigned> tu = u;
+                        tu.push_back(c);
+                        if (rank_of(tu, ~0u) == (int)tu.size()) u = tu;
+                    }
+                    uint32_t W[32] = {};
+                    W[0] = (uint32_t)sw.wide | 3u; W[1] = (sw.wide & 1) ? (uint32_t)sw.l_nvar : 0u; W[2] = (sw.wide & 2) ? (uint32_t)sw.s_nvar : 0u;
+                    for (int j = 0; j < NTB; ++j) { W[4 + j] = image(TLm, u[j]); W[12 + j] = image(TSm, u[j]); }
+                    for (int j = 0; j < 4; ++j)
+                        for (int b = 0; b < NTB; ++b) {
+                            if (__builtin_popcount(u[b] & sw.lvmask[j]) & 1) W[20 + j] |= 1u << b;
+                            if (__builtin_popcount(u[b] & sw.svmask[j]) & 1) W[24 + j] |= 1u << b;
+                        }
+                    if (lc.size() & 1) lc.push_back(0.0);
+                    const int at = (int)lc.size();
+                    lc.resize(lc.size() + 16);
+                    std::memcpy(&lc[at], W, sizeof(W));
+                    x.pad = px.n_chains * 16 + at + 1;
+                }
                 for (int c = 0; c < 4; ++c) {       // register bits (zC, xC, zB, xB, zA, xA) = masks 0..5
                     x.lC[c] = ((c & 1) ? S(sw.lmask[0]) : 0u) ^ ((c & 2) ? S(sw.lmask[1]) : 0u);
                     x.lB[c] = ((c & 1) ? S(sw.lmask[2]) : 0u) ^ ((c & 2) ? S(sw.lmask[3]) : 0u);
@@ -1515,9 +1576,9 @@ static cudaError_t build_stream_tables(const Plan& p, DevPlan* d) {
             const Sweep3& sw_first = p.sweeps3[p.phases[ps.first_phase].first_sweep];
             const Phase& ph_last = p.phases[ps.first_phase + ps.n_phases - 1];
             const Sweep3& sw_last = p.sweeps3[ph_last.first_sweep + ph_last.n_sweeps - 1];
-            if (pi > 0 && p.opt_bulk && side(pin, sw_first, sw_first.lmask, false, px.first_A, px.first_B, px.first_C))
+            if (pi > 0 && p.opt_bulk && !sw_first.wide && side(pin, sw_first, sw_first.lmask, false, px.first_A, px.first_B, px.first_C))
                 px.load_mode = p.opt_bulk == 2 ? LOAD_DIRECT : LOAD_BULK;
-            if (p.opt_direct_store && side(pout, sw_last, sw_last.smask, true, px.last_A, px.last_B, px.last_C))
+            if (p.opt_direct_store && !sw_last.wide && side(pout, sw_last, sw_last.smask, true, px.last_A, px.last_B, px.last_C))
                 px.store_mode = STORE_DIRECT;
         }
         if (px.smem > (k == 7 ? 227u : 56u) * 1024) continue;       // k = 6: keep four CTAs per SM
@@ -2156,6 +2217,8 @@ int dmx_plan_set_option(dmx_plan* plan, const char* key, int value) {
     } else if (k == "frame32s") {
         if (value != 0 && value != 1 && value != 8 && value != 16) return fail(DMX_ERR_INVALID, "frame32s must be 0, 1 (= 8), 8 or 16");
         plan->p.opt_frame32s = value;
+    } else if (k == "wide") {
+        plan->p.opt_wide = value != 0;
     } else if (k == "scale_smem") {
         plan->p.opt_scale_smem = value != 0;
     } else if (k == "direct_store") {

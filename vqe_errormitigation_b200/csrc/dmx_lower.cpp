@@ -6,6 +6,7 @@
 // No CUDA in this file; it is exercised on CPU by tests/test_lowering.py through dmx_plan_dump().
 #include <algorithm>
 #include <array>
+#include <cstdlib>
 #include <cmath>
 #include <complex>
 #include <cstdio>
@@ -966,7 +967,432 @@ struct TripleBuilder {
         mus.clear(); new_chains.clear(); new_factors.clear();
     }
 
+    // ---- tile-wide monomials (plan option "wide") --------------------------------------------------------------------
+    struct MonoT {           // out[a] = sc[a] * in[src[a]] over the 4^k tile-local indices
+        std::vector<uint32_t> src;
+        std::vector<double> sc;
+        bool trivial = true;
+        explicit MonoT(int E = 0) : src(E), sc(E, 1.0) { for (int a = 0; a < E; ++a) src[a] = (uint32_t)a; }
+        void then(const MonoT& m) {      // apply m after this
+            const size_t E = src.size();
+            std::vector<uint32_t> ns(E);
+            std::vector<double> nc(E);
+            for (size_t a = 0; a < E; ++a) { ns[a] = src[m.src[a]]; nc[a] = m.sc[a] * sc[m.src[a]]; }
+            src.swap(ns); sc.swap(nc);
+            trivial = false;
+        }
+        void swap_with(MonoT& o) { src.swap(o.src); sc.swap(o.sc); std::swap(trivial, o.trivial); }
+    };
+
+    // block -> monomial over the whole tile (any resident qubits)
+    bool as_mono_tile(const Block& b, MonoT& out) const {
+        if (b.kind != BK_FIXED || (b.cls != CLS_MONO && b.cls != CLS_DIAG && b.cls != CLS_IDENT)) return false;
+        const int dim = b.dim();
+        std::vector<int> src(dim, -1);
+        std::vector<double> sc(dim, 0.0);
+        for (int a = 0; a < dim; ++a) {
+            for (int c = 0; c < dim; ++c)
+                if (b.M[a * dim + c] != 0.0) { if (src[a] >= 0) return false; src[a] = c; sc[a] = b.M[a * dim + c]; }
+            if (src[a] < 0) return false;
+        }
+        for (int a = 0; a < dim; ++a)
+            for (int c = 0; c < dim; ++c)
+                if (src[a ^ c] != (src[a] ^ src[c])) return false;
+        const int E = 1 << (2 * (int)tile_q.size());
+        out = MonoT(E);
+        out.trivial = false;
+        if (b.nq == 1) {
+            const int sh = local_pos[b.q[0]];
+            for (int a = 0; a < E; ++a) {
+                const int c = (a >> sh) & 3;
+                out.src[a] = (uint32_t)((a & ~(3 << sh)) | (src[c] << sh));
+                out.sc[a] = sc[c];
+            }
+        } else {
+            const int s0 = local_pos[b.q[0]], s1 = local_pos[b.q[1]];
+            for (int a = 0; a < E; ++a) {
+                const int c = (((a >> s0) & 3) << 2) | ((a >> s1) & 3);
+                const int sv = src[c];
+                out.src[a] = (uint32_t)((a & ~(3 << s0) & ~(3 << s1)) | ((sv >> 2) << s0) | ((sv & 3) << s1));
+                out.sc[a] = sc[c];
+            }
+        }
+        return true;
+    }
+
+    // canonical tile index of (thread index t, register code e) for the current triple
+    uint32_t canon(uint32_t t, int e) const {
+        int ps[3] = {local_pos[T[0]], local_pos[T[1]], local_pos[T[2]]};
+        std::sort(ps, ps + 3);
+        uint32_t a = t;
+        for (int j = 0; j < 3; ++j) a = ((a >> ps[j]) << (ps[j] + 2)) | (a & ((1u << ps[j]) - 1u));
+        return a | code_offset(e);
+    }
+
+    struct WideSide {
+        bool wide = false;        // needs the tmask / variant form (else the legacy triple-local form is exact)
+        int nvar = 0;
+        uint32_t tmask[8] = {}, rmask[6] = {}, vmask[4] = {};
+        std::vector<double> table;    // [2^nvar][64]
+        bool all_one = true;          // every scale is exactly 1
+    };
+
+    // Analyse one side of a sweep.  load: v[e] = sc[a] * tile[src[a]] with a = canon(t, e); store: the element of a goes to
+    // dst[a] = src^-1[a] with scale sc[dst[a]].  False when the scales need more than 16 thread-dependent variants or the
+    // thread classes are not the cosets of a subspace.
+    bool analyse(const MonoT& m, bool store, WideSide& out) const {
+        const int k = (int)tile_q.size(), E = 1 << (2 * k), NTB = 2 * (k - 3), NT = 1 << NTB;
+        std::vector<uint32_t> dst;
+        if (store) { dst.resize(E); for (int a = 0; a < E; ++a) dst[m.src[a]] = (uint32_t)a; }
+        auto image = [&](uint32_t a) { return store ? dst[a] : m.src[a]; };
+        auto scale = [&](uint32_t a) { return store ? m.sc[dst[a]] : m.sc[a]; };
+        out = WideSide();
+        for (int j = 0; j < NTB; ++j) out.tmask[j] = image(canon(1u << j, 0));
+        for (int j = 0; j < 6; ++j) out.rmask[j] = image(canon(0, 1 << j));
+        uint32_t triple_bits = 0;
+        for (int s2 = 0; s2 < 3; ++s2) triple_bits |= 3u << local_pos[T[s2]];
+        bool identity_threads = true;
+        for (int j = 0; j < NTB; ++j) identity_threads = identity_threads && out.tmask[j] == canon(1u << j, 0);
+        bool local_regs = true;
+        for (int j = 0; j < 6; ++j) local_regs = local_regs && !(out.rmask[j] & ~triple_bits);
+        // thread classes by scale vector
+        std::map<std::vector<double>, int> cls;
+        std::vector<int> cls_of(NT);
+        std::vector<std::vector<double>> vecs;
+        for (int t = 0; t < NT; ++t) {
+            std::vector<double> v(64);
+            for (int e = 0; e < 64; ++e) { v[e] = scale(canon((uint32_t)t, e)); out.all_one = out.all_one && v[e] == 1.0; }
+            auto it = cls.find(v);
+            if (it == cls.end()) { it = cls.emplace(v, (int)vecs.size()).first; vecs.push_back(v); }
+            cls_of[t] = it->second;
+        }
+        const int V = (int)vecs.size();
+        if (V > 16 || (V & (V - 1))) return false;
+        int nvar = 0;
+        while ((1 << nvar) < V) ++nvar;
+        if (V > 1) {
+            // the threads of class(0) must form a subspace K and the classes its cosets; variant bits = functionals vanishing on K
+            std::vector<uint32_t> K;
+            for (int t = 0; t < NT; ++t) if (cls_of[t] == cls_of[0]) K.push_back((uint32_t)t);
+            if ((int)K.size() * V != NT) return false;
+            for (int t = 0; t < NT; ++t)
+                for (uint32_t kk : K) if (cls_of[t ^ kk] != cls_of[t]) return false;
+            std::vector<unsigned> chosen;
+            for (uint32_t f = 1; f < (uint32_t)NT && (int)chosen.size() < nvar; ++f) {
+                bool ok = true;
+                for (uint32_t kk : K) if (__builtin_popcount(f & kk) & 1) { ok = false; break; }
+                if (!ok) continue;
+                std::vector<unsigned> trial = chosen;
+                trial.push_back(f);
+                if (gf2_rank_small(trial) == (int)trial.size()) chosen.push_back(f);
+            }
+            if ((int)chosen.size() != nvar) return false;
+            for (int j = 0; j < nvar; ++j) out.vmask[j] = chosen[j];
+        }
+        out.nvar = nvar;
+        out.table.assign((size_t)V * 64, 1.0);
+        std::vector<char> filled(V, 0);
+        for (int t = 0; t < NT; ++t) {
+            int var = 0;
+            for (int j = 0; j < nvar; ++j) var |= (__builtin_popcount((uint32_t)t & out.vmask[j]) & 1) << j;
+            if (!filled[var]) { std::copy(vecs[cls_of[t]].begin(), vecs[cls_of[t]].end(), out.table.begin() + (size_t)var * 64); filled[var] = 1; }
+            else for (int e = 0; e < 64; ++e) if (out.table[(size_t)var * 64 + e] != vecs[cls_of[t]][e]) return false;   // functionals do not separate
+        }
+        out.wide = !(identity_threads && local_regs && V == 1);
+        return true;
+    }
+
+    static int gf2_rank_small(std::vector<unsigned> v) {
+        int rank = 0;
+        for (int bit = 0; bit < 16; ++bit) {
+            int piv = -1;
+            for (size_t i = rank; i < v.size(); ++i) if ((v[i] >> bit) & 1u) { piv = (int)i; break; }
+            if (piv < 0) continue;
+            std::swap(v[rank], v[piv]);
+            for (size_t i = 0; i < v.size(); ++i) if ((int)i != rank && ((v[i] >> bit) & 1u)) v[i] ^= v[rank];
+            ++rank;
+        }
+        return rank;
+    }
+
+    size_t wide_doubles = 0;      // variant tables + descriptors of this pass (bounded: they live in shared memory)
+
+    // shared-memory bytes the pass needs so far beside the tile (chain matrices + every coefficient table its sweeps and
+    // micro-ops name), counted like pass_stream_eligible does
+    size_t pass_bytes() const {
+        std::map<int, int> tables;
+        size_t extra = 0;
+        auto mu_table = [&](const MicroOp& m) {
+            switch (m.kind) {
+                case MU3_MAT: if (!m.a2) tables[m.a0] = 16; break;
+                case MU3_DIAG: tables[m.a0] = 4; break;
+                case MU3_DIAG2: tables[m.a0] = 16; break;
+                case MU3_MAT2: tables[m.a0] = 256; break;
+                default: break;
+            }
+        };
+        for (size_t si = (size_t)phase.first_sweep; si < p.sweeps3.size(); ++si) {
+            const Sweep3& sw = p.sweeps3[si];
+            if (sw.load_perm) tables[sw.lcoef] = std::max(tables[sw.lcoef], 64 << ((sw.wide & 1) ? sw.l_nvar : 0));
+            if (sw.store_perm) tables[sw.scoef] = std::max(tables[sw.scoef], 64 << ((sw.wide & 2) ? sw.s_nvar : 0));
+            if (sw.wide) extra += 16;
+            for (int mi = 0; mi < sw.n_mu; ++mi) mu_table(p.mus[sw.first_mu + mi]);
+        }
+        for (const MicroOp& m : mus) mu_table(m);
+        size_t coefs = extra;
+        for (const auto& t : tables) coefs += (size_t)((t.second + 1) & ~1);
+        const size_t chains = p.chains.size() - (size_t)phase.first_chain + new_chains.size() + 3;     // + the slots still pending
+        return chains * 128 + coefs * 8;
+    }
+
+    void emit_wide(const WideSide& ls, const WideSide& ss, bool lead_trivial, bool trail_trivial) {
+        for (int s2 = 0; s2 < 3; ++s2) flush_slot(s2);
+        if (mus.empty() && lead_trivial && trail_trivial) return;
+        Sweep3 sw{};
+        for (int s2 = 0; s2 < 3; ++s2) sw.p[s2] = local_pos[T[s2]];
+        const int chain_base = (int)p.chains.size() - phase.first_chain;
+        const int factor_base = (int)p.factors.size();
+        for (ChainDev ch : new_chains) { ch.first_factor += factor_base; p.chains.push_back(ch); }
+        p.factors.insert(p.factors.end(), new_factors.begin(), new_factors.end());
+        for (MicroOp& m : mus)
+            if (m.kind == MU3_MAT && m.a2) m.a0 += chain_base;
+        for (int j = 0; j < 6; ++j) { sw.lmask[j] = code_offset(1 << j); sw.smask[j] = code_offset(1 << j); }
+        const int NTB = 2 * ((int)tile_q.size() - 3);
+        if (!lead_trivial) {
+            for (int j = 0; j < 6; ++j) sw.lmask[j] = ls.rmask[j];
+            if (!ls.all_one || ls.wide) {
+                sw.load_perm = 1;
+                sw.lcoef = cc.get(p, ls.table);
+                flops += 1.0;
+            }
+            if (ls.wide) {
+                sw.wide |= 1 | 4;
+                sw.l_nvar = ls.nvar;
+                for (int j = 0; j < NTB; ++j) sw.ltmask[j] = ls.tmask[j];
+                for (int j = 0; j < ls.nvar; ++j) sw.lvmask[j] = ls.vmask[j];
+                wide_doubles += ls.table.size();
+            } else if (!sw.load_perm) {
+                sw.load_perm = 1;      // pure permutation: the kernel takes the mask path only when load_perm is set
+                sw.lcoef = cc.get(p, ls.table);
+            }
+        }
+        if (!trail_trivial) {
+            for (int j = 0; j < 6; ++j) sw.smask[j] = ss.rmask[j];
+            sw.store_perm = 1;
+            sw.scoef = cc.get(p, ss.table);
+            flops += 1.0;
+            if (ss.wide) {
+                sw.wide |= 2 | 4;
+                sw.s_nvar = ss.nvar;
+                for (int j = 0; j < NTB; ++j) sw.stmask[j] = ss.tmask[j];
+                for (int j = 0; j < ss.nvar; ++j) sw.svmask[j] = ss.vmask[j];
+                wide_doubles += ss.table.size();
+            }
+        }
+        if (sw.wide) wide_doubles += 16;
+        sw.first_mu = (int)p.mus.size(); sw.n_mu = (int)mus.size();
+        p.mus.insert(p.mus.end(), mus.begin(), mus.end());
+        p.sweeps3.push_back(sw);
+        if (record) record->push_back({T[0], T[1], T[2]});
+        sweeps_elems += 1.0;
+        mus.clear(); new_chains.clear(); new_factors.clear();
+    }
+
+    // Sweep builder with tile-wide leading / trailing monomials.  The triple is chosen for the DENSE work: the builder looks
+    // through the monomial blocks that are ready (they cost no register residency any more) and takes the qubits of the
+    // earliest dense blocks behind them.
+    void run_wide(const std::vector<int>& order) {
+        const int n = p.n, k = (int)tile_q.size(), E = 1 << (2 * k);
+        // the pass's tables share the CTA's shared memory with the tile (pass_stream_eligible: 20 KB for 6-qubit tiles,
+        // 90 KB for 7); a wide side is only taken while its variant table still fits, with room left for the rest of the pass
+        const size_t PASS_LIMIT = (k == 7 ? 90u : 20u) * 1024 - 3072;
+        std::vector<std::vector<int>> qq(n);
+        std::vector<size_t> head(n, 0);
+        std::map<int, MonoT> mono_of;              // blocks of this pass that are tile-wide monomials
+        for (int bi : order) {
+            const Block& b = p.blocks[bi];
+            if (b.kind == BK_VAR) throw std::runtime_error("triple sweeps do not take variant blocks");
+            qq[b.q[0]].push_back(bi);
+            if (b.nq == 2) qq[b.q[1]].push_back(bi);
+            MonoT m;
+            if (as_mono_tile(b, m)) mono_of.emplace(bi, std::move(m));
+        }
+        auto front_of = [&](const std::vector<size_t>& h, int q) { return h[q] < qq[q].size() ? qq[q][h[q]] : -1; };
+        auto ready_in = [&](const std::vector<size_t>& h, int bi) {
+            const Block& b = p.blocks[bi];
+            for (int s2 = 0; s2 < b.nq; ++s2) if (front_of(h, b.q[s2]) != bi) return false;
+            return true;
+        };
+        auto pop_in = [&](std::vector<size_t>& h, int bi) {
+            const Block& b = p.blocks[bi];
+            for (int s2 = 0; s2 < b.nq; ++s2) ++h[b.q[s2]];
+        };
+        auto earliest_ready = [&](const std::vector<size_t>& h, bool want_mono, bool want_dense, const std::vector<char>* skip) {
+            int best = -1;
+            for (int q : tile_q) {
+                const int f = front_of(h, q);
+                if (f < 0 || !ready_in(h, f) || (best >= 0 && f >= best)) continue;
+                (void)skip;
+                const bool mono = mono_of.count(f) != 0;
+                if ((mono && !want_mono) || (!mono && !want_dense)) continue;
+                best = f;
+            }
+            return best;
+        };
+        size_t remaining = order.size();
+        while (remaining > 0) {
+            // ---- triple: look through the ready monomials, take the qubits of the earliest dense blocks ----
+            for (int attempt = 0; attempt < 2; ++attempt) {
+                int nt = 0;
+                T[0] = T[1] = T[2] = -1;
+                if (attempt == 0) {
+                    std::vector<size_t> h2 = head;
+                    while (true) { const int bi = earliest_ready(h2, true, false, nullptr); if (bi < 0) break; pop_in(h2, bi); }
+                    std::vector<int> dense;
+                    for (int q : tile_q) { const int f = front_of(h2, q); if (f >= 0 && ready_in(h2, f)) dense.push_back(f); }
+                    std::sort(dense.begin(), dense.end());
+                    dense.erase(std::unique(dense.begin(), dense.end()), dense.end());
+                    for (int bi : dense) {
+                        const Block& b = p.blocks[bi];
+                        int need = 0;
+                        for (int s2 = 0; s2 < b.nq; ++s2) need += slot_of(b.q[s2]) < 0;
+                        if (nt + need > 3) continue;
+                        for (int s2 = 0; s2 < b.nq; ++s2) if (slot_of(b.q[s2]) < 0) T[nt++] = b.q[s2];
+                    }
+                    // further dense work on the chosen qubits' neighbours: partners along pending two-qubit dense blocks
+                    while (nt > 0 && nt < 3) {
+                        int best_q = -1, best_i = 1 << 30;
+                        for (int s2 = 0; s2 < nt; ++s2)
+                            for (size_t t = h2[T[s2]]; t < qq[T[s2]].size(); ++t) {
+                                const Block& nb = p.blocks[qq[T[s2]][t]];
+                                if (nb.nq != 2 || mono_of.count(qq[T[s2]][t])) continue;
+                                const int partner = nb.q[0] == T[s2] ? nb.q[1] : nb.q[0];
+                                if (slot_of(partner) >= 0) continue;
+                                if (qq[T[s2]][t] < best_i) { best_i = qq[T[s2]][t]; best_q = partner; }
+                                break;
+                            }
+                        if (best_q < 0) break;
+                        T[nt++] = best_q;
+                    }
+                    if (nt == 0) {       // only monomials are left in this pass: any triple will do
+                        const int b0 = earliest_ready(head, true, true, nullptr);
+                        if (b0 < 0) throw std::runtime_error("triple builder: no ready block");
+                        T[nt++] = p.blocks[b0].q[0];
+                        if (p.blocks[b0].nq == 2) T[nt++] = p.blocks[b0].q[1];
+                    }
+                    // spectators: the qubits whose dense work comes next
+                    while (nt < 3) {
+                        int best_q = -1, best_i = 1 << 30;
+                        for (int q : tile_q) {
+                            if (slot_of(q) >= 0) continue;
+                            int f = (1 << 30) - 1;
+                            for (size_t t = h2[q]; t < qq[q].size(); ++t) if (!mono_of.count(qq[q][t])) { f = qq[q][t]; break; }
+                            if (f < best_i) { best_i = f; best_q = q; }
+                        }
+                        if (best_q < 0) throw std::runtime_error("triple builder: tile has fewer than three qubits");
+                        T[nt++] = best_q;
+                    }
+                } else {
+                    // fallback (guarantees progress): the earliest ready block's own qubits, as the local builder does
+                    const int b0 = earliest_ready(head, true, true, nullptr);
+                    if (b0 < 0) throw std::runtime_error("triple builder: no ready block");
+                    T[nt++] = p.blocks[b0].q[0];
+                    if (p.blocks[b0].nq == 2) T[nt++] = p.blocks[b0].q[1];
+                    while (nt < 3) {
+                        int best_q = -1, best_i = 1 << 30;
+                        for (int q : tile_q) {
+                            if (slot_of(q) >= 0) continue;
+                            const int f = front_of(head, q) >= 0 ? front_of(head, q) : (1 << 30) - 1;
+                            if (f < best_i) { best_i = f; best_q = q; }
+                        }
+                        if (best_q < 0) throw std::runtime_error("triple builder: tile has fewer than three qubits");
+                        T[nt++] = best_q;
+                    }
+                }
+                // ---- absorb ----
+                std::vector<size_t> h = head;
+                size_t popped = 0;
+                MonoT lead(E), trail(E);
+                WideSide ls, ss;
+                analyse(lead, false, ls);
+                analyse(trail, true, ss);
+                auto budget_ok = [&](const WideSide& cand, const WideSide& other) {
+                    if (!cand.wide) return true;
+                    return pass_bytes() + (cand.table.size() + (other.wide ? other.table.size() : 0) + 64 + 16) * 8 <= PASS_LIMIT;
+                };
+                // stage 0: leading monomials, anywhere in the tile
+                while (true) {
+                    const int bi = earliest_ready(h, true, false, nullptr);
+                    if (bi < 0) break;
+                    // a monomial inside the triple may also wait for the body (one-qubit) - keep the local builder's order: lead
+                    MonoT cand = lead;
+                    cand.then(mono_of.at(bi));
+                    WideSide cs;
+                    if (!analyse(cand, false, cs) || !budget_ok(cs, ss)) break;
+                    lead.swap_with(cand); ls = cs;
+                    pop_in(h, bi); ++popped;
+                }
+                // stage 1: dense work inside the triple (one-qubit blocks of any class queue per slot)
+                bool to_trailing = false;
+                while (!to_trailing) {
+                    int bi = -1;
+                    for (int s2 = 0; s2 < 3; ++s2) {
+                        const int f = front_of(h, T[s2]);
+                        if (f < 0 || !ready_in(h, f) || (bi >= 0 && f >= bi)) continue;
+                        const Block& b = p.blocks[f];
+                        bool inside = true;
+                        for (int t = 0; t < b.nq; ++t) inside = inside && slot_of(b.q[t]) >= 0;
+                        if (inside) bi = f;
+                    }
+                    if (bi < 0) break;
+                    const Block& b = p.blocks[bi];
+                    if (b.nq == 1) { pend[slot_of(b.q[0])].push_back(bi); pop_in(h, bi); ++popped; continue; }
+                    if (mono_of.count(bi) && b.cls == CLS_MONO) { to_trailing = true; break; }
+                    int s0 = slot_of(b.q[0]), s1 = slot_of(b.q[1]);
+                    std::vector<double> M = b.M;
+                    if (s0 > s1) { M = swap_qubits(M); std::swap(s0, s1); }
+                    flush_slot(s0); flush_slot(s1);
+                    const int pair = s0 == 0 ? (s1 == 1 ? 0 : 1) : 2;
+                    const int cls = classify(M, 16);
+                    if (cls == CLS_DIAG || cls == CLS_IDENT) {
+                        std::vector<double> dg(16);
+                        for (int i = 0; i < 16; ++i) dg[i] = M[i * 16 + i];
+                        if (cls != CLS_IDENT) { mus.push_back(mu(MU3_DIAG2, cc.get(p, dg), pair)); flops += 1.0; }
+                    } else {
+                        mus.push_back(mu(MU3_MAT2, cc.get(p, M), pair));
+                        flops += 31.0;
+                    }
+                    pop_in(h, bi); ++popped;
+                }
+                // stage 2: trailing monomials, anywhere in the tile - but never past a pending one-qubit block of the body
+                while (true) {
+                    const int bi = earliest_ready(h, true, false, nullptr);
+                    if (bi < 0) break;
+                    MonoT cand = trail;
+                    cand.then(mono_of.at(bi));
+                    WideSide cs;
+                    if (!analyse(cand, true, cs) || !budget_ok(cs, ls)) break;
+                    trail.swap_with(cand); ss = cs;
+                    pop_in(h, bi); ++popped;
+                }
+                if (popped == 0) {
+                    for (int s2 = 0; s2 < 3; ++s2) pend[s2].clear();
+                    if (attempt == 1) throw std::runtime_error("triple builder: no progress");
+                    continue;
+                }
+                head = h;
+                remaining -= popped;
+                emit_wide(ls, ss, lead.trivial, trail.trivial);
+                break;
+            }
+        }
+        phase.n_sweeps = (int)p.sweeps3.size() - phase.first_sweep;
+        phase.n_chains = (int)p.chains.size() - phase.first_chain;
+        if (phase.n_sweeps > 0) p.phases.push_back(phase);
+    }
+
     void run(const std::vector<int>& order) {
+        if (p.opt_wide && tile_q.size() >= 4) { run_wide(order); return; }
         const int n = p.n;
         std::vector<std::vector<int>> qq(n);
         std::vector<size_t> head(n, 0);
@@ -1205,8 +1631,9 @@ bool pass_stream_eligible(const Plan& p, const Pass& ps) {
             if (p.triples) {
                 const Sweep3& sw = p.sweeps3[phase.first_sweep + si];
                 first_mu = sw.first_mu; n_mu = sw.n_mu;
-                if (sw.load_perm) tables[sw.lcoef] = 64;
-                if (sw.store_perm) tables[sw.scoef] = 64;
+                if (sw.load_perm) tables[sw.lcoef] = std::max(tables[sw.lcoef], 64 << ((sw.wide & 1) ? sw.l_nvar : 0));
+                if (sw.store_perm) tables[sw.scoef] = std::max(tables[sw.scoef], 64 << ((sw.wide & 2) ? sw.s_nvar : 0));
+                if (sw.wide) tables[-1 - (phase.first_sweep + si)] = 16;      // descriptor
             } else {
                 const SweepDev& sw = p.sweeps[phase.first_sweep + si];
                 first_mu = sw.first_mu; n_mu = sw.n_mu;
@@ -1230,10 +1657,12 @@ bool pass_stream_eligible(const Plan& p, const Pass& ps) {
             }
         }
     }
-    if (n_sweeps > STREAM_MAX_SWEEPS || n_mus > STREAM_MAX_MUS) return false;
     size_t coefs = 0;
     for (const auto& t : tables) coefs += (size_t)((t.second + 1) & ~1);
-    return (size_t)n_chains * 128 + coefs * 8 <= (k == 7 ? 90u : 20u) * 1024;
+    const bool ok = n_sweeps <= STREAM_MAX_SWEEPS && n_mus <= STREAM_MAX_MUS && (size_t)n_chains * 128 + coefs * 8 <= (k == 7 ? 90u : 20u) * 1024;
+    if (!ok && std::getenv("DMX_VERBOSE"))
+        std::fprintf(stderr, "[dmx] pass not eligible: %d sweeps, %d micro-ops, %d chains, %zu table doubles\n", n_sweeps, n_mus, n_chains, coefs);
+    return ok;
 }
 
 // Remapping pass builder (see Pass::pos_in / pos_out).  Same DAG-greedy block selection as schedule_streaming, but no
@@ -1389,25 +1818,43 @@ static void schedule_streaming_remap(Plan& p) {
     // when neither of the two lowest-positioned qubits of that side is register-resident in that sweep: the 16 lanes of
     // a half-warp then walk the 16 doubles of a 128-byte run (conflict-free shared-memory reads, full-line stores).
     std::vector<std::array<int, 3>> first3(L, std::array<int, 3>{-1, -1, -1}), last3(L, std::array<int, 3>{-1, -1, -1});
+    // Wide sweeps are decided per pass: a pass whose tables no longer fit beside the tile (pass_stream_eligible), or that
+    // would need more sweeps than the triple-local builder, is built by the local builder instead.
+    std::vector<char> pass_wide(L, 0);
+    const int want_wide = p.opt_wide;
     if (p.opt_triples && k >= 3) {
         for (size_t pi = 0; pi < L; ++pi) {
             if (orders[pi].empty()) continue;
-            const size_t n_sw = p.sweeps3.size(), n_mu = p.mus.size(), n_ch = p.chains.size(), n_fa = p.factors.size(), n_ph = p.phases.size(),
-                         n_co = p.coefs.size();
             std::vector<int> tq, lp(n, -1);
             for (int q = 0; q < n; ++q) if (tiles[pi][q]) tq.push_back(q);
             for (size_t i = 0; i < tq.size(); ++i) lp[tq[i]] = 2 * (int)i;
-            CoefCache scratch;
-            std::vector<std::array<int, 3>> rec;
-            {
-                TripleBuilder tb(p, scratch, lp, tq);
-                tb.record = &rec;
-                tb.run(orders[pi]);
+            size_t local_sweeps = 0;
+            for (int mode = 0; mode <= (want_wide ? 1 : 0); ++mode) {
+                const size_t n_sw = p.sweeps3.size(), n_mu = p.mus.size(), n_ch = p.chains.size(), n_fa = p.factors.size(), n_ph = p.phases.size(),
+                             n_co = p.coefs.size();
+                CoefCache scratch;
+                std::vector<std::array<int, 3>> rec;
+                p.opt_wide = mode;
+                bool ok = true;
+                {
+                    TripleBuilder tb(p, scratch, lp, tq);
+                    tb.record = &rec;
+                    tb.run(orders[pi]);
+                }
+                if (mode == 1) {
+                    Pass probe;
+                    probe.tile_q = tq;
+                    probe.first_phase = (int)n_ph; probe.n_phases = (int)p.phases.size() - (int)n_ph;
+                    ok = pass_stream_eligible(p, probe) && rec.size() < local_sweeps;
+                } else {
+                    local_sweeps = rec.size();
+                }
+                p.sweeps3.resize(n_sw); p.mus.resize(n_mu); p.chains.resize(n_ch); p.factors.resize(n_fa); p.phases.resize(n_ph); p.coefs.resize(n_co);
+                if (ok && !rec.empty()) { first3[pi] = rec.front(); last3[pi] = rec.back(); pass_wide[pi] = (char)mode; }
             }
-            p.sweeps3.resize(n_sw); p.mus.resize(n_mu); p.chains.resize(n_ch); p.factors.resize(n_fa); p.phases.resize(n_ph); p.coefs.resize(n_co);
-            if (!rec.empty()) { first3[pi] = rec.front(); last3[pi] = rec.back(); }
         }
     }
+    p.opt_wide = want_wide;
     auto in3 = [](const std::array<int, 3>& t, int q) { return t[0] == q || t[1] == q || t[2] == q; };
     std::vector<std::vector<int>> pos(L + 1, std::vector<int>(n));
     for (int q = 0; q < n; ++q) pos[L][q] = n - 1 - q;
@@ -1517,8 +1964,10 @@ static void schedule_streaming_remap(Plan& p) {
         pass.first_phase = (int)p.phases.size();
         if (!orders[pi].empty()) {
             if (p.triples) {
+                p.opt_wide = pass_wide[pi];
                 TripleBuilder sb(p, cc, local_pos, pass.tile_q);
                 sb.run(orders[pi]);
+                p.opt_wide = want_wide;
                 flops += sb.flops;
                 sweeps += sb.sweeps_elems;
             } else {
@@ -1969,6 +2418,7 @@ static bool build_frame(Plan& p, std::string& why) {
 
 void lower_plan(Plan& p) {
     if (p.n < 1 || p.n > DMX_MAX_QUBITS) throw std::runtime_error("n_qubits out of range");
+    if (const char* env = std::getenv("DMX_WIDE")) p.opt_wide = std::atoi(env) != 0;      // test hook: whole-suite A/B of the wide builder
     p.blocks.clear(); p.rots.clear(); p.mus.clear(); p.sweeps.clear(); p.factors.clear(); p.chains.clear(); p.phases.clear();
     p.coefs.clear(); p.passes.clear();
     p.remapped = false; p.triples = false; p.sweeps3.clear(); p.f32_n = 0;
@@ -2022,10 +2472,16 @@ void lower_plan(Plan& p) {
             try {
                 schedule_streaming_remap(p);
                 remapped = true;
-            } catch (const std::runtime_error&) {
+            } catch (const std::runtime_error& e) {
                 remapped = false;      // e.g. a builder limit: fall back to the pinned-qubit scheduler below
+                if (std::getenv("DMX_VERBOSE")) std::fprintf(stderr, "[dmx] remapping scheduler gave up: %s\n", e.what());
             }
-            for (const Pass& ps : p.passes) remapped = remapped && (ps.n_phases == 0 || pass_stream_eligible(p, ps));
+            for (size_t pi = 0; pi < p.passes.size(); ++pi) {
+                const Pass& ps = p.passes[pi];
+                const bool ok = ps.n_phases == 0 || pass_stream_eligible(p, ps);
+                if (!ok && remapped && std::getenv("DMX_VERBOSE")) std::fprintf(stderr, "[dmx] pass %zu is not eligible for the stream kernel\n", pi);
+                remapped = remapped && ok;
+            }
             if (!remapped) {   // the generic tile kernel only knows the standard layout: re-plan with pinned low qubits
                 p.mus.clear(); p.sweeps.clear(); p.sweeps3.clear(); p.factors.clear(); p.chains.clear(); p.phases.clear(); p.coefs.clear(); p.passes.clear();
                 p.triples = false;
@@ -2139,6 +2595,16 @@ std::string dump_plan(const Plan& p) {
         for (int j = 0; j < 6; ++j) os << (j ? "," : "") << w.lmask[j];
         os << " smask=";
         for (int j = 0; j < 6; ++j) os << (j ? "," : "") << w.smask[j];
+        if (w.wide) {
+            os << " wide=" << w.wide << " lnvar=" << w.l_nvar << " snvar=" << w.s_nvar << " ltmask=";
+            for (int j = 0; j < 8; ++j) os << (j ? "," : "") << w.ltmask[j];
+            os << " stmask=";
+            for (int j = 0; j < 8; ++j) os << (j ? "," : "") << w.stmask[j];
+            os << " lvmask=";
+            for (int j = 0; j < 4; ++j) os << (j ? "," : "") << w.lvmask[j];
+            os << " svmask=";
+            for (int j = 0; j < 4; ++j) os << (j ? "," : "") << w.svmask[j];
+        }
         os << "\n";
     }
     for (size_t i = 0; i < p.mus.size(); ++i)

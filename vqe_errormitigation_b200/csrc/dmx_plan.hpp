@@ -94,12 +94,24 @@ enum Mu3Kind : int32_t {
     MU3_MAT2 = 19    // dense 16x16 at a0 on slot pair a1
 };
 
-struct Sweep3 {       // 88 bytes
+struct Sweep3 {
     int32_t p[3];             // tile-local bit positions of the codes of slots A, B, C
     int32_t first_mu, n_mu;
     int32_t load_perm, lcoef; // load:  v[e] = coef[lcoef + e] * tile[base ^ X_l(e)]   (64 scales; skipped when !load_perm)
     int32_t store_perm, scoef;// store: tile[base ^ X_s(e)] = coef[scoef + e] * v[e]
     uint32_t lmask[6], smask[6];
+    // "Wide" monomials (plan option "wide"): leading / trailing Clifford x Pauli-noise blocks on ANY qubits of the tile, not
+    // only on the register triple.  Their GF(2)-linear permutation rides on the exchange addressing - the thread's base
+    // becomes a linear image of its index (tmask) and the register masks may reach outside the triple - and their diagonal
+    // part becomes a 64-entry scale table that depends on the thread only through a few parities of its index (variants).
+    //   load : v[e] = coef[lcoef + 64 * var_l(t) + e] * tile[T_l(t) ^ X_l(e)],  T_l(t) = XOR_j t_j * ltmask[j]
+    //   store: tile[T_s(t) ^ X_s(e)] = coef[scoef + 64 * var_s(t) + e] * v[e],  var(t) = sum_j parity(t & vmask[j]) << j
+    // t = the thread's values of the non-triple tile bits in ascending position.  A wide sweep reads and writes different
+    // address sets, so the kernel puts a block barrier between its loads and its stores (bit 2).
+    int32_t wide = 0;         // bit 0: load side, bit 1: store side, bit 2: barrier between loads and stores
+    int32_t l_nvar = 0, s_nvar = 0;
+    uint32_t ltmask[8] = {}, stmask[8] = {};
+    uint32_t lvmask[4] = {}, svmask[4] = {};
 };
 
 struct ChainFactor {  // one factor of a per-circuit 1-qubit matrix product (applied in order)
@@ -180,6 +192,7 @@ struct Plan {
     int opt_frame32s = 1;               // one-rotation-class parameter sweeps: 32 circuits per warp (dmx_frame32s_kernel)
     int opt_seg_cpb = 8;                // circuits per warp / thread of the frame kernels
     int opt_bulk = 1;                   // streaming tile load: 0 register staging, 1 cp.async.bulk + mbarrier, 2 direct global loads
+    int opt_wide = 0;                   // streaming triple sweeps: absorb tile-wide leading / trailing monomial blocks (Sweep3::wide)
     int opt_scale_smem = 0;             // streaming: permutation scale tables in shared memory (LDS.128) instead of the constant bank
     int opt_direct_store = 1;           // streaming: the last sweep of a pass writes its registers straight to global memory
     bool finalized = false;

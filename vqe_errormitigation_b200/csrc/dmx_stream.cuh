@@ -67,7 +67,9 @@ struct SweepX3 {              // 128 bytes
     int32_t first_mu, n_mu;
     int32_t lscale, sscale;   // 64 scales: >= 0 offset into StreamArgs3::cfix (constant bank), <= -2 offset -(v+2) into the
                               // shared-memory coefficient area, -1 none
-    int32_t pad;
+    int32_t pad;              // wide sweeps (Sweep3::wide): 1 + offset (doubles, in the shared-memory coefficient area) of a 32-word
+                              // descriptor {flags, l_nvar, s_nvar, -, ltm[8], stm[8], lvm[4], svm[4]}; the masks ltm / stm are
+                              // swizzled byte offsets, the variant tables [2^nvar][64] sit at lscale / sscale (shared memory)
     uint32_t lA[4], lB[4], lC[4];   // load : byte offset of register e = lA[e >> 4] ^ lB[(e >> 2) & 3] ^ lC[e & 3]
     uint32_t sA[4], sB[4], sC[4];   // store: same
 };
@@ -564,11 +566,32 @@ __global__ void __launch_bounds__(THREADS, THREADS == 256 ? 1 : 4) dmx_stream3_k
     for (int si = 0; si < a.n_sweeps; ++si) {
         const SweepX3& sw = a.sweeps[si];
         unsigned sb = swz_hd(insert2_hd(insert2_hd(insert2_hd((unsigned)tid, sw.p[0]), sw.p[1]), sw.p[2])) << 3;
+        // wide sweep: the thread's base is a GF(2)-linear image of its index (per side), its scale table one of 2^nvar variants
+        unsigned sbl = sb, sbs = sb, wflags = 0;
+        int lvar = 0, svar = 0;
+        if (sw.pad) {
+            constexpr int NTB = THREADS == 64 ? 6 : 8;
+            const unsigned* __restrict__ W = reinterpret_cast<const unsigned*>(cf + (sw.pad - 1));
+            wflags = W[0];
+            if (wflags & 1u) {
+                sbl = 0;
+#pragma unroll
+                for (int j = 0; j < NTB; ++j) sbl ^= ((tid >> j) & 1) ? W[4 + j] : 0u;
+                for (unsigned j = 0; j < W[1]; ++j) lvar |= (__popc((unsigned)tid & W[20 + j]) & 1) << j;
+            }
+            if (wflags & 2u) {
+                sbs = 0;
+#pragma unroll
+                for (int j = 0; j < NTB; ++j) sbs ^= ((tid >> j) & 1) ? W[12 + j] : 0u;
+                for (unsigned j = 0; j < W[2]; ++j) svar |= (__popc((unsigned)tid & W[24 + j]) & 1) << j;
+            }
+        }
         double v[64];
         if (si == 0 && a.load_mode >= LOAD_BULK) {
             // this thread holds the elements whose non-register qubits, taken in LOAD-LINEAR order, spell tid: that is the
             // identity its store into the swizzled tile-local layout must use
             sb = swz_hd(deposit_pairs((unsigned)tid, a.first_tl)) << 3;
+            sbs = sb;
             // first sweep on the LINEAR image of the tile (what the bulk copy delivered, or global memory itself): the
             // thread's non-register bits fill the remaining index bits in ascending order, so a half-warp walks the 16
             // doubles of a 128-byte run
@@ -602,17 +625,19 @@ __global__ void __launch_bounds__(THREADS, THREADS == 256 ? 1 : 4) dmx_stream3_k
 #pragma unroll
             for (int i = 0; i < 16; ++i) ab[i] = sw.lA[i >> 2] ^ sw.lB[i & 3];
 #pragma unroll
-            for (int c = 0; c < 4; ++c) sc[c] = sb ^ sw.lC[c];
+            for (int c = 0; c < 4; ++c) sc[c] = sbl ^ sw.lC[c];
 #pragma unroll
             for (int e = 0; e < 64; ++e) v[e] = *reinterpret_cast<const double*>(tb + (sc[e & 3] ^ ab[e >> 2]));
             if (sw.lscale >= 0) {
 #pragma unroll
                 for (int e = 0; e < 64; ++e) v[e] *= a.cfix[sw.lscale + e];
             } else if (sw.lscale <= -2) {
-                const double2* __restrict__ lc = reinterpret_cast<const double2*>(cf - (sw.lscale + 2));
+                const double2* __restrict__ lc = reinterpret_cast<const double2*>(cf - (sw.lscale + 2) + lvar * 64);
 #pragma unroll
                 for (int e = 0; e < 32; ++e) { const double2 s = lc[e]; v[2 * e] *= s.x; v[2 * e + 1] *= s.y; }
             }
+            // a wide sweep writes other addresses than it reads: every thread must have loaded before anyone stores
+            if (wflags & 4u) __syncthreads();
         }
         for (int mi = 0; mi < sw.n_mu; ++mi) {
             const MuX m = a.mus[sw.first_mu + mi];
@@ -644,7 +669,7 @@ __global__ void __launch_bounds__(THREADS, THREADS == 256 ? 1 : 4) dmx_stream3_k
 #pragma unroll
                 for (int e = 0; e < 64; ++e) v[e] *= a.cfix[sw.sscale + e];
             } else if (sw.sscale <= -2) {
-                const double2* __restrict__ sc2 = reinterpret_cast<const double2*>(cf - (sw.sscale + 2));
+                const double2* __restrict__ sc2 = reinterpret_cast<const double2*>(cf - (sw.sscale + 2) + svar * 64);
 #pragma unroll
                 for (int e = 0; e < 32; ++e) { const double2 s = sc2[e]; v[2 * e] *= s.x; v[2 * e + 1] *= s.y; }
             }
@@ -664,7 +689,7 @@ __global__ void __launch_bounds__(THREADS, THREADS == 256 ? 1 : 4) dmx_stream3_k
 #pragma unroll
             for (int i = 0; i < 16; ++i) ab[i] = sw.sA[i >> 2] ^ sw.sB[i & 3];
 #pragma unroll
-            for (int c = 0; c < 4; ++c) sc[c] = sb ^ sw.sC[c];
+            for (int c = 0; c < 4; ++c) sc[c] = sbs ^ sw.sC[c];
 #pragma unroll
             for (int e = 0; e < 64; ++e) *reinterpret_cast<double*>(tb + (sc[e & 3] ^ ab[e >> 2])) = v[e];
         }
