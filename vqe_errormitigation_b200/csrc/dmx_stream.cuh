@@ -505,6 +505,8 @@ __device__ __forceinline__ void dense2_64(double (&v)[64], const double* __restr
     }
 }
 
+// (Measured and rejected, profiles/r2_stream3_experiments.txt: __maxnreg__(200) - five CTAs per SM, 80 B of spills outside the
+// sweep loop - runs HEA-10 at 7 577 circuits/s against 8 235 with four CTAs at 238 registers.)
 template <int THREADS, bool GENERAL>
 __global__ void __launch_bounds__(THREADS, THREADS == 256 ? 1 : 4) dmx_stream3_kernel(const __grid_constant__ StreamArgs3 a) {
     constexpr int NITER = 32;                               // 4^k / (2 * THREADS)
