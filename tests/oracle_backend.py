@@ -60,7 +60,33 @@ def _energies(self, params=None, variants=None, *, batch=None, out=None, workspa
     return _FakeTensor(_energies_host(self, params, variants, batch))
 
 
+def _shot_expectations(probs, shots, masks, seed, first_row=0):
+    """numpy Philox restatement of dmx_shot_expectations (tests/philox_ref.py) on a host array."""
+    import philox_ref
+    arr = probs._a if isinstance(probs, _FakeTensor) else np.asarray(probs)
+    if not isinstance(shots, (int, np.integer)):
+        shots = np.asarray(shots)
+    return _FakeTensor(philox_ref.shot_expectations(arr, shots, [int(m) for m in masks], int(seed), int(first_row)))
+
+
+def _sampled_energies(self, params, meas_reps, seed):
+    """SampledEnergyProgram.energies without a device: same rows, same Philox streams, same weights."""
+    M = len(self.variant_rows)
+    if params is None:
+        params = self.lifted[None, :] if self.prog.n_params else None
+    B = 1 if params is None else len(params)
+    p = None if params is None else np.repeat(np.asarray(params, np.float64), M, axis=0)
+    v = np.tile(self.variant_rows, (B, 1))
+    probs = self.prog.probabilities(p, v, batch=B * M, renormalise=True)
+    expect = _shot_expectations(probs, meas_reps, self.masks, seed).numpy()
+    w = np.tile(self.weights, (B, 1))
+    return (expect * w).sum(axis=1).reshape(B, M).sum(axis=1) + self.identity
+
+
 def install(monkeypatch):
+    from vqe_errormitigation_b200.data_containers import model_hydrogen
+    monkeypatch.setattr(engine, "shot_expectations", _shot_expectations)
+    monkeypatch.setattr(model_hydrogen.SampledEnergyProgram, "energies", _sampled_energies)
     monkeypatch.setattr(engine.CircuitProgram, "energies_host", _energies_host)
     monkeypatch.setattr(engine.CircuitProgram, "energies", _energies)
     monkeypatch.setattr(engine.CircuitProgram, "density", _density)
