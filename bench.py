@@ -912,7 +912,10 @@ def main():
         for key in ALSO:
             t0 = time.perf_counter()
             try:
-                res = run_workload(WORKLOADS[key](), ctx, ALSO_STEPS[key], 3, with_cpu_baseline=not args.no_cpu_baseline,
+                wl_k = WORKLOADS[key]()
+                # a short CPU baseline for the riders the oracle evaluates in milliseconds (n <= 7); one 10-qubit circuit costs
+                # it ~40 s and a 12-qubit one hours - run `--workload hea10|lih12` for those
+                res = run_workload(wl_k, ctx, ALSO_STEPS[key], 3, with_cpu_baseline=not args.no_cpu_baseline and wl_k["builder"].n_qubits <= 7,
                                    with_e2e=not args.no_e2e, cpu_budget_s=2.5)
             except Exception as exc:  # noqa: BLE001 - a rider must not take the headline line down
                 if world > 1:

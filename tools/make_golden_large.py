@@ -43,8 +43,13 @@ def lih12_26_inputs(n_params: int) -> np.ndarray:
 def main():
     import bench
     from oracle import c_oracle as CO
-    args = [a for a in sys.argv[1:] if not a.startswith("--")]
-    threads = int(sys.argv[sys.argv.index("--threads") + 1]) if "--threads" in sys.argv else max(1, CO.max_threads() - 2)
+    argv = sys.argv[1:]
+    threads = max(1, CO.max_threads() - 2)
+    if "--threads" in argv:
+        i = argv.index("--threads")
+        threads = int(argv[i + 1])
+        del argv[i:i + 2]
+    args = [a for a in argv if not a.startswith("--")]
     which = args or ["hea10", "lih12_26", "lih12_full"]
     for key in which:
         t0 = time.time()
@@ -65,7 +70,7 @@ def main():
         e = CO.energy_batch(b.n_qubits, list(b.ops), b.pool(), terms, params=params, n_params=len(b.param_names),
                             threads=threads, wide=True)
         _save(key, {"energies": [float(v) for v in e], "rows": int(len(e)), "n_ops": len(b.ops), "n_params": len(b.param_names),
-                    "param_names": list(b.param_names), "params_sha": __import__("hashlib").sha256(np.ascontiguousarray(params).tobytes()).hexdigest(),
+                    "params_sha": __import__("hashlib").sha256(np.ascontiguousarray(params).tobytes()).hexdigest(),
                     "oracle": "oracle/dm_oracle.c orc_energy_batch_wide", "seconds": round(time.time() - t0, 1)})
         print(key, e, f"{time.time() - t0:.0f} s", flush=True)
 
