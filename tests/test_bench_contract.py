@@ -48,3 +48,41 @@ def test_every_record_parses():
     for path in glob.glob(os.path.join(ROOT, "profiles", "r1_bench_*.json")):
         with open(path) as fh:
             assert "value" in json.load(fh), path
+
+
+def test_round2_default_record_carries_every_config_and_parity():
+    """The round-2 default line: headline contract keys, a parity figure per workload (all within the 1e-10 bar), the `also`
+    block with BASELINE configs[2..4] + the batch-axes and 7-qubit riders, each with roofline and end-to-end numbers."""
+    d = load("r2_bench_default_v3.json")
+    assert [k for k in BASE if k not in d] == []
+    assert d["parity_max_abs_err"] is not None and d["parity_max_abs_err"] < 1e-10
+    assert d["e2e"]["value"] != d["value"] and d["e2e"]["in_flight"] >= 1 and d["e2e"]["h2d_bytes_per_step"] == 65536 * 8
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["by_threads"].keys() >= {"1", "6"}
+    also = d["also"]
+    assert set(also) >= {"h2_qem", "hea10", "lih12", "h2_bonds", "swap7_qem"}
+    for key, rec in also.items():
+        assert "error" not in rec, (key, rec)
+        assert rec["value"] > 0 and rec["ms_per_step"] > 0 and rec["gpu_launches"] >= rec["steps"]
+        assert rec["parity_max_abs_err"] is not None and rec["parity_max_abs_err"] < 1e-10, key
+        assert {"bound", "achieved", "peak", "unit", "frac", "traffic"} <= set(rec["roofline"])
+        assert {"value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step"} <= set(rec["e2e"])
+    for key in ("hea10", "lih12"):
+        rf = also[key]["roofline"]
+        assert rf["bound"] == "hbm" and 0 < rf["frac_executed"] < rf["frac"]       # canonical bytes vs the bytes really moved
+    assert also["hea10"]["roofline"]["frac"] >= 0.70 and also["lih12"]["roofline"]["frac"] >= 0.70
+    assert also["h2_qem"]["estimator"]["value"] > 0 and also["h2_qem"]["e2e"]["unique_rows"] < also["h2_qem"]["e2e"]["rows_represented"]
+
+
+def test_round2_multi_gpu_records():
+    for name, n in (("r2_bench_default_n2_v1.json", 2), ("r2_bench_default_n8_v2.json", 8)):
+        d = load(name)
+        assert d["n_gpus"] == n and d["scaling"] == "weak" and d["value"] > 0.9 * n * 3.3e9
+        est = d["also"]["h2_qem"]["estimator"]
+        assert "NCCL all-reduce" in est["contains"] and est["variants_per_estimate"] == 125000 * n
+
+
+def test_round2_reference_arm_record():
+    d = load("r2_bench_reference_arm_v3.json")
+    assert d["impl"] == "reference" and d["cpu_baseline"]["kind"] == "port" and "libdmx.so is not loaded" in d["native"]
+    assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+
