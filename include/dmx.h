@@ -145,11 +145,20 @@ int dmx_plan_set_hamiltonian_groups(dmx_plan* plan, int n_groups, const double* 
  * Execution switches (also per plan - they are read from the plan at launch time, so one plan's setting never changes
  * how another plan runs):
  *   "stream_kernel"   0/1  0 = generic tile kernel for every streaming pass (default 1)
- *   "bulk"            0/1  streaming: cp.async.bulk + mbarrier tile staging, double-buffered persistent CTAs (default 1)
+ *   "bulk"            0-2  streaming tile loads: 1 = one cp.async.bulk + mbarrier per contiguous tile (default), 0 = register
+ *                          staging, 2 = direct global loads in the first sweep
+ *   "direct_store"    0/1  streaming: the last sweep stores its registers straight to HBM where the layout allows (default 1)
+ *   "wide"            0/1  streaming: tile-wide Clifford x Pauli-noise sweeps (default 0: measured slower)
+ *   "scale_smem"      0/1  streaming: scale tables in shared memory instead of the constant bank (default 0: measured slower)
  *   "stream_chunk"    n    circuits per streaming pass launch, 0 = automatic (default 0)
  *   "frame32"         0/1  compact warp-per-circuit frame kernel when <= 32 coefficients are live (default 1)
+ *   "frame32s"        v    sweep form of the frame kernel (one rotation class, no variant table): 0 never, 1 automatic
+ *                          (default: from 2^15 circuits a launch, the fewest circuits per warp - 8 / 16 / 24 / 32 - whose
+ *                          warps are all resident at once), 8 / 16 = 32 circuits per warp advanced 8 / 16 at a time,
+ *                          40 / 48 / 56 / 64 = always 8 / 16 / 24 / 32 circuits per warp
  *   "segment_cpb"     4|8  circuits per warp / thread of the frame kernels (default 8)
  *   "host_zero_copy"  0/1  dmx_energy_batch_host works in place on mapped page-locked buffers (default 1)
+ *   "host_streams"    n    dmx_energy_batch_host_async: consecutive in-flight batches rotate over n streams, 1..8 (default 4)
  *   "host_chunk_rows" n    rows per chunk of the dmx_energy_batch_host DMA pipeline, >= 1024 (default 32768)
  */
 int dmx_plan_set_option(dmx_plan* plan, const char* key, int value);

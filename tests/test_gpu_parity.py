@@ -601,6 +601,21 @@ def test_async_host_call_matches_sync():
     prog.host_sync()
     for o in outs:
         assert np.array_equal(o, want)
+    # in-flight calls rotate over "host_streams" streams: distinct inputs per call, every stream count, full-size batches
+    for streams in (1, 3, 8):
+        prog_s, _ = h2_program(host_streams=streams)
+        ins, outs = [], []
+        for k in range(11):
+            a = engine.pinned_empty((65536, 1))
+            a[:, 0] = np.linspace(-0.5 + 0.01 * k, 0.5, 65536)
+            ins.append(a)
+            outs.append(engine.pinned_empty(65536))
+            outs[-1][:] = 0
+        for a, o in zip(ins, outs):
+            prog_s.energies_host(a, out=o, nowait=True)
+        prog_s.host_sync()
+        for a, o in zip(ins, outs):
+            assert np.array_equal(o, prog_s.energies_host(a))
     # pageable buffers: the async entry point falls back to a synchronous call
     q = np.linspace(-0.4, 0.4, 17).reshape(-1, 1)
     assert np.allclose(prog.energies_host(q, nowait=True), prog.energies_host(q), atol=0, rtol=0)

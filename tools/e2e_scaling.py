@@ -49,9 +49,10 @@ def measure(prog, depth, active=True):
     return float(t.item()) / STEPS * 1e6
 
 
-for zero_copy in (1, 0):
+for zero_copy, streams in ((1, 4), (1, 2), (1, 1), (0, 1)):
     bench.PLAN_OPTIONS.clear()
     bench.PLAN_OPTIONS["host_zero_copy"] = zero_copy
+    bench.PLAN_OPTIONS["host_streams"] = streams
     wl = bench.workload_h2_sweep()
     prog = bench.get_prog(wl)
     for depth in (1, 2, 4, 8):
@@ -60,7 +61,7 @@ for zero_copy in (1, 0):
         all_us = measure(prog, depth)
         solo_us = measure(prog, depth, active=rank == 0)
         if rank == 0:
-            print(f"zero_copy={zero_copy} depth={depth}: all {world} ranks {all_us:7.2f} us/step ({world * B / all_us * 1e6:.3e} circuits/s)   "
+            print(f"zero_copy={zero_copy} streams={streams} depth={depth}: all {world} ranks {all_us:7.2f} us/step ({world * B / all_us * 1e6:.3e} circuits/s)   "
                   f"rank 0 alone {solo_us:7.2f} us/step ({B / solo_us * 1e6:.3e})", flush=True)
 if world > 1:
     dist.destroy_process_group()

@@ -618,6 +618,7 @@ struct Frame32Args {
     const unsigned char* partner; // [nseg][32] partner lane | 0x80 (rotation moves this coefficient)
     const int* cs_sel;            // [nseg] rotation class or < 0 (constant coefficients)
     const RotInfo* classes;
+    RotInfo cls0;                 // classes[0] by value (CSMODE 1 reads the angle without a dependent table load)
     const double* init;           // [32]
     const double* eweight;        // [groups][32]
     const int* group;             // optional coefficient row per circuit
@@ -669,6 +670,17 @@ __global__ void __launch_bounds__(256, DMX_F32_MINB) dmx_frame32_kernel(const Fr
     double* sw1 = reinterpret_cast<double*>(smem_base + off_sw + (unsigned)a.nseg * 32u * 16u);     // [nseg][32] w1
     unsigned char* spart = smem_base + off_sw + (unsigned)a.nseg * 32u * 24u;
     int* ssel = reinterpret_cast<int*>(smem_base + off_sw + (unsigned)a.nseg * 32u * 25u);
+    // Every first-touch load of a launch misses to HBM (the tables are a few KB, but a sweep step starts cold), so the
+    // lane constants and the first round's angle are requested BEFORE the staging loop and its barrier: one DRAM round
+    // trip for all of them instead of one per dependent level (tables -> barrier -> constants -> class -> angle).
+    const double init = a.init[lane];
+    const double ew0 = a.eweight[lane];
+    const int orig_l = a.orig[lane];
+    double x_first = 0.0;
+    if (CSMODE == 1 && !(!VAR && a.stage_io)) {
+        const long long bf = ((long long)blockIdx.x * 8 + warp) * CPB + lane;
+        if (lane < CPB && bf < a.batch) x_first = a.params[bf * a.n_params + a.cls0.param];
+    }
     for (int i = threadIdx.x; i < a.nseg * 32; i += 256) {
         const double2 w = a.w[i];
         const unsigned char pbyte = a.partner[i];
@@ -688,14 +700,12 @@ __global__ void __launch_bounds__(256, DMX_F32_MINB) dmx_frame32_kernel(const Fr
     double* const io = reinterpret_cast<double*>(smem_base);                 // [8 * CPB] angles in, energies out
     if (STAGE_IO && threadIdx.x < 8 * CPB) {
         const long long b = (long long)blockIdx.x * 8 * CPB + threadIdx.x;
-        io[threadIdx.x] = b < a.batch ? a.params[b * a.n_params + a.classes[0].param] : 0.0;
+        io[threadIdx.x] = b < a.batch ? a.params[b * a.n_params + a.cls0.param] : 0.0;
     }
     __syncthreads();
     const long long ngroups = (a.batch + CPB - 1) / CPB;
     const long long gwarp = (long long)blockIdx.x * 8 + warp, nwarps = (long long)gridDim.x * 8;
-    const double init = a.init[lane];
-    const double ew0 = a.eweight[lane];
-    const int p = a.orig[lane] < 0 ? 0 : a.orig[lane];
+    const int p = orig_l < 0 ? 0 : orig_l;
 
     // Every warp runs the same number of rounds (rows past the batch are predicated off at the loads and stores): with a
     // trip count that depends only on kernel parameters the compiler can prove the warp converged and emits bare SHFLs
@@ -711,8 +721,8 @@ __global__ void __launch_bounds__(256, DMX_F32_MINB) dmx_frame32_kernel(const Fr
             // at the barrier behind a DRAM round trip plus a sincos, and the kernel spills at 64 registers.)
             double sv = 0.0, cv = 1.0;
             if (lane < CPB && b0 + lane < a.batch) {
-                const RotInfo ri = a.classes[0];
-                const double x = (STAGE_IO && it == 0) ? io[warp * CPB + lane] : a.params[(b0 + lane) * a.n_params + ri.param];
+                const RotInfo ri = a.cls0;
+                const double x = it == 0 ? (STAGE_IO ? io[warp * CPB + lane] : x_first) : a.params[(b0 + lane) * a.n_params + ri.param];
                 sincos(ri.scale * x + ri.offset, &sv, &cv);
             }
 #pragma unroll
@@ -891,13 +901,14 @@ __global__ void __launch_bounds__(256, DMX_F32_MINB) dmx_frame32_kernel(const Fr
 
 // ---------------------------------------------------------------------------------------------------------
 // frame32, sweep form ("frame32s"): parameter sweeps of a plan with ONE rotation class and no variant table (the noisy
-// H2 UCCSD energy sweep, BASELINE configs[1]).  A warp owns 32 consecutive circuits: one coalesced 256-byte parameter
-// load, ONE sincos for all 32 lanes (the 8-circuit kernel above spends a third of its FP64 instructions on a sincos that
-// only 8 lanes use), then four rounds of 8 circuits through the segment tables (read through L1: no staging, no block
-// barrier), and one coalesced 256-byte store of the 32 energies.  Table entry per (segment, lane): (wc, wk, w1, partner).
+// H2 UCCSD energy sweep, BASELINE configs[1]).  A warp owns cw = 32 (or 16 / 8) consecutive circuits: one coalesced
+// parameter load, ONE sincos for cw lanes (the 8-circuit kernel above spends a third of its instructions on a sincos that
+// only 8 lanes use), then cw / 8 rounds of 8 circuits through the segment tables (read through L1: no staging, no block
+// barrier), and one coalesced store of the cw energies.  Table entry per (segment, lane): (wc, wk, w1, partner).
 // ---------------------------------------------------------------------------------------------------------
 struct Frame32sArgs {
     int nseg, n_params;
+    int cw;                       // circuits per warp: 32 (large batches), or 16 / 8 so that a mid-size batch still fills the SMs
     long long batch;
     const double4* tab;           // [nseg][32]: x = wc, y = wk (own-coefficient factor = fma(wc, cos, wk)), z = w1, w = partner lane (bits)
     RotInfo cls;                  // the single rotation class
@@ -910,25 +921,30 @@ struct Frame32sArgs {
 
 template <int CPB>      // circuits advanced together by one warp: 8 (four rounds per warp) or 16 (two rounds, twice the ILP)
 __global__ void __launch_bounds__(64) dmx_frame32s_kernel(const Frame32sArgs a) {
-    constexpr int NSUB = 32 / CPB, LPC = 32 / CPB;
+    constexpr int LPC = 32 / CPB;
     const int lane = threadIdx.x & 31;
+    const int nsub = a.cw / CPB;      // kernel parameter: uniform, the shuffles below stay bare
 
     const long long w = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    const long long b = w * 32 + lane;
+    const long long b = w * a.cw + lane;
+    const bool mine_row = lane < a.cw && b < a.batch;
+    // the segment table is read one entry ahead in the loop below; on a cold launch that is nseg serial DRAM round trips
+    // for the first warps of every SM, so ask for all of it up front (a.nseg prefetches per lane, no registers held)
+    for (int k = 0; k < a.nseg; ++k) asm volatile("prefetch.global.L1 [%0];" :: "l"(a.tab + k * 32 + lane));
     // rows past the batch are predicated off at the load and the store: every warp runs the same instruction stream, so
     // the shuffles need no convergence barrier
     double sv = 0.0, cv = 1.0;
     {
         double theta = a.cls.offset;
-        if (b < a.batch) theta = fma(a.cls.scale, a.params[b * a.n_params + a.cls.param], a.cls.offset);
+        if (mine_row) theta = fma(a.cls.scale, a.params[b * a.n_params + a.cls.param], a.cls.offset);
         sincos(theta, &sv, &cv);
     }
     const double init = __ldg(a.init + lane);
     const double ew0 = __ldg(a.eweight + lane);
-    const int g_lane = (a.group && b < a.batch) ? a.group[b] : 0;
+    const int g_lane = (a.group && mine_row) ? a.group[b] : 0;
     double eout = 0.0;
 #pragma unroll 1
-    for (int sub = 0; sub < NSUB; ++sub) {
+    for (int sub = 0; sub < nsub; ++sub) {
         double2 csr[CPB];
 #pragma unroll
         for (int c = 0; c < CPB; ++c) csr[c] = make_double2(__shfl_sync(0xffffffffu, cv, sub * CPB + c), __shfl_sync(0xffffffffu, sv, sub * CPB + c));
@@ -978,7 +994,7 @@ __global__ void __launch_bounds__(64) dmx_frame32s_kernel(const Frame32sArgs a) 
         const double mine = __shfl_sync(0xffffffffu, e[0], (lane & (CPB - 1)) * LPC);
         if (lane / CPB == sub) eout = mine;
     }
-    if (b < a.batch) a.out[b] = eout;
+    if (mine_row) a.out[b] = eout;
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -1295,6 +1311,9 @@ struct DevPlan {
     cudaStream_t stream = nullptr, s_in = nullptr, s_out = nullptr;   // host-buffer API: compute / copy-in / copy-out
     static constexpr int MAX_CHUNKS = 8;
     cudaEvent_t ev_in[MAX_CHUNKS] = {}, ev_k[MAX_CHUNKS] = {};
+    static constexpr int MAX_XS = 8;     // streams the asynchronous host calls rotate over
+    cudaStream_t xs[MAX_XS] = {};
+    unsigned async_calls = 0;
     void* h_stage = nullptr; size_t h_cap = 0;
     void* d_stage = nullptr; size_t d_cap = 0;
     std::mutex mu;       // host-buffer API staging (held for the whole dmx_energy_batch_host call)
@@ -1735,6 +1754,7 @@ static void free_devplan(DevPlan* d) {
     cudaFree(d->slots); cudaFree(d->labels);
     cudaFree(d->g_tab4); cudaFree(d->g_w); cudaFree(d->g_partner); cudaFree(d->g_cs_sel); cudaFree(d->g_init); cudaFree(d->g_ew); cudaFree(d->g_orig);
     for (auto& px : d->passx) cudaFree(px.coefs);
+    for (int i = 0; i < DevPlan::MAX_XS; ++i) if (d->xs[i]) cudaStreamDestroy(d->xs[i]);
     if (d->h_stage) cudaFreeHost(d->h_stage);
     if (d->d_stage) cudaFree(d->d_stage);
     if (d->stream) {
@@ -2095,22 +2115,43 @@ static int run_segment(Plan& p, DevPlan* d, long long batch, const double* param
         g.orig = d->g_orig; g.params = params; g.variants = variants; g.slots = d->slots; g.labels = d->labels; g.coefs = d->coefs;
         g.out = out; g.worklist = a.worklist; g.work_count = a.work_count; g.group = group;
         g.any_const = 0;
+        if (!p.f_classes.empty()) g.cls0 = p.f_classes[0];
         for (int k = 0; k < p.nseg; ++k) g.any_const |= p.fsegs[k].cs_sel < 0;
         g.stage_io = host_mapped ? 1 : 0;
         // Measured on B200 (profiles/r2_frame32s_ab.txt): 14 warps per SM leave the issue slots idle at the BASELINE batch
         // (65 536 circuits: 20.4 us against 18.6 us for the 8-circuit kernel with its 32 warps per SM), but from ~5e5
         // circuits per launch the leaner instruction stream wins (2^20: 6.45e9 against 5.99e9 circuits/s, 2^22: 6.87e9
         // against 6.27e9).  opt_frame32s: 0 never, 1 automatic (large batches), 8 / 16 always with that many circuits a round.
-        const bool sweep_form = p.opt_frame32s > 1 || (p.opt_frame32s == 1 && batch >= (1 << 19));
-        if (sweep_form && mode == 1 && !variants && !g.any_const) {
-            // parameter sweep with one rotation class: 32 circuits per warp (dmx_frame32s_kernel)
+        // Mid-size batches (round 2, second pass): the BASELINE batch is 8192 warp-rounds of the 8-circuit kernel = 1.7 waves
+        // of the 4736 resident warps, each paying a sincos that 8 lanes use; with 24 circuits per warp it is 2731 warps -
+        // one wave - and a third of the sincos work.  opt_frame32s: 0 never, 1 automatic (from 2^15 circuits a launch),
+        // 8 / 16 always 32 circuits per warp with that many advanced together, 32 + cw: always cw circuits per warp
+        // (cw = 8 / 16 / 24 / 32).
+        int cw = 0, cpb = 8;
+        if (p.opt_frame32s == 1 && batch >= (1 << 15)) {
+            // fewest circuits per warp (most parallelism) whose warps are all resident at once
+            static int warps_per_sm = 0;
+            if (!warps_per_sm) {
+                int ctas = 0;
+                CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas, dmx_frame32s_kernel<8>, 64, 0));
+                warps_per_sm = std::max(2, 2 * ctas);
+            }
+            const long long resident = (long long)d->sm_count * warps_per_sm;
+            cw = 32;
+            for (int c = 8; c < 32; c += 8)
+                if ((batch + c - 1) / c <= resident) { cw = c; break; }
+        }
+        else if (p.opt_frame32s == 8 || p.opt_frame32s == 16) { cw = 32; cpb = p.opt_frame32s; }
+        else if (p.opt_frame32s > 32) cw = p.opt_frame32s - 32;
+        if (cw && mode == 1 && !variants && !g.any_const) {
+            // parameter sweep with one rotation class (dmx_frame32s_kernel)
             Frame32sArgs f{};
-            f.nseg = p.nseg; f.n_params = p.n_params; f.batch = batch; f.tab = d->g_tab4; f.cls = p.f_classes[0];
+            f.nseg = p.nseg; f.n_params = p.n_params; f.cw = cw; f.batch = batch; f.tab = d->g_tab4; f.cls = p.f_classes[0];
             f.init = d->g_init; f.eweight = d->g_ew; f.group = group; f.params = params; f.out = out;
-            const long long warps = (batch + 31) / 32;
+            const long long warps = (batch + cw - 1) / cw;
             const long long grid = (warps + 1) / 2;
             if (grid >= (1LL << 31)) return done(fail(DMX_ERR_UNSUPPORTED, "batch too large for one launch"));
-            if (p.opt_frame32s == 16) dmx_frame32s_kernel<16><<<(unsigned)grid, 64, 0, st>>>(f);
+            if (cpb == 16) dmx_frame32s_kernel<16><<<(unsigned)grid, 64, 0, st>>>(f);
             else dmx_frame32s_kernel<8><<<(unsigned)grid, 64, 0, st>>>(f);
             ++g_launches;
             CUDA_TRY(cudaGetLastError());
@@ -2203,6 +2244,9 @@ int dmx_plan_set_option(dmx_plan* plan, const char* key, int value) {
         plan->p.opt_stream_chunk = value;
     } else if (k == "host_zero_copy") {
         plan->p.opt_host_zero_copy = value != 0;
+    } else if (k == "host_streams") {
+        if (value < 1 || value > DevPlan::MAX_XS) return fail(DMX_ERR_INVALID, "host_streams must be in 1..8");
+        plan->p.opt_host_streams = value;
     } else if (k == "host_chunk_rows") {
         if (value < 1024) return fail(DMX_ERR_INVALID, "host_chunk_rows must be >= 1024");
         plan->p.opt_host_chunk_rows = value;
@@ -2215,7 +2259,8 @@ int dmx_plan_set_option(dmx_plan* plan, const char* key, int value) {
         if (value < 0 || value > 2) return fail(DMX_ERR_INVALID, "bulk must be 0 (register staging), 1 (cp.async.bulk) or 2 (direct global loads)");
         plan->p.opt_bulk = value;
     } else if (k == "frame32s") {
-        if (value != 0 && value != 1 && value != 8 && value != 16) return fail(DMX_ERR_INVALID, "frame32s must be 0, 1 (= 8), 8 or 16");
+        if (value != 0 && value != 1 && value != 8 && value != 16 && value != 40 && value != 48 && value != 56 && value != 64)
+            return fail(DMX_ERR_INVALID, "frame32s must be 0, 1 (automatic), 8, 16 or 32 + circuits per warp (40, 48, 56, 64)");
         plan->p.opt_frame32s = value;
     } else if (k == "wide") {
         plan->p.opt_wide = value != 0;
@@ -2539,6 +2584,7 @@ int dmx_plan_host_sync(dmx_plan* plan) {
     if (!d || !d->stream) return DMX_OK;       // nothing was ever queued
     std::lock_guard<std::mutex> lock(d->mu);
     CUDA_TRY(cudaStreamSynchronize(d->stream));
+    for (int i = 0; i < DevPlan::MAX_XS; ++i) if (d->xs[i]) CUDA_TRY(cudaStreamSynchronize(d->xs[i]));
     return DMX_OK;
 }
 
@@ -2571,8 +2617,19 @@ static int energy_batch_host_impl(dmx_plan* plan, int64_t batch, const double* h
         const double* const p_dev = h_params ? (const double*)mapped_alias(h_params) : nullptr;
         const int* const g_dev = h_group ? (const int*)mapped_alias(h_group) : nullptr;
         if (e_dev && (p_dev || !h_params) && (g_dev || !h_group)) {
+            if (!wait) {
+                // dmx_energy_batch_host_async: consecutive batches rotate over a few streams, so the 1.7-wave tail of one
+                // launch overlaps the head of the next (they are independent: every call has its own result buffer); the
+                // caller collects with dmx_plan_host_sync
+                cudaStream_t xs = d->stream;
+                if (p.opt_host_streams > 1) {
+                    const int slot = (int)(d->async_calls++ % (unsigned)std::min(p.opt_host_streams, DevPlan::MAX_XS));
+                    if (!d->xs[slot]) CUDA_TRY(cudaStreamCreateWithFlags(&d->xs[slot], cudaStreamNonBlocking));
+                    xs = d->xs[slot];
+                }
+                return energy_impl(plan, batch, p_dev, nullptr, e_dev, nullptr, 0, xs, g_dev, true);
+            }
             rc = energy_impl(plan, batch, p_dev, nullptr, e_dev, nullptr, 0, d->stream, g_dev, true);
-            if (!wait) return rc;            // dmx_energy_batch_host_async: the caller collects with dmx_plan_host_sync
             const cudaError_t e = cudaStreamSynchronize(d->stream);
             if (rc) return rc;
             CUDA_TRY(e);

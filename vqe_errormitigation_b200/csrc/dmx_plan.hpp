@@ -187,6 +187,7 @@ struct Plan {
     int opt_stream_kernel = 1;          // 0 -> generic dmx_tile_kernel for every streaming pass
     long long opt_stream_chunk = 0;     // circuits per streaming pass launch (0: automatic)
     int opt_host_zero_copy = 1;         // dmx_energy_batch_host works in place on mapped page-locked buffers
+    int opt_host_streams = 4;           // dmx_energy_batch_host_async: streams consecutive in-flight batches rotate over
     long long opt_host_chunk_rows = 32768;
     int opt_frame32 = 1;                // compact warp-per-circuit frame kernel when <= 32 coefficients are live
     int opt_frame32s = 1;               // one-rotation-class parameter sweeps: 32 circuits per warp (dmx_frame32s_kernel)

@@ -261,9 +261,10 @@ class CircuitProgram:
         return C.c_void_p(t.data_ptr()) if t is not None else None
 
     def energies(self, params=None, variants=None, *, batch: Optional[int] = None, out=None, workspace_states: Optional[int] = None,
-                 groups=None):
-        """Re Tr(rho_b H) for every row; returns a CUDA float64 tensor [B] (async on the current stream).  ``groups[B]``
-        (int32): coefficient row of every circuit for programs built with ``coefficient_groups``."""
+                 groups=None, stream=None):
+        """Re Tr(rho_b H) for every row; returns a CUDA float64 tensor [B] (async on the current stream, or on ``stream`` -
+        a ``torch.cuda.Stream`` or a raw ``cudaStream_t`` value; independent batches on different streams overlap).
+        ``groups[B]`` (int32): coefficient row of every circuit for programs built with ``coefficient_groups``."""
         if not self.has_hamiltonian:
             raise ValueError("program was built without a Hamiltonian")
         torch, dev, p_t, v_t, B = self._prep(params, variants, batch)
@@ -276,7 +277,13 @@ class CircuitProgram:
             states = workspace_states if workspace_states else min(B, 64)
             nbytes = int(self.info["workspace_bytes_per_state"]) * states
         ws = self._ws(torch, dev, nbytes)
-        stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+        if stream is None:
+            stream = torch.cuda.current_stream().cuda_stream
+        elif not isinstance(stream, int):
+            stream = stream.cuda_stream
+        if nbytes and stream != torch.cuda.current_stream().cuda_stream:
+            raise ValueError("streaming plans share one workspace: run them on the current stream")
+        stream = C.c_void_p(stream)
         if groups is not None:
             g_t = torch.as_tensor(groups, device=dev).to(torch.int32).contiguous()
             if g_t.numel() != B:
