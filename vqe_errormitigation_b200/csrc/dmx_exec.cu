@@ -908,7 +908,8 @@ __global__ void __launch_bounds__(256, DMX_F32_MINB) dmx_frame32_kernel(const Fr
 // ---------------------------------------------------------------------------------------------------------
 struct Frame32sArgs {
     int nseg, n_params;
-    int cw;                       // circuits per warp: 32 (large batches), or 16 / 8 so that a mid-size batch still fills the SMs
+    int cw;                       // circuits per warp: 32 (large batches), or 24 / 16 / 8 so that a mid-size batch still fills the SMs
+    int stage_io;                 // parameters / energies are mapped HOST memory: one contiguous block per CTA through shared memory
     long long batch;
     const double4* tab;           // [nseg][32]: x = wc, y = wk (own-coefficient factor = fma(wc, cos, wk)), z = w1, w = partner lane (bits)
     RotInfo cls;                  // the single rotation class
@@ -919,8 +920,10 @@ struct Frame32sArgs {
     double* out;
 };
 
-template <int CPB>      // circuits advanced together by one warp: 8 (four rounds per warp) or 16 (two rounds, twice the ILP)
-__global__ void __launch_bounds__(64) dmx_frame32s_kernel(const Frame32sArgs a) {
+// Four CTAs per SM (126 registers): measured against six (80 registers) and eight (64, spilling) CTAs per SM on the H2 sweep,
+// isolated launch 18.4 / 18.6 / 18.9 us, streamed 7.66e9 / 7.00e9 / 6.52e9 circuits/s (profiles/r2_frame32s_ab.txt).
+template <int CPB>      // circuits advanced together by one warp: 8 or 16 (twice the ILP, 128 registers)
+__global__ void __launch_bounds__(128, 4) dmx_frame32s_kernel(const Frame32sArgs a) {
     constexpr int LPC = 32 / CPB;
     const int lane = threadIdx.x & 31;
     const int nsub = a.cw / CPB;      // kernel parameter: uniform, the shuffles below stay bare
@@ -928,21 +931,41 @@ __global__ void __launch_bounds__(64) dmx_frame32s_kernel(const Frame32sArgs a) 
     const long long w = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const long long b = w * a.cw + lane;
     const bool mine_row = lane < a.cw && b < a.batch;
-    // the segment table is read one entry ahead in the loop below; on a cold launch that is nseg serial DRAM round trips
-    // for the first warps of every SM, so ask for all of it up front (a.nseg prefetches per lane, no registers held)
-    for (int k = 0; k < a.nseg; ++k) asm volatile("prefetch.global.L1 [%0];" :: "l"(a.tab + k * 32 + lane));
+    // Segment table -> shared memory, as two planes of double2 ((wc, wk) and (w1, partner)) so that each LDS.128 of the loop
+    // below is conflict-free.  All of a thread's loads are independent: one DRAM round trip on a cold launch.  (Reading the
+    // table through L1 instead made every segment of every round wait for a load - 20.5 us per 65 536 circuits whatever
+    // the circuits per warp; prefetch.global.L1 ahead of the loop was worse still, 24.8 - 30.5 us: profiles/r2_frame32s_ab.txt.)
+    double2* const tabA = reinterpret_cast<double2*>(dmx_smem);
+    double2* const tabB = tabA + a.nseg * 32;
+    // Mapped host buffers (zero-copy end-to-end calls): the CTA's 4 cw circuits are consecutive rows, so their angles come
+    // in - and their energies go out - as ONE contiguous block of up to 1 KB per CTA through `io` instead of one partial
+    // line per warp (PCIe transaction rate, see dmx_frame32_kernel); the table barrier below covers the inbound block.
+    double* const io = reinterpret_cast<double*>(tabB + a.nseg * 32);          // [128]
+    const long long row_t = (long long)blockIdx.x * 4 * a.cw + threadIdx.x;
+    const bool mine_t = (int)threadIdx.x < 4 * a.cw && row_t < a.batch;
+    double x = 0.0;
+    if (a.stage_io) { if (mine_t) io[threadIdx.x] = a.params[row_t * a.n_params + a.cls.param]; }
+    else if (mine_row) x = a.params[b * a.n_params + a.cls.param];
+    {
+        const double2* const src = reinterpret_cast<const double2*>(a.tab);
+        for (int i = threadIdx.x; i < a.nseg * 32; i += blockDim.x) {
+            tabA[i] = __ldg(src + 2 * i);
+            tabB[i] = __ldg(src + 2 * i + 1);
+        }
+    }
     // rows past the batch are predicated off at the load and the store: every warp runs the same instruction stream, so
     // the shuffles need no convergence barrier
-    double sv = 0.0, cv = 1.0;
-    {
-        double theta = a.cls.offset;
-        if (mine_row) theta = fma(a.cls.scale, a.params[b * a.n_params + a.cls.param], a.cls.offset);
-        sincos(theta, &sv, &cv);
-    }
     const double init = __ldg(a.init + lane);
     const double ew0 = __ldg(a.eweight + lane);
     const int g_lane = (a.group && mine_row) ? a.group[b] : 0;
+    if (a.stage_io) {
+        __syncthreads();
+        if (mine_row) x = io[(threadIdx.x >> 5) * a.cw + lane];
+    }
+    double sv, cv;
+    sincos(fma(a.cls.scale, x, a.cls.offset), &sv, &cv);
     double eout = 0.0;
+    if (!a.stage_io) __syncthreads();       // table staged (the angle load and the sincos overlap the staging loads of the other warps)
 #pragma unroll 1
     for (int sub = 0; sub < nsub; ++sub) {
         double2 csr[CPB];
@@ -951,9 +974,8 @@ __global__ void __launch_bounds__(64) dmx_frame32s_kernel(const Frame32sArgs a) 
         double r[CPB];
 #pragma unroll
         for (int c = 0; c < CPB; ++c) r[c] = init;
-        const double2* const tab2 = reinterpret_cast<const double2*>(a.tab);
         auto entry = [&](int k) {
-            const double2 lo = __ldg(tab2 + 2 * (k * 32 + lane)), hi = __ldg(tab2 + 2 * (k * 32 + lane) + 1);
+            const double2 lo = tabA[k * 32 + lane], hi = tabB[k * 32 + lane];
             return make_double4(lo.x, lo.y, hi.x, hi.y);
         };
         double4 t_n = a.nseg > 0 ? entry(0) : make_double4(0.0, 1.0, 0.0, 0.0);
@@ -994,7 +1016,13 @@ __global__ void __launch_bounds__(64) dmx_frame32s_kernel(const Frame32sArgs a) 
         const double mine = __shfl_sync(0xffffffffu, e[0], (lane & (CPB - 1)) * LPC);
         if (lane / CPB == sub) eout = mine;
     }
-    if (mine_row) a.out[b] = eout;
+    if (a.stage_io) {
+        if (lane < a.cw) io[(threadIdx.x >> 5) * a.cw + lane] = eout;      // each warp overwrites only the angles it read itself
+        __syncthreads();
+        if (mine_t) a.out[row_t] = io[threadIdx.x];
+    } else if (mine_row) {
+        a.out[b] = eout;
+    }
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -1311,6 +1339,7 @@ struct DevPlan {
     cudaStream_t stream = nullptr, s_in = nullptr, s_out = nullptr;   // host-buffer API: compute / copy-in / copy-out
     static constexpr int MAX_CHUNKS = 8;
     cudaEvent_t ev_in[MAX_CHUNKS] = {}, ev_k[MAX_CHUNKS] = {};
+    int f32s_warps_per_sm = 0;           // resident warps of dmx_frame32s_kernel with this plan's table (occupancy query, once)
     static constexpr int MAX_XS = 8;     // streams the asynchronous host calls rotate over
     cudaStream_t xs[MAX_XS] = {};
     unsigned async_calls = 0;
@@ -2118,41 +2147,42 @@ static int run_segment(Plan& p, DevPlan* d, long long batch, const double* param
         if (!p.f_classes.empty()) g.cls0 = p.f_classes[0];
         for (int k = 0; k < p.nseg; ++k) g.any_const |= p.fsegs[k].cs_sel < 0;
         g.stage_io = host_mapped ? 1 : 0;
-        // Measured on B200 (profiles/r2_frame32s_ab.txt): 14 warps per SM leave the issue slots idle at the BASELINE batch
-        // (65 536 circuits: 20.4 us against 18.6 us for the 8-circuit kernel with its 32 warps per SM), but from ~5e5
-        // circuits per launch the leaner instruction stream wins (2^20: 6.45e9 against 5.99e9 circuits/s, 2^22: 6.87e9
-        // against 6.27e9).  opt_frame32s: 0 never, 1 automatic (large batches), 8 / 16 always with that many circuits a round.
-        // Mid-size batches (round 2, second pass): the BASELINE batch is 8192 warp-rounds of the 8-circuit kernel = 1.7 waves
-        // of the 4736 resident warps, each paying a sincos that 8 lanes use; with 24 circuits per warp it is 2731 warps -
-        // one wave - and a third of the sincos work.  opt_frame32s: 0 never, 1 automatic (from 2^15 circuits a launch),
-        // 8 / 16 always 32 circuits per warp with that many advanced together, 32 + cw: always cw circuits per warp
-        // (cw = 8 / 16 / 24 / 32).
+        // Sweep form (dmx_frame32s_kernel) from 2^15 circuits a launch.  Measured on B200 (profiles/r2_frame32s_ab.txt, tables
+        // staged in shared memory): the H2 sweep streams at 7.7e9 circuits/s against 6.2e9 for the 8-circuit kernel (whose warps
+        // each pay a sincos that 8 lanes use); an isolated 65 536-circuit launch reads 18.4 us with either - that figure is
+        // the event pair, the launch latency and one warp's critical path (tools/launch_floor.py), not the kernel.
+        // opt_frame32s: 0 never, 1 automatic, 8 / 16 always 32 circuits per warp with that many advanced together,
+        // 32 + cw: always cw circuits per warp (cw = 8 / 16 / 24 / 32).
         int cw = 0, cpb = 8;
-        if (p.opt_frame32s == 1 && batch >= (1 << 15)) {
+        const int f32s_opt = p.opt_frame32s;
+        // (mapped host buffers stay on the 8-circuit kernel: its 1024 CTAs each moving a 512-byte block keep more PCIe reads in
+        // flight than 512 CTAs moving 1 KB - 4.38e9 against 3.96e9 circuits/s end to end)
+        if (f32s_opt == 1 && batch >= (1 << 15) && !host_mapped) {
             // fewest circuits per warp (most parallelism) whose warps are all resident at once
-            static int warps_per_sm = 0;
-            if (!warps_per_sm) {
+            if (!d->f32s_warps_per_sm) {
                 int ctas = 0;
-                CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas, dmx_frame32s_kernel<8>, 64, 0));
-                warps_per_sm = std::max(2, 2 * ctas);
+                CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas, dmx_frame32s_kernel<8>, 128, (size_t)p.nseg * 1024 + 1024));
+                d->f32s_warps_per_sm = std::max(4, 4 * ctas);
             }
-            const long long resident = (long long)d->sm_count * warps_per_sm;
+            const long long resident = (long long)d->sm_count * d->f32s_warps_per_sm;
             cw = 32;
             for (int c = 8; c < 32; c += 8)
                 if ((batch + c - 1) / c <= resident) { cw = c; break; }
         }
-        else if (p.opt_frame32s == 8 || p.opt_frame32s == 16) { cw = 32; cpb = p.opt_frame32s; }
-        else if (p.opt_frame32s > 32) cw = p.opt_frame32s - 32;
-        if (cw && mode == 1 && !variants && !g.any_const) {
+        else if (f32s_opt == 8 || f32s_opt == 16) { cw = 32; cpb = f32s_opt; }
+        else if (f32s_opt > 32) cw = f32s_opt - 32;
+        if (cw && mode == 1 && !variants && !g.any_const && p.nseg <= 44) {
             // parameter sweep with one rotation class (dmx_frame32s_kernel)
             Frame32sArgs f{};
             f.nseg = p.nseg; f.n_params = p.n_params; f.cw = cw; f.batch = batch; f.tab = d->g_tab4; f.cls = p.f_classes[0];
             f.init = d->g_init; f.eweight = d->g_ew; f.group = group; f.params = params; f.out = out;
+            f.stage_io = host_mapped ? 1 : 0;
             const long long warps = (batch + cw - 1) / cw;
-            const long long grid = (warps + 1) / 2;
+            const long long grid = (warps + 3) / 4;
+            const size_t smem = (size_t)p.nseg * 1024 + 1024;   // tables + io block, <= 45 KB: inside the default dynamic limit
             if (grid >= (1LL << 31)) return done(fail(DMX_ERR_UNSUPPORTED, "batch too large for one launch"));
-            if (cpb == 16) dmx_frame32s_kernel<16><<<(unsigned)grid, 64, 0, st>>>(f);
-            else dmx_frame32s_kernel<8><<<(unsigned)grid, 64, 0, st>>>(f);
+            if (cpb == 16) dmx_frame32s_kernel<16><<<(unsigned)grid, 128, smem, st>>>(f);
+            else dmx_frame32s_kernel<8><<<(unsigned)grid, 128, smem, st>>>(f);
             ++g_launches;
             CUDA_TRY(cudaGetLastError());
             return done(DMX_OK);
