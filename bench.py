@@ -7,7 +7,9 @@
 Default workload = BASELINE.json configs[1]: H2 STO-3G 4-qubit UCCSD ansatz, depolarize(1e-3) after every 1-qubit
 gate and TwoQubitDepolarizingChannel(1e-3) after every CNOT, parameter sweep of 65,536 circuits per launch.  A
 "step" is one launch of the hot path over one batch; inputs are resident in HBM for `value`, in host memory for
-`e2e` (dmx_energy_batch_host: H2D + kernels + D2H inside the timed region).  Multi-GPU: one process per GPU
+`e2e` (dmx_energy_batch_host: H2D + kernels + D2H inside the timed region).  Microsecond-scale steps are timed as ONE
+event region around the K steps (queued back to back over four streams, inputs cycled past the L2); the per-step-event
+figure of round 1 is kept as `isolated` (see run_workload and tools/launch_floor.py for why).  Multi-GPU: one process per GPU
 (torchrun), the batch is weak-scaled (each rank owns its own 65,536 circuits), no data-path collective
 (independent circuits) — time is max over ranks.
 
@@ -844,6 +846,8 @@ def run_workload(wl, ctx, steps: int, warmup: int, with_cpu_baseline: bool, with
     kernel_s = ms_per_step * 1e-3
     kern = {0: "dmx_tile_kernel", 1: "dmx_frame32_kernel (dmx_frame_kernel when more than 32 coefficients are live)",
             2: "dmx_stream3_kernel / dmx_stream3b_kernel (streaming passes)"}[info["path"]]
+    if info["path"] == 1 and variants_h is None and info["n_params"] == 1 and B >= 32768 and PLAN_OPTIONS.get("frame32s", 1) != 0:
+        kern = "dmx_frame32s_kernel (sweep form of the frame kernel: 32 circuits per warp, tables in shared memory)"
     traffic = ncu_util = None
     tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
     if os.path.exists(tpath):

@@ -73,6 +73,23 @@ def test_round2_default_record_carries_every_config_and_parity():
     assert also["h2_qem"]["estimator"]["value"] > 0 and also["h2_qem"]["e2e"]["unique_rows"] < also["h2_qem"]["e2e"]["rows_represented"]
 
 
+def test_round2_streamed_protocol_record():
+    """Second half of round 2: microsecond-scale workloads time their K steps in ONE event region (4 streams, distinct buffers
+    cycled past the L2); the per-step-event figure stays as `isolated` and must be the smaller one."""
+    d = load("r2_bench_default_v4.json")
+    assert [k for k in BASE if k not in d] == []
+    assert d["parity_max_abs_err"] < 1e-10 and d["gpu_launches"] == d["steps"]
+    assert "ONE pair of CUDA events" in d["config"]["timing"] and "L2" in d["config"]["l2"]
+    assert 0 < d["isolated"]["value"] < d["value"] and d["isolated"]["steps"] >= 1
+    assert abs(d["ms_per_step"] * 1e-3 * d["value"] - 65536) < 1.0          # value = batch / step time
+    assert d["e2e"]["in_flight"] >= 8 and d["e2e"]["streams"] == 4 and d["e2e"]["value"] > d["e2e"]["synchronous"]["value"]
+    for key in ("h2_qem", "h2_bonds", "swap7_qem"):
+        rec = d["also"][key]
+        assert rec["isolated"]["value"] <= rec["value"] * 1.05 and rec["parity_max_abs_err"] < 1e-10
+    for key in ("hea10", "lih12"):
+        assert "isolated" not in d["also"][key]                              # streaming steps keep per-step events
+
+
 def test_round2_multi_gpu_records():
     for name, n in (("r2_bench_default_n2_v1.json", 2), ("r2_bench_default_n8_v2.json", 8)):
         d = load(name)
