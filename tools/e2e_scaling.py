@@ -1,6 +1,7 @@
 """End-to-end host-call study under torchrun (one rank per GPU): the noisy-H2 sweep through dmx_energy_batch_host with
 page-locked buffers, for several in-flight depths and transfer modes, all ranks active and rank 0 alone.
-    torchrun --nproc-per-node N tools/e2e_scaling.py"""
+    torchrun --nproc-per-node N tools/e2e_scaling.py [quick]
+DMX_BENCH_NUMA=0 switches the NUMA-local core pinning of bench.pin_rank_to_cores off (even split of the allowed cores)."""
 import os
 import sys
 import time
@@ -14,11 +15,15 @@ import bench
 from vqe_errormitigation_b200 import engine
 
 rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
-if world > 1:
-    bench.pin_rank_to_cores(local, world)
+pinned = bench.pin_rank_to_cores(local, world) if world > 1 else (None, None)
 torch.cuda.set_device(local)
 if world > 1:
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    rows = [None] * world
+    dist.all_gather_object(rows, (rank, pinned, sorted(os.sched_getaffinity(0))[:3]))
+    if rank == 0:
+        print("pinning (rank, (cores, numa node), first cores):", rows, flush=True)
+QUICK = len(sys.argv) > 1 and sys.argv[1] == "quick"
 B, STEPS = 65536, 400
 
 
@@ -49,13 +54,13 @@ def measure(prog, depth, active=True):
     return float(t.item()) / STEPS * 1e6
 
 
-for zero_copy, streams in ((1, 4), (1, 2), (1, 1), (0, 1)):
+for zero_copy, streams in (((1, 4), (0, 1)) if QUICK else ((1, 4), (1, 2), (1, 1), (0, 1))):
     bench.PLAN_OPTIONS.clear()
     bench.PLAN_OPTIONS["host_zero_copy"] = zero_copy
     bench.PLAN_OPTIONS["host_streams"] = streams
     wl = bench.workload_h2_sweep()
     prog = bench.get_prog(wl)
-    for depth in (1, 2, 4, 8):
+    for depth in ((1, 8, 16) if QUICK else (1, 2, 4, 8)):
         if zero_copy == 0 and depth > 1:
             continue
         all_us = measure(prog, depth)
