@@ -228,6 +228,43 @@ def test_qp_variants_match_oracle(options):
         assert abs(got[b] - want) < TOL, (b, got[b], want)
 
 
+def test_variant_rows_position_independent_and_unaligned_table():
+    """The frame kernel walks a group's identifier rows as one run of 32-bit words: the energies of a row must not depend on
+    where it sits in the batch (shifted by 1..9 identity rows: every alignment of the 122-byte rows inside the 128-byte
+    steps, ragged last groups) nor on the alignment of the table pointer (byte path), bit for bit - and rows with many
+    corrections or R-type entries still take the general path."""
+    torch = torch_cuda()
+    terms = h2_terms()
+    n1, n2 = [O.bit_flip(1e-3), O.depolarize(1e-3)], [O.two_qubit_depolarize(1e-3)]
+    prog, gates = qp_noisy_variant_program(n1, n2, terms)
+    ham = O.pauli_terms_to_matrix(4, *terms)
+    arity = np.array([len(g[1]) for g in gates])
+    rng = np.random.default_rng(314)
+    B = 61
+    v = np.zeros((B, 122), np.uint8)
+    for b in range(B):
+        for s in rng.choice(122, int(rng.integers(0, 7)), replace=False):
+            v[b, s] = rng.integers(1, 4) if arity[s] == 1 else 16 * rng.integers(0, 4) + rng.integers(0, 4)
+    v[7, [0, 121]] = [3, 2]                                  # first and last slot of a row
+    v[11, 5] = 7                                             # R-type correction: general path
+    v[13, :40] = np.where(arity[:40] == 1, 1, 17)            # more entries than the compact list holds: general path
+    base = prog.energies(None, torch.tensor(v, device="cuda")).cpu().numpy()
+    for b in (0, 7, 11, 13, 60):
+        want = oracle_energy(O.variant_ops(gates, n1, n2, v[b]), 4, ham)
+        assert abs(base[b] - want) < TOL, (b, base[b], want)
+    for shift in range(1, 10):
+        shifted = np.concatenate([np.zeros((shift, 122), np.uint8), v])
+        got = prog.energies(None, torch.tensor(shifted, device="cuda")).cpu().numpy()
+        assert np.array_equal(got[shift:], base), shift
+        assert np.all(got[:shift] == got[0])
+    for off in (1, 2, 3):                                    # table pointer not 4-byte aligned
+        buf = torch.zeros(B * 122 + off, dtype=torch.uint8, device="cuda")
+        view = buf[off:].view(B, 122)
+        view.copy_(torch.tensor(v, device="cuda"))
+        assert view.data_ptr() % 4 == off
+        assert np.array_equal(prog.energies(None, view).cpu().numpy(), base), off
+
+
 def test_one_plan_on_two_streams_concurrently():
     """include/dmx.h: a finalized plan may be used from several streams at once (per-call worklist / reduction
     scratch).  Two different variant tables - both with rows that take the general path - are evaluated and reduced on

@@ -645,6 +645,89 @@ __device__ __noinline__ double frame32_variant_factor(const SlotDev* __restrict_
     return sd.nq == 1 ? t[idx * 4 + lab] : t[(idx >> 4) * 4 + (lab >> 2)] * t[(idx & 15u) * 4 + (lab & 3u)] * t[64 + lab];
 }
 
+// Scan of one group's identifier rows (kept out of line: its registers must not count against the segment loop's 64).
+// Returns stage_any; fills act[] / nact[] (per-warp shared memory) and pushes rows that need the general path.
+template <int CPB>
+__device__ __noinline__ unsigned frame32_scan_group(const uint8_t* __restrict__ variants, int n_slots, long long batch, const SlotDev* __restrict__ slots,
+                                                    int* worklist, int* work_count, long long b0, int lane, unsigned* act, int* nact) {
+    unsigned stage_any = 0u;
+    __syncwarp();
+    if (lane < CPB) nact[lane] = 0;
+    __syncwarp();
+    unsigned general = 0u;                                  // bit c: row c needs the general path (uniform)
+    const long long rows_here = batch - b0 < CPB ? batch - b0 : CPB;
+    const unsigned nsl = (unsigned)n_slots;
+    const unsigned valid = rows_here > 0 ? (unsigned)rows_here * nsl : 0u;      // bytes of this group inside the table
+    const uint8_t* const gbase = variants + b0 * n_slots;
+    const bool word_ok = (reinterpret_cast<unsigned long long>(variants) & 3ull) == 0ull;
+    for (unsigned f0 = 0; f0 < valid; f0 += 128u) {
+        const unsigned f = f0 + 4u * lane;
+        unsigned word = 0u;
+        if (word_ok && f + 4u <= valid) {
+            word = *reinterpret_cast<const unsigned*>(gbase + f);
+        } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                if (f + j < valid) word |= (unsigned)gbase[f + j] << (8 * j);
+        }
+        if (!__any_sync(0xffffffffu, word != 0u)) continue;        // identity entries only: nothing to record
+        const int c_lo = (int)(f0 / nsl);
+        const int c_hi = (int)min((f0 + 127u) / nsl, (unsigned)(CPB - 1));
+        unsigned ent[4];                // (stage << 20 | slot << 8 | idx) of this lane's four bytes, 0 = identity
+        int row[4];
+        bool gen[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            unsigned idx = (word >> (8 * j)) & 255u;
+            int sl = 0, seg = -1;
+            row[j] = -1;
+            if (idx) {
+                row[j] = (int)((f + j) / nsl);
+                sl = (int)(f + j - (unsigned)row[j] * nsl);
+                seg = slots[sl].seg;
+                if (seg < 0) idx = 0u;                              // slot not present in the circuit
+            }
+            const bool nz = idx != 0u;
+            gen[j] = nz && !((slots[sl].diag_ok[idx >> 5] >> (idx & 31u)) & 1u);
+            ent[j] = nz ? ((unsigned)seg << 20) | ((unsigned)sl << 8) | idx : 0u;
+            stage_any |= __reduce_or_sync(0xffffffffu, nz ? (seg < 31 ? 1u << seg : 0x80000000u) : 0u);
+        }
+        const unsigned below = (1u << lane) - 1u;
+        for (int cc = c_lo; cc <= c_hi; ++cc) {               // rows this 128-byte step touches (uniform bounds)
+            unsigned m[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) m[j] = __ballot_sync(0xffffffffu, ent[j] != 0u && row[j] == cc);
+            if (!(m[0] | m[1] | m[2] | m[3])) continue;
+            if (__any_sync(0xffffffffu, (gen[0] && row[0] == cc) || (gen[1] && row[1] == cc) || (gen[2] && row[2] == cc) || (gen[3] && row[3] == cc)))
+                general |= 1u << cc;
+            // entries are recorded in ascending slot order (flat index 4 * lane + j), whatever the row's alignment in the
+            // step: equal rows give bit-identical energies wherever they sit in the batch
+            const int base = nact[cc];
+            int pos = base + __popc(m[0] & below) + __popc(m[1] & below) + __popc(m[2] & below) + __popc(m[3] & below);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                if ((m[j] >> lane) & 1u) {
+                    if (pos < SEG_MAXACT) act[cc * SEG_MAXACT + pos] = ent[j];
+                    ++pos;
+                }
+            }
+            __syncwarp();
+            if (lane == 0) nact[cc] = base + __popc(m[0]) + __popc(m[1]) + __popc(m[2]) + __popc(m[3]);
+            __syncwarp();
+        }
+    }
+    if (lane < CPB) {
+        const int cnt = nact[lane];
+        const bool gen = ((general >> lane) & 1u) || cnt > SEG_MAXACT;
+        if (gen) {
+            nact[lane] = -1;
+            worklist[atomicAdd(work_count, 1)] = (int)(b0 + lane);
+        }
+    }
+    __syncwarp();
+    return stage_any;
+}
+
 // VAR = false: plain parameter sweeps (no variant code, fewer registers); VAR = true: QP variant rows.
 #ifndef DMX_F32_MINB
 #define DMX_F32_MINB 4       // 64 registers (no spills): four 256-thread CTAs per SM
@@ -677,7 +760,7 @@ __global__ void __launch_bounds__(256, DMX_F32_MINB) dmx_frame32_kernel(const Fr
     const double ew0 = a.eweight[lane];
     const int orig_l = a.orig[lane];
     double x_first = 0.0;
-    if (CSMODE == 1 && !(!VAR && a.stage_io)) {
+    if (CSMODE == 1 && !VAR && !a.stage_io) {
         const long long bf = ((long long)blockIdx.x * 8 + warp) * CPB + lane;
         if (lane < CPB && bf < a.batch) x_first = a.params[bf * a.n_params + a.cls0.param];
     }
@@ -714,6 +797,17 @@ __global__ void __launch_bounds__(256, DMX_F32_MINB) dmx_frame32_kernel(const Fr
     for (long long it = 0; it < rounds; ++it) {
         const long long grp = gwarp + it * nwarps;
         const long long b0 = grp * CPB;
+        // Variant rows: the non-identity entries of each row are compacted into act[c][] as (stage << 20 | slot << 8 | idx);
+        // stage_any has a bit per stage that holds at least one entry of some circuit of the group.
+        // The CPB identifier rows of a group are ONE contiguous run of CPB * n_slots bytes (8-byte aligned relative to the
+        // table), and almost all of it is zero (identity entries): the warp walks the run as 32-bit words, 128 bytes per step,
+        // and only a step that holds a non-zero byte does any per-entry work.  (Round 2, first half: one byte load per slot
+        // and row with its own 64-bit address arithmetic - 41 % of the kernel's instructions,
+        // profiles/r2_ncu_full_frame32var_kernel_v1.txt.)
+        unsigned stage_any = 0u;
+        if (VAR) stage_any = frame32_scan_group<CPB>(a.variants, a.n_slots, a.batch, a.slots, a.worklist, a.work_count, b0, lane, act, nact);
+
+        // (cos, sin) after the variant scan: the scan needs the registers
         double2 csr[CPB];
         if (CSMODE == 1) {
             // (Measured and rejected, profiles/r2_frame32s_ab.txt: computing the CTA's 64 (cos, sin) pairs once by 64 fully
@@ -722,7 +816,7 @@ __global__ void __launch_bounds__(256, DMX_F32_MINB) dmx_frame32_kernel(const Fr
             double sv = 0.0, cv = 1.0;
             if (lane < CPB && b0 + lane < a.batch) {
                 const RotInfo ri = a.cls0;
-                const double x = it == 0 ? (STAGE_IO ? io[warp * CPB + lane] : x_first) : a.params[(b0 + lane) * a.n_params + ri.param];
+                const double x = (it == 0 && !VAR) ? (STAGE_IO ? io[warp * CPB + lane] : x_first) : a.params[(b0 + lane) * a.n_params + ri.param];
                 sincos(ri.scale * x + ri.offset, &sv, &cv);
             }
 #pragma unroll
@@ -744,60 +838,6 @@ __global__ void __launch_bounds__(256, DMX_F32_MINB) dmx_frame32_kernel(const Fr
                 __syncwarp();
             }
         }
-        // Variant rows: the non-identity entries of each row are compacted into act[c][] as (stage << 20 | slot << 8 | idx);
-        // stage_any has a bit per stage that holds at least one entry of some circuit of the group.
-        unsigned stage_any = 0u;
-        if (VAR) {
-            __syncwarp();
-            int count[CPB];
-            bool general[CPB];
-#pragma unroll
-            for (int c = 0; c < CPB; ++c) { count[c] = 0; general[c] = false; }
-            for (int s00 = 0; s00 < a.n_slots; s00 += 128) {
-                // all identifier bytes of the CPB rows first (CPB x 4 independent loads per lane), then the compaction
-                unsigned pk[CPB];
-#pragma unroll
-                for (int c = 0; c < CPB; ++c) {
-                    pk[c] = 0u;
-                    if (b0 + c < a.batch) {
-                        const uint8_t* row = a.variants + (b0 + c) * a.n_slots;
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            const int s = s00 + 32 * j + lane;
-                            if (s < a.n_slots) pk[c] |= (unsigned)row[s] << (8 * j);
-                        }
-                    }
-                }
-#pragma unroll
-                for (int c = 0; c < CPB; ++c) {
-                    if (!__any_sync(0xffffffffu, pk[c] != 0u)) continue;       // identity row: nothing to record
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const int s = s00 + 32 * j + lane;
-                        unsigned idx = (pk[c] >> (8 * j)) & 255u;
-                        int seg = -1;
-                        if (idx) { seg = a.slots[s].seg; if (seg < 0) idx = 0; }     // slot not present in the circuit
-                        const bool nz = idx != 0;
-                        if (nz && !((a.slots[s].diag_ok[idx >> 5] >> (idx & 31)) & 1u)) general[c] = true;
-                        const unsigned m = __ballot_sync(0xffffffffu, nz);
-                        const int pos = count[c] + __popc(m & ((1u << lane) - 1u));
-                        if (nz && pos < SEG_MAXACT) act[c * SEG_MAXACT + pos] = ((unsigned)seg << 20) | ((unsigned)s << 8) | idx;
-                        stage_any |= __reduce_or_sync(0xffffffffu, nz ? (seg < 31 ? 1u << seg : 0x80000000u) : 0u);
-                        count[c] += __popc(m);
-                    }
-                }
-            }
-#pragma unroll
-            for (int c = 0; c < CPB; ++c) {
-                const bool gen = __any_sync(0xffffffffu, general[c]) || count[c] > SEG_MAXACT;
-                if (lane == 0) {
-                    nact[c] = gen ? -1 : count[c];
-                    if (gen) a.worklist[atomicAdd(a.work_count, 1)] = (int)(b0 + c);
-                }
-            }
-            __syncwarp();
-        }
-
         double r[CPB];
 #pragma unroll
         for (int c = 0; c < CPB; ++c) r[c] = init;
@@ -2112,7 +2152,9 @@ static int launch_frame32_impl(const Frame32Args& a, int sm_count, cudaStream_t 
 
 template <int CPB, int CSMODE>
 static int launch_frame32(const Frame32Args& a, int sm_count, cudaStream_t st) {
-    return a.variants ? launch_frame32_impl<CPB, CSMODE, true>(a, sm_count, st) : launch_frame32_impl<CPB, CSMODE, false>(a, sm_count, st);
+    // variant rows with one rotation class take the general-class kernel ((cos, sin) in shared memory): holding them in
+    // registers next to the variant bookkeeping spills 300 B at 64 registers
+    return a.variants ? launch_frame32_impl<CPB, CSMODE == 1 ? 2 : CSMODE, true>(a, sm_count, st) : launch_frame32_impl<CPB, CSMODE, false>(a, sm_count, st);
 }
 
 
