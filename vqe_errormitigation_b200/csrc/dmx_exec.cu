@@ -660,17 +660,35 @@ __device__ __noinline__ unsigned frame32_scan_group(const uint8_t* __restrict__ 
     const unsigned valid = rows_here > 0 ? (unsigned)rows_here * nsl : 0u;      // bytes of this group inside the table
     const uint8_t* const gbase = variants + b0 * n_slots;
     const bool word_ok = (reinterpret_cast<unsigned long long>(variants) & 3ull) == 0ull;
-    for (unsigned f0 = 0; f0 < valid; f0 += 128u) {
-        const unsigned f = f0 + 4u * lane;
-        unsigned word = 0u;
-        if (word_ok && f + 4u <= valid) {
-            word = *reinterpret_cast<const unsigned*>(gbase + f);
-        } else {
+    // Eight 128-byte steps are loaded ahead (independent loads: one memory round trip for the 976 bytes of an H2 group
+    // instead of one per step - the serial loads were 27 % of the kernel's stall samples), and a group whose rows are all
+    // identity leaves after ONE vote.
+    constexpr int AHEAD = 8;
+    for (unsigned s0 = 0; s0 < valid; s0 += 128u * AHEAD) {
+        unsigned words[AHEAD];
+        unsigned any = 0u;
 #pragma unroll
-            for (int j = 0; j < 4; ++j)
-                if (f + j < valid) word |= (unsigned)gbase[f + j] << (8 * j);
+        for (int i = 0; i < AHEAD; ++i) {
+            const unsigned fi = s0 + 128u * i + 4u * lane;
+            words[i] = 0u;
+            if (word_ok && fi + 4u <= valid) {
+                words[i] = *reinterpret_cast<const unsigned*>(gbase + fi);
+            } else if (fi < valid) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    if (fi + j < valid) words[i] |= (unsigned)gbase[fi + j] << (8 * j);
+            }
+            any |= words[i];
         }
-        if (!__any_sync(0xffffffffu, word != 0u)) continue;        // identity entries only: nothing to record
+        if (!__any_sync(0xffffffffu, any != 0u)) continue;          // identity entries only: nothing to record
+#pragma unroll 1
+      for (int i = 0; i < AHEAD; ++i) {
+        unsigned word = words[0];
+#pragma unroll
+        for (int q = 1; q < AHEAD; ++q) word = i == q ? words[q] : word;       // selects: `words` stays in registers
+        if (!__any_sync(0xffffffffu, word != 0u)) continue;
+        const unsigned f0 = s0 + 128u * i;
+        const unsigned f = f0 + 4u * lane;
         const int c_lo = (int)(f0 / nsl);
         const int c_hi = (int)min((f0 + 127u) / nsl, (unsigned)(CPB - 1));
         unsigned ent[4];                // (stage << 20 | slot << 8 | idx) of this lane's four bytes, 0 = identity
@@ -682,8 +700,10 @@ __device__ __noinline__ unsigned frame32_scan_group(const uint8_t* __restrict__ 
             int sl = 0, seg = -1;
             row[j] = -1;
             if (idx) {
-                row[j] = (int)((f + j) / nsl);
-                sl = (int)(f + j - (unsigned)row[j] * nsl);
+                int rj = c_lo;                                       // the step touches rows c_lo .. c_hi (two or three of them)
+                for (int cc = c_lo + 1; cc <= c_hi; ++cc) rj += (f + j >= (unsigned)cc * nsl) ? 1 : 0;
+                row[j] = rj;
+                sl = (int)(f + j - (unsigned)rj * nsl);
                 seg = slots[sl].seg;
                 if (seg < 0) idx = 0u;                              // slot not present in the circuit
             }
@@ -715,6 +735,7 @@ __device__ __noinline__ unsigned frame32_scan_group(const uint8_t* __restrict__ 
             if (lane == 0) nact[cc] = base + __popc(m[0]) + __popc(m[1]) + __popc(m[2]) + __popc(m[3]);
             __syncwarp();
         }
+      }
     }
     if (lane < CPB) {
         const int cnt = nact[lane];
