@@ -633,9 +633,10 @@ struct Frame32Args {
     int* work_count;
 };
 
-// diagonal factor of variant entry `ent` for the coefficient whose frame index is p (kept out of line: it runs for a few
-// entries per row, inlining it into the unrolled circuit loop only bloats the instruction footprint)
-__device__ __noinline__ double frame32_variant_factor(const SlotDev* __restrict__ slots, const uint8_t* __restrict__ labels,
+// diagonal factor of variant entry `ent` for the coefficient whose frame index is p.  Inlined ONCE: the entry loop of the
+// kernel runs over the circuits of a group with a run-time index (a call in the segment loop pinned the eight circuit
+// registers to the callee-saved set and cost ~30 register moves per segment, 13 % of the QEM kernel's instructions).
+__device__ __forceinline__ double frame32_variant_factor(const SlotDev* __restrict__ slots, const uint8_t* __restrict__ labels,
                                                       const double* __restrict__ coefs, unsigned ent, int p) {
     const int s = (ent >> 8) & 4095u;
     const unsigned idx = ent & 255u;
@@ -870,12 +871,16 @@ __global__ void __launch_bounds__(256, DMX_F32_MINB) dmx_frame32_kernel(const Fr
         if (a.nseg > 0) { sel_n = ssel[0]; wk_n = sw[lane]; w1_n = sw1[lane]; pb_n = spart[lane]; }
         for (int k = 0; k <= a.nseg; ++k) {
             if (VAR && ((stage_any >> (k < 31 ? k : 31)) & 1u)) {
-#pragma unroll
+#pragma unroll 1
                 for (int c = 0; c < CPB; ++c) {
                     const int na = nact[c];
                     for (int e = 0; e < na; ++e) {
                         const unsigned ent = act[c * SEG_MAXACT + e];
-                        if ((int)(ent >> 20) == k) r[c] *= frame32_variant_factor(a.slots, a.labels, a.coefs, ent, p);
+                        if ((int)(ent >> 20) == k) {
+                            const double fac = frame32_variant_factor(a.slots, a.labels, a.coefs, ent, p);
+#pragma unroll
+                            for (int cc = 0; cc < CPB; ++cc) r[cc] *= cc == c ? fac : 1.0;
+                        }
                     }
                 }
             }
