@@ -40,7 +40,17 @@ def test_device_sampler_is_bit_exact_with_reference():
     rng = np.random.default_rng(11)
     qps = [rng.normal(size=k) for k in (16, 256, 16, 2, 1, 256, 16)] + [np.array([1.3, -0.1, -0.1, -0.1] + [0.0] * 12)]
     odd = [np.array([0.7, -0.3]), np.array([1.0]), np.array([-2.0, 1.0, 0.5])]      # 3 slots x stride 3: sub-tables need padding to 16 B
-    for tables in (qps, odd, odd[:1], qps[:5]):
+    # 150 slots of near-identity tables (the QEM regime: the whole-group fast test decides almost every lane), some with a
+    # NEGATIVE or ZERO-weight identity entry (sign summary; threshold 0 = the identity is never drawn), more than 128 slots
+    wide = []
+    for k in range(150):
+        t = np.array([1.0 + 3e-3, -1e-3, -1e-3, -1e-3])
+        if k % 7 == 3:
+            t = -t
+        if k % 31 == 5:
+            t = np.array([0.0, 0.6, -0.4, 0.2])
+        wide.append(t)
+    for tables in (qps, odd, odd[:1], qps[:5], wide, wide[:122], wide[:129]):
         for batch, seed, first in ((1, 0, 0), (4097, 123456789012345, 0), (1000, 5, (1 << 33) + 17)):
             dv, ds = engine.qp_sample_variants(tables, batch, seed, first_sample=first)
             rv, rs = P.sample_variants(tables, batch, seed, first_sample=first)

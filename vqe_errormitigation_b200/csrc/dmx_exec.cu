@@ -1257,58 +1257,79 @@ __device__ __forceinline__ void philox4x32_10(unsigned (&c)[4], unsigned k0, uns
 
 // One warp per sample.  One Philox call serves FOUR consecutive gate slots: counter (sample lo, sample hi, slot / 4, 0), key = seed,
 // slot s takes word s % 4 as u = (word + 0.5) / 2^32 and idx = first cdf entry > u (cdf[last] = 1).  Entry 0 (the identity
-// correction, probability ~ 1 - O(p)) is tested first; only the rare other draws run the binary search.
+// correction, probability ~ 1 - O(p)) is tested first; only the rare other draws run the binary search.  The identity test
+// runs on integers: cdf[0] > (word + 0.5) / 2^32  <=>  word < ceil(cdf[0] * 2^32 - 0.5) =: thr0 (every step exact in double),
+// which takes four int -> double conversions and FP64 compares per lane off the FP64 pipe.
 __global__ void __launch_bounds__(256) dmx_qp_sample_kernel(int n_slots, const int* __restrict__ n_choices, const double* __restrict__ cdf,
                                      const unsigned char* __restrict__ sgn /* 0: +, 1: -, 2: zero */, int stride,
-                                     const double2* __restrict__ cdf0 /* [ceil(S/4)*2]: first cdf entry of every slot (padding: 2.0) */,
+                                     const ulonglong2* __restrict__ thr0 /* [ceil(S/4)*2]: identity threshold of every slot, see below (padding: 2^32) */,
                                      const unsigned* __restrict__ sgn0 /* [ceil(S/4)]: sign code of entry 0, 4 slots per word */,
+                                     const uint4* __restrict__ thr32 /* [ceil(S/4)]: thr0 - 1 as 32-bit words (fast test: word <= thr32) */,
+                                     const unsigned* __restrict__ summ /* [ceil(S/4)]: bit 0 sign parity, bit 1 zero weight of the four identity
+                                                                          entries, bit 2: some threshold is 0 (no fast test) */,
                                      unsigned long long seed, unsigned long long first_sample, long long batch,
                                      unsigned char* __restrict__ variants, double* __restrict__ signs) {
     const int lane = threadIdx.x & 31;
-    const long long b = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if (b >= batch) return;
-    const unsigned long long gidx = first_sample + (unsigned long long)b;
-    unsigned char* const out = variants + b * n_slots;
-    const bool aligned = (reinterpret_cast<unsigned long long>(out) & 3ull) == 0;      // this row's 4-slot words are word stores
-    int neg = 0, zero = 0;
-    for (int g = lane; 4 * g < n_slots; g += 32) {
-        unsigned c[4] = {(unsigned)gidx, (unsigned)(gidx >> 32), (unsigned)g, 0u};
-        philox4x32_10(c, (unsigned)seed, (unsigned)(seed >> 32));
-        // entry 0 of the four slots from the compact tables (coalesced); the full rows (stride apart) only for other draws
-        const double2 fa = cdf0[2 * g], fb = cdf0[2 * g + 1];
-        const double first[4] = {fa.x, fa.y, fb.x, fb.y};
-        const unsigned s0 = sgn0[g];
-        unsigned packed = 0u;
+    // Persistent warps walk the samples with a grid stride and keep the tables of their first slot group (every group when
+    // the circuit has <= 128 slots) in registers.  ncu (profiles/r2_ncu_full_sampler_kernel_v1.txt): 260 instructions per
+    // sample, ALU pipe 56 % - the kernel is instruction bound, so the common case is kept short: ONE chained 32-bit test
+    // says that all four slots of a lane drew the identity (99.4 % of the lane-groups at p = 1e-3), and then the signs
+    // come from a per-group summary word; only the other lanes look at slots one by one.
+    const long long warp0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+    uint4 q0 = make_uint4(~0u, ~0u, ~0u, ~0u);
+    unsigned sum0 = 0u;
+    if (4 * lane < n_slots) { q0 = thr32[lane]; sum0 = summ[lane]; }
+    for (long long b = warp0; b < batch; b += nwarps) {
+        const unsigned long long gidx = first_sample + (unsigned long long)b;
+        unsigned char* const out = variants + b * n_slots;
+        const unsigned misalign = (unsigned)(reinterpret_cast<unsigned long long>(out) & 3ull);      // 0: word stores, 2: half-word stores
+        unsigned neg = 0u, zero = 0u;
+        for (int g = lane; 4 * g < n_slots; g += 32) {
+            unsigned c[4] = {(unsigned)gidx, (unsigned)(gidx >> 32), (unsigned)g, 0u};
+            philox4x32_10(c, (unsigned)seed, (unsigned)(seed >> 32));
+            const uint4 q = g == lane ? q0 : thr32[g];
+            const unsigned sm = g == lane ? sum0 : summ[g];
+            unsigned packed = 0u;
+            if (c[0] <= q.x && c[1] <= q.y && c[2] <= q.z && c[3] <= q.w && !(sm & 4u)) {
+                neg ^= sm & 1u;
+                zero |= (sm >> 1) & 1u;
+            } else {
+                // slot by slot: entry 0 from the compact tables, the full rows (stride apart) only for the other draws
+                const ulonglong2 fa = thr0[2 * g], fb = thr0[2 * g + 1];
+                const unsigned long long first[4] = {fa.x, fa.y, fb.x, fb.y};
+                const unsigned s0 = sgn0[g];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const int s = 4 * g + i;
-            const double u = ((double)c[i] + 0.5) * (1.0 / 4294967296.0);
-            int sg = (s0 >> (8 * i)) & 255u;
-            if (!(first[i] > u)) {             // never for the padding slots (first = 2)
-                const double* __restrict__ row = cdf + (size_t)s * stride;
-                int hi = n_choices[s] - 1, lo = hi > 0 ? 1 : 0;
-                while (lo < hi) {
-                    const int mid = (lo + hi) >> 1;
-                    if (row[mid] > u) hi = mid; else lo = mid + 1;
+                for (int i = 0; i < 4; ++i) {
+                    const int s = 4 * g + i;
+                    unsigned sg = (s0 >> (8 * i)) & 255u;
+                    if (!((unsigned long long)c[i] < first[i])) {             // never for the padding slots (threshold 2^32)
+                        const double u = ((double)c[i] + 0.5) * (1.0 / 4294967296.0);
+                        const double* __restrict__ row = cdf + (size_t)s * stride;
+                        int hi = n_choices[s] - 1, lo = hi > 0 ? 1 : 0;
+                        while (lo < hi) {
+                            const int mid = (lo + hi) >> 1;
+                            if (row[mid] > u) hi = mid; else lo = mid + 1;
+                        }
+                        packed |= (unsigned)lo << (8 * i);
+                        sg = sgn[(size_t)s * stride + lo];
+                    }
+                    neg ^= sg == 1u;
+                    zero |= sg == 2u;
                 }
-                packed |= (unsigned)lo << (8 * i);
-                sg = sgn[(size_t)s * stride + lo];
             }
-            neg ^= sg == 1;
-            zero |= sg == 2;
+            if (4 * g + 3 < n_slots && misalign == 0u) {
+                *reinterpret_cast<unsigned*>(out + 4 * g) = packed;
+            } else if (4 * g + 3 < n_slots && misalign == 2u) {
+                *reinterpret_cast<unsigned short*>(out + 4 * g) = (unsigned short)packed;
+                *reinterpret_cast<unsigned short*>(out + 4 * g + 2) = (unsigned short)(packed >> 16);
+            } else {
+                for (int i = 0; i < 4 && 4 * g + i < n_slots; ++i) out[4 * g + i] = (unsigned char)(packed >> (8 * i));
+            }
         }
-        if (aligned && 4 * g + 3 < n_slots) {
-            *reinterpret_cast<unsigned*>(out + 4 * g) = packed;
-        } else {
-            for (int i = 0; i < 4 && 4 * g + i < n_slots; ++i) out[4 * g + i] = (unsigned char)(packed >> (8 * i));
-        }
+        neg = __reduce_xor_sync(0xffffffffu, neg);
+        zero = __reduce_or_sync(0xffffffffu, zero);
+        if (lane == 0) signs[b] = zero ? 0.0 : (neg ? -1.0 : 1.0);
     }
-#pragma unroll
-    for (int off = 16; off > 0; off >>= 1) {
-        neg ^= __shfl_xor_sync(0xffffffffu, neg, off);
-        zero |= __shfl_xor_sync(0xffffffffu, zero, off);
-    }
-    if (lane == 0) signs[b] = zero ? 0.0 : (neg ? -1.0 : 1.0);
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -1369,9 +1390,9 @@ __global__ void __launch_bounds__(128) dmx_shot_expect_kernel(const double* __re
 
 // device tables of a QP sampler (dmx_qp_sampler_create): [cdf | first cdf entries | n_choices | first sign codes | sign codes]
 struct dmx_qp_sampler {
-    int n_slots = 0, stride = 0, device = -1;
+    int n_slots = 0, stride = 0, device = -1, sm_count = 0;
     char* d = nullptr;
-    size_t cb = 0, fb = 0, nb = 0, gb = 0;
+    size_t cb = 0, fb = 0, nb = 0, gb = 0, sb = 0, qb = 0;      // byte sizes of the sub-tables (each 16-byte aligned)
 };
 
 // ---------------------------------------------------------------------------------------------------------
@@ -2558,19 +2579,41 @@ int dmx_qp_sampler_create(int n_slots, const int32_t* n_choices, const double* q
         }
     }
     const int groups = (n_slots + 3) / 4;
-    std::vector<double> first((size_t)groups * 4, 2.0);
+    // identity thresholds: cdf[0] > (word + 0.5) / 2^32  <=>  word < ceil(cdf[0] * 2^32 - 0.5); both products are exact in double
+    std::vector<unsigned long long> first((size_t)groups * 4, 1ull << 32);
     std::vector<unsigned char> sg0((size_t)groups * 4, 0);
-    for (int s = 0; s < n_slots; ++s) { first[s] = cdf[(size_t)s * stride]; sg0[s] = sg[(size_t)s * stride]; }
+    for (int s = 0; s < n_slots; ++s) {
+        const double x = cdf[(size_t)s * stride] * 4294967296.0 - 0.5;
+        first[s] = x <= 0.0 ? 0ull : (x >= 4294967296.0 ? 1ull << 32 : (unsigned long long)std::ceil(x));
+        sg0[s] = sg[(size_t)s * stride];
+    }
+    // fast identity test of a whole lane-group: word <= threshold - 1 on 32 bits, plus the sign summary of the four identity entries
+    std::vector<unsigned> fast((size_t)groups * 5, 0u);           // [groups] uint4 thresholds, then [groups] summary words
+    for (int g = 0; g < groups; ++g) {
+        unsigned summary = 0u;
+        for (int i = 0; i < 4; ++i) {
+            const unsigned long long t = first[(size_t)g * 4 + i];
+            fast[(size_t)g * 4 + i] = t ? (unsigned)(t - 1) : 0u;
+            if (!t) summary |= 4u;
+            if (g * 4 + i < n_slots) {
+                if (sg0[(size_t)g * 4 + i] == 1) summary ^= 1u;
+                if (sg0[(size_t)g * 4 + i] == 2) summary |= 2u;
+            }
+        }
+        fast[(size_t)groups * 4 + g] = summary;
+    }
     auto* sm = new dmx_qp_sampler();
     sm->n_slots = n_slots; sm->stride = stride;
-    // every sub-table starts 16-byte aligned (cdf0 is read as double2)
-    sm->cb = (cdf.size() * 8 + 15) & ~(size_t)15; sm->fb = first.size() * 8; sm->nb = ((size_t)n_slots * 4 + 15) & ~(size_t)15; sm->gb = sg0.size();
-    if (cudaGetDevice(&sm->device) != cudaSuccess || cudaMalloc((void**)&sm->d, sm->cb + sm->fb + sm->nb + sm->gb + sg.size()) != cudaSuccess ||
+    // every sub-table starts 16-byte aligned (thr0 is read as ulonglong2)
+    sm->cb = (cdf.size() * 8 + 15) & ~(size_t)15; sm->fb = first.size() * 8; sm->nb = ((size_t)n_slots * 4 + 15) & ~(size_t)15; sm->gb = (sg0.size() + 15) & ~(size_t)15; sm->qb = fast.size() * 4; sm->sb = ((sg.size() + 15) & ~(size_t)15);
+    if (cudaGetDevice(&sm->device) != cudaSuccess || cudaDeviceGetAttribute(&sm->sm_count, cudaDevAttrMultiProcessorCount, sm->device) != cudaSuccess ||
+        sm->sm_count < 1 || cudaMalloc((void**)&sm->d, sm->cb + sm->fb + sm->nb + sm->gb + sm->sb + sm->qb) != cudaSuccess ||
         cudaMemcpy(sm->d, cdf.data(), cdf.size() * 8, cudaMemcpyHostToDevice) != cudaSuccess ||
         cudaMemcpy(sm->d + sm->cb, first.data(), sm->fb, cudaMemcpyHostToDevice) != cudaSuccess ||
         cudaMemcpy(sm->d + sm->cb + sm->fb, n_choices, (size_t)n_slots * 4, cudaMemcpyHostToDevice) != cudaSuccess ||
-        cudaMemcpy(sm->d + sm->cb + sm->fb + sm->nb, sg0.data(), sm->gb, cudaMemcpyHostToDevice) != cudaSuccess ||
-        cudaMemcpy(sm->d + sm->cb + sm->fb + sm->nb + sm->gb, sg.data(), sg.size(), cudaMemcpyHostToDevice) != cudaSuccess) {
+        cudaMemcpy(sm->d + sm->cb + sm->fb + sm->nb, sg0.data(), sg0.size(), cudaMemcpyHostToDevice) != cudaSuccess ||
+        cudaMemcpy(sm->d + sm->cb + sm->fb + sm->nb + sm->gb, sg.data(), sg.size(), cudaMemcpyHostToDevice) != cudaSuccess ||
+        cudaMemcpy(sm->d + sm->cb + sm->fb + sm->nb + sm->gb + sm->sb, fast.data(), sm->qb, cudaMemcpyHostToDevice) != cudaSuccess) {
         const cudaError_t e = cudaGetLastError();
         if (sm->d) cudaFree(sm->d);
         delete sm;
@@ -2594,12 +2637,13 @@ int dmx_qp_sampler_draw(const dmx_qp_sampler* sm, uint64_t seed, uint64_t first_
     CUDA_TRY(cudaGetDevice(&dev));
     if (dev != sm->device) return fail(DMX_ERR_STATE, "sampler tables live on another device");
     const int threads = 256;
-    const long long grid = (batch * 32 + threads - 1) / threads;
-    if (grid >= (1LL << 31)) return fail(DMX_ERR_UNSUPPORTED, "batch too large for one launch");
+    const long long grid = std::min<long long>((batch * 32 + threads - 1) / threads, (long long)sm->sm_count * 8);      // persistent: 64 warps per SM
     const char* base = sm->d;
     dmx_qp_sample_kernel<<<(unsigned)grid, threads, 0, (cudaStream_t)stream>>>(
         sm->n_slots, (const int*)(base + sm->cb + sm->fb), (const double*)base, (const unsigned char*)(base + sm->cb + sm->fb + sm->nb + sm->gb),
-        sm->stride, (const double2*)(base + sm->cb), (const unsigned*)(base + sm->cb + sm->fb + sm->nb), seed, first_sample, batch, d_variants,
+        sm->stride, (const ulonglong2*)(base + sm->cb), (const unsigned*)(base + sm->cb + sm->fb + sm->nb),
+        (const uint4*)(base + sm->cb + sm->fb + sm->nb + sm->gb + sm->sb),
+        (const unsigned*)(base + sm->cb + sm->fb + sm->nb + sm->gb + sm->sb + (size_t)((sm->n_slots + 3) / 4) * 16), seed, first_sample, batch, d_variants,
         d_signs);
     ++g_launches;
     CUDA_TRY(cudaGetLastError());
