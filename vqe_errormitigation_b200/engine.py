@@ -285,7 +285,8 @@ class CircuitProgram:
             raise ValueError("streaming plans share one workspace: run them on the current stream")
         stream = C.c_void_p(stream)
         if groups is not None:
-            g_t = torch.as_tensor(groups, device=dev).to(torch.int32).contiguous()
+            g_t = groups if (isinstance(groups, torch.Tensor) and groups.dtype == torch.int32 and groups.device == dev
+                             and groups.is_contiguous()) else torch.as_tensor(groups, device=dev).to(torch.int32).contiguous()
             if g_t.numel() != B:
                 raise ValueError(f"groups has {g_t.numel()} entries for a batch of {B}")
             check(self._lib.dmx_energy_batch_grouped(self._handle, B, self._ptr(p_t), self._ptr(v_t), self._ptr(g_t), self._ptr(out),
