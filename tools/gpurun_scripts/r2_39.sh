@@ -1,0 +1,14 @@
+set -x
+python - <<'PY'
+import subprocess, json, sys
+def run(wl, opts, steps):
+    cmd = [sys.executable, "bench.py", "--workload", wl, "--steps", str(steps), "--warmup", "3", "--no-cpu-baseline", "--no-also", "--no-e2e"] + sum([["--opt", o] for o in opts], [])
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    try:
+        d = json.loads(r.stdout.strip().splitlines()[-1])
+        print(f"{wl:9s} {str(opts):24s} value {d['value']:.5g}  ms {d['ms_per_step']:.3f} parity {d['parity_max_abs_err']} fexec {d['roofline']['frac_executed']:.3f}", flush=True)
+    except Exception as e:
+        print(wl, opts, "FAILED", r.stdout[-300:], r.stderr[-800:], flush=True)
+for c in (0, 8, 16, 32, 128, 256):
+    run("hea10", [f"stream_chunk={c}"], 3)
+PY
