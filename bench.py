@@ -231,7 +231,9 @@ def workload_hea10():
     # SURVEY.md §8d canonical traffic: one read + one write of complex128 rho per layer = depth * 32 B * 4^n
     return dict(key="hea10",
                 name=f"synthetic 10-qubit hardware-efficient ansatz depth 20, noise on every gate, batch {B} per step (BASELINE configs[3])",
-                builder=b, batch=B, make_inputs=make_inputs, terms=terms, options={"tile_qubits": 6},
+                # 7 resident qubits: 10 passes / 103 sweeps instead of 18 / 112 at 6 - 8 365 vs 8 081 circuits/s (the 12-qubit
+                # workload prefers 6: 22.8 vs 19.7 evals/s; profiles/r2_stream3_experiments.txt)
+                builder=b, batch=B, make_inputs=make_inputs, terms=terms, options={"tile_qubits": 7},
                 canonical_bytes=depth * 32.0 * 4.0 ** n, cpu_sample=16, golden="hea10", parity_rows=[0, 1])
 
 

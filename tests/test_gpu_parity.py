@@ -515,9 +515,10 @@ def _large_golden(key):
 
 
 def test_hea10_depth20_bench_workload_against_c_oracle():
-    """BASELINE configs[3] exactly as bench.workload_hea10 builds it (10 qubits, depth 20, 1160 ops, 100 Pauli terms, 18
-    remapped passes / 112 triple sweeps): rows 0-1 of the bench inputs against the C oracle run live (one circuit per
-    thread, ~1 min) and against the committed golden energies the same oracle produced (tools/make_golden_large.py)."""
+    """BASELINE configs[3] exactly as bench.workload_hea10 builds it (10 qubits, depth 20, 1160 ops, 100 Pauli terms; 10
+    remapped passes / 103 triple sweeps on its 7-qubit tiles, 18 / 112 on 6-qubit tiles - both checked): rows 0-1 of the
+    bench inputs against the C oracle run live (one circuit per thread, ~1 min) and against the committed golden energies
+    the same oracle produced (tools/make_golden_large.py)."""
     import bench
     from oracle import c_oracle as CO
     torch = torch_cuda()
@@ -530,6 +531,14 @@ def test_hea10_depth20_bench_workload_against_c_oracle():
     assert np.max(np.abs(got - want)) < TOL, (got, want)
     gold = _large_golden("hea10")
     assert gold is not None and np.max(np.abs(np.array(gold["energies"]) - want)) < 1e-12
+    from vqe_errormitigation_b200 import engine
+    passes = {}
+    for tile in (6, 7):
+        other = engine.CircuitProgram(wl["builder"], hamiltonian=wl["terms"], options={"tile_qubits": tile})
+        passes[tile] = other.info["n_passes"]
+        e_t = other.energies(torch.tensor(params), workspace_states=2).cpu().numpy()
+        assert np.max(np.abs(e_t - want)) < TOL, (tile, e_t, want)
+    assert passes[7] < passes[6] and prog.info["n_passes"] in passes.values()
     # the same rows inside a full-size launch (64 circuits in flight per pass) give the same numbers
     big = wl["make_inputs"](0)[0][:130]
     e_big = prog.energies(torch.tensor(big)).cpu().numpy()
