@@ -768,7 +768,7 @@ def run_workload(wl, ctx, steps: int, warmup: int, with_cpu_baseline: bool, with
         # driver calls it; the library rotates them over "host_streams" (4) streams, so the partial last wave of one launch
         # overlaps the next launch - which is why this figure can exceed `value`, whose launches are timed one at a time
         # with an L2 flush between them.  Streaming plans run one synchronous call per step.
-        depth = 32 if info["path"] == 1 and groups_h is None else 1
+        depth = 16 if info["path"] == 1 and groups_h is None else 1
         params_p, groups_p = pinned(params_h), pinned(groups_h)
         res = [engine.pinned_empty(B) for _ in range(depth)]
 

@@ -76,7 +76,7 @@ def test_round2_default_record_carries_every_config_and_parity():
 def test_round2_streamed_protocol_record():
     """Second half of round 2: microsecond-scale workloads time their K steps in ONE event region (4 streams, distinct buffers
     cycled past the L2); the per-step-event figure stays as `isolated` and must be the smaller one."""
-    d = load("r2_bench_default_v5.json")
+    d = load("r2_bench_default_v6.json")
     assert [k for k in BASE if k not in d] == []
     assert d["parity_max_abs_err"] < 1e-10 and d["gpu_launches"] == d["steps"]
     assert "ONE pair of CUDA events" in d["config"]["timing"] and "L2" in d["config"]["l2"]
