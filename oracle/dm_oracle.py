@@ -95,6 +95,85 @@ def probabilities(rho: np.ndarray, renormalise: bool = True) -> np.ndarray:
     return p / p.sum() if renormalise else p
 
 
+# ---- measurement with collapse: the per-repetition path of DensityMatrixSimulator ------------------------
+def _outcome_probabilities(t: np.ndarray, n: int, qubits: Sequence[int]) -> np.ndarray:
+    """cirq/sim/density_matrix_utils.py::_probs [cirq-0.8.2]: |diag rho| summed over the unmeasured qubits for every
+    outcome of ``qubits`` (big-endian over the listed qubits), then divided by its sum."""
+    diag = np.abs(np.diagonal(t.reshape(1 << n, 1 << n))).astype(np.float64).reshape((2,) * n)
+    k = len(qubits)
+    probs = np.zeros(1 << k)
+    for b in range(1 << k):
+        sl = [slice(None)] * n
+        for i, q in enumerate(qubits):
+            sl[q] = (b >> (k - 1 - i)) & 1
+        probs[b] = diag[tuple(sl)].sum()
+    return probs / probs.sum()
+
+
+def _collapse(t: np.ndarray, n: int, qubits: Sequence[int], outcome: int, prob: float) -> np.ndarray:
+    """measure_density_matrix [cirq-0.8.2]: everything outside the outcome's row AND column slice is zeroed, then
+    ``out /= probs[result]``."""
+    k = len(qubits)
+    mask = np.ones(t.shape, dtype=bool)
+    sl = [slice(None)] * (2 * n)
+    for i, q in enumerate(qubits):
+        bit = (outcome >> (k - 1 - i)) & 1
+        sl[q] = bit
+        sl[q + n] = bit
+    mask[tuple(sl)] = False
+    out = t.copy()
+    out[mask] = 0
+    return out / prob
+
+
+def run_repeat(n: int, ops: Iterable[Op], repetitions: int, rng=np.random, dtype=np.complex128):
+    """DensityMatrixSimulator._run_sweep_repeat [cirq-0.8.2]: every repetition is simulated on its own and every "m" op
+    draws an outcome and collapses the state.  Returns {key: uint8 [repetitions, bits]}."""
+    ops = list(ops)
+    records = {}
+    for _ in range(repetitions):
+        t = np.zeros((2,) * (2 * n), dtype=dtype)
+        t[(0,) * (2 * n)] = 1.0
+        for kind, qubits, payload in ops:
+            if kind != "m":
+                t = apply_op(t, n, kind, qubits, payload)
+                continue
+            probs = _outcome_probabilities(t, n, qubits)
+            result = int(rng.choice(len(probs), p=probs))
+            t = _collapse(t, n, qubits, result, probs[result])
+            k = len(qubits)
+            records.setdefault(payload, []).append([(result >> (k - 1 - i)) & 1 for i in range(k)])
+    return {key: np.array(v, dtype=np.uint8) for key, v in records.items()}
+
+
+def measurement_distribution(n: int, ops: Iterable[Op], dtype=np.complex128):
+    """The distribution ``run_repeat`` samples from, by walking every branch: {tuple of all measured bits in circuit order:
+    probability}, plus the collapsed final density matrix of every branch {bits: rho} (what ``simulate`` would return)."""
+    ops = list(ops)
+    dist, finals = {}, {}
+
+    def walk(t, start, bits, prob):
+        for i in range(start, len(ops)):
+            kind, qubits, payload = ops[i]
+            if kind != "m":
+                t = apply_op(t, n, kind, qubits, payload)
+                continue
+            probs = _outcome_probabilities(t, n, qubits)
+            k = len(qubits)
+            for b in range(1 << k):
+                if probs[b] > 0.0:
+                    walk(_collapse(t, n, qubits, b, probs[b]), i + 1, bits + tuple((b >> (k - 1 - j)) & 1 for j in range(k)),
+                         prob * probs[b])
+            return
+        dist[bits] = dist.get(bits, 0.0) + prob
+        finals[bits] = t.reshape(1 << n, 1 << n)
+
+    t0 = np.zeros((2,) * (2 * n), dtype=dtype)
+    t0[(0,) * (2 * n)] = 1.0
+    walk(t0, 0, (), 1.0)
+    return dist, finals
+
+
 # ---- gate / channel definitions (cirq 0.8.2 conventions, App. B.1) --------------------------------------
 
 I2 = np.eye(2, dtype=complex)

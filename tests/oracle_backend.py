@@ -28,10 +28,21 @@ def _batch(self, params, variants, batch):
     return p, v, sizes.pop()
 
 
-def _energies_host(self, params=None, variants=None, batch=None):
+def _energies_host(self, params=None, variants=None, batch=None, groups=None):
     p, v, B = _batch(self, params, variants, batch)
-    return CO.energy_batch(self.n_qubits, self.ops, self.pool, self.hamiltonian, params=p, variants=v, batch=B,
-                           n_params=self.n_params, n_slots=self.n_slots, threads=2)
+    if groups is None:
+        return CO.energy_batch(self.n_qubits, self.ops, self.pool, self.hamiltonian, params=p, variants=v, batch=B,
+                               n_params=self.n_params, n_slots=self.n_slots, threads=2)
+    # coefficient groups: the oracle evaluates the rows of every group with that group's weights
+    groups = np.asarray(groups).reshape(-1)
+    x, z, _ = self.hamiltonian
+    out = np.empty(B)
+    for g in np.unique(groups):
+        rows = np.flatnonzero(groups == g)
+        out[rows] = CO.energy_batch(self.n_qubits, self.ops, self.pool, (x, z, self.coefficient_groups[g]),
+                                    params=None if p is None else p[rows], variants=None if v is None else v[rows], batch=len(rows),
+                                    n_params=self.n_params, n_slots=self.n_slots, threads=2)
+    return out
 
 
 def _density(self, params=None, variants=None, *, batch=None):
@@ -56,8 +67,8 @@ class _FakeTensor:
         return self._a
 
 
-def _energies(self, params=None, variants=None, *, batch=None, out=None, workspace_states=None):
-    return _FakeTensor(_energies_host(self, params, variants, batch))
+def _energies(self, params=None, variants=None, *, batch=None, out=None, workspace_states=None, groups=None, stream=None):
+    return _FakeTensor(_energies_host(self, params, variants, batch, groups))
 
 
 def _shot_expectations(probs, shots, masks, seed, first_row=0):

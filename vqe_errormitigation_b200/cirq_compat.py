@@ -865,6 +865,17 @@ class Circuit:
     def has_measurements(self) -> bool:
         return any(isinstance(op.gate, MeasurementGate) for op in self.all_operations())
 
+    def are_all_measurements_terminal(self) -> bool:
+        """No operation (a later measurement included) acts on a measured qubit afterwards (cirq ``Circuit`` method that
+        decides between evolve-once sampling and per-repetition simulation)."""
+        measured = set()
+        for op in self.all_operations():
+            if measured.intersection(op.qubits):
+                return False
+            if isinstance(op.gate, MeasurementGate):
+                measured.update(op.qubits)
+        return True
+
     def _is_parameterized_(self):
         return any(is_parameterized(op) for op in self.all_operations())
 
@@ -965,7 +976,11 @@ class DensityMatrixSimulator:
     """Facade with cirq's call surface; ``simulate`` / ``run`` evolve on the GPU (engine.CircuitProgram).
 
     Differences from cirq 0.8.2, on purpose: dtype defaults to complex128 (cirq: complex64 — SURVEY.md §0
-    item 2; the north star requires FP64); mid-circuit measurements are not supported.
+    item 2; the north star requires FP64).  Circuits whose measurements are all terminal are evolved once and sampled from
+    the diagonal; measurements with gates after them go through ``trajectories.TrajectoryProgram`` (cirq: one simulation
+    per repetition with ``measure_density_matrix`` collapses; here: the outcome tree walked level by level as variant
+    batches).  ``simulate`` collapses every measurement of its single run, like cirq's; ``ignore_measurement_results``
+    replaces the collapse by the dephasing channel.
     """
 
     def __init__(self, *, dtype=np.complex128, noise=None, seed=None, ignore_measurement_results: bool = False):
@@ -982,16 +997,39 @@ class DensityMatrixSimulator:
     def simulate(self, program: Circuit, param_resolver=None, qubit_order=None, initial_state=None) -> DensityMatrixTrialResult:
         if initial_state is not None:
             raise NotImplementedError("only the |0...0> initial state is supported")
-        prog, params = self._program(program, param_resolver, qubit_order)
-        rho = prog.density(params)[0]
+        measurements = {}
+        if program.has_measurements():
+            from . import engine, trajectories
+            resolved = resolve_parameters(program, param_resolver) if param_resolver is not None else program
+            if self._ignore_measurement_results:
+                builder, qubits, meas, _, _ = engine.lower_circuit(resolved, qubit_order, dephase_measurements=True)
+                rho = engine.CircuitProgram(builder, qubits=qubits, measurements=meas).density(None)[0]
+            else:
+                tp, params = trajectories.program_for_circuit(resolved, qubit_order)
+                rho, measurements = tp.simulate(self._rng, params)
+                qubits = tp.qubits
+        else:
+            prog, params = self._program(program, param_resolver, qubit_order)
+            rho, qubits = prog.density(params)[0], prog.qubits
         if np.dtype(self._dtype) != np.complex128:
             rho = rho.astype(self._dtype)
-        return DensityMatrixTrialResult(rho, prog.qubits, ParamResolver(param_resolver))
+        result = DensityMatrixTrialResult(rho, qubits, ParamResolver(param_resolver))
+        result.measurements = measurements
+        return result
 
     def run(self, program: Circuit, param_resolver=None, repetitions: int = 1) -> TrialResult:
-        prog, params = self._program(program, param_resolver, None)
-        if not prog.measurements:
+        if not program.has_measurements():
             raise ValueError("Circuit has no measurements to sample.")
+        keys = [op.gate.key for op in program.all_operations() if isinstance(op.gate, MeasurementGate)]
+        repeated = sorted({k for k in keys if keys.count(k) > 1})
+        if repeated:       # cirq: SimulatesSamples.run_sweep -> _verify_unique_measurement_keys
+            raise ValueError("Measurement key {} repeated".format(",".join(repeated)))
+        if not program.are_all_measurements_terminal():
+            from . import trajectories
+            resolved = resolve_parameters(program, param_resolver) if param_resolver is not None else program
+            tp, params = trajectories.program_for_circuit(resolved, None)
+            return TrialResult(tp.run(repetitions, self._rng, params), repetitions)
+        prog, params = self._program(program, param_resolver, None)
         probs = prog.probabilities(params, renormalise=True)[0]
         return sample_measurements(probs, prog, repetitions, self._rng)
 

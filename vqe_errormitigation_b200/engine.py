@@ -145,6 +145,16 @@ class ProgramBuilder:
     def pool(self) -> np.ndarray:
         return np.concatenate(self._pool) if self._pool else np.zeros(0)
 
+    def prefix(self, n_ops: int) -> "ProgramBuilder":
+        """The first ``n_ops`` ops as a builder of their own (same matrix pool, parameter columns and variant columns, so
+        the rows of the full program fit every prefix): the state *at* a mid-circuit measurement (trajectories.py)."""
+        out = ProgramBuilder(self.n_qubits)
+        out.ops = list(self.ops[:n_ops])
+        out._pool, out._pool_len, out._pool_index = self._pool, self._pool_len, self._pool_index
+        out.param_names = list(self.param_names)
+        out.n_slots = self.n_slots
+        return out
+
 
 class CircuitProgram:
     """A finalized ``dmx_plan`` plus what the Python callers need (qubit order, parameter names, measurements)."""
@@ -165,6 +175,7 @@ class CircuitProgram:
         self.ops = list(builder.ops)
         self.pool = builder.pool()
         self.hamiltonian = hamiltonian
+        self.coefficient_groups = None if coefficient_groups is None else np.ascontiguousarray(coefficient_groups, np.float64)
         self._handle = C.c_void_p()
         ops = (DmxOp * max(len(builder.ops), 1))(*builder.ops)
         pool = np.ascontiguousarray(builder.pool(), dtype=np.float64)
@@ -524,7 +535,21 @@ def compile_circuit(circuit: cirq.Circuit, qubit_order: Optional[Sequence] = Non
     return prog, (np.array([lifted], np.float64) if lift_numeric_rotations else None), key
 
 
-def lower_circuit(circuit: cirq.Circuit, qubit_order=None, lift_numeric_rotations: bool = False):
+# one-qubit basis table of a measurement site: index 0 = not (yet) measured, 1 / 2 = collapsed onto |0> / |1>
+_P0 = np.array([[1, 0], [0, 0]], complex)
+_P1 = np.array([[0, 0], [0, 1]], complex)
+MEASUREMENT_SITE_TABLE = [np.eye(2, dtype=complex), _P0, _P1] + [np.eye(2, dtype=complex)] * 13
+
+
+def lower_circuit(circuit: cirq.Circuit, qubit_order=None, lift_numeric_rotations: bool = False, sites: Optional[list] = None,
+                  dephase_measurements: bool = False):
+    """Circuit -> (builder, qubits, measurements, lifted angles, structure key).
+
+    Measurements: by default only terminal ones are accepted (cirq then evolves once and samples the diagonal).  With
+    ``sites`` (a list to fill) every measured qubit becomes a VARIANT slot over ``MEASUREMENT_SITE_TABLE`` and a record
+    ``(slot, qubit position, n_ops before it, measurement index, bit index)`` - the collapse points of cirq's per-shot
+    simulation (``DensityMatrixSimulator._run_sweep_repeat`` / ``simulate`` [cirq-0.8.2]); ``dephase_measurements`` instead
+    applies the channel {|0><0|, |1><1|} (cirq's ``ignore_measurement_results=True``)."""
     qubits = list(qubit_order) if qubit_order is not None else sorted(circuit.all_qubits())
     pos = {q: i for i, q in enumerate(qubits)}
     n = len(qubits)
@@ -540,12 +565,21 @@ def lower_circuit(circuit: cirq.Circuit, qubit_order=None, lift_numeric_rotation
         gate = op.gate
         idx = [pos[q] for q in op.qubits]
         if isinstance(gate, cirq.MeasurementGate):
+            if sites is not None:
+                for bit, q in enumerate(idx):
+                    n_before = len(b.ops)
+                    slot = b.add_variant([q], MEASUREMENT_SITE_TABLE)
+                    sites.append((slot, q, n_before, len(measurements), bit))
+            elif dephase_measurements:
+                for q in idx:
+                    b.add_kraus([q], [_P0, _P1])
             measurements.append((gate.key, idx, gate.invert_mask))
             measured.update(idx)
             key.append(("M", tuple(idx), gate.key))
             return
-        if measured.intersection(idx):
-            raise NotImplementedError("mid-circuit measurement: only terminal measurements are supported")
+        if sites is None and not dephase_measurements and measured.intersection(idx):
+            raise NotImplementedError("mid-circuit measurement in an evolve-once program: use trajectories.TrajectoryProgram "
+                                      "(DensityMatrixSimulator.run / simulate do)")
         if len(idx) > 2:
             dec = getattr(op, "_decompose_", None)
             if dec is None:

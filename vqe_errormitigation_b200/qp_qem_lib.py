@@ -6,9 +6,14 @@ Differences from the reference, on purpose:
   * ``QPSamp.sampled_measurement`` draws all ``sample_reps`` circuit variants at once and evaluates them as ONE GPU
     batch (the reference loops serially, "will be parallelized", QP_QEM_lib.py:753); shots are then drawn from
     the exact outcome probability of each variant;
-  * projector basis operations are applied in their matrix form (``basis_ops``: ``Pz``), not as mid-circuit
-    ``MeasurementGate``s (``basis_ops_sim``) — for the noise models this code can mitigate their quasi-probability
-    is exactly zero, so they are never drawn (SURVEY.md App. C.3);
+  * ``sampled_measurement`` applies projector basis operations in their matrix form (``basis_ops``: ``Pz``).  The
+    reference builds its sampled circuit from ``basis_ops_sim`` (QP_QEM_lib.py:787-791), whose projectors are
+    ``MeasurementGate(1, key='M')`` — the key of the terminal measurement, so a circuit that drew one is rejected by
+    cirq's ``run()`` ("Measurement key M repeated"); for the noise models this code can mitigate the
+    quasi-probability of those operations is exactly zero, so they are never drawn.  The
+    measurement dialect itself is available: ``sampled_circuit_sim`` builds that circuit with distinct keys and
+    ``postselected_expectation`` runs it through the engine's mid-circuit measurement path (``trajectories``) with
+    the post-selection Ref. 2 prescribes;
   * plotting at the end of ``run_experiment`` is omitted; undefined names of the original (``protocols`` at :135,
     ``error_type`` at :542) are not reproduced.
 """
@@ -124,8 +129,8 @@ def basis_ops():
 
 
 def basis_ops_sim():
-    """Same, with projectors as ``MeasurementGate(1, key='M')`` (QP_QEM_lib.py:191-243).  Kept for API parity;
-    the engine does not simulate mid-circuit measurement."""
+    """Same, with projectors as ``MeasurementGate(1, key='M')`` (QP_QEM_lib.py:191-243): "postselection detailed in
+    Ref. 2" — a shot counts only when every such measurement reads 0 (``QPSamp.postselected_expectation``)."""
     return _basis_tuples(lambda: cirq.MeasurementGate(1, key="M"))
 
 
@@ -332,6 +337,52 @@ class QPSamp:
         rng = np.random.default_rng(np.random.randint(0, 2 ** 31 - 1))
         hits = rng.binomial(meas_reps, np.clip(p0, 0.0, 1.0))
         self.exp_sampled.append(float(np.mean(signs * (2.0 * hits / meas_reps - 1.0))))
+
+    def sampled_circuit_sim(self, row: Sequence[int]):
+        """The sampled circuit of identifier ``row`` (one basis-operation index per gate) in the ``basis_ops_sim`` dialect, as
+        QP_QEM_lib.py:758-795 assembles it: gate, noise, the basis operation as a gate tuple with ``MeasurementGate``s where it
+        projects, noise again unless the operation is the identity.  The inserted measurements get their own keys
+        (``P<gate>.<qubit>.<k>``; the reference re-uses 'M').  Returns (circuit, inserted keys)."""
+        out = cirq.Circuit()
+        keys: List[str] = []
+
+        def place(tup, qubit, tag):
+            for k, g in enumerate(tup):
+                if isinstance(g, cirq.MeasurementGate):
+                    keys.append(f"P{tag}.{k}")
+                    out.append(cirq.MeasurementGate(1, key=keys[-1]).on(qubit))
+                else:
+                    out.append(g.on(qubit))
+
+        s = 0
+        for op in self.circuit.all_operations():
+            out.append(op)
+            if isinstance(op.gate, cirq.MeasurementGate):
+                continue
+            noise = noise_model(dim=len(op.qubits), error_type=self.error_type, error=self.error)
+            out.append(noise(*op.qubits))
+            idx = int(row[s])
+            if len(op.qubits) == 1:
+                place(self.B_ops_circuit[idx], op.qubits[0], f"{s}.0")
+            else:
+                place(self.B_ops_circuit[idx >> 4], op.qubits[0], f"{s}.0")
+                place(self.B_ops_circuit[idx & 15], op.qubits[1], f"{s}.1")
+            if idx != 0:
+                out.append(noise(*op.qubits))
+            s += 1
+        return out, keys
+
+    def postselected_expectation(self, row: Sequence[int], meas_reps: int, simulator=None) -> float:
+        """<Z> of the terminal measurement over the shots whose inserted measurements all read 0, per shot TAKEN (the
+        unnormalised estimate post-selection gives: rejected shots count as 0)."""
+        circuit, keys = self.sampled_circuit_sim(row)
+        sim = simulator if simulator is not None else cirq.DensityMatrixSimulator()
+        result = sim.run(circuit, repetitions=meas_reps)
+        keep = np.ones(meas_reps, dtype=bool)
+        for k in keys:
+            keep &= ~result.measurements[k].any(axis=1)
+        final = result.measurements["M"][:, 0].astype(np.int64)
+        return float(np.sum(keep * (1 - 2 * final)) / meas_reps)
 
     def _plain_measurement(self, circuit, meas_reps) -> float:
         result = cirq.DensityMatrixSimulator().run(circuit, repetitions=meas_reps)
