@@ -172,8 +172,11 @@ __device__ __forceinline__ void dense16(double (&v)[16], const double* __restric
 
 extern __shared__ __align__(16) double dmx_smem[];
 
-template <int G>
-__global__ void __launch_bounds__(512) dmx_tile_kernel(const TileArgs a) {
+// G = 16-coefficient groups a thread carries per sweep; MAXT = CTA size bound.  A 7-qubit tile (1024 groups) runs either as
+// 512 threads x 2 groups or as 1024 threads x 1 group (plan option "tile_threads"): the tile fills an SM's shared memory, so
+// the second form is the only way to put 32 warps instead of 16 behind the barrier-separated sweeps.
+template <int G, int MAXT = 512>
+__global__ void __launch_bounds__(MAXT) dmx_tile_kernel(const TileArgs a) {
     double* tile = dmx_smem;
     const int tid = threadIdx.x, nthr = blockDim.x;
     const int tbits = 2 * a.k + a.pad;               // index bits of one circuit's tile
@@ -1910,13 +1913,14 @@ static int pass_max_chains(const Plan& p, const Pass& ps) {
 
 static int launch_tile(const TileArgs& a, int grid, int threads, int groups_per_thread, size_t smem, cudaStream_t st) {
     static std::mutex mu;
-    static size_t configured[2] = {0, 0};
-    const int gi = groups_per_thread == 2 ? 1 : 0;
+    static size_t configured[3] = {0, 0, 0};
+    const int gi = threads == 1024 ? 2 : (groups_per_thread == 2 ? 1 : 0);
     {
         std::lock_guard<std::mutex> lock(mu);
         if (smem > configured[gi]) {
             const int want = (int)std::max(smem, (size_t)48 * 1024);
-            if (gi) CUDA_TRY(cudaFuncSetAttribute(dmx_tile_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, want));
+            if (gi == 2) CUDA_TRY(cudaFuncSetAttribute(dmx_tile_kernel<1, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, want));
+            else if (gi) CUDA_TRY(cudaFuncSetAttribute(dmx_tile_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, want));
             else CUDA_TRY(cudaFuncSetAttribute(dmx_tile_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, want));
             configured[gi] = want;
         }
@@ -1931,9 +1935,11 @@ static int launch_tile(const TileArgs& a, int grid, int threads, int groups_per_
         at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
         at[0].val.programmaticStreamSerializationAllowed = 1;
         cfg.attrs = at; cfg.numAttrs = 1;
-        if (gi) CUDA_TRY(cudaLaunchKernelEx(&cfg, dmx_tile_kernel<2>, a));
+        if (gi == 2) CUDA_TRY(cudaLaunchKernelEx(&cfg, dmx_tile_kernel<1, 1024>, a));
+        else if (gi) CUDA_TRY(cudaLaunchKernelEx(&cfg, dmx_tile_kernel<2>, a));
         else CUDA_TRY(cudaLaunchKernelEx(&cfg, dmx_tile_kernel<1>, a));
-    } else if (gi) dmx_tile_kernel<2><<<grid, threads, smem, st>>>(a);
+    } else if (gi == 2) dmx_tile_kernel<1, 1024><<<grid, threads, smem, st>>>(a);
+    else if (gi) dmx_tile_kernel<2><<<grid, threads, smem, st>>>(a);
     else dmx_tile_kernel<1><<<grid, threads, smem, st>>>(a);
     ++g_launches;
     CUDA_TRY(cudaGetLastError());
@@ -1942,9 +1948,10 @@ static int launch_tile(const TileArgs& a, int grid, int threads, int groups_per_
 
 enum OutMode { OUT_ENERGY = 1, OUT_PAULI = 2 };
 
-static void tile_geometry(unsigned elems, int* threads, int* gpt) {
+static void tile_geometry(unsigned elems, int* threads, int* gpt, int wide_cta = 0) {
     const unsigned ng = elems >> 4;
-    if (ng > 512) { *threads = 512; *gpt = 2; }
+    if (ng > 512 && wide_cta) { *threads = 1024; *gpt = 1; }
+    else if (ng > 512) { *threads = 512; *gpt = 2; }
     else if (ng > 256) { *threads = 512; *gpt = 1; }
     else { *threads = 256; *gpt = 1; }
 }
@@ -1968,7 +1975,7 @@ static int run_tile_single(Plan& p, DevPlan* d, long long batch, const double* p
     a.group = group;
     const unsigned E = (unsigned)a.cpb << (2 * p.n + a.pad);
     int threads, gpt;
-    tile_geometry(E, &threads, &gpt);
+    tile_geometry(E, &threads, &gpt, p.opt_tile_threads == 1024);
     const size_t smem = (size_t)E * 8 + (size_t)a.cpb * a.max_chains * 128;
     if (smem > 227 * 1024) return fail(DMX_ERR_UNSUPPORTED, "tile does not fit shared memory");
     long long groups = (batch + a.cpb - 1) / a.cpb;
@@ -2387,6 +2394,9 @@ int dmx_plan_set_option(dmx_plan* plan, const char* key, int value) {
         plan->p.opt_scale_smem = value != 0;
     } else if (k == "direct_store") {
         plan->p.opt_direct_store = value != 0;
+    } else if (k == "tile_threads") {
+        if (value != 512 && value != 1024) return fail(DMX_ERR_INVALID, "tile_threads must be 512 or 1024");
+        plan->p.opt_tile_threads = value;
     } else return fail(DMX_ERR_INVALID, "unknown option: " + k);
     return DMX_OK;
 }

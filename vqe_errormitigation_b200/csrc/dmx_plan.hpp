@@ -195,6 +195,7 @@ struct Plan {
     int opt_bulk = 1;                   // streaming tile load: 0 register staging, 1 cp.async.bulk + mbarrier, 2 direct global loads
     int opt_wide = 0;                   // streaming triple sweeps: absorb tile-wide leading / trailing monomial blocks (Sweep3::wide)
     int opt_scale_smem = 0;             // streaming: permutation scale tables in shared memory (LDS.128) instead of the constant bank
+    int opt_tile_threads = 512;         // whole-state 7-qubit tiles: 512 threads x 2 groups or 1024 threads x 1 group per sweep
     int opt_direct_store = 1;           // streaming: the last sweep of a pass writes its registers straight to global memory
     bool finalized = false;
 
