@@ -899,6 +899,9 @@ def run_workload(wl, ctx, steps: int, warmup: int, with_cpu_baseline: bool, with
             2: "dmx_stream3_kernel / dmx_stream3b_kernel (streaming passes)"}[info["path"]]
     if info["path"] == 1 and variants_h is None and info["n_params"] == 1 and B >= 32768 and PLAN_OPTIONS.get("frame32s", 1) != 0:
         kern = "dmx_frame32s_kernel (sweep form of the frame kernel: 32 circuits per warp, tables in shared memory)"
+    if (info["path"] == 1 and variants_h is None and info["n_params"] == 1 and B >= 2048 and PLAN_OPTIONS.get("frame16t", 1) != 0
+            and "\nf16 n=" in prog.dump()):
+        kern = "dmx_frame16t_kernel (thread-per-circuit form of the frame kernel: 16 touched coefficients in registers, XOR-paired per segment)"
     traffic = ncu_util = None
     tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
     if os.path.exists(tpath):

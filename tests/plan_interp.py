@@ -90,6 +90,11 @@ def parse(dump: str) -> dict:
             plan["f32"] = {"n": int(kv["n"]), "orig": _nums(kv["orig"], int), "init": _nums(kv["init"]), "eweight": _nums(kv["eweight"]), "segs": []}
         elif head == "f32seg":
             plan["f32"]["segs"].append({"partner": _nums(kv["partner"], int), "w": _nums(kv["w"]).reshape(32, 2)})
+        elif head == "f16":
+            plan["f16"] = {"n": int(kv["n"]), "lane": _nums(kv["lane"], int), "mask": _nums(kv["mask"], int), "init": _nums(kv["init"]),
+                           "eweight": _nums(kv["eweight"]), "segs": []}
+        elif head == "f16seg":
+            plan["f16"]["segs"].append(_nums(kv["tab"]).reshape(16, 4))
         elif head == "fclass":
             plan["fclasses"].append({"param": int(kv["param"]), "scale": float(kv["scale"]), "offset": float(kv["offset"])})
         elif head == "flabel":
@@ -470,6 +475,23 @@ def run_frame32(plan, params=None, variants=None):
         cme = np.where((np.asarray(seg["partner"]) & 0x80) != 0, cm, 1.0)     # bit 7: the rotation moves this coefficient
         r = cme * (w0 * r) + sm * (w1 * other)
     return float(np.dot(f32["eweight"], r))
+
+
+def run_frame16t(plan, params):
+    """Interpret the thread-per-circuit tables as dmx_frame16t_kernel does: 16 slots, slot i pairs with i ^ mask[k]."""
+    f16 = plan.get("f16")
+    if f16 is None:
+        return None
+    cl = plan["fclasses"][0]
+    th = cl["scale"] * params[cl["param"]] + cl["offset"]
+    c, s = np.cos(th), np.sin(th)
+    r = f16["init"].copy()
+    idx = np.arange(16)
+    for k, tab in enumerate(f16["segs"]):
+        m = int(f16["mask"][k])
+        own = tab[:, 0] * c + tab[:, 1]
+        r = own * r + (tab[:, 2] * s) * r[idx ^ m]
+    return float(np.dot(f16["eweight"][:16], r) + f16["eweight"][16])
 
 
 def run_frame(plan, params=None, variants=None):

@@ -251,7 +251,8 @@ BOND_LENGTHS = [0.1, 0.2, 0.3, 0.4, 0.5, 0.6, 0.7, 0.7414, 0.8, 0.9, 1.0, 1.1, 1
 def test_grouped_energies_match_per_molecule_plans():
     """Coefficient groups (dmx_plan_set_hamiltonian_groups / dmx_energy_batch_grouped): ONE noisy-H2 plan with one
     coefficient row per bond length gives, row by row, the energies of 30 separate per-molecule plans and of the oracle -
-    on the device path, the host path (DMA pipeline and zero-copy) and through the frame32s sweep kernel."""
+    on the device path, the host path (DMA pipeline and zero-copy), through the thread-per-circuit kernel (the default at
+    this batch size), the frame32s sweep kernel and the warp-per-circuit kernels."""
     import torch
     from workloads import h2_terms, h2_ops, build_program
     from oracle import dm_oracle as O
@@ -273,7 +274,7 @@ def test_grouped_energies_match_per_molecule_plans():
     B = 4099
     alphas = rng.uniform(-0.4, 0.4, size=(B, 1))
     groups = rng.integers(0, len(keys), size=B).astype(np.int32)
-    for opts in ({}, {"frame32s": 8}, {"frame32": 0}, {"segments": 0}):
+    for opts in ({}, {"frame16t": 2}, {"frame16t": 0}, {"frame16t": 0, "frame32s": 8}, {"frame32": 0}, {"segments": 0}):
         prog = engine.CircuitProgram(b, hamiltonian=terms[0], coefficient_groups=rows, options=opts)
         got = prog.energies(torch.tensor(alphas, device="cuda"), groups=torch.tensor(groups, device="cuda")).cpu().numpy()
         for g in (0, 7, 29):
@@ -286,7 +287,7 @@ def test_grouped_energies_match_per_molecule_plans():
         assert abs(got[i] - O.energy_sparse(rho, O.pauli_terms_to_matrix(4, *terms[groups[i]]))) < 1e-10
         host = prog.energies_host(alphas, groups=groups)                       # pageable buffers: DMA pipeline
         assert np.max(np.abs(host - got)) < 1e-13
-        if not opts:
+        if not opts or opts.get("frame16t") == 2:
             pa, pg, po = engine.pinned_empty((B, 1)), engine.pinned_empty(B, np.int32), engine.pinned_empty(B)
             pa[...] = alphas
             pg[...] = groups

@@ -51,6 +51,44 @@ def test_h2_lowering(noise, options):
                 assert plan["f32"]["n"] <= 24              # noisy / clean H2: at most 24 of 256 coefficients matter
             if "f32" in plan:
                 assert abs(PI.run_frame32(plan, [a]) - want) < TOL
+            if noise != "ampdamp":
+                # thread-per-circuit form: the 8 UCCSD rotations touch 16 coefficients (rank-4 XOR pattern), 7 are constants
+                assert plan["f16"]["n"] == 16 and all(0 < m < 16 for m in plan["f16"]["mask"])
+                assert abs(PI.run_frame16t(plan, [a]) - want) < TOL
+
+
+def test_frame16t_tables_on_random_single_class_circuits():
+    """One-parameter Clifford + Pauli-noise + rotation circuits: whenever the lowering offers the thread-per-circuit tables
+    they reproduce the oracle; circuits whose rotations touch more than 16 coefficients must not offer them."""
+    rng = np.random.default_rng(2026)
+    cliff1 = [O.H, O.rx(np.pi / 2), O.rx(-np.pi / 2), O.rx(np.pi), O.rz(np.pi / 2), O.X, O.Z]
+    offered = 0
+    for trial in range(24):
+        n = int(rng.integers(2, 5))
+        ops = []
+        for _ in range(int(rng.integers(10, 40))):
+            kind = rng.integers(0, 4)
+            if kind == 0:
+                ops.append(("u", (int(rng.integers(n)),), cliff1[int(rng.integers(len(cliff1)))]))
+            elif kind == 1:
+                a, b = rng.choice(n, 2, replace=False)
+                ops.append(("u", (int(a), int(b)), O.CNOT))
+                ops.append(("k", (int(a), int(b)), O.two_qubit_depolarize(0.01)))
+            elif kind == 2:
+                ops.append(("k", (int(rng.integers(n)),), O.asymmetric_depolarize(0.01, 0.02, 0.005)))
+            else:
+                ops.append(("r", (int(rng.integers(n)),), (int(rng.integers(3)), "t0", 2.0, 0.0)))
+        terms = random_hamiltonian(rng, n, 6)
+        prog = build_program(ops, n, terms)
+        plan = PI.parse(prog.dump())
+        if "f16" not in plan:
+            continue
+        offered += 1
+        assert plan["f16"]["n"] <= 16 and len(plan["fclasses"]) == 1
+        for val in rng.normal(size=3):
+            want = O.energy_sparse(O.simulate(n, resolve(ops, prog.param_names, [val])), O.pauli_terms_to_matrix(n, *terms))
+            assert abs(PI.run_frame16t(plan, [val]) - want) < TOL
+    assert offered >= 3
 
 
 def test_frame_relabelling_keeps_h2_exchanges_inside_warps():

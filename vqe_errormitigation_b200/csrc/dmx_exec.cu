@@ -1095,6 +1095,104 @@ __global__ void __launch_bounds__(128, 4) dmx_frame32s_kernel(const Frame32sArgs
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// frame32, thread-per-circuit form ("frame16t"): parameter sweeps of a plan with ONE rotation class, no variant slots and
+// at most 16 coefficients that any rotation touches (Plan::f16_*; noisy H2 UCCSD: 16 of the 23 live ones, the other 7 are
+// constants of the plan).  One THREAD carries one circuit: its 16 coefficients stay in registers from the initial state
+// to the energy, a segment pairs register i with register i ^ mask - the mask is a property of the plan, so each of the
+// 16 possible values is its own unrolled code path chosen by a warp-uniform switch - and the segment weights come from
+// shared memory as broadcast LDS.128.  No shuffles (the warp-per-circuit kernels spend 2 SHFL.32 per circuit and
+// segment and idle 9 of 32 lanes), no per-warp sincos shared by 8 lanes: 4 FP64 instructions per coefficient and segment.
+// ---------------------------------------------------------------------------------------------------------
+struct Frame16tArgs {
+    int nseg, n_params;
+    long long batch;
+    const double4* tab;           // [nseg][16]: x = wc, y = wk (own factor = fma(wc, cos, wk)), z = w1 (partner factor = w1 * sin)
+    const double* eweight;        // [groups][17]: 16 weights + the group's constant
+    const int* group;             // optional coefficient row per circuit
+    const double* params;
+    double* out;
+    RotInfo cls;
+    double init[16];
+    unsigned char mask[48];
+};
+
+template <int M>
+__device__ __forceinline__ void f16_segment(double (&r)[16], const double4* __restrict__ T, double c, double s) {
+    if (M == 0) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) { const double4 t = T[i]; r[i] *= fma(t.x, c, t.y); }
+    } else {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            const int j = i ^ M;
+            if (j > i) {
+                const double4 ti = T[i], tj = T[j];
+                const double ri = r[i], rj = r[j];
+                // same rounding sequence as the warp-per-circuit kernels: sin * (w1 * partner) + (wc * cos + wk) * own
+                r[i] = fma(s, ti.z * rj, fma(ti.x, c, ti.y) * ri);
+                r[j] = fma(s, tj.z * ri, fma(tj.x, c, tj.y) * rj);
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(128) dmx_frame16t_kernel(const __grid_constant__ Frame16tArgs a) {
+    double4* const stab = reinterpret_cast<double4*>(dmx_smem);                 // [nseg][16]
+    double* const sew = reinterpret_cast<double*>(stab + a.nseg * 16);          // [17] weights of group 0
+    const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool mine = b < a.batch;
+    // the angle first: its DRAM round trip overlaps the table staging
+    const double x = mine ? a.params[b * a.n_params + a.cls.param] : 0.0;
+    const int g = (a.group && mine) ? a.group[b] : 0;
+    {
+        const double2* const src = reinterpret_cast<const double2*>(a.tab);
+        double2* const dst = reinterpret_cast<double2*>(stab);
+        for (int i = threadIdx.x; i < a.nseg * 32; i += blockDim.x) dst[i] = __ldg(src + i);
+    }
+    if (threadIdx.x < 17) sew[threadIdx.x] = __ldg(a.eweight + threadIdx.x);
+    double sv, cv;
+    sincos(fma(a.cls.scale, x, a.cls.offset), &sv, &cv);
+    double r[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) r[i] = a.init[i];
+    __syncthreads();
+#pragma unroll 1
+    for (int k = 0; k < a.nseg; ++k) {
+        const double4* __restrict__ T = stab + k * 16;
+        switch (a.mask[k]) {                   // kernel parameter: uniform
+            case 0: f16_segment<0>(r, T, cv, sv); break;
+            case 1: f16_segment<1>(r, T, cv, sv); break;
+            case 2: f16_segment<2>(r, T, cv, sv); break;
+            case 3: f16_segment<3>(r, T, cv, sv); break;
+            case 4: f16_segment<4>(r, T, cv, sv); break;
+            case 5: f16_segment<5>(r, T, cv, sv); break;
+            case 6: f16_segment<6>(r, T, cv, sv); break;
+            case 7: f16_segment<7>(r, T, cv, sv); break;
+            case 8: f16_segment<8>(r, T, cv, sv); break;
+            case 9: f16_segment<9>(r, T, cv, sv); break;
+            case 10: f16_segment<10>(r, T, cv, sv); break;
+            case 11: f16_segment<11>(r, T, cv, sv); break;
+            case 12: f16_segment<12>(r, T, cv, sv); break;
+            case 13: f16_segment<13>(r, T, cv, sv); break;
+            case 14: f16_segment<14>(r, T, cv, sv); break;
+            default: f16_segment<15>(r, T, cv, sv); break;
+        }
+    }
+    double e;
+    if (a.group) {
+        const double* __restrict__ ew = a.eweight + (size_t)g * 17;
+        e = __ldg(ew + 16);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) e = fma(__ldg(ew + i), r[i], e);
+    } else {
+        e = sew[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) e = fma(sew[i], r[i], e);
+    }
+    if (mine) a.out[b] = e;
+}
+
+// ---------------------------------------------------------------------------------------------------------
 // small kernels
 // ---------------------------------------------------------------------------------------------------------
 __global__ void dmx_energy_kernel(const double* __restrict__ state, int n, long long batch, const uint32_t* __restrict__ term_idx,
@@ -1422,6 +1520,8 @@ struct DevPlan {
     int n_eterms = 0, n_smem_segs = 0;
     // compact frame (frame32)
     double4* g_tab4 = nullptr;     // frame32s: (wc, wk, w1, partner) per (segment, lane)
+    double4* h_tab16 = nullptr;    // frame16t: (wc, wk, w1, -) per (segment, slot)
+    double* h_ew16 = nullptr;      // frame16t: [groups][17]
     double2* g_w = nullptr; unsigned char* g_partner = nullptr; int* g_cs_sel = nullptr; double* g_init = nullptr; double* g_ew = nullptr; int* g_orig = nullptr;
     SlotDev* slots = nullptr;
     uint8_t* labels = nullptr;
@@ -1839,6 +1939,13 @@ static int upload_plan(Plan& p, DevPlan* d, int dev) {
                     }
                 CUDA_TRY(upload(&d->g_tab4, t4));
             }
+            if (p.f16_n > 0) {
+                std::vector<double4> t16((size_t)K * 16);
+                for (size_t i = 0; i < t16.size(); ++i)
+                    t16[i] = make_double4(p.f16_tab[i * 4], p.f16_tab[i * 4 + 1], p.f16_tab[i * 4 + 2], p.f16_tab[i * 4 + 3]);
+                CUDA_TRY(upload(&d->h_tab16, t16));
+                CUDA_TRY(upload(&d->h_ew16, p.f16_eweight_g));
+            }
             CUDA_TRY(upload(&d->g_partner, p.f32_partner));
             CUDA_TRY(upload(&d->g_cs_sel, sel));
             CUDA_TRY(upload(&d->g_init, p.f32_init));
@@ -1871,6 +1978,7 @@ static void free_devplan(DevPlan* d) {
     cudaFree(d->coefs); cudaFree(d->rots); cudaFree(d->term_idx); cudaFree(d->term_coef);
     cudaFree(d->f_w); cudaFree(d->f_segs); cudaFree(d->f_classes); cudaFree(d->f_init); cudaFree(d->f_eweight); cudaFree(d->f_eslot);
     cudaFree(d->slots); cudaFree(d->labels);
+    cudaFree(d->h_tab16); cudaFree(d->h_ew16);
     cudaFree(d->g_tab4); cudaFree(d->g_w); cudaFree(d->g_partner); cudaFree(d->g_cs_sel); cudaFree(d->g_init); cudaFree(d->g_ew); cudaFree(d->g_orig);
     for (auto& px : d->passx) cudaFree(px.coefs);
     for (int i = 0; i < DevPlan::MAX_XS; ++i) if (d->xs[i]) cudaStreamDestroy(d->xs[i]);
@@ -2249,6 +2357,22 @@ static int run_segment(Plan& p, DevPlan* d, long long batch, const double* param
         // the event pair, the launch latency and one warp's critical path (tools/launch_floor.py), not the kernel.
         // opt_frame32s: 0 never, 1 automatic, 8 / 16 always 32 circuits per warp with that many advanced together,
         // 32 + cw: always cw circuits per warp (cw = 8 / 16 / 24 / 32).
+        // Thread-per-circuit form (dmx_frame16t_kernel) for batches that give every SM a few warps of circuits; single
+        // evaluations and small batches keep the warp-per-circuit kernels (one circuit's latency spread over 32 lanes).
+        if (p.f16_n > 0 && p.opt_frame16t && mode == 1 && !variants && !g.any_const && batch >= 2048 && (!host_mapped || p.opt_frame16t == 2)) {
+            Frame16tArgs f{};
+            f.nseg = p.nseg; f.n_params = p.n_params; f.batch = batch; f.tab = d->h_tab16; f.eweight = d->h_ew16; f.group = group;
+            f.params = params; f.out = out; f.cls = p.f_classes[0];
+            for (int i = 0; i < 16; ++i) f.init[i] = p.f16_init[i];
+            for (int k = 0; k < p.nseg; ++k) f.mask[k] = p.f16_mask[k];
+            const long long grid = (batch + 127) / 128;
+            if (grid >= (1LL << 31)) return done(fail(DMX_ERR_UNSUPPORTED, "batch too large for one launch"));
+            const size_t smem = (size_t)p.nseg * 512 + 256;
+            dmx_frame16t_kernel<<<(unsigned)grid, 128, smem, st>>>(f);
+            ++g_launches;
+            CUDA_TRY(cudaGetLastError());
+            return done(DMX_OK);
+        }
         int cw = 0, cpb = 8;
         const int f32s_opt = p.opt_frame32s;
         // (mapped host buffers stay on the 8-circuit kernel: its 1024 CTAs each moving a 512-byte block keep more PCIe reads in
@@ -2394,6 +2518,9 @@ int dmx_plan_set_option(dmx_plan* plan, const char* key, int value) {
         plan->p.opt_scale_smem = value != 0;
     } else if (k == "direct_store") {
         plan->p.opt_direct_store = value != 0;
+    } else if (k == "frame16t") {
+        if (value < 0 || value > 2) return fail(DMX_ERR_INVALID, "frame16t must be 0 (never), 1 (device-resident batches) or 2 (also mapped host buffers)");
+        plan->p.opt_frame16t = value;
     } else if (k == "tile_threads") {
         if (value != 512 && value != 1024) return fail(DMX_ERR_INVALID, "tile_threads must be 512 or 1024");
         plan->p.opt_tile_threads = value;

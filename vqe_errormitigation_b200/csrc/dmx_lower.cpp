@@ -2276,6 +2276,91 @@ static void build_frame32(Plan& p) {
     }
 }
 
+// Thread-per-circuit tables (Plan::f16_*) from the compact frame.  Needs the per-group compact energy weights.
+static void build_frame16t(Plan& p) {
+    p.f16_n = 0;
+    const int K = p.nseg;
+    if (p.f32_n <= 0 || p.f_classes.size() != 1 || K < 1 || K > 48 || p.n_slots != 0) return;
+    for (int k = 0; k < K; ++k) if (p.fsegs[k].cs_sel != 0) return;            // every segment is a rotation of the one class
+    auto flagged = [&](int k, int l) { return (p.f32_partner[(size_t)k * 32 + l] & 0x80u) != 0; };
+    std::vector<int> touched;
+    std::vector<unsigned> used_masks;
+    for (int l = 0; l < 32; ++l) {
+        if (p.f32_orig[l] < 0) continue;
+        bool any = false;
+        for (int k = 0; k < K; ++k) any = any || flagged(k, l);
+        if (any) touched.push_back(l);
+    }
+    if (touched.empty() || touched.size() > 16) return;
+    for (int k = 0; k < K; ++k) {
+        bool any = false;
+        for (int l : touched) any = any || flagged(k, l);
+        if (any && p.fsegs[k].xor_mask) used_masks.push_back((unsigned)p.fsegs[k].xor_mask);
+    }
+    // reduced echelon basis of span{masks}: every pivot bit is set in exactly one basis vector
+    std::vector<unsigned> basis;
+    std::vector<int> pivot;
+    for (unsigned v : used_masks) {
+        for (size_t j = 0; j < basis.size(); ++j) if ((v >> pivot[j]) & 1u) v ^= basis[j];
+        if (!v) continue;
+        const int pb = 31 - __builtin_clz(v);
+        for (size_t j = 0; j < basis.size(); ++j) if ((basis[j] >> pb) & 1u) basis[j] ^= v;
+        basis.push_back(v); pivot.push_back(pb);
+    }
+    const int rho = (int)basis.size();
+    if (rho > 4) return;
+    auto coords = [&](unsigned t) { unsigned c = 0; for (int j = 0; j < rho; ++j) c |= ((t >> pivot[j]) & 1u) << j; return c; };
+    auto rep = [&](unsigned t) { for (int j = 0; j < rho; ++j) if ((t >> pivot[j]) & 1u) t ^= basis[j]; return t; };
+    std::vector<unsigned> reps;
+    std::vector<int> slot_of(32, -1), lane_of_slot(16, -1);
+    for (int l : touched) {
+        const unsigned t = (unsigned)p.f32_orig[l], r = rep(t);
+        size_t c = 0;
+        while (c < reps.size() && reps[c] != r) ++c;
+        if (c == reps.size()) reps.push_back(r);
+        if (((c + 1) << rho) > 16) return;
+        const int sl = (int)((c << rho) | coords(t));
+        if (lane_of_slot[sl] >= 0) return;                                       // cannot happen for distinct t; defensive
+        slot_of[l] = sl; lane_of_slot[sl] = l;
+    }
+    p.f16_mask.assign(K, 0);
+    p.f16_tab.assign((size_t)K * 64, 0.0);
+    p.f16_init.assign(16, 0.0);
+    for (int k = 0; k < K; ++k) {
+        bool any = false;
+        for (int l : touched) any = any || flagged(k, l);
+        const unsigned m = any ? coords((unsigned)p.fsegs[k].xor_mask) : 0u;
+        p.f16_mask[k] = (uint8_t)m;
+        for (int i = 0; i < 16; ++i) {
+            double* e = &p.f16_tab[((size_t)k * 16 + i) * 4];
+            const int l = lane_of_slot[i];
+            if (l < 0) { e[1] = 1.0; continue; }
+            const double w0 = p.f32_w[((size_t)k * 32 + l) * 2], w1 = p.f32_w[((size_t)k * 32 + l) * 2 + 1];
+            if (flagged(k, l)) { e[0] = w0; e[2] = w1; } else { e[1] = w0; }
+            if (w1 != 0.0) {
+                const int lp = p.f32_partner[(size_t)k * 32 + l] & 31;
+                if (slot_of[lp] != (i ^ (int)m)) return;                          // partner outside the XOR pattern: keep frame32
+            }
+        }
+    }
+    for (int i = 0; i < 16; ++i) if (lane_of_slot[i] >= 0) p.f16_init[i] = p.f32_init[lane_of_slot[i]];
+    const size_t G = (size_t)std::max(p.n_groups, 1);
+    p.f16_eweight_g.assign(G * 17, 0.0);
+    for (size_t g = 0; g < G; ++g) {
+        for (int i = 0; i < 16; ++i) if (lane_of_slot[i] >= 0) p.f16_eweight_g[g * 17 + i] = p.f32_eweight_g[g * 32 + lane_of_slot[i]];
+        double c = 0.0;                                                           // coefficients no rotation touches: constants of the plan
+        for (int l = 0; l < 32; ++l) {
+            if (p.f32_orig[l] < 0 || slot_of[l] >= 0) continue;
+            double v = p.f32_init[l];
+            for (int k = 0; k < K; ++k) v *= p.f32_w[((size_t)k * 32 + l) * 2];
+            c += p.f32_eweight_g[g * 32 + l] * v;
+        }
+        p.f16_eweight_g[g * 17 + 16] = c;
+    }
+    p.f16_lane = lane_of_slot;
+    p.f16_n = (int)touched.size();
+}
+
 static bool build_frame(Plan& p, std::string& why) {
     const int K = p.nseg;
     std::vector<int> holder(SEG_E), nh(SEG_E);
@@ -2411,6 +2496,7 @@ static bool build_frame(Plan& p, std::string& why) {
                     if (p.f32_orig[l] >= 0) p.f32_eweight_g[g * 32 + l] = p.f_eweight_g[g * SEG_E + p.f32_orig[l]];
         }
     }
+    build_frame16t(p);
     return true;
 }
 
@@ -2421,7 +2507,7 @@ void lower_plan(Plan& p) {
     if (const char* env = std::getenv("DMX_WIDE")) p.opt_wide = std::atoi(env) != 0;      // test hook: whole-suite A/B of the wide builder
     p.blocks.clear(); p.rots.clear(); p.mus.clear(); p.sweeps.clear(); p.factors.clear(); p.chains.clear(); p.phases.clear();
     p.coefs.clear(); p.passes.clear();
-    p.remapped = false; p.triples = false; p.sweeps3.clear(); p.f32_n = 0;
+    p.remapped = false; p.triples = false; p.sweeps3.clear(); p.f32_n = 0; p.f16_n = 0;
     p.cpb = plan_cpb(p.n);
     p.segs.clear(); p.slots.clear(); p.term_idx.clear(); p.term_coef.clear();
     std::memset(&p.info, 0, sizeof(p.info));
@@ -2518,6 +2604,8 @@ void lower_plan(Plan& p) {
         for (const FrameSeg& fs : p.fsegs) smem_segs += !fs.use_shfl;
         // the compact frame kernel executes the segments on 32 lanes per circuit instead of 256 threads
         in.flops_per_circuit = (p.nseg * 4.0 + 1.0) * (p.f32_n > 0 ? 32.0 : (double)SEG_E) + 2.0 * p.e_w.size();
+        // thread-per-circuit form: 16 slots x (fma + 2 mul + fma = 6 flops) per segment, 16 fma for the energy
+        if (p.f16_n > 0 && p.opt_frame16t) in.flops_per_circuit = p.nseg * 96.0 + 32.0;
         // per circuit: smem-exchange segments move 8 B out + 8 B in per coefficient; the energy stage a few terms
         in.smem_bytes_per_circuit = smem_segs * SEG_E * 16.0 + 16.0 * p.e_w.size();
         in.hbm_bytes_per_circuit = io;
@@ -2651,6 +2739,19 @@ std::string dump_plan(const Plan& p) {
                 os << "f32seg " << k;
                 dump_ints(os, "partner", std::vector<int>(p.f32_partner.begin() + (size_t)k * 32, p.f32_partner.begin() + (size_t)(k + 1) * 32));
                 dump_vec(os, "w", std::vector<double>(p.f32_w.begin() + (size_t)k * 64, p.f32_w.begin() + (size_t)(k + 1) * 64));
+                os << "\n";
+            }
+        }
+        if (p.f16_n > 0) {
+            os << "f16 n=" << p.f16_n;
+            dump_ints(os, "lane", p.f16_lane);
+            dump_ints(os, "mask", std::vector<int>(p.f16_mask.begin(), p.f16_mask.end()));
+            dump_vec(os, "init", p.f16_init);
+            dump_vec(os, "eweight", std::vector<double>(p.f16_eweight_g.begin(), p.f16_eweight_g.begin() + 17));
+            os << "\n";
+            for (int k = 0; k < p.nseg; ++k) {
+                os << "f16seg " << k;
+                dump_vec(os, "tab", std::vector<double>(p.f16_tab.begin() + (size_t)k * 64, p.f16_tab.begin() + (size_t)(k + 1) * 64));
                 os << "\n";
             }
         }

@@ -248,6 +248,19 @@ struct Plan {
     std::vector<double> f32_w;        // [nseg][32][2]
     std::vector<double> f32_init, f32_eweight;   // [32]
 
+    // Thread-per-circuit form of the compact frame ("frame16t", dmx_frame16t_kernel): one rotation class, at most 16
+    // coefficients that any rotation ever touches.  A rotation pairs coefficient t with t ^ xor_mask in the frame index
+    // space, so the touched coefficients sit in a few cosets of span{xor masks} (GF(2) rank <= 4) and can be numbered
+    // 0..15 such that every segment pairs slot i with slot i ^ f16_mask[k]: a compile-time register pattern per mask value,
+    // no shuffles, no lane idles.  Coefficients no rotation touches are constants of the plan and fold into the energy.
+    int f16_n = 0;                       // touched coefficients (0: form not available)
+    std::vector<int> f16_lane;           // [16] compact-frame lane (f32 index) held by slot i, -1 = unused slot
+    std::vector<uint8_t> f16_mask;       // [nseg]
+    std::vector<double> f16_tab;         // [nseg][16][4] = (wc, wk, w1, 0): own factor fma(wc, cos, wk), partner factor w1 * sin
+    std::vector<double> f16_init;        // [16]
+    std::vector<double> f16_eweight_g;   // [max(n_groups, 1)][17]: 16 energy weights + the constant part of that group
+    int opt_frame16t = 1;                // 0 never, 1 device-resident batches from 2048 circuits, 2 also mapped host buffers
+
     dmx_plan_info info{};
 
     // device mirror (owned by dmx_exec.cu)
