@@ -1136,7 +1136,7 @@ __device__ __forceinline__ void f16_segment(double (&r)[16], const double4* __re
     }
 }
 
-__global__ void __launch_bounds__(128) dmx_frame16t_kernel(const __grid_constant__ Frame16tArgs a) {
+__global__ void __launch_bounds__(256) dmx_frame16t_kernel(const __grid_constant__ Frame16tArgs a) {
     double4* const stab = reinterpret_cast<double4*>(dmx_smem);                 // [nseg][16]
     double* const sew = reinterpret_cast<double*>(stab + a.nseg * 16);          // [17] weights of group 0
     const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -2365,10 +2365,11 @@ static int run_segment(Plan& p, DevPlan* d, long long batch, const double* param
             f.params = params; f.out = out; f.cls = p.f_classes[0];
             for (int i = 0; i < 16; ++i) f.init[i] = p.f16_init[i];
             for (int k = 0; k < p.nseg; ++k) f.mask[k] = p.f16_mask[k];
-            const long long grid = (batch + 127) / 128;
+            const int threads = p.opt_f16_threads;
+            const long long grid = (batch + threads - 1) / threads;
             if (grid >= (1LL << 31)) return done(fail(DMX_ERR_UNSUPPORTED, "batch too large for one launch"));
             const size_t smem = (size_t)p.nseg * 512 + 256;
-            dmx_frame16t_kernel<<<(unsigned)grid, 128, smem, st>>>(f);
+            dmx_frame16t_kernel<<<(unsigned)grid, threads, smem, st>>>(f);
             ++g_launches;
             CUDA_TRY(cudaGetLastError());
             return done(DMX_OK);
@@ -2521,6 +2522,9 @@ int dmx_plan_set_option(dmx_plan* plan, const char* key, int value) {
     } else if (k == "frame16t") {
         if (value < 0 || value > 2) return fail(DMX_ERR_INVALID, "frame16t must be 0 (never), 1 (device-resident batches) or 2 (also mapped host buffers)");
         plan->p.opt_frame16t = value;
+    } else if (k == "frame16t_threads") {
+        if (value != 64 && value != 128 && value != 256) return fail(DMX_ERR_INVALID, "frame16t_threads must be 64, 128 or 256");
+        plan->p.opt_f16_threads = value;
     } else if (k == "tile_threads") {
         if (value != 512 && value != 1024) return fail(DMX_ERR_INVALID, "tile_threads must be 512 or 1024");
         plan->p.opt_tile_threads = value;

@@ -259,6 +259,7 @@ struct Plan {
     std::vector<double> f16_tab;         // [nseg][16][4] = (wc, wk, w1, 0): own factor fma(wc, cos, wk), partner factor w1 * sin
     std::vector<double> f16_init;        // [16]
     std::vector<double> f16_eweight_g;   // [max(n_groups, 1)][17]: 16 energy weights + the constant part of that group
+    int opt_f16_threads = 128;           // CTA size of dmx_frame16t_kernel
     int opt_frame16t = 1;                // 0 never, 1 device-resident batches from 2048 circuits, 2 also mapped host buffers
 
     dmx_plan_info info{};
