@@ -91,10 +91,14 @@ def parse(dump: str) -> dict:
         elif head == "f32seg":
             plan["f32"]["segs"].append({"partner": _nums(kv["partner"], int), "w": _nums(kv["w"]).reshape(32, 2)})
         elif head == "f16":
-            plan["f16"] = {"n": int(kv["n"]), "lane": _nums(kv["lane"], int), "mask": _nums(kv["mask"], int), "init": _nums(kv["init"]),
-                           "eweight": _nums(kv["eweight"]), "segs": []}
+            plan["f16"] = {"n": int(kv["n"]), "scaled": int(kv["scaled"]), "lane": _nums(kv["lane"], int), "mask": _nums(kv["mask"], int),
+                           "init": _nums(kv["init"]), "eweight": _nums(kv["eweight"]), "segs": [], "kappa": []}
+            if "sweight" in kv:
+                plan["f16"]["sweight"] = _nums(kv["sweight"])
         elif head == "f16seg":
             plan["f16"]["segs"].append(_nums(kv["tab"]).reshape(16, 4))
+            if "kappa" in kv:
+                plan["f16"]["kappa"].append(_nums(kv["kappa"]))
         elif head == "fclass":
             plan["fclasses"].append({"param": int(kv["param"]), "scale": float(kv["scale"]), "offset": float(kv["offset"])})
         elif head == "flabel":
@@ -492,6 +496,29 @@ def run_frame16t(plan, params):
         own = tab[:, 0] * c + tab[:, 1]
         r = own * r + (tab[:, 2] * s) * r[idx ^ m]
     return float(np.dot(f16["eweight"][:16], r) + f16["eweight"][16])
+
+
+def run_frame16t_scaled(plan, params):
+    """The scaled form of dmx_frame16t_kernel: rho_i' = cos rho_i + kappa_i sin rho_j, kappa stored per pair in loop order."""
+    f16 = plan.get("f16")
+    if f16 is None or not f16["scaled"]:
+        return None
+    cl = plan["fclasses"][0]
+    th = cl["scale"] * params[cl["param"]] + cl["offset"]
+    c, s = np.cos(th), np.sin(th)
+    r = f16["init"].copy()
+    for k, kap in enumerate(f16["kappa"]):
+        m = int(f16["mask"][k])
+        new = r.copy()
+        pair = 0
+        for i in range(16):
+            j = i ^ m
+            if j > i:
+                new[i] = kap[2 * pair] * (s * r[j]) + c * r[i]
+                new[j] = kap[2 * pair + 1] * (s * r[i]) + c * r[j]
+                pair += 1
+        r = new
+    return float(np.dot(f16["sweight"][:16], r) + f16["sweight"][16])
 
 
 def run_frame(plan, params=None, variants=None):

@@ -129,11 +129,13 @@ def test_thread_per_circuit_kernel_against_oracle_and_warp_kernels():
     for name, (n1, n2) in noises.items():
         thread = build_program(h2_ops(n1, n2), 4, terms)
         warp = build_program(h2_ops(n1, n2), 4, terms, frame16t=0)
-        assert "f16 n=16" in thread.dump(), name
+        general = build_program(h2_ops(n1, n2), 4, terms, frame16t_scaled=0)      # four-instruction form with explicit weights
+        assert "f16 n=16 scaled=1" in thread.dump(), name
         for B in (65536, 2048, 2049, 4099):
             a = np.linspace(-0.5, 0.5, B).reshape(-1, 1) if B == 65536 else rng.normal(0, 0.4, size=(B, 1))
             got = thread.energies(torch.tensor(a)).cpu().numpy()
             assert np.max(np.abs(got - warp.energies(torch.tensor(a)).cpu().numpy())) < 1e-14, (name, B)
+            assert np.max(np.abs(got - general.energies(torch.tensor(a)).cpu().numpy())) < 1e-14, (name, B)
             for i in (0, 1, B // 3, B - 1):
                 assert abs(got[i] - oracle_energy(h2_ops(n1, n2, alpha=a[i, 0]), 4, ham)) < TOL, (name, B, i)
     # below 2048 circuits the call stays on the warp-per-circuit kernels: identical results with the form switched off

@@ -55,6 +55,7 @@ def test_h2_lowering(noise, options):
                 # thread-per-circuit form: the 8 UCCSD rotations touch 16 coefficients (rank-4 XOR pattern), 7 are constants
                 assert plan["f16"]["n"] == 16 and all(0 < m < 16 for m in plan["f16"]["mask"])
                 assert abs(PI.run_frame16t(plan, [a]) - want) < TOL
+                assert plan["f16"]["scaled"] == 1 and abs(PI.run_frame16t_scaled(plan, [a]) - want) < TOL
 
 
 def test_frame16t_tables_on_random_single_class_circuits():
@@ -62,7 +63,7 @@ def test_frame16t_tables_on_random_single_class_circuits():
     they reproduce the oracle; circuits whose rotations touch more than 16 coefficients must not offer them."""
     rng = np.random.default_rng(2026)
     cliff1 = [O.H, O.rx(np.pi / 2), O.rx(-np.pi / 2), O.rx(np.pi), O.rz(np.pi / 2), O.X, O.Z]
-    offered = 0
+    offered = scaled = 0
     for trial in range(24):
         n = int(rng.integers(2, 5))
         ops = []
@@ -85,10 +86,13 @@ def test_frame16t_tables_on_random_single_class_circuits():
             continue
         offered += 1
         assert plan["f16"]["n"] <= 16 and len(plan["fclasses"]) == 1
+        scaled += plan["f16"]["scaled"]
         for val in rng.normal(size=3):
             want = O.energy_sparse(O.simulate(n, resolve(ops, prog.param_names, [val])), O.pauli_terms_to_matrix(n, *terms))
             assert abs(PI.run_frame16t(plan, [val]) - want) < TOL
-    assert offered >= 3
+            if plan["f16"]["scaled"]:
+                assert abs(PI.run_frame16t_scaled(plan, [val]) - want) < TOL
+    assert offered >= 3 and scaled >= 1
 
 
 def test_frame_relabelling_keeps_h2_exchanges_inside_warps():

@@ -1106,7 +1106,8 @@ __global__ void __launch_bounds__(128, 4) dmx_frame32s_kernel(const Frame32sArgs
 struct Frame16tArgs {
     int nseg, n_params;
     long long batch;
-    const double4* tab;           // [nseg][16]: x = wc, y = wk (own factor = fma(wc, cos, wk)), z = w1 (partner factor = w1 * sin)
+    const void* tab;              // general form: double4 [nseg][16], x = wc, y = wk (own factor = fma(wc, cos, wk)), z = w1 (partner
+                                  // factor = w1 * sin); scaled form: double2 [nseg][8], (kappa_i, kappa_j) per pair
     const double* eweight;        // [groups][17]: 16 weights + the group's constant
     const int* group;             // optional coefficient row per circuit
     const double* params;
@@ -1136,9 +1137,47 @@ __device__ __forceinline__ void f16_segment(double (&r)[16], const double4* __re
     }
 }
 
+// index of the pair (i, i ^ M), i < i ^ M, in ascending order of i
+__host__ __device__ constexpr int f16_pair_index(int i, int M) {
+    int n = 0;
+    for (int q = 0; q < i; ++q) n += ((q ^ M) > q) ? 1 : 0;
+    return n;
+}
+
+// Scaled form (Plan::f16_scaled): rho_i' = cos * rho_i + kappa_i * (sin * rho_j); the table holds (kappa_i, kappa_j) per pair in
+// the order of this loop, one LDS.128 each.
+template <int M>
+__device__ __forceinline__ void f16_segment_scaled(double (&r)[16], const double2* __restrict__ Kp, double c, double s) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+        const int j = i ^ M;
+        if (j > i) {
+            const double2 kp = Kp[f16_pair_index(i, M)];
+            const double ri = r[i], rj = r[j];
+            r[i] = fma(kp.x, s * rj, c * ri);
+            r[j] = fma(kp.y, s * ri, c * rj);
+        }
+    }
+}
+
+#define DMX_F16_SWITCH(FN, ...)                                                                   \
+    switch (a.mask[k]) {                   /* kernel parameter: uniform */                        \
+        case 1: FN<1>(__VA_ARGS__); break;   case 2: FN<2>(__VA_ARGS__); break;                   \
+        case 3: FN<3>(__VA_ARGS__); break;   case 4: FN<4>(__VA_ARGS__); break;                   \
+        case 5: FN<5>(__VA_ARGS__); break;   case 6: FN<6>(__VA_ARGS__); break;                   \
+        case 7: FN<7>(__VA_ARGS__); break;   case 8: FN<8>(__VA_ARGS__); break;                   \
+        case 9: FN<9>(__VA_ARGS__); break;   case 10: FN<10>(__VA_ARGS__); break;                 \
+        case 11: FN<11>(__VA_ARGS__); break; case 12: FN<12>(__VA_ARGS__); break;                 \
+        case 13: FN<13>(__VA_ARGS__); break; case 14: FN<14>(__VA_ARGS__); break;                 \
+        case 15: FN<15>(__VA_ARGS__); break; default: FN<0>(__VA_ARGS__); break;                  \
+    }
+
+template <bool SCALED>
 __global__ void __launch_bounds__(256) dmx_frame16t_kernel(const __grid_constant__ Frame16tArgs a) {
-    double4* const stab = reinterpret_cast<double4*>(dmx_smem);                 // [nseg][16]
-    double* const sew = reinterpret_cast<double*>(stab + a.nseg * 16);          // [17] weights of group 0
+    // table: [nseg][16] double4 (general form) or [nseg][8] double2 (scaled form); then the 17 energy weights of group 0
+    const int tab_d2 = a.nseg * (SCALED ? 8 : 32);
+    double2* const stab = reinterpret_cast<double2*>(dmx_smem);
+    double* const sew = reinterpret_cast<double*>(stab + tab_d2);
     const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const bool mine = b < a.batch;
     // the angle first: its DRAM round trip overlaps the table staging
@@ -1146,8 +1185,7 @@ __global__ void __launch_bounds__(256) dmx_frame16t_kernel(const __grid_constant
     const int g = (a.group && mine) ? a.group[b] : 0;
     {
         const double2* const src = reinterpret_cast<const double2*>(a.tab);
-        double2* const dst = reinterpret_cast<double2*>(stab);
-        for (int i = threadIdx.x; i < a.nseg * 32; i += blockDim.x) dst[i] = __ldg(src + i);
+        for (int i = threadIdx.x; i < tab_d2; i += blockDim.x) stab[i] = __ldg(src + i);
     }
     if (threadIdx.x < 17) sew[threadIdx.x] = __ldg(a.eweight + threadIdx.x);
     double sv, cv;
@@ -1158,24 +1196,12 @@ __global__ void __launch_bounds__(256) dmx_frame16t_kernel(const __grid_constant
     __syncthreads();
 #pragma unroll 1
     for (int k = 0; k < a.nseg; ++k) {
-        const double4* __restrict__ T = stab + k * 16;
-        switch (a.mask[k]) {                   // kernel parameter: uniform
-            case 0: f16_segment<0>(r, T, cv, sv); break;
-            case 1: f16_segment<1>(r, T, cv, sv); break;
-            case 2: f16_segment<2>(r, T, cv, sv); break;
-            case 3: f16_segment<3>(r, T, cv, sv); break;
-            case 4: f16_segment<4>(r, T, cv, sv); break;
-            case 5: f16_segment<5>(r, T, cv, sv); break;
-            case 6: f16_segment<6>(r, T, cv, sv); break;
-            case 7: f16_segment<7>(r, T, cv, sv); break;
-            case 8: f16_segment<8>(r, T, cv, sv); break;
-            case 9: f16_segment<9>(r, T, cv, sv); break;
-            case 10: f16_segment<10>(r, T, cv, sv); break;
-            case 11: f16_segment<11>(r, T, cv, sv); break;
-            case 12: f16_segment<12>(r, T, cv, sv); break;
-            case 13: f16_segment<13>(r, T, cv, sv); break;
-            case 14: f16_segment<14>(r, T, cv, sv); break;
-            default: f16_segment<15>(r, T, cv, sv); break;
+        if (SCALED) {
+            const double2* __restrict__ Kp = stab + k * 8;
+            DMX_F16_SWITCH(f16_segment_scaled, r, Kp, cv, sv)
+        } else {
+            const double4* __restrict__ T = reinterpret_cast<const double4*>(stab) + k * 16;
+            DMX_F16_SWITCH(f16_segment, r, T, cv, sv)
         }
     }
     double e;
@@ -1522,6 +1548,8 @@ struct DevPlan {
     double4* g_tab4 = nullptr;     // frame32s: (wc, wk, w1, partner) per (segment, lane)
     double4* h_tab16 = nullptr;    // frame16t: (wc, wk, w1, -) per (segment, slot)
     double* h_ew16 = nullptr;      // frame16t: [groups][17]
+    double* h_kap16 = nullptr;     // frame16t, scaled form: [nseg][16]
+    double* h_sw16 = nullptr;      // frame16t, scaled form: [groups][17]
     double2* g_w = nullptr; unsigned char* g_partner = nullptr; int* g_cs_sel = nullptr; double* g_init = nullptr; double* g_ew = nullptr; int* g_orig = nullptr;
     SlotDev* slots = nullptr;
     uint8_t* labels = nullptr;
@@ -1945,6 +1973,10 @@ static int upload_plan(Plan& p, DevPlan* d, int dev) {
                     t16[i] = make_double4(p.f16_tab[i * 4], p.f16_tab[i * 4 + 1], p.f16_tab[i * 4 + 2], p.f16_tab[i * 4 + 3]);
                 CUDA_TRY(upload(&d->h_tab16, t16));
                 CUDA_TRY(upload(&d->h_ew16, p.f16_eweight_g));
+                if (p.f16_scaled) {
+                    CUDA_TRY(upload(&d->h_kap16, p.f16_kappa));
+                    CUDA_TRY(upload(&d->h_sw16, p.f16_sweight_g));
+                }
             }
             CUDA_TRY(upload(&d->g_partner, p.f32_partner));
             CUDA_TRY(upload(&d->g_cs_sel, sel));
@@ -1978,7 +2010,7 @@ static void free_devplan(DevPlan* d) {
     cudaFree(d->coefs); cudaFree(d->rots); cudaFree(d->term_idx); cudaFree(d->term_coef);
     cudaFree(d->f_w); cudaFree(d->f_segs); cudaFree(d->f_classes); cudaFree(d->f_init); cudaFree(d->f_eweight); cudaFree(d->f_eslot);
     cudaFree(d->slots); cudaFree(d->labels);
-    cudaFree(d->h_tab16); cudaFree(d->h_ew16);
+    cudaFree(d->h_tab16); cudaFree(d->h_ew16); cudaFree(d->h_kap16); cudaFree(d->h_sw16);
     cudaFree(d->g_tab4); cudaFree(d->g_w); cudaFree(d->g_partner); cudaFree(d->g_cs_sel); cudaFree(d->g_init); cudaFree(d->g_ew); cudaFree(d->g_orig);
     for (auto& px : d->passx) cudaFree(px.coefs);
     for (int i = 0; i < DevPlan::MAX_XS; ++i) if (d->xs[i]) cudaStreamDestroy(d->xs[i]);
@@ -2361,15 +2393,18 @@ static int run_segment(Plan& p, DevPlan* d, long long batch, const double* param
         // evaluations and small batches keep the warp-per-circuit kernels (one circuit's latency spread over 32 lanes).
         if (p.f16_n > 0 && p.opt_frame16t && mode == 1 && !variants && !g.any_const && batch >= 2048 && (!host_mapped || p.opt_frame16t == 2)) {
             Frame16tArgs f{};
-            f.nseg = p.nseg; f.n_params = p.n_params; f.batch = batch; f.tab = d->h_tab16; f.eweight = d->h_ew16; f.group = group;
+            const bool scaled = p.f16_scaled && p.opt_f16_scaled;
+            f.nseg = p.nseg; f.n_params = p.n_params; f.batch = batch; f.group = group;
+            f.tab = scaled ? (const void*)d->h_kap16 : (const void*)d->h_tab16; f.eweight = scaled ? d->h_sw16 : d->h_ew16;
             f.params = params; f.out = out; f.cls = p.f_classes[0];
             for (int i = 0; i < 16; ++i) f.init[i] = p.f16_init[i];
             for (int k = 0; k < p.nseg; ++k) f.mask[k] = p.f16_mask[k];
             const int threads = p.opt_f16_threads;
             const long long grid = (batch + threads - 1) / threads;
             if (grid >= (1LL << 31)) return done(fail(DMX_ERR_UNSUPPORTED, "batch too large for one launch"));
-            const size_t smem = (size_t)p.nseg * 512 + 256;
-            dmx_frame16t_kernel<<<(unsigned)grid, threads, smem, st>>>(f);
+            const size_t smem = (size_t)p.nseg * (scaled ? 128 : 512) + 256;
+            if (scaled) dmx_frame16t_kernel<true><<<(unsigned)grid, threads, smem, st>>>(f);
+            else dmx_frame16t_kernel<false><<<(unsigned)grid, threads, smem, st>>>(f);
             ++g_launches;
             CUDA_TRY(cudaGetLastError());
             return done(DMX_OK);
@@ -2522,6 +2557,8 @@ int dmx_plan_set_option(dmx_plan* plan, const char* key, int value) {
     } else if (k == "frame16t") {
         if (value < 0 || value > 2) return fail(DMX_ERR_INVALID, "frame16t must be 0 (never), 1 (device-resident batches) or 2 (also mapped host buffers)");
         plan->p.opt_frame16t = value;
+    } else if (k == "frame16t_scaled") {
+        plan->p.opt_f16_scaled = value != 0;
     } else if (k == "frame16t_threads") {
         if (value != 64 && value != 128 && value != 256) return fail(DMX_ERR_INVALID, "frame16t_threads must be 64, 128 or 256");
         plan->p.opt_f16_threads = value;

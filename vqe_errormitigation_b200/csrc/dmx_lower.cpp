@@ -2359,6 +2359,43 @@ static void build_frame16t(Plan& p) {
     }
     p.f16_lane = lane_of_slot;
     p.f16_n = (int)touched.size();
+
+    // scaled form
+    p.f16_scaled = 0;
+    bool all_moved = true;
+    for (int k = 0; k < K && all_moved; ++k) {
+        if (p.f16_mask[k] == 0) all_moved = false;
+        for (int i = 0; i < 16 && all_moved; ++i) {
+            const int l = lane_of_slot[i];
+            if (l >= 0 && (!flagged(k, l) || p.f32_w[((size_t)k * 32 + l) * 2] == 0.0)) all_moved = false;
+        }
+    }
+    if (!all_moved) return;
+    std::vector<double> lam(16, 1.0), nl(16);
+    p.f16_kappa.assign((size_t)K * 16, 0.0);
+    for (int k = 0; k < K; ++k) {
+        const int m = p.f16_mask[k];
+        int pair = 0;
+        for (int i = 0; i < 16; ++i) {
+            const int j = i ^ m;
+            if (j < i) continue;
+            const int ij[2] = {i, j};
+            for (int h = 0; h < 2; ++h) {
+                const int a = ij[h], b = ij[1 - h], l = lane_of_slot[a];
+                nl[a] = lam[a];
+                if (l < 0) continue;
+                const double wc = p.f32_w[((size_t)k * 32 + l) * 2], w1 = p.f32_w[((size_t)k * 32 + l) * 2 + 1];
+                if (w1 != 0.0) p.f16_kappa[(size_t)k * 16 + 2 * pair + h] = w1 * lam[b] / (wc * lam[a]);
+                nl[a] = wc * lam[a];
+            }
+            ++pair;
+        }
+        lam = nl;
+    }
+    p.f16_sweight_g = p.f16_eweight_g;
+    for (size_t g = 0; g < G; ++g)
+        for (int i = 0; i < 16; ++i) p.f16_sweight_g[g * 17 + i] *= lam[i];
+    p.f16_scaled = 1;
 }
 
 static bool build_frame(Plan& p, std::string& why) {
@@ -2605,7 +2642,7 @@ void lower_plan(Plan& p) {
         // the compact frame kernel executes the segments on 32 lanes per circuit instead of 256 threads
         in.flops_per_circuit = (p.nseg * 4.0 + 1.0) * (p.f32_n > 0 ? 32.0 : (double)SEG_E) + 2.0 * p.e_w.size();
         // thread-per-circuit form: 16 slots x (fma + 2 mul + fma = 6 flops) per segment, 16 fma for the energy
-        if (p.f16_n > 0 && p.opt_frame16t) in.flops_per_circuit = p.nseg * 96.0 + 32.0;
+        if (p.f16_n > 0 && p.opt_frame16t) in.flops_per_circuit = p.nseg * (p.f16_scaled && p.opt_f16_scaled ? 64.0 : 96.0) + 32.0;
         // per circuit: smem-exchange segments move 8 B out + 8 B in per coefficient; the energy stage a few terms
         in.smem_bytes_per_circuit = smem_segs * SEG_E * 16.0 + 16.0 * p.e_w.size();
         in.hbm_bytes_per_circuit = io;
@@ -2743,15 +2780,17 @@ std::string dump_plan(const Plan& p) {
             }
         }
         if (p.f16_n > 0) {
-            os << "f16 n=" << p.f16_n;
+            os << "f16 n=" << p.f16_n << " scaled=" << p.f16_scaled;
             dump_ints(os, "lane", p.f16_lane);
             dump_ints(os, "mask", std::vector<int>(p.f16_mask.begin(), p.f16_mask.end()));
             dump_vec(os, "init", p.f16_init);
             dump_vec(os, "eweight", std::vector<double>(p.f16_eweight_g.begin(), p.f16_eweight_g.begin() + 17));
+            if (p.f16_scaled) dump_vec(os, "sweight", std::vector<double>(p.f16_sweight_g.begin(), p.f16_sweight_g.begin() + 17));
             os << "\n";
             for (int k = 0; k < p.nseg; ++k) {
                 os << "f16seg " << k;
                 dump_vec(os, "tab", std::vector<double>(p.f16_tab.begin() + (size_t)k * 64, p.f16_tab.begin() + (size_t)(k + 1) * 64));
+                if (p.f16_scaled) dump_vec(os, "kappa", std::vector<double>(p.f16_kappa.begin() + (size_t)k * 16, p.f16_kappa.begin() + (size_t)(k + 1) * 16));
                 os << "\n";
             }
         }

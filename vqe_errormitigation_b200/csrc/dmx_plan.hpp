@@ -259,6 +259,15 @@ struct Plan {
     std::vector<double> f16_tab;         // [nseg][16][4] = (wc, wk, w1, 0): own factor fma(wc, cos, wk), partner factor w1 * sin
     std::vector<double> f16_init;        // [16]
     std::vector<double> f16_eweight_g;   // [max(n_groups, 1)][17]: 16 energy weights + the constant part of that group
+    // Scaled form (every rotation moves every used slot, which is what a chain of Pauli exponentials on one orbit does): the
+    // own-coefficient weights wc are carried as a per-slot scale lambda that only the host tracks (lambda' = wc * lambda), the
+    // kernel evolves rho = r / lambda by rho_i' = cos * rho_i + kappa_i * (sin * rho_j), kappa = w1 lambda_j / (wc lambda_i) -
+    // three FP64 instructions and 8 bytes of table per slot and segment instead of four and 32 - and lambda folds into the
+    // energy weights.  f16_kappa is stored in the order the unrolled pair loop of mask f16_mask[k] consumes it.
+    int f16_scaled = 0;
+    std::vector<double> f16_kappa;       // [nseg][16]: (kappa_i, kappa_j) of the p-th pair (i < j = i ^ mask) at [2p], [2p + 1]
+    std::vector<double> f16_sweight_g;   // [max(n_groups, 1)][17]: energy weights times the final lambda + the constant part
+    int opt_f16_scaled = 1;              // use the scaled form of dmx_frame16t_kernel when the plan offers it
     int opt_f16_threads = 128;           // CTA size of dmx_frame16t_kernel
     int opt_frame16t = 1;                // 0 never, 1 device-resident batches from 2048 circuits, 2 also mapped host buffers
 
