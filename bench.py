@@ -902,6 +902,8 @@ def run_workload(wl, ctx, steps: int, warmup: int, with_cpu_baseline: bool, with
     if (info["path"] == 1 and variants_h is None and info["n_params"] == 1 and B >= 2048 and PLAN_OPTIONS.get("frame16t", 1) != 0
             and "\nf16 n=" in prog.dump()):
         kern = "dmx_frame16t_kernel (thread-per-circuit form of the frame kernel: 16 touched coefficients in registers, XOR-paired per segment)"
+    if (info["path"] == 1 and variants_h is not None and B >= 2048 and PLAN_OPTIONS.get("frame16t", 1) != 0 and " const=1" in prog.dump()):
+        kern = "dmx_frame16v_kernel (thread-per-row form for QP variant batches: constant-coefficient scaled segments, precomputed diagonal corrections)"
     traffic = ncu_util = None
     tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
     if os.path.exists(tpath):

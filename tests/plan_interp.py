@@ -91,10 +91,14 @@ def parse(dump: str) -> dict:
         elif head == "f32seg":
             plan["f32"]["segs"].append({"partner": _nums(kv["partner"], int), "w": _nums(kv["w"]).reshape(32, 2)})
         elif head == "f16":
-            plan["f16"] = {"n": int(kv["n"]), "scaled": int(kv["scaled"]), "lane": _nums(kv["lane"], int), "mask": _nums(kv["mask"], int),
+            plan["f16"] = {"n": int(kv["n"]), "scaled": int(kv["scaled"]), "const": int(kv["const"]), "lane": _nums(kv["lane"], int), "mask": _nums(kv["mask"], int),
                            "init": _nums(kv["init"]), "eweight": _nums(kv["eweight"]), "segs": [], "kappa": []}
             if "sweight" in kv:
                 plan["f16"]["sweight"] = _nums(kv["sweight"])
+            if "static" in kv:
+                plan["f16"]["static"] = _nums(kv["static"], int)
+                plan["f16"]["cstat"] = _nums(kv["cstat"])
+                plan["f16"]["facrow"] = _nums(kv["facrow"], int)
         elif head == "f16seg":
             plan["f16"]["segs"].append(_nums(kv["tab"]).reshape(16, 4))
             if "kappa" in kv:
@@ -519,6 +523,61 @@ def run_frame16t_scaled(plan, params):
                 pair += 1
         r = new
     return float(np.dot(f16["sweight"][:16], r) + f16["sweight"][16])
+
+
+def run_frame16v(plan, variants):
+    """The constant-coefficient thread-per-row form (dmx_frame16v_kernel): rho_i' = rho_i + kappa_i rho_j per segment, the row's
+    diagonal corrections applied by stage in (stage, slot) order to the 16 slots and to the untouched coefficients."""
+    f16 = plan.get("f16")
+    if f16 is None or not f16["const"]:
+        return None
+    orig = np.asarray(plan["f32"]["orig"])
+    cf = plan["coefs"]
+    lanes, stat = [int(x) for x in f16["lane"]], [int(x) for x in f16["static"]]
+    ents = []
+    for s, v in enumerate(variants if variants is not None else []):
+        v = int(v)
+        if v == 0 or s not in plan["slots"] or plan["slots"][s]["seg"] < 0:
+            continue
+        sl = plan["slots"][s]
+        if not (int(sl["diag_ok"][v >> 5]) >> (v & 31)) & 1:
+            return None
+        assert f16["facrow"][s] >= 0
+        ents.append((int(sl["seg"]), s, v))
+    ents.sort()
+
+    def fac(s, v, lane):
+        sl = plan["slots"][s]
+        lab = int(plan["flabels"][s][orig[lane]])
+        tb = sl["tab"]
+        if sl["nq"] == 1:
+            return cf[tb + v * 4 + lab]
+        return cf[tb + (v >> 4) * 4 + (lab >> 2)] * cf[tb + (v & 15) * 4 + (lab & 3)] * cf[tb + 64 + lab]
+
+    r = f16["init"].copy()
+    F = np.ones(len(stat))
+    nseg = plan["nseg"]
+    for k in range(nseg + 1):
+        for seg, s, v in ents:
+            if seg != k:
+                continue
+            for i, lane in enumerate(lanes):
+                if lane >= 0:
+                    r[i] *= fac(s, v, lane)
+            for j, lane in enumerate(stat):
+                F[j] *= fac(s, v, lane)
+        if k == nseg:
+            break
+        m, kap = int(f16["mask"][k]), f16["kappa"][k]
+        new, pair = r.copy(), 0
+        for i in range(16):
+            j = i ^ m
+            if j > i:
+                new[i] = kap[2 * pair] * r[j] + r[i]
+                new[j] = kap[2 * pair + 1] * r[i] + r[j]
+                pair += 1
+        r = new
+    return float(np.dot(f16["sweight"][:16], r) + np.dot(f16["cstat"][:len(stat)], F))
 
 
 def run_frame(plan, params=None, variants=None):

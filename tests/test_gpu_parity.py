@@ -266,6 +266,58 @@ def test_qp_variants_match_oracle(options):
         assert abs(got[b] - want) < TOL, (b, got[b], want)
 
 
+def test_thread_per_row_variant_kernel_against_oracle_and_warp_kernel():
+    """dmx_frame16v_kernel (batches from 2048 variant rows: one thread per row, constant-coefficient scaled segments, diagonal
+    corrections from a precomputed table): rows drawn from the reference distribution, stress rows (several Pauli corrections,
+    R-type / projector entries, more entries than the per-row list holds -> general path), ragged batches, every alignment
+    of the table pointer - against the C oracle at 1e-10, against the warp-per-row kernel to rounding, and bit for bit
+    independent of the row's position."""
+    torch = torch_cuda()
+    terms = h2_terms()
+    n1, n2 = [O.bit_flip(1e-3), O.depolarize(1e-3)], [O.two_qubit_depolarize(1e-3)]
+    prog, gates = qp_noisy_variant_program(n1, n2, terms)
+    warp, _ = qp_noisy_variant_program(n1, n2, terms, frame16t=0)
+    assert "f16 n=16 scaled=0 const=1" in prog.dump()
+    ham = O.pauli_terms_to_matrix(4, *terms)
+    arity = np.array([len(g[1]) for g in gates])
+    rng = np.random.default_rng(2718)
+    B = 4099
+    v = np.zeros((B, 122), np.uint8)
+    for b in range(B):
+        kind = b % 8
+        if kind < 5:                                             # the reference distribution: mostly identity rows
+            k = int(rng.random() < 0.35)
+        else:
+            k = int(rng.integers(1, 7))
+        for s in rng.choice(122, k, replace=False):
+            if kind == 7 and rng.random() < 0.3:                 # any basis operation incl. rotations and projectors
+                v[b, s] = rng.integers(0, 16) if arity[s] == 1 else rng.integers(0, 256)
+            else:
+                v[b, s] = rng.integers(1, 4) if arity[s] == 1 else 16 * rng.integers(0, 4) + rng.integers(0, 4)
+    v[7, [0, 121]] = [3, 2]                                      # first and last slot of a row
+    v[11, 5] = 7                                                 # R-type correction: general path
+    v[13, :40] = np.where(arity[:40] == 1, 1, 17)                # more entries than the per-row list holds: general path
+    v[4098, 60] = 2                                              # last row of a ragged CTA
+    base = prog.energies(None, torch.tensor(v, device="cuda")).cpu().numpy()
+    ref = warp.energies(None, torch.tensor(v, device="cuda")).cpu().numpy()
+    assert np.max(np.abs(base - ref)) < 1e-13
+    for b in list(range(0, 64)) + [4098]:
+        want = oracle_energy(O.variant_ops(gates, n1, n2, v[b]), 4, ham)
+        assert abs(base[b] - want) < TOL, (b, base[b], want)
+    for shift in (1, 2, 3, 31, 127):
+        shifted = np.concatenate([np.zeros((shift, 122), np.uint8), v])
+        got = prog.energies(None, torch.tensor(shifted, device="cuda")).cpu().numpy()
+        assert np.array_equal(got[shift:], base), shift
+        assert np.all(got[:shift] == got[0])
+    for off in (1, 2, 3):                                        # table pointer not 4-byte aligned
+        buf = torch.zeros(B * 122 + off, dtype=torch.uint8, device="cuda")
+        view = buf[off:].view(B, 122)
+        view.copy_(torch.tensor(v))
+        assert np.array_equal(prog.energies(None, view).cpu().numpy(), base), off
+    host = prog.energies_host(None, v)                           # DMA pipeline -> the same kernel
+    assert np.array_equal(host, base)
+
+
 def test_variant_rows_position_independent_and_unaligned_table():
     """The frame kernel walks a group's identifier rows as one run of 32-bit words: the energies of a row must not depend on
     where it sits in the batch (shifted by 1..9 identity rows: every alignment of the 122-byte rows inside the 128-byte

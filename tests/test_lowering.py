@@ -182,7 +182,20 @@ def test_variant_lowering_against_golden():
             assert abs(seg - case["energy"]) < TOL
             assert abs(frame - case["energy"]) < TOL
             assert abs(PI.run_frame32(plan, None, v) - case["energy"]) < TOL
+            assert abs(PI.run_frame16v(plan, v) - case["energy"]) < TOL       # thread-per-row form (dmx_frame16v_kernel)
     assert general >= 1
+    assert plan["f16"]["const"] == 1 and plan["f16"]["n"] == 16 and len(plan["f16"]["static"]) == 7
+    # random rows of diagonal corrections (Pauli basis operations, indices 1-3 per qubit) against the oracle
+    rng = np.random.default_rng(8)
+    n_slots = prog.n_slots
+    gates = O.h2_gate_list(ALPHA_STAR)
+    for trial in range(12):
+        v = np.zeros(n_slots, np.uint8)
+        for s in rng.choice(n_slots, size=int(rng.integers(1, 6)), replace=False):
+            nq = plan["slots"][int(s)]["nq"]
+            v[s] = int(rng.integers(1, 4)) if nq == 1 else 16 * int(rng.integers(0, 4)) + int(rng.integers(0, 4))
+        want = O.energy_sparse(O.simulate(4, O.variant_ops(gates, n1, n2, v)), O.pauli_terms_to_matrix(4, *h2_terms()))
+        assert abs(PI.run_frame16v(plan, v) - want) < TOL, (trial, v.nonzero())
 
 
 def test_streaming_schedule_partitions_all_blocks():

@@ -1219,6 +1219,165 @@ __global__ void __launch_bounds__(256) dmx_frame16t_kernel(const __grid_constant
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// frame16v: thread-per-ROW form for QP variant batches of a resolved circuit (Plan::f16_const).  The segments have constant
+// coefficients, so in the scaled form a segment is ONE DFMA per slot (rho_i' = rho_i + kappa_i rho_j); a row's non-identity
+// entries (a handful in 122 bytes) are found by a warp-wide word scan of the 32 contiguous rows the warp owns and handed to
+// the owning thread through shared memory, sorted by (stage, slot) so that equal rows give bit-identical energies wherever
+// they sit; each entry multiplies the 16 slots and the (otherwise constant) untouched coefficients by one 192-byte row of
+// precomputed diagonal factors.  Rows with a non-diagonal correction (R-type / projector basis operations) or more than
+// F16V_MAXACT entries go to the worklist of the general tile path, exactly like dmx_frame32_kernel's.
+// ---------------------------------------------------------------------------------------------------------
+constexpr int F16V_MAXACT = 6;
+
+struct Frame16vArgs {
+    int nseg, n_slots;
+    long long batch;
+    const double2* kappa;         // [nseg][8]: (kappa_i, kappa_j) per pair in loop order
+    const double* sweight;        // [groups][17]: energy weights x final scale, + unused
+    const double* cstat;          // [groups][8]: energy weight x constant value of the untouched coefficients
+    const int* group;
+    const uint8_t* variants;
+    const SlotDev* slots;
+    const int* fac_row;           // [n_slots]
+    const double* fac;            // [rows][24]
+    double* out;
+    int* worklist;
+    int* work_count;
+    double init[16];
+    unsigned char mask[48];
+};
+
+template <int M>
+__device__ __forceinline__ void f16_segment_const(double (&r)[16], const double2* __restrict__ Kp) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+        const int j = i ^ M;
+        if (j > i) {
+            const double2 kp = Kp[f16_pair_index(i, M)];
+            const double ri = r[i], rj = r[j];
+            r[i] = fma(kp.x, rj, ri);
+            r[j] = fma(kp.y, ri, rj);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(128) dmx_frame16v_kernel(const __grid_constant__ Frame16vArgs a) {
+    double2* const skap = reinterpret_cast<double2*>(dmx_smem);                 // [nseg][8]
+    double* const sew = reinterpret_cast<double*>(skap + a.nseg * 8);           // [16] weights + [8] static terms of group 0 (+ pad)
+    unsigned* const act = reinterpret_cast<unsigned*>(sew + 26);                // [128][F16V_MAXACT]
+    int* const nact = reinterpret_cast<int*>(act + 128 * F16V_MAXACT);          // [128]
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const long long row0 = (long long)blockIdx.x * 128;
+    const long long b = row0 + tid;
+    const bool mine = b < a.batch;
+    nact[tid] = 0;
+    for (int i = tid; i < a.nseg * 8; i += 128) skap[i] = __ldg(a.kappa + i);
+    if (tid < 16) sew[tid] = __ldg(a.sweight + tid);
+    else if (tid < 24) sew[tid] = __ldg(a.cstat + (tid - 16));
+    __syncthreads();
+
+    // ---- scan of the warp's 32 rows: one contiguous run of 32 * n_slots bytes, walked as 32-bit words ----
+    {
+        const long long wrow0 = row0 + 32 * warp;
+        const long long rows_here = a.batch - wrow0 < 32 ? a.batch - wrow0 : 32;
+        const unsigned S = (unsigned)a.n_slots;
+        const unsigned valid = rows_here > 0 ? (unsigned)rows_here * S : 0u;
+        const uint8_t* const gbase = a.variants + wrow0 * (long long)S;
+        const bool word_ok = (reinterpret_cast<unsigned long long>(gbase) & 3ull) == 0ull;
+        constexpr int AHEAD = 8;
+        for (unsigned s0 = 0; s0 < valid; s0 += 128u * AHEAD) {
+            unsigned words[AHEAD];
+            unsigned any = 0u;
+#pragma unroll
+            for (int i = 0; i < AHEAD; ++i) {
+                const unsigned f = s0 + 128u * i + 4u * lane;
+                words[i] = 0u;
+                if (word_ok && f + 4u <= valid) {
+                    words[i] = __ldcs(reinterpret_cast<const unsigned*>(gbase + f));
+                } else if (f < valid) {
+                    for (int j = 0; j < 4; ++j)
+                        if (f + j < valid) words[i] |= (unsigned)gbase[f + j] << (8 * j);
+                }
+                any |= words[i];
+            }
+            if (any == 0u) continue;                       // identity entries only (the common case): nothing to record
+#pragma unroll 1
+            for (int i = 0; i < AHEAD; ++i) {
+                unsigned word = words[0];
+#pragma unroll
+                for (int q = 1; q < AHEAD; ++q) word = i == q ? words[q] : word;
+                if (word == 0u) continue;
+                const unsigned f = s0 + 128u * i + 4u * lane;
+                for (int j = 0; j < 4; ++j) {
+                    const unsigned idx = (word >> (8 * j)) & 255u;
+                    if (!idx) continue;
+                    const unsigned fb = f + j, r = fb / S, sl = fb - r * S;
+                    const int seg = a.slots[sl].seg;
+                    if (seg < 0) continue;                  // slot not present in the circuit
+                    const bool diag = (a.slots[sl].diag_ok[idx >> 5] >> (idx & 31u)) & 1u;
+                    const int lr = 32 * warp + (int)r;
+                    const int pos = atomicAdd(&nact[lr], diag ? 1 : 1000);      // a non-diagonal entry forces the general path
+                    if (diag && pos < F16V_MAXACT) act[lr * F16V_MAXACT + pos] = ((unsigned)seg << 20) | (sl << 8) | idx;
+                }
+            }
+        }
+        __syncwarp();
+    }
+    int cnt = nact[tid];
+    unsigned* const mya = act + tid * F16V_MAXACT;
+    if (cnt > F16V_MAXACT) {
+        if (mine) a.worklist[atomicAdd(a.work_count, 1)] = (int)b;
+        return;                                             // no block barrier and no shuffle below: the thread may leave
+    }
+    // (stage, slot) order, whatever order the warp's atomics recorded the entries in
+    for (int i = 1; i < cnt; ++i) {
+        const unsigned v = mya[i];
+        int j = i - 1;
+        while (j >= 0 && mya[j] > v) { mya[j + 1] = mya[j]; --j; }
+        mya[j + 1] = v;
+    }
+
+    double r[16], F[8];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) r[i] = a.init[i];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) F[j] = 1.0;
+    int next = 0;
+    unsigned ent = cnt > 0 ? mya[0] : 0xffffffffu;
+#pragma unroll 1
+    for (int k = 0; k <= a.nseg; ++k) {
+        while ((ent >> 20) == (unsigned)k) {
+            const double2* __restrict__ row = reinterpret_cast<const double2*>(a.fac + ((size_t)a.fac_row[(ent >> 8) & 4095u] + (ent & 255u)) * 24);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) { const double2 f2 = __ldg(row + i); r[2 * i] *= f2.x; r[2 * i + 1] *= f2.y; }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { const double2 f2 = __ldg(row + 8 + j); F[2 * j] *= f2.x; F[2 * j + 1] *= f2.y; }
+            ++next;
+            ent = next < cnt ? mya[next] : 0xffffffffu;
+        }
+        if (k == a.nseg) break;
+        const double2* __restrict__ Kp = skap + k * 8;
+        DMX_F16_SWITCH(f16_segment_const, r, Kp)
+    }
+    double e = 0.0;
+    if (a.group) {
+        const int g = mine ? a.group[b] : 0;
+        const double* __restrict__ ew = a.sweight + (size_t)g * 17;
+        const double* __restrict__ cs = a.cstat + (size_t)g * 8;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) e = fma(__ldg(cs + j), F[j], e);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) e = fma(__ldg(ew + i), r[i], e);
+    } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) e = fma(sew[16 + j], F[j], e);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) e = fma(sew[i], r[i], e);
+    }
+    if (mine) a.out[b] = e;
+}
+
+// ---------------------------------------------------------------------------------------------------------
 // small kernels
 // ---------------------------------------------------------------------------------------------------------
 __global__ void dmx_energy_kernel(const double* __restrict__ state, int n, long long batch, const uint32_t* __restrict__ term_idx,
@@ -1550,6 +1709,9 @@ struct DevPlan {
     double* h_ew16 = nullptr;      // frame16t: [groups][17]
     double* h_kap16 = nullptr;     // frame16t, scaled form: [nseg][16]
     double* h_sw16 = nullptr;      // frame16t, scaled form: [groups][17]
+    double* h_cstat = nullptr;     // frame16v: [groups][8]
+    int* h_facrow = nullptr;       // frame16v: [n_slots]
+    double* h_fac = nullptr;       // frame16v: [rows][24]
     double2* g_w = nullptr; unsigned char* g_partner = nullptr; int* g_cs_sel = nullptr; double* g_init = nullptr; double* g_ew = nullptr; int* g_orig = nullptr;
     SlotDev* slots = nullptr;
     uint8_t* labels = nullptr;
@@ -1973,9 +2135,14 @@ static int upload_plan(Plan& p, DevPlan* d, int dev) {
                     t16[i] = make_double4(p.f16_tab[i * 4], p.f16_tab[i * 4 + 1], p.f16_tab[i * 4 + 2], p.f16_tab[i * 4 + 3]);
                 CUDA_TRY(upload(&d->h_tab16, t16));
                 CUDA_TRY(upload(&d->h_ew16, p.f16_eweight_g));
-                if (p.f16_scaled) {
+                if (p.f16_scaled || p.f16_const) {
                     CUDA_TRY(upload(&d->h_kap16, p.f16_kappa));
                     CUDA_TRY(upload(&d->h_sw16, p.f16_sweight_g));
+                }
+                if (p.f16_const) {
+                    CUDA_TRY(upload(&d->h_cstat, p.f16_cstat_g));
+                    CUDA_TRY(upload(&d->h_facrow, p.f16_fac_row));
+                    CUDA_TRY(upload(&d->h_fac, p.f16_fac));
                 }
             }
             CUDA_TRY(upload(&d->g_partner, p.f32_partner));
@@ -2011,6 +2178,7 @@ static void free_devplan(DevPlan* d) {
     cudaFree(d->f_w); cudaFree(d->f_segs); cudaFree(d->f_classes); cudaFree(d->f_init); cudaFree(d->f_eweight); cudaFree(d->f_eslot);
     cudaFree(d->slots); cudaFree(d->labels);
     cudaFree(d->h_tab16); cudaFree(d->h_ew16); cudaFree(d->h_kap16); cudaFree(d->h_sw16);
+    cudaFree(d->h_cstat); cudaFree(d->h_facrow); cudaFree(d->h_fac);
     cudaFree(d->g_tab4); cudaFree(d->g_w); cudaFree(d->g_partner); cudaFree(d->g_cs_sel); cudaFree(d->g_init); cudaFree(d->g_ew); cudaFree(d->g_orig);
     for (auto& px : d->passx) cudaFree(px.coefs);
     for (int i = 0; i < DevPlan::MAX_XS; ++i) if (d->xs[i]) cudaStreamDestroy(d->xs[i]);
@@ -2389,6 +2557,23 @@ static int run_segment(Plan& p, DevPlan* d, long long batch, const double* param
         // the event pair, the launch latency and one warp's critical path (tools/launch_floor.py), not the kernel.
         // opt_frame32s: 0 never, 1 automatic, 8 / 16 always 32 circuits per warp with that many advanced together,
         // 32 + cw: always cw circuits per warp (cw = 8 / 16 / 24 / 32).
+        // QP variant rows of a resolved circuit: one thread per row (dmx_frame16v_kernel); rows it cannot take land on the
+        // worklist of the general tile path like the warp kernel's
+        if (p.f16_n > 0 && p.f16_const && p.opt_frame16t && mode == 0 && variants && batch >= 2048 && !host_mapped) {
+            Frame16vArgs f{};
+            f.nseg = p.nseg; f.n_slots = p.n_slots; f.batch = batch; f.kappa = reinterpret_cast<const double2*>(d->h_kap16);
+            f.sweight = d->h_sw16; f.cstat = d->h_cstat; f.group = group; f.variants = variants; f.slots = d->slots;
+            f.fac_row = d->h_facrow; f.fac = d->h_fac; f.out = out; f.worklist = a.worklist; f.work_count = a.work_count;
+            for (int i = 0; i < 16; ++i) f.init[i] = p.f16_init[i];
+            for (int k = 0; k < p.nseg; ++k) f.mask[k] = p.f16_mask[k];
+            const long long grid = (batch + 127) / 128;
+            if (grid >= (1LL << 31)) return done(fail(DMX_ERR_UNSUPPORTED, "batch too large for one launch"));
+            const size_t smem = (size_t)p.nseg * 128 + 26 * 8 + 128 * F16V_MAXACT * 4 + 128 * 4;
+            dmx_frame16v_kernel<<<(unsigned)grid, 128, smem, st>>>(f);
+            ++g_launches;
+            CUDA_TRY(cudaGetLastError());
+            return done(run_tile_single(p, d, batch, params, variants, out, OUT_ENERGY, wl + 1, wl, st, group));
+        }
         // Thread-per-circuit form (dmx_frame16t_kernel) for batches that give every SM a few warps of circuits; single
         // evaluations and small batches keep the warp-per-circuit kernels (one circuit's latency spread over 32 lanes).
         if (p.f16_n > 0 && p.opt_frame16t && mode == 1 && !variants && !g.any_const && batch >= 2048 && (!host_mapped || p.opt_frame16t == 2)) {

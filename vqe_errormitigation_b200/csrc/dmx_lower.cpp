@@ -2280,8 +2280,12 @@ static void build_frame32(Plan& p) {
 static void build_frame16t(Plan& p) {
     p.f16_n = 0;
     const int K = p.nseg;
-    if (p.f32_n <= 0 || p.f_classes.size() != 1 || K < 1 || K > 48 || p.n_slots != 0) return;
-    for (int k = 0; k < K; ++k) if (p.fsegs[k].cs_sel != 0) return;            // every segment is a rotation of the one class
+    p.f16_const = 0;
+    if (p.f32_n <= 0 || K < 1 || K > 48) return;
+    const bool rot_mode = p.f_classes.size() == 1 && p.n_slots == 0;           // parameter sweeps: one rotation class, no variant slots
+    const bool const_mode = p.f_classes.empty() && p.n_slots > 0;              // QP variant batches of a resolved circuit
+    if (!rot_mode && !const_mode) return;
+    for (int k = 0; k < K; ++k) if (rot_mode ? p.fsegs[k].cs_sel != 0 : p.fsegs[k].cs_sel >= 0) return;
     auto flagged = [&](int k, int l) { return (p.f32_partner[(size_t)k * 32 + l] & 0x80u) != 0; };
     std::vector<int> touched;
     std::vector<unsigned> used_masks;
@@ -2336,7 +2340,7 @@ static void build_frame16t(Plan& p) {
             const int l = lane_of_slot[i];
             if (l < 0) { e[1] = 1.0; continue; }
             const double w0 = p.f32_w[((size_t)k * 32 + l) * 2], w1 = p.f32_w[((size_t)k * 32 + l) * 2 + 1];
-            if (flagged(k, l)) { e[0] = w0; e[2] = w1; } else { e[1] = w0; }
+            if (flagged(k, l) && rot_mode) { e[0] = w0; e[2] = w1; } else { e[1] = w0; e[2] = w1; }
             if (w1 != 0.0) {
                 const int lp = p.f32_partner[(size_t)k * 32 + l] & 31;
                 if (slot_of[lp] != (i ^ (int)m)) return;                          // partner outside the XOR pattern: keep frame32
@@ -2359,6 +2363,70 @@ static void build_frame16t(Plan& p) {
     }
     p.f16_lane = lane_of_slot;
     p.f16_n = (int)touched.size();
+
+    if (const_mode) {
+        // scaled constant form + correction tables
+        p.f16_scaled = 0;
+        std::vector<int> stat;
+        for (int l = 0; l < 32; ++l) if (p.f32_orig[l] >= 0 && slot_of[l] < 0) stat.push_back(l);
+        if (stat.size() > 8) { p.f16_n = 0; return; }
+        std::vector<double> lam(16, 1.0), nl(16);
+        p.f16_kappa.assign((size_t)K * 16, 0.0);
+        for (int k = 0; k < K; ++k) {
+            const int m = p.f16_mask[k];
+            nl = lam;
+            for (int i = 0; i < 16; ++i) {
+                const int l = lane_of_slot[i];
+                if (l < 0) continue;
+                const double w0 = p.f32_w[((size_t)k * 32 + l) * 2], w1 = p.f32_w[((size_t)k * 32 + l) * 2 + 1];
+                if (w0 == 0.0) { p.f16_n = 0; return; }
+                nl[i] = w0 * lam[i];
+                if (m == 0 || w1 == 0.0) continue;
+                const int j = i ^ m, lo = i < j ? i : j;
+                int pair = 0;
+                for (int q = 0; q < lo; ++q) pair += ((q ^ m) > q) ? 1 : 0;
+                p.f16_kappa[(size_t)k * 16 + 2 * pair + (i < j ? 0 : 1)] = w1 * lam[j] / (w0 * lam[i]);
+            }
+            lam = nl;
+        }
+        p.f16_sweight_g = p.f16_eweight_g;
+        for (size_t g = 0; g < G; ++g)
+            for (int i = 0; i < 16; ++i) p.f16_sweight_g[g * 17 + i] *= lam[i];
+        p.f16_static_lane = stat;
+        p.f16_cstat_g.assign(G * 8, 0.0);
+        for (size_t g = 0; g < G; ++g)
+            for (size_t j = 0; j < stat.size(); ++j) {
+                double v = p.f32_init[stat[j]];
+                for (int k = 0; k < K; ++k) v *= p.f32_w[((size_t)k * 32 + stat[j]) * 2];
+                p.f16_cstat_g[g * 8 + j] = p.f32_eweight_g[g * 32 + stat[j]] * v;
+            }
+        p.f16_fac_row.assign(p.n_slots, -1);
+        size_t rows = 0;
+        for (int sl = 0; sl < p.n_slots; ++sl) {
+            if (p.slots[sl].seg < 0) continue;
+            p.f16_fac_row[sl] = (int)rows;
+            rows += p.slots[sl].nq == 1 ? 16 : 256;
+        }
+        p.f16_fac.assign(rows * 24, 1.0);
+        for (int sl = 0; sl < p.n_slots; ++sl) {
+            if (p.f16_fac_row[sl] < 0) continue;
+            const SlotInfo& si = p.slots[sl];
+            const double* t = p.coefs.data() + si.tab_off;
+            const int nidx = si.nq == 1 ? 16 : 256;
+            for (int v = 1; v < nidx; ++v) {
+                if (!((si.diag_ok[v >> 5] >> (v & 31)) & 1u)) continue;
+                double* row = &p.f16_fac[((size_t)p.f16_fac_row[sl] + v) * 24];
+                for (int c = 0; c < 24; ++c) {
+                    const int l = c < 16 ? lane_of_slot[c] : (c - 16 < (int)stat.size() ? stat[c - 16] : -1);
+                    if (l < 0) continue;
+                    const unsigned lab = p.f_labels[(size_t)sl * SEG_E + p.f32_orig[l]];
+                    row[c] = si.nq == 1 ? t[v * 4 + lab] : t[(v >> 4) * 4 + (lab >> 2)] * t[(v & 15) * 4 + (lab & 3u)] * t[64 + lab];
+                }
+            }
+        }
+        p.f16_const = 1;
+        return;
+    }
 
     // scaled form
     p.f16_scaled = 0;
@@ -2643,6 +2711,8 @@ void lower_plan(Plan& p) {
         in.flops_per_circuit = (p.nseg * 4.0 + 1.0) * (p.f32_n > 0 ? 32.0 : (double)SEG_E) + 2.0 * p.e_w.size();
         // thread-per-circuit form: 16 slots x (fma + 2 mul + fma = 6 flops) per segment, 16 fma for the energy
         if (p.f16_n > 0 && p.opt_frame16t) in.flops_per_circuit = p.nseg * (p.f16_scaled && p.opt_f16_scaled ? 64.0 : 96.0) + 32.0;
+        // thread-per-row variant form: one fma per slot and segment, 24 fma for the energy (corrections: a few rows in a hundred)
+        if (p.f16_n > 0 && p.opt_frame16t && p.f16_const) in.flops_per_circuit = p.nseg * 32.0 + 48.0;
         // per circuit: smem-exchange segments move 8 B out + 8 B in per coefficient; the energy stage a few terms
         in.smem_bytes_per_circuit = smem_segs * SEG_E * 16.0 + 16.0 * p.e_w.size();
         in.hbm_bytes_per_circuit = io;
@@ -2780,17 +2850,22 @@ std::string dump_plan(const Plan& p) {
             }
         }
         if (p.f16_n > 0) {
-            os << "f16 n=" << p.f16_n << " scaled=" << p.f16_scaled;
+            os << "f16 n=" << p.f16_n << " scaled=" << p.f16_scaled << " const=" << p.f16_const;
             dump_ints(os, "lane", p.f16_lane);
             dump_ints(os, "mask", std::vector<int>(p.f16_mask.begin(), p.f16_mask.end()));
             dump_vec(os, "init", p.f16_init);
             dump_vec(os, "eweight", std::vector<double>(p.f16_eweight_g.begin(), p.f16_eweight_g.begin() + 17));
-            if (p.f16_scaled) dump_vec(os, "sweight", std::vector<double>(p.f16_sweight_g.begin(), p.f16_sweight_g.begin() + 17));
+            if (p.f16_scaled || p.f16_const) dump_vec(os, "sweight", std::vector<double>(p.f16_sweight_g.begin(), p.f16_sweight_g.begin() + 17));
+            if (p.f16_const) {
+                dump_ints(os, "static", p.f16_static_lane);
+                dump_vec(os, "cstat", std::vector<double>(p.f16_cstat_g.begin(), p.f16_cstat_g.begin() + 8));
+                dump_ints(os, "facrow", p.f16_fac_row);
+            }
             os << "\n";
             for (int k = 0; k < p.nseg; ++k) {
                 os << "f16seg " << k;
                 dump_vec(os, "tab", std::vector<double>(p.f16_tab.begin() + (size_t)k * 64, p.f16_tab.begin() + (size_t)(k + 1) * 64));
-                if (p.f16_scaled) dump_vec(os, "kappa", std::vector<double>(p.f16_kappa.begin() + (size_t)k * 16, p.f16_kappa.begin() + (size_t)(k + 1) * 16));
+                if (p.f16_scaled || p.f16_const) dump_vec(os, "kappa", std::vector<double>(p.f16_kappa.begin() + (size_t)k * 16, p.f16_kappa.begin() + (size_t)(k + 1) * 16));
                 os << "\n";
             }
         }

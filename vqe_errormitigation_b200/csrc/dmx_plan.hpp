@@ -267,6 +267,14 @@ struct Plan {
     int f16_scaled = 0;
     std::vector<double> f16_kappa;       // [nseg][16]: (kappa_i, kappa_j) of the p-th pair (i < j = i ^ mask) at [2p], [2p + 1]
     std::vector<double> f16_sweight_g;   // [max(n_groups, 1)][17]: energy weights times the final lambda + the constant part
+    // Constant-coefficient form with variant slots (QP error-mitigation batches of a resolved circuit, dmx_frame16v_kernel):
+    // r_i' = w0 r_i + w1 r_j per segment, scaled like above to rho_i' = rho_i + kappa_i rho_j (one DFMA per slot and segment);
+    // the coefficients no rotation touches are constants times the product of the row's diagonal corrections.
+    int f16_const = 0;
+    std::vector<int> f16_static_lane;    // compact-frame lanes of the untouched live coefficients (at most 8)
+    std::vector<double> f16_cstat_g;     // [max(n_groups, 1)][8]: energy weight x constant value of those coefficients
+    std::vector<int> f16_fac_row;        // [n_slots] first row of the slot's correction table, -1: slot absent from the circuit
+    std::vector<double> f16_fac;         // [rows][24]: diagonal correction of (slot, index) on the 16 slots + 8 static coefficients
     int opt_f16_scaled = 1;              // use the scaled form of dmx_frame16t_kernel when the plan offers it
     int opt_f16_threads = 128;           // CTA size of dmx_frame16t_kernel
     int opt_frame16t = 1;                // 0 never, 1 device-resident batches from 2048 circuits, 2 also mapped host buffers
