@@ -1261,75 +1261,99 @@ __device__ __forceinline__ void f16_segment_const(double (&r)[16], const double2
     }
 }
 
+// one non-identity byte of a row: slot `sl`, basis-operation index `idx` -> entry in the thread's own list
+__device__ __forceinline__ void f16v_add_entry(const SlotDev* __restrict__ slots, unsigned sl, unsigned idx, unsigned* mya, int& cnt, bool& general) {
+    const int seg = slots[sl].seg;
+    if (seg < 0) return;                                    // slot not present in the circuit
+    if (!((slots[sl].diag_ok[idx >> 5] >> (idx & 31u)) & 1u)) { general = true; return; }
+    if (cnt < F16V_MAXACT) mya[cnt] = ((unsigned)seg << 20) | (sl << 8) | idx;
+    else general = true;
+    ++cnt;
+}
+
 __global__ void __launch_bounds__(128) dmx_frame16v_kernel(const __grid_constant__ Frame16vArgs a) {
     double2* const skap = reinterpret_cast<double2*>(dmx_smem);                 // [nseg][8]
     double* const sew = reinterpret_cast<double*>(skap + a.nseg * 8);           // [16] weights + [8] static terms of group 0 (+ pad)
     unsigned* const act = reinterpret_cast<unsigned*>(sew + 26);                // [128][F16V_MAXACT]
-    int* const nact = reinterpret_cast<int*>(act + 128 * F16V_MAXACT);          // [128]
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    unsigned* const srow = act + 128 * F16V_MAXACT;                             // the CTA's 128 rows, as loaded (+ 2 words of slack)
+    const int tid = threadIdx.x;
     const long long row0 = (long long)blockIdx.x * 128;
     const long long b = row0 + tid;
     const bool mine = b < a.batch;
-    nact[tid] = 0;
+    const unsigned S = (unsigned)a.n_slots;
+    {
+        // ---- the CTA's rows are ONE contiguous run of 128 * n_slots bytes: coalesced 16-byte loads into shared memory ----
+        const long long rows_here = a.batch - row0 < 128 ? a.batch - row0 : 128;
+        const unsigned nbytes = (unsigned)rows_here * S;
+        const uint8_t* const gbase = a.variants + row0 * (long long)S;
+        if ((reinterpret_cast<unsigned long long>(gbase) & 15ull) == 0ull) {
+            const unsigned n16 = nbytes >> 4;
+            const uint4* const src = reinterpret_cast<const uint4*>(gbase);
+            uint4* const dst = reinterpret_cast<uint4*>(srow);
+            for (unsigned i = tid; i < n16; i += 128) dst[i] = __ldcs(src + i);
+            uint8_t* const sb = reinterpret_cast<uint8_t*>(srow);
+            for (unsigned i = (n16 << 4) + tid; i < nbytes; i += 128) sb[i] = gbase[i];
+        } else {
+            uint8_t* const sb = reinterpret_cast<uint8_t*>(srow);
+            for (unsigned i = tid; i < nbytes; i += 128) sb[i] = gbase[i];
+        }
+    }
     for (int i = tid; i < a.nseg * 8; i += 128) skap[i] = __ldg(a.kappa + i);
     if (tid < 16) sew[tid] = __ldg(a.sweight + tid);
     else if (tid < 24) sew[tid] = __ldg(a.cstat + (tid - 16));
     __syncthreads();
 
-    // ---- scan of the warp's 32 rows: one contiguous run of 32 * n_slots bytes, walked as 32-bit words ----
+    // ---- the thread's own row: n_slots bytes at byte offset tid * n_slots, read as aligned words and funnel-shifted; almost
+    // all of it is zero, so the loop only remembers the last non-zero word (predicated, no branch) and the entries are
+    // decoded after it, by all the lanes that have one at the same time ----
+    unsigned* const mya = act + tid * F16V_MAXACT;
+    int cnt = 0;
+    bool general = false;
     {
-        const long long wrow0 = row0 + 32 * warp;
-        const long long rows_here = a.batch - wrow0 < 32 ? a.batch - wrow0 : 32;
-        const unsigned S = (unsigned)a.n_slots;
-        const unsigned valid = rows_here > 0 ? (unsigned)rows_here * S : 0u;
-        const uint8_t* const gbase = a.variants + wrow0 * (long long)S;
-        const bool word_ok = (reinterpret_cast<unsigned long long>(gbase) & 3ull) == 0ull;
-        constexpr int AHEAD = 8;
-        for (unsigned s0 = 0; s0 < valid; s0 += 128u * AHEAD) {
-            unsigned words[AHEAD];
-            unsigned any = 0u;
+        const unsigned o = (unsigned)tid * S, sh = (o & 3u) * 8u;
+        const unsigned* const wbase = srow + (o >> 2);
+        const unsigned nwords = (S + 3u) >> 2;
+        const unsigned tail = S & 3u;
+        const unsigned tail_mask = tail ? (1u << (8u * tail)) - 1u : 0xffffffffu;
+        unsigned lo = mine ? wbase[0] : 0u, nzw = 0u, nzi = 0u, nnz = 0u;
+        for (unsigned i = 0; i < nwords; ++i) {
+            const unsigned hi = mine ? wbase[i + 1] : 0u;
+            unsigned w = __funnelshift_r(lo, hi, sh);
+            if (i + 1 == nwords) w &= tail_mask;
+            lo = hi;
+            const bool nz = w != 0u;
+            nzw = nz ? w : nzw;
+            nzi = nz ? i : nzi;
+            nnz += nz ? 1u : 0u;
+        }
+        if (nnz == 1u) {
 #pragma unroll
-            for (int i = 0; i < AHEAD; ++i) {
-                const unsigned f = s0 + 128u * i + 4u * lane;
-                words[i] = 0u;
-                if (word_ok && f + 4u <= valid) {
-                    words[i] = __ldcs(reinterpret_cast<const unsigned*>(gbase + f));
-                } else if (f < valid) {
-                    for (int j = 0; j < 4; ++j)
-                        if (f + j < valid) words[i] |= (unsigned)gbase[f + j] << (8 * j);
-                }
-                any |= words[i];
+            for (int j = 0; j < 4; ++j) {
+                const unsigned idx = (nzw >> (8 * j)) & 255u;
+                if (idx) f16v_add_entry(a.slots, 4u * nzi + j, idx, mya, cnt, general);
             }
-            if (any == 0u) continue;                       // identity entries only (the common case): nothing to record
+        } else if (nnz > 1u) {
+            lo = wbase[0];
 #pragma unroll 1
-            for (int i = 0; i < AHEAD; ++i) {
-                unsigned word = words[0];
-#pragma unroll
-                for (int q = 1; q < AHEAD; ++q) word = i == q ? words[q] : word;
-                if (word == 0u) continue;
-                const unsigned f = s0 + 128u * i + 4u * lane;
+            for (unsigned i = 0; i < nwords; ++i) {
+                const unsigned hi = wbase[i + 1];
+                unsigned w = __funnelshift_r(lo, hi, sh);
+                if (i + 1 == nwords) w &= tail_mask;
+                lo = hi;
+                if (!w) continue;
+#pragma unroll 1
                 for (int j = 0; j < 4; ++j) {
-                    const unsigned idx = (word >> (8 * j)) & 255u;
-                    if (!idx) continue;
-                    const unsigned fb = f + j, r = fb / S, sl = fb - r * S;
-                    const int seg = a.slots[sl].seg;
-                    if (seg < 0) continue;                  // slot not present in the circuit
-                    const bool diag = (a.slots[sl].diag_ok[idx >> 5] >> (idx & 31u)) & 1u;
-                    const int lr = 32 * warp + (int)r;
-                    const int pos = atomicAdd(&nact[lr], diag ? 1 : 1000);      // a non-diagonal entry forces the general path
-                    if (diag && pos < F16V_MAXACT) act[lr * F16V_MAXACT + pos] = ((unsigned)seg << 20) | (sl << 8) | idx;
+                    const unsigned idx = (w >> (8 * j)) & 255u;
+                    if (idx) f16v_add_entry(a.slots, 4u * i + j, idx, mya, cnt, general);
                 }
             }
         }
-        __syncwarp();
     }
-    int cnt = nact[tid];
-    unsigned* const mya = act + tid * F16V_MAXACT;
-    if (cnt > F16V_MAXACT) {
+    if (general) {
         if (mine) a.worklist[atomicAdd(a.work_count, 1)] = (int)b;
         return;                                             // no block barrier and no shuffle below: the thread may leave
     }
-    // (stage, slot) order, whatever order the warp's atomics recorded the entries in
+    // (stage, slot) order (slots are found in ascending order; a later slot may belong to an earlier stage)
     for (int i = 1; i < cnt; ++i) {
         const unsigned v = mya[i];
         int j = i - 1;
@@ -2559,7 +2583,7 @@ static int run_segment(Plan& p, DevPlan* d, long long batch, const double* param
         // 32 + cw: always cw circuits per warp (cw = 8 / 16 / 24 / 32).
         // QP variant rows of a resolved circuit: one thread per row (dmx_frame16v_kernel); rows it cannot take land on the
         // worklist of the general tile path like the warp kernel's
-        if (p.f16_n > 0 && p.f16_const && p.opt_frame16t && mode == 0 && variants && batch >= 2048 && !host_mapped) {
+        if (p.f16_n > 0 && p.f16_const && p.opt_frame16t && mode == 0 && variants && batch >= 2048 && !host_mapped && p.n_slots <= 300) {
             Frame16vArgs f{};
             f.nseg = p.nseg; f.n_slots = p.n_slots; f.batch = batch; f.kappa = reinterpret_cast<const double2*>(d->h_kap16);
             f.sweight = d->h_sw16; f.cstat = d->h_cstat; f.group = group; f.variants = variants; f.slots = d->slots;
@@ -2568,7 +2592,7 @@ static int run_segment(Plan& p, DevPlan* d, long long batch, const double* param
             for (int k = 0; k < p.nseg; ++k) f.mask[k] = p.f16_mask[k];
             const long long grid = (batch + 127) / 128;
             if (grid >= (1LL << 31)) return done(fail(DMX_ERR_UNSUPPORTED, "batch too large for one launch"));
-            const size_t smem = (size_t)p.nseg * 128 + 26 * 8 + 128 * F16V_MAXACT * 4 + 128 * 4;
+            const size_t smem = (size_t)p.nseg * 128 + 26 * 8 + 128 * F16V_MAXACT * 4 + (((size_t)128 * p.n_slots + 15) & ~(size_t)15) + 16;
             dmx_frame16v_kernel<<<(unsigned)grid, 128, smem, st>>>(f);
             ++g_launches;
             CUDA_TRY(cudaGetLastError());
