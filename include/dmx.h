@@ -156,6 +156,14 @@ int dmx_plan_set_hamiltonian_groups(dmx_plan* plan, int n_groups, const double* 
  *                          (default: from 2^15 circuits a launch, the fewest circuits per warp - 8 / 16 / 24 / 32 - whose
  *                          warps are all resident at once), 8 / 16 = 32 circuits per warp advanced 8 / 16 at a time,
  *                          40 / 48 / 56 / 64 = always 8 / 16 / 24 / 32 circuits per warp
+ *   "frame16t"        0-2  thread-per-circuit forms of the frame kernel for plans whose rotations touch at most 16 coefficients
+ *                          in an XOR pattern (noisy H2 UCCSD: 16 of 23 live ones): dmx_frame16t_kernel for one-parameter sweeps,
+ *                          dmx_frame16v_kernel for QP variant batches of a resolved circuit.  0 = never, 1 = device-resident
+ *                          batches from 2048 circuits (default), 2 = also mapped host buffers (measured slower end to end)
+ *   "frame16t_scaled" 0/1  sweeps: carry the own-coefficient weights as host-tracked scales, 3 instead of 4 FP64 instructions
+ *                          per coefficient and segment, when every rotation moves every touched coefficient (default 1)
+ *   "frame16t_threads" n   CTA size of dmx_frame16t_kernel: 64, 128 (default) or 256
+ *   "tile_threads"    n    whole-state 7-qubit tiles: 512 threads x 2 coefficient groups (default) or 1024 x 1 (measured slower)
  *   "segment_cpb"     4|8  circuits per warp / thread of the frame kernels (default 8)
  *   "host_zero_copy"  0/1  dmx_energy_batch_host works in place on mapped page-locked buffers (default 1)
  *   "host_streams"    n    dmx_energy_batch_host_async: consecutive in-flight batches rotate over n streams, 1..8 (default 4)

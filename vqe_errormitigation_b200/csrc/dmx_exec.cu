@@ -1261,21 +1261,25 @@ __device__ __forceinline__ void f16_segment_const(double (&r)[16], const double2
     }
 }
 
-// one non-identity byte of a row: slot `sl`, basis-operation index `idx` -> entry in the thread's own list
-__device__ __forceinline__ void f16v_add_entry(const SlotDev* __restrict__ slots, unsigned sl, unsigned idx, unsigned* mya, int& cnt, bool& general) {
-    const int seg = slots[sl].seg;
-    if (seg < 0) return;                                    // slot not present in the circuit
+// one non-identity byte of a row: slot `sl`, basis-operation index `idx` -> entry in the thread's own list.  An entry is
+// (stage << 12 | slot, row of the correction table): the sort key and everything the segment loop needs, so applying a
+// correction costs no dependent table look-up.
+__device__ __forceinline__ void f16v_add_entry(const SlotDev* __restrict__ slots, const int2* __restrict__ smeta, unsigned sl, unsigned idx,
+                                               uint2* mya, int& cnt, bool& general) {
+    const int2 meta = smeta[sl];                            // (stage, first table row) from shared memory
+    if (meta.x < 0) return;                                 // slot not present in the circuit
     if (!((slots[sl].diag_ok[idx >> 5] >> (idx & 31u)) & 1u)) { general = true; return; }
-    if (cnt < F16V_MAXACT) mya[cnt] = ((unsigned)seg << 20) | (sl << 8) | idx;
+    if (cnt < F16V_MAXACT) mya[cnt] = make_uint2(((unsigned)meta.x << 12) | sl, (unsigned)meta.y + idx);
     else general = true;
     ++cnt;
 }
 
-__global__ void __launch_bounds__(128) dmx_frame16v_kernel(const __grid_constant__ Frame16vArgs a) {
+__global__ void __launch_bounds__(128, 7) dmx_frame16v_kernel(const __grid_constant__ Frame16vArgs a) {
     double2* const skap = reinterpret_cast<double2*>(dmx_smem);                 // [nseg][8]
     double* const sew = reinterpret_cast<double*>(skap + a.nseg * 8);           // [16] weights + [8] static terms of group 0 (+ pad)
-    unsigned* const act = reinterpret_cast<unsigned*>(sew + 26);                // [128][F16V_MAXACT]
-    unsigned* const srow = act + 128 * F16V_MAXACT;                             // the CTA's 128 rows, as loaded (+ 2 words of slack)
+    uint2* const act = reinterpret_cast<uint2*>(sew + 26);                      // [128][F16V_MAXACT]
+    int2* const smeta = reinterpret_cast<int2*>(act + 128 * F16V_MAXACT);       // [n_slots] (stage, first correction-table row)
+    unsigned* const srow = reinterpret_cast<unsigned*>(smeta + ((a.n_slots + 1) & ~1)); // the CTA's 128 rows, as loaded (+ slack)
     const int tid = threadIdx.x;
     const long long row0 = (long long)blockIdx.x * 128;
     const long long b = row0 + tid;
@@ -1299,6 +1303,7 @@ __global__ void __launch_bounds__(128) dmx_frame16v_kernel(const __grid_constant
         }
     }
     for (int i = tid; i < a.nseg * 8; i += 128) skap[i] = __ldg(a.kappa + i);
+    for (int i = tid; i < a.n_slots; i += 128) smeta[i] = make_int2(a.slots[i].seg, __ldg(a.fac_row + i));
     if (tid < 16) sew[tid] = __ldg(a.sweight + tid);
     else if (tid < 24) sew[tid] = __ldg(a.cstat + (tid - 16));
     __syncthreads();
@@ -1306,7 +1311,7 @@ __global__ void __launch_bounds__(128) dmx_frame16v_kernel(const __grid_constant
     // ---- the thread's own row: n_slots bytes at byte offset tid * n_slots, read as aligned words and funnel-shifted; almost
     // all of it is zero, so the loop only remembers the last non-zero word (predicated, no branch) and the entries are
     // decoded after it, by all the lanes that have one at the same time ----
-    unsigned* const mya = act + tid * F16V_MAXACT;
+    uint2* const mya = act + tid * F16V_MAXACT;
     int cnt = 0;
     bool general = false;
     {
@@ -1316,6 +1321,7 @@ __global__ void __launch_bounds__(128) dmx_frame16v_kernel(const __grid_constant
         const unsigned tail = S & 3u;
         const unsigned tail_mask = tail ? (1u << (8u * tail)) - 1u : 0xffffffffu;
         unsigned lo = mine ? wbase[0] : 0u, nzw = 0u, nzi = 0u, nnz = 0u;
+#pragma unroll 4
         for (unsigned i = 0; i < nwords; ++i) {
             const unsigned hi = mine ? wbase[i + 1] : 0u;
             unsigned w = __funnelshift_r(lo, hi, sh);
@@ -1330,7 +1336,7 @@ __global__ void __launch_bounds__(128) dmx_frame16v_kernel(const __grid_constant
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 const unsigned idx = (nzw >> (8 * j)) & 255u;
-                if (idx) f16v_add_entry(a.slots, 4u * nzi + j, idx, mya, cnt, general);
+                if (idx) f16v_add_entry(a.slots, smeta, 4u * nzi + j, idx, mya, cnt, general);
             }
         } else if (nnz > 1u) {
             lo = wbase[0];
@@ -1344,7 +1350,7 @@ __global__ void __launch_bounds__(128) dmx_frame16v_kernel(const __grid_constant
 #pragma unroll 1
                 for (int j = 0; j < 4; ++j) {
                     const unsigned idx = (w >> (8 * j)) & 255u;
-                    if (idx) f16v_add_entry(a.slots, 4u * i + j, idx, mya, cnt, general);
+                    if (idx) f16v_add_entry(a.slots, smeta, 4u * i + j, idx, mya, cnt, general);
                 }
             }
         }
@@ -1355,9 +1361,9 @@ __global__ void __launch_bounds__(128) dmx_frame16v_kernel(const __grid_constant
     }
     // (stage, slot) order (slots are found in ascending order; a later slot may belong to an earlier stage)
     for (int i = 1; i < cnt; ++i) {
-        const unsigned v = mya[i];
+        const uint2 v = mya[i];
         int j = i - 1;
-        while (j >= 0 && mya[j] > v) { mya[j + 1] = mya[j]; --j; }
+        while (j >= 0 && mya[j].x > v.x) { mya[j + 1] = mya[j]; --j; }
         mya[j + 1] = v;
     }
 
@@ -1367,17 +1373,17 @@ __global__ void __launch_bounds__(128) dmx_frame16v_kernel(const __grid_constant
 #pragma unroll
     for (int j = 0; j < 8; ++j) F[j] = 1.0;
     int next = 0;
-    unsigned ent = cnt > 0 ? mya[0] : 0xffffffffu;
+    uint2 ent = cnt > 0 ? mya[0] : make_uint2(0xffffffffu, 0u);
 #pragma unroll 1
     for (int k = 0; k <= a.nseg; ++k) {
-        while ((ent >> 20) == (unsigned)k) {
-            const double2* __restrict__ row = reinterpret_cast<const double2*>(a.fac + ((size_t)a.fac_row[(ent >> 8) & 4095u] + (ent & 255u)) * 24);
+        while ((ent.x >> 12) == (unsigned)k) {
+            const double2* __restrict__ row = reinterpret_cast<const double2*>(a.fac + (size_t)ent.y * 24);
 #pragma unroll
             for (int i = 0; i < 8; ++i) { const double2 f2 = __ldg(row + i); r[2 * i] *= f2.x; r[2 * i + 1] *= f2.y; }
 #pragma unroll
             for (int j = 0; j < 4; ++j) { const double2 f2 = __ldg(row + 8 + j); F[2 * j] *= f2.x; F[2 * j + 1] *= f2.y; }
             ++next;
-            ent = next < cnt ? mya[next] : 0xffffffffu;
+            ent = next < cnt ? mya[next] : make_uint2(0xffffffffu, 0u);
         }
         if (k == a.nseg) break;
         const double2* __restrict__ Kp = skap + k * 8;
@@ -2592,7 +2598,8 @@ static int run_segment(Plan& p, DevPlan* d, long long batch, const double* param
             for (int k = 0; k < p.nseg; ++k) f.mask[k] = p.f16_mask[k];
             const long long grid = (batch + 127) / 128;
             if (grid >= (1LL << 31)) return done(fail(DMX_ERR_UNSUPPORTED, "batch too large for one launch"));
-            const size_t smem = (size_t)p.nseg * 128 + 26 * 8 + 128 * F16V_MAXACT * 4 + (((size_t)128 * p.n_slots + 15) & ~(size_t)15) + 16;
+            const size_t smem = (size_t)p.nseg * 128 + 26 * 8 + 128 * F16V_MAXACT * 8 + (size_t)((p.n_slots + 1) & ~1) * 8 +
+                                (((size_t)128 * p.n_slots + 15) & ~(size_t)15) + 16;
             dmx_frame16v_kernel<<<(unsigned)grid, 128, smem, st>>>(f);
             ++g_launches;
             CUDA_TRY(cudaGetLastError());
