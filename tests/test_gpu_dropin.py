@@ -119,14 +119,25 @@ def test_batched_lockstep_optimiser_on_gpu():
 def test_swap_test_seven_qubits():
     q = cirq.LineQubit.range(7)
     circuit = Q.swap_circuit(3, q)
-    rho = cirq.DensityMatrixSimulator().simulate(circuit).final_density_matrix
+
+    def unmeasured(c):      # simulate() collapses a measured circuit like cirq's (trajectories.py); the state BEFORE the measurement:
+        return cirq.Circuit(op for op in c.all_operations() if not isinstance(op.gate, cirq.MeasurementGate))
+
+    rho = cirq.DensityMatrixSimulator().simulate(unmeasured(circuit), qubit_order=q).final_density_matrix
     ref = O.simulate(7, O.from_circuit(circuit, q)[1])
     assert np.max(np.abs(rho - ref)) < TOL
     assert abs(2 * np.real(np.trace(rho[:64, :64])) - 1 - 0.5) < 1e-12          # ideal SWAP-test value (reference: 0.4999999404 in c64)
     noisy = Q.noisy_circuit(circuit, "depolarize", 1e-3)
-    rho_n = cirq.DensityMatrixSimulator().simulate(noisy).final_density_matrix
+    rho_n = cirq.DensityMatrixSimulator().simulate(unmeasured(noisy), qubit_order=q).final_density_matrix
     ref_n = O.simulate(7, O.from_circuit(noisy, q)[1])
     assert np.max(np.abs(rho_n - ref_n)) < TOL
+    # with the terminal measurement in place simulate() returns the state collapsed onto the outcome it drew
+    res = cirq.DensityMatrixSimulator(seed=4).simulate(noisy, qubit_order=q)
+    bit = int(res.measurements["M"][0])
+    keep = slice(0, 64) if bit == 0 else slice(64, 128)
+    want = np.zeros_like(ref_n)
+    want[keep, keep] = ref_n[keep, keep] / np.real(np.trace(ref_n[keep, keep]))
+    assert np.max(np.abs(res.final_density_matrix - want)) < TOL
     np.random.seed(3)
     s = Q.QPSamp(circuit, "depolarize", 1e-3)
     ideal, noisy_v, mitigated = s.run_experiment(meas_reps=4000, sample_reps=4000, stat_reps=1, verbose=False)[0]
