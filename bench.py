@@ -696,7 +696,9 @@ def run_workload(wl, ctx, steps: int, warmup: int, with_cpu_baseline: bool, with
             torch.cuda.synchronize()
             wall0 = time.perf_counter()
             flush.zero_()
-            torch.cuda._sleep(2_000_000)          # ~1 ms device-side spin: the host queues the K launches behind it
+            # device-side spin (~1 ms per 50 steps): the host queues the K launches behind it (a launch costs the Python
+            # loop ~8.5 us; without the head start a step shorter than that would time the host, not the GPU)
+            torch.cuda._sleep(2_000_000 * min(-(-steps // 50), 40))
             launches0 = engine.launch_count()
             ev0.record()
             burst(steps)

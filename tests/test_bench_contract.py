@@ -90,6 +90,24 @@ def test_round2_streamed_protocol_record():
         assert "isolated" not in d["also"][key]                              # streaming steps keep per-step events
 
 
+def test_round2_thread_per_circuit_record():
+    """Final state of round 2: the sweep and the QP variant batch run on the thread-per-circuit kernels; the record names them,
+    keeps the contract keys and the parity field, and the roofline is stated on the flops those kernels execute."""
+    d = load("r2_bench_default_v7.json")
+    assert [k for k in BASE if k not in d] == []
+    assert d["parity_max_abs_err"] < 1e-10 and d["gpu_launches"] == d["steps"]
+    assert d["roofline"]["kernel"].startswith("dmx_frame16t_kernel") and d["roofline"]["executed_flops_per_circuit"] == 8 * 64 + 32
+    assert abs(d["roofline"]["frac"] - d["roofline"]["achieved"] / d["roofline"]["peak"]) < 1e-12
+    assert abs(d["ms_per_step"] * 1e-3 * d["value"] - 65536) < 1.0 and d["value"] > 2.0 * 7.2e9       # warp kernels: 7.2e9
+    assert 0 < d["isolated"]["value"] < d["value"] and d["e2e"]["value"] > d["e2e"]["synchronous"]["value"]
+    qem = d["also"]["h2_qem"]
+    assert qem["roofline"]["kernel"].startswith("dmx_frame16v_kernel") and qem["parity_max_abs_err"] < 1e-10
+    assert qem["value"] > 2.0 * 2.9e9 and qem["estimator"]["value"] > 0
+    assert d["also"]["h2_bonds"]["value"] > 2.0 * 6.5e9 and d["also"]["h2_bonds"]["parity_max_abs_err"] < 1e-10
+    for key in ("hea10", "lih12", "swap7_qem"):
+        assert d["also"][key]["parity_max_abs_err"] < 1e-10
+
+
 def test_round2_multi_gpu_records():
     for name, n in (("r2_bench_default_n2_v1.json", 2), ("r2_bench_default_n8_v2.json", 8)):
         d = load(name)

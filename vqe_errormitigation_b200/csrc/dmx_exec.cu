@@ -2589,7 +2589,9 @@ static int run_segment(Plan& p, DevPlan* d, long long batch, const double* param
         // 32 + cw: always cw circuits per warp (cw = 8 / 16 / 24 / 32).
         // QP variant rows of a resolved circuit: one thread per row (dmx_frame16v_kernel); rows it cannot take land on the
         // worklist of the general tile path like the warp kernel's
-        if (p.f16_n > 0 && p.f16_const && p.opt_frame16t && mode == 0 && variants && batch >= 2048 && !host_mapped && p.n_slots <= 300) {
+        const size_t f16v_smem = (size_t)p.nseg * 128 + 26 * 8 + 128 * F16V_MAXACT * 8 + (size_t)((p.n_slots + 1) & ~1) * 8 +
+                                 (((size_t)128 * p.n_slots + 15) & ~(size_t)15) + 16;          // tables + entry lists + the CTA's 128 rows
+        if (p.f16_n > 0 && p.f16_const && p.opt_frame16t && mode == 0 && variants && batch >= 2048 && !host_mapped && f16v_smem <= 48 * 1024) {
             Frame16vArgs f{};
             f.nseg = p.nseg; f.n_slots = p.n_slots; f.batch = batch; f.kappa = reinterpret_cast<const double2*>(d->h_kap16);
             f.sweight = d->h_sw16; f.cstat = d->h_cstat; f.group = group; f.variants = variants; f.slots = d->slots;
@@ -2598,9 +2600,7 @@ static int run_segment(Plan& p, DevPlan* d, long long batch, const double* param
             for (int k = 0; k < p.nseg; ++k) f.mask[k] = p.f16_mask[k];
             const long long grid = (batch + 127) / 128;
             if (grid >= (1LL << 31)) return done(fail(DMX_ERR_UNSUPPORTED, "batch too large for one launch"));
-            const size_t smem = (size_t)p.nseg * 128 + 26 * 8 + 128 * F16V_MAXACT * 8 + (size_t)((p.n_slots + 1) & ~1) * 8 +
-                                (((size_t)128 * p.n_slots + 15) & ~(size_t)15) + 16;
-            dmx_frame16v_kernel<<<(unsigned)grid, 128, smem, st>>>(f);
+            dmx_frame16v_kernel<<<(unsigned)grid, 128, f16v_smem, st>>>(f);
             ++g_launches;
             CUDA_TRY(cudaGetLastError());
             return done(run_tile_single(p, d, batch, params, variants, out, OUT_ENERGY, wl + 1, wl, st, group));
