@@ -108,6 +108,15 @@ def test_round2_thread_per_circuit_record():
         assert d["also"][key]["parity_max_abs_err"] < 1e-10
 
 
+def test_round2_final_multi_gpu_records():
+    for name, n in (("r2_bench_default_n2_v3.json", 2), ("r2_bench_default_n8_v4.json", 8)):
+        d = load(name)
+        assert d["n_gpus"] == n and d["scaling"] == "weak" and d["value"] > 0.85 * n * 2.3e10
+        assert d["roofline"]["kernel"].startswith("dmx_frame16t_kernel") and d["parity_max_abs_err"] < 1e-10
+        est = d["also"]["h2_qem"]["estimator"]
+        assert "NCCL all-reduce" in est["contains"] and est["variants_per_estimate"] == 125000 * n
+
+
 def test_round2_multi_gpu_records():
     for name, n in (("r2_bench_default_n2_v1.json", 2), ("r2_bench_default_n8_v2.json", 8)):
         d = load(name)
