@@ -236,6 +236,16 @@ void dmx_qp_sampler_destroy(dmx_qp_sampler* sampler);
 int dmx_qp_sample_variants(int n_slots, const int32_t* n_choices, const double* qp, int stride, uint64_t seed,
                            uint64_t first_sample, int64_t batch, uint8_t* d_variants, double* d_signs, void* stream);
 
+/* Draw and evaluate in one call: d_energy[b] = energy of the variant row that dmx_qp_sampler_draw(sampler, seed, first_sample, ...)
+ * would write for sample b, d_signs[b] = its sign - the inner loop of IErrorMitigationManager.get_mu_effective
+ * (src/error_mitigation.py:401-452: identifiers -> process_circuit -> sign * weight * value) without the identifier table: on
+ * plans with the thread-per-row form (resolved Clifford + Pauli-noise circuits such as noisy H2, see "frame16t") one thread
+ * runs a sample's Philox stream, keeps its few non-identity draws and evolves the row (dmx_frame16q_kernel); other whole-state
+ * plans draw into stream-ordered scratch and run dmx_energy_batch.  Bit-identical to the two-step path.  The plan must have no
+ * circuit parameters (a resolved circuit) and as many variant slots as the sampler; streaming plans: DMX_ERR_UNSUPPORTED. */
+int dmx_qp_sampled_energies(dmx_plan* plan, const dmx_qp_sampler* sampler, uint64_t seed, uint64_t first_sample, int64_t batch,
+                            double* d_energy, double* d_signs, void* stream);
+
 /* Shot sampling on the device - the sampling half of DensityMatrixSimulator.run as the reference uses it
  * (src/data_containers/model_hydrogen.py:132,155: evolve once, draw `repetitions` outcomes from |diag rho|, histogram) and the
  * parity read-out of measure_observable (:103-112,136-166: expectation = 2 P(even parity on the term's qubits) - 1).

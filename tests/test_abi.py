@@ -23,7 +23,7 @@ def declared_functions():
 def test_header_symbols_exported_and_bound():
     lib = _lib.load()
     names = declared_functions()
-    assert len(names) == 28
+    assert len(names) == 29
     for name in names:
         assert hasattr(lib, name), f"{name} declared in include/dmx.h but not exported by libdmx.so"
         assert name in _lib.EXPORTS, f"{name} has no ctypes prototype in _lib.py"

@@ -89,6 +89,63 @@ def test_device_resident_mitigation_estimator():
     assert abs(mean - ideal) < 6 * stderr + 1e-4 and abs(mean - ideal) < abs(noisy - ideal)
 
 
+@pytest.mark.gpu
+def test_fused_draw_and_evaluate_is_bit_identical_to_the_two_step_path():
+    """dmx_qp_sampled_energies (dmx_frame16q_kernel: one thread draws AND evaluates one sample) against QpSampler.draw +
+    CircuitProgram.energies on the same (seed, first_sample): signs and energies bit for bit - with the circuit's own
+    quasi-probabilities, with tables that put weight on R-type / projector operations (those samples are re-drawn into a
+    compact table for the general tile path), with tables dense enough to overflow a thread's entry list, on ragged batches
+    and stream offsets; and against the numpy Philox restatement + the C oracle for a few samples."""
+    import torch
+    from oracle import dm_oracle as O
+    from test_gpu_parity import oracle_energy, qp_noisy_variant_program
+    from workloads import h2_terms
+    from vqe_errormitigation_b200 import engine
+    terms = h2_terms()
+    ham = O.pauli_terms_to_matrix(4, *terms)
+    n1, n2 = [O.bit_flip(1e-3), O.depolarize(1e-3)], [O.two_qubit_depolarize(1e-3)]
+    prog, gates = qp_noisy_variant_program(n1, n2, terms)
+    assert " const=1" in prog.dump()
+    arity = [len(g[1]) for g in gates]
+    rng = np.random.default_rng(99)
+
+    def tables(kind):
+        out = []
+        for a in arity:
+            k = 16 if a == 1 else 256
+            t = np.zeros(k)
+            t[0] = 1.0 + 4e-3
+            pauli = [1, 2, 3] if a == 1 else [16 * i + j for i in range(4) for j in range(4) if i or j]
+            for j in pauli:
+                t[j] = -4e-3 / len(pauli) * rng.uniform(0.5, 1.5)
+            if kind == "rtype":                       # weight on rotations / projectors: general path
+                t[7 if a == 1 else 7 * 16 + 2] = 3e-3
+            if kind == "dense":                       # ~8 non-identity draws per row: the entry list overflows for some rows
+                t[0] = 1.0
+                for j in pauli:
+                    t[j] = 0.07 / len(pauli)
+            out.append(t)
+        return out
+
+    for kind in ("pauli", "rtype", "dense"):
+        qps = tables(kind)
+        sampler = engine.QpSampler(qps)
+        for batch, seed, first in ((4099, 7, 0), (2048, 123456789012345, (1 << 33) + 5), (130, 3, 17)):
+            values, signs = sampler.sampled_energies(prog, batch, seed, first_sample=first)
+            rows, signs2 = sampler.draw(batch, seed, first_sample=first)
+            want = prog.energies(None, rows)
+            assert torch.equal(signs, signs2), (kind, batch)
+            if batch >= 2048:                         # the two-step path runs the same thread-per-row arithmetic
+                assert torch.equal(values, want), (kind, batch, float((values - want).abs().max()))
+            else:                                     # ... and the warp-per-row kernel below 2048 rows: equal to rounding
+                assert float((values - want).abs().max()) < 1e-13
+        ref_rows, ref_signs = P.sample_variants(qps, 64, 7)
+        values, signs = sampler.sampled_energies(prog, 4099, 7)
+        assert np.array_equal(signs[:64].cpu().numpy(), ref_signs)
+        for b in range(0, 64, 7):
+            assert abs(float(values[b]) - oracle_energy(O.variant_ops(gates, n1, n2, ref_rows[b]), 4, ham)) < 1e-10, (kind, b)
+
+
 def test_reference_shot_sampler_statistics():
     """numpy restatement of the device shot sampler (philox_ref.shot_expectations): parity expectations converge to the exact
     values of the distribution, every mask is read from the same shots, rows use independent streams."""

@@ -70,6 +70,7 @@ EXPORTS = {
     "dmx_qp_reduce": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
     "dmx_qp_sampler_create": (C.c_int, [C.c_int, C.POINTER(C.c_int32), C.POINTER(C.c_double), C.c_int, C.POINTER(C.c_void_p)]),
     "dmx_qp_sampler_draw": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "dmx_qp_sampled_energies": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),
     "dmx_qp_sampler_destroy": (None, [C.c_void_p]),
     "dmx_qp_sample_variants": (C.c_int, [C.c_int, C.POINTER(C.c_int32), C.POINTER(C.c_double), C.c_int, C.c_uint64, C.c_uint64,
                                          C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),

@@ -96,6 +96,7 @@ struct TileArgs {
     int n_terms;
     const int* group;           // optional: circuit b uses coefficient row group[b] (row 0 when NULL)
     double* out;
+    int variants_compact;       // worklist runs: the variant row of worklist entry i is row i of `variants` (not row worklist[i])
 };
 
 __device__ __forceinline__ unsigned map_bits(unsigned v, const BitRun* runs, int n) {
@@ -357,7 +358,7 @@ __global__ void __launch_bounds__(MAXT) dmx_tile_kernel(const TileArgs a) {
                                 const long long ci = c_first + c;
                                 unsigned idx = 0;
                                 if (a.variants && ci < total) {
-                                    const long long b = a.worklist ? a.worklist[ci] : ci + a.circuit_offset;
+                                    const long long b = a.variants_compact ? ci : (a.worklist ? a.worklist[ci] : ci + a.circuit_offset);
                                     idx = a.variants[b * a.n_slots + m.a0];
                                 }
                                 if (!idx) break;
@@ -1274,6 +1275,61 @@ __device__ __forceinline__ void f16v_add_entry(const SlotDev* __restrict__ slots
     ++cnt;
 }
 
+// the part of a thread-per-row kernel after the row's entries are known: sort them, evolve, energy
+__device__ __forceinline__ void f16v_finish(const Frame16vArgs& a, const double2* __restrict__ skap, const double* __restrict__ sew, uint2* mya, int cnt,
+                                            bool general, bool mine, long long b) {
+    if (general) {
+        if (mine) a.worklist[atomicAdd(a.work_count, 1)] = (int)b;
+        return;                                             // no block barrier and no shuffle below: the thread may leave
+    }
+    // (stage, slot) order (slots are found in ascending order; a later slot may belong to an earlier stage)
+    for (int i = 1; i < cnt; ++i) {
+        const uint2 v = mya[i];
+        int j = i - 1;
+        while (j >= 0 && mya[j].x > v.x) { mya[j + 1] = mya[j]; --j; }
+        mya[j + 1] = v;
+    }
+
+    double r[16], F[8];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) r[i] = a.init[i];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) F[j] = 1.0;
+    int next = 0;
+    uint2 ent = cnt > 0 ? mya[0] : make_uint2(0xffffffffu, 0u);
+#pragma unroll 1
+    for (int k = 0; k <= a.nseg; ++k) {
+        while ((ent.x >> 12) == (unsigned)k) {
+            const double2* __restrict__ row = reinterpret_cast<const double2*>(a.fac + (size_t)ent.y * 24);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) { const double2 f2 = __ldg(row + i); r[2 * i] *= f2.x; r[2 * i + 1] *= f2.y; }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { const double2 f2 = __ldg(row + 8 + j); F[2 * j] *= f2.x; F[2 * j + 1] *= f2.y; }
+            ++next;
+            ent = next < cnt ? mya[next] : make_uint2(0xffffffffu, 0u);
+        }
+        if (k == a.nseg) break;
+        const double2* __restrict__ Kp = skap + k * 8;
+        DMX_F16_SWITCH(f16_segment_const, r, Kp)
+    }
+    double e = 0.0;
+    if (a.group) {
+        const int g = mine ? a.group[b] : 0;
+        const double* __restrict__ ew = a.sweight + (size_t)g * 17;
+        const double* __restrict__ cs = a.cstat + (size_t)g * 8;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) e = fma(__ldg(cs + j), F[j], e);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) e = fma(__ldg(ew + i), r[i], e);
+    } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) e = fma(sew[16 + j], F[j], e);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) e = fma(sew[i], r[i], e);
+    }
+    if (mine) a.out[b] = e;
+}
+
 __global__ void __launch_bounds__(128, 7) dmx_frame16v_kernel(const __grid_constant__ Frame16vArgs a) {
     double2* const skap = reinterpret_cast<double2*>(dmx_smem);                 // [nseg][8]
     double* const sew = reinterpret_cast<double*>(skap + a.nseg * 8);           // [16] weights + [8] static terms of group 0 (+ pad)
@@ -1355,56 +1411,7 @@ __global__ void __launch_bounds__(128, 7) dmx_frame16v_kernel(const __grid_const
             }
         }
     }
-    if (general) {
-        if (mine) a.worklist[atomicAdd(a.work_count, 1)] = (int)b;
-        return;                                             // no block barrier and no shuffle below: the thread may leave
-    }
-    // (stage, slot) order (slots are found in ascending order; a later slot may belong to an earlier stage)
-    for (int i = 1; i < cnt; ++i) {
-        const uint2 v = mya[i];
-        int j = i - 1;
-        while (j >= 0 && mya[j].x > v.x) { mya[j + 1] = mya[j]; --j; }
-        mya[j + 1] = v;
-    }
-
-    double r[16], F[8];
-#pragma unroll
-    for (int i = 0; i < 16; ++i) r[i] = a.init[i];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) F[j] = 1.0;
-    int next = 0;
-    uint2 ent = cnt > 0 ? mya[0] : make_uint2(0xffffffffu, 0u);
-#pragma unroll 1
-    for (int k = 0; k <= a.nseg; ++k) {
-        while ((ent.x >> 12) == (unsigned)k) {
-            const double2* __restrict__ row = reinterpret_cast<const double2*>(a.fac + (size_t)ent.y * 24);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) { const double2 f2 = __ldg(row + i); r[2 * i] *= f2.x; r[2 * i + 1] *= f2.y; }
-#pragma unroll
-            for (int j = 0; j < 4; ++j) { const double2 f2 = __ldg(row + 8 + j); F[2 * j] *= f2.x; F[2 * j + 1] *= f2.y; }
-            ++next;
-            ent = next < cnt ? mya[next] : make_uint2(0xffffffffu, 0u);
-        }
-        if (k == a.nseg) break;
-        const double2* __restrict__ Kp = skap + k * 8;
-        DMX_F16_SWITCH(f16_segment_const, r, Kp)
-    }
-    double e = 0.0;
-    if (a.group) {
-        const int g = mine ? a.group[b] : 0;
-        const double* __restrict__ ew = a.sweight + (size_t)g * 17;
-        const double* __restrict__ cs = a.cstat + (size_t)g * 8;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) e = fma(__ldg(cs + j), F[j], e);
-#pragma unroll
-        for (int i = 0; i < 16; ++i) e = fma(__ldg(ew + i), r[i], e);
-    } else {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) e = fma(sew[16 + j], F[j], e);
-#pragma unroll
-        for (int i = 0; i < 16; ++i) e = fma(sew[i], r[i], e);
-    }
-    if (mine) a.out[b] = e;
+    f16v_finish(a, skap, sew, mya, cnt, general, mine, b);
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -1584,8 +1591,11 @@ __global__ void __launch_bounds__(256) dmx_qp_sample_kernel(int n_slots, const i
                                      const unsigned* __restrict__ summ /* [ceil(S/4)]: bit 0 sign parity, bit 1 zero weight of the four identity
                                                                           entries, bit 2: some threshold is 0 (no fast test) */,
                                      unsigned long long seed, unsigned long long first_sample, long long batch,
-                                     unsigned char* __restrict__ variants, double* __restrict__ signs) {
+                                     unsigned char* __restrict__ variants, double* __restrict__ signs,
+                                     const int* __restrict__ sample_list = nullptr /* list mode: row b is sample first_sample + sample_list[b] ... */,
+                                     const int* __restrict__ list_count = nullptr /* ... for b < *list_count (device-side count) */) {
     const int lane = threadIdx.x & 31;
+    if (list_count) batch = *list_count;
     // Persistent warps walk the samples with a grid stride and keep the tables of their first slot group (every group when
     // the circuit has <= 128 slots) in registers.  ncu (profiles/r2_ncu_full_sampler_kernel_v1.txt): 260 instructions per
     // sample, ALU pipe 56 % - the kernel is instruction bound, so the common case is kept short: ONE chained 32-bit test
@@ -1596,7 +1606,7 @@ __global__ void __launch_bounds__(256) dmx_qp_sample_kernel(int n_slots, const i
     unsigned sum0 = 0u;
     if (4 * lane < n_slots) { q0 = thr32[lane]; sum0 = summ[lane]; }
     for (long long b = warp0; b < batch; b += nwarps) {
-        const unsigned long long gidx = first_sample + (unsigned long long)b;
+        const unsigned long long gidx = first_sample + (unsigned long long)(sample_list ? (long long)sample_list[b] : b);
         unsigned char* const out = variants + b * n_slots;
         const unsigned misalign = (unsigned)(reinterpret_cast<unsigned long long>(out) & 3ull);      // 0: word stores, 2: half-word stores
         unsigned neg = 0u, zero = 0u;
@@ -1644,8 +1654,93 @@ __global__ void __launch_bounds__(256) dmx_qp_sample_kernel(int n_slots, const i
         }
         neg = __reduce_xor_sync(0xffffffffu, neg);
         zero = __reduce_or_sync(0xffffffffu, zero);
-        if (lane == 0) signs[b] = zero ? 0.0 : (neg ? -1.0 : 1.0);
+        if (lane == 0 && signs) signs[b] = zero ? 0.0 : (neg ? -1.0 : 1.0);
     }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// frame16q: draw AND evaluate - one thread per SAMPLE of the quasi-probability estimator.  The thread runs the sampler's own
+// Philox stream (same counters, thresholds, cumulative tables and sign rules as dmx_qp_sample_kernel, so sample b is the row
+// dmx_qp_sampler_draw would write), keeps the few non-identity draws as entries and finishes like dmx_frame16v_kernel; the
+// identifier table (122 bytes per sample) is never written or read.  Samples the thread-per-row form cannot take are listed;
+// dmx_qp_sampled_energies re-draws exactly those into a compact table for the tile kernel.
+// ---------------------------------------------------------------------------------------------------------
+struct Frame16qArgs {
+    Frame16vArgs v;
+    const int* n_choices;
+    const double* cdf;
+    const unsigned char* sgn;
+    int stride;
+    const ulonglong2* thr0;
+    const unsigned* sgn0;
+    const uint4* thr32;
+    const unsigned* summ;
+    unsigned long long seed, first_sample;
+    double* signs;
+};
+
+__global__ void __launch_bounds__(128, 7) dmx_frame16q_kernel(const __grid_constant__ Frame16qArgs q) {
+    const Frame16vArgs& a = q.v;
+    const int ng = (a.n_slots + 3) >> 2;
+    double2* const skap = reinterpret_cast<double2*>(dmx_smem);                 // [nseg][8]
+    double* const sew = reinterpret_cast<double*>(skap + a.nseg * 8);           // [16] + [8] (+ pad)
+    uint2* const act = reinterpret_cast<uint2*>(sew + 26);                      // [128][F16V_MAXACT]
+    int2* const smeta = reinterpret_cast<int2*>(act + 128 * F16V_MAXACT);       // [n_slots]
+    uint4* const sthr = reinterpret_cast<uint4*>(smeta + ((a.n_slots + 1) & ~1)); // [ng] identity thresholds of four slots
+    unsigned* const ssum = reinterpret_cast<unsigned*>(sthr + ng);              // [ng]
+    const int tid = threadIdx.x;
+    const long long b = (long long)blockIdx.x * 128 + tid;
+    const bool mine = b < a.batch;
+    for (int i = tid; i < a.nseg * 8; i += 128) skap[i] = __ldg(a.kappa + i);
+    for (int i = tid; i < a.n_slots; i += 128) smeta[i] = make_int2(a.slots[i].seg, __ldg(a.fac_row + i));
+    for (int i = tid; i < ng; i += 128) { sthr[i] = __ldg(q.thr32 + i); ssum[i] = __ldg(q.summ + i); }
+    if (tid < 16) sew[tid] = __ldg(a.sweight + tid);
+    else if (tid < 24) sew[tid] = __ldg(a.cstat + (tid - 16));
+    __syncthreads();
+    if (!mine) return;
+
+    uint2* const mya = act + tid * F16V_MAXACT;
+    int cnt = 0;
+    bool general = false;
+    unsigned neg = 0u, zero = 0u;
+    const unsigned long long gidx = q.first_sample + (unsigned long long)b;
+#pragma unroll 1
+    for (int g = 0; g < ng; ++g) {
+        unsigned c[4] = {(unsigned)gidx, (unsigned)(gidx >> 32), (unsigned)g, 0u};
+        philox4x32_10(c, (unsigned)q.seed, (unsigned)(q.seed >> 32));
+        const uint4 t = sthr[g];
+        const unsigned sm = ssum[g];
+        if (c[0] <= t.x && c[1] <= t.y && c[2] <= t.z && c[3] <= t.w && !(sm & 4u)) {
+            neg ^= sm & 1u;
+            zero |= (sm >> 1) & 1u;
+            continue;
+        }
+        const ulonglong2 fa = q.thr0[2 * g], fb = q.thr0[2 * g + 1];
+        const unsigned long long first[4] = {fa.x, fa.y, fb.x, fb.y};
+        const unsigned s0 = q.sgn0[g];
+#pragma unroll 1
+        for (int i = 0; i < 4; ++i) {
+            const int s = 4 * g + i;
+            unsigned sg = (s0 >> (8 * i)) & 255u;
+            const unsigned ci = i == 0 ? c[0] : (i == 1 ? c[1] : (i == 2 ? c[2] : c[3]));
+            const unsigned long long fi = i == 0 ? first[0] : (i == 1 ? first[1] : (i == 2 ? first[2] : first[3]));
+            if (!((unsigned long long)ci < fi)) {             // never for the padding slots (threshold 2^32)
+                const double u = ((double)ci + 0.5) * (1.0 / 4294967296.0);
+                const double* __restrict__ row = q.cdf + (size_t)s * q.stride;
+                int hi = q.n_choices[s] - 1, lo = hi > 0 ? 1 : 0;
+                while (lo < hi) {
+                    const int mid = (lo + hi) >> 1;
+                    if (row[mid] > u) hi = mid; else lo = mid + 1;
+                }
+                sg = q.sgn[(size_t)s * q.stride + lo];
+                if (lo) f16v_add_entry(a.slots, smeta, (unsigned)s, (unsigned)lo, mya, cnt, general);
+            }
+            neg ^= sg == 1u;
+            zero |= sg == 2u;
+        }
+    }
+    q.signs[b] = zero ? 0.0 : (neg ? -1.0 : 1.0);
+    f16v_finish(a, skap, sew, mya, cnt, general, mine, b);
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -2303,7 +2398,8 @@ static void fill_common(TileArgs& a, Plan& p, DevPlan* d, const Pass& ps, const 
 
 // Whole-state-in-smem execution (n <= 7).  worklist != nullptr: run only the listed circuits (energy only).
 static int run_tile_single(Plan& p, DevPlan* d, long long batch, const double* params, const uint8_t* variants, double* out,
-                           int mode, const int* worklist, const int* work_count, cudaStream_t st, const int* group = nullptr) {
+                           int mode, const int* worklist, const int* work_count, cudaStream_t st, const int* group = nullptr,
+                           bool variants_compact = false) {
     const Pass& ps = p.passes[0];
     TileArgs a{};
     fill_common(a, p, d, ps, params, variants);
@@ -2311,6 +2407,7 @@ static int run_tile_single(Plan& p, DevPlan* d, long long batch, const double* p
     a.k = p.n; a.cpb = p.cpb; a.batch = batch; a.worklist = worklist; a.work_count = work_count;
     a.epilogue = mode; a.term_idx = d->term_idx; a.term_coef = d->term_coef; a.n_terms = (int)p.term_idx.size(); a.out = out;
     a.group = group;
+    a.variants_compact = variants_compact ? 1 : 0;
     const unsigned E = (unsigned)a.cpb << (2 * p.n + a.pad);
     int threads, gpt;
     tile_geometry(E, &threads, &gpt, p.opt_tile_threads == 1024);
@@ -3042,6 +3139,67 @@ int dmx_qp_sampler_draw(const dmx_qp_sampler* sm, uint64_t seed, uint64_t first_
     ++g_launches;
     CUDA_TRY(cudaGetLastError());
     return DMX_OK;
+}
+
+int dmx_qp_sampled_energies(dmx_plan* plan, const dmx_qp_sampler* sm, uint64_t seed, uint64_t first_sample, int64_t batch,
+                            double* d_energy, double* d_signs, void* stream) {
+    int rc = check_exec(plan, batch, nullptr, d_energy);
+    if (rc) return rc;
+    if (!sm || (batch > 0 && !d_signs)) return fail(DMX_ERR_INVALID, "NULL argument");
+    Plan& p = plan->p;
+    if (p.term_idx.empty()) return fail(DMX_ERR_STATE, "no Hamiltonian set");
+    if (sm->n_slots != p.n_slots) return fail(DMX_ERR_INVALID, "sampler and plan have different numbers of variant slots");
+    if (p.path == 2) return fail(DMX_ERR_UNSUPPORTED, "streaming plans take dmx_qp_sampler_draw + dmx_energy_batch (caller-owned workspace)");
+    DevPlan* d;
+    rc = ensure_device(p, &d);
+    if (rc) return rc;
+    if (sm->device != d->device) return fail(DMX_ERR_STATE, "sampler tables live on another device");
+    if (batch == 0) return DMX_OK;
+    NvtxRange nvtx("dmx:qp_sampled_energies");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int ng = (p.n_slots + 3) / 4;
+    const char* base = sm->d;
+    const int* n_choices = (const int*)(base + sm->cb + sm->fb);
+    const double* cdf = (const double*)base;
+    const unsigned char* sgn = (const unsigned char*)(base + sm->cb + sm->fb + sm->nb + sm->gb);
+    const ulonglong2* thr0 = (const ulonglong2*)(base + sm->cb);
+    const unsigned* sgn0 = (const unsigned*)(base + sm->cb + sm->fb + sm->nb);
+    const uint4* thr32 = (const uint4*)(base + sm->cb + sm->fb + sm->nb + sm->gb + sm->sb);
+    const unsigned* summ = (const unsigned*)(base + sm->cb + sm->fb + sm->nb + sm->gb + sm->sb + (size_t)ng * 16);
+    const size_t smem = (size_t)p.nseg * 128 + 26 * 8 + 128 * F16V_MAXACT * 8 + (size_t)((p.n_slots + 1) & ~1) * 8 + (size_t)ng * 20 + 16;
+    const bool fused = p.path == 1 && p.f16_n > 0 && p.f16_const && p.opt_frame16t && p.f_classes.empty() && smem <= 48 * 1024 && batch < (1LL << 31);
+    // scratch, stream-ordered: [count | sample list] and the identifier rows (all of them on the two-step path, the listed ones otherwise)
+    int* wl = nullptr;
+    uint8_t* rows = nullptr;
+    CUDA_TRY(cudaMallocAsync((void**)&rows, (size_t)batch * p.n_slots, st));
+    struct Release { void* a; void* b; cudaStream_t st; ~Release() { if (a) cudaFreeAsync(a, st); if (b) cudaFreeAsync(b, st); } } release{rows, nullptr, st};
+    if (!fused) {
+        rc = dmx_qp_sampler_draw(sm, seed, first_sample, batch, rows, d_signs, stream);
+        if (rc) return rc;
+        return energy_impl(plan, batch, nullptr, rows, d_energy, nullptr, 0, st);
+    }
+    CUDA_TRY(cudaMallocAsync((void**)&wl, (size_t)(batch + 1) * sizeof(int), st));
+    release.b = wl;
+    CUDA_TRY(cudaMemsetAsync(wl, 0, sizeof(int), st));
+    Frame16qArgs q{};
+    Frame16vArgs& f = q.v;
+    f.nseg = p.nseg; f.n_slots = p.n_slots; f.batch = batch; f.kappa = reinterpret_cast<const double2*>(d->h_kap16);
+    f.sweight = d->h_sw16; f.cstat = d->h_cstat; f.group = nullptr; f.variants = nullptr; f.slots = d->slots;
+    f.fac_row = d->h_facrow; f.fac = d->h_fac; f.out = d_energy; f.worklist = wl + 1; f.work_count = wl;
+    for (int i = 0; i < 16; ++i) f.init[i] = p.f16_init[i];
+    for (int k = 0; k < p.nseg; ++k) f.mask[k] = p.f16_mask[k];
+    q.n_choices = n_choices; q.cdf = cdf; q.sgn = sgn; q.stride = sm->stride; q.thr0 = thr0; q.sgn0 = sgn0; q.thr32 = thr32; q.summ = summ;
+    q.seed = seed; q.first_sample = first_sample; q.signs = d_signs;
+    dmx_frame16q_kernel<<<(unsigned)((batch + 127) / 128), 128, smem, st>>>(q);
+    ++g_launches;
+    CUDA_TRY(cudaGetLastError());
+    // listed samples (a non-diagonal basis operation, or more entries than a thread keeps): drawn again, row i = list entry i,
+    // and evaluated by the general tile path
+    dmx_qp_sample_kernel<<<(unsigned)std::max(1, sm->sm_count), 256, 0, st>>>(p.n_slots, n_choices, cdf, sgn, sm->stride, thr0, sgn0, thr32, summ,
+                                                                             seed, first_sample, batch, rows, nullptr, wl + 1, wl);
+    ++g_launches;
+    CUDA_TRY(cudaGetLastError());
+    return run_tile_single(p, d, batch, nullptr, rows, d_energy, OUT_ENERGY, wl + 1, wl, st, nullptr, true);
 }
 
 int dmx_qp_sample_variants(int n_slots, const int32_t* n_choices, const double* qp, int stride, uint64_t seed, uint64_t first_sample,

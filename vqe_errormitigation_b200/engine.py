@@ -454,6 +454,20 @@ class QpSampler:
                                             C.c_void_p(variants.data_ptr()), C.c_void_p(signs.data_ptr()), stream))
         return variants, signs
 
+    def sampled_energies(self, program: "CircuitProgram", batch: int, seed: int, first_sample: int = 0):
+        """(energies float64 [batch], signs float64 [batch]) CUDA tensors of the variant rows ``draw(batch, seed, first_sample)``
+        would produce, without materialising them where the plan allows (``dmx_qp_sampled_energies``: one thread draws and
+        evaluates one sample) - the device loop of ``IErrorMitigationManager.get_mu_effective``.  Bit-identical to
+        ``program.energies(None, draw(...)[0])``."""
+        torch = _require_cuda()
+        dev = torch.device("cuda", torch.cuda.current_device())
+        values = torch.empty(batch, dtype=torch.float64, device=dev)
+        signs = torch.empty(batch, dtype=torch.float64, device=dev)
+        stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+        check(self._lib.dmx_qp_sampled_energies(program._handle, self._handle, C.c_uint64(seed), C.c_uint64(first_sample), batch,
+                                                C.c_void_p(values.data_ptr()), C.c_void_p(signs.data_ptr()), stream))
+        return values, signs
+
     def __del__(self):
         handle, self._handle = getattr(self, "_handle", None), None
         if handle:

@@ -656,6 +656,10 @@ class IErrorMitigationManager:
         import torch
         from . import parallel
         prog = self._variant_program()
+        if prog.info["path"] == 1 and hi > lo and hasattr(sampler, "sampled_energies"):
+            # register-resident plans: one kernel draws and evaluates (dmx_qp_sampled_energies), no identifier table
+            values, signs = sampler.sampled_energies(prog, hi - lo, seed, first_sample=lo)
+            return parallel.sharded_sums(values, signs)
         variants, signs = sampler.draw(hi - lo, seed, first_sample=lo)
         if prog.info["path"] != 1 and hi > lo:
             uniq, inverse, counts = _unique_rows(variants)
