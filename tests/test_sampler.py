@@ -127,16 +127,23 @@ def test_fused_draw_and_evaluate_is_bit_identical_to_the_two_step_path():
             out.append(t)
         return out
 
+    launches = {}
     for kind in ("pauli", "rtype", "dense"):
         qps = tables(kind)
         sampler = engine.QpSampler(qps)
+        n0 = engine.launch_count()
+        sampler.sampled_energies(prog, 4099, 1)
+        launches[kind] = engine.launch_count() - n0
         for batch, seed, first in ((4099, 7, 0), (2048, 123456789012345, (1 << 33) + 5), (130, 3, 17)):
             values, signs = sampler.sampled_energies(prog, batch, seed, first_sample=first)
             rows, signs2 = sampler.draw(batch, seed, first_sample=first)
             want = prog.energies(None, rows)
             assert torch.equal(signs, signs2), (kind, batch)
-            if batch >= 2048:                         # the two-step path runs the same thread-per-row arithmetic
+            if batch >= 2048 and kind != "dense":     # the two-step path runs the same thread-per-row arithmetic
                 assert torch.equal(values, want), (kind, batch, float((values - want).abs().max()))
+            elif batch >= 2048:                       # rows with more than 6 entries: local-memory list here, tile kernel there
+                assert float((values - want).abs().max()) < 1e-13
+                assert float((values == want).double().mean()) > 0.2          # the rows that fit the list are bit-identical
             else:                                     # ... and the warp-per-row kernel below 2048 rows: equal to rounding
                 assert float((values - want).abs().max()) < 1e-13
         ref_rows, ref_signs = P.sample_variants(qps, 64, 7)
@@ -144,6 +151,8 @@ def test_fused_draw_and_evaluate_is_bit_identical_to_the_two_step_path():
         assert np.array_equal(signs[:64].cpu().numpy(), ref_signs)
         for b in range(0, 64, 7):
             assert abs(float(values[b]) - oracle_energy(O.variant_ops(gates, n1, n2, ref_rows[b]), 4, ham)) < 1e-10, (kind, b)
+    # one launch when no drawable operation can need the general path, three (kernel, re-draw of the listed samples, tile kernel) otherwise
+    assert launches == {"pauli": 1, "rtype": 3, "dense": 1}
 
 
 def test_reference_shot_sampler_statistics():

@@ -1679,6 +1679,12 @@ struct Frame16qArgs {
     double* signs;
 };
 
+constexpr int F16Q_SPILL = 320;      // entries of the overflow list (local memory): one per slot of the largest plan taken without a worklist
+
+// DEFER = true: samples with a non-diagonal draw or more than F16V_MAXACT entries are listed for the general path.
+// DEFER = false (the host has checked that no drawable basis operation of the sampler is non-diagonal in this plan): nothing
+// is listed; the one-in-10^10 row with more than F16V_MAXACT non-identity draws continues in a local-memory list.
+template <bool DEFER>
 __global__ void __launch_bounds__(128, 7) dmx_frame16q_kernel(const __grid_constant__ Frame16qArgs q) {
     const Frame16vArgs& a = q.v;
     const int ng = (a.n_slots + 3) >> 2;
@@ -1699,7 +1705,8 @@ __global__ void __launch_bounds__(128, 7) dmx_frame16q_kernel(const __grid_const
     __syncthreads();
     if (!mine) return;
 
-    uint2* const mya = act + tid * F16V_MAXACT;
+    uint2* mya = act + tid * F16V_MAXACT;
+    uint2 spill[DEFER ? 1 : F16Q_SPILL];
     int cnt = 0;
     bool general = false;
     unsigned neg = 0u, zero = 0u;
@@ -1733,13 +1740,32 @@ __global__ void __launch_bounds__(128, 7) dmx_frame16q_kernel(const __grid_const
                     if (row[mid] > u) hi = mid; else lo = mid + 1;
                 }
                 sg = q.sgn[(size_t)s * q.stride + lo];
-                if (lo) f16v_add_entry(a.slots, smeta, (unsigned)s, (unsigned)lo, mya, cnt, general);
+                if (lo) {
+                    if (!DEFER && cnt == F16V_MAXACT && mya != spill) {          // the shared-memory list is full: continue in local memory
+                        for (int e = 0; e < F16V_MAXACT; ++e) spill[e] = mya[e];
+                        mya = spill;
+                    }
+                    if (!DEFER && mya == spill) {
+                        const int2 meta = smeta[s];
+                        if (meta.x >= 0) {
+                            if (!((a.slots[s].diag_ok[lo >> 5] >> (lo & 31)) & 1u)) general = true;
+                            else if (cnt < F16Q_SPILL) mya[cnt++] = make_uint2(((unsigned)meta.x << 12) | (unsigned)s, (unsigned)meta.y + (unsigned)lo);
+                            else general = true;
+                        }
+                    } else {
+                        f16v_add_entry(a.slots, smeta, (unsigned)s, (unsigned)lo, mya, cnt, general);
+                    }
+                }
             }
             neg ^= sg == 1u;
             zero |= sg == 2u;
         }
     }
     q.signs[b] = zero ? 0.0 : (neg ? -1.0 : 1.0);
+    if (!DEFER && general) {            // cannot happen with tables the host has checked; never pass a wrong number on silently
+        a.out[b] = __longlong_as_double(0x7ff8000000000000LL);
+        return;
+    }
     f16v_finish(a, skap, sew, mya, cnt, general, mine, b);
 }
 
@@ -1804,6 +1830,8 @@ struct dmx_qp_sampler {
     int n_slots = 0, stride = 0, device = -1, sm_count = 0;
     char* d = nullptr;
     size_t cb = 0, fb = 0, nb = 0, gb = 0, sb = 0, qb = 0;      // byte sizes of the sub-tables (each 16-byte aligned)
+    std::vector<uint32_t> drawable;                             // host: [n_slots][8] bit idx = the draw can return idx (non-zero weight, or
+                                                                // the last entry, whose cumulative value is forced to 1)
 };
 
 // ---------------------------------------------------------------------------------------------------------
@@ -3069,6 +3097,10 @@ int dmx_qp_sampler_create(int n_slots, const int32_t* n_choices, const double* q
             sg[(size_t)s * stride + i] = row[i] == 0.0 ? 2 : (row[i] < 0.0 ? 1 : 0);
         }
     }
+    std::vector<uint32_t> drawable((size_t)n_slots * 8, 0u);
+    for (int s = 0; s < n_slots; ++s)
+        for (int i = 0; i < n_choices[s]; ++i)
+            if (qp[(size_t)s * stride + i] != 0.0 || i == n_choices[s] - 1) drawable[(size_t)s * 8 + (i >> 5)] |= 1u << (i & 31);
     const int groups = (n_slots + 3) / 4;
     // identity thresholds: cdf[0] > (word + 0.5) / 2^32  <=>  word < ceil(cdf[0] * 2^32 - 0.5); both products are exact in double
     std::vector<unsigned long long> first((size_t)groups * 4, 1ull << 32);
@@ -3094,7 +3126,7 @@ int dmx_qp_sampler_create(int n_slots, const int32_t* n_choices, const double* q
         fast[(size_t)groups * 4 + g] = summary;
     }
     auto* sm = new dmx_qp_sampler();
-    sm->n_slots = n_slots; sm->stride = stride;
+    sm->n_slots = n_slots; sm->stride = stride; sm->drawable = drawable;
     // every sub-table starts 16-byte aligned (thr0 is read as ulonglong2)
     sm->cb = (cdf.size() * 8 + 15) & ~(size_t)15; sm->fb = first.size() * 8; sm->nb = ((size_t)n_slots * 4 + 15) & ~(size_t)15; sm->gb = (sg0.size() + 15) & ~(size_t)15; sm->qb = fast.size() * 4; sm->sb = ((sg.size() + 15) & ~(size_t)15);
     if (cudaGetDevice(&sm->device) != cudaSuccess || cudaDeviceGetAttribute(&sm->sm_count, cudaDevAttrMultiProcessorCount, sm->device) != cudaSuccess ||
@@ -3178,21 +3210,34 @@ int dmx_qp_sampled_energies(dmx_plan* plan, const dmx_qp_sampler* sm, uint64_t s
         if (rc) return rc;
         return energy_impl(plan, batch, nullptr, rows, d_energy, nullptr, 0, st);
     }
-    CUDA_TRY(cudaMallocAsync((void**)&wl, (size_t)(batch + 1) * sizeof(int), st));
-    release.b = wl;
-    CUDA_TRY(cudaMemsetAsync(wl, 0, sizeof(int), st));
+    // can a draw of this sampler be a non-diagonal basis operation of this plan (R-type / projector corrections)?
+    bool may_defer = p.n_slots > F16Q_SPILL;
+    for (int sl = 0; sl < p.n_slots && !may_defer; ++sl) {
+        if (p.slots[sl].seg < 0) continue;
+        for (int w = 0; w < 8; ++w) {
+            const uint32_t nonid = sm->drawable[(size_t)sl * 8 + w] & (w == 0 ? ~1u : ~0u);
+            if (nonid & ~p.slots[sl].diag_ok[w]) { may_defer = true; break; }
+        }
+    }
+    if (may_defer) {
+        CUDA_TRY(cudaMallocAsync((void**)&wl, (size_t)(batch + 1) * sizeof(int), st));
+        release.b = wl;
+        CUDA_TRY(cudaMemsetAsync(wl, 0, sizeof(int), st));
+    }
     Frame16qArgs q{};
     Frame16vArgs& f = q.v;
     f.nseg = p.nseg; f.n_slots = p.n_slots; f.batch = batch; f.kappa = reinterpret_cast<const double2*>(d->h_kap16);
     f.sweight = d->h_sw16; f.cstat = d->h_cstat; f.group = nullptr; f.variants = nullptr; f.slots = d->slots;
-    f.fac_row = d->h_facrow; f.fac = d->h_fac; f.out = d_energy; f.worklist = wl + 1; f.work_count = wl;
+    f.fac_row = d->h_facrow; f.fac = d->h_fac; f.out = d_energy; f.worklist = wl ? wl + 1 : nullptr; f.work_count = wl;
     for (int i = 0; i < 16; ++i) f.init[i] = p.f16_init[i];
     for (int k = 0; k < p.nseg; ++k) f.mask[k] = p.f16_mask[k];
     q.n_choices = n_choices; q.cdf = cdf; q.sgn = sgn; q.stride = sm->stride; q.thr0 = thr0; q.sgn0 = sgn0; q.thr32 = thr32; q.summ = summ;
     q.seed = seed; q.first_sample = first_sample; q.signs = d_signs;
-    dmx_frame16q_kernel<<<(unsigned)((batch + 127) / 128), 128, smem, st>>>(q);
+    if (may_defer) dmx_frame16q_kernel<true><<<(unsigned)((batch + 127) / 128), 128, smem, st>>>(q);
+    else dmx_frame16q_kernel<false><<<(unsigned)((batch + 127) / 128), 128, smem, st>>>(q);
     ++g_launches;
     CUDA_TRY(cudaGetLastError());
+    if (!may_defer) return DMX_OK;                    // one launch: nothing can need the general path
     // listed samples (a non-diagonal basis operation, or more entries than a thread keeps): drawn again, row i = list entry i,
     // and evaluated by the general tile path
     dmx_qp_sample_kernel<<<(unsigned)std::max(1, sm->sm_count), 256, 0, st>>>(p.n_slots, n_choices, cdf, sgn, sm->stride, thr0, sgn0, thr32, summ,
