@@ -1711,17 +1711,11 @@ __global__ void __launch_bounds__(128, 7) dmx_frame16q_kernel(const __grid_const
     bool general = false;
     unsigned neg = 0u, zero = 0u;
     const unsigned long long gidx = q.first_sample + (unsigned long long)b;
-#pragma unroll 1
-    for (int g = 0; g < ng; ++g) {
-        unsigned c[4] = {(unsigned)gidx, (unsigned)(gidx >> 32), (unsigned)g, 0u};
-        philox4x32_10(c, (unsigned)q.seed, (unsigned)(q.seed >> 32));
-        const uint4 t = sthr[g];
-        const unsigned sm = ssum[g];
-        if (c[0] <= t.x && c[1] <= t.y && c[2] <= t.z && c[3] <= t.w && !(sm & 4u)) {
-            neg ^= sm & 1u;
-            zero |= (sm >> 1) & 1u;
-            continue;
-        }
+    // a lane-group (four slots, one Philox call) that is not all-identity - 0.6 % of them at p = 1e-3 - needs a search of the
+    // cumulative tables in global memory: a chain of dependent loads.  Taken inside the loop, the warp's 32 samples would
+    // pay those chains one after the other; the loop only notes the group (up to four per sample, packed in a word) and
+    // the chains run after it, for all lanes that have one at the same time.
+    auto slow_group = [&](int g, const unsigned (&c)[4]) {
         const ulonglong2 fa = q.thr0[2 * g], fb = q.thr0[2 * g + 1];
         const unsigned long long first[4] = {fa.x, fa.y, fb.x, fb.y};
         const unsigned s0 = q.sgn0[g];
@@ -1760,6 +1754,31 @@ __global__ void __launch_bounds__(128, 7) dmx_frame16q_kernel(const __grid_const
             neg ^= sg == 1u;
             zero |= sg == 2u;
         }
+    };
+    unsigned pend = 0u;
+    int npend = 0;
+#pragma unroll 1
+    for (int g = 0; g < ng; ++g) {
+        unsigned c[4] = {(unsigned)gidx, (unsigned)(gidx >> 32), (unsigned)g, 0u};
+        philox4x32_10(c, (unsigned)q.seed, (unsigned)(q.seed >> 32));
+        const uint4 t = sthr[g];
+        const unsigned sm = ssum[g];
+        if (c[0] <= t.x && c[1] <= t.y && c[2] <= t.z && c[3] <= t.w && !(sm & 4u)) {
+            neg ^= sm & 1u;
+            zero |= (sm >> 1) & 1u;
+        } else if (npend < 4 && g < 256) {
+            pend |= (unsigned)g << (8 * npend);
+            ++npend;
+        } else {
+            slow_group(g, c);
+        }
+    }
+#pragma unroll 1
+    for (int e = 0; e < npend; ++e) {
+        const int g = (int)((pend >> (8 * e)) & 255u);
+        unsigned c[4] = {(unsigned)gidx, (unsigned)(gidx >> 32), (unsigned)g, 0u};
+        philox4x32_10(c, (unsigned)q.seed, (unsigned)(q.seed >> 32));
+        slow_group(g, c);
     }
     q.signs[b] = zero ? 0.0 : (neg ? -1.0 : 1.0);
     if (!DEFER && general) {            // cannot happen with tables the host has checked; never pass a wrong number on silently
@@ -1830,8 +1849,7 @@ struct dmx_qp_sampler {
     int n_slots = 0, stride = 0, device = -1, sm_count = 0;
     char* d = nullptr;
     size_t cb = 0, fb = 0, nb = 0, gb = 0, sb = 0, qb = 0;      // byte sizes of the sub-tables (each 16-byte aligned)
-    std::vector<uint32_t> drawable;                             // host: [n_slots][8] bit idx = the draw can return idx (non-zero weight, or
-                                                                // the last entry, whose cumulative value is forced to 1)
+    std::vector<uint32_t> drawable;                             // host: [n_slots][8] bit idx = some 32-bit word draws idx
 };
 
 // ---------------------------------------------------------------------------------------------------------
@@ -3097,10 +3115,18 @@ int dmx_qp_sampler_create(int n_slots, const int32_t* n_choices, const double* q
             sg[(size_t)s * stride + i] = row[i] == 0.0 ? 2 : (row[i] < 0.0 ? 1 : 0);
         }
     }
+    // idx is drawable iff some 32-bit word w has cdf[idx - 1] <= (w + 0.5) / 2^32 < cdf[idx]: the number of words below a
+    // cumulative value is ceil(cdf * 2^32 - 0.5) clamped to [0, 2^32] (the identity-threshold formula below)
     std::vector<uint32_t> drawable((size_t)n_slots * 8, 0u);
-    for (int s = 0; s < n_slots; ++s)
-        for (int i = 0; i < n_choices[s]; ++i)
-            if (qp[(size_t)s * stride + i] != 0.0 || i == n_choices[s] - 1) drawable[(size_t)s * 8 + (i >> 5)] |= 1u << (i & 31);
+    for (int s = 0; s < n_slots; ++s) {
+        unsigned long long below = 0ull;
+        for (int i = 0; i < n_choices[s]; ++i) {
+            const double x = cdf[(size_t)s * stride + i] * 4294967296.0 - 0.5;
+            const unsigned long long t = x <= 0.0 ? 0ull : (x >= 4294967296.0 ? 1ull << 32 : (unsigned long long)std::ceil(x));
+            if (t > below) drawable[(size_t)s * 8 + (i >> 5)] |= 1u << (i & 31);
+            below = std::max(below, t);
+        }
+    }
     const int groups = (n_slots + 3) / 4;
     // identity thresholds: cdf[0] > (word + 0.5) / 2^32  <=>  word < ceil(cdf[0] * 2^32 - 0.5); both products are exact in double
     std::vector<unsigned long long> first((size_t)groups * 4, 1ull << 32);
