@@ -829,7 +829,8 @@ def run_workload(wl, ctx, steps: int, warmup: int, with_cpu_baseline: bool, with
         samp_s = timed(sampled, steps)
         e2e["device_sampling"] = {"value": world * B * steps / samp_s, "unit": UNIT, "h2d_bytes_per_step": int(wl["qp_bytes"]),
                                   "d2h_bytes_per_step": 24,
-                                  "api": "IErrorMitigationManager.get_mu_effective_sampled (dmx_qp_sampler_draw + dmx_energy_batch + "
+                                  "api": "IErrorMitigationManager.get_mu_effective_sampled (dmx_qp_sampled_energies - draw + evaluate in one "
+                                         "kernel on register-resident plans, dmx_qp_sampler_draw + dmx_energy_batch otherwise - + "
                                          "dmx_qp_reduce + all-reduce of 3 doubles over NCCL when N > 1)",
                                   "estimate": [float(est[0][0]), float(est[0][1]), int(est[0][2])]}
 
