@@ -3229,9 +3229,10 @@ int dmx_qp_sampled_energies(dmx_plan* plan, const dmx_qp_sampler* sm, uint64_t s
     // scratch, stream-ordered: [count | sample list] and the identifier rows (all of them on the two-step path, the listed ones otherwise)
     int* wl = nullptr;
     uint8_t* rows = nullptr;
-    CUDA_TRY(cudaMallocAsync((void**)&rows, (size_t)batch * p.n_slots, st));
-    struct Release { void* a; void* b; cudaStream_t st; ~Release() { if (a) cudaFreeAsync(a, st); if (b) cudaFreeAsync(b, st); } } release{rows, nullptr, st};
+    struct Release { void* a; void* b; cudaStream_t st; ~Release() { if (a) cudaFreeAsync(a, st); if (b) cudaFreeAsync(b, st); } } release{nullptr, nullptr, st};
     if (!fused) {
+        CUDA_TRY(cudaMallocAsync((void**)&rows, (size_t)batch * p.n_slots, st));
+        release.a = rows;
         rc = dmx_qp_sampler_draw(sm, seed, first_sample, batch, rows, d_signs, stream);
         if (rc) return rc;
         return energy_impl(plan, batch, nullptr, rows, d_energy, nullptr, 0, st);
@@ -3246,6 +3247,8 @@ int dmx_qp_sampled_energies(dmx_plan* plan, const dmx_qp_sampler* sm, uint64_t s
         }
     }
     if (may_defer) {
+        CUDA_TRY(cudaMallocAsync((void**)&rows, (size_t)batch * p.n_slots, st));
+        release.a = rows;
         CUDA_TRY(cudaMallocAsync((void**)&wl, (size_t)(batch + 1) * sizeof(int), st));
         release.b = wl;
         CUDA_TRY(cudaMemsetAsync(wl, 0, sizeof(int), st));
