@@ -108,6 +108,19 @@ def test_round2_thread_per_circuit_record():
         assert d["also"][key]["parity_max_abs_err"] < 1e-10
 
 
+def test_round2_final_record_with_fused_estimator():
+    d, before = load("r2_bench_default_v8.json"), load("r2_bench_default_v7.json")
+    assert [k for k in BASE if k not in d] == [] and d["parity_max_abs_err"] < 1e-10
+    assert d["roofline"]["kernel"].startswith("dmx_frame16t_kernel") and d["value"] > 2.0e10 and d["e2e"]["value"] > 4.0e9
+    est, est0 = d["also"]["h2_qem"]["estimator"], before["also"]["h2_qem"]["estimator"]
+    assert est["value"] > 1.3 * est0["value"] and est["variants_per_estimate"] == 125000         # draw + evaluate in one kernel
+    assert "dmx_qp_sampled_energies" in d["also"]["h2_qem"]["e2e"]["device_sampling"]["api"]
+    for key in ("h2_qem", "hea10", "lih12", "h2_bonds", "swap7_qem"):
+        assert d["also"][key]["parity_max_abs_err"] < 1e-10
+    ref = load("r2_bench_reference_arm_v8.json")
+    assert ref["impl"] == "reference" and "libdmx.so is not loaded" in ref["native"] and ref["value"] < 1e5
+
+
 def test_round2_final_multi_gpu_records():
     for name, n in (("r2_bench_default_n2_v3.json", 2), ("r2_bench_default_n8_v4.json", 8)):
         d = load(name)
