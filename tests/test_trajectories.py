@@ -226,3 +226,20 @@ def test_qpsamp_measurement_dialect_matches_the_projector_matrices(backend):
     reps = 40000
     got = samp.postselected_expectation(row, reps, cirq.DensityMatrixSimulator(seed=9))
     assert abs(got - want) < 5 * np.sqrt(mat.sum() / reps)
+
+
+def test_wide_mid_circuit_measurement_is_split_into_groups(backend):
+    """Seven qubits measured at once in the middle of a circuit: more bits than one grouped batch evaluates
+    (trajectories.MAX_GROUP_BITS), so the sites are walked as two levels - the joint distribution must not notice."""
+    q = cirq.LineQubit.range(7)
+    ops = [cirq.ry(0.4 + 0.3 * i)(q[i]) for i in range(7)] + [cirq.CNOT(q[i], q[i + 1]) for i in range(0, 6, 2)]
+    ops += [cirq.measure(*q, key="all7"), cirq.H(q[0]), cirq.CNOT(q[0], q[6]), cirq.measure(q[0], q[6], key="end")]
+    circuit = cirq.Circuit(_noise(ops, 0.01))
+    tp = trajectories.TrajectoryProgram(circuit, q)
+    assert [len(g.sites) for g in tp.groups] == [trajectories.MAX_GROUP_BITS, 1] and len(tp.final_sites) == 2
+    n, oops = O.from_circuit(circuit, q)
+    want, _ = O.measurement_distribution(n, oops)
+    got = _engine_distribution(tp)
+    assert abs(sum(got.values()) - 1.0) < 1e-12
+    worst = max(abs(want.get(b, 0.0) - got.get(b, 0.0)) for b in set(want) | set(got))
+    assert worst < 1e-12, worst
