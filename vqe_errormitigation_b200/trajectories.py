@@ -45,9 +45,12 @@ class _Group:
 class TrajectoryProgram:
     """A resolved circuit with measurements anywhere, compiled for trajectory sampling."""
 
-    def __init__(self, circuit, qubit_order=None):
+    def __init__(self, circuit, qubit_order=None, _lowered=None):
         sites: list = []
-        builder, qubits, measurements, lifted, key = engine.lower_circuit(circuit, qubit_order, lift_numeric_rotations=True, sites=sites)
+        if _lowered is not None:            # program_for_circuit has lowered the circuit already (for the cache key)
+            builder, qubits, measurements, lifted, key, sites = _lowered
+        else:
+            builder, qubits, measurements, lifted, key = engine.lower_circuit(circuit, qubit_order, lift_numeric_rotations=True, sites=sites)
         keys = [m[0] for m in measurements]
         dup = sorted({k for k in keys if keys.count(k) > 1})
         if dup:
@@ -219,8 +222,8 @@ _CACHE_SIZE = 16
 def program_for_circuit(resolved, qubit_order=None) -> Tuple[TrajectoryProgram, Optional[np.ndarray]]:
     """Structure-keyed cache (like ``engine.program_for_circuit``): circuits that differ only in rotation angles share the
     compiled prefix programs.  Returns the program and this circuit's angle row."""
-    probe: list = []
-    _, qubits, _, lifted, key = engine.lower_circuit(resolved, qubit_order, lift_numeric_rotations=True, sites=probe)
+    sites: list = []
+    builder, qubits, measurements, lifted, key = engine.lower_circuit(resolved, qubit_order, lift_numeric_rotations=True, sites=sites)
     try:
         device = engine._require_cuda().cuda.current_device()
     except RuntimeError:
@@ -228,7 +231,7 @@ def program_for_circuit(resolved, qubit_order=None) -> Tuple[TrajectoryProgram, 
     full_key = (tuple(qubits), key, device)
     tp = _CACHE.get(full_key)
     if tp is None:
-        tp = TrajectoryProgram(resolved, qubit_order)
+        tp = TrajectoryProgram(resolved, qubit_order, _lowered=(builder, qubits, measurements, lifted, key, sites))
         _CACHE[full_key] = tp
         while len(_CACHE) > _CACHE_SIZE:
             _CACHE.popitem(last=False)
