@@ -402,3 +402,35 @@ def test_coefficient_groups_lowering():
     c = np.ones(1)
     assert lib.dmx_plan_set_hamiltonian_groups(h, 1, c.ctypes.data_as(C.POINTER(C.c_double))) == -5      # strings first (DMX_ERR_STATE)
     lib.dmx_plan_destroy(h)
+
+
+# ---- remaining cirq names of the reference's QPU (processor_quantum.py:48-56) ---------------------------------------------
+
+def test_simulator_and_sample_facades(monkeypatch):
+    """``cirq.Simulator`` / ``cirq.sample`` as ``QPU.get_trial_results`` / ``get_noisy_trial_result`` call them."""
+    oracle_backend.install(monkeypatch)
+    q = cirq.LineQubit.range(2)
+    body = [cirq.ry(1.1).on(q[0]), cirq.rx(0.4).on(q[1]), cirq.CNOT(q[0], q[1])]
+    # simulate: the state vector of the pure final state, up to the one global phase
+    psi = cirq.Simulator().simulate(cirq.Circuit(body)).state_vector()
+    rho = O.simulate(2, O.from_circuit(cirq.Circuit(body))[1])
+    assert np.allclose(np.outer(psi, psi.conj()), rho, atol=1e-12)
+    assert abs(np.imag(psi[np.argmax(abs(psi))])) < 1e-15
+    with pytest.raises(ValueError):
+        cirq.Simulator().simulate(cirq.Circuit(body + [cirq.depolarize(0.1).on(q[0])]))
+    # run / sample: terminal measurement records with the distribution of diag(rho)
+    measured = cirq.Circuit(body + [cirq.measure(q[0], q[1], key="m")])
+    np.random.seed(11)
+    res = QPU.get_trial_results(measured, None, 20000)
+    freq = np.array([res.histogram(key="m")[k] for k in range(4)]) / 20000
+    assert np.allclose(freq, np.real(np.diag(rho)), atol=4 * 0.5 / np.sqrt(20000))
+    model = INoiseModel([cirq.depolarize(0.2)], [TwoQubitDepolarizingChannel(0.2)], "d")
+    wrapper = INoiseWrapper(HydrogenAnsatz(), model)
+    noisy = QPU.get_noisy_trial_result(measured, None, 20000, noise_model=wrapper)
+    noisy_rho = O.simulate(2, O.from_circuit(cirq._with_noise(cirq.Circuit(body), wrapper))[1])
+    nfreq = np.array([noisy.histogram(key="m")[k] for k in range(4)]) / 20000
+    assert np.allclose(nfreq, np.real(np.diag(noisy_rho)), atol=4 * 0.5 / np.sqrt(20000))
+    assert not np.allclose(np.diag(noisy_rho), np.diag(rho), atol=0.02)       # the noise model did act
+    # module paths the reference's annotations spell out
+    assert cirq.circuits.circuit is cirq.Circuit and cirq.study.resolver is cirq.ParamResolver
+    assert cirq.ops.gate_features.SingleQubitGate is cirq.SingleQubitGate

@@ -1064,3 +1064,90 @@ class _Protocols:
 
 
 protocols = _Protocols()
+
+
+# --------------------------------------------------------------------------------------------------
+# remaining names the reference touches (processor_quantum.py:48-56, error_mitigation.py:743-791 and its type annotations)
+# --------------------------------------------------------------------------------------------------
+
+
+def _with_noise(program: Circuit, noise) -> Circuit:
+    """The circuit a ``NoiseModel`` turns ``program`` into: every non-measurement operation through ``noisy_operation``
+    (INoiseWrapper is the reference's NoiseModel, i_noise_wrapper.py:73-119)."""
+    if noise is None:
+        return program
+    noisy = Circuit()
+    for op in program.all_operations():
+        noisy.append(op if isinstance(op.gate, MeasurementGate) else noise.noisy_operation(op))
+    return noisy
+
+
+def sample(program: Circuit, *, noise=None, param_resolver=None, repetitions: int = 1, dtype=np.complex128) -> TrialResult:
+    """``cirq.sample`` (reference: ``QPU.get_noisy_trial_result``, processor_quantum.py:55-56): run ``program`` - with the
+    noise model applied when one is given - and return the sampled measurement records."""
+    return DensityMatrixSimulator(dtype=dtype).run(_with_noise(program, noise), param_resolver=param_resolver, repetitions=repetitions)
+
+
+class WaveFunctionTrialResult:
+    def __init__(self, final_state: np.ndarray, qubits: Sequence[Qid], params: ParamResolver, measurements: Dict[str, np.ndarray]):
+        self.final_state = final_state
+        self.qubits = list(qubits)
+        self.params = params
+        self.measurements = measurements
+
+    def state_vector(self) -> np.ndarray:
+        return self.final_state
+
+
+class Simulator:
+    """``cirq.Simulator`` (reference: ``QPU.get_trial_results``, processor_quantum.py:48-52).  The engine has one state
+    representation, so a noiseless run samples the density-matrix evolution (same distribution); ``simulate`` returns the state
+    vector of the pure final state with the global phase fixed by a real, positive largest amplitude (cirq keeps the phase the
+    gates accumulate: amplitudes agree up to that one factor).  Circuits with channels belong to DensityMatrixSimulator."""
+
+    def __init__(self, *, dtype=np.complex128, seed=None):
+        self._dtype = dtype
+        self._dm = DensityMatrixSimulator(dtype=np.complex128, seed=seed)
+
+    def run(self, program: Circuit, param_resolver=None, repetitions: int = 1) -> TrialResult:
+        return self._dm.run(program, param_resolver=param_resolver, repetitions=repetitions)
+
+    def simulate(self, program: Circuit, param_resolver=None, qubit_order=None, initial_state=None) -> WaveFunctionTrialResult:
+        res = self._dm.simulate(program, param_resolver=param_resolver, qubit_order=qubit_order, initial_state=initial_state)
+        rho = res.final_density_matrix
+        if abs(np.real(np.trace(rho @ rho)) - np.real(np.trace(rho)) ** 2) > 1e-9:
+            raise ValueError("cirq.Simulator: the final state is mixed (the circuit has channels) - use DensityMatrixSimulator")
+        k = int(np.argmax(np.real(np.diag(rho))))
+        psi = rho[:, k] / np.sqrt(np.real(rho[k, k]))
+        return WaveFunctionTrialResult(psi.astype(self._dtype), res.qubits, res.params, getattr(res, "measurements", {}))
+
+
+class CircuitDiagramInfo:
+    def __init__(self, wire_symbols, exponent=1, connected: bool = True):
+        self.wire_symbols = tuple(wire_symbols)
+        self.exponent = exponent
+        self.connected = connected
+
+
+class CircuitDiagramInfoArgs:
+    def __init__(self, known_qubits=None, known_qubit_count=None, use_unicode_characters: bool = True, precision=3, qubit_map=None):
+        self.known_qubits, self.known_qubit_count = known_qubits, known_qubit_count
+        self.use_unicode_characters, self.precision, self.qubit_map = use_unicode_characters, precision, qubit_map
+
+
+NOISE_MODEL_LIKE = object          # typing alias in cirq ('cirq.NOISE_MODEL_LIKE' appears in an annotation only)
+
+
+class _Namespace:
+    def __init__(self, **names):
+        self.__dict__.update(names)
+
+
+ops = _Namespace(gate_features=_Namespace(SingleQubitGate=SingleQubitGate, TwoQubitGate=TwoQubitGate, ThreeQubitGate=ThreeQubitGate),
+                 pauli_gates=_Namespace(X=X, Y=Y, Z=Z), identity=_Namespace(I=I),
+                 SingleQubitGate=SingleQubitGate, TwoQubitGate=TwoQubitGate, ThreeQubitGate=ThreeQubitGate, Gate=Gate,
+                 GateOperation=GateOperation, MeasurementGate=MeasurementGate, X=X, Y=Y, Z=Z, I=I, H=H, CNOT=CNOT)
+circuits = _Namespace(circuit=Circuit, Circuit=Circuit, Moment=Moment, InsertStrategy=InsertStrategy)
+study = _Namespace(resolver=ParamResolver, ParamResolver=ParamResolver, TrialResult=TrialResult)
+protocols.CircuitDiagramInfo = CircuitDiagramInfo
+protocols.CircuitDiagramInfoArgs = CircuitDiagramInfoArgs

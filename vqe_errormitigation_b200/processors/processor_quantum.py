@@ -63,18 +63,14 @@ class QPU:
 
     @staticmethod
     def get_trial_results(r_c: cirq.Circuit, r, max_iter: int):
-        """Reference :48-52 uses the pure-state cirq.Simulator; a noiseless density-matrix run samples the same
-        distribution."""
-        return cirq.DensityMatrixSimulator().run(program=r_c, param_resolver=r, repetitions=max_iter)
+        """Reference :48-52: ``cirq.Simulator().run`` (the facade samples the noiseless density-matrix evolution: same
+        distribution)."""
+        return cirq.Simulator().run(program=r_c, param_resolver=r, repetitions=max_iter)
 
     @staticmethod
     def get_noisy_trial_result(r_c: cirq.Circuit, r, max_iter: int, noise_model=None):
-        if noise_model is not None:
-            noisy = cirq.Circuit()
-            for op in r_c.all_operations():
-                noisy.append(op if isinstance(op.gate, cirq.MeasurementGate) else noise_model.noisy_operation(op))
-            r_c = noisy
-        return cirq.DensityMatrixSimulator().run(program=r_c, param_resolver=r, repetitions=max_iter)
+        """Reference :55-56: ``cirq.sample(program, noise, param_resolver, repetitions)``."""
+        return cirq.sample(program=r_c, noise=noise_model, param_resolver=r, repetitions=max_iter)
 
     @staticmethod
     def get_initial_state_circuit(w: IWaveFunction) -> cirq.Circuit:
