@@ -434,3 +434,77 @@ def test_simulator_and_sample_facades(monkeypatch):
     # module paths the reference's annotations spell out
     assert cirq.circuits.circuit is cirq.Circuit and cirq.study.resolver is cirq.ParamResolver
     assert cirq.ops.gate_features.SingleQubitGate is cirq.SingleQubitGate
+
+
+def test_error_mitigation_module_helpers(monkeypatch, capsys):
+    """Module-level names of src/error_mitigation.py that sit beside the manager (:585-744) and the diagram symbols."""
+    from vqe_errormitigation_b200.error_mitigation import (SingleQubitLeakageChannel, decomposition_time_test, get_hardcoded_noise,
+                                                           simulate_error_mitigation)
+    oracle_backend.install(monkeypatch)
+    # matrix-level noise wrappers: trace preserving, and equal to the channel of the same name applied to the gate matrix
+    g = cirq.unitary(cirq.rx(0.3))
+    dep = get_hardcoded_noise("depolar", 0.03)(g)
+    want = sum(p * (k @ g @ k.conj().T) for p, k in cirq.mixture(cirq.depolarize(0.03)))
+    assert np.allclose(dep, want, atol=1e-15)
+    g2 = cirq.unitary(cirq.CNOT)
+    dep2 = get_hardcoded_noise("depolar", 0.03)(g2)
+    want2 = sum(p * (k @ g2 @ k.conj().T) for p, k in cirq.mixture(TwoQubitDepolarizingChannel(0.03)))
+    assert np.allclose(dep2, want2, atol=1e-15)
+    z = np.diag([1.0, -1.0])
+    assert np.allclose(get_hardcoded_noise("dephase", 0.2)(g), 0.8 * g + 0.2 * z @ g @ z)
+    assert get_hardcoded_noise("default", 0.2)(g) is g
+    with pytest.raises(NotImplementedError):
+        get_hardcoded_noise("other", 0.1)
+    decomposition_time_test(cirq.unitary(cirq.H))
+    out = capsys.readouterr().out
+    assert "Sum of quasi-probabilities: 1.0" in out.replace("0.9999999999999", "1.0") and "difference: " in out
+    assert float(out.rsplit("difference: ", 1)[1]) < 1e-12
+    # four-way comparison on a 2-qubit circuit with an ndarray objective: mitigation moves the noisy value back to the ideal
+    q = cirq.LineQubit.range(2)
+    clean = cirq.Circuit([cirq.ry(0.9).on(q[0]), cirq.CNOT(q[0], q[1]), cirq.rx(0.4).on(q[1])])
+    model = INoiseModel([cirq.depolarize(0.02)], [TwoQubitDepolarizingChannel(0.02)], "d")
+    objective = np.kron(O.Z, O.Z) + 0.5 * np.kron(O.Z, O.I2)
+    np.random.seed(5)
+    mu_ideal, mu_noisy, mu_eff = simulate_error_mitigation(clean, model, 4000, "two qubits", objective)
+    rho = O.simulate(2, O.from_circuit(clean)[1])
+    assert abs(mu_ideal - O.energy_elementwise(rho, objective)) < 1e-12
+    assert abs(mu_noisy - mu_ideal) > 0.02 and abs(mu_eff - mu_ideal) < 0.35 * abs(mu_noisy - mu_ideal)
+    # diagram symbols
+    info = TwoQubitDepolarizingChannel(0.03)._circuit_diagram_info_(None)
+    assert info.wire_symbols == ("D(0.002)", "D(0.002)")
+    assert SingleQubitPauliChannel(0.1, 0.0, 0.0)._circuit_diagram_info_(None).wire_symbols == ("D(0.900)",)
+    assert SingleQubitLeakageChannel(0.25)._circuit_diagram_info_(None).wire_symbols == ("L(0.250)",)
+
+
+def test_gate_set_tomography_estimate(monkeypatch):
+    """``QP_QEM_lib.o_tilde_1q_tomo`` (:520-590): sampled entries against Tr(Q_j . G(rho_k)) for a unitary, a noisy unitary and a
+    post-selected projector tuple of ``basis_ops_sim``."""
+    from vqe_errormitigation_b200 import qp_qem_lib as L
+    oracle_backend.install(monkeypatch)
+    q = cirq.LineQubit(0)
+    reps = 20000
+    tol = 5 / np.sqrt(reps)
+    preps = [np.eye(2), O.X, cirq.unitary(cirq.ry(np.pi / 2)), cirq.unitary(cirq.rx(-np.pi / 2))]
+    rho0 = np.diag([1.0, 0.0]).astype(complex)
+    states = [u @ rho0 @ u.conj().T for u in preps]
+    paulis = [O.I2, O.X, O.Y, O.Z]
+
+    def exact(channel):
+        return np.array([[np.real(np.trace(pj @ channel(rk))) for rk in states] for pj in paulis])
+
+    np.random.seed(3)
+    u = cirq.unitary(cirq.rx(0.7))
+    got = L.o_tilde_1q_tomo(cirq.rx(0.7).on(q), reps, noisy=False, error=0.0)
+    assert np.allclose(got.real, exact(lambda r: u @ r @ u.conj().T), atol=tol) and np.all(got[0] == 1)
+
+    def dep(r, p=0.1):
+        return (1 - 4 * p / 3) * r + (4 * p / 3) * np.trace(r) * np.eye(2) / 2
+
+    got = L.o_tilde_1q_tomo(cirq.rx(0.7).on(q), reps, noisy=True, error=0.1)
+    assert np.allclose(got.real, exact(lambda r: dep(dep(u @ dep(r) @ u.conj().T))), atol=tol)
+    # pi_x-type entry of basis_ops_sim: (rx^3, measure 'M', rx) - post-selected on M = 0, unnormalised
+    ops = L.apply_to_qubit(L.basis_ops_sim()[11], q)
+    mats = [cirq.unitary(g) for g in L.basis_ops()[11]]
+    full = mats[2] @ mats[1] @ mats[0]
+    got = L.o_tilde_1q_tomo(ops, reps, noisy=False, error=0.0)
+    assert np.allclose(got.real, exact(lambda r: full @ r @ full.conj().T), atol=tol)

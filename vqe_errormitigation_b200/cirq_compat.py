@@ -59,6 +59,14 @@ class GridQubit(Qid):
     def is_adjacent(self, other) -> bool:
         return isinstance(other, GridQubit) and abs(self.row - other.row) + abs(self.col - other.col) == 1
 
+    @staticmethod
+    def rect(rows: int, cols: int, top: int = 0, left: int = 0) -> List["GridQubit"]:
+        return [GridQubit(r, c) for r in range(top, top + rows) for c in range(left, left + cols)]
+
+    @staticmethod
+    def square(diameter: int, top: int = 0, left: int = 0) -> List["GridQubit"]:
+        return GridQubit.rect(diameter, diameter, top, left)
+
     def __repr__(self):
         return f"cirq.GridQubit({self.row}, {self.col})"
 

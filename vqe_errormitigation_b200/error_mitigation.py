@@ -734,6 +734,91 @@ def reconstruct_from_basis(quasi_probabilities: List[float], basis_set: List[np.
     return sum(q * b for q, b in zip(quasi_probabilities, basis_set))
 
 
+def simulate_error_mitigation(clean_circuit: cirq.Circuit, noise_model: INoiseModel, process_circuit_count: int, desc: str,
+                              hamiltonian_objective: Union[np.ndarray, IWaveFunction, None] = None) -> Tuple[float, float, float]:
+    """The reference's four-way comparison (:585-655): {noiseless, noisy} x {plain, mitigated} estimates of one circuit,
+    returning (mu_ideal, mu_noisy, mu_effective).  The plain column is always read from the density matrix, the mitigated
+    one from measurements unless the objective is an ndarray (:604,628).  Each cell is one variant batch on the GPU.  The
+    2 x 2 histogram figure is drawn only when matplotlib is importable (the reference always draws; nothing here needs it)."""
+    density = isinstance(hamiltonian_objective, np.ndarray)
+    mu = {}
+    cells = {}
+    for i, noisy in enumerate((False, True)):
+        for j, mitigate in enumerate((False, True)):
+            manager = IErrorMitigationManager(clean_circuit=clean_circuit, noise_model=noise_model if noisy else INoiseModel.empty(),
+                                              hamiltonian_objective=hamiltonian_objective)
+            manager.set_identifier_range(process_circuit_count)
+            values, mu[i, j] = manager.get_mu_effective(error_mitigation=mitigate, density_representation=True if j == 0 else density,
+                                                        meas_reps=1)
+            cells[i, j] = (values, manager)
+    mu_ideal, mu_noisy, mu_effective = mu[0, 0], mu[1, 0], mu[1, 1]
+    try:
+        import matplotlib.pyplot as plt
+    except ImportError:
+        return mu_ideal, mu_noisy, mu_effective
+    fig, axs = plt.subplots(2, 2, tight_layout=True)
+    fig.suptitle(f'{desc} using {"density matrix" if density else "measurements"} (#mitigation circuits={process_circuit_count})', fontsize=16)
+    for (i, j), (values, manager) in cells.items():
+        axs[i][j].title.set_text(f"measurement histogram.\n(Info: {manager._noise_model.get_description()}, error mitigation={bool(j)})")
+        axs[i][j].set_xlabel("relative measurement")
+        axs[i][j].set_ylabel("Bin count")
+        axs[i][j].hist(values, bins=20)
+        if i:
+            axs[i][j].axvline(x=mu[i, j], linewidth=1, color="r", label=f"C E[mu_eff] = {np.round(mu[i, j], 5)}\n|eps| = {np.round(abs(mu[i, j] - mu_ideal), 5)}")
+        axs[i][j].axvline(x=mu_ideal, linewidth=1, color="g", label=f"mu_ideal = {np.round(mu_ideal, 5)}")
+        axs[i][j].legend()
+    return mu_ideal, mu_noisy, mu_effective
+
+
+def get_hardcoded_noise(name: str, p: float) -> Callable[[np.ndarray], np.ndarray]:
+    """Deprecated in the reference (:658-716), kept for callers: matrix-level noise G -> sum_k c_k P_k G P_k^dagger on a 2x2 or
+    4x4 gate matrix.  'depolar': (1 - 4p/3) + p/3 per Pauli incl. I (4x4: 1 - 16p/15, p/15 over the 16 products);
+    'dephase': (1 - p) + p Z G Z (4x4: (1 - p) + p/3 over IZ, ZI, ZZ); 'default': identity."""
+
+    def conjugated(gate: np.ndarray, head: float, terms) -> np.ndarray:
+        gate = np.asarray(gate)
+        out = head * gate.astype(complex)
+        for c, b in terms:
+            out = out + c * (b @ (gate @ b.conj().T))
+        return out
+
+    def depolarize(gate: np.ndarray) -> np.ndarray:
+        dim = np.asarray(gate).shape[0]
+        if dim not in (2, 4):
+            raise NotImplementedError
+        paulis = list(BasisUnitarySet.get_observable_set(dim=dim))
+        k = dim * dim
+        return conjugated(gate, 1 - p * k / (k - 1), [(p / (k - 1), b) for b in paulis])
+
+    def dephase(gate: np.ndarray) -> np.ndarray:
+        dim = np.asarray(gate).shape[0]
+        if dim == 2:
+            return conjugated(gate, 1 - p, [(p, _Z)])
+        if dim == 4:
+            return conjugated(gate, 1 - p, [(p / 3, np.kron(a, b)) for a, b in ((_I, _Z), (_Z, _I), (_Z, _Z))])
+        raise NotImplementedError
+
+    table = {"default": lambda gate: gate, "depolar": depolarize, "dephase": dephase}
+    if name not in table:
+        raise NotImplementedError(name)
+    return table[name]
+
+
+def decomposition_time_test(gate: np.ndarray):
+    """Times one quasi-probability decomposition and prints its reconstruction error (reference :728-738).  The reference
+    solves the 2x2 / 4x4 ``gate`` against the raw operation matrices - a non-square system - and then compares shapes that
+    differ; here the gate's Pauli-transfer matrix is decomposed in the PTM basis, the solve ``get_qp_lookup`` performs."""
+    import time
+    start = time.time()
+    target = BasisUnitarySet.pauli_transfer_matrix(gate=gate)
+    basis_set = list(BasisUnitarySet.get_ptm_basis_set(dim=gate.shape[0]))
+    qp = BasisUnitarySet.get_quasiprobabilities(target=target, basis_set=basis_set)
+    rebuilt = reconstruct_from_basis(qp, basis_set)
+    print(f"Calculation time: {time.time() - start} sec.")
+    print(f"Sum of quasi-probabilities: {sum(qp)}")
+    print(f"Target vs Reconst. difference: {get_matrix_difference(rebuilt, target)}")
+
+
 def get_matrix_difference(a: np.ndarray, b: np.ndarray) -> float:
     return float(np.linalg.norm(np.asarray(a) - np.asarray(b)))
 
@@ -769,6 +854,13 @@ class TwoQubitDepolarizingChannel(cirq.TwoQubitGate):
     def __str__(self) -> str:
         return f"two_qubit_depolarize(p={self._p!r})"
 
+    def _circuit_diagram_info_(self, args: "cirq.CircuitDiagramInfoArgs") -> "cirq.CircuitDiagramInfo":
+        return cirq.protocols.CircuitDiagramInfo(wire_symbols=("D({:.3f})".format(self._p),) * 2)
+
+    def _json_dict_(self) -> Dict[str, Any]:
+        """cirq's ``obj_to_dict_helper(self, ['p'])`` (QP_QEM_lib.py:134-135) with the stored per-term probability."""
+        return {"cirq_type": type(self).__name__, "p": self._p}
+
 
 class SingleQubitPauliChannel(cirq.SingleQubitGate):
     def __init__(self, p_x: float, p_y: float, p_z: float) -> None:
@@ -790,6 +882,9 @@ class SingleQubitPauliChannel(cirq.SingleQubitGate):
 
     def __str__(self) -> str:
         return f"single_qubit_asymmetry_depolarize(p_x={self._p_x}, p_y={self._p_y}, p_z={self._p_z})"
+
+    def _circuit_diagram_info_(self, args: "cirq.CircuitDiagramInfoArgs") -> "cirq.CircuitDiagramInfo":
+        return cirq.protocols.CircuitDiagramInfo(wire_symbols=("D({:.3f})".format(self._p_i),))
 
 
 class TwoQubitPauliChannel(cirq.TwoQubitGate):
@@ -819,6 +914,9 @@ class TwoQubitPauliChannel(cirq.TwoQubitGate):
     def __str__(self) -> str:
         return f"two_qubit_asymmetry_depolarize(p_x={self._p_x}, p_y={self._p_y}, p_z={self._p_z})"
 
+    def _circuit_diagram_info_(self, args: "cirq.CircuitDiagramInfoArgs") -> "cirq.CircuitDiagramInfo":
+        return cirq.protocols.CircuitDiagramInfo(wire_symbols=("D({:.3f})".format(self._p_i),) * 2)
+
 
 _P0 = np.array([[1, 0], [0, 0]], dtype=complex)
 _P1 = np.array([[0, 0], [0, 1]], dtype=complex)
@@ -845,6 +943,9 @@ class SingleQubitLeakageChannel(cirq.SingleQubitGate):
 
     __repr__ = __str__
 
+    def _circuit_diagram_info_(self, args: "cirq.CircuitDiagramInfoArgs") -> "cirq.CircuitDiagramInfo":
+        return cirq.protocols.CircuitDiagramInfo(wire_symbols=("L({:.3f})".format(self._p),))
+
 
 class TwoQubitLeakageChannel(cirq.TwoQubitGate):
     def __init__(self, p: float) -> None:
@@ -868,3 +969,6 @@ class TwoQubitLeakageChannel(cirq.TwoQubitGate):
         return f"two_qubit_leakage(p={self._p})"
 
     __repr__ = __str__
+
+    def _circuit_diagram_info_(self, args: "cirq.CircuitDiagramInfoArgs") -> "cirq.CircuitDiagramInfo":
+        return cirq.protocols.CircuitDiagramInfo(wire_symbols=("L({:.3f})".format(self._p),) * 2)

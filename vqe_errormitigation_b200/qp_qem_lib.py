@@ -235,6 +235,38 @@ def o_tilde_1q(gate, noisy, error_type, error):
     return _o_tilde(gate, 1, noisy, error_type, error)
 
 
+def o_tilde_1q_tomo(gate, repetitions, noisy, error, error_type="depolarize"):
+    """Gate-set-tomography estimate of a 1-qubit operation from sampled shots (QP_QEM_lib.py:520-590): entry [j][k] is the
+    expectation of Q_j in {I, X, Y, Z} after preparing k in {|0>, |1>, |+>, |+i>} (``tomo_ops``), applying ``gate`` and rotating
+    the measurement axis (``U_ops``); noise after the preparation and after the rotation, and after every gate of ``gate`` when
+    ``noisy``.  An operation holding a ``MeasurementGate`` keyed 'M' (``basis_ops_sim``) is post-selected on M = 0:
+    (N_0 - N_1) / repetitions, i.e. the unnormalised projector.  The reference body reads a module-level ``error_type`` that it
+    never defines (a NameError whenever ``noisy``); here it is a trailing keyword.  The 16 circuits go through
+    ``cirq.Simulator().run`` like the reference's - terminal-only ones as one evolution + shots, the post-selected ones as
+    outcome-tree trajectories (``trajectories.TrajectoryProgram``)."""
+    ops = list(gate) if isinstance(gate, (tuple, list)) else [gate]
+    qubit = ops[0].qubits[0]
+    noise = noise_model(dim=1, error_type=error_type if noisy else None, error=error)(qubit)
+    body = [(g, noise) for g in ops] if noisy else ops
+    tomo_ops = [cirq.I(qubit), cirq.X(qubit), cirq.ry(np.pi / 2)(qubit), cirq.rx(-np.pi / 2)(qubit)]
+    u_ops = [cirq.I(qubit), cirq.H(qubit), cirq.rx(np.pi / 2)(qubit), cirq.I(qubit)]
+    o_q = np.zeros((4, 4), dtype=complex)
+    for j, k in it.product(range(4), repeat=2):
+        circuit = cirq.Circuit(tomo_ops[k], noise, body, u_ops[j], noise)
+        postselected = circuit.has_measurements()
+        circuit.append(cirq.measure(qubit, key="M_post"))
+        result = cirq.Simulator().run(program=circuit, repetitions=repetitions)
+        if postselected:
+            hist = result.multi_measurement_histogram(keys=("M", "M_post"))
+            n_0, n_1 = hist[(0, 0)], hist[(0, 1)]
+            o_q[j][k] = (n_0 + n_1) / repetitions if j == 0 else (n_0 - n_1) / repetitions
+        elif j == 0:
+            o_q[j][k] = 1
+        else:
+            o_q[j][k] = 2 * result.histogram(key="M_post")[0] / repetitions - 1
+    return o_q
+
+
 def o_tilde_2q(gate, noisy, error_type, error):
     return _o_tilde(gate, 2, noisy, error_type, error)
 
