@@ -324,6 +324,11 @@ def test_remaining_experiment_loops_on_the_oracle_backend(monkeypatch, capsys):
     more = E.hydrogen_energy_spectrum(measure_count=1, identifier_count=1000, atomic_distance_list=[0.4, 1.0], previous=first, max_cpu_iter=6)
     assert [len(v) for v in more[0]] == [2, 2] and more[0][0][0] == first[0][0][0]          # resumed run extends the stored lists
     assert abs(more[3][1] - h2_golden()["molecules"]["1.0"]["fci_energy"]) < 1e-12
+    errors, fit = E.sampling_noise_scaling(shot_list=[20, 2000], reps=3, prob=1e-4, max_iter=60)
+    assert list(errors) == [20, 2000] and errors[2000] < errors[20] < 1.0 and fit is not None and fit[0] < 0
+    q = cirq.LineQubit.range(2)
+    rho = E.simulate_density_matrix(cirq.Circuit([cirq.H(q[0]), cirq.measure(q[0], key="a"), cirq.CNOT(q[0], q[1])]))
+    assert np.allclose(rho, np.diag([0.5, 0, 0, 0.5]), atol=1e-12)          # measurement = dephasing: no coherence survives
     capsys.readouterr()
 
 

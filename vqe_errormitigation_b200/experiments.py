@@ -31,6 +31,40 @@ def asymmetric_pauli_noise_model(prob: float) -> INoiseModel:
     return INoiseModel(noise_gates_1q=channel_1q, noise_gates_2q=channel_2q, description=f'asymmetric depolarization (p_tot={16 * prob})')
 
 
+def simulate_density_matrix(circuit: cirq.Circuit) -> np.ndarray:
+    """Final density matrix with measurements treated as dephasing (visual_testing.py:109-112)."""
+    return cirq.DensityMatrixSimulator(ignore_measurement_results=True).simulate(program=circuit).final_density_matrix
+
+
+def sampling_noise_scaling(shot_list: Optional[Sequence[int]] = None, reps: int = 10, prob: float = 1e-4, max_iter: int = 1000):
+    """``sampling_noise_scaling`` (visual_testing.py:334-387): error of the QP-mitigated Tr(rho H) of the optimised H2 ansatz
+    against the number of sampled circuits.  Returns ({count: mean |estimate - optimum| over ``reps``}, (slope, intercept) of
+    the reference's linear fit of the error over log10(count), or None when the fit fails).  Every estimate is one
+    variant batch; the reference omits ``meas_reps`` in its call (a TypeError as shipped) - 1 here, unused on the density path."""
+    from .main import get_log_experiment
+    ansatz = HydrogenAnsatz()
+    noise_model = asymmetric_pauli_noise_model(prob)
+    circuit = INoiseWrapper(ansatz, noise_model).get_clean_circuit()
+    result = CPU.get_optimized_state(w=ansatz, max_iter=max_iter)
+    parameters = ansatz.operator_parameters
+    parameters.update(v=result.optimal_parameters)
+    resolved_circuit = QPU.get_resolved_circuit(circuit, parameters)
+    observable = QPU.get_hamiltonian_objective_operator(ansatz)
+    observable = observable.toarray() if hasattr(observable, "toarray") else np.asarray(observable)
+
+    def experiment(process_circuit_count: int) -> float:
+        return CPU.get_mitigated_expectation(clean_circuit=resolved_circuit, noise_model=noise_model, process_circuit_count=process_circuit_count,
+                                             hamiltonian_objective=observable, meas_reps=1)
+
+    shot_list = [int(shot) for shot in np.logspace(1, 4, 10)] if shot_list is None else [int(shot) for shot in shot_list]
+    errors = get_log_experiment(shot_list=shot_list, expectation=result.optimal_value, experiment=experiment, reps=reps)
+    try:
+        fit = tuple(float(c) for c in np.polyfit(np.log10(np.array(shot_list)), np.array(list(errors.values())), 1))
+    except (np.linalg.LinAlgError, TypeError):
+        fit = None
+    return errors, fit
+
+
 def similarity_swap_circuit(prob: float = 1e-4, measure_count: int = 100, identifier_count: int = 1000,
                             density_representation: bool = False) -> ISimilarityCollection:
     """``similarity_plot_swap_circuit(overwrite=True)`` (visual_testing.py:492-524): 3+3-qubit SWAP test,
