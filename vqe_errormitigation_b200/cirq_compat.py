@@ -1081,7 +1081,10 @@ protocols = _Protocols()
 
 def _with_noise(program: Circuit, noise) -> Circuit:
     """The circuit a ``NoiseModel`` turns ``program`` into: every non-measurement operation through ``noisy_operation``
-    (INoiseWrapper is the reference's NoiseModel, i_noise_wrapper.py:73-119)."""
+    (INoiseWrapper is the reference's NoiseModel, i_noise_wrapper.py:73-119).  Measurements stay as they are so that terminal
+    ones remain terminal; cirq 0.8.2's default ``noisy_moment`` hands measurement operations to ``noisy_operation`` too (from
+    memory - cirq is not installable here), which would append a channel behind the read-out.  The reference never calls the
+    two legacy helpers that reach this (``QPU.get_noisy_trial_result`` has no caller), so the difference is unpinned."""
     if noise is None:
         return program
     noisy = Circuit()
