@@ -192,3 +192,64 @@ def test_swap_test_noisy_value_matches_reference_stored_run():
     assert abs(z0 - rec["mean"]) < standard_error          # 0.456024 vs 0.456066 +- 0.00085
     ideal = O.probabilities(O.simulate(n, gates))
     assert abs(float(ideal[:64].sum() - ideal[64:].sum()) - 0.5) < 1e-13
+
+
+def _embed(n, qubits, m):
+    """Full 2^n x 2^n matrix of a k-qubit operator on ``qubits`` (qubit 0 = most significant bit), element by element: an
+    index-arithmetic construction that shares nothing with the oracle's tensordot / moveaxis path."""
+    k, dim = len(qubits), 1 << n
+    shifts = [n - 1 - q for q in qubits]
+    clear = dim - 1
+    for s in shifts:
+        clear &= ~(1 << s)
+    full = np.zeros((dim, dim), dtype=complex)
+    for col in range(dim):
+        sub_c = sum(((col >> s) & 1) << (k - 1 - i) for i, s in enumerate(shifts))
+        for sub_r in range(1 << k):
+            if m[sub_r, sub_c] == 0:
+                continue
+            row = col & clear
+            for i, s in enumerate(shifts):
+                row |= ((sub_r >> (k - 1 - i)) & 1) << s
+            full[row, col] = m[sub_r, sub_c]
+    return full
+
+
+def test_noisy_energies_by_an_independent_liouville_restatement():
+    """Third arithmetic path for the noisy values no reference fixture pins: the whole circuit as ONE 256 x 256
+    superoperator S = prod_ops sum_k K (x) conj(K) acting on the row-major vec(rho) - no per-op density-matrix update at all -
+    against the per-op oracle, the stored golden energies and SURVEY App. A.4's values."""
+    ham = O.pauli_terms_to_matrix(4, *h2_terms())
+    cases = [((O.depolarize(1e-3),), (O.two_qubit_depolarize(1e-3),), ALPHA_STAR, -1.0559477031919418),
+             ((O.depolarize(1e-3),), (O.two_qubit_depolarize(1e-3),), 0.0, -1.0380841518615922),
+             ((O.bit_flip(1e-3), O.depolarize(1e-3)), (O.two_qubit_depolarize(1e-3),), ALPHA_STAR, None),
+             ((O.amplitude_damp(0.01),), (O.two_qubit_pauli_channel(1e-4, 1e-4, 6e-4),), 0.3, None)]
+    for n1, n2, alpha, known in cases:
+        ops = h2_ops(list(n1), list(n2), alpha=alpha)
+        total = np.eye(256, dtype=complex)
+        for kind, qubits, payload in ops:
+            kraus = [payload] if kind == "u" else payload
+            step = sum(np.kron(f, f.conj()) for f in (_embed(4, qubits, np.asarray(kr, complex)) for kr in kraus))
+            total = step @ total
+        vec0 = np.zeros(256, dtype=complex)
+        vec0[0] = 1.0
+        rho = (total @ vec0).reshape(16, 16)
+        ref = O.simulate(4, ops)
+        assert np.max(np.abs(rho - ref)) < 1e-13
+        energy = float(np.real(np.trace(rho @ ham)))
+        assert abs(energy - O.energy_sparse(ref, ham)) < 1e-12
+        if known is not None:
+            assert abs(energy - known) < 1e-12
+    # a quasi-probability variant row with every kind of basis operation (Pauli, R-type, projector; 1- and 2-qubit)
+    rng = np.random.default_rng(11)
+    gates = O.h2_gate_list(ALPHA_STAR)
+    identifier = [int(rng.integers(0, 16 if len(q) == 1 else 256)) if rng.random() < 0.15 else 0 for _, q, _ in gates]
+    assert sum(1 for i in identifier if i) >= 10
+    ops = O.variant_ops(gates, [O.depolarize(1e-3)], [O.two_qubit_depolarize(1e-3)], identifier)
+    vec = np.zeros(256, dtype=complex)
+    vec[0] = 1.0
+    for kind, qubits, payload in ops:
+        kraus = [payload] if kind == "u" else payload
+        vec = sum(np.kron(f, f.conj()) for f in (_embed(4, qubits, np.asarray(kr, complex)) for kr in kraus)) @ vec
+    ref = O.simulate(4, ops)
+    assert np.max(np.abs(vec.reshape(16, 16) - ref)) < 1e-13 * max(1.0, np.max(np.abs(ref)))
