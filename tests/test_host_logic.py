@@ -447,3 +447,35 @@ def test_error_mitigation_module_helpers(monkeypatch, capsys):
     assert info.wire_symbols == ("D(0.002)", "D(0.002)")
     assert SingleQubitPauliChannel(0.1, 0.0, 0.0)._circuit_diagram_info_(None).wire_symbols == ("D(0.900)",)
     assert SingleQubitLeakageChannel(0.25)._circuit_diagram_info_(None).wire_symbols == ("L(0.250)",)
+
+
+def test_lockstep_restarts_keep_the_sampled_cobyla_semantics(monkeypatch, capsys):
+    """``get_collection_ground_states(..., lockstep=True)``: the cpu_iter restarts of a noisy wave function as lock-step COBYLA
+    chains on the batched ``measure_observable`` objective - same start point, own shots per chain, values distributed like the
+    serial loop's (reference processor_classic.py:18-44)."""
+    oracle_backend.install(monkeypatch)
+    model = INoiseModel([cirq.depolarize(1e-3)], [TwoQubitDepolarizingChannel(1e-3)], "d")
+    n_w = INoiseWrapper(HydrogenAnsatz(), model)
+    program = n_w.sampled_energy_program()
+    assert program.prog.param_names == ["alpha0"] and program.variant_rows.shape == (5, 4)
+    np.random.seed(7)
+    funs, xs = CPU.get_custom_optimized_states_lockstep(n_w, restarts=6, max_cpu_iter=12, max_qpu_iter=20000)
+    assert funs.shape == (6,) and xs.shape == (6, 1) and len(set(funs.tolist())) == 6          # independent shots per chain
+    assert n_w.operator_parameters["alpha0"] == 0.0                                            # the shared table is untouched
+    np.random.seed(7)
+    again, _ = CPU.get_custom_optimized_states_lockstep(n_w, restarts=6, max_cpu_iter=12, max_qpu_iter=20000)
+    assert np.array_equal(funs, again)                                                         # np.random.seed fixes the run
+    serial = np.array([CPU.get_custom_optimized_state(INoiseWrapper(HydrogenAnsatz(), model), max_cpu_iter=12, max_qpu_iter=20000)[0]
+                       for _ in range(6)])
+    exact = -1.0559477031919418             # Tr(rho H) at alpha*: the sampled optimum scatters around it (shot noise ~ 0.6 / sqrt(shots))
+    assert abs(funs.mean() - exact) < 0.02 and abs(serial.mean() - exact) < 0.02
+    assert 0.25 < (funs.std() + 1e-4) / (serial.std() + 1e-4) < 4.0
+    assert np.all(np.abs(xs[:, 0] - ALPHA_STAR) < 0.3)
+    # through the collection driver: one container per (noise model, bond length) with cpu_iter values each
+    collection = IMeasurementCollection(w=HydrogenAnsatz(), p_space=[0.7, 0.8], n_space=[model])
+    containers = CPU.get_collection_ground_states(collection, cpu_iter=3, qpu_iter=4000, lockstep=True)
+    assert len(containers) == 2 and all(len(c._optimized_exp_values) == 3 for c in containers)
+    for c, r in zip(containers, ("0.7", "0.8")):
+        assert all(abs(v - h2_golden()["molecules"][r]["fci_energy"]) < 0.15 for v in c._optimized_exp_values)
+        assert abs(c.fci_value - h2_golden()["molecules"][r]["fci_energy"]) < 1e-12
+    assert capsys.readouterr().out.count("par: ") == 6

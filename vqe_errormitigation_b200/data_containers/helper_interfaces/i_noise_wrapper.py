@@ -81,6 +81,11 @@ class INoiseWrapper(IWaveFunction, cirq.NoiseModel):
     def observable_measurement(self):
         return self._ideal_wave_function.observable_measurement()
 
+    def sampled_energy_program(self, circuit: cirq.Circuit = None, noise_wrapper=None):
+        """Batched sampled-energy program of the wrapped ansatz on the noisy circuit (symbols kept) under this wrapper's noise."""
+        return self._ideal_wave_function.sampled_energy_program(self.get_noisy_circuit() if circuit is None else circuit,
+                                                                self._noise_channel if noise_wrapper is None else noise_wrapper)
+
     def _generate_qubits(self) -> Sequence[cirq.Qid]:
         return self._ideal_wave_function._generate_qubits()
 

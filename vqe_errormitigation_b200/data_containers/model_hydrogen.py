@@ -67,6 +67,13 @@ class HydrogenAnsatz(IGeneralizedUCCSD):
 
         return measure_observable, 5
 
+    def sampled_energy_program(self, circuit: cirq.Circuit, noise_wrapper: Callable) -> "SampledEnergyProgram":
+        """The batched form of the objective ``observable_measurement`` returns: ``circuit`` may keep its symbols, the
+        program's ``energies(params[B, P], meas_reps, seed)`` then samples every parameter row's five measurement circuits
+        in one launch (``CPU.get_custom_optimized_states_lockstep``)."""
+        hamiltonian = jordan_wigner(self.molecule.get_molecular_hamiltonian())
+        return SampledEnergyProgram(circuit, self.qubits, hamiltonian, noise_wrapper, IGeneralizedUCCSD.pauli_basis_map())
+
 
 class SampledEnergyProgram:
     """``measure_observable`` (reference model_hydrogen.py:114-175) as a batched device program.

@@ -35,11 +35,21 @@ class OptimizationTrialResult:
 
 class CPU:
     @staticmethod
-    def get_collection_ground_states(collection: IMeasurementCollection, cpu_iter: int, qpu_iter: int) -> List[IContainer]:
-        """noise models x bond lengths x ``cpu_iter`` restarts (reference :18-44)."""
+    def get_collection_ground_states(collection: IMeasurementCollection, cpu_iter: int, qpu_iter: int, lockstep: bool = False) -> List[IContainer]:
+        """noise models x bond lengths x ``cpu_iter`` restarts (reference :18-44).  ``lockstep=True`` (not in the reference)
+        keeps the objective and the optimiser - shot-based ``measure_observable``, scipy COBYLA, ``cpu_iter`` iterations from
+        the ansatz's current parameters - and advances the ``cpu_iter`` restarts of a noisy wave function together
+        (:meth:`get_custom_optimized_states_lockstep`): one launch per optimiser round instead of one per restart and round."""
         result = []
         for wave_function, description in collection.get_wave_functions():
             values = []
+            if lockstep and isinstance(wave_function, INoiseWrapper) and hasattr(wave_function._ideal_wave_function, "sampled_energy_program"):
+                funs, pars = CPU.get_custom_optimized_states_lockstep(wave_function, restarts=cpu_iter, max_cpu_iter=cpu_iter, max_qpu_iter=qpu_iter)
+                for value, par in zip(funs, pars):
+                    print(f"par: {par}, val: {value}")
+                result.append(IContainer(m_param=wave_function.molecule_parameters, e_values=[float(v) for v in funs],
+                                         m_data=wave_function.molecule, label=description))
+                continue
             for _ in range(cpu_iter):
                 if isinstance(wave_function, INoiseWrapper):
                     value, par = CPU.get_custom_optimized_state(n_w=copy.deepcopy(wave_function), max_cpu_iter=cpu_iter, max_qpu_iter=qpu_iter)
@@ -88,6 +98,29 @@ class CPU:
         x0 = np.fromiter(operator_params.dict.values(), dtype=float)
         res = optimize.minimize(fun=optimize_func, x0=x0, method="COBYLA", options={"maxiter": max_cpu_iter}, tol=1e-6)
         return res.fun, res.x
+
+    @staticmethod
+    def get_custom_optimized_states_lockstep(n_w: INoiseWrapper, restarts: int, max_cpu_iter: int, max_qpu_iter: int) -> Tuple[np.ndarray, np.ndarray]:
+        """``restarts`` independent runs of :meth:`get_custom_optimized_state` (reference :52-92) - the loop body of
+        ``get_collection_ground_states`` :34-38 - advanced in lock-step.  Every run is scipy's own COBYLA on the sampled
+        ``measure_observable`` objective from the same start point (the ansatz's current parameters; the reference deep-copies
+        the wave function per restart), with its own shots: parameter row b, measurement circuit m draws from Philox stream
+        b * 5 + m of a seed taken from numpy's global RNG per round, so ``np.random.seed`` still fixes the whole run.  One
+        optimiser round of all runs = one launch of 5 * restarts circuits + one shot kernel
+        (``SampledEnergyProgram.energies(params[B, P])``).  The shared parameter table is left untouched (the serial path
+        leaves the last evaluated point in it).  Returns (fun[restarts], x[restarts, P])."""
+        program = n_w.sampled_energy_program()
+        names = list(n_w.operator_parameters)
+        cols = [names.index(nm) for nm in program.prog.param_names]
+
+        def batch_objective(xs: np.ndarray) -> np.ndarray:
+            seed = int(np.random.randint(0, 2 ** 31 - 1))
+            if not cols:               # a circuit without symbols: one sampled value serves every (identical) request
+                return np.repeat(program.energies(None, max_qpu_iter, seed), len(xs))
+            return program.energies(np.ascontiguousarray(xs[:, cols]), max_qpu_iter, seed)
+
+        x0 = np.fromiter(n_w.operator_parameters.dict.values(), dtype=float)
+        return lockstep_minimize(batch_objective, np.tile(x0, (int(restarts), 1)), max_cpu_iter, tol=1e-6)
 
     @staticmethod
     def get_mitigated_optimized_state(w: IWaveFunction, n: INoiseModel, max_optimization_iter: int, max_mitigation_count: int) -> float:
