@@ -118,7 +118,8 @@ def hamiltonian_density_vs_measure(prob_list: Optional[Sequence[float]] = None, 
     """``hamiltonian_density_vs_measure`` (visual_testing.py:402-447): the deterministic Tr(rho H) of the noisy optimised
     ansatz against ``count`` shot-based ``measure_observable`` energies per (noise level, shots).  Returns
     (error[i, j] = |Tr(rho H) - mean|, spread[i, j] = std, prob_list, meas_reps); the reference's Pool(6) over the
-    ``count`` repetitions (:438-439) is a plain loop here — every repetition is five GPU evolutions."""
+    ``count`` repetitions (:438-439) becomes one batch per (noise level, shots): ``count`` parameter rows x five measurement circuits
+    in one launch, shots drawn on the device (``SampledEnergyProgram.energies``)."""
     ansatz = HydrogenAnsatz()
     result = CPU.get_optimized_state(w=ansatz, max_iter=max_iter)
     parameters = ansatz.operator_parameters
@@ -133,9 +134,17 @@ def hamiltonian_density_vs_measure(prob_list: Optional[Sequence[float]] = None, 
         noisy_ansatz = INoiseWrapper(ansatz, noise_model)
         circuit = noisy_ansatz.get_noisy_circuit()
         exp_fidelity = QPU.get_simulated_noisy_expectation_value(w=noisy_ansatz, r_c=circuit, r=parameters.get_resolved())
-        resolved_circuit = QPU.get_resolved_circuit(circuit, parameters)
+        program = noisy_ansatz.sampled_energy_program(circuit)
+        names = list(parameters)
+        row = np.array([[parameters[nm] for nm in program.prog.param_names]], dtype=float) if program.prog.param_names else None
+        assert row is None or set(program.prog.param_names) <= set(names)
         for j, meas in enumerate(meas_reps):
-            exp_measure = np.array([observable_process(resolved_circuit, noise_model.get_operators, meas) for _ in range(count)])
+            # the ``count`` repetitions are rows of one batch (own Philox streams), not ``count`` calls of observable_process
+            seed = int(np.random.randint(0, 2 ** 31 - 1))
+            if row is None:
+                exp_measure = np.array([observable_process(circuit, noise_model.get_operators, meas) for _ in range(count)])
+            else:
+                exp_measure = program.energies(np.repeat(row, count, axis=0), meas, seed)
             error_list[i][j] = abs(exp_fidelity - np.mean(exp_measure))
             error_var_list[i][j] = abs(np.std(exp_measure))
     return error_list, error_var_list, prob_list, meas_reps
@@ -151,9 +160,11 @@ def circuit_parameter_optimization(prob_list: Optional[Sequence[float]] = None, 
     exp_list, opt_list = [], []
     for prob in prob_list:
         noisy_ansatz = INoiseWrapper(w_class=ansatz, noise_model=asymmetric_pauli_noise_model(float(prob)))
-        results = [CPU.get_custom_optimized_state(n_w=noisy_ansatz, max_cpu_iter=max_cpu_iter, max_qpu_iter=max_qpu_iter) for _ in range(count)]
-        exp_list.append([value for value, _params in results])
-        opt_list.append([params[0] for _value, params in results])
+        # the reference maps the runs over Pool(6) workers, each with its own pickled copy of the wrapper: ``count`` independent
+        # COBYLA runs from the same start point - here lock-step chains, one launch per optimiser round
+        values, params = CPU.get_custom_optimized_states_lockstep(noisy_ansatz, restarts=count, max_cpu_iter=max_cpu_iter, max_qpu_iter=max_qpu_iter)
+        exp_list.append([float(v) for v in values])
+        opt_list.append([float(x[0]) for x in params])
     return exp_list, opt_list, prob_list
 
 
