@@ -181,6 +181,27 @@ def raw_and_mitigated(n_w: INoiseWrapper, noise_model: INoiseModel, max_qpu_iter
     return exp_noisy_value, exp_mitig_value
 
 
+def raw_and_mitigated_repeated(n_w: INoiseWrapper, noise_model: INoiseModel, repetitions: int, max_qpu_iter: int, max_cpu_iter: int = 10):
+    """``repetitions`` x :func:`raw_and_mitigated` the way the reference runs them - ``Pool(6).map`` over pickled copies of one
+    ``RawAndMitigatedClass`` (visual_testing.py:800-801,887-888), i.e. every repetition starts from the parent's parameters and
+    the parent's ansatz is never modified.  The noisy optimisations advance in lock-step (one launch per COBYLA round); each
+    optimum then gets its QP-mitigated estimate.  Returns [(noisy, mitigated)] * repetitions."""
+    ansatz_parameters = n_w.operator_parameters
+    start = dict(ansatz_parameters.dict)
+    values, params = CPU.get_custom_optimized_states_lockstep(n_w, restarts=repetitions, max_cpu_iter=max_cpu_iter, max_qpu_iter=max_qpu_iter)
+    results = []
+    try:
+        for exp_noisy_value, opt_params in zip(values, params):
+            ansatz_parameters.update(v=opt_params)
+            circuit_noisy_param = QPU.get_resolved_circuit(c=n_w.get_clean_circuit(), p=ansatz_parameters)
+            manager = IErrorMitigationManager(clean_circuit=circuit_noisy_param, noise_model=noise_model, hamiltonian_objective=n_w)
+            manager.set_identifier_range(max_qpu_iter)
+            results.append((float(exp_noisy_value), manager.get_mu_effective(error_mitigation=True, density_representation=False, meas_reps=1)[1]))
+    finally:
+        ansatz_parameters.dict.update(start)
+    return results
+
+
 def full_raw_vs_mitigation_per_noise(measure_count: int, identifier_count: int, prob_list: Optional[Sequence[float]] = None,
                                      max_cpu_iter: int = 10):
     """``full_raw_vs_mitigation_per_noise(overwrite=True)`` (visual_testing.py:778-812): per noise level ``measure_count``
@@ -191,7 +212,7 @@ def full_raw_vs_mitigation_per_noise(measure_count: int, identifier_count: int, 
     for prob in prob_list:
         noise_model = asymmetric_pauli_noise_model(float(prob))
         noisy_ansatz = INoiseWrapper(w_class=ansatz, noise_model=noise_model)
-        results = [raw_and_mitigated(noisy_ansatz, noise_model, identifier_count, max_cpu_iter) for _ in range(measure_count)]
+        results = raw_and_mitigated_repeated(noisy_ansatz, noise_model, measure_count, identifier_count, max_cpu_iter)
         exp_noisy_list.append([noisy for noisy, _ in results])
         exp_mitig_list.append([mitigated for _, mitigated in results])
     return exp_noisy_list, exp_mitig_list, prob_list
@@ -212,7 +233,7 @@ def hydrogen_energy_spectrum(measure_count: int, identifier_count: int, atomic_d
     for i, atomic_distance in enumerate(atomic_distance_list):
         ansatz = HydrogenAnsatz(mol_param=round(float(atomic_distance), 2))
         noisy_ansatz = INoiseWrapper(w_class=ansatz, noise_model=noise_model)
-        results = [raw_and_mitigated(noisy_ansatz, noise_model, identifier_count, max_cpu_iter) for _ in range(measure_count)]
+        results = raw_and_mitigated_repeated(noisy_ansatz, noise_model, measure_count, identifier_count, max_cpu_iter)
         exp_noisy_list[i].extend(noisy for noisy, _ in results)
         exp_mitig_list[i].extend(mitigated for _, mitigated in results)
         fci_energy.append(float(ansatz.molecule.fci_energy))
