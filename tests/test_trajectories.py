@@ -243,3 +243,32 @@ def test_wide_mid_circuit_measurement_is_split_into_groups(backend):
     assert abs(sum(got.values()) - 1.0) < 1e-12
     worst = max(abs(want.get(b, 0.0) - got.get(b, 0.0)) for b in set(want) | set(got))
     assert worst < 1e-12, worst
+
+
+def test_simulate_with_unmeasured_qubits_at_the_final_measurement(monkeypatch):
+    """Found by tools/fuzz_lowering.py --trajectories: when the circuit ends in a measurement of SOME qubits, the collapsed
+    state of ``simulate`` is divided by the marginal probability of the measured bits (cirq: ``out /= probs[result]`` per
+    measurement gate), not by the probability of the whole basis state the final draw landed on.  CPU double only - the GPU
+    runs the same host code."""
+    oracle_backend.install(monkeypatch)
+    trajectories._CACHE.clear()
+    engine._PROGRAM_CACHE.clear()
+    q = cirq.LineQubit.range(4)
+    ops = [cirq.H(q[1]), cirq.measure(q[2], q[3], q[0], key="m0"), cirq.depolarize(0.03).on(q[2]), cirq.H(q[3]),
+           cirq.CNOT(q[0], q[2]), cirq.ry(0.4)(q[0]), cirq.measure(q[1], q[0], key="m1")]
+    circuit = cirq.Circuit(ops)
+    n, oracle_ops = O.from_circuit(circuit, q)
+    _, finals = O.measurement_distribution(n, oracle_ops)
+    spec = trajectories.TrajectoryProgram(circuit, q).measurements
+    sim = cirq.DensityMatrixSimulator(seed=3)
+    seen = set()
+    for _ in range(12):
+        res = sim.simulate(circuit, qubit_order=q)
+        masked = tuple(int(b) for key, _, _ in spec for b in res.measurements[key])
+        seen.add(masked)
+        rho = finals[_raw_bits(spec, masked)]
+        assert abs(np.trace(res.final_density_matrix) - 1.0) < 1e-12
+        assert np.abs(res.final_density_matrix - rho).max() < 1e-12
+    assert len(seen) >= 2
+    trajectories._CACHE.clear()
+    engine._PROGRAM_CACHE.clear()

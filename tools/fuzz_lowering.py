@@ -1,0 +1,268 @@
+"""Seed sweep of the random lowering checks of tests/test_lowering.py (CPU only: the dumped plan tables are replayed by
+tests/plan_interp.py and compared with the oracle).  ``python tools/fuzz_lowering.py [first_seed] [n_seeds] [--stream | --ansatz | --trajectories]`` prints one line
+per failure and a summary; exit code 1 when anything failed."""
+import os
+import sys
+import traceback
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path[:0] = [ROOT, os.path.join(ROOT, "tests")]
+
+import plan_interp as PI                                                      # noqa: E402
+from oracle import dm_oracle as O                                             # noqa: E402
+from test_gpu_parity import random_circuit, random_hamiltonian, resolve       # noqa: E402
+from test_lowering import pauli_vector                                        # noqa: E402
+from workloads import build_program                                           # noqa: E402
+
+TOL = 1e-10
+CLIFF1 = [O.H, O.rx(np.pi / 2), O.rx(-np.pi / 2), O.rx(np.pi), O.rz(np.pi / 2), O.X, O.Z]
+
+
+def clifford_rotation_circuit(rng, n, length, n_params):
+    ops = []
+    for _ in range(length):
+        kind = rng.integers(0, 5 if n_params > 1 else 4)
+        if kind == 0:
+            ops.append(("u", (int(rng.integers(n)),), CLIFF1[int(rng.integers(len(CLIFF1)))]))
+        elif kind == 1 and n > 1:
+            a, b = rng.choice(n, 2, replace=False)
+            ops.append(("u", (int(a), int(b)), O.CNOT))
+            ops.append(("k", (int(a), int(b)), O.two_qubit_depolarize(0.01)))
+        elif kind == 2:
+            ops.append(("k", (int(rng.integers(n)),), O.asymmetric_depolarize(0.01, 0.02, 0.005)))
+        elif kind == 3:
+            name = f"t{int(rng.integers(n_params))}"
+            ops.append(("r", (int(rng.integers(n)),), (int(rng.integers(3)), name, float(rng.choice([1.0, -1.0, 2.0])), float(rng.choice([0.0, 0.0, 0.3])))))
+        else:
+            ops.append(("u", (int(rng.integers(n)),), O.rz(float(rng.normal()))))
+    return ops
+
+
+def one_seed(seed):
+    rng = np.random.default_rng(seed)
+    checked = []
+    # (1) general circuits: fused blocks and packed device ops
+    n = int(rng.integers(1, 6))
+    ops = random_circuit(rng, n, depth=int(rng.integers(5, 40)))
+    terms = random_hamiltonian(rng, n, int(rng.integers(1, 12)))
+    ham = O.pauli_terms_to_matrix(n, *terms)
+    prog = build_program(ops, n, terms)
+    plan = PI.parse(prog.dump())
+    vals = rng.normal(size=max(prog.n_params, 1))
+    rho = O.simulate(n, resolve(ops, prog.param_names, vals))
+    want_r = pauli_vector(rho, n)
+    for name, r in (("blocks", PI.run_blocks(plan, vals)), ("devops", PI.run_devops(plan, vals))):
+        assert np.max(np.abs(r - want_r)) < TOL, (name, n)
+        assert abs(PI.energy(plan, r) - O.energy_sparse(rho, ham)) < TOL, (name, "energy")
+    checked.append("general")
+    # (2) Clifford + rotation circuits: frame tables, compact frame, thread-per-circuit tables
+    for n_params in (1, 3):
+        n = int(rng.integers(2, 5))
+        ops = clifford_rotation_circuit(rng, n, int(rng.integers(8, 45)), n_params)
+        terms = random_hamiltonian(rng, n, int(rng.integers(1, 12)))
+        prog = build_program(ops, n, terms)
+        plan = PI.parse(prog.dump())
+        vals = rng.normal(size=max(prog.n_params, 1))
+        want = O.energy_sparse(O.simulate(n, resolve(ops, prog.param_names, vals)), O.pauli_terms_to_matrix(n, *terms))
+        if prog.info["path"] == 1 and "fsegs" in plan:
+            assert abs(PI.run_frame(plan, vals) - want) < TOL, ("frame", n, n_params)
+            checked.append("frame")
+        if "f32" in plan:
+            assert abs(PI.run_frame32(plan, vals) - want) < TOL, ("frame32", n, n_params)
+            checked.append("f32")
+        if "f16" in plan and prog.n_params == 1:
+            assert abs(PI.run_frame16t(plan, vals) - want) < TOL, ("frame16t", n)
+            checked.append("f16")
+            if plan["f16"]["scaled"]:
+                assert abs(PI.run_frame16t_scaled(plan, vals) - want) < TOL, ("frame16t scaled", n)
+                checked.append("f16s")
+    return checked
+
+
+def pauli_exponential_gates(rng, n, n_strings, alpha=None):
+    """UCCSD-shaped gate list (i_wave_function.py:158-189): HF-like rx(pi) flips, then per random Pauli string the basis change,
+    the CNOT ladder over its support, rz(2 sign alpha) on the last qubit, and everything undone.  alpha=None keeps the symbol."""
+    gates = [("u", (q,), O.rx(np.pi)) for q in range(n) if rng.random() < 0.5]
+    for _ in range(n_strings):
+        support = sorted(int(q) for q in rng.choice(n, size=int(rng.integers(1, n + 1)), replace=False))
+        letters = [str(rng.choice(["X", "Y", "Z"])) for _ in support]
+        sign = float(rng.choice([1.0, -1.0]))
+        for q, p in zip(support, letters):
+            if p != "Z":
+                gates.append(("u", (q,), O.H if p == "X" else O.rx(-np.pi / 2)))
+        for a, b in zip(support[:-1], support[1:]):
+            gates.append(("u", (a, b), O.CNOT))
+        if alpha is None:
+            gates.append(("r", (support[-1],), (2, "alpha0", 2.0 * sign, 0.0)))
+        else:
+            gates.append(("u", (support[-1],), O.rz(2.0 * sign * alpha)))
+        for a, b in reversed(list(zip(support[:-1], support[1:]))):
+            gates.append(("u", (a, b), O.CNOT))
+        for q, p in zip(support, letters):
+            if p != "Z":
+                gates.append(("u", (q,), O.H if p == "X" else O.rx(np.pi / 2)))
+    return gates
+
+
+def pauli_noise(rng):
+    n1 = [[O.depolarize(1e-3)], [O.asymmetric_depolarize(1e-3, 2e-3, 5e-4)], [O.bit_flip(1e-3), O.depolarize(1e-3)], [O.phase_flip(2e-3)]][int(rng.integers(4))]
+    n2 = [[O.two_qubit_depolarize(1e-3)], [O.two_qubit_pauli_channel(1e-3, 1e-3, 6e-3)], []][int(rng.integers(3))]
+    return n1, n2
+
+
+def one_ansatz_seed(seed):
+    """Thread-per-circuit tables (dmx_frame16t_kernel / dmx_frame16v_kernel) on UCCSD-shaped circuits with Pauli noise."""
+    rng = np.random.default_rng(seed)
+    checked = []
+    n = int(rng.integers(2, 5))
+    n_strings = int(rng.integers(1, 9))
+    n1, n2 = pauli_noise(rng)
+    terms = random_hamiltonian(rng, n, int(rng.integers(1, 16)))
+    ham = O.pauli_terms_to_matrix(n, *terms)
+    # (a) one symbol: parameter sweep
+    gates = pauli_exponential_gates(np.random.default_rng(seed + 10 ** 6), n, n_strings)
+    ops = O.with_noise(gates, n1, n2)
+    prog = build_program(ops, n, terms)
+    plan = PI.parse(prog.dump())
+    for val in rng.normal(size=2):
+        want = O.energy_sparse(O.simulate(n, resolve(ops, prog.param_names, [val])), ham)
+        assert abs(PI.energy(plan, PI.run_devops(plan, [val])) - want) < TOL, ("devops", n)
+        if prog.info["path"] == 1 and "fsegs" in plan:
+            assert abs(PI.run_frame(plan, [val]) - want) < TOL, ("frame", n)
+        if "f32" in plan:
+            assert abs(PI.run_frame32(plan, [val]) - want) < TOL, ("frame32", n)
+        if "f16" in plan and not plan["f16"]["const"]:
+            assert abs(PI.run_frame16t(plan, [val]) - want) < TOL, ("frame16t", n)
+            checked.append("f16t")
+            if plan["f16"]["scaled"]:
+                assert abs(PI.run_frame16t_scaled(plan, [val]) - want) < TOL, ("frame16t scaled", n)
+                checked.append("f16ts")
+    # (b) the same circuit resolved, a variant slot after every gate: QP identifier rows
+    alpha = float(rng.normal() * 0.3)
+    gates = pauli_exponential_gates(np.random.default_rng(seed + 10 ** 6), n, n_strings, alpha=alpha)
+    basis = O.basis_operations()
+    vops = []
+    for slot, (kind, qs, pl) in enumerate(gates):
+        noise = n1 if len(qs) == 1 else n2
+        vops.append((kind, qs, pl))
+        vops += [("k", qs, kr) for kr in noise]
+        vops.append(("v", qs, (basis, slot)))
+        vops += [("ck", qs, (kr, slot)) for kr in noise]
+    prog = build_program(vops, n, terms)
+    plan = PI.parse(prog.dump())
+    arity = [len(g[1]) for g in gates]
+    for trial in range(6):
+        v = np.zeros(len(gates), np.uint8)
+        for slot in rng.choice(len(gates), size=min(len(gates), int(rng.integers(0, 9))), replace=False):
+            if trial < 4:          # Pauli corrections (what the reference distribution draws)
+                v[slot] = int(rng.integers(1, 4)) if arity[slot] == 1 else 16 * int(rng.integers(0, 4)) + int(rng.integers(0, 4))
+            else:                  # any basis operation
+                v[slot] = int(rng.integers(0, 16)) if arity[slot] == 1 else int(rng.integers(0, 256))
+        want = O.energy_sparse(O.simulate(n, O.variant_ops(gates, n1, n2, v)), ham)
+        scale = max(1.0, abs(want))
+        assert abs(PI.energy(plan, PI.run_devops(plan, None, v)) - want) < TOL * scale, ("variant devops", n)
+        checked.append("var")
+        for name, fn in (("segments", PI.run_segments), ("frame", PI.run_frame), ("frame32", PI.run_frame32)):
+            if name == "frame32" and "f32" not in plan:
+                continue
+            if name != "segments" and "fsegs" not in plan:
+                continue
+            got = fn(plan, None, v)
+            if got is not None:
+                assert abs(got - want) < TOL * scale, ("variant " + name, n)
+        got = PI.run_frame16v(plan, v) if "f32" in plan else None
+        if got is not None:
+            assert abs(got - want) < TOL * scale, ("frame16v", n)
+            checked.append("f16v")
+    return checked
+
+
+def one_trajectory_seed(seed):
+    """Mid-circuit measurement (vqe_errormitigation_b200/trajectories.py) on the CPU test double: the outcome tree of a random
+    circuit with measurements anywhere against the oracle's explicit projections (tests/test_trajectories.py's check)."""
+    import pytest
+    import oracle_backend
+    import test_trajectories as TT
+    from vqe_errormitigation_b200 import cirq_compat as cirq
+    from vqe_errormitigation_b200 import engine, trajectories
+    from vqe_errormitigation_b200.error_mitigation import IBasisGateSingle
+    rng = np.random.default_rng(seed)
+    n = int(rng.integers(1, 5))
+    q = cirq.LineQubit.range(n)
+    ops, n_meas = [], 0
+    for _ in range(int(rng.integers(3, 16))):
+        kind = int(rng.integers(0, 7))
+        a = int(rng.integers(n))
+        if kind == 0:
+            ops.append([cirq.H, cirq.X, cirq.Z][int(rng.integers(3))](q[a]))
+        elif kind == 1:
+            ops.append([cirq.rx, cirq.ry, cirq.rz][int(rng.integers(3))](float(rng.normal()))(q[a]))
+        elif kind == 2 and n > 1:
+            b = int(rng.choice([x for x in range(n) if x != a]))
+            ops.append(cirq.CNOT(q[a], q[b]))
+        elif kind == 3:
+            ops.append(cirq.depolarize(0.03).on(q[a]) if rng.random() < 0.7 else cirq.amplitude_damp(0.1).on(q[a]))
+        elif kind == 4 and rng.random() < 0.3:
+            ops.append(IBasisGateSingle(np.array([[1.0, 0.0], [0.0, float(rng.uniform(0.3, 0.9))]], complex)).on(q[a]))
+        elif n_meas < 4:
+            k = int(rng.integers(1, min(n, 3) + 1))
+            qs = [q[int(x)] for x in rng.choice(n, size=k, replace=False)]
+            invert = tuple(bool(rng.integers(2)) for _ in qs) if rng.random() < 0.4 else ()
+            ops.append(cirq.measure(*qs, key=f"m{n_meas}", invert_mask=invert))
+            n_meas += 1
+    if n_meas == 0:
+        ops.insert(len(ops) // 2, cirq.measure(q[0], key="m0"))
+    circuit = cirq.Circuit(ops)
+    mp = pytest.MonkeyPatch()
+    try:
+        oracle_backend.install(mp)
+        trajectories._CACHE.clear()
+        engine._PROGRAM_CACHE.clear()
+        nq, oops = O.from_circuit(circuit, q)
+        want, finals = O.measurement_distribution(nq, oops)
+        tp = trajectories.TrajectoryProgram(circuit, q)
+        got = TT._engine_distribution(tp)
+        assert abs(sum(got.values()) - 1.0) < 1e-10, "distribution does not sum to 1"
+        for bits in set(want) | set(got):
+            assert abs(want.get(bits, 0.0) - got.get(bits, 0.0)) < 1e-10, ("outcome probability", bits)
+        res = cirq.DensityMatrixSimulator(seed=seed).simulate(circuit, qubit_order=q)
+        masked = tuple(int(b) for key, _, _ in tp.measurements for b in res.measurements[key])
+        rho = finals[TT._raw_bits(tp.measurements, masked)]
+        assert np.abs(res.final_density_matrix - rho).max() < 1e-10, "collapsed final state"
+    finally:
+        mp.undo()
+        trajectories._CACHE.clear()
+        engine._PROGRAM_CACHE.clear()
+    return ["tree", "simulate"]
+
+
+def one_stream_seed(seed):
+    """The streaming (state in HBM) lowering: triple sweeps and wide monomial sweeps on 8 qubits, both tile sizes."""
+    import test_lowering as TL
+    for tile in (6, 7):
+        TL.test_triple_sweep_lowering_random_clifford_mix(seed, tile)
+        TL.test_wide_monomial_sweeps_random_clifford_mix(seed, tile)
+    return ["sweep3", "sweep3", "wide", "wide"]
+
+
+def main():
+    args = [a for a in sys.argv[1:] if not a.startswith("--")]
+    first = int(args[0]) if len(args) > 0 else 1000
+    count = int(args[1]) if len(args) > 1 else 100
+    run = one_stream_seed if "--stream" in sys.argv else one_ansatz_seed if "--ansatz" in sys.argv else one_trajectory_seed if "--trajectories" in sys.argv else one_seed
+    failures, tally = 0, {}
+    for seed in range(first, first + count):
+        try:
+            for name in run(seed):
+                tally[name] = tally.get(name, 0) + 1
+        except Exception:                                                     # noqa: BLE001 - report and go on
+            failures += 1
+            print(f"seed {seed}: {traceback.format_exc().strip().splitlines()[-1]}", flush=True)
+    print(f"seeds {first}..{first + count - 1}: {failures} failure(s); checks run {tally}")
+    return 1 if failures else 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

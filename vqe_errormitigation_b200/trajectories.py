@@ -121,7 +121,8 @@ class TrajectoryProgram:
         grp = np.tile(np.arange(G, dtype=np.int32), U)
         e = prog.energies(self._params(U * G, params), v, groups=grp)
         p = np.abs(np.asarray(e.cpu().numpy(), np.float64).reshape(U, G))
-        return p / p.sum(axis=1, keepdims=True)
+        total = p.sum(axis=1, keepdims=True)          # a prefix of probability ~1e-300 leaves a numerically zero state: no outcomes
+        return np.divide(p, total, out=np.zeros_like(p), where=total > 0.0)
 
     # ---- sampling ------------------------------------------------------------------------------------------
     def sample(self, repetitions: int, rng=np.random, params=None, collapse_final: bool = False):
@@ -148,10 +149,19 @@ class TrajectoryProgram:
                                                           renormalise=True))
             final = _draw_rows(probs, inv, rng)
             if collapse_final:
+                # the collapse projects the MEASURED qubits only: the shot's weight is the marginal probability of their bits
+                # (cirq divides by each terminal measurement's conditional probability in turn - the product is this marginal),
+                # not the probability of the whole basis state that was drawn
                 n = self.n_qubits
-                weight *= probs[inv, final]
+                measured = 0
                 for slot, q, *_ in self.final_sites:
+                    measured |= 1 << (n - 1 - q)
                     codes[:, slot] = 1 + ((final >> (n - 1 - q)) & 1)
+                states = np.arange(probs.shape[1], dtype=np.int64)
+                for lo in range(0, R, 4096):              # [shots, 2^n] agreement mask in bounded pieces
+                    hi = min(R, lo + 4096)
+                    agree = (states[None, :] & measured) == (final[lo:hi, None] & measured)
+                    weight[lo:hi] *= (probs[inv[lo:hi]] * agree).sum(axis=1)
         return codes, weight, final
 
     def records(self, codes: np.ndarray, final: Optional[np.ndarray]) -> Dict[str, np.ndarray]:
