@@ -479,3 +479,18 @@ def test_lockstep_restarts_keep_the_sampled_cobyla_semantics(monkeypatch, capsys
         assert all(abs(v - h2_golden()["molecules"][r]["fci_energy"]) < 0.15 for v in c._optimized_exp_values)
         assert abs(c.fci_value - h2_golden()["molecules"][r]["fci_energy"]) < 1e-12
     assert capsys.readouterr().out.count("par: ") == 6
+
+
+def test_three_qubit_gates_lower_through_their_gate_decomposition(monkeypatch):
+    """Found by tools/fuzz_lowering.py --circuits: an undecomposed TOFFOLI, or a CSWAP operation rebuilt by
+    ``resolve_parameters`` (a plain GateOperation), must lower through the gate's own ``_decompose_`` - exact for the unitary."""
+    import sympy
+    oracle_backend.install(monkeypatch)
+    q = cirq.LineQubit.range(4)
+    circuit = cirq.Circuit([cirq.H(q[0]), cirq.ry(0.7)(q[1]), cirq.rx(sympy.Symbol("t"))(q[2]), cirq.TOFFOLI(q[0], q[1], q[3]),
+                            cirq.CSWAP(q[3], q[0], q[2]), cirq.depolarize(0.02)(q[2])])
+    resolver = cirq.ParamResolver({"t": 0.4})
+    want = O.simulate(4, O.from_circuit(cirq.resolve_parameters(circuit, resolver), q)[1])
+    for program, res in ((circuit, resolver), (cirq.resolve_parameters(circuit, resolver), None)):
+        got = cirq.DensityMatrixSimulator().simulate(program, param_resolver=res, qubit_order=q).final_density_matrix
+        assert np.abs(got - want).max() < 1e-12

@@ -1,5 +1,5 @@
 """Seed sweep of the random lowering checks of tests/test_lowering.py (CPU only: the dumped plan tables are replayed by
-tests/plan_interp.py and compared with the oracle).  ``python tools/fuzz_lowering.py [first_seed] [n_seeds] [--stream | --ansatz | --trajectories]`` prints one line
+tests/plan_interp.py and compared with the oracle).  ``python tools/fuzz_lowering.py [first_seed] [n_seeds] [--stream | --ansatz | --trajectories | --circuits]`` prints one line
 per failure and a summary; exit code 1 when anything failed."""
 import os
 import sys
@@ -238,20 +238,123 @@ def one_trajectory_seed(seed):
     return ["tree", "simulate"]
 
 
+def one_circuit_seed(seed):
+    """The circuit-facing side (engine.lower_circuit behind DensityMatrixSimulator / QPU-style energy programs) on the CPU test
+    double: random circuits over the whole gate vocabulary of cirq_compat, symbols included, against the oracle's own reading of
+    the same circuit (O.from_circuit)."""
+    import pytest
+    import sympy
+    import oracle_backend
+    from vqe_errormitigation_b200 import cirq_compat as cirq
+    from vqe_errormitigation_b200 import engine, trajectories
+    from vqe_errormitigation_b200.error_mitigation import (IBasisGateSingle, IBasisGateTwo, SingleQubitPauliChannel, TwoQubitDepolarizingChannel,
+                                                           TwoQubitPauliChannel)
+    rng = np.random.default_rng(seed)
+    n = int(rng.integers(1, 6))
+    kind_q = int(rng.integers(3))
+    q = cirq.LineQubit.range(n) if kind_q == 0 else [cirq.GridQubit(i // 2, i % 2) for i in range(n)] if kind_q == 1 else \
+        [cirq.NamedQubit(f"q{chr(97 + i)}") for i in range(n)]
+    symbols = [sympy.Symbol(f"s{i}") for i in range(3)]
+    values = {f"s{i}": float(rng.normal()) for i in range(3)}
+    ops = []
+    for _ in range(int(rng.integers(3, 30))):
+        kind = int(rng.integers(0, 12))
+        a = int(rng.integers(n))
+        others = [x for x in range(n) if x != a]
+        b = int(rng.choice(others)) if others else None
+        if kind == 0:
+            ops.append([cirq.X, cirq.Y, cirq.Z, cirq.H, cirq.S, cirq.T, cirq.I][int(rng.integers(7))](q[a]))
+        elif kind == 1:
+            ops.append([cirq.rx, cirq.ry, cirq.rz][int(rng.integers(3))](float(rng.normal()))(q[a]))
+        elif kind == 2:
+            angle = float(rng.choice([1.0, -2.0, 0.5])) * symbols[int(rng.integers(3))] + float(rng.choice([0.0, 0.3]))
+            ops.append([cirq.rx, cirq.ry, cirq.rz][int(rng.integers(3))](angle)(q[a]))
+        elif kind == 3:
+            ops.append(([cirq.X, cirq.Y, cirq.Z, cirq.H][int(rng.integers(4))] ** float(rng.uniform(-1, 1)))(q[a]))
+        elif kind == 4 and b is not None:
+            ops.append([cirq.CNOT, cirq.CZ, cirq.SWAP][int(rng.integers(3))](q[a], q[b]))
+        elif kind == 5 and b is not None:
+            ops.append(([cirq.CNOT, cirq.CZ, cirq.SWAP][int(rng.integers(3))] ** float(rng.uniform(-1, 1)))(q[a], q[b]))
+        elif kind == 6 and len(others) >= 2:
+            b2, c2 = (int(x) for x in rng.choice(others, 2, replace=False))
+            gate = [cirq.CSWAP, cirq.TOFFOLI][int(rng.integers(2))](q[a], q[b2], q[c2])
+            ops.append(gate._decompose_() if hasattr(gate, "_decompose_") and rng.random() < 0.5 else gate)
+        elif kind == 7:
+            ops.append([cirq.depolarize(0.02), cirq.bit_flip(0.03), cirq.phase_flip(0.04), cirq.amplitude_damp(0.1), cirq.phase_damp(0.2),
+                        cirq.asymmetric_depolarize(0.01, 0.02, 0.03), SingleQubitPauliChannel(0.01, 0.0, 0.05)][int(rng.integers(7))](q[a]))
+        elif kind == 8 and b is not None:
+            ops.append([TwoQubitDepolarizingChannel(0.03), TwoQubitPauliChannel(0.01, 0.02, 0.03)][int(rng.integers(2))](q[a], q[b]))
+        elif kind == 9:
+            m = rng.normal(size=(2, 2)) + 1j * rng.normal(size=(2, 2))
+            ops.append(IBasisGateSingle(m / np.linalg.norm(m, 2)).on(q[a]))
+        elif kind == 10 and b is not None:
+            m = np.linalg.qr(rng.normal(size=(4, 4)) + 1j * rng.normal(size=(4, 4)))[0]
+            ops.append((IBasisGateTwo(m) if rng.random() < 0.5 else cirq.MatrixGate(m)).on(q[a], q[b]))
+        elif kind == 11 and rng.random() < 0.3:
+            ops.append(cirq.MatrixGate(np.linalg.qr(rng.normal(size=(2, 2)) + 1j * rng.normal(size=(2, 2)))[0]).on(q[a]))
+    if not ops:
+        ops.append(cirq.H(q[0]))
+    strategy = [cirq.InsertStrategy.EARLIEST, cirq.InsertStrategy.NEW, cirq.InsertStrategy.INLINE][int(rng.integers(3))]
+    circuit = cirq.Circuit(ops, strategy=strategy)
+    order = [q[i] for i in rng.permutation(n)] if rng.random() < 0.3 else None
+    used = list(order) if order is not None else sorted(circuit.all_qubits())
+    resolver = cirq.ParamResolver(values)
+    resolved = cirq.resolve_parameters(circuit, resolver)
+    nq, oracle_ops = O.from_circuit(resolved, used)
+    want = O.simulate(nq, oracle_ops)
+    scale = max(1.0, float(np.abs(want).max()))
+    mp = pytest.MonkeyPatch()
+    try:
+        oracle_backend.install(mp)
+        trajectories._CACHE.clear()
+        engine._PROGRAM_CACHE.clear()
+        got = cirq.DensityMatrixSimulator().simulate(circuit, param_resolver=resolver, qubit_order=order).final_density_matrix
+        assert got.shape == want.shape and np.abs(got - want).max() < 1e-10 * scale, "simulate (resolver)"
+        again = cirq.DensityMatrixSimulator().simulate(resolved, qubit_order=order).final_density_matrix
+        assert np.abs(again - want).max() < 1e-10 * scale, "simulate (resolved circuit)"
+        # the symbolic circuit as one plan with parameter columns, and its energy on random Pauli terms
+        terms = random_hamiltonian(rng, nq, int(rng.integers(1, 8)))
+        prog, _, _ = engine.compile_circuit(circuit, used, hamiltonian=terms)
+        row = None if not prog.n_params else np.array([[values[nm] for nm in prog.param_names]])
+        e = float(prog.energies_host(row, batch=1)[0])
+        e_want = float(np.real(np.trace(want @ O.pauli_terms_to_matrix(nq, *terms))))
+        assert abs(e - e_want) < 1e-10 * scale, "energy (symbolic plan)"
+    finally:
+        mp.undo()
+        trajectories._CACHE.clear()
+        engine._PROGRAM_CACHE.clear()
+    return ["simulate", "energy"]
+
+
 def one_stream_seed(seed):
-    """The streaming (state in HBM) lowering: triple sweeps and wide monomial sweeps on 8 qubits, both tile sizes."""
+    """The streaming (state in HBM) lowering on 8 qubits: pair / triple sweeps, wide monomial sweeps, both tile sizes, remapped
+    or fixed tiles - numerics only (the sweep-count expectations of tests/test_lowering.py are about speed, not parity)."""
     import test_lowering as TL
-    for tile in (6, 7):
-        TL.test_triple_sweep_lowering_random_clifford_mix(seed, tile)
-        TL.test_wide_monomial_sweeps_random_clifford_mix(seed, tile)
-    return ["sweep3", "sweep3", "wide", "wide"]
+    n = 8
+    rng = np.random.default_rng(800 + seed)
+    ops = TL._clifford_mix_circuit(rng, n, int(rng.integers(20, 80)))
+    terms = random_hamiltonian(rng, n, int(rng.integers(1, 14)))
+    ham = O.pauli_terms_to_matrix(n, *terms)
+    checked = []
+    want = vals = None
+    for options in ({"tile_qubits": 6, "wide": 0}, {"tile_qubits": 6, "wide": 1}, {"tile_qubits": 7, "wide": 0}, {"tile_qubits": 7, "wide": 1},
+                    {"tile_qubits": 7, "triples": 0}, {"tile_qubits": 6, "remap": 0}, {"tile_qubits": 5}):
+        prog = build_program(ops, n, terms, **options)
+        plan = PI.parse(prog.dump())
+        assert prog.info["path"] == 2, ("not a streaming plan", options)
+        if want is None:
+            vals = rng.uniform(-1, 1, size=prog.n_params)
+            want = O.energy_sparse(O.simulate(n, resolve(ops, prog.param_names, vals)), ham)
+        assert abs(PI.energy(plan, PI.run_devops(plan, vals)) - want) < TOL, ("stream", options)
+        checked.append("stream")
+    return checked
 
 
 def main():
     args = [a for a in sys.argv[1:] if not a.startswith("--")]
     first = int(args[0]) if len(args) > 0 else 1000
     count = int(args[1]) if len(args) > 1 else 100
-    run = one_stream_seed if "--stream" in sys.argv else one_ansatz_seed if "--ansatz" in sys.argv else one_trajectory_seed if "--trajectories" in sys.argv else one_seed
+    run = one_stream_seed if "--stream" in sys.argv else one_ansatz_seed if "--ansatz" in sys.argv else one_trajectory_seed if "--trajectories" in sys.argv else one_circuit_seed if "--circuits" in sys.argv else one_seed
     failures, tally = 0, {}
     for seed in range(first, first + count):
         try:

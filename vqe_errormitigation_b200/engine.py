@@ -596,9 +596,13 @@ def lower_circuit(circuit: cirq.Circuit, qubit_order=None, lift_numeric_rotation
                                       "(DensityMatrixSimulator.run / simulate do)")
         if len(idx) > 2:
             dec = getattr(op, "_decompose_", None)
-            if dec is None:
+            if dec is not None:
+                parts = dec()
+            elif hasattr(gate, "_decompose_"):          # e.g. an operation rebuilt by resolve_parameters, or TOFFOLI(...)
+                parts = gate._decompose_(list(op.qubits))
+            else:
                 raise NotImplementedError(f"{gate} acts on {len(idx)} qubits and has no decomposition")
-            for sub in cirq.flatten_op_tree(dec()):
+            for sub in cirq.flatten_op_tree(parts):
                 emit(sub)
             return
         axis = getattr(gate, "_axis", None)
