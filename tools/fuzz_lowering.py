@@ -1,5 +1,5 @@
 """Seed sweep of the random lowering checks of tests/test_lowering.py (CPU only: the dumped plan tables are replayed by
-tests/plan_interp.py and compared with the oracle).  ``python tools/fuzz_lowering.py [first_seed] [n_seeds] [--stream | --ansatz | --trajectories | --circuits]`` prints one line
+tests/plan_interp.py and compared with the oracle).  ``python tools/fuzz_lowering.py [first_seed] [n_seeds] [--stream | --ansatz | --trajectories | --circuits | --mitigation]`` prints one line
 per failure and a summary; exit code 1 when anything failed."""
 import os
 import sys
@@ -326,6 +326,108 @@ def one_circuit_seed(seed):
     return ["simulate", "energy"]
 
 
+def one_mitigation_seed(seed):
+    """IErrorMitigationManager on the CPU test double: (1) the batched variant program against the reference-shaped
+    ``get_updated_circuit`` of each row, simulated by the oracle; (2) on a one- or two-gate circuit the COMPLETE quasi-probability
+    sum over all identifier rows reproduces the noiseless value (the estimator's defining identity)."""
+    import itertools
+    import pytest
+    import oracle_backend
+    from vqe_errormitigation_b200 import cirq_compat as cirq
+    from vqe_errormitigation_b200 import engine
+    from vqe_errormitigation_b200.data_containers.helper_interfaces.i_noise_wrapper import INoiseModel
+    from vqe_errormitigation_b200.error_mitigation import (IErrorMitigationManager, SingleQubitPauliChannel, TwoQubitDepolarizingChannel,
+                                                           TwoQubitPauliChannel)
+    rng = np.random.default_rng(seed)
+
+    def random_gate(q, n, allow_two=True):
+        a = int(rng.integers(n))
+        kind = int(rng.integers(0, 4 if (allow_two and n > 1) else 3))
+        if kind == 0:
+            return [cirq.H, cirq.X, cirq.S, cirq.T][int(rng.integers(4))](q[a])
+        if kind in (1, 2):
+            return [cirq.rx, cirq.ry, cirq.rz][int(rng.integers(3))](float(rng.normal()))(q[a])
+        b = int(rng.choice([x for x in range(n) if x != a]))
+        return [cirq.CNOT, cirq.CZ][int(rng.integers(2))](q[a], q[b])
+
+    def random_model():
+        p = float(rng.choice([1e-3, 1e-2, 5e-2]))
+        n1 = [[cirq.depolarize(p)], [cirq.bit_flip(p), cirq.depolarize(p)], [SingleQubitPauliChannel(p, p, 6 * p)], [cirq.phase_flip(p)]][int(rng.integers(4))]
+        n2 = [[TwoQubitDepolarizingChannel(p)], [TwoQubitPauliChannel(p, p, 6 * p)], []][int(rng.integers(3))]
+        return INoiseModel(n1, n2, "fuzz")
+
+    def objective_for(n):
+        if rng.random() < 0.3:
+            return None
+        h = rng.normal(size=(1 << n, 1 << n))
+        return h + h.T
+
+    def expected(circuit, objective, n, q):
+        rho = O.simulate(n, O.from_circuit(circuit, q)[1])
+        if objective is None:
+            return O.energy_elementwise(rho, np.kron(np.eye(1 << (n - 1)), O.Z))
+        return O.energy_elementwise(rho, objective)
+
+    checked = []
+    mp = pytest.MonkeyPatch()
+    try:
+        oracle_backend.install(mp)
+        engine._PROGRAM_CACHE.clear()
+        # (1) random rows of a longer circuit
+        n = int(rng.integers(1, 4))
+        q = cirq.LineQubit.range(n)
+        clean = cirq.Circuit([random_gate(q, n) for _ in range(int(rng.integers(2, 10)))] + [cirq.H(x) for x in q])
+        model, objective = random_model(), objective_for(n)
+        mgr = IErrorMitigationManager(clean, model, objective)
+        gate_ops = [op for op in clean.all_operations()]
+        rows = np.zeros((6, len(gate_ops)), np.uint8)
+        for r in range(1, 6):
+            for s in rng.choice(len(gate_ops), size=min(len(gate_ops), int(rng.integers(1, 4))), replace=False):
+                rows[r, s] = int(rng.integers(0, 16)) if len(gate_ops[s].qubits) == 1 else int(rng.integers(0, 256))
+        values, _ = mgr.evaluate_variants(rows)
+        for r in range(6):
+            circuit = IErrorMitigationManager.get_updated_circuit(clean, model.get_operators, list(rows[r]))
+            want = expected(circuit, objective, n, q)
+            assert abs(values[r] - want) < 1e-10 * max(1.0, abs(want)), ("variant row", r)
+        checked.append("rows")
+        # (2) every identifier row of a tiny circuit (all 16 / 256 basis operations of every slot).  The complete
+        # quasi-probability sum is NOT the ideal value exactly: the reference re-applies the noise after a non-identity
+        # correction (error_mitigation.py:528-572), which leaves a residual of order p * (cost - 1) - bounded loosely below
+        n = int(rng.integers(1, 3))
+        q = cirq.LineQubit.range(n)
+        if n == 1:
+            ops = [random_gate(q, 1)] + ([random_gate(q, 1)] if rng.random() < 0.5 else [])
+        else:
+            ops = [[cirq.CNOT, cirq.CZ][int(rng.integers(2))](q[0], q[1])] if rng.random() < 0.5 else \
+                [random_gate([q[0]], 1), random_gate([q[1]], 1)]
+        clean = cirq.Circuit(ops)
+        model, objective = random_model(), objective_for(n)
+        mgr = IErrorMitigationManager(clean, model, objective)
+        qps = mgr.quasi_probabilities()
+        sizes = [len(qp) for qp in qps]
+        rows = np.array(list(itertools.product(*[range(k) for k in sizes])), np.uint8)
+        weights = np.prod([np.asarray(qp)[rows[:, s]] for s, qp in enumerate(qps)], axis=0)
+        keep = np.ones(len(rows), bool)
+        values, _ = mgr.evaluate_variants(rows)
+        for r in range(len(rows)):
+            want = expected(IErrorMitigationManager.get_updated_circuit(clean, model.get_operators, list(rows[r])), objective, n, q)
+            assert abs(values[r] - want) < 1e-10 * max(1.0, abs(want)), ("tiny circuit row", list(rows[r]))
+        ideal = expected(clean, objective, n, q)
+        cost = float(np.prod([np.sum(np.abs(qp)) for qp in qps]))
+        scale = 1.0 if objective is None else float(np.abs(np.diagonal(objective)).max())
+        assert abs(float(np.dot(weights, values)) - ideal) < 3.0 * (cost - 1.0 + 1e-9) * 0.1 * max(scale, 1e-3) + 1e-9, "complete sum far from ideal"
+        # and the signs / cost bookkeeping: cost * sign * |w| / cost == w
+        signs = mgr.variant_signs(rows[keep])
+        parity = np.prod([np.sign(np.asarray(qp)[rows[:, s]]) for s, qp in enumerate(qps)], axis=0)     # (the product itself can underflow)
+        assert np.array_equal(signs, parity), "variant signs"
+        assert abs(mgr.total_cost() - float(np.prod([np.sum(np.abs(qp)) for qp in qps]))) < 1e-12, "total cost"
+        checked.append("sum")
+    finally:
+        mp.undo()
+        engine._PROGRAM_CACHE.clear()
+    return checked
+
+
 def one_stream_seed(seed):
     """The streaming (state in HBM) lowering on 8 qubits: pair / triple sweeps, wide monomial sweeps, both tile sizes, remapped
     or fixed tiles - numerics only (the sweep-count expectations of tests/test_lowering.py are about speed, not parity)."""
@@ -354,7 +456,7 @@ def main():
     args = [a for a in sys.argv[1:] if not a.startswith("--")]
     first = int(args[0]) if len(args) > 0 else 1000
     count = int(args[1]) if len(args) > 1 else 100
-    run = one_stream_seed if "--stream" in sys.argv else one_ansatz_seed if "--ansatz" in sys.argv else one_trajectory_seed if "--trajectories" in sys.argv else one_circuit_seed if "--circuits" in sys.argv else one_seed
+    run = one_stream_seed if "--stream" in sys.argv else one_ansatz_seed if "--ansatz" in sys.argv else one_trajectory_seed if "--trajectories" in sys.argv else one_circuit_seed if "--circuits" in sys.argv else one_mitigation_seed if "--mitigation" in sys.argv else one_seed
     failures, tally = 0, {}
     for seed in range(first, first + count):
         try:
