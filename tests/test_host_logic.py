@@ -494,3 +494,41 @@ def test_three_qubit_gates_lower_through_their_gate_decomposition(monkeypatch):
     for program, res in ((circuit, resolver), (cirq.resolve_parameters(circuit, resolver), None)):
         got = cirq.DensityMatrixSimulator().simulate(program, param_resolver=res, qubit_order=q).final_density_matrix
         assert np.abs(got - want).max() < 1e-12
+
+
+def test_fermion_algebra_against_explicit_matrices():
+    """openfermion_compat (the reference's ansatz and Hamiltonian builders call these, i_wave_function.py:98-139,
+    processor_quantum.py:74-78): jordan_wigner, normal_ordered and hermitian_conjugated of random fermion operators against
+    explicit 2^n x 2^n ladder matrices a_j = Z..Z (x) |0><1| (x) I..I, and pauli_masks against get_sparse_operator."""
+    rng = np.random.default_rng(5)
+    n = 4
+    lower = np.array([[0, 1], [0, 0]], dtype=complex)
+
+    def ladder(mode, dagger):
+        m = np.eye(1, dtype=complex)
+        for j in range(n):
+            m = np.kron(m, O.Z if j < mode else lower if j == mode else O.I2)
+        return m.conj().T if dagger else m
+
+    def matrix(op):
+        total = np.zeros((1 << n, 1 << n), dtype=complex)
+        for term, coeff in op.terms.items():
+            m = np.eye(1 << n, dtype=complex)
+            for mode, dagger in term:
+                m = m @ ladder(mode, dagger)
+            total += coeff * m
+        return total
+
+    for _ in range(40):
+        op = of.FermionOperator()
+        for _ in range(int(rng.integers(1, 5))):
+            term = " ".join(f"{int(rng.integers(n))}{'^' if rng.random() < 0.5 else ''}" for _ in range(int(rng.integers(1, 5))))
+            op += of.FermionOperator(term, complex(rng.normal(), rng.normal()))
+        want = matrix(op)
+        jw = of.jordan_wigner(op)
+        assert np.abs(of.get_sparse_operator(jw, n_qubits=n).toarray() - want).max() < 1e-12
+        assert np.abs(matrix(of.normal_ordered(op)) - want).max() < 1e-12
+        assert np.abs(matrix(of.hermitian_conjugated(op)) - want.conj().T).max() < 1e-12
+        herm = of.jordan_wigner(op + of.hermitian_conjugated(op))
+        x, z, c = of.pauli_masks(herm, n)
+        assert np.abs(O.pauli_terms_to_matrix(n, x, z, c) - (want + want.conj().T)).max() < 1e-12
