@@ -231,11 +231,52 @@ def one_trajectory_seed(seed):
         masked = tuple(int(b) for key, _, _ in tp.measurements for b in res.measurements[key])
         rho = finals[TT._raw_bits(tp.measurements, masked)]
         assert np.abs(res.final_density_matrix - rho).max() < 1e-10, "collapsed final state"
+        # run() records on a classical circuit (X / CNOT / SWAP only): every shot must read the bits a classical simulation
+        # gives, invert masks applied, whether the measurements are terminal (evolve once + sample) or not (trajectories)
+        m = int(rng.integers(1, 5))
+        cq = cirq.LineQubit.range(m)
+        bits = [0] * m
+        cops, expect, n_keys = [], {}, 0
+        terminal_only = bool(rng.integers(2))
+        body = int(rng.integers(2, 14))
+        for step in range(body):
+            a = int(rng.integers(m))
+            others = [x for x in range(m) if x != a]
+            kind = int(rng.integers(0, 4))
+            if kind == 0 or not others:
+                cops.append(cirq.X(cq[a]))
+                bits[a] ^= 1
+            elif kind == 1:
+                b = int(rng.choice(others))
+                cops.append(cirq.CNOT(cq[a], cq[b]))
+                bits[b] ^= bits[a]
+            elif kind == 2:
+                b = int(rng.choice(others))
+                cops.append(cirq.SWAP(cq[a], cq[b]))
+                bits[a], bits[b] = bits[b], bits[a]
+            elif not terminal_only and n_keys < 3:
+                qs = [int(x) for x in rng.choice(m, size=int(rng.integers(1, m + 1)), replace=False)]
+                invert = tuple(bool(rng.integers(2)) for _ in qs) if rng.random() < 0.5 else ()
+                cops.append(cirq.measure(*[cq[x] for x in qs], key=f"k{n_keys}", invert_mask=invert))
+                expect[f"k{n_keys}"] = [bits[x] ^ (1 if i < len(invert) and invert[i] else 0) for i, x in enumerate(qs)]
+                n_keys += 1
+        for _ in range(int(rng.integers(1, 3))):
+            qs = [int(x) for x in rng.choice(m, size=int(rng.integers(1, m + 1)), replace=False)]
+            invert = tuple(bool(rng.integers(2)) for _ in qs) if rng.random() < 0.5 else ()
+            cops.append(cirq.measure(*[cq[x] for x in qs], key=f"k{n_keys}", invert_mask=invert))
+            expect[f"k{n_keys}"] = [bits[x] ^ (1 if i < len(invert) and invert[i] else 0) for i, x in enumerate(qs)]
+            n_keys += 1
+        trajectories._CACHE.clear()
+        engine._PROGRAM_CACHE.clear()
+        result = cirq.DensityMatrixSimulator(seed=seed).run(cirq.Circuit(cops), repetitions=3)
+        for key, want_bits in expect.items():
+            got_bits = np.asarray(result.measurements[key])
+            assert got_bits.shape == (3, len(want_bits)) and (got_bits == np.array(want_bits)).all(), ("run() record", key)
     finally:
         mp.undo()
         trajectories._CACHE.clear()
         engine._PROGRAM_CACHE.clear()
-    return ["tree", "simulate"]
+    return ["tree", "simulate", "records"]
 
 
 def one_circuit_seed(seed):
