@@ -49,8 +49,7 @@ def sampling_noise_scaling(shot_list: Optional[Sequence[int]] = None, reps: int 
     parameters = ansatz.operator_parameters
     parameters.update(v=result.optimal_parameters)
     resolved_circuit = QPU.get_resolved_circuit(circuit, parameters)
-    observable = QPU.get_hamiltonian_objective_operator(ansatz)
-    observable = observable.toarray() if hasattr(observable, "toarray") else np.asarray(observable)
+    observable = QPU.get_hamiltonian_objective_operator(ansatz)      # scipy sparse: the manager takes Tr(rho H) with the full H
 
     def experiment(process_circuit_count: int) -> float:
         return CPU.get_mitigated_expectation(clean_circuit=resolved_circuit, noise_model=noise_model, process_circuit_count=process_circuit_count,
