@@ -17,6 +17,14 @@ from test_lowering import pauli_vector                                        # 
 from workloads import build_program                                           # noqa: E402
 
 TOL = 1e-10
+PLAN_OPTIONS = {}          # --opt key=value (plan options of dmx_plan_set_option, e.g. fuse=0) for the default and --ansatz modes
+_build_program = build_program
+
+
+def build_program(ops, n, hamiltonian=None, **options):          # noqa: F811 - the sweep's own wrapper
+    merged = dict(PLAN_OPTIONS)
+    merged.update(options)
+    return _build_program(ops, n, hamiltonian, **merged)
 CLIFF1 = [O.H, O.rx(np.pi / 2), O.rx(-np.pi / 2), O.rx(np.pi), O.rz(np.pi / 2), O.X, O.Z]
 
 
@@ -66,7 +74,7 @@ def one_seed(seed):
         plan = PI.parse(prog.dump())
         vals = rng.normal(size=max(prog.n_params, 1))
         want = O.energy_sparse(O.simulate(n, resolve(ops, prog.param_names, vals)), O.pauli_terms_to_matrix(n, *terms))
-        if prog.info["path"] == 1 and "fsegs" in plan:
+        if prog.info["path"] == 1 and "fsegs" in plan and "f_init" in plan:
             assert abs(PI.run_frame(plan, vals) - want) < TOL, ("frame", n, n_params)
             checked.append("frame")
         if "f32" in plan:
@@ -129,7 +137,7 @@ def one_ansatz_seed(seed):
     for val in rng.normal(size=2):
         want = O.energy_sparse(O.simulate(n, resolve(ops, prog.param_names, [val])), ham)
         assert abs(PI.energy(plan, PI.run_devops(plan, [val])) - want) < TOL, ("devops", n)
-        if prog.info["path"] == 1 and "fsegs" in plan:
+        if prog.info["path"] == 1 and "fsegs" in plan and "f_init" in plan:
             assert abs(PI.run_frame(plan, [val]) - want) < TOL, ("frame", n)
         if "f32" in plan:
             assert abs(PI.run_frame32(plan, [val]) - want) < TOL, ("frame32", n)
@@ -167,7 +175,9 @@ def one_ansatz_seed(seed):
         for name, fn in (("segments", PI.run_segments), ("frame", PI.run_frame), ("frame32", PI.run_frame32)):
             if name == "frame32" and "f32" not in plan:
                 continue
-            if name != "segments" and "fsegs" not in plan:
+            if name != "segments" and ("fsegs" not in plan or "f_init" not in plan):
+                continue
+            if name == "segments" and "e_w" not in plan:          # plan option segments=0: no segment tables were built
                 continue
             got = fn(plan, None, v)
             if got is not None:
@@ -494,7 +504,13 @@ def one_stream_seed(seed):
 
 
 def main():
-    args = [a for a in sys.argv[1:] if not a.startswith("--")]
+    argv = list(sys.argv[1:])
+    while "--opt" in argv:
+        i = argv.index("--opt")
+        key, value = argv[i + 1].split("=")
+        PLAN_OPTIONS[key] = int(value)
+        del argv[i:i + 2]
+    args = [a for a in argv if not a.startswith("--")]
     first = int(args[0]) if len(args) > 0 else 1000
     count = int(args[1]) if len(args) > 1 else 100
     run = one_stream_seed if "--stream" in sys.argv else one_ansatz_seed if "--ansatz" in sys.argv else one_trajectory_seed if "--trajectories" in sys.argv else one_circuit_seed if "--circuits" in sys.argv else one_mitigation_seed if "--mitigation" in sys.argv else one_seed
