@@ -1,5 +1,5 @@
 """Seed sweep of the random lowering checks of tests/test_lowering.py (CPU only: the dumped plan tables are replayed by
-tests/plan_interp.py and compared with the oracle).  ``python tools/fuzz_lowering.py [first_seed] [n_seeds] [--stream | --ansatz | --trajectories | --circuits | --mitigation]`` prints one line
+tests/plan_interp.py and compared with the oracle).  ``python tools/fuzz_lowering.py [first_seed] [n_seeds] [--stream | --ansatz | --trajectories | --circuits | --mitigation | --tile]`` prints one line
 per failure and a summary; exit code 1 when anything failed."""
 import os
 import sys
@@ -479,6 +479,38 @@ def one_mitigation_seed(seed):
     return checked
 
 
+def one_tile_seed(seed):
+    """Whole-state tile plans (6 and 7 qubits, dmx_tile_kernel's packed device ops): energies on 30 random Pauli terms, with
+    parameters and with a few variant slots."""
+    rng = np.random.default_rng(seed)
+    n = int(rng.integers(6, 8))
+    ops = random_circuit(rng, n, depth=int(rng.integers(10, 40)))
+    basis = O.basis_operations()
+    slots = 0
+    for _ in range(int(rng.integers(0, 4))):
+        at = int(rng.integers(len(ops) + 1))
+        ops.insert(at, ("v", (int(rng.integers(n)),), (basis, slots)))
+        slots += 1
+    terms = random_hamiltonian(rng, n, 30)
+    ham = O.pauli_terms_to_matrix(n, *terms)
+    prog = build_program(ops, n, terms)
+    plan = PI.parse(prog.dump())
+    vals = rng.normal(size=max(prog.n_params, 1))
+    variant = np.array([int(rng.integers(0, 16)) for _ in range(slots)], np.uint8) if slots else None
+    resolved = []
+    for kind, qs, pl in resolve(ops, prog.param_names, vals):
+        if kind == "v":
+            resolved.append(("u", qs, pl[0][int(variant[pl[1]])]))
+        else:
+            resolved.append((kind, qs, pl))
+    want = O.energy_sparse(O.simulate(n, resolved), ham)
+    scale = max(1.0, abs(want))
+    for name, fn in (("blocks", PI.run_blocks), ("devops", PI.run_devops)):
+        got = PI.energy(plan, fn(plan, vals, variant))
+        assert abs(got - want) < TOL * scale, (name, n)
+    return ["tile%d" % n]
+
+
 def one_stream_seed(seed):
     """The streaming (state in HBM) lowering on 8 qubits: pair / triple sweeps, wide monomial sweeps, both tile sizes, remapped
     or fixed tiles - numerics only (the sweep-count expectations of tests/test_lowering.py are about speed, not parity)."""
@@ -513,7 +545,7 @@ def main():
     args = [a for a in argv if not a.startswith("--")]
     first = int(args[0]) if len(args) > 0 else 1000
     count = int(args[1]) if len(args) > 1 else 100
-    run = one_stream_seed if "--stream" in sys.argv else one_ansatz_seed if "--ansatz" in sys.argv else one_trajectory_seed if "--trajectories" in sys.argv else one_circuit_seed if "--circuits" in sys.argv else one_mitigation_seed if "--mitigation" in sys.argv else one_seed
+    run = one_stream_seed if "--stream" in sys.argv else one_ansatz_seed if "--ansatz" in sys.argv else one_trajectory_seed if "--trajectories" in sys.argv else one_circuit_seed if "--circuits" in sys.argv else one_mitigation_seed if "--mitigation" in sys.argv else one_tile_seed if "--tile" in sys.argv else one_seed
     failures, tally = 0, {}
     for seed in range(first, first + count):
         try:
