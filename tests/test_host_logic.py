@@ -533,3 +533,20 @@ def test_fermion_algebra_against_explicit_matrices():
         herm = of.jordan_wigner(op + of.hermitian_conjugated(op))
         x, z, c = of.pauli_masks(herm, n)
         assert np.abs(O.pauli_terms_to_matrix(n, x, z, c) - (want + want.conj().T)).max() < 1e-12
+
+
+def test_unmitigated_estimate_uses_meas_reps_once(monkeypatch):
+    """error_mitigation=False: the identity circuit stands for all ``count`` identifiers - ``count`` result entries and
+    meas_reps * count shots in total (reference error_mitigation.py:386-399), whatever ``meas_reps`` is."""
+    oracle_backend.install(monkeypatch)
+    q = cirq.LineQubit.range(2)
+    clean = cirq.Circuit([cirq.ry(0.8).on(q[0]), cirq.CNOT(q[0], q[1]), cirq.measure(q[0], key="M")])
+    mgr = IErrorMitigationManager(clean, INoiseModel([cirq.depolarize(0.01)], [TwoQubitDepolarizingChannel(0.01)], "d"), None)
+    mgr.set_identifier_range(50)
+    seen = []
+    monkeypatch.setattr("vqe_errormitigation_b200.engine.shot_expectations",
+                        lambda probs, shots, masks, seed, first_row=0: (seen.append(np.asarray(shots).copy()),
+                                                                        oracle_backend._shot_expectations(probs, shots, masks, seed, first_row))[1])
+    values, mu = mgr.get_mu_effective(error_mitigation=False, density_representation=False, meas_reps=7)
+    assert len(values) == 50 and np.all(values == values[0]) and abs(mu - values[0]) < 1e-15
+    assert [int(np.sum(s)) for s in seen] == [350]
