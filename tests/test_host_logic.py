@@ -535,9 +535,10 @@ def test_fermion_algebra_against_explicit_matrices():
         assert np.abs(O.pauli_terms_to_matrix(n, x, z, c) - (want + want.conj().T)).max() < 1e-12
 
 
-def test_unmitigated_estimate_uses_meas_reps_once(monkeypatch):
-    """error_mitigation=False: the identity circuit stands for all ``count`` identifiers - ``count`` result entries and
-    meas_reps * count shots in total (reference error_mitigation.py:386-399), whatever ``meas_reps`` is."""
+def test_unmitigated_estimate_keeps_the_reference_multiplicity(monkeypatch):
+    """error_mitigation=False: the reference hands process_circuit ONE identity item of multiplicity count * meas_reps
+    (error_mitigation.py:434), so meas_reps enters the shot count twice (:386) and the result list has count * meas_reps
+    entries (:399).  Kept as is - all of the reference's callers use meas_reps = 1."""
     oracle_backend.install(monkeypatch)
     q = cirq.LineQubit.range(2)
     clean = cirq.Circuit([cirq.ry(0.8).on(q[0]), cirq.CNOT(q[0], q[1]), cirq.measure(q[0], key="M")])
@@ -547,6 +548,6 @@ def test_unmitigated_estimate_uses_meas_reps_once(monkeypatch):
     monkeypatch.setattr("vqe_errormitigation_b200.engine.shot_expectations",
                         lambda probs, shots, masks, seed, first_row=0: (seen.append(np.asarray(shots).copy()),
                                                                         oracle_backend._shot_expectations(probs, shots, masks, seed, first_row))[1])
-    values, mu = mgr.get_mu_effective(error_mitigation=False, density_representation=False, meas_reps=7)
-    assert len(values) == 50 and np.all(values == values[0]) and abs(mu - values[0]) < 1e-15
-    assert [int(np.sum(s)) for s in seen] == [350]
+    values, mu = mgr.get_mu_effective(error_mitigation=False, density_representation=False, meas_reps=3)
+    assert len(values) == 150 and np.all(values == values[0]) and abs(mu - values[0]) < 1e-15
+    assert [int(np.sum(s)) for s in seen] == [450]

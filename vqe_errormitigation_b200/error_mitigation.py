@@ -637,9 +637,9 @@ class IErrorMitigationManager:
             scale = float(np.prod(weights))
         else:
             rows = np.zeros((1, len(self._gate_ops)), np.uint8)
-            # one identity row standing for every drawn identifier: meas_reps * count shots in total (``_measure_rows`` applies
-            # meas_reps), ``count`` result entries - the reference's [measurement] * value over its dictionary (:399,449)
-            counts = np.array([self._identifier_count], np.int64)
+            # one identity row with multiplicity count * meas_reps, exactly the reference's item (:434): process_circuit then
+            # takes meas_reps * that many shots (meas_reps enters twice) and returns that many result entries - kept as is
+            counts = np.array([self._identifier_count * meas_reps], np.int64)
             signs, scale = np.ones(1), 1.0
         if rows.shape[0] == 0:
             return np.zeros(0), float("nan")
