@@ -314,6 +314,9 @@ def test_remaining_experiment_loops_on_the_oracle_backend(monkeypatch, capsys):
     assert len(exp_list) == len(opt_list) == 1 and len(exp_list[0]) == 2 and all(-1.1 < v < -0.95 for v in exp_list[0])
     assert all(abs(a) < 0.2 for a in opt_list[0])                    # COBYLA's halving steps end near alpha* = 0.0141
     noisy, mitigated, probs = E.full_raw_vs_mitigation_per_noise(measure_count=1, identifier_count=2000, prob_list=[1e-4], max_cpu_iter=6)
+    pairs = E.raw_and_mitigated_repeated(INoiseWrapper(HydrogenAnsatz(), E.asymmetric_pauli_noise_model(1e-4)), E.asymmetric_pauli_noise_model(1e-4),
+                                         repetitions=2, max_qpu_iter=2000, max_cpu_iter=6)
+    assert len(pairs) == 2 and all(-1.2 < a < -0.9 and -1.3 < b < -0.9 for a, b in pairs)
     fci = h2_golden()["molecules"]["0.7414"]["fci_energy"]
     assert len(noisy) == len(mitigated) == 1 and abs(mitigated[0][0] - fci) < 0.12 and -1.1 < noisy[0][0] < -0.9
     # bond-length sweeps: r = 0.0 has no molecular data and H2_1.8.hdf5 stops after the SCF step -> NaN rows (reference :983-986)

@@ -181,10 +181,11 @@ def raw_and_mitigated(n_w: INoiseWrapper, noise_model: INoiseModel, max_qpu_iter
 
 
 def raw_and_mitigated_repeated(n_w: INoiseWrapper, noise_model: INoiseModel, repetitions: int, max_qpu_iter: int, max_cpu_iter: int = 10):
-    """``repetitions`` x :func:`raw_and_mitigated` the way the reference runs them - ``Pool(6).map`` over pickled copies of one
-    ``RawAndMitigatedClass`` (visual_testing.py:800-801,887-888), i.e. every repetition starts from the parent's parameters and
-    the parent's ansatz is never modified.  The noisy optimisations advance in lock-step (one launch per COBYLA round); each
-    optimum then gets its QP-mitigated estimate.  Returns [(noisy, mitigated)] * repetitions."""
+    """``repetitions`` x :func:`raw_and_mitigated` with the noisy optimisations advanced in lock-step (one launch per COBYLA
+    round); each optimum then gets its QP-mitigated estimate.  NOT the reference's order of events: its drivers call
+    ``process()`` in a serial loop on one shared wrapper (visual_testing.py:800-801,893-894), so every repetition starts from
+    the previous repetition's optimum; here every repetition starts from the parameters the wrapper holds on entry, which are
+    restored on exit.  Opt-in through ``lockstep=True`` of the two drivers below.  Returns [(noisy, mitigated)] * repetitions."""
     ansatz_parameters = n_w.operator_parameters
     start = dict(ansatz_parameters.dict)
     values, params = CPU.get_custom_optimized_states_lockstep(n_w, restarts=repetitions, max_cpu_iter=max_cpu_iter, max_qpu_iter=max_qpu_iter)
@@ -202,7 +203,7 @@ def raw_and_mitigated_repeated(n_w: INoiseWrapper, noise_model: INoiseModel, rep
 
 
 def full_raw_vs_mitigation_per_noise(measure_count: int, identifier_count: int, prob_list: Optional[Sequence[float]] = None,
-                                     max_cpu_iter: int = 10):
+                                     max_cpu_iter: int = 10, lockstep: bool = False):
     """``full_raw_vs_mitigation_per_noise(overwrite=True)`` (visual_testing.py:778-812): per noise level ``measure_count``
     x (noisy, mitigated).  Returns (exp_noisy_list, exp_mitig_list, prob_list) as stored in ``H2_Measure_Raw_vs_Mitigated``."""
     ansatz = HydrogenAnsatz()
@@ -211,14 +212,15 @@ def full_raw_vs_mitigation_per_noise(measure_count: int, identifier_count: int, 
     for prob in prob_list:
         noise_model = asymmetric_pauli_noise_model(float(prob))
         noisy_ansatz = INoiseWrapper(w_class=ansatz, noise_model=noise_model)
-        results = raw_and_mitigated_repeated(noisy_ansatz, noise_model, measure_count, identifier_count, max_cpu_iter)
+        results = raw_and_mitigated_repeated(noisy_ansatz, noise_model, measure_count, identifier_count, max_cpu_iter) if lockstep else \
+            [raw_and_mitigated(noisy_ansatz, noise_model, identifier_count, max_cpu_iter) for _ in range(measure_count)]
         exp_noisy_list.append([noisy for noisy, _ in results])
         exp_mitig_list.append([mitigated for _, mitigated in results])
     return exp_noisy_list, exp_mitig_list, prob_list
 
 
 def hydrogen_energy_spectrum(measure_count: int, identifier_count: int, atomic_distance_list: Optional[Sequence[float]] = None,
-                             previous=None, prob: float = 1e-4, max_cpu_iter: int = 10):
+                             previous=None, prob: float = 1e-4, max_cpu_iter: int = 10, lockstep: bool = False):
     """``hydrogen_energy_spectrum(overwrite=True)`` (visual_testing.py:863-909): (noisy, mitigated) energies along the bond
     length, ``measure_count`` repetitions per point; ``previous`` is an earlier result tuple to extend (the reference
     re-reads ``H2_Full_Spectrum_C<n>`` and appends, :866-871).  Returns (exp_noisy_list, exp_mitig_list,
@@ -232,7 +234,8 @@ def hydrogen_energy_spectrum(measure_count: int, identifier_count: int, atomic_d
     for i, atomic_distance in enumerate(atomic_distance_list):
         ansatz = HydrogenAnsatz(mol_param=round(float(atomic_distance), 2))
         noisy_ansatz = INoiseWrapper(w_class=ansatz, noise_model=noise_model)
-        results = raw_and_mitigated_repeated(noisy_ansatz, noise_model, measure_count, identifier_count, max_cpu_iter)
+        results = raw_and_mitigated_repeated(noisy_ansatz, noise_model, measure_count, identifier_count, max_cpu_iter) if lockstep else \
+            [raw_and_mitigated(noisy_ansatz, noise_model, identifier_count, max_cpu_iter) for _ in range(measure_count)]
         exp_noisy_list[i].extend(noisy for noisy, _ in results)
         exp_mitig_list[i].extend(mitigated for _, mitigated in results)
         fci_energy.append(float(ansatz.molecule.fci_energy))
