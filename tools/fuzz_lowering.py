@@ -1,5 +1,5 @@
 """Seed sweep of the random lowering checks of tests/test_lowering.py (CPU only: the dumped plan tables are replayed by
-tests/plan_interp.py and compared with the oracle).  ``python tools/fuzz_lowering.py [first_seed] [n_seeds] [--stream | --ansatz | --trajectories | --circuits | --mitigation | --tile]`` prints one line
+tests/plan_interp.py and compared with the oracle).  ``python tools/fuzz_lowering.py [first_seed] [n_seeds] [--stream | --ansatz | --trajectories | --circuits | --mitigation | --tile] [--opt key=value] [--qubits N]`` prints one line
 per failure and a summary; exit code 1 when anything failed."""
 import os
 import sys
@@ -17,6 +17,7 @@ from test_lowering import pauli_vector                                        # 
 from workloads import build_program                                           # noqa: E402
 
 TOL = 1e-10
+STREAM_QUBITS = 8          # --qubits N for --stream (8 ... 10; the interpreter takes ~6 s per 9-qubit seed)
 PLAN_OPTIONS = {}          # --opt key=value (plan options of dmx_plan_set_option, e.g. fuse=0) for the default and --ansatz modes
 _build_program = build_program
 
@@ -515,7 +516,7 @@ def one_stream_seed(seed):
     """The streaming (state in HBM) lowering on 8 qubits: pair / triple sweeps, wide monomial sweeps, both tile sizes, remapped
     or fixed tiles - numerics only (the sweep-count expectations of tests/test_lowering.py are about speed, not parity)."""
     import test_lowering as TL
-    n = 8
+    n = STREAM_QUBITS
     rng = np.random.default_rng(800 + seed)
     ops = TL._clifford_mix_circuit(rng, n, int(rng.integers(20, 80)))
     terms = random_hamiltonian(rng, n, int(rng.integers(1, 14)))
@@ -541,6 +542,11 @@ def main():
         i = argv.index("--opt")
         key, value = argv[i + 1].split("=")
         PLAN_OPTIONS[key] = int(value)
+        del argv[i:i + 2]
+    if "--qubits" in argv:
+        global STREAM_QUBITS
+        i = argv.index("--qubits")
+        STREAM_QUBITS = int(argv[i + 1])
         del argv[i:i + 2]
     args = [a for a in argv if not a.startswith("--")]
     first = int(args[0]) if len(args) > 0 else 1000
