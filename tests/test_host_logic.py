@@ -554,3 +554,21 @@ def test_unmitigated_estimate_keeps_the_reference_multiplicity(monkeypatch):
     values, mu = mgr.get_mu_effective(error_mitigation=False, density_representation=False, meas_reps=3)
     assert len(values) == 150 and np.all(values == values[0]) and abs(mu - values[0]) < 1e-15
     assert [int(np.sum(s)) for s in seen] == [450]
+
+
+def test_circuit_text_diagram():
+    """``print(circuit)`` (reference main.py:50) draws a cirq-style diagram; the reference's channel classes supply their
+    own wire symbols through ``_circuit_diagram_info_`` (error_mitigation.py:784-786,821-822)."""
+    import sympy
+    q = cirq.LineQubit.range(3)
+    circuit = cirq.Circuit([cirq.H(q[0]), cirq.rx(sympy.Symbol("a") * 2)(q[1]), cirq.CNOT(q[0], q[2]), TwoQubitDepolarizingChannel(0.015)(q[0], q[2]),
+                            SingleQubitPauliChannel(0.1, 0.0, 0.0)(q[1]), cirq.CSWAP(q[0], q[1], q[2]), cirq.measure(q[0], q[2], key="M")])
+    text = str(circuit)
+    lines = text.splitlines()
+    assert len(lines) == 5 and lines[0].startswith("0: ───H") and lines[2].startswith("1: ───Rx(") and lines[4].startswith("2: ───")
+    assert "D(0.001)" in lines[0] and "D(0.001)" in lines[4] and "D(0.900)" in lines[2]          # the channels' own symbols
+    assert "@" in lines[0] and "X" in lines[4] and "M('M')" in lines[0] and lines[4].rstrip("─").endswith("M")
+    assert "│" in lines[1] and "│" in lines[3] and "┼" in lines[2]                                # CNOT / measure cross qubit 1
+    assert len({len(line) for line in (lines[0], lines[2], lines[4])}) == 1                        # wires end together
+    assert repr(circuit).splitlines()[0].strip().startswith("0: H(0)")                            # the moment list stays available
+    assert str(cirq.Circuit()) == ""

@@ -908,13 +908,79 @@ class Circuit:
             state = np.moveaxis(state, list(range(k)), axes)
         return state.reshape(1 << n, 1 << n)
 
-    def __str__(self):
+    def __repr__(self):
         lines = []
         for i, m in enumerate(self._moments):
             lines.append(f"{i:4d}: " + "  ".join(repr(op) for op in m.operations))
         return "\n".join(lines)
 
-    __repr__ = __str__
+    @staticmethod
+    def _wire_symbols(op) -> Tuple[str, ...]:
+        """Diagram symbols of one operation, one per qubit: the gate's own ``_circuit_diagram_info_`` when it has one (the
+        reference's channel classes do, error_mitigation.py:784-786 ...), cirq's usual glyphs for the common gates otherwise."""
+        gate, k = op.gate, len(op.qubits)
+        info = getattr(gate, "_circuit_diagram_info_", None)
+        if info is not None:
+            symbols = tuple(info(CircuitDiagramInfoArgs(known_qubits=op.qubits, known_qubit_count=k)).wire_symbols)
+            if len(symbols) == k:
+                return symbols
+        if isinstance(gate, MeasurementGate):
+            return (f"M('{gate.key}')",) + ("M",) * (k - 1)
+        exponent = getattr(gate, "_exponent", 1)
+        power = "" if exponent == 1 else f"^{exponent:.4g}" if isinstance(exponent, (int, float)) else f"^({exponent})"
+        if isinstance(gate, CNotPowGate):
+            return ("@", "X" + power)
+        if isinstance(gate, CZPowGate):
+            return ("@", "@" + power)
+        if isinstance(gate, SwapPowGate):
+            return ("\u00d7", "\u00d7" + power)
+        if isinstance(gate, CCXPowGate):
+            return ("@", "@", "X" + power)
+        if isinstance(gate, CSwapGate):
+            return ("@", "\u00d7", "\u00d7")
+        if isinstance(gate, (XPowGate, YPowGate, ZPowGate)) and getattr(gate, "_global_shift", 0) == -0.5:
+            turns = f"{exponent:.4g}\u03c0" if isinstance(exponent, (int, float)) else f"{exponent}*\u03c0"
+            return (f"R{gate._name.lower()}({turns})",)
+        if isinstance(gate, _EigenGate):
+            return (gate._name + power,) + tuple(f"#{i + 2}" for i in range(k - 1))
+        label = str(gate)
+        return (label,) + tuple(f"#{i + 2}" for i in range(k - 1))
+
+    def to_text_diagram(self, qubit_order: Optional[Sequence[Qid]] = None) -> str:
+        """cirq-style text diagram: one wire per qubit, one column per moment, vertical bars joining the wires of a
+        multi-qubit operation (what ``print(circuit)`` shows in the reference's drivers, main.py:50)."""
+        qubits = list(qubit_order) if qubit_order is not None else sorted(self.all_qubits())
+        if not qubits:
+            return ""
+        row = {q: 2 * i for i, q in enumerate(qubits)}
+        n_rows = 2 * len(qubits) - 1
+        labels = [str(q) + ": " for q in qubits]
+        width = max(len(lab) for lab in labels)
+        lines = [(labels[r // 2].ljust(width) if r % 2 == 0 else " " * width) for r in range(n_rows)]
+        for moment in self._moments:
+            cells = [None] * n_rows
+            for op in moment.operations:
+                symbols = self._wire_symbols(op)
+                rows = [row[q] for q in op.qubits]
+                for r in range(min(rows) + 1, max(rows)):
+                    cells[r] = "\u253c" if r % 2 == 0 else "\u2502"
+                for r, sym in zip(rows, symbols):
+                    cells[r] = sym
+            col = max([len(c) for c in cells if c is not None] + [1])
+            for r in range(n_rows):
+                fill = "\u2500" if r % 2 == 0 else " "
+                cell = cells[r] if cells[r] is not None else fill
+                pad = col - len(cell)
+                if r % 2 == 0:
+                    lines[r] += fill * 3 + cell + fill * pad
+                else:
+                    lines[r] += " " * 3 + cell + " " * pad
+        for r in range(0, n_rows, 2):
+            lines[r] += "\u2500" * 3
+        return "\n".join(line.rstrip() for line in lines)
+
+    def __str__(self):
+        return self.to_text_diagram()
 
 
 # --------------------------------------------------------------------------------------------------
