@@ -412,12 +412,18 @@ def one_mitigation_seed(seed):
         if rng.random() < 0.3:
             return None
         h = rng.normal(size=(1 << n, 1 << n))
+        if rng.random() < 0.4:          # scipy sparse objective: `*` is the matrix product, the full Tr(H rho) (reference :382)
+            import scipy.sparse
+            g = h + 1j * rng.normal(size=h.shape)
+            return scipy.sparse.csc_matrix(g + g.conj().T)
         return h + h.T
 
     def expected(circuit, objective, n, q):
         rho = O.simulate(n, O.from_circuit(circuit, q)[1])
         if objective is None:
             return O.energy_elementwise(rho, np.kron(np.eye(1 << (n - 1)), O.Z))
+        if hasattr(objective, "toarray"):
+            return float(np.real(np.trace(objective.toarray() @ rho)))
         return O.energy_elementwise(rho, objective)
 
     checked = []
@@ -466,7 +472,7 @@ def one_mitigation_seed(seed):
             assert abs(values[r] - want) < 1e-10 * max(1.0, abs(want)), ("tiny circuit row", list(rows[r]))
         ideal = expected(clean, objective, n, q)
         cost = float(np.prod([np.sum(np.abs(qp)) for qp in qps]))
-        scale = 1.0 if objective is None else float(np.abs(np.diagonal(objective)).max())
+        scale = 1.0 if objective is None else float(np.abs(objective.toarray() if hasattr(objective, "toarray") else np.diagonal(objective)).max())
         assert abs(float(np.dot(weights, values)) - ideal) < 3.0 * (cost - 1.0 + 1e-9) * 0.1 * max(scale, 1e-3) + 1e-9, "complete sum far from ideal"
         # and the signs / cost bookkeeping: cost * sign * |w| / cost == w
         signs = mgr.variant_signs(rows[keep])
